@@ -1,0 +1,122 @@
+/*
+ * robotoc_b200.h -- C ABI of the B200-native Riccati / KKT inner loop (librobotoc_b200.so).
+ *
+ * This is the drop-in boundary behind robotoc::OCPSolver / UnconstrOCPSolver.  The reference has no
+ * FFI seam; the seam is the C++ member API of its solver classes.  Every entry point below names
+ * the reference interface it replaces (paths relative to the reference tree, commit d30d404).
+ *
+ * Conventions
+ *  - plain C types only: opaque handle, int return codes (0 = RBT_OK), double* buffers, void* stream
+ *    (a cudaStream_t; NULL = the legacy default stream).  No C++/torch types cross this boundary.
+ *  - all arithmetic is IEEE fp64; records are laid out by rbt_layout.h, arrays are [batch][grid][record].
+ *  - "host" pointers may be pageable or pinned; "dev" pointers are CUDA device pointers on the handle's
+ *    device.  All work is stream-ordered; call rbt_sync() (or synchronise the stream) before reading
+ *    host outputs.
+ *  - there is NO CPU fallback: every compute entry point fails with RBT_ERR_CUDA if no usable
+ *    sm_100 device is present.
+ */
+#ifndef ROBOTOC_B200_H_
+#define ROBOTOC_B200_H_
+
+#include "rbt_layout.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+  RBT_OK = 0,
+  RBT_ERR_ARG = 1,     /* invalid argument (reference: std::out_of_range / std::invalid_argument, ocp_solver.cpp:29-49) */
+  RBT_ERR_CUDA = 2,    /* CUDA runtime / no device */
+  RBT_ERR_STATE = 3,   /* call order (e.g. no schedule set) */
+  RBT_ERR_NUMERIC = 4  /* non-positive pivot met in a Cholesky (reference: assert(llt_.info()==Success), riccati_factorizer.cpp:50) */
+};
+
+/* which buffer, for rbt_dev_ptr / rbt_download / rbt_upload */
+enum {
+  RBT_BUF_KKT = 0,   /* KKT records          (input)  */
+  RBT_BUF_RIC = 1,   /* Riccati records      (output of backward) */
+  RBT_BUF_FACT = 2,  /* factorized KKT F,H,G,lu (optional output of backward; the reference mutates kkt in place) */
+  RBT_BUF_DIR = 3,   /* direction records    (output of forward) */
+  RBT_BUF_DX0 = 4,   /* initial state direction dx0, [batch][nx] (input of forward) */
+  RBT_BUF_INFO = 5   /* per-OCP int status flags, [batch] (as doubles are not used: int32) */
+};
+
+typedef struct rbt_handle rbt_handle;
+
+/* Layout query by field name (e.g. "k_Fxx", "r_stride"); returns -1 for an unknown name. */
+int rbt_layout_get(const rbt_dims* dims, const char* field);
+int rbt_ulayout_get(int nv, const char* field);
+
+/* Library / device probe: returns RBT_OK and fills sm (e.g. 100) and n_sm when a CUDA device is usable. */
+int rbt_device_info(int device, int* sm, int* n_sm, char* name, int name_len);
+const char* rbt_version(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Constrained path -- replaces robotoc::RiccatiRecursion
+ *   ctor RiccatiRecursion(const OCP&, double max_dts0)            include/robotoc/riccati/riccati_recursion.hpp:35
+ *   (data sized N+1+reserved events; here n_grid_max)             src/riccati/riccati_recursion.cpp:10-16
+ * --------------------------------------------------------------------------------------------- */
+int rbt_create(const rbt_dims* dims, int n_grid_max, int batch, int device, rbt_handle** out);
+int rbt_destroy(rbt_handle* h);
+
+/* Stage control table for the whole horizon (n_grid = time_discretization.size(), i.e. N+1 grid points,
+ * last one Terminal) and the STO regularisation.
+ *   replaces: the TimeDiscretization& argument of backward/forwardRiccatiRecursion (riccati_recursion.hpp:66-84)
+ *             and RiccatiRecursion::setRegularization(max_dts0)   (riccati_recursion.hpp:58) */
+int rbt_set_schedule(rbt_handle* h, const rbt_stage_ctrl* ctrl, int n_grid, double max_dts0);
+
+/* Device buffers owned by the handle (so a GPU producer can fill KKT records in place). */
+double* rbt_dev_ptr(rbt_handle* h, int which);
+long long rbt_buf_doubles(rbt_handle* h, int which); /* size of that buffer in doubles for the current schedule */
+
+int rbt_upload(rbt_handle* h, int which, const double* host, void* stream);   /* RBT_BUF_KKT or RBT_BUF_DX0 */
+int rbt_download(rbt_handle* h, int which, double* host, void* stream);       /* any output buffer */
+int rbt_download_info(rbt_handle* h, int* host_flags, void* stream);          /* per-OCP Cholesky status */
+
+/* RiccatiRecursion::backwardRiccatiRecursion(time_discretization, kkt_matrix, kkt_residual, factorization)
+ *   src/riccati/riccati_recursion.cpp:32-80.  Reads RBT_BUF_KKT, writes RBT_BUF_RIC (P,s,K,k,M,m,STO terms,
+ *   STOPolicy) and, if write_fact != 0, RBT_BUF_FACT (the values the reference leaves in Qxx,Qxu,Quu,lu). */
+int rbt_riccati_backward(rbt_handle* h, int write_fact, void* stream);
+
+/* RiccatiRecursion::forwardRiccatiRecursion(time_discretization, kkt_matrix, kkt_residual, factorization, d)
+ *   src/riccati/riccati_recursion.cpp:83-131.  Reads RBT_BUF_KKT, RBT_BUF_RIC, RBT_BUF_DX0; writes RBT_BUF_DIR. */
+int rbt_riccati_forward(rbt_handle* h, void* stream);
+
+/* One call with HOST buffers: upload kkt + dx0, backward, forward, download what is asked for (NULL = skip).
+ * This is the call an OCPSolver::updateSolution (src/solver/ocp_solver.cpp:118-123) adaptor makes. */
+int rbt_riccati_solve_host(rbt_handle* h, const double* kkt_host, const double* dx0_host, double* ric_host,
+                           double* dir_host, void* stream);
+
+int rbt_sync(rbt_handle* h, void* stream);
+const char* rbt_last_error(rbt_handle* h);
+/* number of kernel launches issued by this handle since creation (bench.py's gpu_launches) */
+long long rbt_launch_count(rbt_handle* h);
+
+/* ---------------------------------------------------------------------------------------------
+ * Unconstrained path -- replaces robotoc::UnconstrRiccatiRecursion
+ *   include/robotoc/riccati/unconstr_riccati_recursion.hpp, src/riccati/unconstr_riccati_recursion.cpp:9-48
+ *   (N stages + terminal, constant dt = T/N, control = acceleration)
+ * --------------------------------------------------------------------------------------------- */
+typedef struct rbt_uhandle rbt_uhandle;
+int rbt_unconstr_create(int nv, int N, double dt, int batch, int device, rbt_uhandle** out);
+int rbt_unconstr_destroy(rbt_uhandle* h);
+double* rbt_unconstr_dev_ptr(rbt_uhandle* h, int which);
+long long rbt_unconstr_buf_doubles(rbt_uhandle* h, int which);
+int rbt_unconstr_upload(rbt_uhandle* h, int which, const double* host, void* stream);
+int rbt_unconstr_download(rbt_uhandle* h, int which, double* host, void* stream);
+int rbt_unconstr_download_info(rbt_uhandle* h, int* host_flags, void* stream);
+/* UnconstrRiccatiRecursion::backwardRiccatiRecursion  unconstr_riccati_recursion.cpp:26-35 */
+int rbt_unconstr_backward(rbt_uhandle* h, int write_fact, void* stream);
+/* UnconstrRiccatiRecursion::forwardRiccatiRecursion   unconstr_riccati_recursion.cpp:37-46 */
+int rbt_unconstr_forward(rbt_uhandle* h, void* stream);
+int rbt_unconstr_solve_host(rbt_uhandle* h, const double* kkt_host, const double* dx0_host, double* ric_host,
+                            double* dir_host, void* stream);
+int rbt_unconstr_sync(rbt_uhandle* h, void* stream);
+const char* rbt_unconstr_last_error(rbt_uhandle* h);
+long long rbt_unconstr_launch_count(rbt_uhandle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ROBOTOC_B200_H_ */

@@ -1,0 +1,13 @@
+"""robotoc_b200 -- B200-native (sm_100a) Riccati / KKT inner loop behind robotoc's OCPSolver API.
+
+Host-side Python mirror of the reference interface for the hot path only:
+  RiccatiRecursion / UnconstrRiccatiRecursion  <-> /root/reference/include/robotoc/riccati/*.hpp
+  TimeDiscretization (control table producer)  <-> /root/reference/src/ocp/time_discretization.cpp
+All compute goes through the C ABI of librobotoc_b200.so (include/robotoc_b200.h); there is no CPU path.
+"""
+from .layout import Dims, Layout, ULayout  # noqa: F401
+from .schedule import GridInfo, TimeDiscretization, stage_ctrl_array  # noqa: F401
+from .riccati import RiccatiRecursion, UnconstrRiccatiRecursion  # noqa: F401
+
+ANYMAL = Dims(nv=18, nu=12, ns_max=12, n_passive=6)
+IIWA14_NV = 7

@@ -1,0 +1,503 @@
+// rbt_api.cu -- C ABI of librobotoc_b200.so (see include/robotoc_b200.h for the reference interfaces replaced).
+// Plumbing only: handles, device buffers, stream-ordered copies and kernel launches.  No CPU compute path.
+#include <cstdio>
+#include <cstring>
+#include <cstdlib>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/robotoc_b200.h"
+#include "riccati_backward.cuh"
+#include "riccati_forward.cuh"
+#include "riccati_unconstr.cuh"
+
+namespace {
+
+struct Err {
+  std::string msg;
+};
+
+#define RBT_CUDA(h, call)                                                                     \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess) {                                                                  \
+      (h)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                          \
+      return RBT_ERR_CUDA;                                                                    \
+    }                                                                                         \
+  } while (0)
+
+template <class K>
+int set_smem(K kernel, size_t bytes) {
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) == cudaSuccess ? 0 : 1;
+}
+
+}  // namespace
+
+struct rbt_handle {
+  rbt_dims dims;
+  rbt_layout L;
+  int n_grid_max = 0, n_grid = 0, batch = 0, device = 0;
+  double max_dts0 = 0.1;
+  rbt_stage_ctrl* d_ctrl = nullptr;
+  double *d_kkt = nullptr, *d_ric = nullptr, *d_fact = nullptr, *d_dir = nullptr, *d_dx0 = nullptr;
+  int* d_info = nullptr;
+  long long launches = 0;
+  std::string err;
+};
+
+struct rbt_uhandle {
+  int nv = 0, N = 0, batch = 0, device = 0;
+  double dt = 0;
+  rbt_ulayout L;
+  double *d_kkt = nullptr, *d_ric = nullptr, *d_fact = nullptr, *d_dir = nullptr, *d_dx0 = nullptr;
+  int* d_info = nullptr;
+  long long launches = 0;
+  std::string err;
+};
+
+// ---- compiled instances ------------------------------------------------------------------------------------------
+// ANYmal (floating base + 4 point contacts): nv=18, nu=12, max_dimf=12     src/robot/robot.cpp:33-60
+#define RBT_INSTANCES(X) X(18, 12, 12)
+
+static bool instance_supported(const rbt_dims& d) {
+#define X(NV, NU, NS) \
+  if (d.nv == NV && d.nu == NU && d.ns_max == NS) return true;
+  RBT_INSTANCES(X)
+#undef X
+  return false;
+}
+
+// All functions below are declared extern "C" in include/robotoc_b200.h; the definitions inherit that linkage.
+
+const char* rbt_version(void) { return "robotoc_b200 0.1 (sm_100a; instances: constrained nv18/nu12/ns12; unconstr nv7)"; }
+
+int rbt_layout_get(const rbt_dims* dims, const char* field) {
+  if (!dims || !field) return -1;
+  rbt_layout L;
+  rbt_make_layout(dims, &L);
+  return rbt_layout_field(&L, field);
+}
+
+int rbt_ulayout_get(int nv, const char* field) {
+  if (nv <= 0 || !field) return -1;
+  rbt_ulayout L;
+  rbt_make_ulayout(nv, &L);
+  return rbt_ulayout_field(&L, field);
+}
+
+int rbt_device_info(int device, int* sm, int* n_sm, char* name, int name_len) {
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+    cudaGetLastError();
+    return RBT_ERR_CUDA;
+  }
+  if (sm) *sm = prop.major * 10 + prop.minor;
+  if (n_sm) *n_sm = prop.multiProcessorCount;
+  if (name && name_len > 0) {
+    std::strncpy(name, prop.name, name_len - 1);
+    name[name_len - 1] = 0;
+  }
+  return RBT_OK;
+}
+
+int rbt_create(const rbt_dims* dims, int n_grid_max, int batch, int device, rbt_handle** out) {
+  if (!dims || !out || n_grid_max < 2 || batch < 1 || dims->nv < 1 || dims->nu < 1 || dims->ns_max < 0) return RBT_ERR_ARG;
+  if (!instance_supported(*dims)) return RBT_ERR_ARG;
+  rbt_handle* h = new rbt_handle();
+  h->dims = *dims;
+  rbt_make_layout(dims, &h->L);
+  h->n_grid_max = n_grid_max;
+  h->batch = batch;
+  h->device = device;
+  *out = h;
+  RBT_CUDA(h, cudaSetDevice(device));
+  const size_t per = size_t(batch) * n_grid_max;
+  RBT_CUDA(h, cudaMalloc(&h->d_ctrl, sizeof(rbt_stage_ctrl) * n_grid_max));
+  RBT_CUDA(h, cudaMalloc(&h->d_kkt, per * h->L.k_stride * 8));
+  RBT_CUDA(h, cudaMalloc(&h->d_ric, per * h->L.r_stride * 8));
+  RBT_CUDA(h, cudaMalloc(&h->d_fact, per * h->L.f_stride * 8));
+  RBT_CUDA(h, cudaMalloc(&h->d_dir, per * h->L.d_stride * 8));
+  RBT_CUDA(h, cudaMalloc(&h->d_dx0, size_t(batch) * h->L.nx * 8));
+  RBT_CUDA(h, cudaMalloc(&h->d_info, size_t(batch) * sizeof(int)));
+  RBT_CUDA(h, cudaMemset(h->d_ric, 0, per * h->L.r_stride * 8));
+  RBT_CUDA(h, cudaMemset(h->d_fact, 0, per * h->L.f_stride * 8));
+  RBT_CUDA(h, cudaMemset(h->d_dir, 0, per * h->L.d_stride * 8));
+  RBT_CUDA(h, cudaMemset(h->d_info, 0, size_t(batch) * sizeof(int)));
+  return RBT_OK;
+}
+
+int rbt_destroy(rbt_handle* h) {
+  if (!h) return RBT_ERR_ARG;
+  cudaSetDevice(h->device);
+  cudaFree(h->d_ctrl);
+  cudaFree(h->d_kkt);
+  cudaFree(h->d_ric);
+  cudaFree(h->d_fact);
+  cudaFree(h->d_dir);
+  cudaFree(h->d_dx0);
+  cudaFree(h->d_info);
+  delete h;
+  return RBT_OK;
+}
+
+int rbt_set_schedule(rbt_handle* h, const rbt_stage_ctrl* ctrl, int n_grid, double max_dts0) {
+  if (!h || !ctrl) return RBT_ERR_ARG;
+  if (n_grid < 2 || n_grid > h->n_grid_max) {
+    h->err = "[rbt_set_schedule] invalid argument: n_grid must be in [2, n_grid_max]";
+    return RBT_ERR_ARG;
+  }
+  if (!(max_dts0 > 0)) {
+    h->err = "[rbt_set_schedule] invalid argument: max_dts0 must be positive";
+    return RBT_ERR_ARG;
+  }
+  for (int i = 0; i < n_grid; ++i) {
+    const rbt_stage_ctrl& c = ctrl[i];
+    const bool last = (i == n_grid - 1);
+    if ((c.type == RBT_TERMINAL) != last || c.type < 0 || c.type > 3 || c.ns < 0 || c.ns > h->dims.ns_max ||
+        (c.type == RBT_IMPACT && (i == 0 || last)) || (c.type == RBT_LIFT && i == 0)) {
+      h->err = "[rbt_set_schedule] invalid argument: inconsistent stage control table at grid " + std::to_string(i);
+      return RBT_ERR_ARG;
+    }
+  }
+  RBT_CUDA(h, cudaSetDevice(h->device));
+  RBT_CUDA(h, cudaMemcpy(h->d_ctrl, ctrl, sizeof(rbt_stage_ctrl) * n_grid, cudaMemcpyHostToDevice));
+  // stage-conditional outputs (M, STO terms, policies) must not leak from a previous schedule
+  RBT_CUDA(h, cudaMemset(h->d_ric, 0, size_t(h->batch) * n_grid * h->L.r_stride * 8));
+  RBT_CUDA(h, cudaMemset(h->d_dir, 0, size_t(h->batch) * n_grid * h->L.d_stride * 8));
+  h->n_grid = n_grid;
+  h->max_dts0 = max_dts0;
+  return RBT_OK;
+}
+
+static double* buf_ptr(rbt_handle* h, int which) {
+  switch (which) {
+    case RBT_BUF_KKT: return h->d_kkt;
+    case RBT_BUF_RIC: return h->d_ric;
+    case RBT_BUF_FACT: return h->d_fact;
+    case RBT_BUF_DIR: return h->d_dir;
+    case RBT_BUF_DX0: return h->d_dx0;
+    default: return nullptr;
+  }
+}
+
+long long rbt_buf_doubles(rbt_handle* h, int which) {
+  if (!h) return -1;
+  const long long per = (long long)h->batch * h->n_grid;
+  switch (which) {
+    case RBT_BUF_KKT: return per * h->L.k_stride;
+    case RBT_BUF_RIC: return per * h->L.r_stride;
+    case RBT_BUF_FACT: return per * h->L.f_stride;
+    case RBT_BUF_DIR: return per * h->L.d_stride;
+    case RBT_BUF_DX0: return (long long)h->batch * h->L.nx;
+    default: return -1;
+  }
+}
+
+double* rbt_dev_ptr(rbt_handle* h, int which) { return h ? buf_ptr(h, which) : nullptr; }
+
+int rbt_upload(rbt_handle* h, int which, const double* host, void* stream) {
+  if (!h || !host || (which != RBT_BUF_KKT && which != RBT_BUF_DX0)) return RBT_ERR_ARG;
+  if (h->n_grid == 0) return RBT_ERR_STATE;
+  RBT_CUDA(h, cudaSetDevice(h->device));
+  RBT_CUDA(h, cudaMemcpyAsync(buf_ptr(h, which), host, size_t(rbt_buf_doubles(h, which)) * 8, cudaMemcpyHostToDevice,
+                              (cudaStream_t)stream));
+  return RBT_OK;
+}
+
+int rbt_download(rbt_handle* h, int which, double* host, void* stream) {
+  if (!h || !host || !buf_ptr(h, which)) return RBT_ERR_ARG;
+  if (h->n_grid == 0) return RBT_ERR_STATE;
+  RBT_CUDA(h, cudaSetDevice(h->device));
+  RBT_CUDA(h, cudaMemcpyAsync(host, buf_ptr(h, which), size_t(rbt_buf_doubles(h, which)) * 8, cudaMemcpyDeviceToHost,
+                              (cudaStream_t)stream));
+  return RBT_OK;
+}
+
+int rbt_download_info(rbt_handle* h, int* host_flags, void* stream) {
+  if (!h || !host_flags) return RBT_ERR_ARG;
+  RBT_CUDA(h, cudaSetDevice(h->device));
+  RBT_CUDA(h, cudaMemcpyAsync(host_flags, h->d_info, size_t(h->batch) * sizeof(int), cudaMemcpyDeviceToHost,
+                              (cudaStream_t)stream));
+  return RBT_OK;
+}
+
+template <int NV, int NU, int NS>
+static int launch_backward(rbt_handle* h, int write_fact, cudaStream_t st) {
+  using C = rbt::BwdCfg<NV, NU, NS>;
+  if (C::STAGE != h->L.k_stage_size || C::EXTRA != h->L.k_extra_size) {
+    h->err = "internal: shared-memory staging size does not match rbt_layout";
+    return RBT_ERR_STATE;
+  }
+  static bool attr_done = false;
+  auto kern = rbt::riccati_backward_kernel<NV, NU, NS>;
+  if (!attr_done) {
+    RBT_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
+    attr_done = true;
+  }
+  rbt::BwdParams p;
+  p.L = h->L;
+  p.ctrl = h->d_ctrl;
+  p.n_grid = h->n_grid;
+  p.batch = h->batch;
+  p.max_dts0 = h->max_dts0;
+  p.kkt = h->d_kkt;
+  p.ric = h->d_ric;
+  p.fact = write_fact ? h->d_fact : nullptr;
+  p.info = h->d_info;
+  p.dbg = getenv("RBT_DEBUG_STOP") ? atoi(getenv("RBT_DEBUG_STOP")) : 0;
+  RBT_CUDA(h, cudaMemsetAsync(h->d_info, 0, size_t(h->batch) * sizeof(int), st));
+  kern<<<h->batch, C::NTHREADS, C::SMEM_BYTES, st>>>(p);
+  RBT_CUDA(h, cudaGetLastError());
+  h->launches += 1;
+  return RBT_OK;
+}
+
+template <int NV, int NU, int NS>
+static int launch_forward(rbt_handle* h, cudaStream_t st) {
+  using C = rbt::FwdCfg<NV, NU, NS>;
+  static bool attr_done = false;
+  auto kern = rbt::riccati_forward_kernel<NV, NU, NS>;
+  if (!attr_done) {
+    RBT_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
+    attr_done = true;
+  }
+  rbt::FwdParams p;
+  p.L = h->L;
+  p.ctrl = h->d_ctrl;
+  p.n_grid = h->n_grid;
+  p.batch = h->batch;
+  p.kkt = h->d_kkt;
+  p.ric = h->d_ric;
+  p.dx0 = h->d_dx0;
+  p.dir = h->d_dir;
+  kern<<<h->batch, C::NTHREADS, C::SMEM_BYTES, st>>>(p);
+  RBT_CUDA(h, cudaGetLastError());
+  h->launches += 1;
+  return RBT_OK;
+}
+
+int rbt_riccati_backward(rbt_handle* h, int write_fact, void* stream) {
+  if (!h) return RBT_ERR_ARG;
+  if (h->n_grid == 0) {
+    h->err = "[rbt_riccati_backward] no schedule set";
+    return RBT_ERR_STATE;
+  }
+  RBT_CUDA(h, cudaSetDevice(h->device));
+#define X(NV, NU, NS) \
+  if (h->dims.nv == NV && h->dims.nu == NU && h->dims.ns_max == NS) return launch_backward<NV, NU, NS>(h, write_fact, (cudaStream_t)stream);
+  RBT_INSTANCES(X)
+#undef X
+  return RBT_ERR_ARG;
+}
+
+int rbt_riccati_forward(rbt_handle* h, void* stream) {
+  if (!h) return RBT_ERR_ARG;
+  if (h->n_grid == 0) {
+    h->err = "[rbt_riccati_forward] no schedule set";
+    return RBT_ERR_STATE;
+  }
+  RBT_CUDA(h, cudaSetDevice(h->device));
+#define X(NV, NU, NS) \
+  if (h->dims.nv == NV && h->dims.nu == NU && h->dims.ns_max == NS) return launch_forward<NV, NU, NS>(h, (cudaStream_t)stream);
+  RBT_INSTANCES(X)
+#undef X
+  return RBT_ERR_ARG;
+}
+
+int rbt_riccati_solve_host(rbt_handle* h, const double* kkt_host, const double* dx0_host, double* ric_host,
+                           double* dir_host, void* stream) {
+  if (!h || !kkt_host || !dx0_host) return RBT_ERR_ARG;
+  int rc;
+  if ((rc = rbt_upload(h, RBT_BUF_KKT, kkt_host, stream))) return rc;
+  if ((rc = rbt_upload(h, RBT_BUF_DX0, dx0_host, stream))) return rc;
+  if ((rc = rbt_riccati_backward(h, 0, stream))) return rc;
+  if ((rc = rbt_riccati_forward(h, stream))) return rc;
+  if (ric_host && (rc = rbt_download(h, RBT_BUF_RIC, ric_host, stream))) return rc;
+  if (dir_host && (rc = rbt_download(h, RBT_BUF_DIR, dir_host, stream))) return rc;
+  return RBT_OK;
+}
+
+int rbt_sync(rbt_handle* h, void* stream) {
+  if (!h) return RBT_ERR_ARG;
+  RBT_CUDA(h, cudaSetDevice(h->device));
+  RBT_CUDA(h, cudaStreamSynchronize((cudaStream_t)stream));
+  return RBT_OK;
+}
+
+const char* rbt_last_error(rbt_handle* h) { return h ? h->err.c_str() : "null handle"; }
+long long rbt_launch_count(rbt_handle* h) { return h ? h->launches : 0; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// unconstrained path
+// ---------------------------------------------------------------------------------------------------------------
+#define RBT_UINSTANCES(X) X(7)
+
+int rbt_unconstr_create(int nv, int N, double dt, int batch, int device, rbt_uhandle** out) {
+  if (!out || nv < 1 || N < 1 || batch < 1 || !(dt > 0)) return RBT_ERR_ARG;
+  bool ok = false;
+#define X(NV) \
+  if (nv == NV) ok = true;
+  RBT_UINSTANCES(X)
+#undef X
+  if (!ok) return RBT_ERR_ARG;
+  rbt_uhandle* h = new rbt_uhandle();
+  h->nv = nv;
+  h->N = N;
+  h->dt = dt;
+  h->batch = batch;
+  h->device = device;
+  rbt_make_ulayout(nv, &h->L);
+  *out = h;
+  RBT_CUDA(h, cudaSetDevice(device));
+  const size_t per = size_t(batch) * (N + 1);
+  RBT_CUDA(h, cudaMalloc(&h->d_kkt, per * h->L.k_stride * 8));
+  RBT_CUDA(h, cudaMalloc(&h->d_ric, per * h->L.r_stride * 8));
+  RBT_CUDA(h, cudaMalloc(&h->d_fact, per * h->L.f_stride * 8));
+  RBT_CUDA(h, cudaMalloc(&h->d_dir, per * h->L.d_stride * 8));
+  RBT_CUDA(h, cudaMalloc(&h->d_dx0, size_t(batch) * h->L.nx * 8));
+  RBT_CUDA(h, cudaMalloc(&h->d_info, size_t(batch) * sizeof(int)));
+  RBT_CUDA(h, cudaMemset(h->d_ric, 0, per * h->L.r_stride * 8));
+  RBT_CUDA(h, cudaMemset(h->d_fact, 0, per * h->L.f_stride * 8));
+  RBT_CUDA(h, cudaMemset(h->d_dir, 0, per * h->L.d_stride * 8));
+  RBT_CUDA(h, cudaMemset(h->d_info, 0, size_t(batch) * sizeof(int)));
+  return RBT_OK;
+}
+
+int rbt_unconstr_destroy(rbt_uhandle* h) {
+  if (!h) return RBT_ERR_ARG;
+  cudaSetDevice(h->device);
+  cudaFree(h->d_kkt);
+  cudaFree(h->d_ric);
+  cudaFree(h->d_fact);
+  cudaFree(h->d_dir);
+  cudaFree(h->d_dx0);
+  cudaFree(h->d_info);
+  delete h;
+  return RBT_OK;
+}
+
+static double* ubuf_ptr(rbt_uhandle* h, int which) {
+  switch (which) {
+    case RBT_BUF_KKT: return h->d_kkt;
+    case RBT_BUF_RIC: return h->d_ric;
+    case RBT_BUF_FACT: return h->d_fact;
+    case RBT_BUF_DIR: return h->d_dir;
+    case RBT_BUF_DX0: return h->d_dx0;
+    default: return nullptr;
+  }
+}
+
+long long rbt_unconstr_buf_doubles(rbt_uhandle* h, int which) {
+  if (!h) return -1;
+  const long long per = (long long)h->batch * (h->N + 1);
+  switch (which) {
+    case RBT_BUF_KKT: return per * h->L.k_stride;
+    case RBT_BUF_RIC: return per * h->L.r_stride;
+    case RBT_BUF_FACT: return per * h->L.f_stride;
+    case RBT_BUF_DIR: return per * h->L.d_stride;
+    case RBT_BUF_DX0: return (long long)h->batch * h->L.nx;
+    default: return -1;
+  }
+}
+
+double* rbt_unconstr_dev_ptr(rbt_uhandle* h, int which) { return h ? ubuf_ptr(h, which) : nullptr; }
+
+int rbt_unconstr_upload(rbt_uhandle* h, int which, const double* host, void* stream) {
+  if (!h || !host || (which != RBT_BUF_KKT && which != RBT_BUF_DX0)) return RBT_ERR_ARG;
+  RBT_CUDA(h, cudaSetDevice(h->device));
+  RBT_CUDA(h, cudaMemcpyAsync(ubuf_ptr(h, which), host, size_t(rbt_unconstr_buf_doubles(h, which)) * 8,
+                              cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  return RBT_OK;
+}
+
+int rbt_unconstr_download(rbt_uhandle* h, int which, double* host, void* stream) {
+  if (!h || !host || !ubuf_ptr(h, which)) return RBT_ERR_ARG;
+  RBT_CUDA(h, cudaSetDevice(h->device));
+  RBT_CUDA(h, cudaMemcpyAsync(host, ubuf_ptr(h, which), size_t(rbt_unconstr_buf_doubles(h, which)) * 8,
+                              cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  return RBT_OK;
+}
+
+int rbt_unconstr_download_info(rbt_uhandle* h, int* host_flags, void* stream) {
+  if (!h || !host_flags) return RBT_ERR_ARG;
+  RBT_CUDA(h, cudaSetDevice(h->device));
+  RBT_CUDA(h, cudaMemcpyAsync(host_flags, h->d_info, size_t(h->batch) * sizeof(int), cudaMemcpyDeviceToHost,
+                              (cudaStream_t)stream));
+  return RBT_OK;
+}
+
+template <int NV>
+static rbt::UParams make_uparams(rbt_uhandle* h, int write_fact) {
+  rbt::UParams p;
+  p.L = h->L;
+  p.N = h->N;
+  p.batch = h->batch;
+  p.dt = h->dt;
+  p.kkt = h->d_kkt;
+  p.ric = h->d_ric;
+  p.fact = write_fact ? h->d_fact : nullptr;
+  p.dx0 = h->d_dx0;
+  p.dir = h->d_dir;
+  p.info = h->d_info;
+  return p;
+}
+
+int rbt_unconstr_backward(rbt_uhandle* h, int write_fact, void* stream) {
+  if (!h) return RBT_ERR_ARG;
+  RBT_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+#define X(NV)                                                                                  \
+  if (h->nv == NV) {                                                                           \
+    if (rbt::UCfg<NV>::KSTRIDE != h->L.k_stride) return RBT_ERR_STATE;                          \
+    RBT_CUDA(h, cudaMemsetAsync(h->d_info, 0, size_t(h->batch) * sizeof(int), st));            \
+    rbt::unconstr_backward_kernel<NV><<<h->batch, 32, 0, st>>>(make_uparams<NV>(h, write_fact)); \
+    RBT_CUDA(h, cudaGetLastError());                                                           \
+    h->launches += 1;                                                                          \
+    return RBT_OK;                                                                             \
+  }
+  RBT_UINSTANCES(X)
+#undef X
+  return RBT_ERR_ARG;
+}
+
+int rbt_unconstr_forward(rbt_uhandle* h, void* stream) {
+  if (!h) return RBT_ERR_ARG;
+  RBT_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+#define X(NV)                                                                         \
+  if (h->nv == NV) {                                                                  \
+    rbt::unconstr_forward_kernel<NV><<<h->batch, 32, 0, st>>>(make_uparams<NV>(h, 0)); \
+    RBT_CUDA(h, cudaGetLastError());                                                  \
+    h->launches += 1;                                                                 \
+    return RBT_OK;                                                                    \
+  }
+  RBT_UINSTANCES(X)
+#undef X
+  return RBT_ERR_ARG;
+}
+
+int rbt_unconstr_solve_host(rbt_uhandle* h, const double* kkt_host, const double* dx0_host, double* ric_host,
+                            double* dir_host, void* stream) {
+  if (!h || !kkt_host || !dx0_host) return RBT_ERR_ARG;
+  int rc;
+  if ((rc = rbt_unconstr_upload(h, RBT_BUF_KKT, kkt_host, stream))) return rc;
+  if ((rc = rbt_unconstr_upload(h, RBT_BUF_DX0, dx0_host, stream))) return rc;
+  if ((rc = rbt_unconstr_backward(h, 0, stream))) return rc;
+  if ((rc = rbt_unconstr_forward(h, stream))) return rc;
+  if (ric_host && (rc = rbt_unconstr_download(h, RBT_BUF_RIC, ric_host, stream))) return rc;
+  if (dir_host && (rc = rbt_unconstr_download(h, RBT_BUF_DIR, dir_host, stream))) return rc;
+  return RBT_OK;
+}
+
+int rbt_unconstr_sync(rbt_uhandle* h, void* stream) {
+  if (!h) return RBT_ERR_ARG;
+  RBT_CUDA(h, cudaSetDevice(h->device));
+  RBT_CUDA(h, cudaStreamSynchronize((cudaStream_t)stream));
+  return RBT_OK;
+}
+
+const char* rbt_unconstr_last_error(rbt_uhandle* h) { return h ? h->err.c_str() : "null handle"; }
+long long rbt_unconstr_launch_count(rbt_uhandle* h) { return h ? h->launches : 0; }
+

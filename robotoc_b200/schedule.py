@@ -1,0 +1,254 @@
+"""Host-side control-table producer.
+
+Restates robotoc::TimeDiscretization::discretize / correctTimeSteps
+(/root/reference/src/ocp/time_discretization.cpp:43-262) and the event bookkeeping of
+robotoc::ContactSequence (/root/reference/src/planner/contact_sequence.cpp:55-95) as far as the
+kernels need it: the per-grid-point GridInfo (grid_info.hpp:25-92) and, from it, the rbt_stage_ctrl
+table shared by a batch of OCPs.  This stays on the host in the reference as well.
+"""
+import math
+from dataclasses import dataclass, field
+from typing import List, Sequence
+
+from . import _lib
+
+INTERMEDIATE, IMPACT, LIFT, TERMINAL = 0, 1, 2, 3  # robotoc::GridType order (grid_info.hpp:14-19)
+_EPS = math.sqrt(2.220446049250313e-16)
+
+
+@dataclass
+class GridInfo:
+    """Field-for-field mirror of robotoc::GridInfo (grid_info.hpp:25-92)."""
+    type: int = INTERMEDIATE
+    t0: float = 0.0
+    t: float = 0.0
+    dt: float = 0.0
+    dt_next: float = 0.0
+    phase: int = 0
+    stage: int = 0
+    impact_index: int = -1
+    lift_index: int = -1
+    stage_in_phase: int = 0
+    num_grids_in_phase: int = 0
+    sto: bool = False
+    sto_next: bool = False
+    switching_constraint: bool = False
+
+
+@dataclass
+class ContactEvents:
+    """The part of ContactSequence the discretization reads: event times, kinds, STO flags and the
+    contact dimension of every phase (dimf) / every impact (impact dimf)."""
+    impact_times: List[float] = field(default_factory=list)
+    lift_times: List[float] = field(default_factory=list)
+    sto_impact: List[bool] = field(default_factory=list)
+    sto_lift: List[bool] = field(default_factory=list)
+    phase_dimf: List[int] = field(default_factory=lambda: [0])   # dimf of contactStatus(phase)
+    impact_dimf: List[int] = field(default_factory=list)         # dimf of impactStatus(impact_index)
+
+    def push_back(self, is_impact: bool, time: float, post_dimf: int, impact_dimf: int = 0, sto: bool = False):
+        """ContactSequence::push_back (contact_sequence.cpp:55-95): an event is an Impact iff new contacts close."""
+        if is_impact:
+            self.impact_times.append(time)
+            self.sto_impact.append(sto)
+            self.impact_dimf.append(impact_dimf)
+        else:
+            self.lift_times.append(time)
+            self.sto_lift.append(sto)
+        self.phase_dimf.append(post_dimf)
+
+
+class TimeDiscretization:
+    """TimeDiscretization(T, N, reserved_num_discrete_events) -- time_discretization.cpp:9-27."""
+
+    def __init__(self, T: float, N: int):
+        if T <= 0:
+            raise ValueError("[TimeDiscretization] invalid argument: 'T' must be positive!")
+        if N <= 0:
+            raise ValueError("[TimeDiscretization] invalid argument: 'N' must be positive!")
+        self.T, self.N = T, N
+        self.grid: List[GridInfo] = []
+        self.num_grids = 0
+
+    def size(self):
+        return self.num_grids + 1
+
+    def __len__(self):
+        return self.size()
+
+    def __getitem__(self, i):
+        return self.grid[i]
+
+    def discretize(self, ev: ContactEvents, t: float = 0.0, sto: bool = True):
+        """discretize (time_discretization.cpp:43-183) followed by the STO flag pass of
+        correctTimeSteps (:219-262).  Time steps are left as produced by discretize."""
+        T, N_ = self.T, self.N
+        n_imp, n_lift = len(ev.impact_times), len(ev.lift_times)
+        size = N_ + n_lift + 2 * n_imp + 1
+        g = [GridInfo() for _ in range(size + 1)]
+        ni = 0
+        nl = 0
+        while ni < n_imp and not ev.impact_times[ni] > t:
+            ni += 1
+        while nl < n_lift and not ev.lift_times[nl] > t:
+            nl += 1
+        dt = T / N_
+        margin = 0.5 * dt
+        stage = 0
+        ti = t
+
+        def fill(st, tt, dtt, typ):
+            g[st].t, g[st].dt, g[st].stage = tt, dtt, st
+            g[st].phase = ni + nl
+            g[st].impact_index = ni - 1
+            g[st].lift_index = nl - 1
+            g[st].type = typ
+
+        while ti + _EPS < t + T:
+            has_imp = ni < n_imp
+            has_lift = nl < n_lift
+            fill(stage, ti, dt, INTERMEDIATE)
+            if has_imp:
+                nt = ev.impact_times[ni]
+                if nt <= ti + dt + _EPS and (nt + margin < t + T):
+                    g[stage].dt = nt - ti
+                    stage += 1
+                    ni += 1
+                    fill(stage, nt, 0.0, IMPACT)
+                    stage += 1
+                    fill(stage, nt, min(ti + dt, t + T) - nt, INTERMEDIATE)
+                    if abs((ti + dt) - nt) < _EPS:
+                        ti += dt
+                        g[stage].dt = ti + dt - nt
+            if has_lift:
+                nt = ev.lift_times[nl]
+                if nt <= ti + dt + _EPS and (nt + margin < t + T):
+                    g[stage].dt = nt - ti
+                    stage += 1
+                    nl += 1
+                    fill(stage, nt, min(ti + dt, t + T) - nt, LIFT)
+                    if abs((ti + dt) - nt) < _EPS:
+                        ti += dt
+                        g[stage].dt = ti + dt - nt
+            stage += 1
+            ti += dt
+        fill(stage, t + T, 0.0, TERMINAL)
+        ng = stage
+        for i in range(ng):
+            g[i].dt_next = g[i + 1].dt
+        g[ng].dt_next = 0.0
+        for i in range(ng - 1):
+            g[i].switching_constraint = (g[i + 2].type == IMPACT)
+        g[ng - 1].switching_constraint = False
+        g[ng].switching_constraint = False
+        for i in range(ng + 1):
+            g[i].t0 = t
+            g[i].sto = False
+            g[i].sto_next = False
+            g[i].stage_in_phase = 1
+            g[i].num_grids_in_phase = 1
+        # count grids (:148-182)
+        sip = 0
+        pstart = 0
+        i = 0
+        while i < ng:
+            if g[i].type == IMPACT:
+                for j in range(pstart, i):
+                    g[j].num_grids_in_phase = sip
+                g[i].stage_in_phase = 0
+                g[i].num_grids_in_phase = 0
+                i += 1
+                sip = 0
+                pstart = i
+            elif g[i].type == LIFT:
+                for j in range(pstart, i):
+                    g[j].num_grids_in_phase = sip
+                sip = 0
+                pstart = i
+            g[i].stage_in_phase = sip
+            sip += 1
+            i += 1
+        for j in range(pstart, ng):
+            g[j].num_grids_in_phase = sip
+        g[ng].stage_in_phase = 0
+        g[ng].num_grids_in_phase = 0
+        self.grid = g[:ng + 1]
+        self.num_grids = ng
+        if sto:
+            self._set_sto(ev)
+        return self
+
+    def _set_sto(self, ev: ContactEvents):
+        """STO flags: time_discretization.cpp:228-261."""
+        g, ng = self.grid, self.num_grids
+        sto_event = []
+        for i in range(ng):
+            if g[i].type == IMPACT:
+                sto_event.append(bool(ev.sto_impact[g[i + 1].impact_index]))
+            elif g[i].type == LIFT:
+                sto_event.append(bool(ev.sto_lift[g[i + 1].lift_index]))
+        if not sto_event:
+            return
+        sto_phase = [sto_event[0]]
+        for i in range(1, len(sto_event)):
+            sto_phase.append(sto_event[i - 1] or sto_event[i])
+        sto_phase.append(sto_event[-1])
+        sto_phase.append(False)
+        for i in range(ng):
+            ph = g[i].phase - g[0].phase
+            g[i].sto = sto_phase[ph]
+            g[i].sto_next = sto_phase[ph + 1]
+        g[ng].sto = False
+        g[ng].sto_next = False
+
+
+def stage_ctrl_array(td: TimeDiscretization, ev: ContactEvents):
+    """GridInfo list -> ctypes array of rbt_stage_ctrl.  The switching-constraint dimension of grid i is the
+    impact dimf of impactStatus(impact_index+1) (ocp_solver.cpp:471-474, kkt_factory.cpp:75-79)."""
+    n = td.size()
+    arr = (_lib.rbt_stage_ctrl * n)()
+    for i, gi in enumerate(td.grid):
+        c = arr[i]
+        c.type = gi.type
+        c.sto = int(gi.sto)
+        c.sto_next = int(gi.sto_next)
+        c.ns = ev.impact_dimf[gi.impact_index + 1] if gi.switching_constraint else 0
+        if gi.type == IMPACT:
+            c.nf = ev.impact_dimf[gi.impact_index]
+        else:
+            c.nf = ev.phase_dimf[gi.phase] if gi.phase < len(ev.phase_dimf) else 0
+        c.ngrids_in_phase = gi.num_grids_in_phase
+        c.dt = gi.dt
+    return arr
+
+
+def plain_schedule(N: int, dt: float, nf: int = 0):
+    """N Intermediate stages + Terminal, no events (e.g. a standing robot)."""
+    arr = (_lib.rbt_stage_ctrl * (N + 1))()
+    for i in range(N + 1):
+        arr[i].type = INTERMEDIATE if i < N else TERMINAL
+        arr[i].dt = dt if i < N else 0.0
+        arr[i].nf = nf
+        arr[i].ngrids_in_phase = N if i < N else 0
+    return arr
+
+
+def anymal_trot_events() -> ContactEvents:
+    """Contact schedule of /root/reference/examples/anymal/trot.cpp:41-47,172-190 (cycle=1):
+    stand(12) -lift@0.04-> LF+RH(6) -impact@0.54-> stand -lift@0.58-> LH+RF(6) -impact@1.08-> stand; T=1.12."""
+    ev = ContactEvents(phase_dimf=[12])
+    t0, swing, ds = 0.04, 0.5, 0.04
+    ev.push_back(False, t0, 6)
+    ev.push_back(True, t0 + swing, 12, impact_dimf=6)
+    ev.push_back(False, t0 + swing + ds, 6)
+    ev.push_back(True, t0 + 2 * swing + ds, 12, impact_dimf=6)
+    return ev
+
+
+def anymal_jump_sto_events() -> ContactEvents:
+    """Contact schedule of /root/reference/examples/anymal/jump_sto.cpp:42-48,131-140:
+    stand(12) -lift@0.4 (sto)-> flying(0) -impact@0.9 (sto)-> stand; T=1.7."""
+    ev = ContactEvents(phase_dimf=[12])
+    ev.push_back(False, 0.70 - 0.3, 0, sto=True)
+    ev.push_back(True, 0.70 + 0.30 - 0.1, 12, impact_dimf=12, sto=True)
+    return ev

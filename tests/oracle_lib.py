@@ -1,0 +1,73 @@
+"""ctypes wrapper around oracle/liboracle.so -- the CPU restatement of the reference (TEST INFRASTRUCTURE)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+LIB = os.path.join(ORACLE_DIR, "liboracle.so")
+
+_lib = None
+
+
+def build():
+    subprocess.run(["make", "-s", "-C", ORACLE_DIR], check=True)
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB):
+        build()
+    from robotoc_b200._lib import rbt_dims, rbt_stage_ctrl
+    L = ctypes.CDLL(LIB)
+    c_int, c_dbl, c_vp = ctypes.c_int, ctypes.c_double, ctypes.c_void_p
+    pdims, pctrl = ctypes.POINTER(rbt_dims), ctypes.POINTER(rbt_stage_ctrl)
+    L.orc_layout_get.argtypes = [pdims, ctypes.c_char_p]
+    L.orc_ulayout_get.argtypes = [c_int, ctypes.c_char_p]
+    L.orc_riccati_backward.argtypes = [pdims, pctrl, c_int, c_dbl, c_vp, c_vp]
+    L.orc_riccati_forward.argtypes = [pdims, pctrl, c_int, c_vp, c_vp, c_vp]
+    L.orc_riccati_batch.argtypes = [pdims, pctrl, c_int, c_dbl, c_int, c_vp, c_vp, c_vp, c_vp, c_int]
+    L.orc_unconstr_backward.argtypes = [c_int, c_int, c_dbl, c_vp, c_vp]
+    L.orc_unconstr_forward.argtypes = [c_int, c_int, c_dbl, c_vp, c_vp, c_vp]
+    L.orc_unconstr_batch.argtypes = [c_int, c_int, c_dbl, c_int, c_vp, c_vp, c_vp, c_vp, c_int]
+    L.orc_backward_full_step.argtypes = [pdims, c_int, c_int, c_int, c_vp, c_vp, c_vp]
+    L.orc_backward_impact_step.argtypes = [pdims, c_int, c_vp, c_vp, c_vp]
+    L.orc_backward_impact_step.restype = None
+    L.orc_phase_transition_step.argtypes = [pdims, c_dbl, c_vp, c_vp, c_vp, c_int]
+    L.orc_phase_transition_step.restype = None
+    L.orc_max_threads.restype = c_int
+    _lib = L
+    return L
+
+
+def ptr(a):
+    assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def riccati_batch(dims, L, ctrl, kkt, dx0, max_dts0=0.1, nthreads=0, forward=True):
+    """Runs the oracle over a batch.  Returns (kkt_mutated, ric, dir, info); kkt is copied first."""
+    lib = load()
+    batch, n_grid = kkt.shape[0], kkt.shape[1]
+    kk = kkt.copy()
+    ric = np.zeros((batch, n_grid, L.r_stride))
+    d = np.zeros((batch, n_grid, L.d_stride)) if forward else None
+    cd = dims.c()
+    info = lib.orc_riccati_batch(ctypes.byref(cd), ctrl, n_grid, max_dts0, batch, ptr(kk), ptr(ric),
+                                 ptr(dx0) if forward else None, ptr(d) if forward else None, nthreads)
+    return kk, ric, d, info
+
+
+def unconstr_batch(nv, UL, N, dt, kkt, dx0, nthreads=0, forward=True):
+    lib = load()
+    batch = kkt.shape[0]
+    kk = kkt.copy()
+    ric = np.zeros((batch, N + 1, UL.r_stride))
+    d = np.zeros((batch, N + 1, UL.d_stride)) if forward else None
+    info = lib.orc_unconstr_batch(nv, N, dt, batch, ptr(kk), ptr(ric), ptr(dx0) if forward else None,
+                                  ptr(d) if forward else None, nthreads)
+    return kk, ric, d, info
