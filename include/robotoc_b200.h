@@ -70,8 +70,16 @@ int rbt_set_schedule(rbt_handle* h, const rbt_stage_ctrl* ctrl, int n_grid, doub
 double* rbt_dev_ptr(rbt_handle* h, int which);
 long long rbt_buf_doubles(rbt_handle* h, int which); /* size of that buffer in doubles for the current schedule */
 
+/* Use a caller-owned device buffer (>= rbt_buf_doubles(h, which) doubles) instead of the handle's own; NULL restores
+ * the internal one.  The reference's solver owns its containers (OCPSolver members kkt_matrix_, riccati_factorization_,
+ * d_; include/robotoc/solver/ocp_solver.hpp:219-236); this lets a GPU front-end or an NCCL all-gather work in place. */
+int rbt_bind_buffer(rbt_handle* h, int which, double* dev);
+
 int rbt_upload(rbt_handle* h, int which, const double* host, void* stream);   /* RBT_BUF_KKT or RBT_BUF_DX0 */
 int rbt_download(rbt_handle* h, int which, double* host, void* stream);       /* any output buffer */
+/* bytes rbt_upload(h, which, ..) actually moves host->device (KKT uploads skip record padding and, on stages without
+ * a switching constraint / STO, the unused switching+STO sections) */
+long long rbt_upload_bytes(rbt_handle* h, int which);
 int rbt_download_info(rbt_handle* h, int* host_flags, void* stream);          /* per-OCP Cholesky status */
 
 /* RiccatiRecursion::backwardRiccatiRecursion(time_discretization, kkt_matrix, kkt_residual, factorization)

@@ -6,7 +6,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librobotoc_b200.so")
+LIB_PATH = os.environ.get("ROBOTOC_B200_LIB", os.path.join(_HERE, "librobotoc_b200.so"))  # env override: A/B builds
 
 
 class rbt_dims(ctypes.Structure):
@@ -23,8 +23,8 @@ _lib = None
 # every symbol include/robotoc_b200.h declares
 EXPORTS = [
     "rbt_layout_get", "rbt_ulayout_get", "rbt_device_info", "rbt_version",
-    "rbt_create", "rbt_destroy", "rbt_set_schedule", "rbt_dev_ptr", "rbt_buf_doubles", "rbt_upload",
-    "rbt_download", "rbt_download_info", "rbt_riccati_backward", "rbt_riccati_forward",
+    "rbt_create", "rbt_destroy", "rbt_set_schedule", "rbt_dev_ptr", "rbt_buf_doubles", "rbt_bind_buffer", "rbt_upload",
+    "rbt_download", "rbt_upload_bytes", "rbt_download_info", "rbt_riccati_backward", "rbt_riccati_forward",
     "rbt_riccati_solve_host", "rbt_sync", "rbt_last_error", "rbt_launch_count",
     "rbt_unconstr_create", "rbt_unconstr_destroy", "rbt_unconstr_dev_ptr", "rbt_unconstr_buf_doubles",
     "rbt_unconstr_upload", "rbt_unconstr_download", "rbt_unconstr_download_info", "rbt_unconstr_backward",
@@ -58,9 +58,12 @@ def lib():
     L.rbt_dev_ptr.restype = c_vp
     L.rbt_buf_doubles.argtypes = [c_vp, c_int]
     L.rbt_buf_doubles.restype = c_ll
+    L.rbt_bind_buffer.argtypes = [c_vp, c_int, c_vp]
     L.rbt_upload.argtypes = [c_vp, c_int, c_vp, c_vp]
     L.rbt_download.argtypes = [c_vp, c_int, c_vp, c_vp]
     L.rbt_download_info.argtypes = [c_vp, c_vp, c_vp]
+    L.rbt_upload_bytes.argtypes = [c_vp, c_int]
+    L.rbt_upload_bytes.restype = c_ll
     L.rbt_riccati_backward.argtypes = [c_vp, c_int, c_vp]
     L.rbt_riccati_forward.argtypes = [c_vp, c_vp]
     L.rbt_riccati_solve_host.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]

@@ -2,6 +2,7 @@
 // Plumbing only: handles, device buffers, stream-ordered copies and kernel launches.  No CPU compute path.
 #include <cstdio>
 #include <cstring>
+#include <cstdint>
 #include <cstdlib>
 #include <string>
 #include <vector>
@@ -41,7 +42,9 @@ struct rbt_handle {
   int n_grid_max = 0, n_grid = 0, batch = 0, device = 0;
   double max_dts0 = 0.1;
   rbt_stage_ctrl* d_ctrl = nullptr;
+  std::vector<rbt_stage_ctrl> ctrl;  // host copy
   double *d_kkt = nullptr, *d_ric = nullptr, *d_fact = nullptr, *d_dir = nullptr, *d_dx0 = nullptr;
+  double* own[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // the handle's own allocations (freed in destroy)
   int* d_info = nullptr;
   long long launches = 0;
   std::string err;
@@ -125,6 +128,11 @@ int rbt_create(const rbt_dims* dims, int n_grid_max, int batch, int device, rbt_
   RBT_CUDA(h, cudaMemset(h->d_fact, 0, per * h->L.f_stride * 8));
   RBT_CUDA(h, cudaMemset(h->d_dir, 0, per * h->L.d_stride * 8));
   RBT_CUDA(h, cudaMemset(h->d_info, 0, size_t(batch) * sizeof(int)));
+  h->own[RBT_BUF_KKT] = h->d_kkt;
+  h->own[RBT_BUF_RIC] = h->d_ric;
+  h->own[RBT_BUF_FACT] = h->d_fact;
+  h->own[RBT_BUF_DIR] = h->d_dir;
+  h->own[RBT_BUF_DX0] = h->d_dx0;
   return RBT_OK;
 }
 
@@ -132,11 +140,7 @@ int rbt_destroy(rbt_handle* h) {
   if (!h) return RBT_ERR_ARG;
   cudaSetDevice(h->device);
   cudaFree(h->d_ctrl);
-  cudaFree(h->d_kkt);
-  cudaFree(h->d_ric);
-  cudaFree(h->d_fact);
-  cudaFree(h->d_dir);
-  cudaFree(h->d_dx0);
+  for (int q = 0; q < 5; ++q) cudaFree(h->own[q]);
   cudaFree(h->d_info);
   delete h;
   return RBT_OK;
@@ -168,6 +172,7 @@ int rbt_set_schedule(rbt_handle* h, const rbt_stage_ctrl* ctrl, int n_grid, doub
   RBT_CUDA(h, cudaMemset(h->d_dir, 0, size_t(h->batch) * n_grid * h->L.d_stride * 8));
   h->n_grid = n_grid;
   h->max_dts0 = max_dts0;
+  h->ctrl.assign(ctrl, ctrl + n_grid);
   return RBT_OK;
 }
 
@@ -197,10 +202,76 @@ long long rbt_buf_doubles(rbt_handle* h, int which) {
 
 double* rbt_dev_ptr(rbt_handle* h, int which) { return h ? buf_ptr(h, which) : nullptr; }
 
+int rbt_bind_buffer(rbt_handle* h, int which, double* dev) {
+  if (!h || which < RBT_BUF_KKT || which > RBT_BUF_DX0) return RBT_ERR_ARG;
+  double* q = dev ? dev : h->own[which];
+  if ((reinterpret_cast<uintptr_t>(q) & 15u) != 0) {
+    h->err = "[rbt_bind_buffer] invalid argument: device buffer must be 16-byte aligned";
+    return RBT_ERR_ARG;
+  }
+  switch (which) {
+    case RBT_BUF_KKT: h->d_kkt = q; break;
+    case RBT_BUF_RIC: h->d_ric = q; break;
+    case RBT_BUF_FACT: h->d_fact = q; break;
+    case RBT_BUF_DIR: h->d_dir = q; break;
+    default: h->d_dx0 = q; break;
+  }
+  return RBT_OK;
+}
+
+// KKT upload plan: one strided copy of the core section [Fxx|Fvu|Fx|lx|lu|Qxx|Qxu|Quu] of every record (record padding and
+// unused switching/STO sections never cross PCIe), plus one strided copy per stage that carries extras.
+static long long kkt_upload(rbt_handle* h, const double* host, cudaStream_t st, bool do_copy, int* rc_out) {
+  const rbt_layout& L = h->L;
+  const size_t pitch = size_t(L.k_stride) * 8;
+  int n_extra = 0;
+  for (const auto& c : h->ctrl) n_extra += (c.ns > 0 || c.sto) ? 1 : 0;
+  const bool wide = n_extra * 2 > h->n_grid;  // most stages carry extras (STO horizons): copy core+extras in one go
+  const size_t width = size_t(wide ? L.k_core_size + L.k_extra_size : L.k_core_size) * 8;
+  const size_t rows = size_t(h->batch) * h->n_grid;
+  long long bytes = (long long)(width * rows);
+  if (do_copy && cudaMemcpy2DAsync(h->d_kkt, pitch, host, pitch, width, rows, cudaMemcpyHostToDevice, st) != cudaSuccess) {
+    *rc_out = RBT_ERR_CUDA;
+    return 0;
+  }
+  if (!wide) {
+    const size_t opitch = pitch * h->n_grid;
+    for (int i = 0; i < h->n_grid; ++i) {
+      const rbt_stage_ctrl& c = h->ctrl[i];
+      if (!(c.ns > 0 || c.sto)) continue;
+      const size_t off = size_t(i) * L.k_stride + L.k_Phix;
+      bytes += (long long)(size_t(L.k_extra_size) * 8 * h->batch);
+      if (do_copy && cudaMemcpy2DAsync(h->d_kkt + off, opitch, host + off, opitch, size_t(L.k_extra_size) * 8, h->batch,
+                                       cudaMemcpyHostToDevice, st) != cudaSuccess) {
+        *rc_out = RBT_ERR_CUDA;
+        return 0;
+      }
+    }
+  }
+  return bytes;
+}
+
+long long rbt_upload_bytes(rbt_handle* h, int which) {
+  if (!h || h->n_grid == 0) return -1;
+  if (which == RBT_BUF_DX0) return rbt_buf_doubles(h, which) * 8;
+  if (which != RBT_BUF_KKT) return -1;
+  int rc = RBT_OK;
+  return kkt_upload(h, nullptr, nullptr, false, &rc);
+}
+
 int rbt_upload(rbt_handle* h, int which, const double* host, void* stream) {
   if (!h || !host || (which != RBT_BUF_KKT && which != RBT_BUF_DX0)) return RBT_ERR_ARG;
   if (h->n_grid == 0) return RBT_ERR_STATE;
   RBT_CUDA(h, cudaSetDevice(h->device));
+  if (which == RBT_BUF_KKT) {
+    int rc = RBT_OK;
+    kkt_upload(h, host, (cudaStream_t)stream, true, &rc);
+    if (rc != RBT_OK) {
+      h->err = std::string("rbt_upload(KKT): ") + cudaGetErrorString(cudaGetLastError());
+      return rc;
+    }
+    return RBT_OK;
+  }
   RBT_CUDA(h, cudaMemcpyAsync(buf_ptr(h, which), host, size_t(rbt_buf_doubles(h, which)) * 8, cudaMemcpyHostToDevice,
                               (cudaStream_t)stream));
   return RBT_OK;
@@ -246,7 +317,6 @@ static int launch_backward(rbt_handle* h, int write_fact, cudaStream_t st) {
   p.ric = h->d_ric;
   p.fact = write_fact ? h->d_fact : nullptr;
   p.info = h->d_info;
-  p.dbg = getenv("RBT_DEBUG_STOP") ? atoi(getenv("RBT_DEBUG_STOP")) : 0;
   RBT_CUDA(h, cudaMemsetAsync(h->d_info, 0, size_t(h->batch) * sizeof(int), st));
   kern<<<h->batch, C::NTHREADS, C::SMEM_BYTES, st>>>(p);
   RBT_CUDA(h, cudaGetLastError());

@@ -8,14 +8,18 @@
 // Design (not a translation):
 //  * CTA = one OCP; the serial sweep i = N-1..0 runs inside the kernel with P_next resident in shared memory.
 //  * [Fxx|Fvu|Fx|lx|lu] of a stage arrives by ONE cp.async.bulk (TMA 1-D) + mbarrier, issued as soon as the previous
-//    stage stops reading the staging buffer, so the copy overlaps the latency-bound Cholesky / solve / symmetrise tail.
+//    stage stops reading the staging buffer, so the copy overlaps the tail of the stage.
 //    Qxx/Qxu/Quu never touch shared memory: they are loaded straight into DMMA accumulator fragments.
-//  * All dense contractions (A^T P, (A^T P) A, B^T P, .. , Y^T Y) run on the fp64 tensor pipe (mma.sync m8n8k4):
-//    warp w owns the 8-row band w of every product; extents that are not multiples of 8 use one pulled-back
-//    (overlapping) tile instead of padding, so the bulk copy lands unpadded.
-//  * algebra: z = s+ - P+ Fx makes  lu += B^T P+ Fx - B^T s+  ==  lu -= Bv^T z_v  and  s = A^T z - lx - H k;
-//    with G = L L^T, Y = L^-1 H^T:  K = -L^-T Y and  P = sym(F - Y^T Y)  (the reference forms G K and K^T (G K)).
-//    Rounding differs from the reference at the 1e-15 level; parity tolerance is 1e-6 relative (BASELINE.json).
+//  * All dense contractions run on the fp64 tensor pipe (mma.sync m8n8k4): GEMM warp w owns the 8-row band w of every
+//    product; extents that are not multiples of 8 use one pulled-back (overlapping) tile instead of padding.
+//  * Warp specialisation: TX "GEMM warps" do A^T P, (A^T P) A, H; one extra "factor warp" builds
+//    G = Quu + Bv^T P_vv Bv, its Cholesky L and L^-1 concurrently (r1 profile: 53 % of all stall samples were warps
+//    parked at barriers behind a single-warp Cholesky + per-thread triangular solves).
+//  * algebra: z = s+ - P+ Fx gives  lu' = lu - Bv^T z_v,  t1 = A^T z - lx;  with  Y = L^-1 H^T,  y = L^-1 lu':
+//        P = sym(F - Y^T Y),   s = t1 + Y^T y,   K = -L^-T Y,   k = -L^-T y
+//    so the critical path needs no triangular solve and no K; K, k are produced by the factor warp off the critical
+//    path.  (The reference forms K = -G^-1 H^T, G K and K^T (G K).)  Rounding differs from the reference at the
+//    1e-15 level; the parity tolerance is 1e-6 relative (BASELINE.json).
 //  * switching-constraint (Schur) stages and STO terms follow the reference formulas with plain shared-memory loops:
 //    they are 2 of 47 stages (trot) / vector-only work.
 #pragma once
@@ -34,7 +38,6 @@ struct BwdParams {
   double* ric;        // [batch][n_grid][r_stride]
   double* fact;       // [batch][n_grid][f_stride] or nullptr
   int* info;          // [batch]
-  int dbg;            // bring-up only: early-exit level (0 = run normally)
 };
 
 template <int NV, int NU, int NS>
@@ -43,27 +46,30 @@ struct BwdCfg {
   static constexpr int LDF = NX + 1;  // padded row stride of the F scratch (conflict-free transpose reads)
   static constexpr int TX = num_tiles(NX);
   static constexpr int TU = num_tiles(NU);
-  static constexpr int NWARPS = TX;
-  static constexpr int NTHREADS = 32 * NWARPS;
+  static constexpr int TV = num_tiles(NV);
+  static constexpr int NGEMM = 32 * TX;        // threads in the GEMM warps
+  static constexpr int NTHREADS = NGEMM + 32;  // + the factor warp
   // shared-memory carve-up (doubles)
   static constexpr int STAGE = NX * NX + ((NV * NU + 1) & ~1) + 2 * ((NX + 1) & ~1) + ((NU + 1) & ~1);
   static constexpr int EXTRA = ((NS * NX + 1) & ~1) + ((NS * NU + 1) & ~1) + ((NS + 1) & ~1) + 2 * ((NX + 1) & ~1) +
                                ((NU + 1) & ~1) + ((NS + 1) & ~1) + 4;
   static constexpr int o_P = 0;
-  static constexpr int o_AtP = o_P + NX * NX;
+  static constexpr int o_AtP = o_P + NX * NX;  // AtP (ld NX) -> [Schur: K^T] -> F scratch (ld LDF)
   static constexpr int o_In = o_AtP + ((NX * LDF + 1) & ~1);
   static constexpr int o_Ex = o_In + STAGE;
-  static constexpr int o_BtP = o_Ex + EXTRA;  // also Y / GK
-  static constexpr int o_H = o_BtP + NU * NX;
-  static constexpr int o_Kt = o_H + NX * NU;
-  static constexpr int o_G = o_Kt + NX * NU;
-  static constexpr int o_vec = o_G + NU * NU;
+  static constexpr int o_Y = o_Ex + EXTRA;  // Y = L^-1 H^T (col-major, ld NU); Schur: G K
+  static constexpr int o_H = o_Y + NU * NX;
+  static constexpr int o_G = o_H + NX * NU;
+  static constexpr int o_Li = o_G + NU * NU;   // L^-1 (col-major)
+  static constexpr int o_Bp = o_Li + NU * NU;  // Bv^T P+_vv (row-major, ld NV)
+  static constexpr int o_vec = o_Bp + ((NU * NV + 1) & ~1);
   // vectors
   static constexpr int v_sn = 0, v_z = v_sn + NX, v_t1 = v_z + NX, v_Psin = v_t1 + NX, v_Phin = v_Psin + NX,
                        v_psix = v_Phin + NX, v_phix = v_psix + NX, v_Psi = v_phix + NX, v_Phi = v_Psi + NX,
-                       v_Pf = v_Phi + NX, v_lu2 = v_Pf + NX, v_k = v_lu2 + NU, v_psiu = v_k + NU, v_phiu = v_psiu + NU,
-                       v_T = v_phiu + NU, v_W = v_T + NU, v_dinv = v_W + NU, v_m = v_dinv + NU, v_mt = v_m + NS,
-                       v_mtn = v_mt + NS, v_dinvS = v_mtn + NS, v_Fxs = v_dinvS + NS, v_scn = v_Fxs + NX, v_sc = v_scn + 8,
+                       v_Pf = v_Phi + NX, v_Fxs = v_Pf + NX, v_lu2 = v_Fxs + NX, v_k = v_lu2 + NU, v_ylu = v_k + NU,
+                       v_psiu = v_ylu + NU, v_phiu = v_psiu + NU, v_tps = v_phiu + NU, v_tph = v_tps + NU,
+                       v_T = v_tph + NU, v_W = v_T + NU, v_dinv = v_W + NU, v_m = v_dinv + NU, v_mt = v_m + NS,
+                       v_mtn = v_mt + NS, v_dinvS = v_mtn + NS, v_scn = v_dinvS + NS, v_sc = v_scn + 8,
                        v_end = v_sc + 8;
   static constexpr int o_bar = (o_vec + v_end + 1) & ~1;
   static constexpr int SMEM_DOUBLES = o_bar + 2;
@@ -72,12 +78,21 @@ struct BwdCfg {
   static constexpr int x_Ginv = 0, x_DG = x_Ginv + NU * NU, x_S = x_DG + NS * NU, x_SDG = x_S + NS * NS,
                        x_M = x_SDG + NS * NU, x_DtM = x_M + NS * NX, x_Gc = x_DtM + NU * NX, x_end = x_Gc + NU * NU;
   static_assert(x_end <= STAGE, "Schur scratch must fit in the staging buffer");
-  static_assert(NX >= 8 && NU >= 8, "DMMA tiling needs extents >= 8");
+  static_assert(NX >= 8 && NU >= 8 && NV >= 8, "DMMA tiling needs extents >= 8");
   static_assert(NX % 2 == 0, "nx even");
+  static_assert(NU <= 32 && NS <= 32, "one-warp Cholesky");
 };
 
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int count) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
 // In-place lower Cholesky of an n x n (n <= NMAX <= 32) column-major matrix in shared memory by ONE warp
-// (lane = row).  dinv[j] = 1 / L_jj.  Returns false on a non-positive pivot (factor then holds garbage).
+// (lane = row; the row being updated lives in registers, finished columns are broadcast through shared memory).
+// dinv[j] = 1 / L_jj.  Returns false on a non-positive pivot (factor then holds garbage).
 template <int NMAX>
 __device__ __forceinline__ bool warp_cholesky(double* A, int n, double* dinv) {
   const int lane = threadIdx.x & 31;
@@ -90,21 +105,21 @@ __device__ __forceinline__ bool warp_cholesky(double* A, int n, double* dinv) {
     if (j < n) {
       const double d = __shfl_sync(0xffffffffu, a[j], j);
       if (!(d > 0.0)) ok = false;
-      const double sd = sqrt(d);
-      const double inv = 1.0 / sd;
-      const double lij = (lane == j) ? sd : a[j] * inv;
+      const double inv = rsqrt(d);
+      const double lij = (lane == j) ? d * inv : a[j] * inv;
       a[j] = lij;
       if (lane == j) dinv[j] = inv;
+      if (lane >= j && lane < n) A[lane + j * n] = lij;
+      __syncwarp();
 #pragma unroll
       for (int k = j + 1; k < NMAX; ++k) {
-        const double lkj = __shfl_sync(0xffffffffu, lij, k < 32 ? k : 0);
-        if (k < n && lane >= k) a[k] = fma(-lij, lkj, a[k]);
+        if (k < n) {
+          const double lkj = A[k + j * n];  // broadcast read
+          if (lane >= k) a[k] = fma(-lij, lkj, a[k]);
+        }
       }
     }
   }
-#pragma unroll
-  for (int k = 0; k < NMAX; ++k)
-    if (lane < n && k <= lane && k < n) A[lane + k * n] = a[k];
   return ok;
 }
 
@@ -123,26 +138,31 @@ __device__ __forceinline__ void chol_solve_smem(const double* Lm, const double* 
 }
 
 template <int NV, int NU, int NS>
-__global__ void __launch_bounds__(BwdCfg<NV, NU, NS>::NTHREADS, 4) riccati_backward_kernel(const BwdParams p) {
+#ifndef RBT_BWD_MIN_CTAS
+#define RBT_BWD_MIN_CTAS 4
+#endif
+__global__ void __launch_bounds__(BwdCfg<NV, NU, NS>::NTHREADS, RBT_BWD_MIN_CTAS) riccati_backward_kernel(const BwdParams p) {
   using C = BwdCfg<NV, NU, NS>;
-  constexpr int NX = C::NX, LDF = C::LDF, TX = C::TX, TU = C::TU, NTHR = C::NTHREADS;
+  constexpr int NX = C::NX, LDF = C::LDF, TX = C::TX, TU = C::TU, TV = C::TV, NTHR = C::NTHREADS, NG = C::NGEMM;
   extern __shared__ __align__(16) double smem[];
   double* sP = smem + C::o_P;
   double* sAtP = smem + C::o_AtP;  // AtP row-major (ld NX); later F scratch row-major (ld LDF)
+  double* sKt = sAtP;              // Schur stages only: K^T col-major (ld NX), between AtP's death and the F spill
   double* sIn = smem + C::o_In;
   double* sA = sIn;            // Fxx col-major
   double* sB = sIn + NX * NX;  // Fvu col-major (ld NV)
   double* sEx = smem + C::o_Ex;
-  double* sBtP = smem + C::o_BtP;  // BtP row-major (ld NX); later Y / GK col-major (ld NU)
-  double* sY = sBtP;
+  double* sY = smem + C::o_Y;    // Y col-major (ld NU)
   double* sH = smem + C::o_H;    // H col-major (ld NX)
-  double* sKt = smem + C::o_Kt;  // K^T col-major (ld NX)
   double* sG = smem + C::o_G;    // G, then its Cholesky factor
+  double* sLi = smem + C::o_Li;  // L^-1 col-major (ld NU), lower triangular (upper part zero)
+  double* sBp = smem + C::o_Bp;  // Bv^T P+_vv row-major (ld NV)
   double* vec = smem + C::o_vec;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::o_bar);
 
   const rbt_layout& L = p.L;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  const bool gemm_warp = warp < TX;
   const int b = blockIdx.x;
   if (b >= p.batch) return;
   const int N = p.n_grid - 1;
@@ -154,7 +174,7 @@ __global__ void __launch_bounds__(BwdCfg<NV, NU, NS>::NTHREADS, 4) riccati_backw
   const double* slx = sIn + (L.k_lx - L.k_Fxx);
   const double* slu = sIn + (L.k_lu - L.k_Fxx);
   // extras (valid only on ns>0 / sto stages)
-  const double* sPhix = sEx + (L.k_Phix - L.k_Phix);
+  const double* sPhix = sEx;
   const double* sPhiu = sEx + (L.k_Phiu - L.k_Phix);
   const double* sp = sEx + (L.k_p - L.k_Phix);
   const double* sfx = sEx + (L.k_fx - L.k_Phix);
@@ -173,10 +193,14 @@ __global__ void __launch_bounds__(BwdCfg<NV, NU, NS>::NTHREADS, 4) riccati_backw
   double* Psi = vec + C::v_Psi;
   double* Phi = vec + C::v_Phi;
   double* Pf = vec + C::v_Pf;
+  double* Fxs = vec + C::v_Fxs;  // copy of Fx (the staging buffer is reused / refilled early)
   double* lu2 = vec + C::v_lu2;
   double* kv = vec + C::v_k;
+  double* ylu = vec + C::v_ylu;
   double* psiu = vec + C::v_psiu;
   double* phiu = vec + C::v_phiu;
+  double* tps = vec + C::v_tps;  // L^-1 psi_u
+  double* tph = vec + C::v_tph;  // L^-1 phi_u
   double* Tv = vec + C::v_T;
   double* Wv = vec + C::v_W;
   double* dinv = vec + C::v_dinv;
@@ -184,7 +208,6 @@ __global__ void __launch_bounds__(BwdCfg<NV, NU, NS>::NTHREADS, 4) riccati_backw
   double* mt = vec + C::v_mt;
   double* mtn = vec + C::v_mtn;
   double* dinvS = vec + C::v_dinvS;
-  double* Fxs = vec + C::v_Fxs;  // copy of Fx (the staging buffer is reused as Schur scratch)
   double* scn = vec + C::v_scn;  // next-stage {xi, chi, rho, eta, iota}
   double* sc = vec + C::v_sc;
 
@@ -232,7 +255,6 @@ __global__ void __launch_bounds__(BwdCfg<NV, NU, NS>::NTHREADS, 4) riccati_backw
   __syncthreads();
 
   uint32_t par0 = 0, par1 = 0;
-  if (p.dbg == 1) return;
 
   for (int i = N - 1; i >= 0; --i) {
     const rbt_stage_ctrl cs = p.ctrl[i];
@@ -240,6 +262,7 @@ __global__ void __launch_bounds__(BwdCfg<NV, NU, NS>::NTHREADS, 4) riccati_backw
     const int ns = impact ? 0 : cs.ns;
     const bool sto = cs.sto != 0, sto_next = cs.sto_next != 0;
     const bool extras = (cs.ns > 0 || cs.sto);
+    const bool plain = !impact && ns == 0;  // factor-warp fast path
     const double* rec = kkt_b + size_t(i) * L.k_stride;
     double* ric = ric_b + size_t(i) * L.r_stride;
     double* fct = fact_b ? fact_b + size_t(i) * L.f_stride : nullptr;
@@ -296,17 +319,18 @@ __global__ void __launch_bounds__(BwdCfg<NV, NU, NS>::NTHREADS, 4) riccati_backw
       }
     }
 
-    const int i0 = tile_off(warp, NX);  // this warp's row band
+    const int i0 = tile_off(gemm_warp ? warp : 0, NX);  // this GEMM warp's row band
+    double cF[TX][2];                                   // F fragments (GEMM warps only)
 
-    // Qxx -> accumulator fragments of F (issued before the wait, consumed after GEMM1)
-    double cF[TX][2];
+    if (gemm_warp) {
+      // Qxx -> accumulator fragments of F (issued before the wait, consumed after GEMM1)
 #pragma unroll
-    for (int n = 0; n < TX; ++n) {
-      const int j0 = tile_off(n, NX);
-      cF[n][0] = __ldg(rec + L.k_Qxx + (i0 + g) + (j0 + 2 * t) * NX);
-      cF[n][1] = __ldg(rec + L.k_Qxx + (i0 + g) + (j0 + 2 * t + 1) * NX);
+      for (int n = 0; n < TX; ++n) {
+        const int j0 = tile_off(n, NX);
+        cF[n][0] = __ldg(rec + L.k_Qxx + (i0 + g) + (j0 + 2 * t) * NX);
+        cF[n][1] = __ldg(rec + L.k_Qxx + (i0 + g) + (j0 + 2 * t + 1) * NX);
+      }
     }
-
     // ---- wait for this stage's blocks
     mbar_wait(&bars[0], par0);
     par0 ^= 1;
@@ -314,46 +338,33 @@ __global__ void __launch_bounds__(BwdCfg<NV, NU, NS>::NTHREADS, 4) riccati_backw
       mbar_wait(&bars[1], par1);
       par1 ^= 1;
     }
-    if (p.dbg == 2) return;
 
-    // ================= phase 1: AtP = A^T P+ (all warps), BtP = Bv^T P+[nv:,:] (warps < TU), z = s+ - P+ Fx
-    {
-      double acc[TX][2];
+    if (gemm_warp) {
+      // ================= phase A (GEMM warps): AtP = A^T P+ ; z = s+ - P+ Fx
+      {
+        double acc[TX][2];
 #pragma unroll
-      for (int n = 0; n < TX; ++n) acc[n][0] = acc[n][1] = 0.0;
+        for (int n = 0; n < TX; ++n) acc[n][0] = acc[n][1] = 0.0;
+        warp_mma_band<NX, TX, NX>(
+            acc, i0, [&](int ii, int k) { return sA[k + ii * NX]; }, [&](int k, int j) { return sP[k + j * NX]; });
+#pragma unroll
+        for (int n = 0; n < TX; ++n) {
+          const int j0 = tile_off(n, NX);
+          *reinterpret_cast<double2*>(&sAtP[(i0 + g) * NX + j0 + 2 * t]) = make_double2(acc[n][0], acc[n][1]);
+        }
+      }
+      matvec_N4(sP, NX, NX, NX, sFx, tid, NG, [&](int r, double a) { z[r] = s_n[r] - a; });
+      if (sto) {
+        if (!impact) matvec_N4(sP, NX, NX, NX, sfx, tid, NG, [&](int r, double a) { Pf[r] = a; });
+        if (tid < NX) Fxs[tid] = sFx[tid];
+      }
+      named_bar_sync(1, NG);      // AtP and z complete among the GEMM warps
+      named_bar_arrive(2, NTHR);  // ... and visible to the factor warp (non-blocking)
+
+      // ================= phase B (GEMM warps): F = Qxx + AtP A ; H = Qxu + AtP[:,nv:] Bv ; t1 = A^T z - lx
       warp_mma_band<NX, TX, NX>(
-          acc, i0, [&](int ii, int k) { return sA[k + ii * NX]; }, [&](int k, int j) { return sP[k + j * NX]; });
-#pragma unroll
-      for (int n = 0; n < TX; ++n) {
-        const int j0 = tile_off(n, NX);
-        *reinterpret_cast<double2*>(&sAtP[(i0 + g) * NX + j0 + 2 * t]) = make_double2(acc[n][0], acc[n][1]);
-      }
-    }
-    if (!impact && warp < TU) {
-      const int u0 = tile_off(warp, NU);
-      double acc[TX][2];
-#pragma unroll
-      for (int n = 0; n < TX; ++n) acc[n][0] = acc[n][1] = 0.0;
-      warp_mma_band<NV, TX, NX>(
-          acc, u0, [&](int u, int k) { return sB[k + u * NV]; }, [&](int k, int j) { return sP[NV + k + j * NX]; });
-#pragma unroll
-      for (int n = 0; n < TX; ++n) {
-        const int j0 = tile_off(n, NX);
-        *reinterpret_cast<double2*>(&sBtP[(u0 + g) * NX + j0 + 2 * t]) = make_double2(acc[n][0], acc[n][1]);
-      }
-    }
-    // z = s+ - P+ Fx   (P+ symmetric; thread per row, conflict-free)
-    matvec_N(sP, NX, NX, NX, sFx, tid, NTHR, [&](int r, double a) { z[r] = s_n[r] - a; });
-    if (sto && !impact) matvec_N(sP, NX, NX, NX, sfx, tid, NTHR, [&](int r, double a) { Pf[r] = a; });
-    if (sto && tid < NX) Fxs[tid] = sFx[tid];
-    __syncthreads();
-    if (p.dbg == 3) return;
-
-    // ================= phase 2: F = Qxx + AtP A ; H = Qxu + AtP[:,nv:] Bv ; G = Quu + BtP[:,nv:] Bv ; vectors
-    warp_mma_band<NX, TX, NX>(
-        cF, i0, [&](int ii, int k) { return sAtP[ii * NX + k]; }, [&](int k, int j) { return sA[k + j * NX]; });
-    if (!impact) {
-      {  // H: this warp's row band, TU column tiles
+          cF, i0, [&](int ii, int k) { return sAtP[ii * NX + k]; }, [&](int k, int j) { return sA[k + j * NX]; });
+      if (!impact) {
         double cH[TU][2];
 #pragma unroll
         for (int n = 0; n < TU; ++n) {
@@ -374,147 +385,200 @@ __global__ void __launch_bounds__(BwdCfg<NV, NU, NS>::NTHREADS, 4) riccati_backw
           }
         }
       }
-      if (warp < TU) {  // G: row band `warp` of BtP[:,nv:] Bv
-        const int u0 = tile_off(warp, NU);
-        double cG[TU][2];
-#pragma unroll
-        for (int n = 0; n < TU; ++n) {
-          const int v0 = tile_off(n, NU);
-          cG[n][0] = __ldg(rec + L.k_Quu + (u0 + g) + (v0 + 2 * t) * NU);
-          cG[n][1] = __ldg(rec + L.k_Quu + (u0 + g) + (v0 + 2 * t + 1) * NU);
-        }
-        warp_mma_band<NV, TU, NU>(
-            cG, u0, [&](int u, int k) { return sBtP[u * NX + NV + k]; }, [&](int k, int v) { return sB[k + v * NV]; });
-#pragma unroll
-        for (int n = 0; n < TU; ++n) {
-          const int v0 = tile_off(n, NU);
-          sG[(u0 + g) + (v0 + 2 * t) * NU] = cG[n][0];
-          sG[(u0 + g) + (v0 + 2 * t + 1) * NU] = cG[n][1];
-          if (fct) {
-            fct[L.f_G + (u0 + g) + (v0 + 2 * t) * NU] = cG[n][0];
-            fct[L.f_G + (u0 + g) + (v0 + 2 * t + 1) * NU] = cG[n][1];
+      matvec_T(sA, NX, NX, NX, z, tid, NG, [&](int c, double a) { t1[c] = a - slx[c]; });
+      if (sto) {
+        if (!impact) {
+          // factorizeHamiltonian (x part): backward_riccati_recursion_factorizer.cpp:48-66; the same lane owns psix[c]
+          matvec_T(sAtP, NX, NX, NX, sfx, tid, NG, [&](int c, double a) { psix[c] = a + shx[c]; });  // AtP fx + hx
+          matvec_T(sA, NX, NX, NX, Psin, tid, NG, [&](int c, double a) { psix[c] += a; });
+          if (sto_next) {
+            matvec_T(sA, NX, NX, NX, Phin, tid, NG, [&](int c, double a) { phix[c] = a; });
+          } else if (tid < NX) {
+            phix[tid] = 0.0;
           }
-        }
-      }
-      // lu' = lu - Bv^T z_v      (== lu + BtP Fx - Bv^T s+_v)
-      matvec_T(sB, NV, NV, NU, z + NV, tid, NTHR, [&](int u, double a) {
-        const double v = slu[u] - a;
-        lu2[u] = v;
-        if (fct) fct[L.f_lu + u] = v;
-      });
-    }
-    // t1 = A^T z - lx
-    matvec_T(sA, NX, NX, NX, z, tid, NTHR, [&](int c, double a) { t1[c] = a - slx[c]; });
-    if (sto) {
-      if (!impact) {
-        // factorizeHamiltonian: backward_riccati_recursion_factorizer.cpp:48-66
-        matvec_T(sAtP, NX, NX, NX, sfx, tid, NTHR, [&](int c, double a) { psix[c] = a + shx[c]; });   // AtP fx + hx
-        matvec_T(sBtP, NX, NX, NU, sfx, tid, NTHR, [&](int u, double a) { psiu[u] = a + shu[u]; });   // BtP fx + hu
-        __syncthreads();
-        matvec_T(sA, NX, NX, NX, Psin, tid, NTHR, [&](int c, double a) { psix[c] += a; });
-        matvec_T(sB, NV, NV, NU, Psin + NV, tid, NTHR, [&](int u, double a) { psiu[u] += a; });
-        if (sto_next) {
-          matvec_T(sA, NX, NX, NX, Phin, tid, NTHR, [&](int c, double a) { phix[c] = a; });
-          matvec_T(sB, NV, NV, NU, Phin + NV, tid, NTHR, [&](int u, double a) { phiu[u] = a; });
         } else {
-          if (tid < NX) phix[tid] = 0.0;
-          if (tid < NU) phiu[tid] = 0.0;
+          // impact + sto: Phi = A^T Phi+      backward_riccati_recursion_factorizer.cpp:160-174
+          matvec_T(sA, NX, NX, NX, Phin, tid, NG, [&](int c, double a) { Phi[c] = a; });
         }
-      } else {
-        // impact + sto: Phi = A^T Phi+      backward_riccati_recursion_factorizer.cpp:160-174
-        matvec_T(sA, NX, NX, NX, Phin, tid, NTHR, [&](int c, double a) { Phi[c] = a; });
       }
-    }
-    __syncthreads();
-
-    // staging buffer is dead on plain stages: prefetch the next stage now (overlaps the serial tail)
-    const bool early_prefetch = !extras;
-    if (early_prefetch && tid == 0 && i > 0) issue_stage_load(i - 1);
-    if (p.dbg == 4) return;
-
-    if (!impact) {
-      if (ns == 0) {
-        // ================= phase 3: L L^T = G (warp 0)
-        if (warp == 0) {
-          if (!warp_cholesky<NU>(sG, NU, dinv)) bad |= 1;
-        }
-        __syncthreads();
-        if (p.dbg == 5) return;
-        // ================= phase 4: Y = L^-1 H^T, K = -L^-T Y, k = -G^-1 lu', [T, W]
-        if (tid < NX + 3) {
-          const int c = tid;
-          double y[NU];
-          bool active = true;
-          if (c < NX) {
+    } else {
+      // ================= factor warp: G = Quu + (Bv^T P+_vv) Bv, L L^T = G, L^-1, lu' = lu - Bv^T z_v, y = L^-1 lu'
+      if (!impact) {
 #pragma unroll
-            for (int u = 0; u < NU; ++u) y[u] = sH[c + u * NX];
-          } else if (c == NX) {
+        for (int ub = 0; ub < TU; ++ub) {  // Bp = Bv^T P+[nv:, nv:]   (NU x NV, K = NV)
+          const int u0 = tile_off(ub, NU);
+          double acc[TV][2];
 #pragma unroll
-            for (int u = 0; u < NU; ++u) y[u] = lu2[u];
-          } else if (c == NX + 1) {
-            active = sto;
+          for (int n = 0; n < TV; ++n) acc[n][0] = acc[n][1] = 0.0;
+          warp_mma_band<NV, TV, NV>(
+              acc, u0, [&](int u, int k) { return sB[k + u * NV]; },
+              [&](int k, int j) { return sP[(NV + k) + (NV + j) * NX]; });
 #pragma unroll
-            for (int u = 0; u < NU; ++u) y[u] = sto ? psiu[u] : 0.0;
-          } else {
-            active = sto && sto_next;
-#pragma unroll
-            for (int u = 0; u < NU; ++u) y[u] = active ? phiu[u] : 0.0;
+          for (int n = 0; n < TV; ++n) {
+            const int j0 = tile_off(n, NV);
+            *reinterpret_cast<double2*>(&sBp[(u0 + g) * NV + j0 + 2 * t]) = make_double2(acc[n][0], acc[n][1]);
           }
-          if (active) {
+        }
+        __syncwarp();
+#pragma unroll
+        for (int ub = 0; ub < TU; ++ub) {  // G = Quu + Bp Bv
+          const int u0 = tile_off(ub, NU);
+          double cG[TU][2];
+#pragma unroll
+          for (int n = 0; n < TU; ++n) {
+            const int v0 = tile_off(n, NU);
+            cG[n][0] = __ldg(rec + L.k_Quu + (u0 + g) + (v0 + 2 * t) * NU);
+            cG[n][1] = __ldg(rec + L.k_Quu + (u0 + g) + (v0 + 2 * t + 1) * NU);
+          }
+          warp_mma_band<NV, TU, NU>(
+              cG, u0, [&](int u, int k) { return sBp[u * NV + k]; }, [&](int k, int v) { return sB[k + v * NV]; });
+#pragma unroll
+          for (int n = 0; n < TU; ++n) {
+            const int v0 = tile_off(n, NU);
+            sG[(u0 + g) + (v0 + 2 * t) * NU] = cG[n][0];
+            sG[(u0 + g) + (v0 + 2 * t + 1) * NU] = cG[n][1];
+            if (fct) {
+              fct[L.f_G + (u0 + g) + (v0 + 2 * t) * NU] = cG[n][0];
+              fct[L.f_G + (u0 + g) + (v0 + 2 * t + 1) * NU] = cG[n][1];
+            }
+          }
+        }
+        __syncwarp();
+        if (plain) {
+          if (!warp_cholesky<NU>(sG, NU, dinv)) bad |= 1;
+          __syncwarp();
+          // L^-1: lane c solves L x = e_c (forward substitution); rows above c are zero
+          if (lane < NU) {
+            const int c = lane;
+            double x[NU];
 #pragma unroll
             for (int a = 0; a < NU; ++a) {
-              double v = y[a];
+              double v = (a == c) ? 1.0 : 0.0;
 #pragma unroll
-              for (int k = 0; k < a; ++k) v = fma(-sG[a + k * NU], y[k], v);
-              y[a] = v * dinv[a];
-            }
-            if (c < NX) {
-#pragma unroll
-              for (int u = 0; u < NU; ++u) sY[u + c * NU] = y[u];
+              for (int k = 0; k < a; ++k) v = fma(-sG[a + k * NU], x[k], v);
+              x[a] = (a >= c) ? v * dinv[a] : 0.0;
             }
 #pragma unroll
-            for (int a = NU - 1; a >= 0; --a) {
-              double v = y[a];
-#pragma unroll
-              for (int k = a + 1; k < NU; ++k) v = fma(-sG[k + a * NU], y[k], v);
-              y[a] = v * dinv[a];
-            }
+            for (int a = 0; a < NU; ++a) sLi[a + c * NU] = x[a];
           }
-          if (c < NX) {
+        }
+      }
+      named_bar_sync(2, NTHR);  // z (and Pf) from the GEMM warps
+      if (!impact) {
+        // lu' = lu - Bv^T z_v      (== lu + BtP Fx - Bv^T s+_v, backward_..factorizer.cpp:43-44)
+        matvec_T(sB, NV, NV, NU, z + NV, lane, 32, [&](int u, double a) {
+          const double v = slu[u] - a;
+          lu2[u] = v;
+          if (fct) fct[L.f_lu + u] = v;
+        });
+        __syncwarp();
+        if (plain && lane < NU) {
+          double a = 0.0;
 #pragma unroll
-            for (int u = 0; u < NU; ++u) {
-              sKt[c + u * NX] = -y[u];
-              ric[L.r_K + c + u * NX] = -y[u];
-            }
-          } else if (c == NX) {
+          for (int v = 0; v < NU; ++v) a = fma(sLi[lane + v * NU], lu2[v], a);
+          ylu[lane] = a;
+        }
+      }
+    }
+    __syncthreads();  // ---- barrier 2: AtP/H/t1 (GEMM warps) and G/L^-1/y (factor warp) are complete
+
+    // staging buffer is dead on plain stages: prefetch the next stage now (overlaps the rest of the stage)
+    const bool early_prefetch = !extras;
+    if (early_prefetch && tid == 0 && i > 0) issue_stage_load(i - 1);
+
+    if (!impact) {
+      if (sto) {
+        // psi_u = BtP fx + hu + Bv^T Psi+_v = Bv^T (P+ fx)_v + hu + Bv^T Psi+_v ; phi_u = Bv^T Phi+_v   (:53-60)
+        // and their images under L^-1 (all small; the factor warp owns them)
+        if (!gemm_warp) {
+          matvec_T(sB, NV, NV, NU, Pf + NV, lane, 32, [&](int u, double a) { psiu[u] = a + shu[u]; });
+          matvec_T(sB, NV, NV, NU, Psin + NV, lane, 32, [&](int u, double a) { psiu[u] += a; });
+          if (sto_next) {
+            matvec_T(sB, NV, NV, NU, Phin + NV, lane, 32, [&](int u, double a) { phiu[u] = a; });
+          } else if (lane < NU) {
+            phiu[lane] = 0.0;
+          }
+          __syncwarp();
+          if (plain) {
+            if (lane < NU) {
+              double a = 0.0, bq = 0.0;
 #pragma unroll
-            for (int u = 0; u < NU; ++u) {
-              kv[u] = -y[u];
-              ric[L.r_k + u] = -y[u];
-            }
-          } else if (c == NX + 1) {
-            if (sto) {
-#pragma unroll
-              for (int u = 0; u < NU; ++u) {
-                Tv[u] = -y[u];
-                ric[L.r_T + u] = -y[u];
+              for (int v = 0; v < NU; ++v) {
+                a = fma(sLi[lane + v * NU], psiu[v], a);
+                bq = fma(sLi[lane + v * NU], phiu[v], bq);
               }
+              tps[lane] = a;
+              tph[lane] = bq;
             }
-          } else {
-            if (sto) {
+            __syncwarp();
+            if (lane < NU) {  // T = -L^-T (L^-1 psi_u), W = -L^-T (L^-1 phi_u)         riccati_factorizer.cpp:126-128
+              double a = 0.0, bq = 0.0;
 #pragma unroll
-              for (int u = 0; u < NU; ++u) {
-                Wv[u] = active ? -y[u] : 0.0;
-                ric[L.r_W + u] = active ? -y[u] : 0.0;
+              for (int v = 0; v < NU; ++v) {
+                a = fma(sLi[v + lane * NU], tps[v], a);
+                bq = fma(sLi[v + lane * NU], tph[v], bq);
               }
+              Tv[lane] = -a;
+              Wv[lane] = sto_next ? -bq : 0.0;
+              ric[L.r_T + lane] = -a;
+              ric[L.r_W + lane] = sto_next ? -bq : 0.0;
             }
           }
         }
         __syncthreads();
-        if (p.dbg == 6) return;
-        // ================= phase 5a: F -= Y^T Y  (tensor pipe), spill F to the scratch for symmetrisation
-        warp_mma_band<NU, TX, NX>(
-            cF, i0, [&](int ii, int k) { return -sY[k + ii * NU]; }, [&](int k, int j) { return sY[k + j * NU]; });
+      }
+      if (plain) {
+        // ================= phase C: Y = L^-1 H^T on the tensor pipe (GEMM warp w: column tile w, all row bands)
+        if (gemm_warp) {
+          const int j0 = tile_off(warp, NX);
+#pragma unroll
+          for (int ub = 0; ub < TU; ++ub) {
+            const int u0 = tile_off(ub, NU);
+            double acc[1][2] = {{0.0, 0.0}};
+            // one 8x8 tile: rows u0.., cols j0..  (fb's column argument is g; the tile origin j0 is added by hand)
+            warp_mma_band<NU, 1, 8>(
+                acc, u0, [&](int u, int k) { return sLi[u + k * NU]; },
+                [&](int k, int jj) { return sH[(j0 + jj) + k * NX]; });
+            sY[(u0 + g) + (j0 + 2 * t) * NU] = acc[0][0];
+            sY[(u0 + g) + (j0 + 2 * t + 1) * NU] = acc[0][1];
+          }
+        }
+        __syncthreads();  // ---- barrier 3: Y complete
+        // ================= phase D
+        if (gemm_warp) {
+          // F -= Y^T Y
+          warp_mma_band<NU, TX, NX>(
+              cF, i0, [&](int ii, int k) { return -sY[k + ii * NU]; }, [&](int k, int j) { return sY[k + j * NU]; });
+          // s = t1 + Y^T y            (== A^T z - lx - H k)
+          matvec_T(sY, NU, NU, NX, ylu, tid, NG, [&](int c, double a) {
+            const double v = t1[c] + a;
+            s_n[c] = v;
+            ric[L.r_s + c] = v;
+          });
+        } else {
+          // K = -L^-T Y  (off the critical path) ; k = -L^-T y
+#pragma unroll
+          for (int ub = 0; ub < TU; ++ub) {
+            const int u0 = tile_off(ub, NU);
+            double acc[TX][2];
+#pragma unroll
+            for (int n = 0; n < TX; ++n) acc[n][0] = acc[n][1] = 0.0;
+            warp_mma_band<NU, TX, NX>(
+                acc, u0, [&](int u, int k) { return -sLi[k + u * NU]; }, [&](int k, int j) { return sY[k + j * NU]; });
+#pragma unroll
+            for (int n = 0; n < TX; ++n) {
+              const int j0 = tile_off(n, NX);
+              *reinterpret_cast<double2*>(&ric[L.r_K + (j0 + 2 * t) + (u0 + g) * NX]) = make_double2(acc[n][0], acc[n][1]);
+            }
+          }
+          if (lane < NU) {
+            double a = 0.0;
+#pragma unroll
+            for (int v = 0; v < NU; ++v) a = fma(sLi[v + lane * NU], ylu[v], a);
+            kv[lane] = -a;
+            ric[L.r_k + lane] = -a;
+          }
+        }
       } else {
         // ================= Schur-complement path (switching constraint)      riccati_factorizer.cpp:58-89
         double* xs = sIn;  // scratch in the dead staging buffer
@@ -529,11 +593,9 @@ __global__ void __launch_bounds__(BwdCfg<NV, NU, NS>::NTHREADS, 4) riccati_backw
           Gc[e] = sG[e];
           Ginv[e] = ((e % NU) == (e / NU)) ? 1.0 : 0.0;
         }
-        for (int e = tid; e < ns * NU; e += NTHR) {  // DG^T <- D^T  (DG[r + u*ns] = D[r + u*ns])
-          DG[e] = sPhiu[e];
-        }
+        for (int e = tid; e < ns * NU; e += NTHR) DG[e] = sPhiu[e];  // DG^T <- D^T
         __syncthreads();
-        if (warp == 0) {
+        if (!gemm_warp) {
           if (!warp_cholesky<NU>(sG, NU, dinv)) bad |= 1;
         }
         __syncthreads();
@@ -551,7 +613,7 @@ __global__ void __launch_bounds__(BwdCfg<NV, NU, NS>::NTHREADS, 4) riccati_backw
         if (tid < ns) mvec[tid] = sp[tid];
         if (tid < ns) mt[tid] = sto ? sPhit[tid] : 0.0;
         __syncthreads();
-        if (warp == 0) {
+        if (!gemm_warp) {
           if (!warp_cholesky<NS>(Sm, ns, dinvS)) bad |= 2;
         }
         __syncthreads();
@@ -570,7 +632,7 @@ __global__ void __launch_bounds__(BwdCfg<NV, NU, NS>::NTHREADS, 4) riccati_backw
           Ginv[e] -= acc;
         }
         __syncthreads();
-        // K = -Ginv H^T - SDG^T C (:67-68);  M -= SDG H^T (:72)
+        // K = -Ginv H^T - SDG^T C (:67-68);  M -= SDG H^T (:72)       (AtP is dead: K^T lives in its buffer)
         for (int e = tid; e < NU * NX; e += NTHR) {
           const int j = e % NX, u = e / NX;
           double a = 0.0;
@@ -637,64 +699,88 @@ __global__ void __launch_bounds__(BwdCfg<NV, NU, NS>::NTHREADS, 4) riccati_backw
           sY[e] = a;
           DtM[e] = d2;
         }
+        // s = t1 - H k - C^T m           backward_..factorizer.cpp:87-90, riccati_factorizer.cpp:88
+        if (tid >= NG - NX && tid < NG) {
+          const int r = tid - (NG - NX);
+          double v = t1[r];
+          for (int u = 0; u < NU; ++u) v = fma(-sH[r + u * NX], kv[u], v);
+          for (int q = 0; q < ns; ++q) v = fma(-sPhix[q + r * ns], mvec[q], v);
+          s_n[r] = v;
+          ric[L.r_s + r] = v;
+        }
         __syncthreads();
-        // F -= K^T (G K)                                                                     backward_..factorizer.cpp:83
-        warp_mma_band<NU, TX, NX>(
-            cF, i0, [&](int ii, int k) { return -sKt[ii + k * NX]; }, [&](int k, int j) { return sY[k + j * NU]; });
-        if (fct) {  // the reference leaves Qxx = F - K^T G K here; spill it before the constraint correction
+        if (gemm_warp) {
+          // F -= K^T (G K)                                                                   backward_..factorizer.cpp:83
+          warp_mma_band<NU, TX, NX>(
+              cF, i0, [&](int ii, int k) { return -sKt[ii + k * NX]; }, [&](int k, int j) { return sY[k + j * NU]; });
+          if (fct) {  // the reference leaves Qxx = F - K^T G K here; spill it before the constraint correction
 #pragma unroll
-          for (int n = 0; n < TX; ++n) {
-            const int j0 = tile_off(n, NX);
-            fct[L.f_F + (i0 + g) + (j0 + 2 * t) * NX] = cF[n][0];
-            fct[L.f_F + (i0 + g) + (j0 + 2 * t + 1) * NX] = cF[n][1];
+            for (int n = 0; n < TX; ++n) {
+              const int j0 = tile_off(n, NX);
+              fct[L.f_F + (i0 + g) + (j0 + 2 * t) * NX] = cF[n][0];
+              fct[L.f_F + (i0 + g) + (j0 + 2 * t + 1) * NX] = cF[n][1];
+            }
+          }
+          // P = sym(F) - KtDtM - KtDtM^T = sym(F - 2 K^T DtM)                                 riccati_factorizer.cpp:85-87
+          warp_mma_band<NU, TX, NX>(
+              cF, i0, [&](int ii, int k) { return -2.0 * sKt[ii + k * NX]; }, [&](int k, int j) { return DtM[k + j * NU]; });
+        }
+        if (sto) {
+          // Psi = psi_x + K^T psi_u + M^T Phit ; Phi = phi_x + K^T phi_u   (K^T still valid in the AtP buffer)
+          if (!gemm_warp) {
+            for (int c = lane; c < NX; c += 32) {
+              double a = psix[c], bq = sto_next ? phix[c] : 0.0;
+              for (int u = 0; u < NU; ++u) {
+                a = fma(sKt[c + u * NX], psiu[u], a);
+                if (sto_next) bq = fma(sKt[c + u * NX], phiu[u], bq);
+              }
+              for (int q = 0; q < ns; ++q) a = fma(Mm[q + c * ns], sPhit[q], a);
+              Psi[c] = a;
+              Phi[c] = bq;
+            }
           }
         }
-        // P = sym(F) - KtDtM - KtDtM^T = sym(F - 2 K^T DtM)                                   riccati_factorizer.cpp:85-87
-        warp_mma_band<NU, TX, NX>(
-            cF, i0, [&](int ii, int k) { return -2.0 * sKt[ii + k * NX]; }, [&](int k, int j) { return DtM[k + j * NU]; });
+        __syncthreads();  // all reads of K^T (AtP buffer) are done before F is spilled into it
       }
+    }
+    if (impact && tid < NX) {
+      s_n[tid] = t1[tid];  // s = A^T z - lx
+      ric[L.r_s + tid] = t1[tid];
     }
 
-    if (p.dbg == 7) return;
-    // ================= phase 5b: spill F (row-major, ld LDF) ; s ; STO scalars
+    // ================= spill F (row-major, ld LDF)
+    if (gemm_warp) {
 #pragma unroll
-    for (int n = 0; n < TX; ++n) {
-      const int j0 = tile_off(n, NX);
-      sAtP[(i0 + g) * LDF + j0 + 2 * t] = cF[n][0];
-      sAtP[(i0 + g) * LDF + j0 + 2 * t + 1] = cF[n][1];
-    }
-    if (tid < NX) {
-      const int r = tid;
-      double v = t1[r];
-      if (!impact) {
-#pragma unroll
-        for (int u = 0; u < NU; ++u) v = fma(-sH[r + u * NX], kv[u], v);
-        if (ns > 0) {
-          for (int q = 0; q < ns; ++q) v = fma(-sPhix[q + r * ns], mvec[q], v);  // s -= C^T m    riccati_factorizer.cpp:88
-        }
+      for (int n = 0; n < TX; ++n) {
+        const int j0 = tile_off(n, NX);
+        sAtP[(i0 + g) * LDF + j0 + 2 * t] = cF[n][0];
+        sAtP[(i0 + g) * LDF + j0 + 2 * t + 1] = cF[n][1];
       }
-      s_n[r] = v;  // old s+ is dead (folded into z)
-      ric[L.r_s + r] = v;
+    }
+    __syncthreads();  // ---- barrier 4: F scratch, s, k complete
+
+    // ================= phase E: P = (F + F^T)/2 -> shared (next stage) and HBM ; STO vectors / scalars
+    for (int e = tid; e < NX * NX; e += NTHR) {
+      const int r = e % NX, c = e / NX;
+      const double f_rc = sAtP[r * LDF + c];
+      const double v = 0.5 * (f_rc + sAtP[c * LDF + r]);
+      sP[e] = v;
+      ric[L.r_P + e] = v;
+      if (fct && ns == 0) fct[L.f_F + e] = f_rc;
     }
     if (sto) {
       if (!impact) {
         // factorizeSTOFactorization: backward_riccati_recursion_factorizer.cpp:94-143 (+ riccati_factorizer.cpp:136-141)
-        if (tid >= 64 && tid < 64 + NX) {
-          const int c = tid - 64;
-          double a = psix[c], bq = sto_next ? phix[c] : 0.0;
-#pragma unroll
-          for (int u = 0; u < NU; ++u) {
-            a = fma(sKt[c + u * NX], psiu[u], a);
-            if (sto_next) bq = fma(sKt[c + u * NX], phiu[u], bq);
+        if (plain) {
+          // Psi = psi_x + K^T psi_u = psi_x - Y^T (L^-1 psi_u) ; Phi likewise
+          matvec_T(sY, NU, NU, NX, tps, tid, NTHR, [&](int c, double a) { Psi[c] = psix[c] - a; });
+          if (sto_next) {
+            matvec_T(sY, NU, NU, NX, tph, tid, NTHR, [&](int c, double a) { Phi[c] = phix[c] - a; });
+          } else if (tid < NX) {
+            Phi[tid] = 0.0;
           }
-          if (ns > 0) {
-            const double* Mm = sIn + C::x_M;
-            for (int q = 0; q < ns; ++q) a = fma(Mm[q + c * ns], sPhit[q], a);
-          }
-          Psi[c] = a;
-          Phi[c] = bq;
         }
-        if (tid == 128) {
+        if (tid == NTHR - 1) {
           double xi = dot_serial(sfx, Pf, NX) + sksc[0] + 2.0 * dot_serial(Psin, sfx, NX) + dot_serial(Tv, psiu, NU) + scn[0];
           double chi = 0.0, rho = 0.0, iota = 0.0;
           if (sto_next) {
@@ -712,26 +798,13 @@ __global__ void __launch_bounds__(BwdCfg<NV, NU, NS>::NTHREADS, 4) riccati_backw
           sc[0] = xi; sc[1] = chi; sc[2] = rho; sc[3] = eta; sc[4] = iota;
         }
       } else {
-        if (tid == 128) {
+        if (tid == NTHR - 1) {
           sc[0] = 0.0; sc[1] = 0.0; sc[2] = scn[2]; sc[3] = 0.0;
           sc[4] = scn[4] + dot_serial(Phin, Fxs, NX);
         }
         if (tid < NX) Psi[tid] = 0.0;
       }
-    }
-    __syncthreads();
-
-    if (p.dbg == 8) return;
-    // ================= phase 6: P = (F + F^T)/2 -> shared (next stage) and HBM ; roll the STO state
-    for (int e = tid; e < NX * NX; e += NTHR) {
-      const int r = e % NX, c = e / NX;
-      const double f_rc = sAtP[r * LDF + c];
-      const double v = 0.5 * (f_rc + sAtP[c * LDF + r]);
-      sP[e] = v;
-      ric[L.r_P + e] = v;
-      if (fct && ns == 0) fct[L.f_F + e] = f_rc;
-    }
-    if (sto) {
+      __syncthreads();
       if (tid < NX) {
         Psin[tid] = Psi[tid];
         Phin[tid] = Phi[tid];
@@ -758,9 +831,8 @@ __global__ void __launch_bounds__(BwdCfg<NV, NU, NS>::NTHREADS, 4) riccati_backw
       }
       if (tid < 8) scn[tid] = 0.0;
     }
-    __syncthreads();
+    __syncthreads();  // ---- barrier 5: P+ / s+ / STO state rolled
     if (!early_prefetch && tid == 0 && i > 0) issue_stage_load(i - 1);
-    if (p.dbg == 9) return;
   }
 
   // ---- final phase transition at stage 0                       riccati_recursion.cpp:75-79

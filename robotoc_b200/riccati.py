@@ -142,6 +142,13 @@ class RiccatiRecursion:
     def dev_ptr(self, which):
         return self._lib.rbt_dev_ptr(self._h, which)
 
+    def bind_buffer(self, which, dev_ptr):
+        """Use a caller-owned device buffer (e.g. a torch tensor's data_ptr()) for `which`; None restores the own one."""
+        _check(self._lib.rbt_bind_buffer(self._h, which, dev_ptr), self._err, "RiccatiRecursion")
+
+    def buf_doubles(self, which):
+        return int(self._lib.rbt_buf_doubles(self._h, which))
+
     def launch_count(self):
         return int(self._lib.rbt_launch_count(self._h))
 
