@@ -50,6 +50,9 @@ typedef struct rbt_stage_ctrl {
   int ns;              /* switching-constraint dimension (0 if !switching_constraint) */
   int nf;              /* active contact dimension dimf of this stage's phase (impact dimf on Impact) */
   int ngrids_in_phase; /* GridInfo::num_grids_in_phase */
+  int contact_mask;    /* bit c set: point contact c is active in this stage's phase (ContactStatus::isContactActive);
+                          on an Impact stage: the contacts of the ImpactStatus */
+  int reserved_;
   double dt;           /* GridInfo::dt */
 } rbt_stage_ctrl;
 

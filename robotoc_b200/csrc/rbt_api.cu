@@ -46,6 +46,10 @@ struct rbt_handle {
   double *d_kkt = nullptr, *d_ric = nullptr, *d_fact = nullptr, *d_dir = nullptr, *d_dx0 = nullptr;
   double* own[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // the handle's own allocations (freed in destroy)
   int* d_info = nullptr;
+  int* d_arrivals = nullptr;  // per-SM CTA arrival counters (CTA de-phasing in the backward kernel)
+  int stagger_ns = 0;
+  long long* d_timeline = nullptr;  // bring-up instrumentation (RBT_TIMELINE_CTA)
+  int timeline_cta = -1;
   long long launches = 0;
   std::string err;
 };
@@ -124,6 +128,13 @@ int rbt_create(const rbt_dims* dims, int n_grid_max, int batch, int device, rbt_
   RBT_CUDA(h, cudaMalloc(&h->d_dir, per * h->L.d_stride * 8));
   RBT_CUDA(h, cudaMalloc(&h->d_dx0, size_t(batch) * h->L.nx * 8));
   RBT_CUDA(h, cudaMalloc(&h->d_info, size_t(batch) * sizeof(int)));
+  RBT_CUDA(h, cudaMalloc(&h->d_arrivals, 1024 * sizeof(int)));
+  h->stagger_ns = getenv("RBT_STAGGER_NS") ? atoi(getenv("RBT_STAGGER_NS")) : 0;
+  if (getenv("RBT_TIMELINE_CTA")) {
+    h->timeline_cta = atoi(getenv("RBT_TIMELINE_CTA"));
+    RBT_CUDA(h, cudaMalloc(&h->d_timeline, size_t(n_grid_max) * 32 * sizeof(long long)));
+    RBT_CUDA(h, cudaMemset(h->d_timeline, 0, size_t(n_grid_max) * 32 * sizeof(long long)));
+  }
   RBT_CUDA(h, cudaMemset(h->d_ric, 0, per * h->L.r_stride * 8));
   RBT_CUDA(h, cudaMemset(h->d_fact, 0, per * h->L.f_stride * 8));
   RBT_CUDA(h, cudaMemset(h->d_dir, 0, per * h->L.d_stride * 8));
@@ -142,6 +153,7 @@ int rbt_destroy(rbt_handle* h) {
   cudaFree(h->d_ctrl);
   for (int q = 0; q < 5; ++q) cudaFree(h->own[q]);
   cudaFree(h->d_info);
+  cudaFree(h->d_arrivals);
   delete h;
   return RBT_OK;
 }
@@ -317,7 +329,12 @@ static int launch_backward(rbt_handle* h, int write_fact, cudaStream_t st) {
   p.ric = h->d_ric;
   p.fact = write_fact ? h->d_fact : nullptr;
   p.info = h->d_info;
+  p.sm_arrivals = h->d_arrivals;
+  p.stagger_ns = h->stagger_ns;
+  p.timeline = h->d_timeline;
+  p.timeline_cta = h->timeline_cta;
   RBT_CUDA(h, cudaMemsetAsync(h->d_info, 0, size_t(h->batch) * sizeof(int), st));
+  if (h->stagger_ns > 0) RBT_CUDA(h, cudaMemsetAsync(h->d_arrivals, 0, 1024 * sizeof(int), st));
   kern<<<h->batch, C::NTHREADS, C::SMEM_BYTES, st>>>(p);
   RBT_CUDA(h, cudaGetLastError());
   h->launches += 1;
@@ -397,6 +414,12 @@ int rbt_sync(rbt_handle* h, void* stream) {
 }
 
 const char* rbt_last_error(rbt_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+// bring-up only (not part of the public header): copy the timeline stamps of the last backward launch
+extern "C" int rbt_debug_timeline(rbt_handle* h, long long* host, int n) {
+  if (!h || !h->d_timeline) return RBT_ERR_STATE;
+  return cudaMemcpy(host, h->d_timeline, size_t(n) * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? RBT_OK : RBT_ERR_CUDA;
+}
 long long rbt_launch_count(rbt_handle* h) { return h ? h->launches : 0; }
 
 // ---------------------------------------------------------------------------------------------------------------

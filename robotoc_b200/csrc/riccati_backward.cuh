@@ -38,6 +38,10 @@ struct BwdParams {
   double* ric;        // [batch][n_grid][r_stride]
   double* fact;       // [batch][n_grid][f_stride] or nullptr
   int* info;          // [batch]
+  int* sm_arrivals;   // [>= #SMs], zeroed before the launch (CTA de-phasing)
+  int stagger_ns;     // delay unit between co-resident CTAs (0 = off)
+  long long* timeline;  // bring-up: [n_grid][2 roles][16] clock64 stamps of CTA `timeline_cta` (nullptr = off)
+  int timeline_cta;
 };
 
 template <int NV, int NU, int NS>
@@ -212,6 +216,11 @@ __global__ void __launch_bounds__(BwdCfg<NV, NU, NS>::NTHREADS, RBT_BWD_MIN_CTAS
   double* sc = vec + C::v_sc;
 
   int bad = 0;  // Cholesky failure flags (thread-local, OR-reduced at the end)
+  const bool tl_on = p.timeline != nullptr && b == p.timeline_cta && lane == 0 && (warp == 0 || !gemm_warp);
+#define RBT_TL(stage, slot)                                                                  \
+  do {                                                                                       \
+    if (tl_on) p.timeline[(size_t(stage) * 2 + (gemm_warp ? 0 : 1)) * 16 + (slot)] = clock64(); \
+  } while (0)
 
   auto issue_stage_load = [&](int st) {
     // one elected thread: stage st's [Fxx|Fvu|Fx|lx|lu] (+ extras when flagged)
@@ -230,6 +239,14 @@ __global__ void __launch_bounds__(BwdCfg<NV, NU, NS>::NTHREADS, RBT_BWD_MIN_CTAS
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
     fence_mbar_init();
+    // De-phase the CTAs that share an SM: they execute identical stage programs, so without an offset they all hit
+    // the tensor pipe together and then all sit in their latency-bound tails together.
+    if (p.stagger_ns > 0) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      const int rank = atomicAdd(&p.sm_arrivals[smid], 1) & 3;
+      for (int q = 0; q < rank; ++q) __nanosleep(p.stagger_ns);
+    }
   }
   __syncthreads();
   if (tid == 0 && N > 0) issue_stage_load(N - 1);
@@ -322,25 +339,30 @@ __global__ void __launch_bounds__(BwdCfg<NV, NU, NS>::NTHREADS, RBT_BWD_MIN_CTAS
     const int i0 = tile_off(gemm_warp ? warp : 0, NX);  // this GEMM warp's row band
     double cF[TX][2];                                   // F fragments (GEMM warps only)
 
-    if (gemm_warp) {
-      // Qxx -> accumulator fragments of F (issued before the wait, consumed after GEMM1)
-#pragma unroll
-      for (int n = 0; n < TX; ++n) {
-        const int j0 = tile_off(n, NX);
-        cF[n][0] = __ldg(rec + L.k_Qxx + (i0 + g) + (j0 + 2 * t) * NX);
-        cF[n][1] = __ldg(rec + L.k_Qxx + (i0 + g) + (j0 + 2 * t + 1) * NX);
-      }
-    }
     // ---- wait for this stage's blocks
+    RBT_TL(i, 0);
     mbar_wait(&bars[0], par0);
     par0 ^= 1;
     if (extras) {
       mbar_wait(&bars[1], par1);
       par1 ^= 1;
     }
+    RBT_TL(i, 1);
 
     if (gemm_warp) {
-      // ================= phase A (GEMM warps): AtP = A^T P+ ; z = s+ - P+ Fx
+      // ================= phase A (GEMM warps): Bp = Bv^T P+_vv (for the factor warp) ; AtP = A^T P+ ; z = s+ - P+ Fx
+      if (!impact) {
+        // TU*TV tiles of the NU x NV product, dealt round-robin to the GEMM warps (K = NV)
+        for (int tile = warp; tile < TU * TV; tile += TX) {
+          const int u0 = tile_off(tile / TV, NU), j0 = tile_off(tile % TV, NV);
+          double acc[1][2] = {{0.0, 0.0}};
+          warp_mma_band<NV, 1, 8>(
+              acc, u0, [&](int u, int k) { return sB[k + u * NV]; },
+              [&](int k, int jj) { return sP[(NV + k) + (NV + j0 + jj) * NX]; });
+          *reinterpret_cast<double2*>(&sBp[(u0 + g) * NV + j0 + 2 * t]) = make_double2(acc[0][0], acc[0][1]);
+        }
+        named_bar_arrive(3, NTHR);  // Bp ready (non-blocking for the GEMM warps)
+      }
       {
         double acc[TX][2];
 #pragma unroll
@@ -353,17 +375,27 @@ __global__ void __launch_bounds__(BwdCfg<NV, NU, NS>::NTHREADS, RBT_BWD_MIN_CTAS
           *reinterpret_cast<double2*>(&sAtP[(i0 + g) * NX + j0 + 2 * t]) = make_double2(acc[n][0], acc[n][1]);
         }
       }
+      RBT_TL(i, 2);
+      // Qxx -> accumulator fragments of F: issued here so the loads fly during z / the barrier, but are not live
+      // (and spilled) across GEMM1
+#pragma unroll
+      for (int n = 0; n < TX; ++n) {
+        const int j0 = tile_off(n, NX);
+        cF[n][0] = __ldg(rec + L.k_Qxx + (i0 + g) + (j0 + 2 * t) * NX);
+        cF[n][1] = __ldg(rec + L.k_Qxx + (i0 + g) + (j0 + 2 * t + 1) * NX);
+      }
       matvec_N4(sP, NX, NX, NX, sFx, tid, NG, [&](int r, double a) { z[r] = s_n[r] - a; });
       if (sto) {
         if (!impact) matvec_N4(sP, NX, NX, NX, sfx, tid, NG, [&](int r, double a) { Pf[r] = a; });
         if (tid < NX) Fxs[tid] = sFx[tid];
       }
       named_bar_sync(1, NG);      // AtP and z complete among the GEMM warps
-      named_bar_arrive(2, NTHR);  // ... and visible to the factor warp (non-blocking)
+      RBT_TL(i, 3);
 
       // ================= phase B (GEMM warps): F = Qxx + AtP A ; H = Qxu + AtP[:,nv:] Bv ; t1 = A^T z - lx
       warp_mma_band<NX, TX, NX>(
           cF, i0, [&](int ii, int k) { return sAtP[ii * NX + k]; }, [&](int k, int j) { return sA[k + j * NX]; });
+      RBT_TL(i, 4);
       if (!impact) {
         double cH[TU][2];
 #pragma unroll
@@ -385,7 +417,17 @@ __global__ void __launch_bounds__(BwdCfg<NV, NU, NS>::NTHREADS, RBT_BWD_MIN_CTAS
           }
         }
       }
+      RBT_TL(i, 5);
+      if (!impact) {
+        // lu' = lu - Bv^T z_v      (== lu + BtP Fx - Bv^T s+_v, backward_..factorizer.cpp:43-44)
+        matvec_T(sB, NV, NV, NU, z + NV, tid, NG, [&](int u, double a) {
+          const double v = slu[u] - a;
+          lu2[u] = v;
+          if (fct) fct[L.f_lu + u] = v;
+        });
+      }
       matvec_T(sA, NX, NX, NX, z, tid, NG, [&](int c, double a) { t1[c] = a - slx[c]; });
+      RBT_TL(i, 6);
       if (sto) {
         if (!impact) {
           // factorizeHamiltonian (x part): backward_riccati_recursion_factorizer.cpp:48-66; the same lane owns psix[c]
@@ -404,22 +446,8 @@ __global__ void __launch_bounds__(BwdCfg<NV, NU, NS>::NTHREADS, RBT_BWD_MIN_CTAS
     } else {
       // ================= factor warp: G = Quu + (Bv^T P+_vv) Bv, L L^T = G, L^-1, lu' = lu - Bv^T z_v, y = L^-1 lu'
       if (!impact) {
-#pragma unroll
-        for (int ub = 0; ub < TU; ++ub) {  // Bp = Bv^T P+[nv:, nv:]   (NU x NV, K = NV)
-          const int u0 = tile_off(ub, NU);
-          double acc[TV][2];
-#pragma unroll
-          for (int n = 0; n < TV; ++n) acc[n][0] = acc[n][1] = 0.0;
-          warp_mma_band<NV, TV, NV>(
-              acc, u0, [&](int u, int k) { return sB[k + u * NV]; },
-              [&](int k, int j) { return sP[(NV + k) + (NV + j) * NX]; });
-#pragma unroll
-          for (int n = 0; n < TV; ++n) {
-            const int j0 = tile_off(n, NV);
-            *reinterpret_cast<double2*>(&sBp[(u0 + g) * NV + j0 + 2 * t]) = make_double2(acc[n][0], acc[n][1]);
-          }
-        }
-        __syncwarp();
+        named_bar_sync(3, NTHR);  // Bp = Bv^T P+[nv:, nv:] from the GEMM warps
+        RBT_TL(i, 2);
 #pragma unroll
         for (int ub = 0; ub < TU; ++ub) {  // G = Quu + Bp Bv
           const int u0 = tile_off(ub, NU);
@@ -444,43 +472,17 @@ __global__ void __launch_bounds__(BwdCfg<NV, NU, NS>::NTHREADS, RBT_BWD_MIN_CTAS
           }
         }
         __syncwarp();
+        RBT_TL(i, 3);
         if (plain) {
           if (!warp_cholesky<NU>(sG, NU, dinv)) bad |= 1;
           __syncwarp();
-          // L^-1: lane c solves L x = e_c (forward substitution); rows above c are zero
-          if (lane < NU) {
-            const int c = lane;
-            double x[NU];
-#pragma unroll
-            for (int a = 0; a < NU; ++a) {
-              double v = (a == c) ? 1.0 : 0.0;
-#pragma unroll
-              for (int k = 0; k < a; ++k) v = fma(-sG[a + k * NU], x[k], v);
-              x[a] = (a >= c) ? v * dinv[a] : 0.0;
-            }
-#pragma unroll
-            for (int a = 0; a < NU; ++a) sLi[a + c * NU] = x[a];
-          }
         }
-      }
-      named_bar_sync(2, NTHR);  // z (and Pf) from the GEMM warps
-      if (!impact) {
-        // lu' = lu - Bv^T z_v      (== lu + BtP Fx - Bv^T s+_v, backward_..factorizer.cpp:43-44)
-        matvec_T(sB, NV, NV, NU, z + NV, lane, 32, [&](int u, double a) {
-          const double v = slu[u] - a;
-          lu2[u] = v;
-          if (fct) fct[L.f_lu + u] = v;
-        });
-        __syncwarp();
-        if (plain && lane < NU) {
-          double a = 0.0;
-#pragma unroll
-          for (int v = 0; v < NU; ++v) a = fma(sLi[lane + v * NU], lu2[v], a);
-          ylu[lane] = a;
-        }
+        RBT_TL(i, 4);
       }
     }
-    __syncthreads();  // ---- barrier 2: AtP/H/t1 (GEMM warps) and G/L^-1/y (factor warp) are complete
+    RBT_TL(i, 7);
+    __syncthreads();  // ---- barrier 2: AtP/H/t1 (GEMM warps) and G = L L^T, lu' (factor warp) are complete
+    RBT_TL(i, 8);
 
     // staging buffer is dead on plain stages: prefetch the next stage now (overlaps the rest of the stage)
     const bool early_prefetch = !extras;
@@ -498,52 +500,51 @@ __global__ void __launch_bounds__(BwdCfg<NV, NU, NS>::NTHREADS, RBT_BWD_MIN_CTAS
           } else if (lane < NU) {
             phiu[lane] = 0.0;
           }
-          __syncwarp();
-          if (plain) {
-            if (lane < NU) {
-              double a = 0.0, bq = 0.0;
-#pragma unroll
-              for (int v = 0; v < NU; ++v) {
-                a = fma(sLi[lane + v * NU], psiu[v], a);
-                bq = fma(sLi[lane + v * NU], phiu[v], bq);
-              }
-              tps[lane] = a;
-              tph[lane] = bq;
-            }
-            __syncwarp();
-            if (lane < NU) {  // T = -L^-T (L^-1 psi_u), W = -L^-T (L^-1 phi_u)         riccati_factorizer.cpp:126-128
-              double a = 0.0, bq = 0.0;
-#pragma unroll
-              for (int v = 0; v < NU; ++v) {
-                a = fma(sLi[v + lane * NU], tps[v], a);
-                bq = fma(sLi[v + lane * NU], tph[v], bq);
-              }
-              Tv[lane] = -a;
-              Wv[lane] = sto_next ? -bq : 0.0;
-              ric[L.r_T + lane] = -a;
-              ric[L.r_W + lane] = sto_next ? -bq : 0.0;
-            }
-          }
         }
         __syncthreads();
       }
       if (plain) {
-        // ================= phase C: Y = L^-1 H^T on the tensor pipe (GEMM warp w: column tile w, all row bands)
+        // ================= phase C: Y = L^-1 [H^T | lu'] by forward substitution, one column per lane spread over the GEMM
+        // warps (column-oriented: 12 dependent steps); the factor warp inverts L meanwhile (needed only for K, T, W).
         if (gemm_warp) {
-          const int j0 = tile_off(warp, NX);
+          constexpr int CPW = (NX + 1 + TX - 1) / TX;  // columns per warp
+          const int c = warp * CPW + lane;
+          if (lane < CPW && c <= NX) {
+            double y[NU];
 #pragma unroll
-          for (int ub = 0; ub < TU; ++ub) {
-            const int u0 = tile_off(ub, NU);
-            double acc[1][2] = {{0.0, 0.0}};
-            // one 8x8 tile: rows u0.., cols j0..  (fb's column argument is g; the tile origin j0 is added by hand)
-            warp_mma_band<NU, 1, 8>(
-                acc, u0, [&](int u, int k) { return sLi[u + k * NU]; },
-                [&](int k, int jj) { return sH[(j0 + jj) + k * NX]; });
-            sY[(u0 + g) + (j0 + 2 * t) * NU] = acc[0][0];
-            sY[(u0 + g) + (j0 + 2 * t + 1) * NU] = acc[0][1];
+            for (int u = 0; u < NU; ++u) y[u] = (c < NX) ? sH[c + u * NX] : lu2[u];
+#pragma unroll
+            for (int k = 0; k < NU; ++k) {
+              y[k] *= dinv[k];
+#pragma unroll
+              for (int a = k + 1; a < NU; ++a) y[a] = fma(-sG[a + k * NU], y[k], y[a]);
+            }
+            if (c < NX) {
+#pragma unroll
+              for (int u = 0; u < NU; ++u) sY[u + c * NU] = y[u];
+            } else {
+#pragma unroll
+              for (int u = 0; u < NU; ++u) ylu[u] = y[u];
+            }
           }
+        } else if (lane < NU) {
+          // L^-1: lane c solves L x = e_c; rows above c are zero
+          const int c = lane;
+          double x[NU];
+#pragma unroll
+          for (int a = 0; a < NU; ++a) x[a] = (a == c) ? 1.0 : 0.0;
+#pragma unroll
+          for (int k = 0; k < NU; ++k) {
+            x[k] *= dinv[k];
+#pragma unroll
+            for (int a = k + 1; a < NU; ++a) x[a] = fma(-sG[a + k * NU], x[k], x[a]);
+          }
+#pragma unroll
+          for (int a = 0; a < NU; ++a) sLi[a + c * NU] = x[a];
         }
+        RBT_TL(i, 9);
         __syncthreads();  // ---- barrier 3: Y complete
+        RBT_TL(i, 10);
         // ================= phase D
         if (gemm_warp) {
           // F -= Y^T Y
@@ -577,6 +578,32 @@ __global__ void __launch_bounds__(BwdCfg<NV, NU, NS>::NTHREADS, RBT_BWD_MIN_CTAS
             for (int v = 0; v < NU; ++v) a = fma(sLi[v + lane * NU], ylu[v], a);
             kv[lane] = -a;
             ric[L.r_k + lane] = -a;
+          }
+          if (sto) {  // images of psi_u / phi_u under L^-1, then T = -L^-T (L^-1 psi_u), W likewise   riccati_factorizer.cpp:126-128
+            __syncwarp();
+            if (lane < NU) {
+              double a = 0.0, bq = 0.0;
+#pragma unroll
+              for (int v = 0; v < NU; ++v) {
+                a = fma(sLi[lane + v * NU], psiu[v], a);
+                bq = fma(sLi[lane + v * NU], phiu[v], bq);
+              }
+              tps[lane] = a;
+              tph[lane] = bq;
+            }
+            __syncwarp();
+            if (lane < NU) {
+              double a = 0.0, bq = 0.0;
+#pragma unroll
+              for (int v = 0; v < NU; ++v) {
+                a = fma(sLi[v + lane * NU], tps[v], a);
+                bq = fma(sLi[v + lane * NU], tph[v], bq);
+              }
+              Tv[lane] = -a;
+              Wv[lane] = sto_next ? -bq : 0.0;
+              ric[L.r_T + lane] = -a;
+              ric[L.r_W + lane] = sto_next ? -bq : 0.0;
+            }
           }
         }
       } else {
@@ -757,7 +784,9 @@ __global__ void __launch_bounds__(BwdCfg<NV, NU, NS>::NTHREADS, RBT_BWD_MIN_CTAS
         sAtP[(i0 + g) * LDF + j0 + 2 * t + 1] = cF[n][1];
       }
     }
+    RBT_TL(i, 11);
     __syncthreads();  // ---- barrier 4: F scratch, s, k complete
+    RBT_TL(i, 12);
 
     // ================= phase E: P = (F + F^T)/2 -> shared (next stage) and HBM ; STO vectors / scalars
     for (int e = tid; e < NX * NX; e += NTHR) {
@@ -831,7 +860,9 @@ __global__ void __launch_bounds__(BwdCfg<NV, NU, NS>::NTHREADS, RBT_BWD_MIN_CTAS
       }
       if (tid < 8) scn[tid] = 0.0;
     }
+    RBT_TL(i, 13);
     __syncthreads();  // ---- barrier 5: P+ / s+ / STO state rolled
+    RBT_TL(i, 14);
     if (!early_prefetch && tid == 0 && i > 0) issue_stage_load(i - 1);
   }
 

@@ -45,17 +45,22 @@ class ContactEvents:
     sto_lift: List[bool] = field(default_factory=list)
     phase_dimf: List[int] = field(default_factory=lambda: [0])   # dimf of contactStatus(phase)
     impact_dimf: List[int] = field(default_factory=list)         # dimf of impactStatus(impact_index)
+    phase_mask: List[int] = field(default_factory=lambda: [0])   # active point contacts of contactStatus(phase), bit per contact
+    impact_mask: List[int] = field(default_factory=list)         # contacts of impactStatus(impact_index)
 
-    def push_back(self, is_impact: bool, time: float, post_dimf: int, impact_dimf: int = 0, sto: bool = False):
+    def push_back(self, is_impact: bool, time: float, post_dimf: int, impact_dimf: int = 0, sto: bool = False,
+                  post_mask: int = None, impact_mask: int = 0):
         """ContactSequence::push_back (contact_sequence.cpp:55-95): an event is an Impact iff new contacts close."""
         if is_impact:
             self.impact_times.append(time)
             self.sto_impact.append(sto)
             self.impact_dimf.append(impact_dimf)
+            self.impact_mask.append(impact_mask if impact_mask else (1 << (impact_dimf // 3)) - 1)
         else:
             self.lift_times.append(time)
             self.sto_lift.append(sto)
         self.phase_dimf.append(post_dimf)
+        self.phase_mask.append(post_mask if post_mask is not None else (1 << (post_dimf // 3)) - 1)
 
 
 class TimeDiscretization:
@@ -215,8 +220,10 @@ def stage_ctrl_array(td: TimeDiscretization, ev: ContactEvents):
         c.ns = ev.impact_dimf[gi.impact_index + 1] if gi.switching_constraint else 0
         if gi.type == IMPACT:
             c.nf = ev.impact_dimf[gi.impact_index]
+            c.contact_mask = ev.impact_mask[gi.impact_index]
         else:
             c.nf = ev.phase_dimf[gi.phase] if gi.phase < len(ev.phase_dimf) else 0
+            c.contact_mask = ev.phase_mask[gi.phase] if gi.phase < len(ev.phase_mask) else 0
         c.ngrids_in_phase = gi.num_grids_in_phase
         c.dt = gi.dt
     return arr
@@ -229,6 +236,7 @@ def plain_schedule(N: int, dt: float, nf: int = 0):
         arr[i].type = INTERMEDIATE if i < N else TERMINAL
         arr[i].dt = dt if i < N else 0.0
         arr[i].nf = nf
+        arr[i].contact_mask = (1 << (nf // 3)) - 1
         arr[i].ngrids_in_phase = N if i < N else 0
     return arr
 
@@ -236,19 +244,20 @@ def plain_schedule(N: int, dt: float, nf: int = 0):
 def anymal_trot_events() -> ContactEvents:
     """Contact schedule of /root/reference/examples/anymal/trot.cpp:41-47,172-190 (cycle=1):
     stand(12) -lift@0.04-> LF+RH(6) -impact@0.54-> stand -lift@0.58-> LH+RF(6) -impact@1.08-> stand; T=1.12."""
-    ev = ContactEvents(phase_dimf=[12])
+    # contact order LF, LH, RF, RH (trot.cpp:34-37)
+    ev = ContactEvents(phase_dimf=[12], phase_mask=[0b1111])
     t0, swing, ds = 0.04, 0.5, 0.04
-    ev.push_back(False, t0, 6)
-    ev.push_back(True, t0 + swing, 12, impact_dimf=6)
-    ev.push_back(False, t0 + swing + ds, 6)
-    ev.push_back(True, t0 + 2 * swing + ds, 12, impact_dimf=6)
+    ev.push_back(False, t0, 6, post_mask=0b1001)                                       # LH, RF swing
+    ev.push_back(True, t0 + swing, 12, impact_dimf=6, post_mask=0b1111, impact_mask=0b0110)
+    ev.push_back(False, t0 + swing + ds, 6, post_mask=0b0110)                          # LF, RH swing
+    ev.push_back(True, t0 + 2 * swing + ds, 12, impact_dimf=6, post_mask=0b1111, impact_mask=0b1001)
     return ev
 
 
 def anymal_jump_sto_events() -> ContactEvents:
     """Contact schedule of /root/reference/examples/anymal/jump_sto.cpp:42-48,131-140:
     stand(12) -lift@0.4 (sto)-> flying(0) -impact@0.9 (sto)-> stand; T=1.7."""
-    ev = ContactEvents(phase_dimf=[12])
-    ev.push_back(False, 0.70 - 0.3, 0, sto=True)
-    ev.push_back(True, 0.70 + 0.30 - 0.1, 12, impact_dimf=12, sto=True)
+    ev = ContactEvents(phase_dimf=[12], phase_mask=[0b1111])
+    ev.push_back(False, 0.70 - 0.3, 0, sto=True, post_mask=0)
+    ev.push_back(True, 0.70 + 0.30 - 0.1, 12, impact_dimf=12, sto=True, post_mask=0b1111, impact_mask=0b1111)
     return ev

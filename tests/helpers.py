@@ -9,9 +9,9 @@ from robotoc_b200.synth import make_kkt, mat
 
 def small_event_schedule(sto=False):
     """ANYmal, T=0.4, N=8: lift at 0.07, impact (dimf 6) at 0.23 -> Lift, Impact, one switching-constraint stage."""
-    ev = ContactEvents(phase_dimf=[12])
-    ev.push_back(False, 0.07, 6, sto=sto)
-    ev.push_back(True, 0.23, 12, impact_dimf=6, sto=sto)
+    ev = ContactEvents(phase_dimf=[12], phase_mask=[0b1111])
+    ev.push_back(False, 0.07, 6, sto=sto, post_mask=0b1001)
+    ev.push_back(True, 0.23, 12, impact_dimf=6, sto=sto, post_mask=0b1111, impact_mask=0b0110)
     td = TimeDiscretization(0.4, 8).discretize(ev, 0.0, sto=sto)
     return td, ev, stage_ctrl_array(td, ev)
 

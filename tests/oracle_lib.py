@@ -20,8 +20,7 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB):
-        build()
+    build()  # make is a no-op when up to date; a stale oracle after a header change would mis-read the control table
     from robotoc_b200._lib import rbt_dims, rbt_stage_ctrl
     L = ctypes.CDLL(LIB)
     c_int, c_dbl, c_vp = ctypes.c_int, ctypes.c_double, ctypes.c_void_p

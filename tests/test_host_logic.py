@@ -1,0 +1,112 @@
+"""CPU-only tests: C-ABI surface, layouts, schedule producer, sharding (no compute calls without a GPU)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle_lib
+from helpers import jump_sto_schedule, small_event_schedule, trot_schedule
+from robotoc_b200 import ANYMAL, Layout, ULayout, _lib
+from robotoc_b200.schedule import IMPACT, INTERMEDIATE, LIFT, TERMINAL
+from robotoc_b200.shard import shard_range
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "robotoc_b200.h")).read()
+    declared = set(re.findall(r"\b(rbt_[a-z_0-9]+)\s*\(", hdr))
+    declared -= {"rbt_make_layout", "rbt_make_ulayout"}
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    L = _lib.lib()
+    for name in declared:
+        assert hasattr(L, name), name
+    assert b"sm_100a" in L.rbt_version()
+
+
+def test_no_cpu_fallback_without_device():
+    """On a box without a GPU the compute entry points must fail loudly, never fall back."""
+    L = _lib.lib()
+    sm, nsm = ctypes.c_int(), ctypes.c_int()
+    if L.rbt_device_info(0, ctypes.byref(sm), ctypes.byref(nsm), None, 0) == 0:
+        pytest.skip("a CUDA device is present")
+    from robotoc_b200 import RiccatiRecursion
+    with pytest.raises(RuntimeError):
+        RiccatiRecursion(ANYMAL, 10, 2)
+
+
+def test_unsupported_dims_are_argument_errors():
+    L = _lib.lib()
+    h = ctypes.c_void_p()
+    d = _lib.rbt_dims(5, 3, 3, 0)
+    assert L.rbt_create(ctypes.byref(d), 10, 2, 0, ctypes.byref(h)) == 1  # RBT_ERR_ARG before touching CUDA
+    assert L.rbt_unconstr_create(0, 10, 0.1, 1, 0, ctypes.byref(h)) == 1
+    assert L.rbt_unconstr_create(7, 10, -0.1, 1, 0, ctypes.byref(h)) == 1
+
+
+def test_layouts_match_between_product_and_oracle():
+    lib = oracle_lib.load()
+    La = Layout(ANYMAL)
+    Lb = Layout(ANYMAL, getter=lib.orc_layout_get)
+    for k, v in vars(La).items():
+        if isinstance(v, int):
+            assert getattr(Lb, k) == v, k
+    Ua, Ub = ULayout(7), ULayout(7, getter=lib.orc_ulayout_get)
+    for k, v in vars(Ua).items():
+        if isinstance(v, int):
+            assert getattr(Ub, k) == v, k
+    # SURVEY.md 8(d) per-stage figures
+    nx, nu, nv = 36, 12, 18
+    assert La.k_core_size == nx * nx + nv * nu + nx * nx + nx * nu + nu * nu + nx + nx + nu == 3468
+    assert La.r_core_size == nx * nx + nx + nu * nx + nu == 1776
+    assert La.k_stride % 16 == 0 and La.r_stride % 16 == 0 and La.d_stride % 16 == 0
+    for f in ("k_Fxx", "k_Fvu", "k_Qxx", "k_Phix", "k_fx", "r_P", "r_K", "r_M", "r_Psi", "r_dtsdx", "d_dx", "d_du"):
+        assert getattr(La, f) % 2 == 0, f  # 16-byte granule of cp.async.bulk
+
+
+def test_trot_schedule_config3():
+    """examples/anymal/trot.cpp:41-47,172-190 with N=40: 47 grid points, 2 Lift, 2 Impact, 2 switching stages (ns=6)."""
+    td, ev, ctrl = trot_schedule(40)
+    types = [c.type for c in ctrl]
+    assert len(ctrl) == 47 and types[-1] == TERMINAL
+    assert types.count(LIFT) == 2 and types.count(IMPACT) == 2
+    sw = [i for i, c in enumerate(ctrl) if c.ns > 0]
+    assert len(sw) == 2 and all(ctrl[i].ns == 6 and ctrl[i + 2].type == IMPACT for i in sw)
+    assert all(c.dt == 0.0 for c in ctrl if c.type in (IMPACT, TERMINAL))
+    assert abs(sum(c.dt for c in ctrl) - 1.12) < 1e-12
+    assert not any(c.sto or c.sto_next for c in ctrl)
+    # contact dimension per phase: 12 -> 6 -> 12 -> 6 -> 12
+    assert [ctrl[0].nf, ctrl[3].nf, ctrl[23].nf, ctrl[30].nf, ctrl[45].nf] == [12, 6, 12, 6, 12]
+
+
+def test_jump_sto_schedule_config4():
+    """examples/anymal/jump_sto.cpp:42-48,131-140 with N=80: 84 grid points, all three phases STO-enabled."""
+    td, ev, ctrl = jump_sto_schedule(80)
+    assert len(ctrl) == 84
+    types = [c.type for c in ctrl]
+    assert types.count(LIFT) == 1 and types.count(IMPACT) == 1
+    imp = types.index(IMPACT)
+    assert ctrl[imp - 2].ns == 12 and ctrl[imp].sto and not ctrl[imp].sto_next
+    assert all(c.sto for c in ctrl[:-1])
+    assert ctrl[0].sto_next and ctrl[types.index(LIFT)].sto_next
+    # num_grids_in_phase is what expandDual divides by (intermediate_stage.cpp:167-172)
+    assert ctrl[0].ngrids_in_phase == types.index(LIFT)
+
+
+def test_small_event_schedule_shapes():
+    td, ev, ctrl = small_event_schedule(sto=False)
+    assert [c.type for c in ctrl].count(INTERMEDIATE) == len(ctrl) - 3
+
+
+@pytest.mark.parametrize("batch,world", [(1024, 8), (1000, 8), (7, 3), (0, 2), (5, 8)])
+def test_shard_range_partitions(batch, world):
+    spans = [shard_range(batch, world, r) for r in range(world)]
+    assert spans[0][0] == 0 and spans[-1][1] == batch
+    for (a, b), (c, d) in zip(spans, spans[1:]):
+        assert b == c and a <= b
+    sizes = [b - a for a, b in spans]
+    assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_range(batch, world, world)
