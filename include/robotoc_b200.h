@@ -19,6 +19,7 @@
 #define ROBOTOC_B200_H_
 
 #include "rbt_layout.h"
+#include "rbt_stage_layout.h"
 
 #ifdef __cplusplus
 extern "C" {
@@ -39,7 +40,14 @@ enum {
   RBT_BUF_FACT = 2,  /* factorized KKT F,H,G,lu (optional output of backward; the reference mutates kkt in place) */
   RBT_BUF_DIR = 3,   /* direction records    (output of forward) */
   RBT_BUF_DX0 = 4,   /* initial state direction dx0, [batch][nx] (input of forward) */
-  RBT_BUF_INFO = 5   /* per-OCP int status flags, [batch] (as doubles are not used: int32) */
+  RBT_BUF_INFO = 5,  /* per-OCP int status flags, [batch] (as doubles are not used: int32) */
+  /* stage layer (rbt_stage_setup): records of include/rbt_stage_layout.h */
+  RBT_BUF_LIN = 6,   /* linearization records (input of condensing) */
+  RBT_BUF_CON = 7,   /* PDIPM records: slack, dual, residual in; cmpl, cond, dslack, ddual out; slack, dual updated */
+  RBT_BUF_EXP = 8,   /* expansion records (MJtJinv, MJtJinv_dIDCdqv, ... kept by condensing for the expansion) */
+  RBT_BUF_SOL = 9,   /* solution records (q, v, a, dv, u, f, lmd, gmm, beta, mu, nu_passive, xi), updated in place */
+  RBT_BUF_XDIR = 10, /* expanded direction records (daf, dbetamu, dnu_passive) */
+  RBT_BUF_STEPS = 11 /* [batch][2] max primal / dual step size over the horizon */
 };
 
 typedef struct rbt_handle rbt_handle;
@@ -95,6 +103,26 @@ int rbt_riccati_forward(rbt_handle* h, void* stream);
  * This is the call an OCPSolver::updateSolution (src/solver/ocp_solver.cpp:118-123) adaptor makes. */
 int rbt_riccati_solve_host(rbt_handle* h, const double* kkt_host, const double* dx0_host, double* ric_host,
                            double* dir_host, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stage layer -- the condensing tail of evalKKT and the expansion / step-size / update half of
+ * robotoc::DirectMultipleShooting (include/robotoc/ocp/direct_multiple_shooting.hpp:86-199)
+ * --------------------------------------------------------------------------------------------- */
+int rbt_stage_layout_get(const rbt_stage_dims* sdims, const char* field);
+/* Allocates the stage-layer buffers.  `table` = the constraints of the OCP (robotoc::Constraints with its joint limits
+ * and friction cones, src/constraints/constraints.cpp); barrier / fraction-to-boundary as in constraint_component_base.hpp:44-45. */
+int rbt_stage_setup(rbt_handle* h, const rbt_stage_dims* sdims, const rbt_constraint_table* table);
+/* "Forms linear system" of {Intermediate,Impact,Terminal}Stage::evalKKT (intermediate_stage.cpp:133-148, impact_stage.cpp:115-121,
+ * terminal_stage.cpp:102-106): Constraints::condenseSlackAndDual, condenseContactDynamics / condenseImpactDynamics,
+ * correctLinearizeStateEquation, STO scaling.  Reads RBT_BUF_LIN, RBT_BUF_CON; writes RBT_BUF_KKT, RBT_BUF_EXP, RBT_BUF_CON. */
+int rbt_condense(rbt_handle* h, void* stream);
+/* DirectMultipleShooting::computeStepSizes + maxPrimalStepSize / maxDualStepSize (direct_multiple_shooting.cpp:174-209):
+ * expandPrimal of every stage, slack/dual directions, fraction-to-boundary, min over the horizon.
+ * Reads RBT_BUF_DIR, RBT_BUF_EXP, RBT_BUF_LIN; writes RBT_BUF_XDIR (daf), RBT_BUF_CON (dslack, ddual), RBT_BUF_STEPS. */
+int rbt_expand_and_step_sizes(rbt_handle* h, void* stream);
+/* DirectMultipleShooting::integrateSolution (direct_multiple_shooting.cpp:212-241) with the step sizes of RBT_BUF_STEPS:
+ * expandDual, correctCostateDirection, SplitSolution::integrate, updateSlack / updateDual. */
+int rbt_update(rbt_handle* h, void* stream);
 
 int rbt_sync(rbt_handle* h, void* stream);
 const char* rbt_last_error(rbt_handle* h);

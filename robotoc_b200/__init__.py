@@ -8,6 +8,8 @@ All compute goes through the C ABI of librobotoc_b200.so (include/robotoc_b200.h
 from .layout import Dims, Layout, ULayout  # noqa: F401
 from .schedule import GridInfo, TimeDiscretization, stage_ctrl_array  # noqa: F401
 from .riccati import RiccatiRecursion, UnconstrRiccatiRecursion  # noqa: F401
+from .stage import StageDims, StageLayout, anymal_constraint_table  # noqa: F401
+from .dms import DirectMultipleShooting  # noqa: F401
 
 ANYMAL = Dims(nv=18, nu=12, ns_max=12, n_passive=6)
 IIWA14_NV = 7

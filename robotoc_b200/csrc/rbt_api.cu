@@ -13,6 +13,7 @@
 #include "riccati_backward.cuh"
 #include "riccati_forward.cuh"
 #include "riccati_unconstr.cuh"
+#include "stage_kernels.cuh"
 
 namespace {
 
@@ -49,6 +50,13 @@ struct rbt_handle {
   int* d_arrivals = nullptr;  // per-SM CTA arrival counters (CTA de-phasing in the backward kernel)
   int stagger_ns = 0;
   long long* d_timeline = nullptr;  // bring-up instrumentation (RBT_TIMELINE_CTA)
+  // stage layer
+  bool stage_ready = false;
+  rbt_stage_dims sdims;
+  rbt_stage_layout S;
+  rbt_constraint_table table;
+  double *d_lin = nullptr, *d_con = nullptr, *d_ex = nullptr, *d_sol = nullptr, *d_xd = nullptr, *d_steps = nullptr,
+         *d_ones = nullptr;
   int timeline_cta = -1;
   long long launches = 0;
   std::string err;
@@ -154,6 +162,14 @@ int rbt_destroy(rbt_handle* h) {
   for (int q = 0; q < 5; ++q) cudaFree(h->own[q]);
   cudaFree(h->d_info);
   cudaFree(h->d_arrivals);
+  cudaFree(h->d_timeline);
+  cudaFree(h->d_lin);
+  cudaFree(h->d_con);
+  cudaFree(h->d_ex);
+  cudaFree(h->d_sol);
+  cudaFree(h->d_xd);
+  cudaFree(h->d_steps);
+  cudaFree(h->d_ones);
   delete h;
   return RBT_OK;
 }
@@ -195,6 +211,12 @@ static double* buf_ptr(rbt_handle* h, int which) {
     case RBT_BUF_FACT: return h->d_fact;
     case RBT_BUF_DIR: return h->d_dir;
     case RBT_BUF_DX0: return h->d_dx0;
+    case RBT_BUF_LIN: return h->d_lin;
+    case RBT_BUF_CON: return h->d_con;
+    case RBT_BUF_EXP: return h->d_ex;
+    case RBT_BUF_SOL: return h->d_sol;
+    case RBT_BUF_XDIR: return h->d_xd;
+    case RBT_BUF_STEPS: return h->d_steps;
     default: return nullptr;
   }
 }
@@ -202,7 +224,14 @@ static double* buf_ptr(rbt_handle* h, int which) {
 long long rbt_buf_doubles(rbt_handle* h, int which) {
   if (!h) return -1;
   const long long per = (long long)h->batch * h->n_grid;
+  if (which >= RBT_BUF_LIN && !h->stage_ready) return -1;
   switch (which) {
+    case RBT_BUF_LIN: return per * h->S.l_stride;
+    case RBT_BUF_CON: return per * h->S.c_stride;
+    case RBT_BUF_EXP: return per * h->S.e_stride;
+    case RBT_BUF_SOL: return per * h->S.s_stride;
+    case RBT_BUF_XDIR: return per * h->S.x_stride;
+    case RBT_BUF_STEPS: return 2LL * h->batch;
     case RBT_BUF_KKT: return per * h->L.k_stride;
     case RBT_BUF_RIC: return per * h->L.r_stride;
     case RBT_BUF_FACT: return per * h->L.f_stride;
@@ -265,14 +294,18 @@ static long long kkt_upload(rbt_handle* h, const double* host, cudaStream_t st, 
 
 long long rbt_upload_bytes(rbt_handle* h, int which) {
   if (!h || h->n_grid == 0) return -1;
-  if (which == RBT_BUF_DX0) return rbt_buf_doubles(h, which) * 8;
+  if (which == RBT_BUF_DX0 || which == RBT_BUF_LIN || which == RBT_BUF_CON || which == RBT_BUF_SOL)
+    return rbt_buf_doubles(h, which) * 8;
   if (which != RBT_BUF_KKT) return -1;
   int rc = RBT_OK;
   return kkt_upload(h, nullptr, nullptr, false, &rc);
 }
 
 int rbt_upload(rbt_handle* h, int which, const double* host, void* stream) {
-  if (!h || !host || (which != RBT_BUF_KKT && which != RBT_BUF_DX0)) return RBT_ERR_ARG;
+  if (!h || !host) return RBT_ERR_ARG;
+  if (which != RBT_BUF_KKT && which != RBT_BUF_DX0 && which != RBT_BUF_LIN && which != RBT_BUF_CON && which != RBT_BUF_SOL)
+    return RBT_ERR_ARG;
+  if (which >= RBT_BUF_LIN && !h->stage_ready) return RBT_ERR_STATE;
   if (h->n_grid == 0) return RBT_ERR_STATE;
   RBT_CUDA(h, cudaSetDevice(h->device));
   if (which == RBT_BUF_KKT) {
@@ -391,6 +424,116 @@ int rbt_riccati_forward(rbt_handle* h, void* stream) {
   RBT_INSTANCES(X)
 #undef X
   return RBT_ERR_ARG;
+}
+
+// ---- stage layer ---------------------------------------------------------------------------------------------------
+int rbt_stage_layout_get(const rbt_stage_dims* sdims, const char* field) {
+  if (!sdims || !field) return -1;
+  rbt_stage_layout S;
+  rbt_make_stage_layout(sdims, &S);
+  return rbt_stage_layout_field(&S, field);
+}
+
+int rbt_stage_setup(rbt_handle* h, const rbt_stage_dims* sd, const rbt_constraint_table* table) {
+  if (!h || !sd || !table) return RBT_ERR_ARG;
+  if (sd->nv != h->dims.nv || sd->nu != h->dims.nu || sd->ns_max != h->dims.ns_max || sd->n_passive != h->dims.n_passive ||
+      sd->nf_max != 12 || table->n_box != sd->n_box || table->n_contacts != sd->n_contacts || sd->n_box > RBT_MAX_BOX_ROWS ||
+      sd->n_contacts > RBT_MAX_CONTACTS || !(table->barrier > 0) || !(table->fraction_to_boundary > 0) ||
+      !(table->fraction_to_boundary <= 1)) {
+    h->err = "[rbt_stage_setup] invalid argument: stage dims / constraint table inconsistent with the handle";
+    return RBT_ERR_ARG;
+  }
+  for (int r = 0; r < table->n_box; ++r) {
+    const rbt_box_row& b = table->box[r];
+    const int lim = (b.var == RBT_VAR_U) ? sd->nu : sd->nv;
+    if (b.var < 0 || b.var > 3 || b.idx < 0 || b.idx >= lim || (b.sign != 1 && b.sign != -1)) {
+      h->err = "[rbt_stage_setup] invalid argument: bad box row " + std::to_string(r);
+      return RBT_ERR_ARG;
+    }
+  }
+  h->sdims = *sd;
+  h->table = *table;
+  rbt_make_stage_layout(sd, &h->S);
+  RBT_CUDA(h, cudaSetDevice(h->device));
+  const size_t per = size_t(h->batch) * h->n_grid_max;
+  RBT_CUDA(h, cudaMalloc(&h->d_lin, per * h->S.l_stride * 8));
+  RBT_CUDA(h, cudaMalloc(&h->d_con, per * h->S.c_stride * 8));
+  RBT_CUDA(h, cudaMalloc(&h->d_ex, per * h->S.e_stride * 8));
+  RBT_CUDA(h, cudaMalloc(&h->d_sol, per * h->S.s_stride * 8));
+  RBT_CUDA(h, cudaMalloc(&h->d_xd, per * h->S.x_stride * 8));
+  RBT_CUDA(h, cudaMalloc(&h->d_steps, size_t(h->batch) * 2 * 8));
+  RBT_CUDA(h, cudaMalloc(&h->d_ones, size_t(h->batch) * 2 * 8));
+  RBT_CUDA(h, cudaMemset(h->d_ex, 0, per * h->S.e_stride * 8));
+  RBT_CUDA(h, cudaMemset(h->d_xd, 0, per * h->S.x_stride * 8));
+  RBT_CUDA(h, cudaMemset(h->d_con, 0, per * h->S.c_stride * 8));
+  std::vector<double> ones(size_t(h->batch) * 2, 1.0);
+  RBT_CUDA(h, cudaMemcpy(h->d_ones, ones.data(), ones.size() * 8, cudaMemcpyHostToDevice));
+  RBT_CUDA(h, cudaMemcpy(h->d_steps, ones.data(), ones.size() * 8, cudaMemcpyHostToDevice));
+  h->stage_ready = true;
+  return RBT_OK;
+}
+
+static rbt::StageParams make_stage_params(rbt_handle* h) {
+  rbt::StageParams p;
+  p.K = h->L;
+  p.S = h->S;
+  p.tab = h->table;
+  p.ctrl = h->d_ctrl;
+  p.n_grid = h->n_grid;
+  p.batch = h->batch;
+  p.lin = h->d_lin;
+  p.con = h->d_con;
+  p.kkt = h->d_kkt;
+  p.ex = h->d_ex;
+  p.dir = h->d_dir;
+  p.xd = h->d_xd;
+  p.sol = h->d_sol;
+  p.steps = h->d_steps;
+  p.info = h->d_info;
+  return p;
+}
+
+#define RBT_STAGE_CHECK(h, what)                                  \
+  if (!(h)) return RBT_ERR_ARG;                                   \
+  if (!(h)->stage_ready || (h)->n_grid == 0) {                    \
+    (h)->err = "[" what "] stage layer not set up / no schedule"; \
+    return RBT_ERR_STATE;                                         \
+  }                                                               \
+  RBT_CUDA(h, cudaSetDevice((h)->device));
+
+int rbt_condense(rbt_handle* h, void* stream) {
+  RBT_STAGE_CHECK(h, "rbt_condense");
+  using C = rbt::CondCfg<18, 12, 12>;
+  auto kern = rbt::condense_kernel<18, 12, 12>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    RBT_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
+    attr_done = true;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  RBT_CUDA(h, cudaMemsetAsync(h->d_info, 0, size_t(h->batch) * sizeof(int), st));
+  kern<<<h->batch * h->n_grid, C::NTHREADS, C::SMEM_BYTES, st>>>(make_stage_params(h));
+  RBT_CUDA(h, cudaGetLastError());
+  h->launches += 1;
+  return RBT_OK;
+}
+
+int rbt_expand_and_step_sizes(rbt_handle* h, void* stream) {
+  RBT_STAGE_CHECK(h, "rbt_expand_and_step_sizes");
+  cudaStream_t st = (cudaStream_t)stream;
+  RBT_CUDA(h, cudaMemcpyAsync(h->d_steps, h->d_ones, size_t(h->batch) * 2 * 8, cudaMemcpyDeviceToDevice, st));
+  rbt::expand_kernel<18, 12, 12><<<h->batch * h->n_grid, 64, 0, st>>>(make_stage_params(h));
+  RBT_CUDA(h, cudaGetLastError());
+  h->launches += 1;
+  return RBT_OK;
+}
+
+int rbt_update(rbt_handle* h, void* stream) {
+  RBT_STAGE_CHECK(h, "rbt_update");
+  rbt::update_kernel<18, 12, 12><<<h->batch * h->n_grid, 64, 0, (cudaStream_t)stream>>>(make_stage_params(h));
+  RBT_CUDA(h, cudaGetLastError());
+  h->launches += 1;
+  return RBT_OK;
 }
 
 int rbt_riccati_solve_host(rbt_handle* h, const double* kkt_host, const double* dx0_host, double* ric_host,

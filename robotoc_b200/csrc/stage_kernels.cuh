@@ -1,0 +1,761 @@
+// stage_kernels.cuh -- stage-parallel kernels of the hot path around the Riccati sweeps.
+//
+//   condense_kernel     PDIPM condensing + contact/impact dynamics condensing + floating-base state-equation correction
+//                       (intermediate_stage.cpp:133-148, contact_dynamics.cpp:55-164, impact_dynamics.cpp:38-80,
+//                        state_equation.cpp:68-87, joint_*_limit.cpp:68-75, friction_cone.cpp:194-235, pdipm.hxx:27-100)
+//   expand_kernel       primal expansion, slack/dual directions, fraction-to-boundary step sizes with the min over the horizon
+//                       (contact_dynamics.cpp:167-174, friction_cone.cpp:238-268, pdipm.hxx:121-164,
+//                        direct_multiple_shooting.cpp:174-209)
+//   update_kernel       dual expansion, costate correction, solution integrate, slack/dual update
+//                       (contact_dynamics.cpp:177-202, state_equation.cpp:90-95, split_solution.cpp:58-90)
+//
+// Unlike the Riccati sweeps these have NO dependency between stages: the grid is batch x n_grid CTAs (48k for config 3),
+// every stage is an independent small dense problem held in shared memory.  Round 1: plain fp64 FMA loops over shared
+// memory (correctness first); the dense products are candidates for the DMMA path of riccati_backward.cuh.
+#pragma once
+#include "rbt_device.cuh"
+#include "riccati_backward.cuh"  // warp_cholesky, chol_solve_smem
+#include "../../include/rbt_stage_layout.h"
+
+namespace rbt {
+
+struct StageParams {
+  rbt_layout K;
+  rbt_stage_layout S;
+  rbt_constraint_table tab;
+  const rbt_stage_ctrl* ctrl;
+  int n_grid;
+  int batch;
+  const double* lin;
+  double* con;
+  double* kkt;
+  double* ex;
+  double* dir;
+  double* xd;
+  double* sol;
+  double* steps;  // [batch][2]
+  int* info;
+};
+
+// C(m x n, ld ldc) = beta*C + alpha * op(A) op(B); all operands in shared (or global) memory; every thread of the CTA calls.
+__device__ __forceinline__ void cta_gemm(int ta, int tb, int m, int n, int k, double alpha, const double* A, int lda,
+                                         const double* B, int ldb, double beta, double* C, int ldc) {
+  for (int e = threadIdx.x; e < m * n; e += blockDim.x) {
+    const int i = e % m, j = e / m;
+    double acc = 0.0;
+    for (int l = 0; l < k; ++l) {
+      const double a = ta ? A[l + i * lda] : A[i + l * lda];
+      const double b = tb ? B[j + l * ldb] : B[l + j * ldb];
+      acc = fma(a, b, acc);
+    }
+    const double c0 = (beta == 0.0) ? 0.0 : beta * C[i + j * ldc];
+    C[i + j * ldc] = fma(alpha, acc, c0);
+  }
+}
+
+__device__ __forceinline__ void inv3_dev(const double* A, int lda, double* B, int ldb) {
+  const double a = A[0], b = A[lda], c = A[2 * lda], d = A[1], e = A[1 + lda], f = A[1 + 2 * lda], g = A[2], h = A[2 + lda],
+               i = A[2 + 2 * lda];
+  const double det = a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g);
+  const double r = 1.0 / det;
+  B[0] = (e * i - f * h) * r; B[ldb] = (c * h - b * i) * r; B[2 * ldb] = (b * f - c * e) * r;
+  B[1] = (f * g - d * i) * r; B[1 + ldb] = (a * i - c * g) * r; B[1 + 2 * ldb] = (c * d - a * f) * r;
+  B[2] = (d * h - e * g) * r; B[2 + ldb] = (b * g - a * h) * r; B[2 + 2 * ldb] = (a * e - b * d) * r;
+}
+
+// SE3JacobianInverse::compute (se3_jacobian_inverse.hxx:17-32); one thread; Jac may be global, Jinv shared/global (ld 6)
+__device__ __forceinline__ void se3_jac_inverse_dev(const double* Jac, double* Jinv) {
+  double tmp[9];
+  for (int q = 0; q < 36; ++q) Jinv[q] = 0.0;
+  inv3_dev(Jac, 6, Jinv, 6);
+  inv3_dev(Jac + 3 + 18, 6, Jinv + 3 + 18, 6);
+  for (int j = 0; j < 3; ++j)
+    for (int i = 0; i < 3; ++i) {
+      double acc = 0.0;
+      for (int l = 0; l < 3; ++l) acc = fma(Jac[i + (3 + l) * 6], Jinv[(3 + l) + (3 + j) * 6], acc);
+      tmp[i + 3 * j] = acc;
+    }
+  for (int j = 0; j < 3; ++j)
+    for (int i = 0; i < 3; ++i) {
+      double acc = 0.0;
+      for (int l = 0; l < 3; ++l) acc = fma(Jinv[i + l * 6], tmp[l + 3 * j], acc);
+      Jinv[i + (3 + j) * 6] = -acc;
+    }
+}
+
+template <int NV, int NU, int NFM>
+struct CondCfg {
+  static constexpr int NX = 2 * NV, NVF = NV + NFM;
+  static constexpr int NTHREADS = 256;
+  static constexpr int o_M = 0;                      // M -> L_M
+  static constexpr int o_Mi = o_M + NV * NV;         // M^-1
+  static constexpr int o_J = o_Mi + NV * NV;         // J (ld NFM)
+  static constexpr int o_JMi = o_J + NFM * NV;       // J M^-1 (ld NFM)
+  static constexpr int o_S = o_JMi + NFM * NV;       // J M^-1 J^T -> chol
+  static constexpr int o_Si = o_S + NFM * NFM;       // its inverse
+  static constexpr int o_Z = o_Si + NFM * NFM;       // Z (ld NVF)
+  static constexpr int o_D = o_Z + NVF * NVF;        // dIDCdqv (ld NVF)
+  static constexpr int o_R = o_D + NVF * NX;         // R (ld NVF)
+  static constexpr int o_Qa = o_R + NVF * NX;        // Qafqv (ld NVF)
+  static constexpr int o_Qu = o_Qa + NVF * NX;       // Qafu_full (ld NVF)
+  static constexpr int o_Qxx = o_Qu + NVF * NV;      // Qxx working copy
+  static constexpr int o_Qff = o_Qxx + NX * NX;      // Qff (ld NFM)
+  static constexpr int o_Qqf = o_Qff + NFM * NFM;    // Qqf (ld NV)
+  static constexpr int o_vec = o_Qqf + NV * NFM;     // IDC(NVF) r(NVF) laf(NVF) haf(NVF) Qaa(NV) la(NV) lf(NFM) lx(NX) lu(NU) Fx(NX) dinv(32) misc
+  static constexpr int v_IDC = 0, v_r = NVF, v_laf = 2 * NVF, v_haf = 3 * NVF, v_Qaa = 4 * NVF, v_la = v_Qaa + NV,
+                       v_lf = v_la + NV, v_lx = v_lf + NFM, v_lu = v_lx + NX, v_Fx = v_lu + NU, v_dinv = v_Fx + NX,
+                       v_w = v_dinv + 32, v_end = v_w + 128;
+  static constexpr int SMEM_DOUBLES = o_vec + v_end;
+  static constexpr size_t SMEM_BYTES = size_t(SMEM_DOUBLES) * 8;
+};
+
+template <int NV, int NU, int NFM>
+__global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS) condense_kernel(const StageParams p) {
+  using C = CondCfg<NV, NU, NFM>;
+  constexpr int NX = C::NX, NVF = C::NVF, NTHR = C::NTHREADS;
+  extern __shared__ __align__(16) double smem[];
+  const rbt_layout& K = p.K;
+  const rbt_stage_layout& S = p.S;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const size_t o = blockIdx.x;  // b * n_grid + i
+  if (o >= size_t(p.batch) * p.n_grid) return;
+  const int i = int(o % p.n_grid), b = int(o / p.n_grid);
+  const rbt_stage_ctrl c = p.ctrl[i];
+  const double* lin = p.lin + o * S.l_stride;
+  double* con = p.con + o * S.c_stride;
+  double* kkt = p.kkt + o * K.k_stride;
+  double* ex = p.ex + o * S.e_stride;
+  const int np = S.np;
+
+  if (c.type == RBT_TERMINAL) {  // terminal_stage.cpp:94-106
+    for (int e = tid; e < NX * NX; e += NTHR) kkt[K.k_Qxx + e] = lin[S.l_Qxx + e];
+    for (int e = tid; e < NX; e += NTHR) kkt[K.k_lx + e] = lin[S.l_lx + e];
+    if (np == 6 && tid == 0) se3_jac_inverse_dev(lin + S.l_se3 + 36, ex + S.e_Fqqpi);
+    return;
+  }
+  const bool impact = (c.type == RBT_IMPACT);
+  const int nf = c.nf, nvf = NV + nf, ns = impact ? 0 : c.ns;
+  const double dt = c.dt;
+  double* sM = smem + C::o_M;
+  double* sMi = smem + C::o_Mi;
+  double* sJ = smem + C::o_J;
+  double* sJMi = smem + C::o_JMi;
+  double* sS = smem + C::o_S;
+  double* sSi = smem + C::o_Si;
+  double* sZ = smem + C::o_Z;
+  double* sD = smem + C::o_D;
+  double* sR = smem + C::o_R;
+  double* sQa = smem + C::o_Qa;
+  double* sQu = smem + C::o_Qu;
+  double* sQxx = smem + C::o_Qxx;
+  double* sQff = smem + C::o_Qff;
+  double* sQqf = smem + C::o_Qqf;
+  double* vec = smem + C::o_vec;
+  double* vIDC = vec + C::v_IDC;
+  double* vr = vec + C::v_r;
+  double* vlaf = vec + C::v_laf;
+  double* vhaf = vec + C::v_haf;
+  double* vQaa = vec + C::v_Qaa;
+  double* vla = vec + C::v_la;
+  double* vlf = vec + C::v_lf;
+  double* vlx = vec + C::v_lx;
+  double* vlu = vec + C::v_lu;
+  double* vFx = vec + C::v_Fx;
+  double* vdinv = vec + C::v_dinv;
+  double* vw = vec + C::v_w;  // per-row PDIPM weights dual/slack (cones) and scratch
+  int bad = 0;
+
+  // ---- stage inputs -> shared memory (the stacked [a;f] blocks are zero beyond nv+nf rows/cols)
+  for (int e = tid; e < C::o_Qxx - C::o_Z; e += NTHR) smem[C::o_Z + e] = 0.0;
+  __syncthreads();
+  for (int e = tid; e < NV * NV; e += NTHR) sM[e] = lin[S.l_M + e];
+  for (int e = tid; e < NFM * NV; e += NTHR) sJ[e] = lin[S.l_J + e];
+  for (int e = tid; e < NVF * NX; e += NTHR) sD[e] = lin[S.l_D + e];
+  for (int e = tid; e < NX * NX; e += NTHR) sQxx[e] = lin[S.l_Qxx + e];
+  for (int e = tid; e < NFM * NFM; e += NTHR) sQff[e] = lin[S.l_Qff + e];
+  for (int e = tid; e < NV * NFM; e += NTHR) sQqf[e] = lin[S.l_Qqf + e];
+  for (int e = tid; e < NVF; e += NTHR) vIDC[e] = lin[S.l_IDC + e];
+  for (int e = tid; e < NV; e += NTHR) {
+    vQaa[e] = lin[S.l_Qaa + e];
+    vla[e] = lin[S.l_la + e];
+  }
+  for (int e = tid; e < NFM; e += NTHR) vlf[e] = lin[S.l_lf + e];
+  for (int e = tid; e < NX; e += NTHR) {
+    vlx[e] = lin[S.l_lx + e];
+    vFx[e] = lin[S.l_Fx + e];
+  }
+  for (int e = tid; e < NU; e += NTHR) vlu[e] = lin[S.l_lu + e];
+  // Quu / Qxu working copies live in the (global) KKT record
+  for (int e = tid; e < NU * NU; e += NTHR) kkt[K.k_Quu + e] = impact ? 0.0 : lin[S.l_Quu + e];
+  __syncthreads();
+
+  // ---- PDIPM condensing (Intermediate / Lift)
+  if (!impact) {
+    const double mu = p.tab.barrier;
+    for (int r = tid; r < p.tab.n_box; r += NTHR) {
+      const rbt_box_row br = p.tab.box[r];
+      const double sl = con[S.c_slack + r], du = con[S.c_dual + r];
+      const double cm = sl * du - mu;
+      const double cd = (du * con[S.c_res + r] - cm) / sl;
+      con[S.c_cmpl + r] = cm;
+      con[S.c_cond + r] = cd;
+      const double w = du / sl;
+      // rows never share a (var, idx, sign) triple, but a lower and an upper limit share the diagonal entry: atomics on shared
+      switch (br.var) {
+        case RBT_VAR_Q: atomicAdd(&sQxx[br.idx + br.idx * NX], w); atomicAdd(&vlx[br.idx], br.sign * cd); break;
+        case RBT_VAR_V: atomicAdd(&sQxx[(NV + br.idx) * (NX + 1)], w); atomicAdd(&vlx[NV + br.idx], br.sign * cd); break;
+        case RBT_VAR_A: atomicAdd(&vQaa[br.idx], w); atomicAdd(&vla[br.idx], br.sign * cd); break;
+        default: atomicAdd(&kkt[K.k_Quu + br.idx * (NU + 1)], w); atomicAdd(&vlu[br.idx], br.sign * cd); break;
+      }
+    }
+    __syncthreads();
+    int fstack = 0;
+    for (int ci = 0; ci < p.tab.n_contacts; ++ci) {
+      const int base = p.tab.n_box + 5 * ci;
+      const bool act = (c.contact_mask >> ci) & 1;
+      if (!act) {
+        if (tid < 5) con[S.c_cond + base + tid] = 0.0;
+        continue;
+      }
+      const double* dgdq = lin + S.l_dgdq + size_t(ci) * 5 * NV;
+      const double* dgdf = lin + S.l_dgdf + size_t(ci) * 15;
+      if (tid < 5) {
+        const double sl = con[S.c_slack + base + tid], du = con[S.c_dual + base + tid];
+        const double cm = sl * du - mu;
+        const double cd = (du * con[S.c_res + base + tid] - cm) / sl;
+        con[S.c_cmpl + base + tid] = cm;
+        con[S.c_cond + base + tid] = cd;
+        vw[tid] = du / sl;
+        vw[8 + tid] = cd;
+      }
+      __syncthreads();
+      for (int j = tid; j < NV + 3; j += NTHR) {
+        double acc = 0.0;
+        if (j < NV) {
+          for (int r = 0; r < 5; ++r) acc = fma(dgdq[r + j * 5], vw[8 + r], acc);
+          vlx[j] += acc;
+        } else {
+          for (int r = 0; r < 5; ++r) acc = fma(dgdf[r + (j - NV) * 5], vw[8 + r], acc);
+          vlf[fstack + j - NV] += acc;
+        }
+      }
+      for (int e = tid; e < NV * (NV + 3); e += NTHR) {
+        const int ii = e % NV, j = e / NV;
+        double acc = 0.0;
+        if (j < NV) {
+          for (int r = 0; r < 5; ++r) acc = fma(dgdq[r + ii * 5] * vw[r], dgdq[r + j * 5], acc);
+          sQxx[ii + j * NX] += acc;
+        } else {
+          for (int r = 0; r < 5; ++r) acc = fma(dgdq[r + ii * 5] * vw[r], dgdf[r + (j - NV) * 5], acc);
+          sQqf[ii + (fstack + j - NV) * NV] += acc;
+        }
+      }
+      if (tid < 9) {
+        const int ii = tid % 3, j = tid / 3;
+        double acc = 0.0;
+        for (int r = 0; r < 5; ++r) acc = fma(dgdf[r + ii * 5] * vw[r], dgdf[r + j * 5], acc);
+        sQff[(fstack + ii) + (fstack + j) * NFM] += acc;
+      }
+      __syncthreads();
+      fstack += 3;
+    }
+  }
+
+  // ---- Z = [[M, J^T],[J, 0]]^-1   (robot.hxx:642-683, dense)
+  for (int e = tid; e < NV * NV; e += NTHR) sMi[e] = ((e % NV) == (e / NV)) ? 1.0 : 0.0;
+  __syncthreads();
+  if (warp == 0) {
+    if (!warp_cholesky<NV>(sM, NV, vdinv)) bad |= 4;
+  }
+  __syncthreads();
+  if (tid < NV) chol_solve_smem(sM, vdinv, NV, sMi + tid * NV, 1);
+  __syncthreads();
+  for (int e = tid; e < NV * NV; e += NTHR) sZ[(e % NV) + (e / NV) * NVF] = sMi[e];
+  if (nf > 0) {
+    cta_gemm(0, 0, nf, NV, NV, 1.0, sJ, NFM, sMi, NV, 0.0, sJMi, NFM);
+    __syncthreads();
+    cta_gemm(0, 1, nf, nf, NV, 1.0, sJMi, NFM, sJ, NFM, 0.0, sS, nf);  // compact ld = nf for the Cholesky
+    for (int e = tid; e < nf * nf; e += NTHR) sSi[e] = ((e % nf) == (e / nf)) ? 1.0 : 0.0;
+    __syncthreads();
+    if (warp == 0) {
+      if (!warp_cholesky<NFM>(sS, nf, vdinv)) bad |= 8;
+    }
+    __syncthreads();
+    if (tid < nf) chol_solve_smem(sS, vdinv, nf, sSi + tid * nf, 1);
+    __syncthreads();
+    for (int e = tid; e < nf * nf; e += NTHR) sZ[(NV + e % nf) + (NV + e / nf) * NVF] = -sSi[e];
+    for (int e = tid; e < NV * nf; e += NTHR) {  // topRight = (J M^-1)^T S^-1
+      const int ii = e % NV, j = e / NV;
+      double acc = 0.0;
+      for (int l = 0; l < nf; ++l) acc = fma(sJMi[l + ii * NFM], sSi[l + j * nf], acc);
+      sZ[ii + (NV + j) * NVF] = acc;
+    }
+    __syncthreads();
+    for (int e = tid; e < NV * NV; e += NTHR) {  // topLeft -= topRight (J M^-1)
+      const int ii = e % NV, j = e / NV;
+      double acc = 0.0;
+      for (int l = 0; l < nf; ++l) acc = fma(sZ[ii + (NV + l) * NVF], sJMi[l + j * NFM], acc);
+      sZ[ii + j * NVF] -= acc;
+    }
+    for (int e = tid; e < NV * nf; e += NTHR) sZ[(NV + e / NV) + (e % NV) * NVF] = sZ[(e % NV) + (NV + e / NV) * NVF];
+  }
+  __syncthreads();
+
+  // ---- R = Z D ; r = Z IDC ; Qafqv ; Qafu ; laf          contact_dynamics.cpp:65-86
+  cta_gemm(0, 0, nvf, NX, nvf, 1.0, sZ, NVF, sD, NVF, 0.0, sR, NVF);
+  if (tid < nvf) {
+    double acc = 0.0;
+    for (int l = 0; l < nvf; ++l) acc = fma(sZ[tid + l * NVF], vIDC[l], acc);
+    vr[tid] = acc;
+  }
+  __syncthreads();
+  for (int e = tid; e < nvf * NX; e += NTHR) {
+    const int ii = e % nvf, j = e / nvf;
+    double v;
+    if (ii < NV) {
+      v = -vQaa[ii] * sR[ii + j * NVF];
+    } else {
+      double acc = 0.0;
+      for (int l = 0; l < nf; ++l) acc = fma(sQff[(ii - NV) + l * NFM], sR[(NV + l) + j * NVF], acc);
+      v = -acc;
+      if (j < NV) v -= sQqf[j + (ii - NV) * NV];
+    }
+    sQa[ii + j * NVF] = v;
+  }
+  if (!impact) {
+    for (int e = tid; e < nvf * NV; e += NTHR) {
+      const int ii = e % nvf, j = e / nvf;
+      double v;
+      if (ii < NV) {
+        v = vQaa[ii] * sZ[ii + j * NVF];
+      } else {
+        double acc = 0.0;
+        for (int l = 0; l < nf; ++l) acc = fma(sQff[(ii - NV) + l * NFM], sZ[(NV + l) + j * NVF], acc);
+        v = acc;
+      }
+      sQu[ii + j * NVF] = v;
+    }
+  }
+  if (tid < nvf) {
+    if (tid < NV) {
+      vlaf[tid] = vla[tid] - vQaa[tid] * vr[tid];
+    } else {
+      double acc = 0.0;
+      for (int l = 0; l < nf; ++l) acc = fma(sQff[(tid - NV) + l * NFM], vr[NV + l], acc);
+      vlaf[tid] = -vlf[tid - NV] - acc;
+    }
+  }
+  __syncthreads();
+
+  // ---- Hessian / gradient condensing                   contact_dynamics.cpp:88-128, impact_dynamics.cpp:64-70
+  for (int e = tid; e < NX * NX; e += NTHR) {
+    const int ii = e % NX, j = e / NX;
+    double acc = 0.0;
+    for (int l = 0; l < nvf; ++l) acc = fma(sR[l + ii * NVF], sQa[l + j * NVF], acc);
+    double v = sQxx[e] - acc;
+    if (ii < NV) {
+      double a2 = 0.0;
+      for (int l = 0; l < nf; ++l) a2 = fma(sQqf[ii + l * NV], sR[(NV + l) + j * NVF], a2);
+      v += a2;
+    }
+    kkt[K.k_Qxx + e] = v;
+  }
+  for (int ii = tid; ii < NX; ii += NTHR) {
+    double acc = 0.0;
+    for (int l = 0; l < nvf; ++l) acc = fma(sR[l + ii * NVF], vlaf[l], acc);
+    double v = vlx[ii] - acc;
+    if (ii < NV) {
+      double a2 = 0.0;
+      for (int l = 0; l < nf; ++l) a2 = fma(sQqf[ii + l * NV], vr[NV + l], a2);
+      v += a2;
+    }
+    kkt[K.k_lx + ii] = v;
+  }
+  if (!impact) {
+    for (int e = tid; e < NX * NV; e += NTHR) {  // [Qxu_passive | Qxu] = -R^T Qafu_full - [Qqf Z_fa ; 0]
+      const int ii = e % NX, j = e / NX;
+      double acc = 0.0;
+      for (int l = 0; l < nvf; ++l) acc = fma(sR[l + ii * NVF], sQu[l + j * NVF], acc);
+      double v = -acc;
+      if (ii < NV) {
+        double a2 = 0.0;
+        for (int l = 0; l < nf; ++l) a2 = fma(sQqf[ii + l * NV], sZ[(NV + l) + j * NVF], a2);
+        v -= a2;
+      }
+      if (j < np) ex[S.e_Qxup + ii + j * NX] = v;
+      else kkt[K.k_Qxu + ii + (j - np) * NX] = v;  // pre-condense Qxu is zero (the cost has no x-u coupling)
+    }
+    for (int e = tid; e < NV * NU; e += NTHR) {  // [Quu_passive_topRight ; Quu +=] = Z[0:nv, :] Qafu_full[:, np:]
+      const int ii = e % NV, j = e / NV;
+      double acc = 0.0;
+      for (int l = 0; l < nvf; ++l) acc = fma(sZ[ii + l * NVF], sQu[l + (np + j) * NVF], acc);
+      if (ii < np) ex[S.e_Quup + ii + j * np] = acc;
+      else kkt[K.k_Quu + (ii - np) + j * NU] += acc;
+    }
+    for (int ii = tid; ii < NV; ii += NTHR) {  // [lu_passive ; lu] += Z[0:nv, :] laf
+      double acc = 0.0;
+      for (int l = 0; l < nvf; ++l) acc = fma(sZ[ii + l * NVF], vlaf[l], acc);
+      if (ii < np) ex[S.e_lup + ii] = lin[S.l_lup + ii] + acc;
+      else kkt[K.k_lu + ii - np] = vlu[ii - np] + acc;
+    }
+  }
+  // ---- state equation rows                                 contact_dynamics.cpp:130-135, impact_dynamics.cpp:71-74
+  const double sdt = impact ? 1.0 : dt;
+  for (int e = tid; e < NX * NX; e += NTHR) {
+    const int ii = e % NX, j = e / NX;
+    double v;
+    if (ii < NV) {
+      if (j < NV) v = (ii == j) ? 1.0 : 0.0;
+      else v = (!impact && ii == j - NV) ? dt : 0.0;
+      if (np == 6 && ii < 6 && j < 6) v = lin[S.l_se3 + ii + j * 6];
+    } else {
+      v = -sdt * sR[(ii - NV) + j * NVF] + ((j >= NV && ii == j) ? 1.0 : 0.0);
+    }
+    sQxx[e] = v;  // Qxx is done with its working copy: reuse it for Fxx (SE(3) correction below)
+  }
+  if (!impact)
+    for (int e = tid; e < NV * NU; e += NTHR) kkt[K.k_Fvu + e] = dt * sZ[(e % NV) + (np + e / NV) * NVF];
+  for (int ii = tid; ii < NX; ii += NTHR) {
+    double v = vFx[ii];
+    if (ii >= NV) v -= sdt * vr[ii - NV];
+    vFx[ii] = v;
+  }
+  // ---- switching constraint                                contact_dynamics.cpp:138-153
+  if (ns > 0) {
+    const double* Phia = lin + S.l_Phia;
+    for (int e = tid; e < ns * NV; e += NTHR) ex[S.e_Phia + e] = Phia[e];
+    for (int e = tid; e < ns * NX; e += NTHR) {
+      const int q = e % ns, j = e / ns;
+      double acc = 0.0;
+      for (int l = 0; l < NV; ++l) acc = fma(Phia[q + l * ns], sR[l + j * NVF], acc);
+      kkt[K.k_Phix + e] = lin[S.l_Phix + e] - acc;
+    }
+    for (int e = tid; e < ns * NU; e += NTHR) {
+      const int q = e % ns, j = e / ns;
+      double acc = 0.0;
+      for (int l = 0; l < NV; ++l) acc = fma(Phia[q + l * ns], sZ[l + (np + j) * NVF], acc);
+      kkt[K.k_Phiu + e] = acc;
+    }
+    for (int q = tid; q < ns; q += NTHR) {
+      double acc = 0.0;
+      for (int l = 0; l < NV; ++l) acc = fma(Phia[q + l * ns], vr[l], acc);
+      kkt[K.k_p + q] = lin[S.l_p + q] - acc;
+      kkt[K.k_Phit + q] = (lin[S.l_Phit + q] - acc) / c.ngrids_in_phase;  // incl. the STO scaling (intermediate_stage.cpp:146-148)
+    }
+  }
+  __syncthreads();
+  // ---- STO sensitivities + scaling                         contact_dynamics.cpp:156-163, intermediate_stage.cpp:140-148
+  if (!impact) {
+    const double g1 = 1.0 / c.ngrids_in_phase;
+    if (tid < nvf) vhaf[tid] = (tid < NV) ? lin[S.l_ha + tid] : -lin[S.l_hf + tid - NV];
+    __syncthreads();
+    if (tid < nvf) ex[S.e_haf + tid] = vhaf[tid];
+    for (int ii = tid; ii < NX; ii += NTHR) {
+      double acc = 0.0;
+      for (int l = 0; l < nvf; ++l) acc = fma(sR[l + ii * NVF], vhaf[l], acc);
+      double v = lin[S.l_hx + ii] - acc;
+      if (ii < NV) {
+        double a2 = 0.0;
+        for (int l = 0; l < nf; ++l) a2 = fma(sQqf[ii + l * NV], vr[NV + l], a2);
+        v += a2 / dt;
+      }
+      kkt[K.k_hx + ii] = v * g1;
+      vw[ii] = lin[S.l_fx + ii];  // fx, SE(3)-corrected below
+    }
+    for (int ii = tid; ii < NU; ii += NTHR) {
+      double acc = 0.0;
+      for (int l = 0; l < nvf; ++l) acc = fma(sZ[(np + ii) + l * NVF], vhaf[l], acc);
+      kkt[K.k_hu + ii] = (lin[S.l_hu + ii] + acc) * g1;
+    }
+    if (tid == 0) {
+      double h = lin[S.l_sc + 0];
+      for (int l = 0; l < nvf; ++l) h = fma(-vr[l], vhaf[l], h);
+      const double Qtt = lin[S.l_sc + 1] * g1 * g1;
+      kkt[K.k_sc + 0] = Qtt;
+      kkt[K.k_sc + 1] = -Qtt;
+      kkt[K.k_sc + 2] = h * g1;
+      kkt[K.k_sc + 3] = 0.0;
+    }
+  }
+  __syncthreads();
+  // ---- floating base: SE(3) correction                     state_equation.cpp:68-87, impact_state_equation.cpp:53-70
+  if (np == 6) {
+    double* Fi = vw + 64;  // Fqq_inv (36)
+    if (tid == 0) se3_jac_inverse_dev(lin + S.l_se3 + 36, ex + S.e_Fqqpi);
+    if (tid == 32) se3_jac_inverse_dev(lin + S.l_se3 + 72, Fi);
+    __syncthreads();
+    double v1 = 0.0, v2 = 0.0, v3 = 0.0;
+    const int ii = tid % 6, j = tid / 6;
+    if (tid < 36) {
+      for (int l = 0; l < 6; ++l) v1 = fma(Fi[ii + l * 6], sQxx[l + j * NX], v1);
+    } else if (tid < 42) {
+      for (int l = 0; l < 6; ++l) {
+        v2 = fma(Fi[ii + l * 6], vFx[l], v2);
+        if (!impact) v3 = fma(Fi[ii + l * 6], vw[l], v3);
+      }
+    }
+    __syncthreads();
+    if (tid < 36) {
+      sQxx[ii + j * NX] = -v1;
+      if (!impact) sQxx[ii + (NV + j) * NX] = -dt * Fi[ii + j * 6];
+    } else if (tid < 42) {
+      vFx[ii] = -v2;
+      if (!impact) vw[ii] = -v3;
+    }
+    __syncthreads();
+  }
+  for (int e = tid; e < NX * NX; e += NTHR) kkt[K.k_Fxx + e] = sQxx[e];
+  for (int e = tid; e < NX; e += NTHR) {
+    kkt[K.k_Fx + e] = vFx[e];
+    if (!impact) kkt[K.k_fx + e] = vw[e] / c.ngrids_in_phase;
+  }
+  // ---- expansion record
+  for (int e = tid; e < NVF * NVF; e += NTHR) ex[S.e_Z + e] = sZ[e];
+  for (int e = tid; e < NVF * NX; e += NTHR) {
+    ex[S.e_R + e] = sR[e];
+    ex[S.e_Qafqv + e] = sQa[e];
+  }
+  if (!impact)
+    for (int e = tid; e < NVF * NV; e += NTHR) ex[S.e_Qafu + e] = sQu[e];
+  for (int e = tid; e < nvf; e += NTHR) {
+    ex[S.e_r + e] = vr[e];
+    ex[S.e_laf + e] = vlaf[e];
+  }
+  bad = __reduce_or_sync(0xffffffffu, bad);
+  if ((tid & 31) == 0 && bad) atomicOr(&p.info[b], bad);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ void atomic_min_pos(double* addr, double v) {  // v > 0: IEEE order == unsigned integer order
+  atomicMin(reinterpret_cast<unsigned long long*>(addr), static_cast<unsigned long long>(__double_as_longlong(v)));
+}
+
+template <int NV, int NU, int NFM>
+__global__ void __launch_bounds__(64) expand_kernel(const StageParams p) {
+  constexpr int NX = 2 * NV, NVF = NV + NFM, NTHR = 64;
+  __shared__ double sdx[NX], sdu[NU], sdaf[NVF], smin[4];
+  const rbt_layout& K = p.K;
+  const rbt_stage_layout& S = p.S;
+  const int tid = threadIdx.x;
+  const size_t o = blockIdx.x;
+  const int i = int(o % p.n_grid), b = int(o / p.n_grid);
+  const rbt_stage_ctrl c = p.ctrl[i];
+  if (c.type == RBT_TERMINAL) return;  // step sizes 1.0 (terminal_stage.cpp:127-136)
+  const bool impact = (c.type == RBT_IMPACT);
+  const int nf = c.nf, nvf = NV + nf, np = S.np;
+  const double* lin = p.lin + o * S.l_stride;
+  const double* ex = p.ex + o * S.e_stride;
+  const double* d = p.dir + o * K.d_stride;
+  double* con = p.con + o * S.c_stride;
+  double* xd = p.xd + o * S.x_stride;
+  for (int e = tid; e < NX; e += NTHR) sdx[e] = d[K.d_dx + e];
+  for (int e = tid; e < NU; e += NTHR) sdu[e] = impact ? 0.0 : d[K.d_du + e];
+  __syncthreads();
+  for (int r = tid; r < nvf; r += NTHR) {  // daf = -R dx + Z[:, np:np+nu] du - r ; df *= -1      contact_dynamics.cpp:167-174
+    double acc = 0.0;
+    for (int k = 0; k < NX; ++k) acc = fma(-ex[S.e_R + r + k * NVF], sdx[k], acc);
+    if (!impact)
+      for (int k = 0; k < NU; ++k) acc = fma(ex[S.e_Z + r + (np + k) * NVF], sdu[k], acc);
+    acc -= ex[S.e_r + r];
+    if (r >= NV) acc = -acc;
+    sdaf[r] = acc;
+    xd[S.x_daf + r] = acc;
+  }
+  if (impact) return;
+  __syncthreads();
+  const double tau = p.tab.fraction_to_boundary;
+  double mp = 1.0, md = 1.0;
+  auto consider = [&](double sl, double dsl, double du, double ddu) {
+    const double fp = -tau * (sl / dsl), fd = -tau * (du / ddu);  // pdipm.hxx:121-142
+    if (fp > 0.0 && fp < 1.0) mp = fmin(mp, fp);
+    if (fd > 0.0 && fd < 1.0) md = fmin(md, fd);
+  };
+  for (int r = tid; r < p.tab.n_box; r += NTHR) {
+    const rbt_box_row br = p.tab.box[r];
+    const double var = br.var == RBT_VAR_Q ? sdx[br.idx] : br.var == RBT_VAR_V ? sdx[NV + br.idx]
+                       : br.var == RBT_VAR_A ? sdaf[br.idx] : sdu[br.idx];
+    const double sl = con[S.c_slack + r], du = con[S.c_dual + r];
+    const double dsl = -br.sign * var - con[S.c_res + r];           // joint_*_limit.cpp:78-82
+    const double ddu = -(du * dsl + con[S.c_cmpl + r]) / sl;        // pdipm.hxx:159-164
+    con[S.c_dslack + r] = dsl;
+    con[S.c_ddual + r] = ddu;
+    consider(sl, dsl, du, ddu);
+  }
+  for (int q = tid; q < 5 * p.tab.n_contacts; q += NTHR) {
+    const int ci = q / 5, r5 = q % 5, r = p.tab.n_box + q;
+    double dsl = 1.0, ddu = 1.0;                                    // friction_cone.cpp:244-245
+    if ((c.contact_mask >> ci) & 1) {
+      const int fstack = 3 * __popc(c.contact_mask & ((1 << ci) - 1));
+      const double* dgdq = lin + S.l_dgdq + size_t(ci) * 5 * NV;
+      const double* dgdf = lin + S.l_dgdf + size_t(ci) * 15;
+      double acc = 0.0;
+      for (int j = 0; j < NV; ++j) acc = fma(dgdq[r5 + j * 5], sdx[j], acc);
+      for (int j = 0; j < 3; ++j) acc = fma(dgdf[r5 + j * 5], sdaf[NV + fstack + j], acc);
+      dsl = -acc - con[S.c_res + r];                                // :253-256
+      ddu = -(con[S.c_dual + r] * dsl + con[S.c_cmpl + r]) / con[S.c_slack + r];
+    }
+    con[S.c_dslack + r] = dsl;
+    con[S.c_ddual + r] = ddu;
+    consider(con[S.c_slack + r], dsl, con[S.c_dual + r], ddu);
+  }
+  mp = warp_min(mp);
+  md = warp_min(md);
+  if ((tid & 31) == 0) {
+    smin[(tid >> 5) * 2] = mp;
+    smin[(tid >> 5) * 2 + 1] = md;
+  }
+  __syncthreads();
+  if (tid == 0) {  // min over the stage, then over the horizon    direct_multiple_shooting.cpp:202-209
+    atomic_min_pos(&p.steps[2 * b], fmin(smin[0], smin[2]));
+    atomic_min_pos(&p.steps[2 * b + 1], fmin(smin[1], smin[3]));
+  }
+}
+
+// free-flyer part of Robot::integrateConfiguration (textbook SE(3) exponential; see oracle/condense_oracle.c)
+__device__ __forceinline__ void integrate_free_flyer_dev(double* q, const double* dq, double step) {
+  const double vx = step * dq[0], vy = step * dq[1], vz = step * dq[2];
+  const double wx = step * dq[3], wy = step * dq[4], wz = step * dq[5];
+  const double th2 = wx * wx + wy * wy + wz * wz, th = sqrt(th2);
+  double bb, cc;
+  if (th < 1e-6) {
+    bb = 0.5 - th2 / 24.0; cc = 1.0 / 6.0 - th2 / 120.0;
+  } else {
+    bb = (1.0 - cos(th)) / th2; cc = (th - sin(th)) / (th2 * th);
+  }
+  const double cx = wy * vz - wz * vy, cy = wz * vx - wx * vz, cz = wx * vy - wy * vx;
+  const double ccx = wy * cz - wz * cy, ccy = wz * cx - wx * cz, ccz = wx * cy - wy * cx;
+  const double tx = vx + bb * cx + cc * ccx, ty = vy + bb * cy + cc * ccy, tz = vz + bb * cz + cc * ccz;
+  const double qx = q[3], qy = q[4], qz = q[5], qw = q[6];
+  const double ux = qy * tz - qz * ty, uy = qz * tx - qx * tz, uz = qx * ty - qy * tx;
+  const double u2x = qy * uz - qz * uy, u2y = qz * ux - qx * uz, u2z = qx * uy - qy * ux;
+  q[0] += tx + 2.0 * (qw * ux + u2x);
+  q[1] += ty + 2.0 * (qw * uy + u2y);
+  q[2] += tz + 2.0 * (qw * uz + u2z);
+  double sh, ch;
+  if (th < 1e-6) { sh = 0.5 - th2 / 48.0; ch = 1.0 - th2 / 8.0; } else { sh = sin(0.5 * th) / th; ch = cos(0.5 * th); }
+  const double ex_ = sh * wx, ey = sh * wy, ez = sh * wz, ew = ch;
+  const double nx_ = qw * ex_ + qx * ew + qy * ez - qz * ey;
+  const double ny = qw * ey - qx * ez + qy * ew + qz * ex_;
+  const double nz = qw * ez + qx * ey - qy * ex_ + qz * ew;
+  const double nw = qw * ew - qx * ex_ - qy * ey - qz * ez;
+  const double nrm = 1.0 / sqrt(nx_ * nx_ + ny * ny + nz * nz + nw * nw);
+  q[3] = nx_ * nrm; q[4] = ny * nrm; q[5] = nz * nrm; q[6] = nw * nrm;
+}
+
+template <int NV, int NU, int NFM>
+__global__ void __launch_bounds__(64) update_kernel(const StageParams p) {
+  constexpr int NX = 2 * NV, NVF = NV + NFM, NTHR = 64;
+  __shared__ double sdx[NX], sdu[NU], slaf[NVF], sdbm[NVF], sdl[NX], sdnup[8];
+  const rbt_layout& K = p.K;
+  const rbt_stage_layout& S = p.S;
+  const int tid = threadIdx.x;
+  const size_t o = blockIdx.x;
+  const int i = int(o % p.n_grid), b = int(o / p.n_grid);
+  const rbt_stage_ctrl c = p.ctrl[i];
+  const bool terminal = (c.type == RBT_TERMINAL), impact = (c.type == RBT_IMPACT);
+  const int nf = terminal ? 0 : c.nf, nvf = NV + nf, np = S.np, ns = (terminal || impact) ? 0 : c.ns;
+  double* ex = p.ex + o * S.e_stride;
+  double* d = p.dir + o * K.d_stride;
+  double* xd = p.xd + o * S.x_stride;
+  double* con = p.con + o * S.c_stride;
+  double* sol = p.sol + o * S.s_stride;
+  const double ap = p.steps[2 * b], ad = p.steps[2 * b + 1];
+  for (int e = tid; e < NX; e += NTHR) {
+    sdx[e] = d[K.d_dx + e];
+    sdl[e] = d[K.d_dlmdgmm + e];
+  }
+  for (int e = tid; e < NU; e += NTHR) sdu[e] = (terminal || impact) ? 0.0 : d[K.d_du + e];
+  __syncthreads();
+  if (!terminal) {
+    const double* dgn = d + K.d_stride + K.d_dlmdgmm + NV;  // dgmm of stage i+1 (never modified by this kernel)
+    const double dt = c.dt;
+    double dts = 0.0;
+    if (!impact && c.ngrids_in_phase > 0) dts = (d[K.d_dts + 1] - d[K.d_dts]) / c.ngrids_in_phase;  // intermediate_stage.cpp:167-170
+    for (int r = tid; r < nvf; r += NTHR) {  // laf += Qafqv dx + Qafu du (+ dt dgmm+ / Phia^T dxi / dts haf)   :191-201
+      double acc = ex[S.e_laf + r];
+      for (int k = 0; k < NX; ++k) acc = fma(ex[S.e_Qafqv + r + k * NVF], sdx[k], acc);
+      if (!impact) {
+        for (int k = 0; k < NU; ++k) acc = fma(ex[S.e_Qafu + r + (np + k) * NVF], sdu[k], acc);
+        if (r < NV) {
+          acc = fma(dt, dgn[r], acc);
+          for (int q = 0; q < ns; ++q) acc = fma(ex[S.e_Phia + q + r * ns], d[K.d_dxi + q], acc);
+        }
+        if (dts < -2.220446049250313e-16 || dts > 2.220446049250313e-16) acc = fma(dts, ex[S.e_haf + r], acc);
+      } else if (r < NV) {
+        acc += dgn[r];                                                               // impact_dynamics.cpp:94
+      }
+      slaf[r] = acc;
+      ex[S.e_laf + r] = acc;
+    }
+    if (!impact && tid < np) {  // dnu_passive            contact_dynamics.cpp:182-190
+      double acc = -ex[S.e_lup + tid];
+      for (int k = 0; k < NU; ++k) acc = fma(-ex[S.e_Quup + tid + k * np], sdu[k], acc);
+      for (int k = 0; k < NX; ++k) acc = fma(-ex[S.e_Qxup + k + tid * NX], sdx[k], acc);
+      for (int k = 0; k < NV; ++k) acc = fma(-dt * ex[S.e_Z + tid + k * NVF], dgn[k], acc);
+      sdnup[tid] = acc;
+      xd[S.x_dnup + tid] = acc;
+    }
+    __syncthreads();
+    for (int r = tid; r < nvf; r += NTHR) {  // dbetamu = -Z laf     :202
+      double acc = 0.0;
+      for (int k = 0; k < nvf; ++k) acc = fma(-ex[S.e_Z + r + k * NVF], slaf[k], acc);
+      sdbm[r] = acc;
+      xd[S.x_dbetamu + r] = acc;
+    }
+  }
+  if (np == 6 && tid < 6) {  // correctCostateDirection     state_equation.cpp:90-95
+    double acc = 0.0;
+    for (int l = 0; l < 6; ++l) acc = fma(ex[S.e_Fqqpi + l + tid * 6], sdl[l], acc);
+    d[K.d_dlmdgmm + tid] = -acc;
+  }
+  __syncthreads();
+  if (np == 6 && tid < 6) sdl[tid] = d[K.d_dlmdgmm + tid];
+  __syncthreads();
+  // ---- SplitSolution::integrate                          split_solution.cpp:58-90
+  if (tid == 0) {
+    if (np == 6) integrate_free_flyer_dev(sol + S.s_q, sdx, ap);
+  }
+  for (int e = tid; e < NV; e += NTHR) {
+    if (np == 6) {
+      if (e >= 6) sol[S.s_q + e + 1] += ap * sdx[e];
+    } else {
+      sol[S.s_q + e] += ap * sdx[e];
+    }
+    sol[S.s_v + e] += ap * sdx[NV + e];
+    sol[S.s_lmd + e] += ap * sdl[e];
+    sol[S.s_gmm + e] += ap * sdl[NV + e];
+    if (!terminal) {
+      const double da = xd[S.x_daf + e];
+      if (!impact) {
+        sol[S.s_a + e] += ap * da;
+        sol[S.s_dv + e] = 0.0;
+      } else {
+        sol[S.s_a + e] = 0.0;
+        sol[S.s_dv + e] += ap * da;
+      }
+      sol[S.s_beta + e] += ap * sdbm[e];
+    }
+  }
+  if (!terminal) {
+    for (int e = tid; e < NU; e += NTHR) sol[S.s_u + e] = impact ? 0.0 : sol[S.s_u + e] + ap * sdu[e];
+    for (int e = tid; e < nf; e += NTHR) {
+      sol[S.s_f + e] += ap * xd[S.x_daf + NV + e];
+      sol[S.s_mu + e] += ap * sdbm[NV + e];
+    }
+    if (!impact) {
+      for (int e = tid; e < np; e += NTHR) sol[S.s_nup + e] += ap * sdnup[e];
+      for (int e = tid; e < ns; e += NTHR) sol[S.s_xi + e] += ap * d[K.d_dxi + e];
+      for (int r = tid; r < S.nc; r += NTHR) {  // updateSlack / updateDual    constraint_component_base.hxx:25-36
+        con[S.c_slack + r] += ap * con[S.c_dslack + r];
+        con[S.c_dual + r] += ad * con[S.c_ddual + r];
+      }
+    }
+  }
+}
+
+}  // namespace rbt

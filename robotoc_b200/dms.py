@@ -1,0 +1,88 @@
+"""Host-side mirror of the part of robotoc::DirectMultipleShooting that is on the hot path
+(/root/reference/include/robotoc/ocp/direct_multiple_shooting.hpp:86-199, src/ocp/direct_multiple_shooting.cpp):
+
+  evalKKT (its "Forms linear system" tail, :129-159 -> intermediate_stage.cpp:133-148)   -> condense()
+  computeStepSizes :174-199, maxPrimalStepSize / maxDualStepSize :202-209                -> computeStepSizes(), max*StepSize()
+  integrateSolution :212-241                                                             -> integrateSolution()
+
+It shares the device buffers (KKT records, direction records) of a RiccatiRecursion handle, so a full hot-path
+iteration is: condense -> backwardRiccatiRecursion -> forwardRiccatiRecursion -> computeStepSizes -> integrateSolution
+without any host round trip.
+"""
+import ctypes
+
+import numpy as np
+
+from .riccati import RiccatiRecursion, _check, _vp
+from .stage import StageDims, StageLayout
+
+LIN, CON, EXP, SOL, XDIR, STEPS = 6, 7, 8, 9, 10, 11
+
+
+class DirectMultipleShooting:
+    def __init__(self, riccati: RiccatiRecursion, sdims: StageDims, table):
+        self.rr = riccati
+        self._lib = riccati._lib
+        self._h = riccati._h
+        self.sdims = sdims
+        self.table = table
+        self.layout = StageLayout(sdims)
+        csd = sdims.c()
+        _check(self._lib.rbt_stage_setup(self._h, ctypes.byref(csd), ctypes.byref(table)), riccati._err,
+               "DirectMultipleShooting")
+
+    def _shape(self, stride):
+        return (self.rr.batch, self.rr.n_grid, stride)
+
+    def _up(self, which, a, stride, stream):
+        if a.shape != self._shape(stride):
+            raise ValueError(f"[DirectMultipleShooting] invalid argument: expected shape {self._shape(stride)}, got {a.shape}")
+        _check(self._lib.rbt_upload(self._h, which, _vp(a), stream), self.rr._err, "DirectMultipleShooting")
+
+    def _down(self, which, shape, stream=None):
+        out = np.empty(shape)
+        _check(self._lib.rbt_download(self._h, which, _vp(out), stream), self.rr._err, "DirectMultipleShooting")
+        self.rr.synchronize(stream)
+        return out
+
+    # -- reference API -----------------------------------------------------------------------------------
+    def condense(self, lin=None, con=None, stream=None):
+        """The condensing tail of evalKKT for every stage of every OCP."""
+        if lin is not None:
+            self._up(LIN, lin, self.layout.l_stride, stream)
+        if con is not None:
+            self._up(CON, con, self.layout.c_stride, stream)
+        _check(self._lib.rbt_condense(self._h, stream), self.rr._err, "DirectMultipleShooting")
+
+    def computeStepSizes(self, stream=None):
+        _check(self._lib.rbt_expand_and_step_sizes(self._h, stream), self.rr._err, "DirectMultipleShooting")
+
+    def _steps(self, stream=None):
+        return self._down(STEPS, (self.rr.batch, 2), stream)
+
+    def maxPrimalStepSize(self, stream=None):
+        return self._steps(stream)[:, 0]
+
+    def maxDualStepSize(self, stream=None):
+        return self._steps(stream)[:, 1]
+
+    def integrateSolution(self, sol=None, stream=None):
+        if sol is not None:
+            self._up(SOL, sol, self.layout.s_stride, stream)
+        _check(self._lib.rbt_update(self._h, stream), self.rr._err, "DirectMultipleShooting")
+
+    # -- data access ---------------------------------------------------------------------------------------
+    def getKKT(self, stream=None):
+        return self._down(0, self._shape(self.rr.layout.k_stride), stream)
+
+    def getExpansionData(self, stream=None):
+        return self._down(EXP, self._shape(self.layout.e_stride), stream)
+
+    def getConstraintData(self, stream=None):
+        return self._down(CON, self._shape(self.layout.c_stride), stream)
+
+    def getSolution(self, stream=None):
+        return self._down(SOL, self._shape(self.layout.s_stride), stream)
+
+    def getExpandedDirection(self, stream=None):
+        return self._down(XDIR, self._shape(self.layout.x_stride), stream)

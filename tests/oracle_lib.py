@@ -39,6 +39,15 @@ def load():
     L.orc_phase_transition_step.argtypes = [pdims, c_dbl, c_vp, c_vp, c_vp, c_int]
     L.orc_phase_transition_step.restype = None
     L.orc_max_threads.restype = c_int
+    from robotoc_b200.stage import rbt_stage_dims, rbt_constraint_table
+    psd, ptab = ctypes.POINTER(rbt_stage_dims), ctypes.POINTER(rbt_constraint_table)
+    L.orc_stage_layout_get.argtypes = [psd, ctypes.c_char_p]
+    L.orc_mjtjinv.argtypes = [c_int, c_int, c_vp, c_vp, c_int, c_vp, c_int]
+    L.orc_condense_batch.argtypes = [psd, ptab, pctrl, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_int]
+    L.orc_expand_batch.argtypes = [psd, ptab, pctrl, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int]
+    L.orc_expand_batch.restype = None
+    L.orc_update_batch.argtypes = [psd, ptab, pctrl, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int]
+    L.orc_update_batch.restype = None
     _lib = L
     return L
 

@@ -1,0 +1,112 @@
+"""GPU parity of the stage layer (rows a10-a16) and of a full hot-path iteration
+condense -> backward -> forward -> step sizes -> update, against the CPU oracle, through the C ABI."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import oracle_lib
+from helpers import rel_err, small_event_schedule, trot_schedule
+from robotoc_b200 import ANYMAL, DirectMultipleShooting, Layout, RiccatiRecursion, StageDims, StageLayout, anymal_constraint_table
+from robotoc_b200.schedule import IMPACT, TERMINAL
+from robotoc_b200.stage import make_stage_inputs
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-8
+
+
+def _oracle_iteration(lib, sd, S, K, table, ctrl, lin, con, sol, dx0):
+    batch, n_grid = lin.shape[0], lin.shape[1]
+    csd = sd.c()
+    kkt = np.zeros((batch, n_grid, K.k_stride))
+    ex = np.zeros((batch, n_grid, S.e_stride))
+    cc, ss = con.copy(), sol.copy()
+    assert lib.orc_condense_batch(ctypes.byref(csd), ctypes.byref(table), ctrl, n_grid, batch, oracle_lib.ptr(lin),
+                                  oracle_lib.ptr(cc), oracle_lib.ptr(kkt), oracle_lib.ptr(ex), 0) == 0
+    cc_after_condense = cc.copy()
+    kk, ric, d, info = oracle_lib.riccati_batch(ANYMAL, K, ctrl, kkt, dx0)
+    assert info == 0
+    xd = np.zeros((batch, n_grid, S.x_stride))
+    steps = np.zeros((batch, 2))
+    lib.orc_expand_batch(ctypes.byref(csd), ctypes.byref(table), ctrl, n_grid, batch, oracle_lib.ptr(lin), oracle_lib.ptr(ex),
+                         oracle_lib.ptr(d), oracle_lib.ptr(cc), oracle_lib.ptr(xd), oracle_lib.ptr(steps), 0)
+    d_before, cc_after_expand, xd_after_expand = d.copy(), cc.copy(), xd.copy()
+    lib.orc_update_batch(ctypes.byref(csd), ctypes.byref(table), ctrl, n_grid, batch, oracle_lib.ptr(ex), oracle_lib.ptr(d),
+                         oracle_lib.ptr(xd), oracle_lib.ptr(cc), oracle_lib.ptr(ss), oracle_lib.ptr(steps), 0)
+    return dict(kkt=kkt, ex0=None, cc_cond=cc_after_condense, ric=ric, d=d_before, cc_exp=cc_after_expand, xd_exp=xd_after_expand,
+                steps=steps, d_upd=d, xd_upd=xd, cc_upd=cc, sol=ss, ex_upd=ex)
+
+
+def _cmp(name, got, ref, tol=TOL):
+    scale = np.max(np.abs(ref))
+    if scale == 0.0:
+        assert np.max(np.abs(got)) == 0.0, f"{name}: expected zeros"
+        return
+    e = np.max(np.abs(got - ref)) / scale
+    assert e < tol, f"{name}: rel err {e:.3e}"
+
+
+def _run(ctrl, batch, seed):
+    lib = oracle_lib.load()
+    table = anymal_constraint_table()
+    sd = StageDims(ANYMAL, nf_max=12, n_contacts=table.n_contacts, n_box=table.n_box)
+    S, K = StageLayout(sd), Layout(ANYMAL)
+    lin, con, sol, dx0 = make_stage_inputs(sd, S, ctrl, batch, seed)
+    ref = _oracle_iteration(lib, sd, S, K, table, ctrl, lin, con, sol, dx0)
+    rr = RiccatiRecursion(ANYMAL, len(ctrl), batch)
+    rr.setTimeDiscretization(ctrl)
+    dms = DirectMultipleShooting(rr, sd, table)
+    dms.condense(lin, con)
+    kkt, cc = dms.getKKT(), dms.getConstraintData()
+    assert int(rr.info().max()) == 0
+    for i, c in enumerate(ctrl):
+        _cmp(f"kkt[{i}]", kkt[:, i], ref["kkt"][:, i])
+        if c.type not in (IMPACT, TERMINAL):
+            for f in ("c_cmpl", "c_cond"):
+                o = getattr(S, f)
+                _cmp(f"{f}[{i}]", cc[:, i, o:o + S.nc], ref["cc_cond"][:, i, o:o + S.nc])
+    rr.backwardRiccatiRecursion()
+    rr.forwardRiccatiRecursion(dx0)
+    d = rr.getDirection()
+    _cmp("direction", d, ref["d"])
+    dms.computeStepSizes()
+    steps = np.stack([dms.maxPrimalStepSize(), dms.maxDualStepSize()], axis=1)
+    _cmp("steps", steps, ref["steps"], 1e-10)
+    xd, cc = dms.getExpandedDirection(), dms.getConstraintData()
+    for i, c in enumerate(ctrl):
+        if c.type == TERMINAL:
+            continue
+        _cmp(f"daf[{i}]", xd[:, i, S.x_daf:S.x_daf + 18 + c.nf], ref["xd_exp"][:, i, S.x_daf:S.x_daf + 18 + c.nf])
+        if c.type != IMPACT:
+            for f in ("c_dslack", "c_ddual"):
+                o = getattr(S, f)
+                _cmp(f"{f}[{i}]", cc[:, i, o:o + S.nc], ref["cc_exp"][:, i, o:o + S.nc])
+    dms.integrateSolution(sol)
+    sol_g, cc, xd, d2 = dms.getSolution(), dms.getConstraintData(), dms.getExpandedDirection(), rr.getDirection()
+    for i, c in enumerate(ctrl):
+        _cmp(f"sol[{i}]", sol_g[:, i], ref["sol"][:, i])
+        _cmp(f"dlmdgmm[{i}]", d2[:, i, K.d_dlmdgmm:K.d_dlmdgmm + 36], ref["d_upd"][:, i, K.d_dlmdgmm:K.d_dlmdgmm + 36])
+        if c.type != TERMINAL:
+            _cmp(f"dbetamu[{i}]", xd[:, i, S.x_dbetamu:S.x_dbetamu + 18 + c.nf], ref["xd_upd"][:, i, S.x_dbetamu:S.x_dbetamu + 18 + c.nf])
+            if c.type != IMPACT:
+                _cmp(f"dnup[{i}]", xd[:, i, S.x_dnup:S.x_dnup + 6], ref["xd_upd"][:, i, S.x_dnup:S.x_dnup + 6])
+                for f in ("c_slack", "c_dual"):
+                    o = getattr(S, f)
+                    _cmp(f"{f}[{i}]", cc[:, i, o:o + S.nc], ref["cc_upd"][:, i, o:o + S.nc])
+    ex = dms.getExpansionData()
+    for i, c in enumerate(ctrl):
+        if c.type != TERMINAL:
+            for f, n in (("e_Z", 900), ("e_R", 1080), ("e_Qafqv", 1080), ("e_r", 30), ("e_laf", 30)):
+                o = getattr(S, f)
+                _cmp(f"{f}[{i}]", ex[:, i, o:o + n], ref["ex_upd"][:, i, o:o + n])
+    rr.close()
+
+
+def test_stage_layer_small_event_schedule():
+    td, ev, ctrl = small_event_schedule(False)
+    _run(ctrl, batch=3, seed=21)
+
+
+def test_stage_layer_trot_n40():
+    td, ev, ctrl = trot_schedule(40)
+    _run(ctrl, batch=2, seed=22)

@@ -1,0 +1,206 @@
+"""Pins oracle/condense_oracle.c (rows a10-a16) by identities that do not reuse its formulas:
+ * MJtJinv == dense inverse of [[M, J^T],[J, 0]]                         (robot.hxx:642-683)
+ * expansion satisfies the linearised contact dynamics it eliminated     (contact_dynamics.cpp:167-174)
+ * the condensed quadratic model == the uncondensed model with (a, f) substituted   (contact_dynamics.cpp:55-128)
+ * PDIPM: box / friction-cone condensing == J^T diag(z/s) J and J^T cond   (joint_*_limit.cpp, friction_cone.cpp:194-235)
+ * fraction-to-boundary keeps slack, dual positive; update == x + alpha dx
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+import oracle_lib
+from helpers import small_event_schedule
+from robotoc_b200 import ANYMAL, Layout
+from robotoc_b200.schedule import IMPACT, TERMINAL, plain_schedule
+from robotoc_b200.stage import (StageDims, StageLayout, anymal_constraint_table, make_stage_inputs, rbt_constraint_table)
+from robotoc_b200.synth import mat
+
+
+def _setup(table, ctrl, batch=2, seed=5):
+    lib = oracle_lib.load()
+    sd = StageDims(ANYMAL, nf_max=12, n_contacts=table.n_contacts, n_box=table.n_box)
+    S = StageLayout(sd, getter=lib.orc_stage_layout_get)
+    K = Layout(ANYMAL, getter=lib.orc_layout_get)
+    lin, con, sol, dx0 = make_stage_inputs(sd, S, ctrl, batch, seed)
+    return lib, sd, S, K, lin, con, sol, dx0
+
+
+def _condense(lib, sd, S, K, table, ctrl, lin, con):
+    batch, n_grid = lin.shape[0], lin.shape[1]
+    kkt = np.zeros((batch, n_grid, K.k_stride))
+    ex = np.zeros((batch, n_grid, S.e_stride))
+    cc = con.copy()
+    csd = sd.c()
+    info = lib.orc_condense_batch(ctypes.byref(csd), ctypes.byref(table), ctrl, n_grid, batch, oracle_lib.ptr(lin),
+                                  oracle_lib.ptr(cc), oracle_lib.ptr(kkt), oracle_lib.ptr(ex), 1)
+    assert info == 0
+    return kkt, ex, cc
+
+
+def test_mjtjinv_is_dense_inverse():
+    lib = oracle_lib.load()
+    rng = np.random.default_rng(0)
+    nv, nf = 18, 12
+    Sm = rng.uniform(-1, 1, (nv, nv))
+    M = np.eye(nv) + 0.1 * Sm @ Sm.T
+    J = rng.uniform(-1, 1, (nf, nv))
+    Z = np.zeros((nv + nf) * (nv + nf))
+    Mc, Jc = np.asfortranarray(M).ravel(order="F").copy(), np.asfortranarray(J).ravel(order="F").copy()
+    assert lib.orc_mjtjinv(nv, nf, oracle_lib.ptr(Mc), oracle_lib.ptr(Jc), nf, oracle_lib.ptr(Z), nv + nf) == 0
+    full = np.block([[M, J.T], [J, np.zeros((nf, nf))]])
+    assert np.allclose(Z.reshape(nv + nf, nv + nf, order="F"), np.linalg.inv(full), rtol=1e-10, atol=1e-12)
+
+
+def test_condensed_model_equals_substituted_model():
+    table = rbt_constraint_table()  # no inequality rows: isolates the dynamics condensing
+    table.barrier, table.fraction_to_boundary = 1e-3, 0.995
+    ctrl = plain_schedule(3, 0.03, 12)
+    lib, sd, S, K, lin, con, sol, dx0 = _setup(table, ctrl)
+    kkt, ex, _ = _condense(lib, sd, S, K, table, ctrl, lin, con)
+    nv, nu, nx, npass, nf, nvfm = 18, 12, 36, 6, 12, 30
+    rng = np.random.default_rng(1)
+    for b in range(2):
+        l, k, e = lin[b, 1], kkt[b, 1], ex[b, 1]
+        M, J = mat(l, S.l_M, nv, nv), mat(l, S.l_J, nf, nv)
+        D, IDC = mat(l, S.l_D, nvfm, nx), l[S.l_IDC:S.l_IDC + nvfm]
+        Qxx0, Quu0 = mat(l, S.l_Qxx, nx, nx), mat(l, S.l_Quu, nu, nu)
+        Qaa, Qff, Qqf = np.diag(l[S.l_Qaa:S.l_Qaa + nv]), mat(l, S.l_Qff, nf, nf), mat(l, S.l_Qqf, nv, nf)
+        lx0, la, lf, lu0 = (l[S.l_lx:S.l_lx + nx], l[S.l_la:S.l_la + nv], l[S.l_lf:S.l_lf + nf], l[S.l_lu:S.l_lu + nu])
+        full_inv = np.linalg.inv(np.block([[M, J.T], [J, np.zeros((nf, nf))]]))
+        Sel = np.zeros((nv + nf, nu))
+        Sel[npass:nv, :] = np.eye(nu)
+
+        def elim(x, u):  # (a, f) from the linearised inverse dynamics + contact constraint
+            ag = full_inv @ (-D @ x + Sel @ u - IDC)
+            return ag[:nv], -ag[nv:]
+
+        def phi(x, u):
+            a, f = elim(x, u)
+            return (0.5 * x @ Qxx0 @ x + 0.5 * a @ Qaa @ a + 0.5 * f @ Qff @ f + x[:nv] @ Qqf @ f + 0.5 * u @ Quu0 @ u
+                    + lx0 @ x + la @ a + lf @ f + lu0 @ u)
+
+        Qxx, Qxu, Quu = mat(k, K.k_Qxx, nx, nx), mat(k, K.k_Qxu, nx, nu), mat(k, K.k_Quu, nu, nu)
+        lx, lu = k[K.k_lx:K.k_lx + nx], k[K.k_lu:K.k_lu + nu]
+
+        def psi(x, u):
+            return 0.5 * x @ Qxx @ x + x @ Qxu @ u + 0.5 * u @ Quu @ u + lx @ x + lu @ u
+
+        for _ in range(4):
+            x0, u0, x1, u1 = rng.uniform(-1, 1, nx), rng.uniform(-1, 1, nu), rng.uniform(-1, 1, nx), rng.uniform(-1, 1, nu)
+            lhs, rhs = phi(x1, u1) - phi(x0, u0), psi(x1, u1) - psi(x0, u0)
+            assert abs(lhs - rhs) < 1e-9 * max(1.0, abs(lhs))
+        # state equation rows produced by condensing: dv+ = dv + dt*da  =>  Fvq, Fvv, Fvu, Fv (contact_dynamics.cpp:130-135)
+        dt = ctrl[1].dt
+        x, u = rng.uniform(-1, 1, nx), rng.uniform(-1, 1, nu)
+        a, _ = elim(x, u)
+        Fxx, Fvu, Fx = mat(k, K.k_Fxx, nx, nx), mat(k, K.k_Fvu, nv, nu), k[K.k_Fx:K.k_Fx + nx]
+        Fv0 = l[S.l_Fx + nv:S.l_Fx + nx]
+        assert np.allclose((Fxx @ x)[nv:] + Fvu @ u + Fx[nv:], x[nv:] + dt * a + Fv0, rtol=1e-10, atol=1e-12)
+
+
+def test_pdipm_condensing_is_JtWJ():
+    table = anymal_constraint_table()
+    td, ev, ctrl = small_event_schedule(False)
+    lib, sd, S, K, lin, con, sol, dx0 = _setup(table, ctrl, batch=1, seed=9)
+    # compare against the same stage condensed WITHOUT inequality rows: the difference must be J^T W J / J^T cond pushed
+    # through the (linear) dynamics condensing.  Checked on Quu / lu, which only the torque limits touch before condensing.
+    empty = rbt_constraint_table()
+    empty.barrier, empty.fraction_to_boundary = table.barrier, table.fraction_to_boundary
+    sd0 = StageDims(ANYMAL, nf_max=12, n_contacts=0, n_box=0)
+    S0 = StageLayout(sd0, getter=lib.orc_stage_layout_get)
+    i = 3  # an Intermediate stage with two feet on the ground
+    assert ctrl[i].type == 0 and ctrl[i].nf == 6
+    kkt, ex, cc = _condense(lib, sd, S, K, table, ctrl, lin, con)
+    slack, dual, res = (con[0, i, S.c_slack:S.c_slack + S.nc], con[0, i, S.c_dual:S.c_dual + S.nc],
+                        con[0, i, S.c_res:S.c_res + S.nc])
+    cmpl = slack * dual - table.barrier
+    cond = (dual * res - cmpl) / slack
+    active = np.ones(S.nc, bool)
+    for ci in range(4):
+        if not (ctrl[i].contact_mask >> ci) & 1:
+            active[72 + 5 * ci:72 + 5 * ci + 5] = False
+    assert np.allclose(cc[0, i, S.c_cmpl:S.c_cmpl + S.nc][active], cmpl[active])
+    assert np.allclose(cc[0, i, S.c_cond:S.c_cond + S.nc][active], cond[active])
+    assert np.all(cc[0, i, S.c_cond:S.c_cond + S.nc][~active] == 0.0)
+    # torque limits rows 48..71: lower (sign -1) then upper (+1) on u[0..11]
+    w = dual / slack
+    dQuu = np.diag(w[48:60] + w[60:72])
+    dlu = -cond[48:60] + cond[60:72]
+    lin0 = np.zeros((1, len(ctrl), S0.l_stride))
+    lin0[..., :min(S0.l_stride, S.l_stride)] = lin[..., :min(S0.l_stride, S.l_stride)]
+    # zero-row table shares the leading sections of the linearization record (dg/dq blocks come last)
+    for f in ("l_M", "l_J", "l_D", "l_IDC", "l_Qaa", "l_Qff", "l_Qqf", "l_Qxx", "l_Quu", "l_lx", "l_la", "l_lf", "l_lu", "l_Fx"):
+        assert getattr(S0, f) == getattr(S, f)
+    lin_mod = lin.copy()
+    Quu_in = mat(lin_mod[0, i], S.l_Quu, 12, 12)
+    Quu_in += dQuu
+    lin_mod[0, i, S.l_lu:S.l_lu + 12] += dlu
+    # strip every other row's effect by zeroing their weights: emulate with a table holding only the torque rows
+    tq = rbt_constraint_table()
+    tq.barrier, tq.fraction_to_boundary, tq.n_contacts = table.barrier, table.fraction_to_boundary, 0
+    tq.n_box = 24
+    for r in range(24):
+        tq.box[r].var, tq.box[r].idx, tq.box[r].sign = 3, r % 12, (-1 if r < 12 else 1)
+    sdq = StageDims(ANYMAL, nf_max=12, n_contacts=0, n_box=24)
+    Sq = StageLayout(sdq, getter=lib.orc_stage_layout_get)
+    linq = np.zeros((1, len(ctrl), Sq.l_stride))
+    linq[..., :Sq.l_dgdq] = lin[..., :Sq.l_dgdq]
+    conq = np.zeros((1, len(ctrl), Sq.c_stride))
+    for name in ("c_slack", "c_dual", "c_res"):
+        conq[0, :, getattr(Sq, name):getattr(Sq, name) + 24] = con[0, :, getattr(S, name) + 48:getattr(S, name) + 72]
+    kq, _, _ = _condense(lib, sdq, Sq, K, tq, ctrl, linq, conq)
+    lin0[..., :S0.l_dgdq] = lin_mod[..., :S0.l_dgdq]
+    k0, _, _ = _condense(lib, sd0, S0, K, empty, ctrl, lin0, np.zeros((1, len(ctrl), S0.c_stride)))
+    assert np.allclose(kq[0, i], k0[0, i], rtol=1e-11, atol=1e-12)
+
+
+def test_expand_update_consistency():
+    table = anymal_constraint_table()
+    td, ev, ctrl = small_event_schedule(False)
+    lib, sd, S, K, lin, con, sol, dx0 = _setup(table, ctrl, batch=2, seed=11)
+    kkt, ex, cc = _condense(lib, sd, S, K, table, ctrl, lin, con)
+    dims = ANYMAL
+    kk, ric, d, info = oracle_lib.riccati_batch(dims, K, ctrl, kkt, dx0)
+    assert info == 0
+    batch, n_grid = 2, len(ctrl)
+    xd = np.zeros((batch, n_grid, S.x_stride))
+    steps = np.zeros((batch, 2))
+    csd = sd.c()
+    lib.orc_expand_batch(ctypes.byref(csd), ctypes.byref(table), ctrl, n_grid, batch, oracle_lib.ptr(lin), oracle_lib.ptr(ex),
+                         oracle_lib.ptr(d), oracle_lib.ptr(cc), oracle_lib.ptr(xd), oracle_lib.ptr(steps), 1)
+    assert np.all(steps > 0) and np.all(steps <= 1)
+    nv, nu, nx, npass, nvfm = 18, 12, 36, 6, 30
+    for b in range(batch):
+        for i in range(n_grid - 1):
+            c = ctrl[i]
+            nf = c.nf
+            l, e = lin[b, i], ex[b, i]
+            M, J = mat(l, S.l_M, nv, nv), mat(l, S.l_J, 12, nv)[:nf]
+            D, IDC = mat(l, S.l_D, nvfm, nx)[:nv + nf], l[S.l_IDC:S.l_IDC + nv + nf]
+            dx, du = d[b, i, K.d_dx:K.d_dx + nx], d[b, i, K.d_du:K.d_du + nu]
+            daf = xd[b, i, S.x_daf:S.x_daf + nv + nf].copy()
+            daf[nv:] *= -1.0  # the reference flips the sign of df after the solve
+            rhs = -D @ dx - IDC
+            if c.type != IMPACT:
+                rhs[npass:nv] += du
+            full = np.block([[M, J.T], [J, np.zeros((nf, nf))]])
+            assert np.allclose(full @ daf, rhs, rtol=1e-9, atol=1e-10)
+    # fraction-to-boundary: the stepped slack / dual stay positive on active rows
+    sl, dsl = cc[..., S.c_slack:S.c_slack + S.nc], cc[..., S.c_dslack:S.c_dslack + S.nc]
+    du_, ddu = cc[..., S.c_dual:S.c_dual + S.nc], cc[..., S.c_ddual:S.c_ddual + S.nc]
+    inter = np.array([c.type not in (IMPACT, TERMINAL) for c in ctrl])
+    for b in range(batch):
+        assert np.all((sl[b] + steps[b, 0] * dsl[b])[inter] > 0)
+        assert np.all((du_[b] + steps[b, 1] * ddu[b])[inter] > 0)
+    sol2, cc2, d2, ex2 = sol.copy(), cc.copy(), d.copy(), ex.copy()
+    lib.orc_update_batch(ctypes.byref(csd), ctypes.byref(table), ctrl, n_grid, batch, oracle_lib.ptr(ex2), oracle_lib.ptr(d2),
+                         oracle_lib.ptr(xd), oracle_lib.ptr(cc2), oracle_lib.ptr(sol2), oracle_lib.ptr(steps), 1)
+    for b in range(batch):
+        a = steps[b, 0]
+        assert np.allclose(sol2[b, :, S.s_v:S.s_v + nv], sol[b, :, S.s_v:S.s_v + nv] + a * d[b, :, K.d_dx + nv:K.d_dx + nx])
+        quat = sol2[b, :, S.s_q + 3:S.s_q + 7]
+        assert np.allclose(np.linalg.norm(quat, axis=1), 1.0)
+        assert np.allclose(sol2[b, :, S.s_q + 7:S.s_q + 19], sol[b, :, S.s_q + 7:S.s_q + 19] + a * d[b, :, K.d_dx + 6:K.d_dx + nv])
+        assert np.allclose(cc2[b][inter][:, S.c_slack:S.c_slack + S.nc], (sl[b] + a * dsl[b])[inter])
