@@ -4,11 +4,13 @@
   python bench.py --gpus N --steps K --warmup W            our arm (one rank per GPU under torchrun for N > 1)
   python bench.py --impl reference --gpus N --steps K ...  the reference's CPU algorithm (oracle port, all host threads)
 
-A "step" is one pass of the hot path over one batch of synthetic, HBM-resident KKT records:
-backward Riccati sweep + forward Riccati sweep for every OCP of the batch (the parity-checked core of
-OCPSolver::updateSolution, /root/reference/src/solver/ocp_solver.cpp:118-123).  Weak scaling: every GPU owns
-`--batch` OCPs (instances are independent); with N > 1 the Newton step is all-gathered once per step over NCCL.
-Prints ONE JSON line (rank 0).  PyTorch is plumbing only (streams, events, pinned memory, torch.distributed).
+A "step" is ONE hot-path SQP iteration for every OCP of the batch, given the stage linearisations
+resident in HBM:  condense (PDIPM + contact/impact dynamics + SE(3) state-equation correction)  ->  backward Riccati
+->  forward Riccati  ->  primal expansion + fraction-to-boundary step sizes  ->  dual expansion + primal/dual update
+(the linear-algebra body of OCPSolver::updateSolution, /root/reference/src/solver/ocp_solver.cpp:118-144).
+Weak scaling: every GPU owns `--batch` OCPs (instances are independent); with N > 1 the Newton step is all-gathered once
+per step over NCCL.  Prints ONE JSON line (rank 0).  PyTorch is plumbing only (streams, events, pinned memory,
+torch.distributed).
 """
 import argparse
 import ctypes
@@ -26,10 +28,12 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np  # noqa: E402
 
 N_HORIZON = 40
-BYTES_PER_STAGE_BWD = (3468 + 1776) * 8      # backward reads 3468 + writes 1776 doubles per standard stage
-BYTES_PER_STAGE_FWD = (3324 + 84) * 8        # forward reads 3324 + writes 84 doubles
-FLOP_PER_STAGE_BWD = 285.7e3                 # SURVEY.md 8(d)
-FLOP_PER_STAGE_FWD = 6.5e3
+# SURVEY.md 8(d) algorithmic figures per standard stage (doubles -> bytes)
+BYTES_PER_STAGE_BWD = (3468 + 1776) * 8      # backward reads 3468 + writes 1776
+BYTES_PER_STAGE_FWD = (3324 + 84) * 8        # forward reads 3324 + writes 84
+BYTES_PER_STAGE_CONDENSE = (2100 + 3600) * 8 + (3468) * 8  # 8(d): condense reads ~2.1k, writes ~3.6k (+ the KKT record when not fused)
+FLOP_PER_STAGE_BWD = 285.7e3
+FLOP_PER_STAGE_CONDENSE = 300e3
 
 
 def parse():
@@ -45,6 +49,7 @@ def parse():
 
 
 def build_problem(batch, seed):
+    """Riccati-only inputs (KKT records) -- used by tools/ and the profiling scripts."""
     from helpers import trot_schedule
     from robotoc_b200 import ANYMAL, Layout
     from robotoc_b200.synth import make_kkt
@@ -53,6 +58,19 @@ def build_problem(batch, seed):
     td, ev, ctrl = trot_schedule(N_HORIZON)
     kkt, dx0 = make_kkt(dims, L, ctrl, batch=batch, seed=seed)
     return dims, L, ctrl, kkt, dx0
+
+
+def build_iteration_problem(batch, seed, getter=None, kgetter=None):
+    from helpers import trot_schedule
+    from robotoc_b200 import ANYMAL, Layout, StageDims, StageLayout, anymal_constraint_table
+    from robotoc_b200.stage import make_stage_inputs
+    table = anymal_constraint_table()
+    sd = StageDims(ANYMAL, nf_max=12, n_contacts=table.n_contacts, n_box=table.n_box)
+    S = StageLayout(sd, getter=getter)
+    K = Layout(ANYMAL, getter=kgetter)
+    td, ev, ctrl = trot_schedule(N_HORIZON)
+    lin, con, sol, dx0 = make_stage_inputs(sd, S, ctrl, batch, seed)
+    return dict(dims=ANYMAL, sd=sd, S=S, K=K, table=table, ctrl=ctrl, lin=lin, con=con, sol=sol, dx0=dx0)
 
 
 def peaks():
@@ -77,28 +95,31 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thr = threading.Thread(target=self._read, daemon=True)
             self.thr.start()
+            time.sleep(0.15)  # let nvidia-smi start sampling before the timed region opens
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def stop(self, t_begin=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.06)
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
-        for r in self.rows:
+        for ts, r in self.rows:
+            if t_begin is not None and ts < t_begin:
+                continue
             f = [x.strip() for x in r.split(",")]
             if len(f) < 6:
                 continue
@@ -114,10 +135,11 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def _oracle_runner(dims, L, ctrl, kkt, dx0):
-    """Returns (lib, cores, run) where run() executes ONE timed pass of the oracle over the batch and returns seconds.
-    The reference mutates its KKT in place, so the input is restored (untimed) before every pass; outputs are
-    preallocated.  Only the C call is timed."""
+def _oracle_runner(pr):
+    """Returns (cores, run): run() executes ONE timed pass of the oracle (CPU restatement of the reference algorithm) over
+    the whole batch -- condense, Riccati backward+forward, step sizes, update -- and returns seconds.  Inputs the algorithm
+    mutates in place are restored (untimed) before every pass; only the C calls are timed.  The thread count is the better
+    of {all logical CPUs, half of them} (hyper-threads hurt this fp64 code)."""
     import ctypes as ct
     import oracle_lib
     lib = oracle_lib.load()
@@ -126,50 +148,72 @@ def _oracle_runner(dims, L, ctrl, kkt, dx0):
         subprocess.run(["make", "-s", "-C", oracle_lib.ORACLE_DIR, "native"], check=True, stdout=subprocess.DEVNULL,
                        stderr=subprocess.DEVNULL)
         nl = ct.CDLL(native)
-        nl.orc_riccati_batch.argtypes = lib.orc_riccati_batch.argtypes
-        nl.orc_max_threads.restype = ct.c_int
+        for fn in ("orc_riccati_batch", "orc_condense_batch", "orc_expand_batch", "orc_update_batch"):
+            getattr(nl, fn).argtypes = getattr(lib, fn).argtypes
+            getattr(nl, fn).restype = getattr(lib, fn).restype
         lib = nl
     except Exception:
         pass
-    cores = int(lib.orc_max_threads())
-    b, n_grid = kkt.shape[0], kkt.shape[1]
-    kk = np.empty_like(kkt)
-    ric = np.zeros((b, n_grid, L.r_stride))
-    d = np.zeros((b, n_grid, L.d_stride))
-    cd = dims.c()
+    ncpu = os.cpu_count() or 1
+    S, K, sd, table, ctrl = pr["S"], pr["K"], pr["sd"], pr["table"], pr["ctrl"]
+    lin, con0, sol0, dx0 = pr["lin"], pr["con"], pr["sol"], pr["dx0"]
+    b, n_grid = lin.shape[0], lin.shape[1]
+    kkt = np.zeros((b, n_grid, K.k_stride))
+    ex = np.zeros((b, n_grid, S.e_stride))
+    ric = np.zeros((b, n_grid, K.r_stride))
+    d = np.zeros((b, n_grid, K.d_stride))
+    xd = np.zeros((b, n_grid, S.x_stride))
+    con, sol = np.empty_like(con0), np.empty_like(sol0)
+    steps = np.zeros((b, 2))
+    csd, cd = sd.c(), pr["dims"].c()
+    P = oracle_lib.ptr
 
-    def run():
-        np.copyto(kk, kkt)
+    def run(nthreads):
+        np.copyto(con, con0)
+        np.copyto(sol, sol0)
         t0 = time.perf_counter()
-        info = lib.orc_riccati_batch(ct.byref(cd), ctrl, n_grid, 0.1, b, oracle_lib.ptr(kk), oracle_lib.ptr(ric),
-                                     oracle_lib.ptr(dx0), oracle_lib.ptr(d), 0)
+        i1 = lib.orc_condense_batch(ct.byref(csd), ct.byref(table), ctrl, n_grid, b, P(lin), P(con), P(kkt), P(ex), nthreads)
+        i2 = lib.orc_riccati_batch(ct.byref(cd), ctrl, n_grid, 0.1, b, P(kkt), P(ric), P(dx0), P(d), nthreads)
+        lib.orc_expand_batch(ct.byref(csd), ct.byref(table), ctrl, n_grid, b, P(lin), P(ex), P(d), P(con), P(xd), P(steps), nthreads)
+        lib.orc_update_batch(ct.byref(csd), ct.byref(table), ctrl, n_grid, b, P(ex), P(d), P(xd), P(con), P(sol), P(steps), nthreads)
         el = time.perf_counter() - t0
-        assert info == 0
+        assert i1 == 0 and i2 == 0
         return el
 
-    return cores, run
+    cands = sorted({ncpu, max(1, ncpu // 2)})
+    best = None
+    for nt in cands:
+        run(nt)
+        t = min(run(nt) for _ in range(2))
+        if best is None or t < best[1]:
+            best = (nt, t)
+    nthreads = best[0]
+    return nthreads, (lambda: run(nthreads))
 
 
-def cpu_leg(dims, L, ctrl, kkt, dx0, min_seconds):
-    """Times the oracle (CPU restatement of the reference algorithm) with all host threads; OCP-iterations/s."""
-    cores, run = _oracle_runner(dims, L, ctrl, kkt, dx0)
-    run()  # warm-up (page faults, thread pool)
+WORKLOAD = "anymal_trot_N40 batch={b}/GPU: full hot-path iteration = condense + riccati backward + riccati forward + step sizes + update"
+
+
+def cpu_leg(pr, min_seconds):
+    cores, run = _oracle_runner(pr)
     n, el = 0, 0.0
     while el < min_seconds:
         el += run()
         n += 1
-    b = kkt.shape[0]
+    b = pr["lin"].shape[0]
     return {"value": b * n / el, "unit": "OCP-iterations/s", "cores": cores, "kind": "port",
-            "sample": f"{n} passes over {b} OCPs (riccati backward+forward; OpenMP over OCP instances, all host threads), "
-                      f"{el:.1f} s of CPU-timed work"}
+            "sample": f"{n} passes over {b} OCPs (same full iteration; OpenMP over OCP instances, {cores} threads = best of "
+                      f"all/half logical CPUs), {el:.1f} s of CPU-timed work"}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    dims, L, ctrl, kkt, dx0 = build_problem(args.batch, 20260927)
-    cores, run = _oracle_runner(dims, L, ctrl, kkt, dx0)
+    import oracle_lib
+    lib = oracle_lib.load()
+    pr = build_iteration_problem(args.batch, 20260927, getter=lib.orc_stage_layout_get, kgetter=lib.orc_layout_get)
+    cores, run = _oracle_runner(pr)
     for _ in range(max(args.warmup, 1)):
         run()
     el = 0.0
@@ -181,9 +225,9 @@ def run_reference(args):
         "value": val, "unit": "OCP-iterations/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"anymal_trot_N40 batch={args.batch} riccati backward+forward", "n_grid": len(ctrl),
+        "config": {"workload": WORKLOAD.format(b=args.batch), "n_grid": len(pr["ctrl"]),
                    "note": "CPU restatement of the reference algorithm (oracle port; Eigen/Pinocchio absent so the reference "
-                           "itself cannot be built), OpenMP over OCP instances on all host threads"},
+                           "itself cannot be built), OpenMP over OCP instances on the host threads"},
         "cpu_baseline": {"value": val, "unit": "OCP-iterations/s", "cores": cores, "kind": "port",
                          "sample": f"{args.steps} passes over {args.batch} OCPs"},
         "e2e": {"value": val, "unit": "OCP-iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -199,8 +243,9 @@ def main():
         return
     import torch
     import torch.distributed as dist
-    from robotoc_b200 import RiccatiRecursion
-    from robotoc_b200.riccati import DIR, KKT
+    from robotoc_b200 import DirectMultipleShooting, RiccatiRecursion
+    from robotoc_b200.riccati import DIR
+    from robotoc_b200.shard import allgather_step
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -210,34 +255,52 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    dims, L, ctrl, kkt, dx0 = build_problem(args.batch, 20260927 + rank)
+    pr = build_iteration_problem(args.batch, 20260927 + rank)
+    dims, S, K, ctrl = pr["dims"], pr["S"], pr["K"], pr["ctrl"]
+    lin, con, sol, dx0 = pr["lin"], pr["con"], pr["sol"], pr["dx0"]
     n_grid = len(ctrl)
     rr = RiccatiRecursion(dims, n_grid, args.batch, device=local)
     rr.setTimeDiscretization(ctrl)
+    dms = DirectMultipleShooting(rr, pr["sd"], pr["table"])
     stream = torch.cuda.current_stream()
     sp = ctypes.c_void_p(stream.cuda_stream)
+    lib = rr._lib
 
     # the Newton step lives in a torch tensor so NCCL can gather it in place
-    d_local = torch.zeros((args.batch, n_grid, L.d_stride), dtype=torch.float64, device="cuda")
+    d_local = torch.zeros((args.batch, n_grid, K.d_stride), dtype=torch.float64, device="cuda")
     rr.bind_buffer(DIR, ctypes.c_void_p(d_local.data_ptr()))
-    d_all = torch.empty((world * args.batch, n_grid, L.d_stride), dtype=torch.float64, device="cuda") if world > 1 else None
+    d_all = torch.empty((world * args.batch, n_grid, K.d_stride), dtype=torch.float64, device="cuda") if world > 1 else None
 
-    # ---- device-resident arm: upload once, time K steps
-    rr.backwardRiccatiRecursion(kkt, stream=sp)   # uploads kkt
-    rr.forwardRiccatiRecursion(dx0, stream=sp)    # uploads dx0
+    # ---- device-resident arm: upload once; every step re-reads the same linearisation / PDIPM / solution records
+    dms.condense(lin, con, stream=sp)
+    rr.backwardRiccatiRecursion(stream=sp)
+    rr.forwardRiccatiRecursion(dx0, stream=sp)
+    dms.computeStepSizes(stream=sp)
+    dms.integrateSolution(sol, stream=sp)
     torch.cuda.synchronize()
+    # the update mutates slack/dual and the solution in place: keep pristine copies and restore them every step (D2D)
+    con_dev0, sol_dev0 = torch.from_numpy(con).cuda(), torch.from_numpy(sol).cuda()
+    con_work, sol_work = con_dev0.clone(), sol_dev0.clone()
+    rr.bind_buffer(7, ctypes.c_void_p(con_work.data_ptr()))
+    rr.bind_buffer(9, ctypes.c_void_p(sol_work.data_ptr()))
+
+    NAMES = ["condense", "riccati_backward", "riccati_forward", "expand_step_sizes", "update"]
 
     def step(ev=None):
+        # restore the records the iteration mutates (D2D, outside the per-kernel event pairs but inside the step time)
+        con_work.copy_(con_dev0)
+        sol_work.copy_(sol_dev0)
+        calls = [lambda: dms.condense(stream=sp), lambda: rr.backwardRiccatiRecursion(stream=sp),
+                 lambda: rr.forwardRiccatiRecursion(stream=sp), lambda: dms.computeStepSizes(stream=sp),
+                 lambda: dms.integrateSolution(stream=sp)]
+        for k, call in enumerate(calls):
+            if ev is not None:
+                ev[k].record(stream)
+            call()
         if ev is not None:
-            ev[0].record(stream)
-        rr.backwardRiccatiRecursion(stream=sp)
-        if ev is not None:
-            ev[1].record(stream)
-        rr.forwardRiccatiRecursion(stream=sp)
-        if ev is not None:
-            ev[2].record(stream)
+            ev[len(calls)].record(stream)
         if world > 1:
-            dist.all_gather_into_tensor(d_all.view(-1), d_local.view(-1))
+            allgather_step(d_local, out=d_all)
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -246,11 +309,12 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
     l0 = rr.launch_count()
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(args.steps)]
     t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     clk = ClockSampler(local)
     if rank == 0:
         clk.start()
+    t_host0 = time.perf_counter()
     t_beg.record(stream)
     for k in range(args.steps):
         step(evs[k])
@@ -259,26 +323,28 @@ def main():
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    clocks = clk.stop() if rank == 0 else None
+    clocks = clk.stop(t_host0) if rank == 0 else None
     launches = rr.launch_count() - l0
     ms = t_beg.elapsed_time(t_end)
-    bwd_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
-    fwd_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
+    kms = {n: float(np.mean([e[k].elapsed_time(e[k + 1]) for e in evs])) for k, n in enumerate(NAMES)}
     if world > 1:
         tt = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms = float(tt.item())
     assert int(rr.info().max()) == 0, "Cholesky failure flagged on device"
+    sol_dev = dms.getSolution()
+    steps_dev = np.stack([dms.maxPrimalStepSize(), dms.maxDualStepSize()], axis=1)
 
     # ---- end-to-end arm: host (pinned) buffers through the one-call C-ABI entry point, H2D + D2H inside the timed region
-    kkt_pin = torch.from_numpy(kkt).pin_memory()
-    dx0_pin = torch.from_numpy(dx0).pin_memory()
-    dir_pin = torch.empty((args.batch, n_grid, L.d_stride), dtype=torch.float64).pin_memory()
-    lib = rr._lib
+    pin = lambda a: torch.from_numpy(a).pin_memory()  # noqa: E731
+    lin_p, con_p, sol_p, dx0_p = pin(lin), pin(con), pin(sol), pin(dx0)
+    sol_o = torch.empty(sol.shape, dtype=torch.float64).pin_memory()
+    con_o = torch.empty(con.shape, dtype=torch.float64).pin_memory()
+    steps_o = torch.empty((args.batch, 2), dtype=torch.float64).pin_memory()
+    P = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
 
     def e2e_step():
-        rc = lib.rbt_riccati_solve_host(rr._h, ctypes.c_void_p(kkt_pin.data_ptr()), ctypes.c_void_p(dx0_pin.data_ptr()),
-                                        None, ctypes.c_void_p(dir_pin.data_ptr()), sp)
+        rc = lib.rbt_iteration_host(rr._h, P(lin_p), P(con_p), P(sol_p), P(dx0_p), P(sol_o), P(con_o), P(steps_o), sp)
         assert rc == 0, rr._err()
 
     e2e_step()
@@ -296,39 +362,48 @@ def main():
         tt = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_ms = float(tt.item())
-    h2d = int(lib.rbt_upload_bytes(rr._h, KKT)) + dx0.nbytes
-    d2h = dir_pin.numel() * 8
-    # the D2H result equals the device-resident result
-    assert np.array_equal(dir_pin.numpy(), d_local.cpu().numpy()), "e2e path disagrees with the device-resident path"
+    h2d = lin.nbytes + con.nbytes + sol.nbytes + dx0.nbytes
+    d2h = sol.nbytes + con.nbytes + steps_o.numel() * 8
+    assert np.array_equal(sol_o.numpy(), sol_dev) and np.array_equal(steps_o.numpy(), steps_dev), \
+        "e2e path disagrees with the device-resident path"
 
     if rank == 0:
         peak, peak_src = peaks()
         units = args.batch * N_HORIZON                       # standard stages per launch
-        ach = BYTES_PER_STAGE_BWD * units / (bwd_ms * 1e-3) / 1e9
+        dom = max(kms, key=kms.get)
+        alg_bytes = {"riccati_backward": BYTES_PER_STAGE_BWD, "riccati_forward": BYTES_PER_STAGE_FWD,
+                     "condense": BYTES_PER_STAGE_CONDENSE}.get(dom, BYTES_PER_STAGE_BWD) * units
+        ach = alg_bytes / (kms[dom] * 1e-3) / 1e9
+        kname = {"riccati_backward": "riccati_backward_kernel<18,12,12>", "condense": "condense_kernel<18,12,12>",
+                 "riccati_forward": "riccati_forward_kernel<18,12,12>"}.get(dom, dom)
         line = {
             "metric": "SQP-iterations/s (ANYmal N=40, batch=1024) at 1/2/4/8 B200 vs CPU ref",
             "value": world * args.batch * args.steps / (ms * 1e-3), "unit": "OCP-iterations/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"anymal_trot_N40 batch={args.batch}/GPU: riccati backward + forward"
-                                   + (" + NCCL all-gather of the step" if world > 1 else ""),
-                       "n_grid": n_grid, "dims": "nv18 nu12 nx36", "parallelism": f"batch-sharded x{world}",
-                       "l2": f"per-step inputs {kkt.nbytes / 1e9:.2f} GB + outputs {rr.buf_doubles(1) * 8 / 1e9:.2f} GB >> 126 MB L2 "
-                             "(no flush needed)"},
+            "config": {"workload": WORKLOAD.format(b=args.batch) + (" + NCCL all-gather of the step" if world > 1 else ""),
+                       "n_grid": n_grid, "dims": "nv18 nu12 nx36, 92 inequality rows/stage", "parallelism": f"batch-sharded x{world}",
+                       "l2": f"per-step working set {(lin.nbytes + rr.buf_doubles(0) * 8 + rr.buf_doubles(1) * 8) / 1e9:.2f} GB "
+                             ">> 126 MB L2 (inputs larger than L2; no flush needed)"},
             "clocks": clocks, "gpu_launches": int(launches),
-            "kernels_ms": {"riccati_backward": bwd_ms, "riccati_forward": fwd_ms},
+            "kernels_ms": kms,
+            "riccati_only": {"value": world * args.batch / ((kms["riccati_backward"] + kms["riccati_forward"]) * 1e-3),
+                             "unit": "OCP-iterations/s", "note": "backward + forward sweeps only (the parity-checked core, 8d)"},
             "e2e": {"value": world * args.batch * args.e2e_steps / (e2e_ms * 1e-3), "unit": "OCP-iterations/s",
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,
-                    "api": "rbt_riccati_solve_host (pinned host KKT in, Newton direction out)"},
-            "roofline": {"bound": "hbm", "kernel": "riccati_backward_kernel<18,12,12>", "achieved": ach, "peak": peak,
-                         "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": BYTES_PER_STAGE_BWD * units,
-                         "fp64_tflops": FLOP_PER_STAGE_BWD * units / (bwd_ms * 1e-3) / 1e12,
-                         "fp64_peak_tflops": 37.1,
-                         "forward": {"achieved": BYTES_PER_STAGE_FWD * units / (fwd_ms * 1e-3) / 1e9, "unit": "GB/s"}},
+                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": args.e2e_steps,
+                    "api": "rbt_iteration_host (pinned host linearisation/PDIPM/solution in; solution, slack/dual, step sizes out)"},
+            "roofline": {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                         "per_kernel_GBps": {
+                             "riccati_backward": BYTES_PER_STAGE_BWD * units / (kms["riccati_backward"] * 1e-3) / 1e9,
+                             "riccati_forward": BYTES_PER_STAGE_FWD * units / (kms["riccati_forward"] * 1e-3) / 1e9,
+                             "condense": BYTES_PER_STAGE_CONDENSE * units / (kms["condense"] * 1e-3) / 1e9},
+                         "fp64_tflops": {"riccati_backward": FLOP_PER_STAGE_BWD * units / (kms["riccati_backward"] * 1e-3) / 1e12,
+                                         "condense": FLOP_PER_STAGE_CONDENSE * units / (kms["condense"] * 1e-3) / 1e12},
+                         "fp64_peak_tflops": 37.1},
         }
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_leg(dims, L, ctrl, kkt, dx0, min_seconds=10.0)
+            line["cpu_baseline"] = cpu_leg(pr, min_seconds=10.0)
         print(json.dumps(line), flush=True)
     rr.close()
     if world > 1:

@@ -124,6 +124,12 @@ int rbt_expand_and_step_sizes(rbt_handle* h, void* stream);
  * expandDual, correctCostateDirection, SplitSolution::integrate, updateSlack / updateDual. */
 int rbt_update(rbt_handle* h, void* stream);
 
+/* One hot-path iteration with HOST buffers -- the linear-algebra body of OCPSolver::updateSolution
+ * (src/solver/ocp_solver.cpp:118-144) given the stage linearisations: upload lin / con / sol / dx0, condense, backward and
+ * forward Riccati, step sizes, update, download the updated solution, the PDIPM data and the step sizes (NULL = skip). */
+int rbt_iteration_host(rbt_handle* h, const double* lin_host, const double* con_host, const double* sol_host,
+                       const double* dx0_host, double* sol_out, double* con_out, double* steps_out, void* stream);
+
 int rbt_sync(rbt_handle* h, void* stream);
 const char* rbt_last_error(rbt_handle* h);
 /* number of kernel launches issued by this handle since creation (bench.py's gpu_launches) */

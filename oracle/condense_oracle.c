@@ -19,18 +19,43 @@
 
 #define IDX(i, j, ld) ((i) + (size_t)(j) * (ld))
 
-static void gemm(int ta, int tb, int m, int n, int k, double alpha, const double* A, int lda, const double* B, int ldb,
-                 double beta, double* C, int ldc) {
-  for (int j = 0; j < n; ++j)
-    for (int i = 0; i < m; ++i) {
-      double acc = 0.0;
-      for (int l = 0; l < k; ++l) {
-        const double a = ta ? A[IDX(l, i, lda)] : A[IDX(i, l, lda)];
-        const double b = tb ? B[IDX(j, l, ldb)] : B[IDX(l, j, ldb)];
-        acc += a * b;
+/* same loop forms as oracle/riccati_oracle.c: column axpy for op(A)=A, simd dot products for op(A)=A^T (gcc vectorises both) */
+static void gemm(int ta, int tb, int m, int n, int k, double alpha, const double* restrict A, int lda,
+                 const double* restrict B, int ldb, double beta, double* restrict C, int ldc) {
+  if (!ta) {
+    for (int j = 0; j < n; ++j) {
+      double* restrict c = C + (size_t)j * ldc;
+      if (beta == 0.0) {
+        for (int i = 0; i < m; ++i) c[i] = 0.0;
+      } else if (beta != 1.0) {
+        for (int i = 0; i < m; ++i) c[i] *= beta;
       }
-      C[IDX(i, j, ldc)] = (beta == 0.0 ? 0.0 : beta * C[IDX(i, j, ldc)]) + alpha * acc;
+      for (int l = 0; l < k; ++l) {
+        const double b = alpha * (tb ? B[IDX(j, l, ldb)] : B[IDX(l, j, ldb)]);
+        const double* restrict a = A + (size_t)l * lda;
+#pragma omp simd
+        for (int i = 0; i < m; ++i) c[i] += a[i] * b;
+      }
     }
+  } else if (!tb) {
+    for (int j = 0; j < n; ++j) {
+      const double* restrict b = B + (size_t)j * ldb;
+      for (int i = 0; i < m; ++i) {
+        const double* restrict a = A + (size_t)i * lda;
+        double acc = 0.0;
+#pragma omp simd reduction(+ : acc)
+        for (int l = 0; l < k; ++l) acc += a[l] * b[l];
+        C[IDX(i, j, ldc)] = (beta == 0.0 ? 0.0 : beta * C[IDX(i, j, ldc)]) + alpha * acc;
+      }
+    }
+  } else {
+    for (int j = 0; j < n; ++j)
+      for (int i = 0; i < m; ++i) {
+        double acc = 0.0;
+        for (int l = 0; l < k; ++l) acc += A[IDX(l, i, lda)] * B[IDX(j, l, ldb)];
+        C[IDX(i, j, ldc)] = (beta == 0.0 ? 0.0 : beta * C[IDX(i, j, ldc)]) + alpha * acc;
+      }
+  }
 }
 
 static int chol_lower(int n, double* A, int lda) {
@@ -505,11 +530,11 @@ static void integrate_free_flyer(double* q, const double* dq, double step) {
   const double vx = step * dq[0], vy = step * dq[1], vz = step * dq[2];
   const double wx = step * dq[3], wy = step * dq[4], wz = step * dq[5];
   const double th2 = wx * wx + wy * wy + wz * wz, th = sqrt(th2);
-  double a, b, cc; /* sin(th)/th, (1-cos th)/th^2, (th - sin th)/th^3 */
+  double b, cc; /* (1-cos th)/th^2, (th - sin th)/th^3 */
   if (th < 1e-6) {
-    a = 1.0 - th2 / 6.0; b = 0.5 - th2 / 24.0; cc = 1.0 / 6.0 - th2 / 120.0;
+    b = 0.5 - th2 / 24.0; cc = 1.0 / 6.0 - th2 / 120.0;
   } else {
-    a = sin(th) / th; b = (1.0 - cos(th)) / th2; cc = (th - sin(th)) / (th2 * th);
+    b = (1.0 - cos(th)) / th2; cc = (th - sin(th)) / (th2 * th);
   }
   /* t = V v,  V = I + b [w]x + cc [w]x^2 */
   const double cx = wy * vz - wz * vy, cy = wz * vx - wx * vz, cz = wx * vy - wy * vx;

@@ -45,13 +45,14 @@ struct rbt_handle {
   rbt_stage_ctrl* d_ctrl = nullptr;
   std::vector<rbt_stage_ctrl> ctrl;  // host copy
   double *d_kkt = nullptr, *d_ric = nullptr, *d_fact = nullptr, *d_dir = nullptr, *d_dx0 = nullptr;
-  double* own[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // the handle's own allocations (freed in destroy)
+  double* own[12] = {};  // the handle's own allocation of a buffer that the caller re-bound (freed in destroy)
   int* d_info = nullptr;
   int* d_arrivals = nullptr;  // per-SM CTA arrival counters (CTA de-phasing in the backward kernel)
   int stagger_ns = 0;
   long long* d_timeline = nullptr;  // bring-up instrumentation (RBT_TIMELINE_CTA)
   // stage layer
   bool stage_ready = false;
+  bool keep_info = false;  // condense's Cholesky flags survive the following backward launch
   rbt_stage_dims sdims;
   rbt_stage_layout S;
   rbt_constraint_table table;
@@ -147,27 +148,22 @@ int rbt_create(const rbt_dims* dims, int n_grid_max, int batch, int device, rbt_
   RBT_CUDA(h, cudaMemset(h->d_fact, 0, per * h->L.f_stride * 8));
   RBT_CUDA(h, cudaMemset(h->d_dir, 0, per * h->L.d_stride * 8));
   RBT_CUDA(h, cudaMemset(h->d_info, 0, size_t(batch) * sizeof(int)));
-  h->own[RBT_BUF_KKT] = h->d_kkt;
-  h->own[RBT_BUF_RIC] = h->d_ric;
-  h->own[RBT_BUF_FACT] = h->d_fact;
-  h->own[RBT_BUF_DIR] = h->d_dir;
-  h->own[RBT_BUF_DX0] = h->d_dx0;
   return RBT_OK;
 }
+
+static double** buf_slot(rbt_handle* h, int which);
 
 int rbt_destroy(rbt_handle* h) {
   if (!h) return RBT_ERR_ARG;
   cudaSetDevice(h->device);
   cudaFree(h->d_ctrl);
-  for (int q = 0; q < 5; ++q) cudaFree(h->own[q]);
+  for (int q = 0; q <= RBT_BUF_XDIR; ++q) {
+    double** slot = buf_slot(h, q);
+    if (slot) cudaFree(h->own[q] ? h->own[q] : *slot);  // never free a caller-owned buffer
+  }
   cudaFree(h->d_info);
   cudaFree(h->d_arrivals);
   cudaFree(h->d_timeline);
-  cudaFree(h->d_lin);
-  cudaFree(h->d_con);
-  cudaFree(h->d_ex);
-  cudaFree(h->d_sol);
-  cudaFree(h->d_xd);
   cudaFree(h->d_steps);
   cudaFree(h->d_ones);
   delete h;
@@ -243,20 +239,33 @@ long long rbt_buf_doubles(rbt_handle* h, int which) {
 
 double* rbt_dev_ptr(rbt_handle* h, int which) { return h ? buf_ptr(h, which) : nullptr; }
 
+static double** buf_slot(rbt_handle* h, int which) {
+  switch (which) {
+    case RBT_BUF_KKT: return &h->d_kkt;
+    case RBT_BUF_RIC: return &h->d_ric;
+    case RBT_BUF_FACT: return &h->d_fact;
+    case RBT_BUF_DIR: return &h->d_dir;
+    case RBT_BUF_DX0: return &h->d_dx0;
+    case RBT_BUF_LIN: return &h->d_lin;
+    case RBT_BUF_CON: return &h->d_con;
+    case RBT_BUF_EXP: return &h->d_ex;
+    case RBT_BUF_SOL: return &h->d_sol;
+    case RBT_BUF_XDIR: return &h->d_xd;
+    default: return nullptr;
+  }
+}
+
 int rbt_bind_buffer(rbt_handle* h, int which, double* dev) {
-  if (!h || which < RBT_BUF_KKT || which > RBT_BUF_DX0) return RBT_ERR_ARG;
+  if (!h) return RBT_ERR_ARG;
+  double** slot = buf_slot(h, which);
+  if (!slot || (which >= RBT_BUF_LIN && !h->stage_ready)) return RBT_ERR_ARG;
+  if (!h->own[which]) h->own[which] = *slot;  // remember the handle's own allocation the first time it is replaced
   double* q = dev ? dev : h->own[which];
   if ((reinterpret_cast<uintptr_t>(q) & 15u) != 0) {
     h->err = "[rbt_bind_buffer] invalid argument: device buffer must be 16-byte aligned";
     return RBT_ERR_ARG;
   }
-  switch (which) {
-    case RBT_BUF_KKT: h->d_kkt = q; break;
-    case RBT_BUF_RIC: h->d_ric = q; break;
-    case RBT_BUF_FACT: h->d_fact = q; break;
-    case RBT_BUF_DIR: h->d_dir = q; break;
-    default: h->d_dx0 = q; break;
-  }
+  *slot = q;
   return RBT_OK;
 }
 
@@ -366,7 +375,8 @@ static int launch_backward(rbt_handle* h, int write_fact, cudaStream_t st) {
   p.stagger_ns = h->stagger_ns;
   p.timeline = h->d_timeline;
   p.timeline_cta = h->timeline_cta;
-  RBT_CUDA(h, cudaMemsetAsync(h->d_info, 0, size_t(h->batch) * sizeof(int), st));
+  if (!h->keep_info) RBT_CUDA(h, cudaMemsetAsync(h->d_info, 0, size_t(h->batch) * sizeof(int), st));
+  h->keep_info = false;
   if (h->stagger_ns > 0) RBT_CUDA(h, cudaMemsetAsync(h->d_arrivals, 0, 1024 * sizeof(int), st));
   kern<<<h->batch, C::NTHREADS, C::SMEM_BYTES, st>>>(p);
   RBT_CUDA(h, cudaGetLastError());
@@ -515,6 +525,7 @@ int rbt_condense(rbt_handle* h, void* stream) {
   kern<<<h->batch * h->n_grid, C::NTHREADS, C::SMEM_BYTES, st>>>(make_stage_params(h));
   RBT_CUDA(h, cudaGetLastError());
   h->launches += 1;
+  h->keep_info = true;
   return RBT_OK;
 }
 
@@ -533,6 +544,25 @@ int rbt_update(rbt_handle* h, void* stream) {
   rbt::update_kernel<18, 12, 12><<<h->batch * h->n_grid, 64, 0, (cudaStream_t)stream>>>(make_stage_params(h));
   RBT_CUDA(h, cudaGetLastError());
   h->launches += 1;
+  return RBT_OK;
+}
+
+int rbt_iteration_host(rbt_handle* h, const double* lin_host, const double* con_host, const double* sol_host,
+                       const double* dx0_host, double* sol_out, double* con_out, double* steps_out, void* stream) {
+  if (!h || !lin_host || !con_host || !sol_host || !dx0_host) return RBT_ERR_ARG;
+  int rc;
+  if ((rc = rbt_upload(h, RBT_BUF_LIN, lin_host, stream))) return rc;
+  if ((rc = rbt_upload(h, RBT_BUF_CON, con_host, stream))) return rc;
+  if ((rc = rbt_upload(h, RBT_BUF_SOL, sol_host, stream))) return rc;
+  if ((rc = rbt_upload(h, RBT_BUF_DX0, dx0_host, stream))) return rc;
+  if ((rc = rbt_condense(h, stream))) return rc;
+  if ((rc = rbt_riccati_backward(h, 0, stream))) return rc;
+  if ((rc = rbt_riccati_forward(h, stream))) return rc;
+  if ((rc = rbt_expand_and_step_sizes(h, stream))) return rc;
+  if ((rc = rbt_update(h, stream))) return rc;
+  if (sol_out && (rc = rbt_download(h, RBT_BUF_SOL, sol_out, stream))) return rc;
+  if (con_out && (rc = rbt_download(h, RBT_BUF_CON, con_out, stream))) return rc;
+  if (steps_out && (rc = rbt_download(h, RBT_BUF_STEPS, steps_out, stream))) return rc;
   return RBT_OK;
 }
 

@@ -192,20 +192,35 @@ __global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS) condense_kerne
   // ---- PDIPM condensing (Intermediate / Lift)
   if (!impact) {
     const double mu = p.tab.barrier;
+    // pass 1: per-row complementarity and condensing coefficient (pdipm.hxx:27-100)
     for (int r = tid; r < p.tab.n_box; r += NTHR) {
-      const rbt_box_row br = p.tab.box[r];
       const double sl = con[S.c_slack + r], du = con[S.c_dual + r];
       const double cm = sl * du - mu;
-      const double cd = (du * con[S.c_res + r] - cm) / sl;
       con[S.c_cmpl + r] = cm;
-      con[S.c_cond + r] = cd;
-      const double w = du / sl;
-      // rows never share a (var, idx, sign) triple, but a lower and an upper limit share the diagonal entry: atomics on shared
-      switch (br.var) {
-        case RBT_VAR_Q: atomicAdd(&sQxx[br.idx + br.idx * NX], w); atomicAdd(&vlx[br.idx], br.sign * cd); break;
-        case RBT_VAR_V: atomicAdd(&sQxx[(NV + br.idx) * (NX + 1)], w); atomicAdd(&vlx[NV + br.idx], br.sign * cd); break;
-        case RBT_VAR_A: atomicAdd(&vQaa[br.idx], w); atomicAdd(&vla[br.idx], br.sign * cd); break;
-        default: atomicAdd(&kkt[K.k_Quu + br.idx * (NU + 1)], w); atomicAdd(&vlu[br.idx], br.sign * cd); break;
+      con[S.c_cond + r] = (du * con[S.c_res + r] - cm) / sl;
+    }
+    __syncthreads();
+    // pass 2: one thread per target entry (var, idx) gathers its rows IN ROW ORDER -- deterministic, unlike atomics
+    // (a lower and an upper limit hit the same diagonal entry)            joint_*_limit.cpp:68-75
+    for (int tgt = tid; tgt < 3 * NV + NU; tgt += NTHR) {
+      const int var = tgt < 3 * NV ? tgt / NV : RBT_VAR_U, idx = tgt < 3 * NV ? tgt % NV : tgt - 3 * NV;
+      double w = 0.0, gsum = 0.0;
+      bool any = false;
+      for (int r = 0; r < p.tab.n_box; ++r) {
+        const rbt_box_row br = p.tab.box[r];
+        if (br.var == var && br.idx == idx) {
+          w += con[S.c_dual + r] / con[S.c_slack + r];
+          gsum += br.sign * con[S.c_cond + r];
+          any = true;
+        }
+      }
+      if (any) {
+        switch (var) {
+          case RBT_VAR_Q: sQxx[idx + idx * NX] += w; vlx[idx] += gsum; break;
+          case RBT_VAR_V: sQxx[(NV + idx) * (NX + 1)] += w; vlx[NV + idx] += gsum; break;
+          case RBT_VAR_A: vQaa[idx] += w; vla[idx] += gsum; break;
+          default: kkt[K.k_Quu + idx * (NU + 1)] += w; vlu[idx] += gsum; break;
+        }
       }
     }
     __syncthreads();
