@@ -522,9 +522,11 @@ int rbt_condense(rbt_handle* h, void* stream) {
   }
   cudaStream_t st = (cudaStream_t)stream;
   RBT_CUDA(h, cudaMemsetAsync(h->d_info, 0, size_t(h->batch) * sizeof(int), st));
-  kern<<<h->batch * h->n_grid, C::NTHREADS, C::SMEM_BYTES, st>>>(make_stage_params(h));
+  rbt::mjtjinv_kernel<18, 12><<<h->batch * h->n_grid, 64, 0, st>>>(make_stage_params(h));  // K1: Z = [[M,J^T],[J,0]]^-1
   RBT_CUDA(h, cudaGetLastError());
-  h->launches += 1;
+  kern<<<h->batch * h->n_grid, C::NTHREADS, C::SMEM_BYTES, st>>>(make_stage_params(h));     // K2: condensing (DMMA)
+  RBT_CUDA(h, cudaGetLastError());
+  h->launches += 2;
   h->keep_info = true;
   return RBT_OK;
 }

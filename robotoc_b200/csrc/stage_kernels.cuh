@@ -83,43 +83,162 @@ __device__ __forceinline__ void se3_jac_inverse_dev(const double* Jac, double* J
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// K1: Z = [[M, J^T],[J, 0]]^-1  (Robot::computeMJtJinv, include/robotoc/robot/robot.hxx:642-683, dense restatement)
+// Pure dependency chains (two Choleskys, two triangular inverses): 64 threads and 16 KB of shared memory per stage, so
+// ~12 stages per SM are in flight and hide each other's fp64 latency.  Writes the full (zero-padded) Z into the
+// expansion record; condense_kernel (K2) reads it back from L2.
+template <int NV, int NFM>
+__global__ void __launch_bounds__(64) mjtjinv_kernel(const StageParams p) {
+  constexpr int NVF = NV + NFM, NTHR = 64;
+  __shared__ double sM[NV * NV], sLi[NV * NV], sMi[NV * NV], sJ[NFM * NV], sJMi[NFM * NV], sS[NFM * NFM], sSl[NFM * NFM],
+      sSi[NFM * NFM], sTR[NV * NFM], sdinv[32];
+  const rbt_stage_layout& S = p.S;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const size_t o = blockIdx.x;
+  const int i = int(o % p.n_grid), b = int(o / p.n_grid);
+  const rbt_stage_ctrl c = p.ctrl[i];
+  if (c.type == RBT_TERMINAL) return;
+  const int nf = c.nf;
+  const double* lin = p.lin + o * S.l_stride;
+  double* Z = p.ex + o * S.e_stride + S.e_Z;
+  int bad = 0;
+  for (int e = tid; e < NV * NV; e += NTHR) sM[e] = lin[S.l_M + e];
+  for (int e = tid; e < NFM * NV; e += NTHR) sJ[e] = ((e % NFM) < nf) ? lin[S.l_J + e] : 0.0;
+  __syncthreads();
+  if (warp == 0) {
+    if (!warp_cholesky<NV>(sM, NV, sdinv)) bad |= 4;
+  }
+  __syncthreads();
+  if (tid < NV) {  // L^-1, column-oriented forward substitution (rows above the diagonal are zero)
+    const int cc = tid;
+    double x[NV];
+#pragma unroll
+    for (int a = 0; a < NV; ++a) x[a] = (a == cc) ? 1.0 : 0.0;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      x[k] *= sdinv[k];
+#pragma unroll
+      for (int a = k + 1; a < NV; ++a) x[a] = fma(-sM[a + k * NV], x[k], x[a]);
+    }
+#pragma unroll
+    for (int a = 0; a < NV; ++a) sLi[a + cc * NV] = x[a];
+  }
+  __syncthreads();
+  for (int e = tid; e < NV * NV; e += NTHR) {  // M^-1 = L^-T L^-1
+    const int r = e % NV, cc = e / NV;
+    double acc = 0.0;
+    for (int k = (r > cc ? r : cc); k < NV; ++k) acc = fma(sLi[k + r * NV], sLi[k + cc * NV], acc);
+    sMi[e] = acc;
+  }
+  __syncthreads();
+  if (nf > 0) {
+    for (int e = tid; e < nf * NV; e += NTHR) {  // J M^-1
+      const int r = e % nf, cc = e / nf;
+      double acc = 0.0;
+      for (int k = 0; k < NV; ++k) acc = fma(sJ[r + k * NFM], sMi[k + cc * NV], acc);
+      sJMi[r + cc * NFM] = acc;
+    }
+    __syncthreads();
+    for (int e = tid; e < nf * nf; e += NTHR) {  // S = J M^-1 J^T   (compact ld = nf)
+      const int r = e % nf, cc = e / nf;
+      double acc = 0.0;
+      for (int k = 0; k < NV; ++k) acc = fma(sJMi[r + k * NFM], sJ[cc + k * NFM], acc);
+      sS[e] = acc;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      if (!warp_cholesky<NFM>(sS, nf, sdinv)) bad |= 8;
+    }
+    __syncthreads();
+    if (tid < nf) {
+      const int cc = tid;
+      double x[NFM];
+#pragma unroll
+      for (int a = 0; a < NFM; ++a) x[a] = (a == cc) ? 1.0 : 0.0;
+#pragma unroll
+      for (int k = 0; k < NFM; ++k) {
+        if (k < nf) {
+          x[k] *= sdinv[k];
+#pragma unroll
+          for (int a = k + 1; a < NFM; ++a)
+            if (a < nf) x[a] = fma(-sS[a + k * nf], x[k], x[a]);
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < NFM; ++a)
+        if (a < nf) sSl[a + cc * nf] = x[a];
+    }
+    __syncthreads();
+    for (int e = tid; e < nf * nf; e += NTHR) {  // S^-1 = Ls^-T Ls^-1
+      const int r = e % nf, cc = e / nf;
+      double acc = 0.0;
+      for (int k = (r > cc ? r : cc); k < nf; ++k) acc = fma(sSl[k + r * nf], sSl[k + cc * nf], acc);
+      sSi[e] = acc;
+    }
+    __syncthreads();
+    for (int e = tid; e < NV * nf; e += NTHR) {  // topRight = (J M^-1)^T S^-1
+      const int r = e % NV, cc = e / NV;
+      double acc = 0.0;
+      for (int l = 0; l < nf; ++l) acc = fma(sJMi[l + r * NFM], sSi[l + cc * nf], acc);
+      sTR[e] = acc;
+    }
+    __syncthreads();
+  }
+  for (int e = tid; e < NVF * NVF; e += NTHR) {
+    const int r = e % NVF, cc = e / NVF;
+    double v = 0.0;
+    if (r < NV && cc < NV) {
+      v = sMi[r + cc * NV];
+      for (int l = 0; l < nf; ++l) v = fma(-sTR[r + l * NV], sJMi[l + cc * NFM], v);  // topLeft -= topRight (J M^-1)
+    } else if (r < NV && cc - NV < nf) {
+      v = sTR[r + (cc - NV) * NV];
+    } else if (cc < NV && r - NV < nf) {
+      v = sTR[cc + (r - NV) * NV];
+    } else if (r >= NV && cc >= NV && r - NV < nf && cc - NV < nf) {
+      v = -sSi[(r - NV) + (cc - NV) * nf];
+    }
+    Z[e] = v;
+  }
+  bad = __reduce_or_sync(0xffffffffu, bad);
+  if ((tid & 31) == 0 && bad) atomicOr(&p.info[b], bad);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K2: everything else of "Forms linear system", with all dense products on the fp64 tensor pipe (DMMA m8n8k4).
 template <int NV, int NU, int NFM>
 struct CondCfg {
   static constexpr int NX = 2 * NV, NVF = NV + NFM;
-  static constexpr int NTHREADS = 256;
-  static constexpr int o_M = 0;                      // M -> L_M
-  static constexpr int o_Mi = o_M + NV * NV;         // M^-1
-  static constexpr int o_J = o_Mi + NV * NV;         // J (ld NFM)
-  static constexpr int o_JMi = o_J + NFM * NV;       // J M^-1 (ld NFM)
-  static constexpr int o_S = o_JMi + NFM * NV;       // J M^-1 J^T -> chol
-  static constexpr int o_Si = o_S + NFM * NFM;       // its inverse
-  static constexpr int o_Z = o_Si + NFM * NFM;       // Z (ld NVF)
-  static constexpr int o_D = o_Z + NVF * NVF;        // dIDCdqv (ld NVF)
-  static constexpr int o_R = o_D + NVF * NX;         // R (ld NVF)
-  static constexpr int o_Qa = o_R + NVF * NX;        // Qafqv (ld NVF)
-  static constexpr int o_Qu = o_Qa + NVF * NX;       // Qafu_full (ld NVF)
-  static constexpr int o_Qxx = o_Qu + NVF * NV;      // Qxx working copy
-  static constexpr int o_Qff = o_Qxx + NX * NX;      // Qff (ld NFM)
-  static constexpr int o_Qqf = o_Qff + NFM * NFM;    // Qqf (ld NV)
-  static constexpr int o_vec = o_Qqf + NV * NFM;     // IDC(NVF) r(NVF) laf(NVF) haf(NVF) Qaa(NV) la(NV) lf(NFM) lx(NX) lu(NU) Fx(NX) dinv(32) misc
+  static constexpr int TX = num_tiles(NX), TF = num_tiles(NVF), TV = num_tiles(NV), TU = num_tiles(NU), TM = num_tiles(NFM);
+  static constexpr int NWARPS = TX;
+  static constexpr int NTHREADS = 32 * NWARPS;
+  static constexpr int o_Z = 0;                     // Z (ld NVF)
+  static constexpr int o_D = o_Z + NVF * NVF;       // dIDCdqv (ld NVF)
+  static constexpr int o_R = o_D + NVF * NX;        // R (ld NVF)
+  static constexpr int o_Qa = o_R + NVF * NX;       // Qafqv (ld NVF)
+  static constexpr int o_Qu = o_Qa + NVF * NX;      // Qafu_full (ld NVF)
+  static constexpr int o_Qff = o_Qu + NVF * NV;     // Qff (ld NFM)
+  static constexpr int o_Qqf = o_Qff + NFM * NFM;   // Qqf (ld NV)
+  static constexpr int o_vec = o_Qqf + NV * NFM;
   static constexpr int v_IDC = 0, v_r = NVF, v_laf = 2 * NVF, v_haf = 3 * NVF, v_Qaa = 4 * NVF, v_la = v_Qaa + NV,
-                       v_lf = v_la + NV, v_lx = v_lf + NFM, v_lu = v_lx + NX, v_Fx = v_lu + NU, v_dinv = v_Fx + NX,
-                       v_w = v_dinv + 32, v_end = v_w + 128;
+                       v_lf = v_la + NV, v_lx = v_lf + NFM, v_lu = v_lx + NX, v_Fx = v_lu + NU, v_fx = v_Fx + NX,
+                       v_Fi = v_fx + NX, v_w = v_Fi + 36, v_end = v_w + 16;
   static constexpr int SMEM_DOUBLES = o_vec + v_end;
   static constexpr size_t SMEM_BYTES = size_t(SMEM_DOUBLES) * 8;
+  static_assert(TF <= NWARPS && TV <= NWARPS && TM <= NWARPS, "one warp per row band");
 };
 
 template <int NV, int NU, int NFM>
-__global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS) condense_kernel(const StageParams p) {
+__global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS, 4) condense_kernel(const StageParams p) {
   using C = CondCfg<NV, NU, NFM>;
-  constexpr int NX = C::NX, NVF = C::NVF, NTHR = C::NTHREADS;
+  constexpr int NX = C::NX, NVF = C::NVF, NTHR = C::NTHREADS, TX = C::TX, TF = C::TF, TV = C::TV, TU = C::TU, TM = C::TM;
   extern __shared__ __align__(16) double smem[];
   const rbt_layout& K = p.K;
   const rbt_stage_layout& S = p.S;
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const size_t o = blockIdx.x;  // b * n_grid + i
   if (o >= size_t(p.batch) * p.n_grid) return;
-  const int i = int(o % p.n_grid), b = int(o / p.n_grid);
+  const int i = int(o % p.n_grid);
   const rbt_stage_ctrl c = p.ctrl[i];
   const double* lin = p.lin + o * S.l_stride;
   double* con = p.con + o * S.c_stride;
@@ -136,18 +255,11 @@ __global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS) condense_kerne
   const bool impact = (c.type == RBT_IMPACT);
   const int nf = c.nf, nvf = NV + nf, ns = impact ? 0 : c.ns;
   const double dt = c.dt;
-  double* sM = smem + C::o_M;
-  double* sMi = smem + C::o_Mi;
-  double* sJ = smem + C::o_J;
-  double* sJMi = smem + C::o_JMi;
-  double* sS = smem + C::o_S;
-  double* sSi = smem + C::o_Si;
   double* sZ = smem + C::o_Z;
   double* sD = smem + C::o_D;
   double* sR = smem + C::o_R;
   double* sQa = smem + C::o_Qa;
   double* sQu = smem + C::o_Qu;
-  double* sQxx = smem + C::o_Qxx;
   double* sQff = smem + C::o_Qff;
   double* sQqf = smem + C::o_Qqf;
   double* vec = smem + C::o_vec;
@@ -161,38 +273,40 @@ __global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS) condense_kerne
   double* vlx = vec + C::v_lx;
   double* vlu = vec + C::v_lu;
   double* vFx = vec + C::v_Fx;
-  double* vdinv = vec + C::v_dinv;
-  double* vw = vec + C::v_w;  // per-row PDIPM weights dual/slack (cones) and scratch
-  int bad = 0;
+  double* vfx = vec + C::v_fx;
+  double* Fi = vec + C::v_Fi;
+  double* vw = vec + C::v_w;
+  double* gQxx = kkt + K.k_Qxx;  // Qxx / Quu working copies live in the (global, L2-resident) KKT record
+  double* gQuu = kkt + K.k_Quu;
 
-  // ---- stage inputs -> shared memory (the stacked [a;f] blocks are zero beyond nv+nf rows/cols)
-  for (int e = tid; e < C::o_Qxx - C::o_Z; e += NTHR) smem[C::o_Z + e] = 0.0;
-  __syncthreads();
-  for (int e = tid; e < NV * NV; e += NTHR) sM[e] = lin[S.l_M + e];
-  for (int e = tid; e < NFM * NV; e += NTHR) sJ[e] = lin[S.l_J + e];
-  for (int e = tid; e < NVF * NX; e += NTHR) sD[e] = lin[S.l_D + e];
-  for (int e = tid; e < NX * NX; e += NTHR) sQxx[e] = lin[S.l_Qxx + e];
-  for (int e = tid; e < NFM * NFM; e += NTHR) sQff[e] = lin[S.l_Qff + e];
-  for (int e = tid; e < NV * NFM; e += NTHR) sQqf[e] = lin[S.l_Qqf + e];
-  for (int e = tid; e < NVF; e += NTHR) vIDC[e] = lin[S.l_IDC + e];
+  // ---- stage inputs -> shared memory (stacked [a;f] blocks are zero beyond nv+nf rows / cols)
+  for (int e = tid; e < NVF * NVF; e += NTHR) sZ[e] = __ldcg(ex + S.e_Z + e);  // written by K1
+  for (int e = tid; e < NVF * NX; e += NTHR) sD[e] = ((e % NVF) < nvf) ? lin[S.l_D + e] : 0.0;
+  for (int e = tid; e < NFM * NFM; e += NTHR) sQff[e] = ((e % NFM) < nf && (e / NFM) < nf) ? lin[S.l_Qff + e] : 0.0;
+  for (int e = tid; e < NV * NFM; e += NTHR) sQqf[e] = ((e / NV) < nf) ? lin[S.l_Qqf + e] : 0.0;
+  for (int e = tid; e < NVF; e += NTHR) vIDC[e] = (e < nvf) ? lin[S.l_IDC + e] : 0.0;
   for (int e = tid; e < NV; e += NTHR) {
     vQaa[e] = lin[S.l_Qaa + e];
     vla[e] = lin[S.l_la + e];
   }
-  for (int e = tid; e < NFM; e += NTHR) vlf[e] = lin[S.l_lf + e];
+  for (int e = tid; e < NFM; e += NTHR) vlf[e] = (e < nf) ? lin[S.l_lf + e] : 0.0;
   for (int e = tid; e < NX; e += NTHR) {
     vlx[e] = lin[S.l_lx + e];
     vFx[e] = lin[S.l_Fx + e];
+    vfx[e] = impact ? 0.0 : lin[S.l_fx + e];
   }
-  for (int e = tid; e < NU; e += NTHR) vlu[e] = lin[S.l_lu + e];
-  // Quu / Qxu working copies live in the (global) KKT record
-  for (int e = tid; e < NU * NU; e += NTHR) kkt[K.k_Quu + e] = impact ? 0.0 : lin[S.l_Quu + e];
+  for (int e = tid; e < NU; e += NTHR) vlu[e] = impact ? 0.0 : lin[S.l_lu + e];
+  for (int e = tid; e < NX * NX; e += NTHR) gQxx[e] = lin[S.l_Qxx + e];
+  for (int e = tid; e < NU * NU; e += NTHR) gQuu[e] = impact ? 0.0 : lin[S.l_Quu + e];
+  if (tid >= NTHR - NVF) {
+    const int r = tid - (NTHR - NVF);
+    vhaf[r] = impact ? 0.0 : (r < NV ? lin[S.l_ha + r] : (r - NV < nf ? -lin[S.l_hf + r - NV] : 0.0));
+  }
   __syncthreads();
 
-  // ---- PDIPM condensing (Intermediate / Lift)
+  // ---- PDIPM condensing (Intermediate / Lift)             pdipm.hxx:27-100, joint_*_limit.cpp:68-75, friction_cone.cpp:194-235
   if (!impact) {
     const double mu = p.tab.barrier;
-    // pass 1: per-row complementarity and condensing coefficient (pdipm.hxx:27-100)
     for (int r = tid; r < p.tab.n_box; r += NTHR) {
       const double sl = con[S.c_slack + r], du = con[S.c_dual + r];
       const double cm = sl * du - mu;
@@ -200,8 +314,7 @@ __global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS) condense_kerne
       con[S.c_cond + r] = (du * con[S.c_res + r] - cm) / sl;
     }
     __syncthreads();
-    // pass 2: one thread per target entry (var, idx) gathers its rows IN ROW ORDER -- deterministic, unlike atomics
-    // (a lower and an upper limit hit the same diagonal entry)            joint_*_limit.cpp:68-75
+    // one thread per target entry (var, idx) gathers its rows IN ROW ORDER: deterministic, unlike atomics
     for (int tgt = tid; tgt < 3 * NV + NU; tgt += NTHR) {
       const int var = tgt < 3 * NV ? tgt / NV : RBT_VAR_U, idx = tgt < 3 * NV ? tgt % NV : tgt - 3 * NV;
       double w = 0.0, gsum = 0.0;
@@ -216,10 +329,10 @@ __global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS) condense_kerne
       }
       if (any) {
         switch (var) {
-          case RBT_VAR_Q: sQxx[idx + idx * NX] += w; vlx[idx] += gsum; break;
-          case RBT_VAR_V: sQxx[(NV + idx) * (NX + 1)] += w; vlx[NV + idx] += gsum; break;
+          case RBT_VAR_Q: gQxx[idx + idx * NX] += w; vlx[idx] += gsum; break;
+          case RBT_VAR_V: gQxx[(NV + idx) * (NX + 1)] += w; vlx[NV + idx] += gsum; break;
           case RBT_VAR_A: vQaa[idx] += w; vla[idx] += gsum; break;
-          default: kkt[K.k_Quu + idx * (NU + 1)] += w; vlu[idx] += gsum; break;
+          default: gQuu[idx * (NU + 1)] += w; vlu[idx] += gsum; break;
         }
       }
     }
@@ -227,8 +340,7 @@ __global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS) condense_kerne
     int fstack = 0;
     for (int ci = 0; ci < p.tab.n_contacts; ++ci) {
       const int base = p.tab.n_box + 5 * ci;
-      const bool act = (c.contact_mask >> ci) & 1;
-      if (!act) {
+      if (!((c.contact_mask >> ci) & 1)) {
         if (tid < 5) con[S.c_cond + base + tid] = 0.0;
         continue;
       }
@@ -259,7 +371,7 @@ __global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS) condense_kerne
         double acc = 0.0;
         if (j < NV) {
           for (int r = 0; r < 5; ++r) acc = fma(dgdq[r + ii * 5] * vw[r], dgdq[r + j * 5], acc);
-          sQxx[ii + j * NX] += acc;
+          gQxx[ii + j * NX] += acc;
         } else {
           for (int r = 0; r < 5; ++r) acc = fma(dgdq[r + ii * 5] * vw[r], dgdf[r + (j - NV) * 5], acc);
           sQqf[ii + (fstack + j - NV) * NV] += acc;
@@ -276,164 +388,217 @@ __global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS) condense_kerne
     }
   }
 
-  // ---- Z = [[M, J^T],[J, 0]]^-1   (robot.hxx:642-683, dense)
-  for (int e = tid; e < NV * NV; e += NTHR) sMi[e] = ((e % NV) == (e / NV)) ? 1.0 : 0.0;
-  __syncthreads();
-  if (warp == 0) {
-    if (!warp_cholesky<NV>(sM, NV, vdinv)) bad |= 4;
-  }
-  __syncthreads();
-  if (tid < NV) chol_solve_smem(sM, vdinv, NV, sMi + tid * NV, 1);
-  __syncthreads();
-  for (int e = tid; e < NV * NV; e += NTHR) sZ[(e % NV) + (e / NV) * NVF] = sMi[e];
-  if (nf > 0) {
-    cta_gemm(0, 0, nf, NV, NV, 1.0, sJ, NFM, sMi, NV, 0.0, sJMi, NFM);
-    __syncthreads();
-    cta_gemm(0, 1, nf, nf, NV, 1.0, sJMi, NFM, sJ, NFM, 0.0, sS, nf);  // compact ld = nf for the Cholesky
-    for (int e = tid; e < nf * nf; e += NTHR) sSi[e] = ((e % nf) == (e / nf)) ? 1.0 : 0.0;
-    __syncthreads();
-    if (warp == 0) {
-      if (!warp_cholesky<NFM>(sS, nf, vdinv)) bad |= 8;
+  // ---- R = Z D (tensor pipe) ; r = Z IDC                    contact_dynamics.cpp:65-66
+  if (warp < TF) {
+    const int i0 = tile_off(warp, NVF);
+    double acc[TX][2];
+#pragma unroll
+    for (int n = 0; n < TX; ++n) acc[n][0] = acc[n][1] = 0.0;
+    warp_mma_band<NVF, TX, NX>(
+        acc, i0, [&](int ii, int k) { return sZ[ii + k * NVF]; }, [&](int k, int j) { return sD[k + j * NVF]; });
+#pragma unroll
+    for (int n = 0; n < TX; ++n) {
+      const int j0 = tile_off(n, NX);
+      sR[(i0 + g) + (j0 + 2 * t) * NVF] = acc[n][0];
+      sR[(i0 + g) + (j0 + 2 * t + 1) * NVF] = acc[n][1];
     }
-    __syncthreads();
-    if (tid < nf) chol_solve_smem(sS, vdinv, nf, sSi + tid * nf, 1);
-    __syncthreads();
-    for (int e = tid; e < nf * nf; e += NTHR) sZ[(NV + e % nf) + (NV + e / nf) * NVF] = -sSi[e];
-    for (int e = tid; e < NV * nf; e += NTHR) {  // topRight = (J M^-1)^T S^-1
-      const int ii = e % NV, j = e / NV;
-      double acc = 0.0;
-      for (int l = 0; l < nf; ++l) acc = fma(sJMi[l + ii * NFM], sSi[l + j * nf], acc);
-      sZ[ii + (NV + j) * NVF] = acc;
-    }
-    __syncthreads();
-    for (int e = tid; e < NV * NV; e += NTHR) {  // topLeft -= topRight (J M^-1)
-      const int ii = e % NV, j = e / NV;
-      double acc = 0.0;
-      for (int l = 0; l < nf; ++l) acc = fma(sZ[ii + (NV + l) * NVF], sJMi[l + j * NFM], acc);
-      sZ[ii + j * NVF] -= acc;
-    }
-    for (int e = tid; e < NV * nf; e += NTHR) sZ[(NV + e / NV) + (e % NV) * NVF] = sZ[(e % NV) + (NV + e / NV) * NVF];
+  } else {
+    matvec_N4(sZ, NVF, NVF, NVF, vIDC, lane, 32, [&](int r, double a) { vr[r] = a; });
   }
   __syncthreads();
 
-  // ---- R = Z D ; r = Z IDC ; Qafqv ; Qafu ; laf          contact_dynamics.cpp:65-86
-  cta_gemm(0, 0, nvf, NX, nvf, 1.0, sZ, NVF, sD, NVF, 0.0, sR, NVF);
-  if (tid < nvf) {
-    double acc = 0.0;
-    for (int l = 0; l < nvf; ++l) acc = fma(sZ[tid + l * NVF], vIDC[l], acc);
-    vr[tid] = acc;
+  // ---- Qafqv, Qafu_full, laf                                contact_dynamics.cpp:68-86
+  for (int e = tid; e < NV * NX; e += NTHR) {  // top rows: -diag(Qaa) R_a
+    const int ii = e % NV, j = e / NV;
+    sQa[ii + j * NVF] = -vQaa[ii] * sR[ii + j * NVF];
   }
-  __syncthreads();
-  for (int e = tid; e < nvf * NX; e += NTHR) {
-    const int ii = e % nvf, j = e / nvf;
-    double v;
-    if (ii < NV) {
-      v = -vQaa[ii] * sR[ii + j * NVF];
-    } else {
-      double acc = 0.0;
-      for (int l = 0; l < nf; ++l) acc = fma(sQff[(ii - NV) + l * NFM], sR[(NV + l) + j * NVF], acc);
-      v = -acc;
-      if (j < NV) v -= sQqf[j + (ii - NV) * NV];
+  if (!impact)
+    for (int e = tid; e < NV * NV; e += NTHR) {  // top rows: diag(Qaa) Z_aa
+      const int ii = e % NV, j = e / NV;
+      sQu[ii + j * NVF] = vQaa[ii] * sZ[ii + j * NVF];
     }
-    sQa[ii + j * NVF] = v;
-  }
-  if (!impact) {
-    for (int e = tid; e < nvf * NV; e += NTHR) {
-      const int ii = e % nvf, j = e / nvf;
+  if (warp < TM) {  // bottom rows of Qafqv: -Qff R_f - [Qqf^T | 0]
+    const int a0 = tile_off(warp, NFM);
+    double acc[TX][2];
+#pragma unroll
+    for (int n = 0; n < TX; ++n) {
+      const int j0 = tile_off(n, NX);
+      acc[n][0] = (j0 + 2 * t < NV) ? -sQqf[(j0 + 2 * t) + (a0 + g) * NV] : 0.0;
+      acc[n][1] = (j0 + 2 * t + 1 < NV) ? -sQqf[(j0 + 2 * t + 1) + (a0 + g) * NV] : 0.0;
+    }
+    warp_mma_band<NFM, TX, NX>(
+        acc, a0, [&](int a, int l) { return -sQff[a + l * NFM]; }, [&](int l, int j) { return sR[(NV + l) + j * NVF]; });
+#pragma unroll
+    for (int n = 0; n < TX; ++n) {
+      const int j0 = tile_off(n, NX);
+      sQa[(NV + a0 + g) + (j0 + 2 * t) * NVF] = acc[n][0];
+      sQa[(NV + a0 + g) + (j0 + 2 * t + 1) * NVF] = acc[n][1];
+    }
+  } else if (!impact && warp < 2 * TM) {  // bottom rows of Qafu_full: Qff Z_fa
+    const int a0 = tile_off(warp - TM, NFM);
+    double acc[TV][2];
+#pragma unroll
+    for (int n = 0; n < TV; ++n) acc[n][0] = acc[n][1] = 0.0;
+    warp_mma_band<NFM, TV, NV>(
+        acc, a0, [&](int a, int l) { return sQff[a + l * NFM]; }, [&](int l, int j) { return sZ[(NV + l) + j * NVF]; });
+#pragma unroll
+    for (int n = 0; n < TV; ++n) {
+      const int j0 = tile_off(n, NV);
+      sQu[(NV + a0 + g) + (j0 + 2 * t) * NVF] = acc[n][0];
+      sQu[(NV + a0 + g) + (j0 + 2 * t + 1) * NVF] = acc[n][1];
+    }
+  } else if (warp == NTHR / 32 - 1) {  // laf
+    for (int r = lane; r < NVF; r += 32) {
       double v;
-      if (ii < NV) {
-        v = vQaa[ii] * sZ[ii + j * NVF];
+      if (r < NV) {
+        v = vla[r] - vQaa[r] * vr[r];
       } else {
         double acc = 0.0;
-        for (int l = 0; l < nf; ++l) acc = fma(sQff[(ii - NV) + l * NFM], sZ[(NV + l) + j * NVF], acc);
-        v = acc;
+        for (int l = 0; l < NFM; ++l) acc = fma(sQff[(r - NV) + l * NFM], vr[NV + l], acc);
+        v = (r - NV < nf) ? -vlf[r - NV] - acc : 0.0;
       }
-      sQu[ii + j * NVF] = v;
-    }
-  }
-  if (tid < nvf) {
-    if (tid < NV) {
-      vlaf[tid] = vla[tid] - vQaa[tid] * vr[tid];
-    } else {
-      double acc = 0.0;
-      for (int l = 0; l < nf; ++l) acc = fma(sQff[(tid - NV) + l * NFM], vr[NV + l], acc);
-      vlaf[tid] = -vlf[tid - NV] - acc;
+      vlaf[r] = v;
     }
   }
   __syncthreads();
 
-  // ---- Hessian / gradient condensing                   contact_dynamics.cpp:88-128, impact_dynamics.cpp:64-70
-  for (int e = tid; e < NX * NX; e += NTHR) {
-    const int ii = e % NX, j = e / NX;
-    double acc = 0.0;
-    for (int l = 0; l < nvf; ++l) acc = fma(sR[l + ii * NVF], sQa[l + j * NVF], acc);
-    double v = sQxx[e] - acc;
-    if (ii < NV) {
-      double a2 = 0.0;
-      for (int l = 0; l < nf; ++l) a2 = fma(sQqf[ii + l * NV], sR[(NV + l) + j * NVF], a2);
-      v += a2;
+  // ---- Hessian condensing on the tensor pipe                contact_dynamics.cpp:88-121, impact_dynamics.cpp:64-66
+  const int i0 = tile_off(warp, NX);
+  {  // Qxx = Qxx' - R^T Qafqv + [Qqf R_f ; 0]
+    double acc[TX][2];
+#pragma unroll
+    for (int n = 0; n < TX; ++n) {
+      const int j0 = tile_off(n, NX);
+      acc[n][0] = __ldcg(gQxx + (i0 + g) + (j0 + 2 * t) * NX);
+      acc[n][1] = __ldcg(gQxx + (i0 + g) + (j0 + 2 * t + 1) * NX);
     }
-    kkt[K.k_Qxx + e] = v;
+    warp_mma_band<NVF, TX, NX>(
+        acc, i0, [&](int ii, int l) { return -sR[l + ii * NVF]; }, [&](int l, int j) { return sQa[l + j * NVF]; });
+    warp_mma_band<NFM, TX, NX>(
+        acc, i0, [&](int ii, int l) { return ii < NV ? sQqf[ii + l * NV] : 0.0; },
+        [&](int l, int j) { return sR[(NV + l) + j * NVF]; });
+    __syncthreads();  // every warp has read its Qxx' fragments before anybody overwrites the record
+#pragma unroll
+    for (int n = 0; n < TX; ++n) {
+      const int j0 = tile_off(n, NX);
+      gQxx[(i0 + g) + (j0 + 2 * t) * NX] = acc[n][0];
+      gQxx[(i0 + g) + (j0 + 2 * t + 1) * NX] = acc[n][1];
+    }
   }
-  for (int ii = tid; ii < NX; ii += NTHR) {
-    double acc = 0.0;
-    for (int l = 0; l < nvf; ++l) acc = fma(sR[l + ii * NVF], vlaf[l], acc);
-    double v = vlx[ii] - acc;
+  if (!impact) {
+    {  // [Qxu_passive | Qxu] = -R^T Qafu_full - [Qqf Z_fa ; 0]          (NX x NV)
+      double acc[TV][2];
+#pragma unroll
+      for (int n = 0; n < TV; ++n) acc[n][0] = acc[n][1] = 0.0;
+      warp_mma_band<NVF, TV, NV>(
+          acc, i0, [&](int ii, int l) { return -sR[l + ii * NVF]; }, [&](int l, int j) { return sQu[l + j * NVF]; });
+      warp_mma_band<NFM, TV, NV>(
+          acc, i0, [&](int ii, int l) { return ii < NV ? -sQqf[ii + l * NV] : 0.0; },
+          [&](int l, int j) { return sZ[(NV + l) + j * NVF]; });
+#pragma unroll
+      for (int n = 0; n < TV; ++n) {
+        const int j0 = tile_off(n, NV);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int j = j0 + 2 * t + q;
+          if (j < np) ex[S.e_Qxup + (i0 + g) + j * NX] = acc[n][q];
+          else kkt[K.k_Qxu + (i0 + g) + (j - np) * NX] = acc[n][q];  // pre-condense Qxu is zero (the cost has no x-u term)
+        }
+      }
+    }
+    if (warp < TV) {  // [Quu_passive_topRight ; Quu' +=] = Z[0:nv, :] Qafu_full[:, np:]     (NV x NU)
+      const int r0 = tile_off(warp, NV);
+      double acc[TU][2];
+#pragma unroll
+      for (int n = 0; n < TU; ++n) {
+        const int j0 = tile_off(n, NU);
+        const int r = r0 + g;
+        acc[n][0] = (r >= np) ? __ldcg(gQuu + (r - np) + (j0 + 2 * t) * NU) : 0.0;
+        acc[n][1] = (r >= np) ? __ldcg(gQuu + (r - np) + (j0 + 2 * t + 1) * NU) : 0.0;
+      }
+      warp_mma_band<NVF, TU, NU>(
+          acc, r0, [&](int ii, int l) { return sZ[ii + l * NVF]; }, [&](int l, int j) { return sQu[l + (np + j) * NVF]; });
+      __syncwarp();
+      // the pulled-back band overlaps the previous one: both hold identical values for shared rows, and both read their
+      // Quu' fragments from a row range only they and their overlap partner touch; order reads before writes CTA-wide
+      named_bar_sync(1, 32 * TV);
+#pragma unroll
+      for (int n = 0; n < TU; ++n) {
+        const int j0 = tile_off(n, NU);
+        const int r = r0 + g;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          if (r < np) ex[S.e_Quup + r + (j0 + 2 * t + q) * np] = acc[n][q];
+          else gQuu[(r - np) + (j0 + 2 * t + q) * NU] = acc[n][q];
+        }
+      }
+    }
+  }
+  // ---- gradients: lx -= R^T laf (+ Qqf r_f) ; [lu_passive ; lu] += Z[0:nv,:] laf          :108-128
+  matvec_T(sR, NVF, NVF, NX, vlaf, tid, NTHR, [&](int ii, double a) {
+    double v = vlx[ii] - a;
     if (ii < NV) {
       double a2 = 0.0;
-      for (int l = 0; l < nf; ++l) a2 = fma(sQqf[ii + l * NV], vr[NV + l], a2);
+      for (int l = 0; l < NFM; ++l) a2 = fma(sQqf[ii + l * NV], vr[NV + l], a2);
       v += a2;
     }
     kkt[K.k_lx + ii] = v;
-  }
+  });
   if (!impact) {
-    for (int e = tid; e < NX * NV; e += NTHR) {  // [Qxu_passive | Qxu] = -R^T Qafu_full - [Qqf Z_fa ; 0]
-      const int ii = e % NX, j = e / NX;
-      double acc = 0.0;
-      for (int l = 0; l < nvf; ++l) acc = fma(sR[l + ii * NVF], sQu[l + j * NVF], acc);
-      double v = -acc;
-      if (ii < NV) {
-        double a2 = 0.0;
-        for (int l = 0; l < nf; ++l) a2 = fma(sQqf[ii + l * NV], sZ[(NV + l) + j * NVF], a2);
-        v -= a2;
-      }
-      if (j < np) ex[S.e_Qxup + ii + j * NX] = v;
-      else kkt[K.k_Qxu + ii + (j - np) * NX] = v;  // pre-condense Qxu is zero (the cost has no x-u coupling)
-    }
-    for (int e = tid; e < NV * NU; e += NTHR) {  // [Quu_passive_topRight ; Quu +=] = Z[0:nv, :] Qafu_full[:, np:]
-      const int ii = e % NV, j = e / NV;
-      double acc = 0.0;
-      for (int l = 0; l < nvf; ++l) acc = fma(sZ[ii + l * NVF], sQu[l + (np + j) * NVF], acc);
-      if (ii < np) ex[S.e_Quup + ii + j * np] = acc;
-      else kkt[K.k_Quu + (ii - np) + j * NU] += acc;
-    }
-    for (int ii = tid; ii < NV; ii += NTHR) {  // [lu_passive ; lu] += Z[0:nv, :] laf
-      double acc = 0.0;
-      for (int l = 0; l < nvf; ++l) acc = fma(sZ[ii + l * NVF], vlaf[l], acc);
-      if (ii < np) ex[S.e_lup + ii] = lin[S.l_lup + ii] + acc;
-      else kkt[K.k_lu + ii - np] = vlu[ii - np] + acc;
-    }
+    matvec_N4(sZ, NVF, NV, NVF, vlaf, tid, NTHR, [&](int ii, double a) {
+      if (ii < np) ex[S.e_lup + ii] = lin[S.l_lup + ii] + a;
+      else kkt[K.k_lu + ii - np] = vlu[ii - np] + a;
+    });
   }
   // ---- state equation rows                                 contact_dynamics.cpp:130-135, impact_dynamics.cpp:71-74
   const double sdt = impact ? 1.0 : dt;
-  for (int e = tid; e < NX * NX; e += NTHR) {
-    const int ii = e % NX, j = e / NX;
-    double v;
-    if (ii < NV) {
-      if (j < NV) v = (ii == j) ? 1.0 : 0.0;
-      else v = (!impact && ii == j - NV) ? dt : 0.0;
-      if (np == 6 && ii < 6 && j < 6) v = lin[S.l_se3 + ii + j * 6];
-    } else {
-      v = -sdt * sR[(ii - NV) + j * NVF] + ((j >= NV && ii == j) ? 1.0 : 0.0);
-    }
-    sQxx[e] = v;  // Qxx is done with its working copy: reuse it for Fxx (SE(3) correction below)
+  if (np == 6) {
+    if (tid == 0) se3_jac_inverse_dev(lin + S.l_se3 + 36, ex + S.e_Fqqpi);  // Fqq_prev_inv   state_equation.cpp:76
+    if (tid == 32) se3_jac_inverse_dev(lin + S.l_se3 + 72, Fi);              // Fqq_inv        :77-78
   }
-  if (!impact)
-    for (int e = tid; e < NV * NU; e += NTHR) kkt[K.k_Fvu + e] = dt * sZ[(e % NV) + (np + e / NV) * NVF];
   for (int ii = tid; ii < NX; ii += NTHR) {
     double v = vFx[ii];
     if (ii >= NV) v -= sdt * vr[ii - NV];
     vFx[ii] = v;
+  }
+  __syncthreads();
+  for (int e = tid; e < NX * NX; e += NTHR) {
+    const int ii = e % NX, j = e / NX;
+    double v;
+    if (ii < NV) {
+      if (np == 6 && ii < 6 && (j < 6 || (j >= NV && j < NV + 6))) {
+        if (j < 6) {  // Fqq top-left = -Fqq_inv * (dSub/dqf top-left)                       state_equation.cpp:80
+          double acc = 0.0;
+          for (int l = 0; l < 6; ++l) acc = fma(Fi[ii + l * 6], lin[S.l_se3 + l + j * 6], acc);
+          v = -acc;
+        } else {      // Fqv top-left = -dt Fqq_inv                                           :81
+          v = impact ? 0.0 : -dt * Fi[ii + (j - NV) * 6];
+        }
+      } else if (j < NV) {
+        v = (ii == j) ? 1.0 : 0.0;
+      } else {
+        v = (!impact && ii == j - NV) ? dt : 0.0;
+      }
+    } else {
+      v = -sdt * sR[(ii - NV) + j * NVF] + ((j >= NV && ii == j) ? 1.0 : 0.0);
+    }
+    kkt[K.k_Fxx + e] = v;
+  }
+  if (!impact)
+    for (int e = tid; e < NV * NU; e += NTHR) kkt[K.k_Fvu + e] = dt * sZ[(e % NV) + (np + e / NV) * NVF];
+  for (int ii = tid; ii < NX; ii += NTHR) {
+    double v = vFx[ii], f = vfx[ii];
+    if (np == 6 && ii < 6) {  // Fq, fq head <- -Fqq_inv * (.)                                :83-85
+      double a1 = 0.0, a2 = 0.0;
+      for (int l = 0; l < 6; ++l) {
+        a1 = fma(Fi[ii + l * 6], vFx[l], a1);
+        a2 = fma(Fi[ii + l * 6], vfx[l], a2);
+      }
+      v = -a1;
+      f = -a2;
+    }
+    kkt[K.k_Fx + ii] = v;
+    if (!impact) kkt[K.k_fx + ii] = f / c.ngrids_in_phase;
   }
   // ---- switching constraint                                contact_dynamics.cpp:138-153
   if (ns > 0) {
@@ -458,86 +623,45 @@ __global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS) condense_kerne
       kkt[K.k_Phit + q] = (lin[S.l_Phit + q] - acc) / c.ngrids_in_phase;  // incl. the STO scaling (intermediate_stage.cpp:146-148)
     }
   }
-  __syncthreads();
   // ---- STO sensitivities + scaling                         contact_dynamics.cpp:156-163, intermediate_stage.cpp:140-148
   if (!impact) {
     const double g1 = 1.0 / c.ngrids_in_phase;
-    if (tid < nvf) vhaf[tid] = (tid < NV) ? lin[S.l_ha + tid] : -lin[S.l_hf + tid - NV];
-    __syncthreads();
-    if (tid < nvf) ex[S.e_haf + tid] = vhaf[tid];
-    for (int ii = tid; ii < NX; ii += NTHR) {
-      double acc = 0.0;
-      for (int l = 0; l < nvf; ++l) acc = fma(sR[l + ii * NVF], vhaf[l], acc);
-      double v = lin[S.l_hx + ii] - acc;
+    matvec_T(sR, NVF, NVF, NX, vhaf, tid, NTHR, [&](int ii, double a) {
+      double v = lin[S.l_hx + ii] - a;
       if (ii < NV) {
         double a2 = 0.0;
-        for (int l = 0; l < nf; ++l) a2 = fma(sQqf[ii + l * NV], vr[NV + l], a2);
+        for (int l = 0; l < NFM; ++l) a2 = fma(sQqf[ii + l * NV], vr[NV + l], a2);
         v += a2 / dt;
       }
       kkt[K.k_hx + ii] = v * g1;
-      vw[ii] = lin[S.l_fx + ii];  // fx, SE(3)-corrected below
-    }
+    });
     for (int ii = tid; ii < NU; ii += NTHR) {
       double acc = 0.0;
-      for (int l = 0; l < nvf; ++l) acc = fma(sZ[(np + ii) + l * NVF], vhaf[l], acc);
+      for (int l = 0; l < NVF; ++l) acc = fma(sZ[(np + ii) + l * NVF], vhaf[l], acc);
       kkt[K.k_hu + ii] = (lin[S.l_hu + ii] + acc) * g1;
     }
     if (tid == 0) {
       double h = lin[S.l_sc + 0];
-      for (int l = 0; l < nvf; ++l) h = fma(-vr[l], vhaf[l], h);
+      for (int l = 0; l < NVF; ++l) h = fma(-vr[l], vhaf[l], h);
       const double Qtt = lin[S.l_sc + 1] * g1 * g1;
       kkt[K.k_sc + 0] = Qtt;
       kkt[K.k_sc + 1] = -Qtt;
       kkt[K.k_sc + 2] = h * g1;
       kkt[K.k_sc + 3] = 0.0;
     }
+    for (int e = tid; e < NVF; e += NTHR) ex[S.e_haf + e] = vhaf[e];
   }
-  __syncthreads();
-  // ---- floating base: SE(3) correction                     state_equation.cpp:68-87, impact_state_equation.cpp:53-70
-  if (np == 6) {
-    double* Fi = vw + 64;  // Fqq_inv (36)
-    if (tid == 0) se3_jac_inverse_dev(lin + S.l_se3 + 36, ex + S.e_Fqqpi);
-    if (tid == 32) se3_jac_inverse_dev(lin + S.l_se3 + 72, Fi);
-    __syncthreads();
-    double v1 = 0.0, v2 = 0.0, v3 = 0.0;
-    const int ii = tid % 6, j = tid / 6;
-    if (tid < 36) {
-      for (int l = 0; l < 6; ++l) v1 = fma(Fi[ii + l * 6], sQxx[l + j * NX], v1);
-    } else if (tid < 42) {
-      for (int l = 0; l < 6; ++l) {
-        v2 = fma(Fi[ii + l * 6], vFx[l], v2);
-        if (!impact) v3 = fma(Fi[ii + l * 6], vw[l], v3);
-      }
-    }
-    __syncthreads();
-    if (tid < 36) {
-      sQxx[ii + j * NX] = -v1;
-      if (!impact) sQxx[ii + (NV + j) * NX] = -dt * Fi[ii + j * 6];
-    } else if (tid < 42) {
-      vFx[ii] = -v2;
-      if (!impact) vw[ii] = -v3;
-    }
-    __syncthreads();
-  }
-  for (int e = tid; e < NX * NX; e += NTHR) kkt[K.k_Fxx + e] = sQxx[e];
-  for (int e = tid; e < NX; e += NTHR) {
-    kkt[K.k_Fx + e] = vFx[e];
-    if (!impact) kkt[K.k_fx + e] = vw[e] / c.ngrids_in_phase;
-  }
-  // ---- expansion record
-  for (int e = tid; e < NVF * NVF; e += NTHR) ex[S.e_Z + e] = sZ[e];
+  // ---- expansion record (Z is already there)
   for (int e = tid; e < NVF * NX; e += NTHR) {
     ex[S.e_R + e] = sR[e];
     ex[S.e_Qafqv + e] = sQa[e];
   }
   if (!impact)
     for (int e = tid; e < NVF * NV; e += NTHR) ex[S.e_Qafu + e] = sQu[e];
-  for (int e = tid; e < nvf; e += NTHR) {
+  for (int e = tid; e < NVF; e += NTHR) {
     ex[S.e_r + e] = vr[e];
     ex[S.e_laf + e] = vlaf[e];
   }
-  bad = __reduce_or_sync(0xffffffffu, bad);
-  if ((tid & 31) == 0 && bad) atomicOr(&p.info[b], bad);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
