@@ -461,6 +461,21 @@ int rbt_stage_setup(rbt_handle* h, const rbt_stage_dims* sd, const rbt_constrain
       return RBT_ERR_ARG;
     }
   }
+  {
+    if (3 * sd->nv + sd->nu > RBT_MAX_TARGETS) {
+      h->err = "[rbt_stage_setup] invalid argument: too many limit targets";
+      return RBT_ERR_ARG;
+    }
+    std::vector<int> cnt(RBT_MAX_TARGETS, 0);
+    for (int r = 0; r < table->n_box; ++r) {
+      const rbt_box_row& b = table->box[r];
+      const int t = (b.var == RBT_VAR_U) ? 3 * sd->nv + b.idx : b.var * sd->nv + b.idx;
+      if (++cnt[t] > 4) {
+        h->err = "[rbt_stage_setup] invalid argument: more than 4 box rows on one variable";
+        return RBT_ERR_ARG;
+      }
+    }
+  }
   h->sdims = *sd;
   h->table = *table;
   rbt_make_stage_layout(sd, &h->S);
@@ -500,6 +515,18 @@ static rbt::StageParams make_stage_params(rbt_handle* h) {
   p.sol = h->d_sol;
   p.steps = h->d_steps;
   p.info = h->d_info;
+  // box rows acting on each target entry (var, idx), in ascending row order (deterministic accumulation on the device)
+  for (int t = 0; t < RBT_MAX_TARGETS; ++t)
+    for (int q = 0; q < 4; ++q) p.tgt_rows[t][q] = -1;
+  for (int r = 0; r < h->table.n_box; ++r) {
+    const rbt_box_row& b = h->table.box[r];
+    const int t = (b.var == RBT_VAR_U) ? 3 * h->sdims.nv + b.idx : b.var * h->sdims.nv + b.idx;
+    for (int q = 0; q < 4; ++q)
+      if (p.tgt_rows[t][q] < 0) {
+        p.tgt_rows[t][q] = (short)r;
+        break;
+      }
+  }
   return p;
 }
 

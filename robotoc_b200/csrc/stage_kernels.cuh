@@ -19,6 +19,7 @@
 
 namespace rbt {
 
+#define RBT_MAX_TARGETS 96
 struct StageParams {
   rbt_layout K;
   rbt_stage_layout S;
@@ -35,6 +36,7 @@ struct StageParams {
   double* sol;
   double* steps;  // [batch][2]
   int* info;
+  short tgt_rows[RBT_MAX_TARGETS][4];  // box rows acting on target (var, idx) = var*nv + idx (u: 3*nv + idx), ascending, -1 = none
 };
 
 // C(m x n, ld ldc) = beta*C + alpha * op(A) op(B); all operands in shared (or global) memory; every thread of the CTA calls.
@@ -89,7 +91,7 @@ __device__ __forceinline__ void se3_jac_inverse_dev(const double* Jac, double* J
 // ~12 stages per SM are in flight and hide each other's fp64 latency.  Writes the full (zero-padded) Z into the
 // expansion record; condense_kernel (K2) reads it back from L2.
 template <int NV, int NFM>
-__global__ void __launch_bounds__(64) mjtjinv_kernel(const StageParams p) {
+__global__ void __launch_bounds__(64, 12) mjtjinv_kernel(const StageParams p) {
   constexpr int NVF = NV + NFM, NTHR = 64;
   __shared__ double sM[NV * NV], sLi[NV * NV], sMi[NV * NV], sJ[NFM * NV], sJMi[NFM * NV], sS[NFM * NFM], sSl[NFM * NFM],
       sSi[NFM * NFM], sTR[NV * NFM], sdinv[32];
@@ -217,13 +219,16 @@ struct CondCfg {
   static constexpr int o_R = o_D + NVF * NX;        // R (ld NVF)
   static constexpr int o_Qa = o_R + NVF * NX;       // Qafqv (ld NVF)
   static constexpr int o_Qu = o_Qa + NVF * NX;      // Qafu_full (ld NVF)
-  static constexpr int o_Qff = o_Qu + NVF * NV;     // Qff (ld NFM)
+  static constexpr int o_Qxx = o_Qu + NVF * NV;     // Qxx working copy (cost Hessian + PDIPM terms), bulk-copied in
+  static constexpr int o_Quu = o_Qxx + NX * NX;     // Quu working copy
+  static constexpr int o_Qff = o_Quu + NU * NU;     // Qff (ld NFM)
   static constexpr int o_Qqf = o_Qff + NFM * NFM;   // Qqf (ld NV)
   static constexpr int o_vec = o_Qqf + NV * NFM;
   static constexpr int v_IDC = 0, v_r = NVF, v_laf = 2 * NVF, v_haf = 3 * NVF, v_Qaa = 4 * NVF, v_la = v_Qaa + NV,
                        v_lf = v_la + NV, v_lx = v_lf + NFM, v_lu = v_lx + NX, v_Fx = v_lu + NU, v_fx = v_Fx + NX,
                        v_Fi = v_fx + NX, v_w = v_Fi + 36, v_end = v_w + 16;
-  static constexpr int SMEM_DOUBLES = o_vec + v_end;
+  static constexpr int o_bar = (o_vec + v_end + 1) & ~1;
+  static constexpr int SMEM_DOUBLES = o_bar + 2;
   static constexpr size_t SMEM_BYTES = size_t(SMEM_DOUBLES) * 8;
   static_assert(TF <= NWARPS && TV <= NWARPS && TM <= NWARPS, "one warp per row band");
 };
@@ -276,12 +281,24 @@ __global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS, 4) condense_ke
   double* vfx = vec + C::v_fx;
   double* Fi = vec + C::v_Fi;
   double* vw = vec + C::v_w;
-  double* gQxx = kkt + K.k_Qxx;  // Qxx / Quu working copies live in the (global, L2-resident) KKT record
-  double* gQuu = kkt + K.k_Quu;
+  double* gQxx = smem + C::o_Qxx;  // Qxx / Quu working copies (shared memory)
+  double* gQuu = smem + C::o_Quu;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + C::o_bar);
 
-  // ---- stage inputs -> shared memory (stacked [a;f] blocks are zero beyond nv+nf rows / cols)
-  for (int e = tid; e < NVF * NVF; e += NTHR) sZ[e] = __ldcg(ex + S.e_Z + e);  // written by K1
-  for (int e = tid; e < NVF * NX; e += NTHR) sD[e] = ((e % NVF) < nvf) ? lin[S.l_D + e] : 0.0;
+  // ---- stage inputs -> shared memory.  The three big blocks (Z from K1, dIDCdqv, Qxx) arrive by cp.async.bulk while the
+  // PDIPM passes below run.  Contract: rows >= nv+nf of dIDCdqv are zero in the linearization record (Z is zero-padded by K1).
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    fence_proxy_async();
+    mbar_expect_tx(bar, uint32_t(NVF * NVF + NVF * NX + NX * NX) * 8u);
+    tma_load_1d(sZ, ex + S.e_Z, uint32_t(NVF * NVF) * 8u, bar);
+    tma_load_1d(sD, lin + S.l_D, uint32_t(NVF * NX) * 8u, bar);
+    tma_load_1d(gQxx, lin + S.l_Qxx, uint32_t(NX * NX) * 8u, bar);
+  }
   for (int e = tid; e < NFM * NFM; e += NTHR) sQff[e] = ((e % NFM) < nf && (e / NFM) < nf) ? lin[S.l_Qff + e] : 0.0;
   for (int e = tid; e < NV * NFM; e += NTHR) sQqf[e] = ((e / NV) < nf) ? lin[S.l_Qqf + e] : 0.0;
   for (int e = tid; e < NVF; e += NTHR) vIDC[e] = (e < nvf) ? lin[S.l_IDC + e] : 0.0;
@@ -296,7 +313,6 @@ __global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS, 4) condense_ke
     vfx[e] = impact ? 0.0 : lin[S.l_fx + e];
   }
   for (int e = tid; e < NU; e += NTHR) vlu[e] = impact ? 0.0 : lin[S.l_lu + e];
-  for (int e = tid; e < NX * NX; e += NTHR) gQxx[e] = lin[S.l_Qxx + e];
   for (int e = tid; e < NU * NU; e += NTHR) gQuu[e] = impact ? 0.0 : lin[S.l_Quu + e];
   if (tid >= NTHR - NVF) {
     const int r = tid - (NTHR - NVF);
@@ -305,89 +321,108 @@ __global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS, 4) condense_ke
   __syncthreads();
 
   // ---- PDIPM condensing (Intermediate / Lift)             pdipm.hxx:27-100, joint_*_limit.cpp:68-75, friction_cone.cpp:194-235
+  // All rows at once: (1) per-row complementarity / condensing coefficient / weight, (2) per-target gather of the box rows
+  // in row order (deterministic; a lower and an upper limit share a diagonal entry), (3) element-parallel application of
+  // the box and friction-cone terms.  Staging aliases the (still unused) Qafqv / Qafu buffers.
   if (!impact) {
     const double mu = p.tab.barrier;
-    for (int r = tid; r < p.tab.n_box; r += NTHR) {
-      const double sl = con[S.c_slack + r], du = con[S.c_dual + r];
-      const double cm = sl * du - mu;
-      con[S.c_cmpl + r] = cm;
-      con[S.c_cond + r] = (du * con[S.c_res + r] - cm) / sl;
-    }
-    __syncthreads();
-    // one thread per target entry (var, idx) gathers its rows IN ROW ORDER: deterministic, unlike atomics
-    for (int tgt = tid; tgt < 3 * NV + NU; tgt += NTHR) {
-      const int var = tgt < 3 * NV ? tgt / NV : RBT_VAR_U, idx = tgt < 3 * NV ? tgt % NV : tgt - 3 * NV;
-      double w = 0.0, gsum = 0.0;
-      bool any = false;
-      for (int r = 0; r < p.tab.n_box; ++r) {
-        const rbt_box_row br = p.tab.box[r];
-        if (br.var == var && br.idx == idx) {
-          w += con[S.c_dual + r] / con[S.c_slack + r];
-          gsum += br.sign * con[S.c_cond + r];
-          any = true;
-        }
-      }
-      if (any) {
-        switch (var) {
-          case RBT_VAR_Q: gQxx[idx + idx * NX] += w; vlx[idx] += gsum; break;
-          case RBT_VAR_V: gQxx[(NV + idx) * (NX + 1)] += w; vlx[NV + idx] += gsum; break;
-          case RBT_VAR_A: vQaa[idx] += w; vla[idx] += gsum; break;
-          default: gQuu[idx * (NU + 1)] += w; vlu[idx] += gsum; break;
-        }
-      }
-    }
-    __syncthreads();
-    int fstack = 0;
-    for (int ci = 0; ci < p.tab.n_contacts; ++ci) {
-      const int base = p.tab.n_box + 5 * ci;
-      if (!((c.contact_mask >> ci) & 1)) {
-        if (tid < 5) con[S.c_cond + base + tid] = 0.0;
-        continue;
-      }
-      const double* dgdq = lin + S.l_dgdq + size_t(ci) * 5 * NV;
-      const double* dgdf = lin + S.l_dgdf + size_t(ci) * 15;
-      if (tid < 5) {
-        const double sl = con[S.c_slack + base + tid], du = con[S.c_dual + base + tid];
+    const int nc = S.nc, nbox = p.tab.n_box, ncon = p.tab.n_contacts;
+    double* cW = sQu;            // weights dual/slack            [ncp]
+    double* cC = sQu + S.ncp;    // condensing coefficients       [ncp]
+    double* tW = sQu + 2 * S.ncp;  // per-target weight sums        [RBT_MAX_TARGETS]
+    double* tG = tW + RBT_MAX_TARGETS;  // per-target gradient sums
+    double* sDq = sQa;           // dg/dq of every contact: 5 x nv each
+    double* sDf = sQa + ncon * 5 * NV;  // dg/df: 5 x 3 each
+    for (int r = tid; r < nc; r += NTHR) {
+      const bool cone = r >= nbox;
+      const bool act = !cone || ((c.contact_mask >> ((r - nbox) / 5)) & 1);
+      double w = 0.0, cd = 0.0;
+      if (act) {
+        const double sl = con[S.c_slack + r], du = con[S.c_dual + r];
         const double cm = sl * du - mu;
-        const double cd = (du * con[S.c_res + base + tid] - cm) / sl;
-        con[S.c_cmpl + base + tid] = cm;
-        con[S.c_cond + base + tid] = cd;
-        vw[tid] = du / sl;
-        vw[8 + tid] = cd;
+        cd = (du * con[S.c_res + r] - cm) / sl;
+        w = du / sl;
+        con[S.c_cmpl + r] = cm;
       }
-      __syncthreads();
-      for (int j = tid; j < NV + 3; j += NTHR) {
-        double acc = 0.0;
-        if (j < NV) {
-          for (int r = 0; r < 5; ++r) acc = fma(dgdq[r + j * 5], vw[8 + r], acc);
-          vlx[j] += acc;
-        } else {
-          for (int r = 0; r < 5; ++r) acc = fma(dgdf[r + (j - NV) * 5], vw[8 + r], acc);
-          vlf[fstack + j - NV] += acc;
+      con[S.c_cond + r] = cd;  // data.cond.setZero() for inactive contacts   friction_cone.cpp:198
+      cW[r] = w;
+      cC[r] = cd;
+    }
+    for (int e = tid; e < ncon * 5 * NV; e += NTHR) sDq[e] = ((c.contact_mask >> (e / (5 * NV))) & 1) ? lin[S.l_dgdq + e] : 0.0;
+    for (int e = tid; e < ncon * 15; e += NTHR) sDf[e] = ((c.contact_mask >> (e / 15)) & 1) ? lin[S.l_dgdf + e] : 0.0;
+    __syncthreads();
+    for (int tgt = tid; tgt < 3 * NV + NU; tgt += NTHR) {
+      double w = 0.0, gs = 0.0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int r = p.tgt_rows[tgt][q];
+        if (r >= 0) {
+          w += cW[r];
+          gs += p.tab.box[r].sign * cC[r];
         }
       }
-      for (int e = tid; e < NV * (NV + 3); e += NTHR) {
-        const int ii = e % NV, j = e / NV;
+      tW[tgt] = w;
+      tG[tgt] = gs;
+    }
+    mbar_wait(bar, 0);  // Z, dIDCdqv, Qxx have landed
+    __syncthreads();
+    // Qqq += diag(box q) + sum_c dg_dq^T diag(w) dg_dq          friction_cone.cpp:217-218
+    for (int e = tid; e < NV * NV; e += NTHR) {
+      const int ii = e % NV, j = e / NV;
+      double acc = (ii == j) ? tW[ii] : 0.0;
+      for (int ci = 0; ci < ncon; ++ci)
+        for (int r = 0; r < 5; ++r) acc = fma(sDq[ci * 5 * NV + r + ii * 5] * cW[nbox + 5 * ci + r], sDq[ci * 5 * NV + r + j * 5], acc);
+      gQxx[ii + j * NX] += acc;
+    }
+    // Qqf[:, stack(c)] += dg_dq^T diag(w) dg_df ;  Qff[stack(c), stack(c)] += dg_df^T diag(w) dg_df     :219-222
+    for (int e = tid; e < NV * 3 * ncon + 9 * ncon; e += NTHR) {
+      const bool isqf = e < NV * 3 * ncon;
+      const int ee = isqf ? e : e - NV * 3 * ncon;
+      const int ci = isqf ? ee / (NV * 3) : ee / 9;
+      if (!((c.contact_mask >> ci) & 1)) continue;
+      const int fstack = 3 * __popc(c.contact_mask & ((1 << ci) - 1));
+      const double* dq = sDq + ci * 5 * NV;
+      const double* df = sDf + ci * 15;
+      const double* w5 = cW + nbox + 5 * ci;
+      if (isqf) {
+        const int ii = (ee % (NV * 3)) % NV, j = (ee % (NV * 3)) / NV;
         double acc = 0.0;
-        if (j < NV) {
-          for (int r = 0; r < 5; ++r) acc = fma(dgdq[r + ii * 5] * vw[r], dgdq[r + j * 5], acc);
-          gQxx[ii + j * NX] += acc;
-        } else {
-          for (int r = 0; r < 5; ++r) acc = fma(dgdq[r + ii * 5] * vw[r], dgdf[r + (j - NV) * 5], acc);
-          sQqf[ii + (fstack + j - NV) * NV] += acc;
-        }
-      }
-      if (tid < 9) {
-        const int ii = tid % 3, j = tid / 3;
+        for (int r = 0; r < 5; ++r) acc = fma(dq[r + ii * 5] * w5[r], df[r + j * 5], acc);
+        sQqf[ii + (fstack + j) * NV] += acc;
+      } else {
+        const int ii = (ee % 9) % 3, j = (ee % 9) / 3;
         double acc = 0.0;
-        for (int r = 0; r < 5; ++r) acc = fma(dgdf[r + ii * 5] * vw[r], dgdf[r + j * 5], acc);
+        for (int r = 0; r < 5; ++r) acc = fma(df[r + ii * 5] * w5[r], df[r + j * 5], acc);
         sQff[(fstack + ii) + (fstack + j) * NFM] += acc;
       }
-      __syncthreads();
-      fstack += 3;
     }
+    // gradients and the remaining diagonals
+    for (int ii = tid; ii < NV; ii += NTHR) {
+      double acc = tG[ii];
+      for (int ci = 0; ci < ncon; ++ci)
+        for (int r = 0; r < 5; ++r) acc = fma(sDq[ci * 5 * NV + r + ii * 5], cC[nbox + 5 * ci + r], acc);  // lq += dg_dq^T cond  :207
+      vlx[ii] += acc;
+      vlx[NV + ii] += tG[NV + ii];
+      gQxx[(NV + ii) * (NX + 1)] += tW[NV + ii];
+      vQaa[ii] += tW[2 * NV + ii];
+      vla[ii] += tG[2 * NV + ii];
+    }
+    for (int ii = tid; ii < NU; ii += NTHR) {
+      gQuu[ii * (NU + 1)] += tW[3 * NV + ii];
+      vlu[ii] += tG[3 * NV + ii];
+    }
+    for (int q = tid; q < 3 * ncon; q += NTHR) {  // lf[stack(c) + j] += dg_df^T cond   :208-209
+      const int ci = q / 3, j = q % 3;
+      if ((c.contact_mask >> ci) & 1) {
+        const int fstack = 3 * __popc(c.contact_mask & ((1 << ci) - 1));
+        double acc = 0.0;
+        for (int r = 0; r < 5; ++r) acc = fma(sDf[ci * 15 + r + j * 5], cC[nbox + 5 * ci + r], acc);
+        vlf[fstack + j] += acc;
+      }
+    }
+    __syncthreads();
   }
-
+  if (impact) mbar_wait(bar, 0);
   // ---- R = Z D (tensor pipe) ; r = Z IDC                    contact_dynamics.cpp:65-66
   if (warp < TF) {
     const int i0 = tile_off(warp, NVF);
@@ -469,20 +504,19 @@ __global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS, 4) condense_ke
 #pragma unroll
     for (int n = 0; n < TX; ++n) {
       const int j0 = tile_off(n, NX);
-      acc[n][0] = __ldcg(gQxx + (i0 + g) + (j0 + 2 * t) * NX);
-      acc[n][1] = __ldcg(gQxx + (i0 + g) + (j0 + 2 * t + 1) * NX);
+      acc[n][0] = gQxx[(i0 + g) + (j0 + 2 * t) * NX];
+      acc[n][1] = gQxx[(i0 + g) + (j0 + 2 * t + 1) * NX];
     }
     warp_mma_band<NVF, TX, NX>(
         acc, i0, [&](int ii, int l) { return -sR[l + ii * NVF]; }, [&](int l, int j) { return sQa[l + j * NVF]; });
     warp_mma_band<NFM, TX, NX>(
         acc, i0, [&](int ii, int l) { return ii < NV ? sQqf[ii + l * NV] : 0.0; },
         [&](int l, int j) { return sR[(NV + l) + j * NVF]; });
-    __syncthreads();  // every warp has read its Qxx' fragments before anybody overwrites the record
 #pragma unroll
     for (int n = 0; n < TX; ++n) {
       const int j0 = tile_off(n, NX);
-      gQxx[(i0 + g) + (j0 + 2 * t) * NX] = acc[n][0];
-      gQxx[(i0 + g) + (j0 + 2 * t + 1) * NX] = acc[n][1];
+      kkt[K.k_Qxx + (i0 + g) + (j0 + 2 * t) * NX] = acc[n][0];
+      kkt[K.k_Qxx + (i0 + g) + (j0 + 2 * t + 1) * NX] = acc[n][1];
     }
   }
   if (!impact) {
@@ -513,15 +547,11 @@ __global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS, 4) condense_ke
       for (int n = 0; n < TU; ++n) {
         const int j0 = tile_off(n, NU);
         const int r = r0 + g;
-        acc[n][0] = (r >= np) ? __ldcg(gQuu + (r - np) + (j0 + 2 * t) * NU) : 0.0;
-        acc[n][1] = (r >= np) ? __ldcg(gQuu + (r - np) + (j0 + 2 * t + 1) * NU) : 0.0;
+        acc[n][0] = (r >= np) ? gQuu[(r - np) + (j0 + 2 * t) * NU] : 0.0;
+        acc[n][1] = (r >= np) ? gQuu[(r - np) + (j0 + 2 * t + 1) * NU] : 0.0;
       }
       warp_mma_band<NVF, TU, NU>(
           acc, r0, [&](int ii, int l) { return sZ[ii + l * NVF]; }, [&](int l, int j) { return sQu[l + (np + j) * NVF]; });
-      __syncwarp();
-      // the pulled-back band overlaps the previous one: both hold identical values for shared rows, and both read their
-      // Quu' fragments from a row range only they and their overlap partner touch; order reads before writes CTA-wide
-      named_bar_sync(1, 32 * TV);
 #pragma unroll
       for (int n = 0; n < TU; ++n) {
         const int j0 = tile_off(n, NU);
@@ -529,7 +559,7 @@ __global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS, 4) condense_ke
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           if (r < np) ex[S.e_Quup + r + (j0 + 2 * t + q) * np] = acc[n][q];
-          else gQuu[(r - np) + (j0 + 2 * t + q) * NU] = acc[n][q];
+          else kkt[K.k_Quu + (r - np) + (j0 + 2 * t + q) * NU] = acc[n][q];
         }
       }
     }
