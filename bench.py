@@ -300,20 +300,22 @@ def main():
         if ev is not None:
             ev[len(calls)].record(stream)
         if world > 1:
-            allgather_step(d_local, out=d_all)
+            allgather_step(d_local, out=d_all)  # the Newton step of every OCP on every rank (one NCCL all-gather)
+            if ev is not None:
+                ev[len(calls) + 1].record(stream)
 
     for _ in range(max(args.warmup, 3)):
         step()
     torch.cuda.synchronize()
+    l0 = rr.launch_count()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(7)] for _ in range(args.steps)]
+    t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    clk = ClockSampler(local)
+    if rank == 0 and not os.environ.get("RBT_BENCH_NO_CLOCKS"):
+        clk.start()  # (sleeps ~0.15 s while nvidia-smi spins up: must happen BEFORE the barrier that aligns the ranks)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    l0 = rr.launch_count()
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(args.steps)]
-    t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    clk = ClockSampler(local)
-    if rank == 0:
-        clk.start()
     t_host0 = time.perf_counter()
     t_beg.record(stream)
     for k in range(args.steps):
@@ -327,6 +329,9 @@ def main():
     launches = rr.launch_count() - l0
     ms = t_beg.elapsed_time(t_end)
     kms = {n: float(np.mean([e[k].elapsed_time(e[k + 1]) for e in evs])) for k, n in enumerate(NAMES)}
+    if world > 1:
+        kms["nccl_allgather_step"] = float(np.mean([e[5].elapsed_time(e[6]) for e in evs]))
+    print(f"[bench] rank {rank}: {ms / args.steps:.3f} ms/step on its own device clock", file=sys.stderr, flush=True)
     if world > 1:
         tt = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)

@@ -20,24 +20,24 @@ def shard_range(batch: int, world: int, rank: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def allgather_step(local, out=None, group=None):
-    """All-gather the per-rank direction tensor [b_local, n_grid, d_stride] into [sum b, n_grid, d_stride].
-    Equal shard sizes use all_gather_into_tensor (one NCCL call, in place into `out`); ragged shards are padded to the
+def allgather_step(local, global_batch=None, out=None, group=None):
+    """All-gather the per-rank tensor [b_local, ...] into [global_batch, ...] (rank-major, i.e. shard_range order).
+    Shard sizes follow from (global_batch, world) -- no size exchange, no host sync.  Equal shards: one
+    all_gather_into_tensor straight into `out` (NCCL, in place); ragged shards (global_batch % world != 0) are padded to the
     largest shard first."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
-    sizes = [torch.zeros(1, dtype=torch.int64, device=local.device) for _ in range(world)]
-    mine = torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device)
-    dist.all_gather(sizes, mine, group=group)
-    sizes = [int(s.item()) for s in sizes]
-    total = sum(sizes)
+    if global_batch is None:
+        global_batch = local.shape[0] * world
+    sizes = [shard_range(global_batch, world, r)[1] - shard_range(global_batch, world, r)[0] for r in range(world)]
+    if sizes[dist.get_rank(group)] != local.shape[0]:
+        raise ValueError("[allgather_step] invalid argument: local shard size does not match shard_range")
     if out is None:
-        out = torch.empty((total,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        out = torch.empty((global_batch,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
     if len(set(sizes)) == 1:
         dist.all_gather_into_tensor(out.view(-1), local.contiguous().view(-1), group=group)
     else:
-        # ragged shards (batch % world != 0): pad to the largest shard, gather, then compact
         mx = max(sizes)
         pad = torch.zeros((mx,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
         pad[:local.shape[0]].copy_(local)

@@ -19,7 +19,7 @@ def _worker(rank, world, port, batch, ragged, out_dir):
     lo, hi = shard_range(batch, world, rank)
     full = torch.arange(batch * 3 * 4, dtype=torch.float64).reshape(batch, 3, 4)  # stands for [batch, n_grid, d_stride]
     local = full[lo:hi].clone()
-    got = allgather_step(local)
+    got = allgather_step(local, global_batch=batch)
     ok = bool(torch.equal(got, full))
     np.save(os.path.join(out_dir, f"ok_{rank}.npy"), np.array([ok, lo, hi]))
     dist.destroy_process_group()
