@@ -1,0 +1,276 @@
+// robotoc_b200/riccati_recursion.hpp -- C++ host-side adaptor with the reference's class and method names on top of the
+// C ABI (include/robotoc_b200.h).  Header-only, C++14, no Eigen: the containers below are the subset of the reference's
+// Split* types that the Riccati path touches, with the reference's member names, column-major like Eigen::MatrixXd
+// (LQRPolicy::K row-major like include/robotoc/riccati/lqr_policy.hpp:18-19).  A reference build would keep its own
+// Eigen-based types and use the pack/unpack helpers with `.data()` pointers.
+//
+//   robotoc::RiccatiRecursion                 include/robotoc/riccati/riccati_recursion.hpp:26-119
+//   robotoc::SplitKKTMatrix / SplitKKTResidual  src/core/split_kkt_matrix.cpp:7-34, src/core/split_kkt_residual.cpp:7-20
+//   robotoc::SplitRiccatiFactorization, LQRPolicy, SplitDirection, GridInfo
+#pragma once
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+extern "C" {
+#include "../robotoc_b200.h"
+}
+
+namespace robotoc_b200 {
+
+struct Matrix {  // column-major, like Eigen::MatrixXd
+  int rows_ = 0, cols_ = 0;
+  std::vector<double> a;
+  Matrix() = default;
+  Matrix(int r, int c) : rows_(r), cols_(c), a(size_t(r) * c, 0.0) {}
+  double& operator()(int i, int j) { return a[size_t(i) + size_t(j) * rows_]; }
+  double operator()(int i, int j) const { return a[size_t(i) + size_t(j) * rows_]; }
+  double* data() { return a.data(); }
+  const double* data() const { return a.data(); }
+  int rows() const { return rows_; }
+  int cols() const { return cols_; }
+  size_t size() const { return a.size(); }
+};
+using Vector = std::vector<double>;
+
+enum class GridType { Intermediate, Impact, Lift, Terminal };  // grid_info.hpp:14-19
+
+struct GridInfo {  // grid_info.hpp:25-92 (fields read on this path)
+  GridType type = GridType::Intermediate;
+  double dt = 0;
+  bool sto = false, sto_next = false, switching_constraint = false;
+  int num_grids_in_phase = 1;
+  int dims = 0;  // dimension of the switching constraint attached to this grid (impact dimf), 0 if none
+  int dimf = 0;  // active contact dimension
+};
+using TimeDiscretization = std::vector<GridInfo>;  // size() == N+1 grid points, last one Terminal
+
+struct SplitKKTMatrix {
+  Matrix Fxx, Fvu, Qxx, Qxu, Quu, Phix_, Phiu_;
+  Vector fx, hx, hu, Phit_;
+  double Qtt = 0, Qtt_prev = 0;
+  int dims_ = 0;
+  SplitKKTMatrix() = default;
+  SplitKKTMatrix(int nv, int nu, int ns_max)
+      : Fxx(2 * nv, 2 * nv), Fvu(nv, nu), Qxx(2 * nv, 2 * nv), Qxu(2 * nv, nu), Quu(nu, nu), Phix_(ns_max, 2 * nv),
+        Phiu_(ns_max, nu), fx(2 * nv), hx(2 * nv), hu(nu), Phit_(ns_max) {}
+  void setSwitchingConstraintDimension(int dims) {
+    dims_ = dims;
+    Phix_ = Matrix(dims, Fxx.rows());
+    Phiu_ = Matrix(dims, Quu.rows());
+    Phit_.assign(dims, 0.0);
+  }
+  int dims() const { return dims_; }
+  Matrix& Phix() { return Phix_; }
+  Matrix& Phiu() { return Phiu_; }
+  Vector& Phit() { return Phit_; }
+};
+
+struct SplitKKTResidual {
+  Vector Fx, lx, lu, P_;
+  double h = 0;
+  SplitKKTResidual() = default;
+  SplitKKTResidual(int nv, int nu) : Fx(2 * nv), lx(2 * nv), lu(nu) {}
+  Vector& P() { return P_; }
+};
+
+struct SplitRiccatiFactorization {
+  Matrix P, M_;
+  Vector s, Psi, Phi, m_;
+  double xi = 0, chi = 0, rho = 0, eta = 0, iota = 0;
+  SplitRiccatiFactorization() = default;
+  explicit SplitRiccatiFactorization(int nv) : P(2 * nv, 2 * nv), s(2 * nv), Psi(2 * nv), Phi(2 * nv) {}
+  Matrix& M() { return M_; }
+  Vector& m() { return m_; }
+};
+
+struct LQRPolicy {
+  Matrix Kt;  // stores K^T column-major == the reference's row-major nu x nx K
+  Vector k, T, W;
+  LQRPolicy() = default;
+  LQRPolicy(int nv, int nu) : Kt(2 * nv, nu), k(nu), T(nu), W(nu) {}
+  double K(int u, int j) const { return Kt(j, u); }
+};
+
+struct SplitDirection {
+  Vector dx, du, dlmdgmm, dxi_;
+  double dts = 0, dts_next = 0;
+  SplitDirection() = default;
+  SplitDirection(int nv, int nu) : dx(2 * nv), du(nu), dlmdgmm(2 * nv) {}
+  Vector& dxi() { return dxi_; }
+};
+
+using KKTMatrix = std::vector<SplitKKTMatrix>;
+using KKTResidual = std::vector<SplitKKTResidual>;
+using RiccatiFactorization = std::vector<SplitRiccatiFactorization>;
+using Direction = std::vector<SplitDirection>;
+
+/// Drop-in for robotoc::RiccatiRecursion (riccati_recursion.hpp:26-119) for ONE OCP (batch = 1).  Batched callers use
+/// the C ABI (or the Python mirror) directly.
+class RiccatiRecursion {
+ public:
+  /// RiccatiRecursion(const OCP& ocp, double max_dts0) -- `dims` and `n_grid_max` (= N+1+reserved events) stand for the OCP.
+  RiccatiRecursion(const rbt_dims& dims, int n_grid_max, double max_dts0 = 0.1, int device = 0)
+      : dims_(dims), n_grid_max_(n_grid_max), max_dts0_(max_dts0) {
+    if (max_dts0 <= 0) throw std::out_of_range("[RiccatiRecursion] invalid argument: 'max_dts0' must be positive!");
+    rbt_make_layout(&dims_, &L_);
+    const int rc = rbt_create(&dims_, n_grid_max, 1, device, &h_);
+    if (rc != RBT_OK) {
+      const std::string msg = h_ ? rbt_last_error(h_) : "unsupported robot dimensions";
+      if (h_) rbt_destroy(h_);
+      h_ = nullptr;
+      throw std::runtime_error("[RiccatiRecursion] cannot create the B200 handle: " + msg);
+    }
+    lqr_policy_.assign(n_grid_max, LQRPolicy(dims_.nv, dims_.nu));
+  }
+  ~RiccatiRecursion() {
+    if (h_) rbt_destroy(h_);
+  }
+  RiccatiRecursion(const RiccatiRecursion&) = delete;
+  RiccatiRecursion& operator=(const RiccatiRecursion&) = delete;
+
+  void setRegularization(double max_dts0) {  // riccati_recursion.hpp:58
+    if (max_dts0 <= 0) throw std::out_of_range("[RiccatiRecursion] invalid argument: 'max_dts0' must be positive!");
+    max_dts0_ = max_dts0;
+  }
+
+  /// riccati_recursion.cpp:32-80.  kkt_matrix / kkt_residual are mutated like the reference (Qxx,Qxu,Quu,lu <- F,H,G,lu').
+  void backwardRiccatiRecursion(const TimeDiscretization& td, KKTMatrix& kkt_matrix, KKTResidual& kkt_residual,
+                                RiccatiFactorization& factorization) {
+    const int n_grid = int(td.size());
+    setSchedule(td);
+    const int nx = L_.nx, nu = L_.nu, nv = L_.nv;
+    kkt_.assign(size_t(n_grid) * L_.k_stride, 0.0);
+    for (int i = 0; i < n_grid; ++i) {
+      double* rec = kkt_.data() + size_t(i) * L_.k_stride;
+      SplitKKTMatrix& km = kkt_matrix[i];
+      SplitKKTResidual& kr = kkt_residual[i];
+      put(rec + L_.k_Qxx, km.Qxx.data(), nx * nx);
+      put(rec + L_.k_lx, kr.lx.data(), nx);
+      if (td[i].type == GridType::Terminal) continue;
+      put(rec + L_.k_Fxx, km.Fxx.data(), nx * nx);
+      put(rec + L_.k_Fx, kr.Fx.data(), nx);
+      if (td[i].type == GridType::Impact) continue;
+      put(rec + L_.k_Fvu, km.Fvu.data(), nv * nu);
+      put(rec + L_.k_Qxu, km.Qxu.data(), nx * nu);
+      put(rec + L_.k_Quu, km.Quu.data(), nu * nu);
+      put(rec + L_.k_lu, kr.lu.data(), nu);
+      const int ns = ctrl_[i].ns;
+      if (ns > 0) {
+        put(rec + L_.k_Phix, km.Phix_.data(), ns * nx);
+        put(rec + L_.k_Phiu, km.Phiu_.data(), ns * nu);
+        put(rec + L_.k_p, kr.P_.data(), ns);
+      }
+      if (td[i].sto) {
+        put(rec + L_.k_fx, km.fx.data(), nx);
+        put(rec + L_.k_hx, km.hx.data(), nx);
+        put(rec + L_.k_hu, km.hu.data(), nu);
+        if (ns > 0) put(rec + L_.k_Phit, km.Phit_.data(), ns);
+        rec[L_.k_sc + 0] = km.Qtt;
+        rec[L_.k_sc + 1] = km.Qtt_prev;
+        rec[L_.k_sc + 2] = kr.h;
+      }
+    }
+    check(rbt_upload(h_, RBT_BUF_KKT, kkt_.data(), nullptr));
+    check(rbt_riccati_backward(h_, /*write_fact=*/1, nullptr));
+    ric_.resize(size_t(n_grid) * L_.r_stride);
+    fact_.resize(size_t(n_grid) * L_.f_stride);
+    check(rbt_download(h_, RBT_BUF_RIC, ric_.data(), nullptr));
+    check(rbt_download(h_, RBT_BUF_FACT, fact_.data(), nullptr));
+    check(rbt_sync(h_, nullptr));
+    factorization.resize(n_grid);
+    for (int i = 0; i < n_grid; ++i) {
+      const double* r = ric_.data() + size_t(i) * L_.r_stride;
+      SplitRiccatiFactorization& f = factorization[i];
+      if (f.P.rows() != nx) f = SplitRiccatiFactorization(nv);
+      get(f.P.data(), r + L_.r_P, nx * nx);
+      get(f.s.data(), r + L_.r_s, nx);
+      get(f.Psi.data(), r + L_.r_Psi, nx);
+      get(f.Phi.data(), r + L_.r_Phi, nx);
+      f.xi = r[L_.r_sc + 0]; f.chi = r[L_.r_sc + 1]; f.rho = r[L_.r_sc + 2]; f.eta = r[L_.r_sc + 3]; f.iota = r[L_.r_sc + 4];
+      if (td[i].type == GridType::Terminal || td[i].type == GridType::Impact) continue;
+      LQRPolicy& pol = lqr_policy_[i];
+      get(pol.Kt.data(), r + L_.r_K, nx * nu);
+      get(pol.k.data(), r + L_.r_k, nu);
+      get(pol.T.data(), r + L_.r_T, nu);
+      get(pol.W.data(), r + L_.r_W, nu);
+      const int ns = ctrl_[i].ns;
+      if (ns > 0) {
+        f.M_ = Matrix(ns, nx);
+        f.m_.assign(ns, 0.0);
+        get(f.M_.data(), r + L_.r_M, ns * nx);
+        get(f.m_.data(), r + L_.r_m, ns);
+      }
+      const double* fc = fact_.data() + size_t(i) * L_.f_stride;  // in-place mutation semantics of the reference
+      get(kkt_matrix[i].Qxx.data(), fc + L_.f_F, nx * nx);
+      get(kkt_matrix[i].Qxu.data(), fc + L_.f_H, nx * nu);
+      get(kkt_matrix[i].Quu.data(), fc + L_.f_G, nu * nu);
+      get(kkt_residual[i].lu.data(), fc + L_.f_lu, nu);
+    }
+  }
+
+  /// riccati_recursion.cpp:83-131; d[0].dx must hold the initial state direction.
+  void forwardRiccatiRecursion(const TimeDiscretization& td, const KKTMatrix&, const KKTResidual&,
+                               const RiccatiFactorization&, Direction& d) {
+    const int n_grid = int(td.size());
+    check(rbt_upload(h_, RBT_BUF_DX0, d[0].dx.data(), nullptr));
+    check(rbt_riccati_forward(h_, nullptr));
+    dir_.resize(size_t(n_grid) * L_.d_stride);
+    check(rbt_download(h_, RBT_BUF_DIR, dir_.data(), nullptr));
+    check(rbt_sync(h_, nullptr));
+    for (int i = 0; i < n_grid; ++i) {
+      const double* r = dir_.data() + size_t(i) * L_.d_stride;
+      get(d[i].dx.data(), r + L_.d_dx, L_.nx);
+      get(d[i].du.data(), r + L_.d_du, L_.nu);
+      get(d[i].dlmdgmm.data(), r + L_.d_dlmdgmm, L_.nx);
+      d[i].dts = r[L_.d_dts];
+      d[i].dts_next = r[L_.d_dts + 1];
+      if (ctrl_[i].ns > 0) {
+        d[i].dxi_.assign(ctrl_[i].ns, 0.0);
+        get(d[i].dxi_.data(), r + L_.d_dxi, ctrl_[i].ns);
+      }
+    }
+  }
+
+  const std::vector<LQRPolicy>& getLQRPolicy() const { return lqr_policy_; }  // riccati_recursion.hpp:104
+  const rbt_layout& layout() const { return L_; }
+
+ private:
+  static void put(double* dst, const double* src, int n) { std::memcpy(dst, src, sizeof(double) * size_t(n)); }
+  static void get(double* dst, const double* src, int n) { std::memcpy(dst, src, sizeof(double) * size_t(n)); }
+  void check(int rc) {
+    if (rc == RBT_OK) return;
+    const std::string msg = rbt_last_error(h_);
+    if (rc == RBT_ERR_ARG) throw std::invalid_argument("[RiccatiRecursion] invalid argument: " + msg);
+    throw std::runtime_error("[RiccatiRecursion] " + msg);
+  }
+  void setSchedule(const TimeDiscretization& td) {
+    if (int(td.size()) > n_grid_max_) throw std::out_of_range("[RiccatiRecursion] invalid argument: horizon longer than reserved");
+    ctrl_.assign(td.size(), rbt_stage_ctrl());
+    for (size_t i = 0; i < td.size(); ++i) {
+      rbt_stage_ctrl& c = ctrl_[i];
+      c.type = int(td[i].type);
+      c.sto = td[i].sto;
+      c.sto_next = td[i].sto_next;
+      c.ns = td[i].switching_constraint ? td[i].dims : 0;
+      c.nf = td[i].dimf;
+      c.ngrids_in_phase = td[i].num_grids_in_phase;
+      c.contact_mask = (1 << (td[i].dimf / 3)) - 1;
+      c.reserved_ = 0;
+      c.dt = td[i].dt;
+    }
+    check(rbt_set_schedule(h_, ctrl_.data(), int(td.size()), max_dts0_));
+  }
+
+  rbt_dims dims_;
+  rbt_layout L_;
+  int n_grid_max_;
+  double max_dts0_;
+  rbt_handle* h_ = nullptr;
+  std::vector<rbt_stage_ctrl> ctrl_;
+  std::vector<LQRPolicy> lqr_policy_;
+  std::vector<double> kkt_, ric_, fact_, dir_;
+};
+
+}  // namespace robotoc_b200
