@@ -20,6 +20,7 @@
 
 #include "rbt_layout.h"
 #include "rbt_stage_layout.h"
+#include "rbt_ustage_layout.h"
 
 #ifdef __cplusplus
 extern "C" {
@@ -154,6 +155,24 @@ int rbt_unconstr_backward(rbt_uhandle* h, int write_fact, void* stream);
 int rbt_unconstr_forward(rbt_uhandle* h, void* stream);
 int rbt_unconstr_solve_host(rbt_uhandle* h, const double* kkt_host, const double* dx0_host, double* ric_host,
                             double* dir_host, void* stream);
+/* Stage layer of the unconstrained path -- the condensing tail of UnconstrIntermediateStage::evalKKT and the expansion /
+ * step-size / update half of robotoc::UnconstrDirectMultipleShooting
+ * (include/robotoc/unconstr/unconstr_direct_multiple_shooting.hpp; src/unconstr/unconstr_direct_multiple_shooting.cpp:88-179).
+ * Records: include/rbt_ustage_layout.h.  `table` holds the joint position / velocity / acceleration / torque limits
+ * (n_contacts must be 0). */
+int rbt_unconstr_stage_layout_get(int nv, int n_box, const char* field);
+int rbt_unconstr_stage_setup(rbt_uhandle* h, const rbt_constraint_table* table);
+/* Constraints::condenseSlackAndDual + UnconstrDynamics::condenseUnconstrDynamics (src/dynamics/unconstr_dynamics.cpp:67-87)
+ * on every stage; terminal stage: Qxx, lx.  Reads RBT_BUF_LIN, RBT_BUF_CON; writes RBT_BUF_KKT, RBT_BUF_EXP, RBT_BUF_CON. */
+int rbt_unconstr_condense(rbt_uhandle* h, void* stream);
+/* UnconstrDirectMultipleShooting::computeStepSizes + maxPrimalStepSize / maxDualStepSize (:128-156): expandPrimal, expandDual
+ * (unconstr_dynamics.cpp:90-104), slack/dual directions, fraction-to-boundary, min over the horizon -> RBT_BUF_STEPS. */
+int rbt_unconstr_expand_and_step_sizes(rbt_uhandle* h, void* stream);
+/* UnconstrDirectMultipleShooting::integrateSolution (:159-179) with the step sizes of RBT_BUF_STEPS. */
+int rbt_unconstr_update(rbt_uhandle* h, void* stream);
+/* The linear-algebra body of UnconstrOCPSolver::updateSolution (src/solver/unconstr_ocp_solver.cpp:101-118) with HOST buffers. */
+int rbt_unconstr_iteration_host(rbt_uhandle* h, const double* lin_host, const double* con_host, const double* sol_host,
+                                const double* dx0_host, double* sol_out, double* con_out, double* steps_out, void* stream);
 int rbt_unconstr_sync(rbt_uhandle* h, void* stream);
 const char* rbt_unconstr_last_error(rbt_uhandle* h);
 long long rbt_unconstr_launch_count(rbt_uhandle* h);

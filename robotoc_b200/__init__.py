@@ -13,3 +13,4 @@ from .dms import DirectMultipleShooting  # noqa: F401
 
 ANYMAL = Dims(nv=18, nu=12, ns_max=12, n_passive=6)
 IIWA14_NV = 7
+from .unconstr_dms import UnconstrDirectMultipleShooting, iiwa14_constraint_table  # noqa: F401

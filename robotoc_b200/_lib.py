@@ -31,7 +31,8 @@ EXPORTS = [
     "rbt_unconstr_create", "rbt_unconstr_destroy", "rbt_unconstr_dev_ptr", "rbt_unconstr_buf_doubles",
     "rbt_unconstr_upload", "rbt_unconstr_download", "rbt_unconstr_download_info", "rbt_unconstr_backward",
     "rbt_unconstr_forward", "rbt_unconstr_solve_host", "rbt_unconstr_sync", "rbt_unconstr_last_error",
-    "rbt_unconstr_launch_count",
+    "rbt_unconstr_launch_count", "rbt_unconstr_stage_layout_get", "rbt_unconstr_stage_setup", "rbt_unconstr_condense",
+    "rbt_unconstr_expand_and_step_sizes", "rbt_unconstr_update", "rbt_unconstr_iteration_host",
 ]
 
 
@@ -97,6 +98,12 @@ def lib():
     L.rbt_unconstr_last_error.restype = ctypes.c_char_p
     L.rbt_unconstr_launch_count.argtypes = [c_vp]
     L.rbt_unconstr_launch_count.restype = c_ll
+    L.rbt_unconstr_stage_layout_get.argtypes = [c_int, c_int, ctypes.c_char_p]
+    L.rbt_unconstr_stage_setup.argtypes = [c_vp, c_vp]
+    L.rbt_unconstr_condense.argtypes = [c_vp, c_vp]
+    L.rbt_unconstr_expand_and_step_sizes.argtypes = [c_vp, c_vp]
+    L.rbt_unconstr_update.argtypes = [c_vp, c_vp]
+    L.rbt_unconstr_iteration_host.argtypes = [c_vp] * 9
     _ = pd
     _lib = L
     return L

@@ -14,6 +14,7 @@
 #include "riccati_forward.cuh"
 #include "riccati_unconstr.cuh"
 #include "stage_kernels.cuh"
+#include "ustage_kernels.cuh"
 
 namespace {
 
@@ -69,6 +70,12 @@ struct rbt_uhandle {
   rbt_ulayout L;
   double *d_kkt = nullptr, *d_ric = nullptr, *d_fact = nullptr, *d_dir = nullptr, *d_dx0 = nullptr;
   int* d_info = nullptr;
+  // stage layer
+  bool stage_ready = false;
+  rbt_ustage_layout S;
+  rbt_constraint_table table;
+  double *d_lin = nullptr, *d_con = nullptr, *d_ex = nullptr, *d_sol = nullptr, *d_xd = nullptr, *d_steps = nullptr,
+         *d_ones = nullptr;
   long long launches = 0;
   std::string err;
 };
@@ -669,6 +676,13 @@ int rbt_unconstr_destroy(rbt_uhandle* h) {
   cudaFree(h->d_dir);
   cudaFree(h->d_dx0);
   cudaFree(h->d_info);
+  cudaFree(h->d_lin);
+  cudaFree(h->d_con);
+  cudaFree(h->d_ex);
+  cudaFree(h->d_sol);
+  cudaFree(h->d_xd);
+  cudaFree(h->d_steps);
+  cudaFree(h->d_ones);
   delete h;
   return RBT_OK;
 }
@@ -680,6 +694,12 @@ static double* ubuf_ptr(rbt_uhandle* h, int which) {
     case RBT_BUF_FACT: return h->d_fact;
     case RBT_BUF_DIR: return h->d_dir;
     case RBT_BUF_DX0: return h->d_dx0;
+    case RBT_BUF_LIN: return h->d_lin;
+    case RBT_BUF_CON: return h->d_con;
+    case RBT_BUF_EXP: return h->d_ex;
+    case RBT_BUF_SOL: return h->d_sol;
+    case RBT_BUF_XDIR: return h->d_xd;
+    case RBT_BUF_STEPS: return h->d_steps;
     default: return nullptr;
   }
 }
@@ -693,6 +713,16 @@ long long rbt_unconstr_buf_doubles(rbt_uhandle* h, int which) {
     case RBT_BUF_FACT: return per * h->L.f_stride;
     case RBT_BUF_DIR: return per * h->L.d_stride;
     case RBT_BUF_DX0: return (long long)h->batch * h->L.nx;
+    default: break;
+  }
+  if (!h->stage_ready) return -1;
+  switch (which) {
+    case RBT_BUF_LIN: return per * h->S.l_stride;
+    case RBT_BUF_CON: return per * h->S.c_stride;
+    case RBT_BUF_EXP: return per * h->S.e_stride;
+    case RBT_BUF_SOL: return per * h->S.s_stride;
+    case RBT_BUF_XDIR: return per * h->S.x_stride;
+    case RBT_BUF_STEPS: return (long long)h->batch * 2;
     default: return -1;
   }
 }
@@ -700,7 +730,13 @@ long long rbt_unconstr_buf_doubles(rbt_uhandle* h, int which) {
 double* rbt_unconstr_dev_ptr(rbt_uhandle* h, int which) { return h ? ubuf_ptr(h, which) : nullptr; }
 
 int rbt_unconstr_upload(rbt_uhandle* h, int which, const double* host, void* stream) {
-  if (!h || !host || (which != RBT_BUF_KKT && which != RBT_BUF_DX0)) return RBT_ERR_ARG;
+  if (!h || !host) return RBT_ERR_ARG;
+  if (which != RBT_BUF_KKT && which != RBT_BUF_DX0 && which != RBT_BUF_LIN && which != RBT_BUF_CON && which != RBT_BUF_SOL)
+    return RBT_ERR_ARG;
+  if (!ubuf_ptr(h, which)) {
+    h->err = "rbt_unconstr_upload: stage layer not set up (rbt_unconstr_stage_setup)";
+    return RBT_ERR_STATE;
+  }
   RBT_CUDA(h, cudaSetDevice(h->device));
   RBT_CUDA(h, cudaMemcpyAsync(ubuf_ptr(h, which), host, size_t(rbt_unconstr_buf_doubles(h, which)) * 8,
                               cudaMemcpyHostToDevice, (cudaStream_t)stream));
@@ -790,6 +826,151 @@ int rbt_unconstr_sync(rbt_uhandle* h, void* stream) {
   if (!h) return RBT_ERR_ARG;
   RBT_CUDA(h, cudaSetDevice(h->device));
   RBT_CUDA(h, cudaStreamSynchronize((cudaStream_t)stream));
+  return RBT_OK;
+}
+
+// ---- stage layer of the unconstrained path
+int rbt_unconstr_stage_layout_get(int nv, int n_box, const char* field) {
+  if (nv < 1 || n_box < 0 || !field) return -1;
+  rbt_ustage_layout S;
+  rbt_make_ustage_layout(nv, n_box, &S);
+  return rbt_ustage_layout_field(&S, field);
+}
+
+int rbt_unconstr_stage_setup(rbt_uhandle* h, const rbt_constraint_table* table) {
+  if (!h || !table) return RBT_ERR_ARG;
+  if (table->n_box < 0 || table->n_box > RBT_MAX_BOX_ROWS || table->n_contacts != 0 || !(table->barrier > 0) ||
+      !(table->fraction_to_boundary > 0 && table->fraction_to_boundary < 1)) {
+    h->err = "rbt_unconstr_stage_setup: invalid constraint table (n_box range, n_contacts must be 0, barrier > 0, 0 < fraction_to_boundary < 1)";
+    return RBT_ERR_ARG;
+  }
+  for (int r = 0; r < table->n_box; ++r) {
+    const rbt_box_row& b = table->box[r];
+    if (b.var < RBT_VAR_Q || b.var > RBT_VAR_U || b.idx < 0 || b.idx >= h->nv || (b.sign != 1 && b.sign != -1)) {
+      h->err = "rbt_unconstr_stage_setup: box row " + std::to_string(r) + " out of range";
+      return RBT_ERR_ARG;
+    }
+  }
+  if (h->stage_ready) {
+    h->err = "rbt_unconstr_stage_setup: already set up";
+    return RBT_ERR_STATE;
+  }
+  RBT_CUDA(h, cudaSetDevice(h->device));
+  rbt_make_ustage_layout(h->nv, table->n_box, &h->S);
+  h->table = *table;
+  const size_t per = size_t(h->batch) * (h->N + 1);
+  RBT_CUDA(h, cudaMalloc(&h->d_lin, per * h->S.l_stride * 8));
+  RBT_CUDA(h, cudaMalloc(&h->d_con, per * h->S.c_stride * 8));
+  RBT_CUDA(h, cudaMalloc(&h->d_ex, per * h->S.e_stride * 8));
+  RBT_CUDA(h, cudaMalloc(&h->d_sol, per * h->S.s_stride * 8));
+  RBT_CUDA(h, cudaMalloc(&h->d_xd, per * h->S.x_stride * 8));
+  RBT_CUDA(h, cudaMalloc(&h->d_steps, size_t(h->batch) * 2 * 8));
+  RBT_CUDA(h, cudaMalloc(&h->d_ones, size_t(h->batch) * 2 * 8));
+  RBT_CUDA(h, cudaMemset(h->d_lin, 0, per * h->S.l_stride * 8));
+  RBT_CUDA(h, cudaMemset(h->d_con, 0, per * h->S.c_stride * 8));
+  RBT_CUDA(h, cudaMemset(h->d_ex, 0, per * h->S.e_stride * 8));
+  RBT_CUDA(h, cudaMemset(h->d_sol, 0, per * h->S.s_stride * 8));
+  RBT_CUDA(h, cudaMemset(h->d_xd, 0, per * h->S.x_stride * 8));
+  std::vector<double> ones(size_t(h->batch) * 2, 1.0);
+  RBT_CUDA(h, cudaMemcpy(h->d_ones, ones.data(), ones.size() * 8, cudaMemcpyHostToDevice));
+  RBT_CUDA(h, cudaMemcpy(h->d_steps, ones.data(), ones.size() * 8, cudaMemcpyHostToDevice));
+  h->stage_ready = true;
+  return RBT_OK;
+}
+
+static rbt::UStageParams make_ustage_params(rbt_uhandle* h) {
+  rbt::UStageParams p;
+  p.K = h->L;
+  p.S = h->S;
+  p.tab = h->table;
+  p.N = h->N;
+  p.batch = h->batch;
+  p.dt = h->dt;
+  p.lin = h->d_lin;
+  p.con = h->d_con;
+  p.kkt = h->d_kkt;
+  p.ex = h->d_ex;
+  p.dir = h->d_dir;
+  p.xd = h->d_xd;
+  p.sol = h->d_sol;
+  p.steps = h->d_steps;
+  return p;
+}
+
+#define RBT_USTAGE_GUARD(h)                                                              \
+  if (!h) return RBT_ERR_ARG;                                                            \
+  if (!h->stage_ready) {                                                                 \
+    h->err = "stage layer not set up: call rbt_unconstr_stage_setup first";              \
+    return RBT_ERR_STATE;                                                                \
+  }                                                                                      \
+  RBT_CUDA(h, cudaSetDevice(h->device));                                                 \
+  cudaStream_t st = (cudaStream_t)stream;
+
+int rbt_unconstr_condense(rbt_uhandle* h, void* stream) {
+  RBT_USTAGE_GUARD(h)
+  const size_t total = size_t(h->batch) * (h->N + 1);
+#define X(NV)                                                                                         \
+  if (h->nv == NV) {                                                                                  \
+    if (rbt::UStageCfg<NV>::LSTRIDE != h->S.l_stride) return RBT_ERR_STATE;                            \
+    constexpr int W = rbt::UStageCfg<NV>::WARPS;                                                      \
+    rbt::ucondense_kernel<NV><<<unsigned((total + W - 1) / W), 32 * W, 0, st>>>(make_ustage_params(h)); \
+    RBT_CUDA(h, cudaGetLastError());                                                                  \
+    h->launches += 1;                                                                                 \
+    return RBT_OK;                                                                                    \
+  }
+  RBT_UINSTANCES(X)
+#undef X
+  return RBT_ERR_ARG;
+}
+
+int rbt_unconstr_expand_and_step_sizes(rbt_uhandle* h, void* stream) {
+  RBT_USTAGE_GUARD(h)
+  const size_t total = size_t(h->batch) * h->N;
+  RBT_CUDA(h, cudaMemcpyAsync(h->d_steps, h->d_ones, size_t(h->batch) * 2 * 8, cudaMemcpyDeviceToDevice, st));
+#define X(NV)                                                                                 \
+  if (h->nv == NV) {                                                                          \
+    rbt::uexpand_kernel<NV><<<unsigned((total + 3) / 4), 128, 0, st>>>(make_ustage_params(h)); \
+    RBT_CUDA(h, cudaGetLastError());                                                          \
+    h->launches += 1;                                                                         \
+    return RBT_OK;                                                                            \
+  }
+  RBT_UINSTANCES(X)
+#undef X
+  return RBT_ERR_ARG;
+}
+
+int rbt_unconstr_update(rbt_uhandle* h, void* stream) {
+  RBT_USTAGE_GUARD(h)
+  const size_t total = size_t(h->batch) * (h->N + 1);
+#define X(NV)                                                                                 \
+  if (h->nv == NV) {                                                                          \
+    rbt::uupdate_kernel<NV><<<unsigned((total + 3) / 4), 128, 0, st>>>(make_ustage_params(h)); \
+    RBT_CUDA(h, cudaGetLastError());                                                          \
+    h->launches += 1;                                                                         \
+    return RBT_OK;                                                                            \
+  }
+  RBT_UINSTANCES(X)
+#undef X
+  return RBT_ERR_ARG;
+}
+
+int rbt_unconstr_iteration_host(rbt_uhandle* h, const double* lin_host, const double* con_host, const double* sol_host,
+                                const double* dx0_host, double* sol_out, double* con_out, double* steps_out,
+                                void* stream) {
+  if (!h || !lin_host || !con_host || !sol_host || !dx0_host) return RBT_ERR_ARG;
+  int rc;
+  if ((rc = rbt_unconstr_upload(h, RBT_BUF_LIN, lin_host, stream))) return rc;
+  if ((rc = rbt_unconstr_upload(h, RBT_BUF_CON, con_host, stream))) return rc;
+  if ((rc = rbt_unconstr_upload(h, RBT_BUF_SOL, sol_host, stream))) return rc;
+  if ((rc = rbt_unconstr_upload(h, RBT_BUF_DX0, dx0_host, stream))) return rc;
+  if ((rc = rbt_unconstr_condense(h, stream))) return rc;
+  if ((rc = rbt_unconstr_backward(h, 0, stream))) return rc;
+  if ((rc = rbt_unconstr_forward(h, stream))) return rc;
+  if ((rc = rbt_unconstr_expand_and_step_sizes(h, stream))) return rc;
+  if ((rc = rbt_unconstr_update(h, stream))) return rc;
+  if (sol_out && (rc = rbt_unconstr_download(h, RBT_BUF_SOL, sol_out, stream))) return rc;
+  if (con_out && (rc = rbt_unconstr_download(h, RBT_BUF_CON, con_out, stream))) return rc;
+  if (steps_out && (rc = rbt_unconstr_download(h, RBT_BUF_STEPS, steps_out, stream))) return rc;
   return RBT_OK;
 }
 

@@ -48,6 +48,19 @@ def load():
     L.orc_expand_batch.restype = None
     L.orc_update_batch.argtypes = [psd, ptab, pctrl, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int]
     L.orc_update_batch.restype = None
+    L.orc_ustage_layout_get.argtypes = [c_int, c_int, ctypes.c_char_p]
+    L.orc_ustage_condense.argtypes = [c_int, ptab, c_int, c_vp, c_vp, c_vp, c_vp]
+    L.orc_ustage_condense.restype = None
+    L.orc_ustage_expand.argtypes = [c_int, ptab, c_dbl, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]
+    L.orc_ustage_expand.restype = None
+    L.orc_ustage_update.argtypes = [c_int, ptab, c_int, c_vp, c_vp, c_vp, c_vp, c_dbl, c_dbl]
+    L.orc_ustage_update.restype = None
+    L.orc_ucondense_batch.argtypes = [c_int, ptab, c_int, c_int, c_vp, c_vp, c_vp, c_vp]
+    L.orc_ucondense_batch.restype = None
+    L.orc_uexpand_batch.argtypes = [c_int, ptab, c_int, c_dbl, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]
+    L.orc_uexpand_batch.restype = None
+    L.orc_uupdate_batch.argtypes = [c_int, ptab, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp]
+    L.orc_uupdate_batch.restype = None
     _lib = L
     return L
 
@@ -79,3 +92,25 @@ def unconstr_batch(nv, UL, N, dt, kkt, dx0, nthreads=0, forward=True):
     info = lib.orc_unconstr_batch(nv, N, dt, batch, ptr(kk), ptr(ric), ptr(dx0) if forward else None,
                                   ptr(d) if forward else None, nthreads)
     return kk, ric, d, info
+
+
+def unconstr_iteration(nv, UL, S, tab, N, dt, lin, con, sol, dx0):
+    """One hot-path iteration of the unconstrained solver on the oracle (UnconstrOCPSolver::updateSolution's linear-algebra
+    body, unconstr_ocp_solver.cpp:101-118).  Returns a dict of every intermediate record."""
+    lib = load()
+    batch = lin.shape[0]
+    con = con.copy()
+    sol = sol.copy()
+    kkt = np.zeros((batch, N + 1, UL.k_stride))
+    ex = np.zeros((batch, N + 1, S.e_stride))
+    lib.orc_ucondense_batch(nv, ctypes.byref(tab), N, batch, ptr(lin), ptr(con), ptr(kkt), ptr(ex))
+    kkt_c = kkt.copy()
+    con_c = con.copy()
+    kk, ric, d, info = unconstr_batch(nv, UL, N, dt, kkt, dx0)
+    xd = np.zeros((batch, N + 1, S.x_stride))
+    steps = np.zeros((batch, 2))
+    lib.orc_uexpand_batch(nv, ctypes.byref(tab), N, dt, batch, ptr(lin), ptr(ex), ptr(d), ptr(con), ptr(xd), ptr(steps))
+    con_e = con.copy()
+    lib.orc_uupdate_batch(nv, ctypes.byref(tab), N, batch, ptr(d), ptr(xd), ptr(con), ptr(sol), ptr(steps))
+    return dict(kkt=kkt_c, ex=ex, con_condensed=con_c, ric=ric, dir=d, xd=xd, steps=steps, con_expanded=con_e, con=con,
+                sol=sol, info=info)
