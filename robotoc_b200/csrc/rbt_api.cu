@@ -486,6 +486,10 @@ int rbt_stage_setup(rbt_handle* h, const rbt_stage_dims* sd, const rbt_constrain
   h->sdims = *sd;
   h->table = *table;
   rbt_make_stage_layout(sd, &h->S);
+  if (h->S.ncp > 160 || h->S.l_stride - h->S.l_dgdq > 512) {  // shared-memory staging areas of expand_kernel
+    h->err = "[rbt_stage_setup] invalid argument: more than 160 inequality rows or more than 4 friction cones";
+    return RBT_ERR_ARG;
+  }
   RBT_CUDA(h, cudaSetDevice(h->device));
   const size_t per = size_t(h->batch) * h->n_grid_max;
   RBT_CUDA(h, cudaMalloc(&h->d_lin, per * h->S.l_stride * 8));
@@ -556,7 +560,7 @@ int rbt_condense(rbt_handle* h, void* stream) {
   }
   cudaStream_t st = (cudaStream_t)stream;
   RBT_CUDA(h, cudaMemsetAsync(h->d_info, 0, size_t(h->batch) * sizeof(int), st));
-  rbt::mjtjinv_kernel<18, 12><<<h->batch * h->n_grid, 64, 0, st>>>(make_stage_params(h));  // K1: Z = [[M,J^T],[J,0]]^-1
+  rbt::mjtjinv_kernel<18, 12><<<(h->batch * h->n_grid + 1) / 2, 64, 0, st>>>(make_stage_params(h));  // K1: Z = [[M,J^T],[J,0]]^-1
   RBT_CUDA(h, cudaGetLastError());
   kern<<<h->batch * h->n_grid, C::NTHREADS, C::SMEM_BYTES, st>>>(make_stage_params(h));     // K2: condensing (DMMA)
   RBT_CUDA(h, cudaGetLastError());
@@ -569,7 +573,7 @@ int rbt_expand_and_step_sizes(rbt_handle* h, void* stream) {
   RBT_STAGE_CHECK(h, "rbt_expand_and_step_sizes");
   cudaStream_t st = (cudaStream_t)stream;
   RBT_CUDA(h, cudaMemcpyAsync(h->d_steps, h->d_ones, size_t(h->batch) * 2 * 8, cudaMemcpyDeviceToDevice, st));
-  rbt::expand_kernel<18, 12, 12><<<h->batch * h->n_grid, 64, 0, st>>>(make_stage_params(h));
+  rbt::expand_kernel<18, 12, 12><<<h->batch * h->n_grid, rbt::XTHR, 0, st>>>(make_stage_params(h));
   RBT_CUDA(h, cudaGetLastError());
   h->launches += 1;
   return RBT_OK;
@@ -577,7 +581,7 @@ int rbt_expand_and_step_sizes(rbt_handle* h, void* stream) {
 
 int rbt_update(rbt_handle* h, void* stream) {
   RBT_STAGE_CHECK(h, "rbt_update");
-  rbt::update_kernel<18, 12, 12><<<h->batch * h->n_grid, 64, 0, (cudaStream_t)stream>>>(make_stage_params(h));
+  rbt::update_kernel<18, 12, 12><<<h->batch * h->n_grid, rbt::XTHR, 0, (cudaStream_t)stream>>>(make_stage_params(h));
   RBT_CUDA(h, cudaGetLastError());
   h->launches += 1;
   return RBT_OK;

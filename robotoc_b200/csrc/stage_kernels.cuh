@@ -87,123 +87,183 @@ __device__ __forceinline__ void se3_jac_inverse_dev(const double* Jac, double* J
 
 // ------------------------------------------------------------------------------------------------------------------
 // K1: Z = [[M, J^T],[J, 0]]^-1  (Robot::computeMJtJinv, include/robotoc/robot/robot.hxx:642-683, dense restatement)
-// Pure dependency chains (two Choleskys, two triangular inverses): 64 threads and 16 KB of shared memory per stage, so
-// ~12 stages per SM are in flight and hide each other's fp64 latency.  Writes the full (zero-padded) Z into the
-// expansion record; condense_kernel (K2) reads it back from L2.
+//
+// One WARP per stage, no CTA barrier.  With M = L L^T, X = L^-1, W = X J^T, S = W^T W = Ls Ls^T, Y = Ls^-1, V = W Y^T,
+// U = X^T V:      Z11 = X^T X - U U^T,   Z12 = U Y,   Z22 = -Y^T Y.
+// The two Choleskys and the two triangular inverses are dependency chains on one warp (lane = row / column); the seven
+// products run on the fp64 tensor pipe (DMMA m8n8k4, ~200 per stage) fed from 11 KB of shared memory per warp, so ~20
+// stages per SM are in flight and hide each other's fp64 latency.  Z goes to the expansion record; K2 reads it from L2.
+template <int NMAX>
+__device__ __forceinline__ bool warp_cholesky_ld(double* A, int ld, int n, double* dinv) {
+  const int lane = threadIdx.x & 31;
+  double a[NMAX];
+#pragma unroll
+  for (int k = 0; k < NMAX; ++k) a[k] = (lane < n && k <= lane && k < n) ? A[lane + k * ld] : 0.0;
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < NMAX; ++j) {
+    if (j < n) {
+      const double d = __shfl_sync(0xffffffffu, a[j], j);
+      if (!(d > 0.0)) ok = false;
+      const double inv = rsqrt(d);
+      const double lij = (lane == j) ? d * inv : a[j] * inv;
+      a[j] = lij;
+      if (lane == j) dinv[j] = inv;
+      if (lane >= j && lane < n) A[lane + j * ld] = lij;
+      __syncwarp();
+#pragma unroll
+      for (int k = j + 1; k < NMAX; ++k) {
+        if (k < n) {
+          const double lkj = A[k + j * ld];  // broadcast read
+          if (lane >= k) a[k] = fma(-lij, lkj, a[k]);
+        }
+      }
+    }
+  }
+  return ok;
+}
+
+// C(M x N) = sum_k fa(i, k) * fb(k, j) on one warp; st(i, j, value) stores one element (overlapped tiles store twice).
+template <int M, int N, int K, class FA, class FB, class ST>
+__device__ __forceinline__ void warp_gemm(FA fa, FB fb, ST st) {
+  constexpr int TM_ = num_tiles(M), TN_ = num_tiles(N);
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int m = 0; m < TM_; ++m) {
+    const int i0 = tile_off(m, M);
+    double acc[TN_][2];
+#pragma unroll
+    for (int n = 0; n < TN_; ++n) acc[n][0] = acc[n][1] = 0.0;
+    warp_mma_band<K, TN_, N>(acc, i0, fa, fb);
+#pragma unroll
+    for (int n = 0; n < TN_; ++n) {
+      const int j0 = tile_off(n, N);
+      st(i0 + g, j0 + 2 * t, acc[n][0]);
+      st(i0 + g, j0 + 2 * t + 1, acc[n][1]);
+    }
+  }
+}
+
 template <int NV, int NFM>
-__global__ void __launch_bounds__(64, 12) mjtjinv_kernel(const StageParams p) {
-  constexpr int NVF = NV + NFM, NTHR = 64;
-  __shared__ double sM[NV * NV], sLi[NV * NV], sMi[NV * NV], sJ[NFM * NV], sJMi[NFM * NV], sS[NFM * NFM], sSl[NFM * NFM],
-      sSi[NFM * NFM], sTR[NV * NFM], sdinv[32];
+struct MjtjCfg {
+  static constexpr int WARPS = 2;
+  static constexpr int o_L = 0, o_X = o_L + NV * NV, o_J = o_X + NV * NV, o_W = o_J + NFM * NV, o_S = o_W + NV * NFM,
+                       o_Y = o_S + NFM * NFM, o_d = o_Y + NFM * NFM, PER_WARP = o_d + 32;
+};
+
+template <int NV, int NFM>
+__global__ void __launch_bounds__(32 * MjtjCfg<NV, NFM>::WARPS, 10) mjtjinv_kernel(const StageParams p) {
+  using C = MjtjCfg<NV, NFM>;
+  constexpr int NVF = NV + NFM;
+  __shared__ __align__(16) double smem[C::WARPS * C::PER_WARP];
   const rbt_stage_layout& S = p.S;
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const size_t o = blockIdx.x;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const size_t o = size_t(blockIdx.x) * C::WARPS + wid;
+  if (o >= size_t(p.batch) * p.n_grid) return;
   const int i = int(o % p.n_grid), b = int(o / p.n_grid);
   const rbt_stage_ctrl c = p.ctrl[i];
   if (c.type == RBT_TERMINAL) return;
   const int nf = c.nf;
   const double* lin = p.lin + o * S.l_stride;
   double* Z = p.ex + o * S.e_stride + S.e_Z;
+  double* sL = smem + wid * C::PER_WARP + C::o_L;
+  double* sX = smem + wid * C::PER_WARP + C::o_X;
+  double* sJ = smem + wid * C::PER_WARP + C::o_J;  // later V (NV x NFM, ld NV)
+  double* sW = smem + wid * C::PER_WARP + C::o_W;  // later U
+  double* sS = smem + wid * C::PER_WARP + C::o_S;
+  double* sY = smem + wid * C::PER_WARP + C::o_Y;
+  double* dinv = smem + wid * C::PER_WARP + C::o_d;
   int bad = 0;
-  for (int e = tid; e < NV * NV; e += NTHR) sM[e] = lin[S.l_M + e];
-  for (int e = tid; e < NFM * NV; e += NTHR) sJ[e] = ((e % NFM) < nf) ? lin[S.l_J + e] : 0.0;
-  __syncthreads();
-  if (warp == 0) {
-    if (!warp_cholesky<NV>(sM, NV, sdinv)) bad |= 4;
-  }
-  __syncthreads();
-  if (tid < NV) {  // L^-1, column-oriented forward substitution (rows above the diagonal are zero)
-    const int cc = tid;
+  for (int e = lane; e < NV * NV; e += 32) sL[e] = lin[S.l_M + e];
+  for (int e = lane; e < NFM * NV; e += 32) sJ[e] = ((e % NFM) < nf) ? lin[S.l_J + e] : 0.0;
+  for (int e = lane; e < NFM * NFM; e += 32) sY[e] = 0.0;
+  __syncwarp();
+  if (!warp_cholesky_ld<NV>(sL, NV, NV, dinv)) bad |= 4;
+  __syncwarp();
+  if (lane < NV) {  // X = L^-1, one column per lane (forward substitution; rows above the diagonal stay zero)
     double x[NV];
 #pragma unroll
-    for (int a = 0; a < NV; ++a) x[a] = (a == cc) ? 1.0 : 0.0;
+    for (int a = 0; a < NV; ++a) x[a] = (a == lane) ? 1.0 : 0.0;
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
-      x[k] *= sdinv[k];
+      x[k] *= dinv[k];
 #pragma unroll
-      for (int a = k + 1; a < NV; ++a) x[a] = fma(-sM[a + k * NV], x[k], x[a]);
+      for (int a = k + 1; a < NV; ++a) x[a] = fma(-sL[a + k * NV], x[k], x[a]);
     }
 #pragma unroll
-    for (int a = 0; a < NV; ++a) sLi[a + cc * NV] = x[a];
+    for (int a = 0; a < NV; ++a) sX[a + lane * NV] = x[a];
   }
-  __syncthreads();
-  for (int e = tid; e < NV * NV; e += NTHR) {  // M^-1 = L^-T L^-1
-    const int r = e % NV, cc = e / NV;
-    double acc = 0.0;
-    for (int k = (r > cc ? r : cc); k < NV; ++k) acc = fma(sLi[k + r * NV], sLi[k + cc * NV], acc);
-    sMi[e] = acc;
-  }
-  __syncthreads();
+  __syncwarp();
   if (nf > 0) {
-    for (int e = tid; e < nf * NV; e += NTHR) {  // J M^-1
-      const int r = e % nf, cc = e / nf;
-      double acc = 0.0;
-      for (int k = 0; k < NV; ++k) acc = fma(sJ[r + k * NFM], sMi[k + cc * NV], acc);
-      sJMi[r + cc * NFM] = acc;
-    }
-    __syncthreads();
-    for (int e = tid; e < nf * nf; e += NTHR) {  // S = J M^-1 J^T   (compact ld = nf)
-      const int r = e % nf, cc = e / nf;
-      double acc = 0.0;
-      for (int k = 0; k < NV; ++k) acc = fma(sJMi[r + k * NFM], sJ[cc + k * NFM], acc);
-      sS[e] = acc;
-    }
-    __syncthreads();
-    if (warp == 0) {
-      if (!warp_cholesky<NFM>(sS, nf, sdinv)) bad |= 8;
-    }
-    __syncthreads();
-    if (tid < nf) {
-      const int cc = tid;
+    // W = X J^T
+    warp_gemm<NV, NFM, NV>([&](int ii, int k) { return sX[ii + k * NV]; }, [&](int k, int j) { return sJ[j + k * NFM]; },
+                           [&](int ii, int j, double v) { sW[ii + j * NV] = v; });
+    __syncwarp();
+    // S = W^T W
+    warp_gemm<NFM, NFM, NV>([&](int ii, int k) { return sW[k + ii * NV]; }, [&](int k, int j) { return sW[k + j * NV]; },
+                            [&](int ii, int j, double v) { sS[ii + j * NFM] = v; });
+    __syncwarp();
+    if (!warp_cholesky_ld<NFM>(sS, NFM, nf, dinv)) bad |= 8;
+    __syncwarp();
+    if (lane < nf) {  // Y = Ls^-1
       double x[NFM];
 #pragma unroll
-      for (int a = 0; a < NFM; ++a) x[a] = (a == cc) ? 1.0 : 0.0;
+      for (int a = 0; a < NFM; ++a) x[a] = (a == lane) ? 1.0 : 0.0;
 #pragma unroll
       for (int k = 0; k < NFM; ++k) {
         if (k < nf) {
-          x[k] *= sdinv[k];
+          x[k] *= dinv[k];
 #pragma unroll
           for (int a = k + 1; a < NFM; ++a)
-            if (a < nf) x[a] = fma(-sS[a + k * nf], x[k], x[a]);
+            if (a < nf) x[a] = fma(-sS[a + k * NFM], x[k], x[a]);
         }
       }
 #pragma unroll
-      for (int a = 0; a < NFM; ++a)
-        if (a < nf) sSl[a + cc * nf] = x[a];
+      for (int a = 0; a < NFM; ++a) sY[a + lane * NFM] = x[a];
     }
-    __syncthreads();
-    for (int e = tid; e < nf * nf; e += NTHR) {  // S^-1 = Ls^-T Ls^-1
-      const int r = e % nf, cc = e / nf;
-      double acc = 0.0;
-      for (int k = (r > cc ? r : cc); k < nf; ++k) acc = fma(sSl[k + r * nf], sSl[k + cc * nf], acc);
-      sSi[e] = acc;
-    }
-    __syncthreads();
-    for (int e = tid; e < NV * nf; e += NTHR) {  // topRight = (J M^-1)^T S^-1
-      const int r = e % NV, cc = e / NV;
-      double acc = 0.0;
-      for (int l = 0; l < nf; ++l) acc = fma(sJMi[l + r * NFM], sSi[l + cc * nf], acc);
-      sTR[e] = acc;
-    }
-    __syncthreads();
+    __syncwarp();
+    // V = W Y^T   (overwrites J)
+    warp_gemm<NV, NFM, NFM>([&](int ii, int k) { return sW[ii + k * NV]; }, [&](int k, int j) { return sY[j + k * NFM]; },
+                            [&](int ii, int j, double v) { sJ[ii + j * NV] = v; });
+    __syncwarp();
+    // U = X^T V   (overwrites W)
+    warp_gemm<NV, NFM, NV>([&](int ii, int k) { return sX[k + ii * NV]; }, [&](int k, int j) { return sJ[k + j * NV]; },
+                           [&](int ii, int j, double v) { sW[ii + j * NV] = v; });
+  } else {
+    for (int e = lane; e < NV * NFM; e += 32) sW[e] = 0.0;
   }
-  for (int e = tid; e < NVF * NVF; e += NTHR) {
-    const int r = e % NVF, cc = e / NVF;
-    double v = 0.0;
-    if (r < NV && cc < NV) {
-      v = sMi[r + cc * NV];
-      for (int l = 0; l < nf; ++l) v = fma(-sTR[r + l * NV], sJMi[l + cc * NFM], v);  // topLeft -= topRight (J M^-1)
-    } else if (r < NV && cc - NV < nf) {
-      v = sTR[r + (cc - NV) * NV];
-    } else if (cc < NV && r - NV < nf) {
-      v = sTR[cc + (r - NV) * NV];
-    } else if (r >= NV && cc >= NV && r - NV < nf && cc - NV < nf) {
-      v = -sSi[(r - NV) + (cc - NV) * nf];
+  __syncwarp();
+  {  // Z11 = X^T X - U U^T
+    constexpr int TV_ = num_tiles(NV);
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int m = 0; m < TV_; ++m) {
+      const int i0 = tile_off(m, NV);
+      double acc[TV_][2];
+#pragma unroll
+      for (int n = 0; n < TV_; ++n) acc[n][0] = acc[n][1] = 0.0;
+      warp_mma_band<NV, TV_, NV>(acc, i0, [&](int ii, int k) { return sX[k + ii * NV]; },
+                                 [&](int k, int j) { return sX[k + j * NV]; });
+      warp_mma_band<NFM, TV_, NV>(acc, i0, [&](int ii, int l) { return -sW[ii + l * NV]; },
+                                  [&](int l, int j) { return sW[j + l * NV]; });
+#pragma unroll
+      for (int n = 0; n < TV_; ++n) {
+        const int j0 = tile_off(n, NV);
+        Z[(i0 + g) + (j0 + 2 * t) * NVF] = acc[n][0];
+        Z[(i0 + g) + (j0 + 2 * t + 1) * NVF] = acc[n][1];
+      }
     }
-    Z[e] = v;
   }
+  // Z12 = U Y (and its transpose), Z22 = -Y^T Y
+  warp_gemm<NV, NFM, NFM>([&](int ii, int l) { return sW[ii + l * NV]; }, [&](int l, int j) { return sY[l + j * NFM]; },
+                          [&](int ii, int j, double v) {
+                            Z[ii + (NV + j) * NVF] = v;
+                            Z[(NV + j) + ii * NVF] = v;
+                          });
+  warp_gemm<NFM, NFM, NFM>([&](int ii, int k) { return -sY[k + ii * NFM]; }, [&](int k, int j) { return sY[k + j * NFM]; },
+                           [&](int ii, int j, double v) { Z[(NV + ii) + (NV + j) * NVF] = v; });
   bad = __reduce_or_sync(0xffffffffu, bad);
-  if ((tid & 31) == 0 && bad) atomicOr(&p.info[b], bad);
+  if (lane == 0 && bad) atomicOr(&p.info[b], bad);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -704,13 +764,25 @@ __device__ __forceinline__ void atomic_min_pos(double* addr, double v) {  // v >
   atomicMin(reinterpret_cast<unsigned long long*>(addr), static_cast<unsigned long long>(__double_as_longlong(v)));
 }
 
+// expand / update: one CTA of 4 warps per (OCP, stage).  The matrices of the expansion record arrive in shared memory by
+// TMA bulk copies (one round trip to HBM instead of a chain of dependent column loads); each warp then owns every 4th
+// column of a mat-vec (lane = row, conflict-free) and the partial sums meet in shared memory.
+constexpr int XTHR = 128;
+
 template <int NV, int NU, int NFM>
-__global__ void __launch_bounds__(64) expand_kernel(const StageParams p) {
-  constexpr int NX = 2 * NV, NVF = NV + NFM, NTHR = 64;
-  __shared__ double sdx[NX], sdu[NU], sdaf[NVF], smin[4];
+__global__ void __launch_bounds__(XTHR) expand_kernel(const StageParams p) {
+  constexpr int NX = 2 * NV, NVF = NV + NFM, NTHR = XTHR;
+  constexpr int RSZ = ((NVF * NX + 1) & ~1) + ((NVF + 1) & ~1);  // R | r (adjacent in the record)
+  constexpr int ZSZ = NVF * NU;
+  __shared__ __align__(16) double sR[RSZ];
+  __shared__ __align__(16) double sZ[ZSZ];
+  __shared__ __align__(16) double sG[512];  // dgdq | dgdf of all contacts
+  __shared__ __align__(16) double sC[4 * 160];  // slack | dual | res | cmpl
+  __shared__ double sdx[NX], sdu[NU], sdaf[NVF], spart[4][32], smin[8];
+  __shared__ __align__(8) uint64_t bar;
   const rbt_layout& K = p.K;
   const rbt_stage_layout& S = p.S;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const size_t o = blockIdx.x;
   const int i = int(o % p.n_grid), b = int(o / p.n_grid);
   const rbt_stage_ctrl c = p.ctrl[i];
@@ -722,66 +794,89 @@ __global__ void __launch_bounds__(64) expand_kernel(const StageParams p) {
   const double* d = p.dir + o * K.d_stride;
   double* con = p.con + o * S.c_stride;
   double* xd = p.xd + o * S.x_stride;
+  const int gsz = S.l_stride - S.l_dgdq;  // dgdq | dgdf | padding: the tail of the linearization record (<= 512 doubles)
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+    uint32_t bytes = RSZ * 8;
+    if (!impact) bytes += ZSZ * 8 + gsz * 8 + 4 * S.ncp * 8;
+    mbar_expect_tx(&bar, bytes);
+    tma_load_1d(sR, ex + S.e_R, RSZ * 8, &bar);
+    if (!impact) {
+      tma_load_1d(sZ, ex + S.e_Z + np * NVF, ZSZ * 8, &bar);
+      tma_load_1d(sG, lin + S.l_dgdq, gsz * 8, &bar);
+      tma_load_1d(sC, con + S.c_slack, 4 * S.ncp * 8, &bar);
+    }
+  }
   for (int e = tid; e < NX; e += NTHR) sdx[e] = d[K.d_dx + e];
   for (int e = tid; e < NU; e += NTHR) sdu[e] = impact ? 0.0 : d[K.d_du + e];
+  const int nbox = p.tab.n_box, ncp = S.ncp;
   __syncthreads();
-  for (int r = tid; r < nvf; r += NTHR) {  // daf = -R dx + Z[:, np:np+nu] du - r ; df *= -1      contact_dynamics.cpp:167-174
+  mbar_wait(&bar, 0);
+  {  // daf = -R dx + Z[:, np:np+nu] du - r ; df *= -1      contact_dynamics.cpp:167-174
     double acc = 0.0;
-    for (int k = 0; k < NX; ++k) acc = fma(-ex[S.e_R + r + k * NVF], sdx[k], acc);
-    if (!impact)
-      for (int k = 0; k < NU; ++k) acc = fma(ex[S.e_Z + r + (np + k) * NVF], sdu[k], acc);
-    acc -= ex[S.e_r + r];
-    if (r >= NV) acc = -acc;
-    sdaf[r] = acc;
-    xd[S.x_daf + r] = acc;
+    if (lane < nvf) {
+      for (int k = wid; k < NX; k += 4) acc = fma(-sR[lane + k * NVF], sdx[k], acc);
+      if (!impact)
+        for (int k = wid; k < NU; k += 4) acc = fma(sZ[lane + k * NVF], sdu[k], acc);
+    }
+    spart[wid][lane] = acc;
+  }
+  __syncthreads();
+  if (tid < nvf) {
+    double acc = (spart[0][tid] + spart[1][tid]) + (spart[2][tid] + spart[3][tid]);
+    acc -= sR[((NVF * NX + 1) & ~1) + tid];
+    if (tid >= NV) acc = -acc;
+    sdaf[tid] = acc;
+    xd[S.x_daf + tid] = acc;
   }
   if (impact) return;
   __syncthreads();
   const double tau = p.tab.fraction_to_boundary;
   double mp = 1.0, md = 1.0;
-  auto consider = [&](double sl, double dsl, double du, double ddu) {
-    const double fp = -tau * (sl / dsl), fd = -tau * (du / ddu);  // pdipm.hxx:121-142
-    if (fp > 0.0 && fp < 1.0) mp = fmin(mp, fp);
-    if (fd > 0.0 && fd < 1.0) md = fmin(md, fd);
-  };
-  for (int r = tid; r < p.tab.n_box; r += NTHR) {
-    const rbt_box_row br = p.tab.box[r];
-    const double var = br.var == RBT_VAR_Q ? sdx[br.idx] : br.var == RBT_VAR_V ? sdx[NV + br.idx]
-                       : br.var == RBT_VAR_A ? sdaf[br.idx] : sdu[br.idx];
-    const double sl = con[S.c_slack + r], du = con[S.c_dual + r];
-    const double dsl = -br.sign * var - con[S.c_res + r];           // joint_*_limit.cpp:78-82
-    const double ddu = -(du * dsl + con[S.c_cmpl + r]) / sl;        // pdipm.hxx:159-164
-    con[S.c_dslack + r] = dsl;
-    con[S.c_ddual + r] = ddu;
-    consider(sl, dsl, du, ddu);
-  }
-  for (int q = tid; q < 5 * p.tab.n_contacts; q += NTHR) {
-    const int ci = q / 5, r5 = q % 5, r = p.tab.n_box + q;
-    double dsl = 1.0, ddu = 1.0;                                    // friction_cone.cpp:244-245
-    if ((c.contact_mask >> ci) & 1) {
-      const int fstack = 3 * __popc(c.contact_mask & ((1 << ci) - 1));
-      const double* dgdq = lin + S.l_dgdq + size_t(ci) * 5 * NV;
-      const double* dgdf = lin + S.l_dgdf + size_t(ci) * 15;
-      double acc = 0.0;
-      for (int j = 0; j < NV; ++j) acc = fma(dgdq[r5 + j * 5], sdx[j], acc);
-      for (int j = 0; j < 3; ++j) acc = fma(dgdf[r5 + j * 5], sdaf[NV + fstack + j], acc);
-      dsl = -acc - con[S.c_res + r];                                // :253-256
-      ddu = -(con[S.c_dual + r] * dsl + con[S.c_cmpl + r]) / con[S.c_slack + r];
+  for (int r = tid; r < S.nc; r += NTHR) {
+    const double c_sl = sC[r], c_du = sC[ncp + r], c_res = sC[2 * ncp + r], c_cm = sC[3 * ncp + r];
+    double dsl, ddu;
+    if (r < nbox) {
+      const rbt_box_row br = p.tab.box[r];
+      const double var = br.var == RBT_VAR_Q ? sdx[br.idx] : br.var == RBT_VAR_V ? sdx[NV + br.idx]
+                         : br.var == RBT_VAR_A ? sdaf[br.idx] : sdu[br.idx];
+      dsl = -br.sign * var - c_res;                                 // joint_*_limit.cpp:78-82
+      ddu = -(c_du * dsl + c_cm) / c_sl;                            // pdipm.hxx:159-164
+    } else {
+      const int q = r - nbox, ci = q / 5, r5 = q % 5;
+      dsl = 1.0; ddu = 1.0;                                         // friction_cone.cpp:244-245
+      if ((c.contact_mask >> ci) & 1) {
+        const int fstack = 3 * __popc(c.contact_mask & ((1 << ci) - 1));
+        const double* dgdq = sG + size_t(ci) * 5 * NV;
+        const double* dgdf = sG + (S.l_dgdf - S.l_dgdq) + size_t(ci) * 15;
+        double a0 = 0.0, a1 = 0.0;
+        for (int j = 0; j < NV; j += 2) {
+          a0 = fma(dgdq[r5 + j * 5], sdx[j], a0);
+          if (j + 1 < NV) a1 = fma(dgdq[r5 + (j + 1) * 5], sdx[j + 1], a1);
+        }
+        double acc = a0 + a1;
+        for (int j = 0; j < 3; ++j) acc = fma(dgdf[r5 + j * 5], sdaf[NV + fstack + j], acc);
+        dsl = -acc - c_res;                                         // :253-256
+        ddu = -(c_du * dsl + c_cm) / c_sl;
+      }
     }
     con[S.c_dslack + r] = dsl;
     con[S.c_ddual + r] = ddu;
-    consider(con[S.c_slack + r], dsl, con[S.c_dual + r], ddu);
+    const double fp = -tau * (c_sl / dsl), fd = -tau * (c_du / ddu);  // pdipm.hxx:121-142
+    if (fp > 0.0 && fp < 1.0) mp = fmin(mp, fp);
+    if (fd > 0.0 && fd < 1.0) md = fmin(md, fd);
   }
   mp = warp_min(mp);
   md = warp_min(md);
-  if ((tid & 31) == 0) {
-    smin[(tid >> 5) * 2] = mp;
-    smin[(tid >> 5) * 2 + 1] = md;
+  if (lane == 0) {
+    smin[wid * 2] = mp;
+    smin[wid * 2 + 1] = md;
   }
   __syncthreads();
   if (tid == 0) {  // min over the stage, then over the horizon    direct_multiple_shooting.cpp:202-209
-    atomic_min_pos(&p.steps[2 * b], fmin(smin[0], smin[2]));
-    atomic_min_pos(&p.steps[2 * b + 1], fmin(smin[1], smin[3]));
+    atomic_min_pos(&p.steps[2 * b], fmin(fmin(smin[0], smin[2]), fmin(smin[4], smin[6])));
+    atomic_min_pos(&p.steps[2 * b + 1], fmin(fmin(smin[1], smin[3]), fmin(smin[5], smin[7])));
   }
 }
 
@@ -790,11 +885,12 @@ __device__ __forceinline__ void integrate_free_flyer_dev(double* q, const double
   const double vx = step * dq[0], vy = step * dq[1], vz = step * dq[2];
   const double wx = step * dq[3], wy = step * dq[4], wz = step * dq[5];
   const double th2 = wx * wx + wy * wy + wz * wz, th = sqrt(th2);
-  double bb, cc;
+  double bb, cc, s2 = 0.0, c2 = 1.0;  // one sincos of the half angle serves both the translation and the quaternion part
   if (th < 1e-6) {
     bb = 0.5 - th2 / 24.0; cc = 1.0 / 6.0 - th2 / 120.0;
   } else {
-    bb = (1.0 - cos(th)) / th2; cc = (th - sin(th)) / (th2 * th);
+    sincos(0.5 * th, &s2, &c2);
+    bb = 2.0 * s2 * s2 / th2; cc = (th - 2.0 * s2 * c2) / (th2 * th);
   }
   const double cx = wy * vz - wz * vy, cy = wz * vx - wx * vz, cz = wx * vy - wy * vx;
   const double ccx = wy * cz - wz * cy, ccy = wz * cx - wx * cz, ccz = wx * cy - wy * cx;
@@ -806,7 +902,7 @@ __device__ __forceinline__ void integrate_free_flyer_dev(double* q, const double
   q[1] += ty + 2.0 * (qw * uy + u2y);
   q[2] += tz + 2.0 * (qw * uz + u2z);
   double sh, ch;
-  if (th < 1e-6) { sh = 0.5 - th2 / 48.0; ch = 1.0 - th2 / 8.0; } else { sh = sin(0.5 * th) / th; ch = cos(0.5 * th); }
+  if (th < 1e-6) { sh = 0.5 - th2 / 48.0; ch = 1.0 - th2 / 8.0; } else { sh = s2 / th; ch = c2; }
   const double ex_ = sh * wx, ey = sh * wy, ez = sh * wz, ew = ch;
   const double nx_ = qw * ex_ + qx * ew + qy * ez - qz * ey;
   const double ny = qw * ey - qx * ez + qy * ew + qz * ex_;
@@ -817,12 +913,19 @@ __device__ __forceinline__ void integrate_free_flyer_dev(double* q, const double
 }
 
 template <int NV, int NU, int NFM>
-__global__ void __launch_bounds__(64) update_kernel(const StageParams p) {
-  constexpr int NX = 2 * NV, NVF = NV + NFM, NTHR = 64;
-  __shared__ double sdx[NX], sdu[NU], slaf[NVF], sdbm[NVF], sdl[NX], sdnup[8];
+__global__ void __launch_bounds__(XTHR) update_kernel(const StageParams p) {
+  constexpr int NX = 2 * NV, NVF = NV + NFM, NTHR = XTHR;
+  constexpr int QSZ = ((NVF * NX + 1) & ~1) + ((NVF * NV + 1) & ~1);  // Qafqv | Qafu (adjacent in the record)
+  constexpr int ZSZ = (NVF * NVF + 1) & ~1;
+  constexpr int PSZ = ((NX * 6 + 1) & ~1) + ((6 * NU + 1) & ~1) + 6;     // Qxup | Quup | lup (floating base: np = 6)
+  __shared__ __align__(16) double sQ[QSZ];
+  __shared__ __align__(16) double sZ[ZSZ];
+  __shared__ __align__(16) double sP[PSZ];
+  __shared__ double sdx[NX], sdu[NU], slaf[NVF], sdl[NX], sdgn[NV], spart[4][32];
+  __shared__ __align__(8) uint64_t bar;
   const rbt_layout& K = p.K;
   const rbt_stage_layout& S = p.S;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const size_t o = blockIdx.x;
   const int i = int(o % p.n_grid), b = int(o / p.n_grid);
   const rbt_stage_ctrl c = p.ctrl[i];
@@ -833,70 +936,52 @@ __global__ void __launch_bounds__(64) update_kernel(const StageParams p) {
   double* xd = p.xd + o * S.x_stride;
   double* con = p.con + o * S.c_stride;
   double* sol = p.sol + o * S.s_stride;
+  const bool nup = !terminal && !impact && np == 6;
+  if (tid == 0 && !terminal) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+    mbar_expect_tx(&bar, (QSZ + ZSZ + (nup ? PSZ : 0)) * 8);
+    tma_load_1d(sQ, ex + S.e_Qafqv, QSZ * 8, &bar);
+    tma_load_1d(sZ, ex + S.e_Z, ZSZ * 8, &bar);
+    if (nup) tma_load_1d(sP, ex + S.e_Qxup, PSZ * 8, &bar);
+  }
   const double ap = p.steps[2 * b], ad = p.steps[2 * b + 1];
   for (int e = tid; e < NX; e += NTHR) {
     sdx[e] = d[K.d_dx + e];
     sdl[e] = d[K.d_dlmdgmm + e];
   }
   for (int e = tid; e < NU; e += NTHR) sdu[e] = (terminal || impact) ? 0.0 : d[K.d_du + e];
+  if (!terminal)
+    for (int e = tid; e < NV; e += NTHR) sdgn[e] = d[K.d_stride + K.d_dlmdgmm + NV + e];  // dgmm of stage i+1 (not modified here)
+  if (!terminal && !impact) {
+    for (int r = tid; r < S.nc; r += NTHR) {  // updateSlack / updateDual    constraint_component_base.hxx:25-36
+      con[S.c_slack + r] += ap * con[S.c_dslack + r];
+      con[S.c_dual + r] += ad * con[S.c_ddual + r];
+    }
+  }
   __syncthreads();
-  if (!terminal) {
-    const double* dgn = d + K.d_stride + K.d_dlmdgmm + NV;  // dgmm of stage i+1 (never modified by this kernel)
-    const double dt = c.dt;
-    double dts = 0.0;
-    if (!impact && c.ngrids_in_phase > 0) dts = (d[K.d_dts + 1] - d[K.d_dts]) / c.ngrids_in_phase;  // intermediate_stage.cpp:167-170
-    for (int r = tid; r < nvf; r += NTHR) {  // laf += Qafqv dx + Qafu du (+ dt dgmm+ / Phia^T dxi / dts haf)   :191-201
-      double acc = ex[S.e_laf + r];
-      for (int k = 0; k < NX; ++k) acc = fma(ex[S.e_Qafqv + r + k * NVF], sdx[k], acc);
-      if (!impact) {
-        for (int k = 0; k < NU; ++k) acc = fma(ex[S.e_Qafu + r + (np + k) * NVF], sdu[k], acc);
-        if (r < NV) {
-          acc = fma(dt, dgn[r], acc);
-          for (int q = 0; q < ns; ++q) acc = fma(ex[S.e_Phia + q + r * ns], d[K.d_dxi + q], acc);
-        }
-        if (dts < -2.220446049250313e-16 || dts > 2.220446049250313e-16) acc = fma(dts, ex[S.e_haf + r], acc);
-      } else if (r < NV) {
-        acc += dgn[r];                                                               // impact_dynamics.cpp:94
-      }
-      slaf[r] = acc;
-      ex[S.e_laf + r] = acc;
-    }
-    if (!impact && tid < np) {  // dnu_passive            contact_dynamics.cpp:182-190
-      double acc = -ex[S.e_lup + tid];
-      for (int k = 0; k < NU; ++k) acc = fma(-ex[S.e_Quup + tid + k * np], sdu[k], acc);
-      for (int k = 0; k < NX; ++k) acc = fma(-ex[S.e_Qxup + k + tid * NX], sdx[k], acc);
-      for (int k = 0; k < NV; ++k) acc = fma(-dt * ex[S.e_Z + tid + k * NVF], dgn[k], acc);
-      sdnup[tid] = acc;
-      xd[S.x_dnup + tid] = acc;
-    }
-    __syncthreads();
-    for (int r = tid; r < nvf; r += NTHR) {  // dbetamu = -Z laf     :202
+  // ---- everything of SplitSolution::integrate (split_solution.cpp:58-90) that does not depend on the dual expansion runs
+  //      while the bulk copies are in flight
+  if (np == 6) {
+    if (tid == 2 * 32) integrate_free_flyer_dev(sol + S.s_q, sdx, ap);
+    if (tid < 6) {  // correctCostateDirection     state_equation.cpp:90-95
       double acc = 0.0;
-      for (int k = 0; k < nvf; ++k) acc = fma(-ex[S.e_Z + r + k * NVF], slaf[k], acc);
-      sdbm[r] = acc;
-      xd[S.x_dbetamu + r] = acc;
+      for (int l = 0; l < 6; ++l) acc = fma(ex[S.e_Fqqpi + l + tid * 6], sdl[l], acc);
+      d[K.d_dlmdgmm + tid] = -acc;
+      sol[S.s_lmd + tid] += ap * (-acc);
     }
-  }
-  if (np == 6 && tid < 6) {  // correctCostateDirection     state_equation.cpp:90-95
-    double acc = 0.0;
-    for (int l = 0; l < 6; ++l) acc = fma(ex[S.e_Fqqpi + l + tid * 6], sdl[l], acc);
-    d[K.d_dlmdgmm + tid] = -acc;
-  }
-  __syncthreads();
-  if (np == 6 && tid < 6) sdl[tid] = d[K.d_dlmdgmm + tid];
-  __syncthreads();
-  // ---- SplitSolution::integrate                          split_solution.cpp:58-90
-  if (tid == 0) {
-    if (np == 6) integrate_free_flyer_dev(sol + S.s_q, sdx, ap);
   }
   for (int e = tid; e < NV; e += NTHR) {
     if (np == 6) {
-      if (e >= 6) sol[S.s_q + e + 1] += ap * sdx[e];
+      if (e >= 6) {
+        sol[S.s_q + e + 1] += ap * sdx[e];
+        sol[S.s_lmd + e] += ap * sdl[e];
+      }
     } else {
       sol[S.s_q + e] += ap * sdx[e];
+      sol[S.s_lmd + e] += ap * sdl[e];
     }
     sol[S.s_v + e] += ap * sdx[NV + e];
-    sol[S.s_lmd + e] += ap * sdl[e];
     sol[S.s_gmm + e] += ap * sdl[NV + e];
     if (!terminal) {
       const double da = xd[S.x_daf + e];
@@ -907,23 +992,78 @@ __global__ void __launch_bounds__(64) update_kernel(const StageParams p) {
         sol[S.s_a + e] = 0.0;
         sol[S.s_dv + e] += ap * da;
       }
-      sol[S.s_beta + e] += ap * sdbm[e];
     }
   }
-  if (!terminal) {
-    for (int e = tid; e < NU; e += NTHR) sol[S.s_u + e] = impact ? 0.0 : sol[S.s_u + e] + ap * sdu[e];
-    for (int e = tid; e < nf; e += NTHR) {
-      sol[S.s_f + e] += ap * xd[S.x_daf + NV + e];
-      sol[S.s_mu + e] += ap * sdbm[NV + e];
-    }
+  if (terminal) return;
+  for (int e = tid; e < NU; e += NTHR) sol[S.s_u + e] = impact ? 0.0 : sol[S.s_u + e] + ap * sdu[e];
+  for (int e = tid; e < nf; e += NTHR) sol[S.s_f + e] += ap * xd[S.x_daf + NV + e];
+  for (int e = tid; e < ns; e += NTHR) sol[S.s_xi + e] += ap * d[K.d_dxi + e];
+  const double dt = c.dt;
+  double dts = 0.0;
+  if (!impact && c.ngrids_in_phase > 0) dts = (d[K.d_dts + 1] - d[K.d_dts]) / c.ngrids_in_phase;  // intermediate_stage.cpp:167-170
+  double extra = 0.0;  // the per-row terms of laf that do not come from the staged matrices
+  if (tid < nvf) {
+    extra = ex[S.e_laf + tid];
     if (!impact) {
-      for (int e = tid; e < np; e += NTHR) sol[S.s_nup + e] += ap * sdnup[e];
-      for (int e = tid; e < ns; e += NTHR) sol[S.s_xi + e] += ap * d[K.d_dxi + e];
-      for (int r = tid; r < S.nc; r += NTHR) {  // updateSlack / updateDual    constraint_component_base.hxx:25-36
-        con[S.c_slack + r] += ap * con[S.c_dslack + r];
-        con[S.c_dual + r] += ad * con[S.c_ddual + r];
+      if (tid < NV) {
+        extra = fma(dt, sdgn[tid], extra);
+        for (int q = 0; q < ns; ++q) extra = fma(ex[S.e_Phia + q + tid * ns], d[K.d_dxi + q], extra);
+      }
+      if (dts < -2.220446049250313e-16 || dts > 2.220446049250313e-16) extra = fma(dts, ex[S.e_haf + tid], extra);
+    } else if (tid < NV) {
+      extra += sdgn[tid];                                                          // impact_dynamics.cpp:94
+    }
+  }
+  mbar_wait(&bar, 0);
+  {  // laf += Qafqv dx + Qafu du (+ dt dgmm+ / Phia^T dxi / dts haf)   contact_dynamics.cpp:191-201
+    double acc = 0.0;
+    if (lane < nvf) {
+      for (int k = wid; k < NX; k += 4) acc = fma(sQ[lane + k * NVF], sdx[k], acc);
+      if (!impact) {
+        const double* sQu = sQ + ((NVF * NX + 1) & ~1) + np * NVF;
+        for (int k = wid; k < NU; k += 4) acc = fma(sQu[lane + k * NVF], sdu[k], acc);
       }
     }
+    spart[wid][lane] = acc;
+  }
+  if (nup && wid == 3) {  // dnu_passive: 4 lanes per row      contact_dynamics.cpp:182-190
+    const int prow = lane >> 2, ppart = lane & 3;
+    const double* sQxup = sP;
+    const double* sQuup = sP + ((NX * 6 + 1) & ~1);
+    const double* slup = sQuup + ((6 * NU + 1) & ~1);
+    double pn = 0.0;
+    if (prow < 6) {
+      for (int k = ppart; k < NU; k += 4) pn = fma(-sQuup[prow + k * 6], sdu[k], pn);
+      for (int k = ppart; k < NX; k += 4) pn = fma(-sQxup[k + prow * NX], sdx[k], pn);
+      for (int k = ppart; k < NV; k += 4) pn = fma(-dt * sZ[prow + k * NVF], sdgn[k], pn);
+    }
+    pn += __shfl_xor_sync(0xffffffffu, pn, 1);
+    pn += __shfl_xor_sync(0xffffffffu, pn, 2);
+    if (prow < 6 && ppart == 0) {
+      pn -= slup[prow];
+      xd[S.x_dnup + prow] = pn;
+      sol[S.s_nup + prow] += ap * pn;
+    }
+  }
+  __syncthreads();
+  if (tid < nvf) {
+    const double acc = extra + ((spart[0][tid] + spart[1][tid]) + (spart[2][tid] + spart[3][tid]));
+    slaf[tid] = acc;
+    ex[S.e_laf + tid] = acc;
+  }
+  __syncthreads();
+  {  // dbetamu = -Z laf     :202
+    double acc = 0.0;
+    if (lane < nvf)
+      for (int k = wid; k < nvf; k += 4) acc = fma(-sZ[lane + k * NVF], slaf[k], acc);
+    spart[wid][lane] = acc;
+  }
+  __syncthreads();
+  if (tid < nvf) {
+    const double acc = (spart[0][tid] + spart[1][tid]) + (spart[2][tid] + spart[3][tid]);
+    xd[S.x_dbetamu + tid] = acc;
+    if (tid < NV) sol[S.s_beta + tid] += ap * acc;
+    else sol[S.s_mu + tid - NV] += ap * acc;
   }
 }
 
