@@ -486,6 +486,23 @@ int rbt_stage_setup(rbt_handle* h, const rbt_stage_dims* sd, const rbt_constrain
   h->sdims = *sd;
   h->table = *table;
   rbt_make_stage_layout(sd, &h->S);
+  {  // condense_kernel lands [l_D, l_Phix) and [l_ha, l_dgdq) of the record in place: the static mirror must match
+    using C = rbt::CondCfg<18, 12, 12>;
+    const rbt_stage_layout& S = h->S;
+    const int gsz = (S.l_dgdf - S.l_dgdq) + ((15 * S.ncon + 1) & ~1);
+    const bool ok = S.l_Phix - S.l_D == C::IN1 && S.l_IDC - S.l_D == C::i_IDC && S.l_Qaa - S.l_D == C::i_Qaa &&
+                    S.l_Qff - S.l_D == C::i_Qff && S.l_Qqf - S.l_D == C::i_Qqf && S.l_Qxx - S.l_D == C::i_Qxx &&
+                    S.l_Quu - S.l_D == C::i_Quu && S.l_lx - S.l_D == C::i_lx && S.l_la - S.l_D == C::i_la &&
+                    S.l_lf - S.l_D == C::i_lf && S.l_lu - S.l_D == C::i_lu && S.l_Fx - S.l_D == C::i_Fx &&
+                    S.l_lup - S.l_D == C::i_lup && S.l_se3 - S.l_D == C::i_se3 && S.l_dgdq - S.l_ha == C::IN2 &&
+                    S.l_hf - S.l_ha == C::j_hf && S.l_hx - S.l_ha == C::j_hx && S.l_hu - S.l_ha == C::j_hu &&
+                    S.l_fx - S.l_ha == C::j_fx && S.l_sc - S.l_ha == C::j_sc &&
+                    5 * S.ncp + gsz <= C::NVF * C::NX;  // PDIPM staging fits in the R buffer
+    if (!ok) {
+      h->err = "[rbt_stage_setup] invalid argument: stage layout not supported by the compiled condensing kernel";
+      return RBT_ERR_ARG;
+    }
+  }
   if (h->S.ncp > 160 || h->S.l_stride - h->S.l_dgdq > 512) {  // shared-memory staging areas of expand_kernel
     h->err = "[rbt_stage_setup] invalid argument: more than 160 inequality rows or more than 4 friction cones";
     return RBT_ERR_ARG;

@@ -268,33 +268,43 @@ __global__ void __launch_bounds__(32 * MjtjCfg<NV, NFM>::WARPS, 10) mjtjinv_kern
 
 // ------------------------------------------------------------------------------------------------------------------
 // K2: everything else of "Forms linear system", with all dense products on the fp64 tensor pipe (DMMA m8n8k4).
+//
+// Shared-memory plan (43 KB -> 5 CTAs per SM).  The part of the linearization record K2 needs is contiguous
+// ([l_D, l_Phix) and [l_ha, l_dgdq)), so it lands IN PLACE with two cp.async.bulk copies and is then used (and
+// modified: PDIPM terms) where it lies; Z (from K1) is a third copy; the PDIPM inputs (slack|dual|res, dg/dq|dg/df)
+// land in the buffer that later holds R.  Only the contact rows of Qafqv / Qafu are materialised (in the dead dIDCdqv
+// buffer): their acceleration rows are diag(Qaa) times rows of R / Z and are formed on the fly in the fragment loads.
 template <int NV, int NU, int NFM>
 struct CondCfg {
   static constexpr int NX = 2 * NV, NVF = NV + NFM;
   static constexpr int TX = num_tiles(NX), TF = num_tiles(NVF), TV = num_tiles(NV), TU = num_tiles(NU), TM = num_tiles(NFM);
   static constexpr int NWARPS = TX;
   static constexpr int NTHREADS = 32 * NWARPS;
-  static constexpr int o_Z = 0;                     // Z (ld NVF)
-  static constexpr int o_D = o_Z + NVF * NVF;       // dIDCdqv (ld NVF)
-  static constexpr int o_R = o_D + NVF * NX;        // R (ld NVF)
-  static constexpr int o_Qa = o_R + NVF * NX;       // Qafqv (ld NVF)
-  static constexpr int o_Qu = o_Qa + NVF * NX;      // Qafu_full (ld NVF)
-  static constexpr int o_Qxx = o_Qu + NVF * NV;     // Qxx working copy (cost Hessian + PDIPM terms), bulk-copied in
-  static constexpr int o_Quu = o_Qxx + NX * NX;     // Quu working copy
-  static constexpr int o_Qff = o_Quu + NU * NU;     // Qff (ld NFM)
-  static constexpr int o_Qqf = o_Qff + NFM * NFM;   // Qqf (ld NV)
-  static constexpr int o_vec = o_Qqf + NV * NFM;
-  static constexpr int v_IDC = 0, v_r = NVF, v_laf = 2 * NVF, v_haf = 3 * NVF, v_Qaa = 4 * NVF, v_la = v_Qaa + NV,
-                       v_lf = v_la + NV, v_lx = v_lf + NFM, v_lu = v_lx + NX, v_Fx = v_lu + NU, v_fx = v_Fx + NX,
-                       v_Fi = v_fx + NX, v_w = v_Fi + 36, v_end = v_w + 16;
+  static constexpr int up2(int x) { return (x + 1) & ~1; }
+  // mirror of the record from l_D to l_Phix (same relative offsets as rbt_make_stage_layout)
+  static constexpr int i_D = 0, i_IDC = i_D + up2(NVF * NX), i_Qaa = i_IDC + up2(NVF), i_Qff = i_Qaa + up2(NV),
+                       i_Qqf = i_Qff + up2(NFM * NFM), i_Qxx = i_Qqf + up2(NV * NFM), i_Quu = i_Qxx + up2(NX * NX),
+                       i_lx = i_Quu + up2(NU * NU), i_la = i_lx + up2(NX), i_lf = i_la + up2(NV), i_lu = i_lf + up2(NFM),
+                       i_Fx = i_lu + up2(NU), i_lup = i_Fx + up2(NX), i_se3 = i_lup + 6, IN1 = i_se3 + 108;
+  // mirror of the record from l_ha to l_dgdq
+  static constexpr int j_ha = 0, j_hf = j_ha + up2(NV), j_hx = j_hf + up2(NFM), j_hu = j_hx + up2(NX), j_fx = j_hu + up2(NU),
+                       j_sc = j_fx + up2(NX), IN2 = j_sc + 4;
+  static constexpr int o_in1 = 0;
+  static constexpr int o_Z = o_in1 + IN1;          // Z (ld NVF)
+  static constexpr int o_R = o_Z + NVF * NVF;      // R (ld NVF); before R exists: PDIPM staging
+  static constexpr int o_in2 = o_R + NVF * NX;
+  static constexpr int o_vec = o_in2 + IN2;
+  static constexpr int v_r = 0, v_laf = NVF, v_haf = 2 * NVF, v_Fi = 3 * NVF, v_FiS = v_Fi + 36, v_end = v_FiS + 36;
   static constexpr int o_bar = (o_vec + v_end + 1) & ~1;
   static constexpr int SMEM_DOUBLES = o_bar + 2;
   static constexpr size_t SMEM_BYTES = size_t(SMEM_DOUBLES) * 8;
-  static_assert(TF <= NWARPS && TV <= NWARPS && TM <= NWARPS, "one warp per row band");
+  static constexpr int QAF = 0, QUF = NFM * NX;    // contact rows of Qafqv (NFM x NX) and Qafu (NFM x NV) inside the dead D buffer
+  static_assert(TF < NWARPS && TV <= NWARPS && 2 * TM < NWARPS, "one warp per row band, one warp left for the vectors");
+  static_assert(NFM * NX + NFM * NV <= NVF * NX, "Qaf | Quf fit in the dIDCdqv buffer");
 };
 
 template <int NV, int NU, int NFM>
-__global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS, 4) condense_kernel(const StageParams p) {
+__global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS, 5) condense_kernel(const StageParams p) {
   using C = CondCfg<NV, NU, NFM>;
   constexpr int NX = C::NX, NVF = C::NVF, NTHR = C::NTHREADS, TX = C::TX, TF = C::TF, TV = C::TV, TU = C::TU, TM = C::TM;
   extern __shared__ __align__(16) double smem[];
@@ -320,87 +330,89 @@ __global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS, 4) condense_ke
   const bool impact = (c.type == RBT_IMPACT);
   const int nf = c.nf, nvf = NV + nf, ns = impact ? 0 : c.ns;
   const double dt = c.dt;
+  double* in1 = smem + C::o_in1;
+  double* sD = in1 + C::i_D;        // dIDCdqv (ld NVF); dead after R = Z D, then:
+  double* sQaf = sD + C::QAF;       //   contact rows of Qafqv (ld NFM)
+  double* sQuf = sD + C::QUF;       //   contact rows of Qafu  (ld NFM)
+  double* vIDC = in1 + C::i_IDC;
+  double* vQaa = in1 + C::i_Qaa;
+  double* sQff = in1 + C::i_Qff;
+  double* sQqf = in1 + C::i_Qqf;
+  double* gQxx = in1 + C::i_Qxx;    // cost Hessian + PDIPM terms (working copy)
+  double* gQuu = in1 + C::i_Quu;
+  double* vlx = in1 + C::i_lx;
+  double* vla = in1 + C::i_la;
+  double* vlf = in1 + C::i_lf;
+  double* vlu = in1 + C::i_lu;
+  double* vFx = in1 + C::i_Fx;
+  const double* vlup = in1 + C::i_lup;
+  const double* sse3 = in1 + C::i_se3;
   double* sZ = smem + C::o_Z;
-  double* sD = smem + C::o_D;
   double* sR = smem + C::o_R;
-  double* sQa = smem + C::o_Qa;
-  double* sQu = smem + C::o_Qu;
-  double* sQff = smem + C::o_Qff;
-  double* sQqf = smem + C::o_Qqf;
+  const double* in2 = smem + C::o_in2;
+  const double* vha = in2 + C::j_ha;
+  const double* vhf = in2 + C::j_hf;
+  const double* vhx = in2 + C::j_hx;
+  const double* vhu = in2 + C::j_hu;
+  const double* vfx = in2 + C::j_fx;
+  const double* vsc = in2 + C::j_sc;
   double* vec = smem + C::o_vec;
-  double* vIDC = vec + C::v_IDC;
   double* vr = vec + C::v_r;
   double* vlaf = vec + C::v_laf;
   double* vhaf = vec + C::v_haf;
-  double* vQaa = vec + C::v_Qaa;
-  double* vla = vec + C::v_la;
-  double* vlf = vec + C::v_lf;
-  double* vlx = vec + C::v_lx;
-  double* vlu = vec + C::v_lu;
-  double* vFx = vec + C::v_Fx;
-  double* vfx = vec + C::v_fx;
   double* Fi = vec + C::v_Fi;
-  double* vw = vec + C::v_w;
-  double* gQxx = smem + C::o_Qxx;  // Qxx / Quu working copies (shared memory)
-  double* gQuu = smem + C::o_Quu;
+  double* FiS = vec + C::v_FiS;
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + C::o_bar);
+  // PDIPM staging inside the (not yet written) R buffer
+  const int ncp = S.ncp, nbox = p.tab.n_box, ncon = p.tab.n_contacts, nc = S.nc;
+  double* cSl = sR;                      // slack | dual | res     (bulk copy)
+  double* sDq = sR + 3 * ncp;            // dg/dq (5 x nv per contact) | dg/df (5 x 3 per contact)   (bulk copy)
+  double* sDf = sDq + (S.l_dgdf - S.l_dgdq);
+  const int gsz = (S.l_dgdf - S.l_dgdq) + ((15 * ncon + 1) & ~1);
+  double* cW = sDq + ((gsz + 1) & ~1);   // weights dual/slack
+  double* cC = cW + ncp;                 // condensing coefficients
 
-  // ---- stage inputs -> shared memory.  The three big blocks (Z from K1, dIDCdqv, Qxx) arrive by cp.async.bulk while the
-  // PDIPM passes below run.  Contract: rows >= nv+nf of dIDCdqv are zero in the linearization record (Z is zero-padded by K1).
   if (tid == 0) {
     mbar_init(bar, 1);
     fence_mbar_init();
-  }
-  __syncthreads();
-  if (tid == 0) {
-    fence_proxy_async();
-    mbar_expect_tx(bar, uint32_t(NVF * NVF + NVF * NX + NX * NX) * 8u);
+    uint32_t bytes = uint32_t(C::IN1 + NVF * NVF + C::IN2) * 8u;
+    if (!impact) bytes += uint32_t(3 * ncp + gsz) * 8u;
+    mbar_expect_tx(bar, bytes);
+    tma_load_1d(in1, lin + S.l_D, uint32_t(C::IN1) * 8u, bar);
     tma_load_1d(sZ, ex + S.e_Z, uint32_t(NVF * NVF) * 8u, bar);
-    tma_load_1d(sD, lin + S.l_D, uint32_t(NVF * NX) * 8u, bar);
-    tma_load_1d(gQxx, lin + S.l_Qxx, uint32_t(NX * NX) * 8u, bar);
-  }
-  for (int e = tid; e < NFM * NFM; e += NTHR) sQff[e] = ((e % NFM) < nf && (e / NFM) < nf) ? lin[S.l_Qff + e] : 0.0;
-  for (int e = tid; e < NV * NFM; e += NTHR) sQqf[e] = ((e / NV) < nf) ? lin[S.l_Qqf + e] : 0.0;
-  for (int e = tid; e < NVF; e += NTHR) vIDC[e] = (e < nvf) ? lin[S.l_IDC + e] : 0.0;
-  for (int e = tid; e < NV; e += NTHR) {
-    vQaa[e] = lin[S.l_Qaa + e];
-    vla[e] = lin[S.l_la + e];
-  }
-  for (int e = tid; e < NFM; e += NTHR) vlf[e] = (e < nf) ? lin[S.l_lf + e] : 0.0;
-  for (int e = tid; e < NX; e += NTHR) {
-    vlx[e] = lin[S.l_lx + e];
-    vFx[e] = lin[S.l_Fx + e];
-    vfx[e] = impact ? 0.0 : lin[S.l_fx + e];
-  }
-  for (int e = tid; e < NU; e += NTHR) vlu[e] = impact ? 0.0 : lin[S.l_lu + e];
-  for (int e = tid; e < NU * NU; e += NTHR) gQuu[e] = impact ? 0.0 : lin[S.l_Quu + e];
-  if (tid >= NTHR - NVF) {
-    const int r = tid - (NTHR - NVF);
-    vhaf[r] = impact ? 0.0 : (r < NV ? lin[S.l_ha + r] : (r - NV < nf ? -lin[S.l_hf + r - NV] : 0.0));
+    tma_load_1d(smem + C::o_in2, lin + S.l_ha, uint32_t(C::IN2) * 8u, bar);
+    if (!impact) {
+      tma_load_1d(cSl, con + S.c_slack, uint32_t(3 * ncp) * 8u, bar);
+      tma_load_1d(sDq, lin + S.l_dgdq, uint32_t(gsz) * 8u, bar);
+    }
   }
   __syncthreads();
+  if (np == 6) {  // the SE(3) inverses are long scalar chains: run them under the bulk copies, straight from global memory
+    if (tid == 32) se3_jac_inverse_dev(lin + S.l_se3 + 36, ex + S.e_Fqqpi);  // Fqq_prev_inv   state_equation.cpp:76
+    if (tid == 64) se3_jac_inverse_dev(lin + S.l_se3 + 72, Fi);              // Fqq_inv        :77-78
+  }
+  mbar_wait(bar, 0);
 
-  // ---- PDIPM condensing (Intermediate / Lift)             pdipm.hxx:27-100, joint_*_limit.cpp:68-75, friction_cone.cpp:194-235
-  // All rows at once: (1) per-row complementarity / condensing coefficient / weight, (2) per-target gather of the box rows
-  // in row order (deterministic; a lower and an upper limit share a diagonal entry), (3) element-parallel application of
-  // the box and friction-cone terms.  Staging aliases the (still unused) Qafqv / Qafu buffers.
+  // ---- phase 1: mask what lies beyond the active contact dimension, per-row PDIPM quantities
+  for (int e = tid; e < NFM * NFM; e += NTHR)
+    if ((e % NFM) >= nf || (e / NFM) >= nf) sQff[e] = 0.0;
+  for (int e = tid; e < NV * NFM; e += NTHR)
+    if ((e / NV) >= nf) sQqf[e] = 0.0;
+  if (tid < NVF) {
+    if (tid >= nvf) vIDC[tid] = 0.0;
+    vhaf[tid] = impact ? 0.0 : (tid < NV ? vha[tid] : (tid - NV < nf ? -vhf[tid - NV] : 0.0));
+    if (tid >= NV && tid - NV >= nf) vlf[tid - NV] = 0.0;
+  }
   if (!impact) {
     const double mu = p.tab.barrier;
-    const int nc = S.nc, nbox = p.tab.n_box, ncon = p.tab.n_contacts;
-    double* cW = sQu;            // weights dual/slack            [ncp]
-    double* cC = sQu + S.ncp;    // condensing coefficients       [ncp]
-    double* tW = sQu + 2 * S.ncp;  // per-target weight sums        [RBT_MAX_TARGETS]
-    double* tG = tW + RBT_MAX_TARGETS;  // per-target gradient sums
-    double* sDq = sQa;           // dg/dq of every contact: 5 x nv each
-    double* sDf = sQa + ncon * 5 * NV;  // dg/df: 5 x 3 each
-    for (int r = tid; r < nc; r += NTHR) {
+    for (int r = tid; r < nc; r += NTHR) {  // pdipm.hxx:27-100
       const bool cone = r >= nbox;
       const bool act = !cone || ((c.contact_mask >> ((r - nbox) / 5)) & 1);
       double w = 0.0, cd = 0.0;
       if (act) {
-        const double sl = con[S.c_slack + r], du = con[S.c_dual + r];
+        const double sl = cSl[r], du = cSl[ncp + r];
         const double cm = sl * du - mu;
-        cd = (du * con[S.c_res + r] - cm) / sl;
+        cd = (du * cSl[2 * ncp + r] - cm) / sl;
         w = du / sl;
         con[S.c_cmpl + r] = cm;
       }
@@ -408,11 +420,18 @@ __global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS, 4) condense_ke
       cW[r] = w;
       cC[r] = cd;
     }
-    for (int e = tid; e < ncon * 5 * NV; e += NTHR) sDq[e] = ((c.contact_mask >> (e / (5 * NV))) & 1) ? lin[S.l_dgdq + e] : 0.0;
-    for (int e = tid; e < ncon * 15; e += NTHR) sDf[e] = ((c.contact_mask >> (e / 15)) & 1) ? lin[S.l_dgdf + e] : 0.0;
-    __syncthreads();
-    for (int tgt = tid; tgt < 3 * NV + NU; tgt += NTHR) {
-      double w = 0.0, gs = 0.0;
+    for (int e = tid; e < 5 * NV * ncon; e += NTHR)
+      if (!((c.contact_mask >> (e / (5 * NV))) & 1)) sDq[e] = 0.0;
+    for (int e = tid; e < 15 * ncon; e += NTHR)
+      if (!((c.contact_mask >> (e / 15)) & 1)) sDf[e] = 0.0;
+  }
+  __syncthreads();
+
+  // ---- phase 2: PDIPM condensing applied to the working copies       joint_*_limit.cpp:68-75, friction_cone.cpp:194-235
+  // A target (variable, index) gathers its box rows in table order (deterministic; a lower and an upper limit share it).
+  if (!impact) {
+    auto gather = [&](int tgt, double& w, double& gs) {
+      w = 0.0; gs = 0.0;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int r = p.tgt_rows[tgt][q];
@@ -421,15 +440,11 @@ __global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS, 4) condense_ke
           gs += p.tab.box[r].sign * cC[r];
         }
       }
-      tW[tgt] = w;
-      tG[tgt] = gs;
-    }
-    mbar_wait(bar, 0);  // Z, dIDCdqv, Qxx have landed
-    __syncthreads();
-    // Qqq += diag(box q) + sum_c dg_dq^T diag(w) dg_dq          friction_cone.cpp:217-218
+    };
+    // Qqq += sum_c dg_dq^T diag(w) dg_dq          friction_cone.cpp:217-218  (box diagonal below)
     for (int e = tid; e < NV * NV; e += NTHR) {
       const int ii = e % NV, j = e / NV;
-      double acc = (ii == j) ? tW[ii] : 0.0;
+      double acc = 0.0;
       for (int ci = 0; ci < ncon; ++ci)
         for (int r = 0; r < 5; ++r) acc = fma(sDq[ci * 5 * NV + r + ii * 5] * cW[nbox + 5 * ci + r], sDq[ci * 5 * NV + r + j * 5], acc);
       gQxx[ii + j * NX] += acc;
@@ -456,23 +471,33 @@ __global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS, 4) condense_ke
         sQff[(fstack + ii) + (fstack + j) * NFM] += acc;
       }
     }
-    // gradients and the remaining diagonals
-    for (int ii = tid; ii < NV; ii += NTHR) {
-      double acc = tG[ii];
+    __syncthreads();  // the Qqq diagonal below touches elements the loop above also updates
+    // gradients and diagonals, one target per thread spread over the warps
+    if (warp == 0 && lane < NV) {
+      double w, gs;
+      gather(lane, w, gs);
+      double acc = gs;
       for (int ci = 0; ci < ncon; ++ci)
-        for (int r = 0; r < 5; ++r) acc = fma(sDq[ci * 5 * NV + r + ii * 5], cC[nbox + 5 * ci + r], acc);  // lq += dg_dq^T cond  :207
-      vlx[ii] += acc;
-      vlx[NV + ii] += tG[NV + ii];
-      gQxx[(NV + ii) * (NX + 1)] += tW[NV + ii];
-      vQaa[ii] += tW[2 * NV + ii];
-      vla[ii] += tG[2 * NV + ii];
-    }
-    for (int ii = tid; ii < NU; ii += NTHR) {
-      gQuu[ii * (NU + 1)] += tW[3 * NV + ii];
-      vlu[ii] += tG[3 * NV + ii];
-    }
-    for (int q = tid; q < 3 * ncon; q += NTHR) {  // lf[stack(c) + j] += dg_df^T cond   :208-209
-      const int ci = q / 3, j = q % 3;
+        for (int r = 0; r < 5; ++r) acc = fma(sDq[ci * 5 * NV + r + lane * 5], cC[nbox + 5 * ci + r], acc);  // lq += dg_dq^T cond  :207
+      vlx[lane] += acc;
+      gQxx[lane * (NX + 1)] += w;
+    } else if (warp == 1 && lane < NV) {
+      double w, gs;
+      gather(NV + lane, w, gs);
+      vlx[NV + lane] += gs;
+      gQxx[(NV + lane) * (NX + 1)] += w;
+    } else if (warp == 2 && lane < NV) {
+      double w, gs;
+      gather(2 * NV + lane, w, gs);
+      vQaa[lane] += w;
+      vla[lane] += gs;
+    } else if (warp == 3 && lane < NU) {
+      double w, gs;
+      gather(3 * NV + lane, w, gs);
+      gQuu[lane * (NU + 1)] += w;
+      vlu[lane] += gs;
+    } else if (warp == 4 && lane < 3 * ncon) {  // lf[stack(c) + j] += dg_df^T cond   :208-209
+      const int ci = lane / 3, j = lane % 3;
       if ((c.contact_mask >> ci) & 1) {
         const int fstack = 3 * __popc(c.contact_mask & ((1 << ci) - 1));
         double acc = 0.0;
@@ -480,10 +505,9 @@ __global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS, 4) condense_ke
         vlf[fstack + j] += acc;
       }
     }
-    __syncthreads();
+    __syncthreads();  // staging (in the R buffer) is dead from here on
   }
-  if (impact) mbar_wait(bar, 0);
-  // ---- R = Z D (tensor pipe) ; r = Z IDC                    contact_dynamics.cpp:65-66
+  // ---- phase 3: R = Z D (tensor pipe) ; r = Z IDC ; Fqq_inv * dSub/dqf         contact_dynamics.cpp:65-66
   if (warp < TF) {
     const int i0 = tile_off(warp, NVF);
     double acc[TX][2];
@@ -499,20 +523,18 @@ __global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS, 4) condense_ke
     }
   } else {
     matvec_N4(sZ, NVF, NVF, NVF, vIDC, lane, 32, [&](int r, double a) { vr[r] = a; });
+    if (np == 6)
+      for (int e = lane; e < 36; e += 32) {  // FiS = Fqq_inv * (dSub/dqf top-left)        state_equation.cpp:80
+        const int ii = e % 6, j = e / 6;
+        double acc = 0.0;
+        for (int l = 0; l < 6; ++l) acc = fma(Fi[ii + l * 6], sse3[l + j * 6], acc);
+        FiS[e] = acc;
+      }
   }
-  __syncthreads();
+  __syncthreads();  // D is dead from here on
 
-  // ---- Qafqv, Qafu_full, laf                                contact_dynamics.cpp:68-86
-  for (int e = tid; e < NV * NX; e += NTHR) {  // top rows: -diag(Qaa) R_a
-    const int ii = e % NV, j = e / NV;
-    sQa[ii + j * NVF] = -vQaa[ii] * sR[ii + j * NVF];
-  }
-  if (!impact)
-    for (int e = tid; e < NV * NV; e += NTHR) {  // top rows: diag(Qaa) Z_aa
-      const int ii = e % NV, j = e / NV;
-      sQu[ii + j * NVF] = vQaa[ii] * sZ[ii + j * NVF];
-    }
-  if (warp < TM) {  // bottom rows of Qafqv: -Qff R_f - [Qqf^T | 0]
+  // ---- phase 4: contact rows of Qafqv and Qafu, laf                       contact_dynamics.cpp:68-86
+  if (warp < TM) {  // Qaf = -Qff R_f - [Qqf^T | 0]
     const int a0 = tile_off(warp, NFM);
     double acc[TX][2];
 #pragma unroll
@@ -526,10 +548,10 @@ __global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS, 4) condense_ke
 #pragma unroll
     for (int n = 0; n < TX; ++n) {
       const int j0 = tile_off(n, NX);
-      sQa[(NV + a0 + g) + (j0 + 2 * t) * NVF] = acc[n][0];
-      sQa[(NV + a0 + g) + (j0 + 2 * t + 1) * NVF] = acc[n][1];
+      sQaf[(a0 + g) + (j0 + 2 * t) * NFM] = acc[n][0];
+      sQaf[(a0 + g) + (j0 + 2 * t + 1) * NFM] = acc[n][1];
     }
-  } else if (!impact && warp < 2 * TM) {  // bottom rows of Qafu_full: Qff Z_fa
+  } else if (!impact && warp < 2 * TM) {  // Quf = Qff Z_fa
     const int a0 = tile_off(warp - TM, NFM);
     double acc[TV][2];
 #pragma unroll
@@ -539,8 +561,8 @@ __global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS, 4) condense_ke
 #pragma unroll
     for (int n = 0; n < TV; ++n) {
       const int j0 = tile_off(n, NV);
-      sQu[(NV + a0 + g) + (j0 + 2 * t) * NVF] = acc[n][0];
-      sQu[(NV + a0 + g) + (j0 + 2 * t + 1) * NVF] = acc[n][1];
+      sQuf[(a0 + g) + (j0 + 2 * t) * NFM] = acc[n][0];
+      sQuf[(a0 + g) + (j0 + 2 * t + 1) * NFM] = acc[n][1];
     }
   } else if (warp == NTHR / 32 - 1) {  // laf
     for (int r = lane; r < NVF; r += 32) {
@@ -553,11 +575,15 @@ __global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS, 4) condense_ke
         v = (r - NV < nf) ? -vlf[r - NV] - acc : 0.0;
       }
       vlaf[r] = v;
+      ex[S.e_laf + r] = v;
+      ex[S.e_r + r] = vr[r];
+      if (!impact) ex[S.e_haf + r] = vhaf[r];
     }
   }
   __syncthreads();
 
-  // ---- Hessian condensing on the tensor pipe                contact_dynamics.cpp:88-121, impact_dynamics.cpp:64-66
+  // ---- phase 5: Hessian condensing on the tensor pipe           contact_dynamics.cpp:88-121, impact_dynamics.cpp:64-66
+  // Qafqv = [-diag(Qaa) R_a ; Qaf], Qafu = [diag(Qaa) Z_aa ; Quf]: the acceleration rows are formed in the fragment loads.
   const int i0 = tile_off(warp, NX);
   {  // Qxx = Qxx' - R^T Qafqv + [Qqf R_f ; 0]
     double acc[TX][2];
@@ -567,8 +593,10 @@ __global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS, 4) condense_ke
       acc[n][0] = gQxx[(i0 + g) + (j0 + 2 * t) * NX];
       acc[n][1] = gQxx[(i0 + g) + (j0 + 2 * t + 1) * NX];
     }
-    warp_mma_band<NVF, TX, NX>(
-        acc, i0, [&](int ii, int l) { return -sR[l + ii * NVF]; }, [&](int l, int j) { return sQa[l + j * NVF]; });
+    warp_mma_band<NV, TX, NX>(
+        acc, i0, [&](int ii, int l) { return -sR[l + ii * NVF]; }, [&](int l, int j) { return -vQaa[l] * sR[l + j * NVF]; });
+    warp_mma_band<NFM, TX, NX>(
+        acc, i0, [&](int ii, int l) { return -sR[(NV + l) + ii * NVF]; }, [&](int l, int j) { return sQaf[l + j * NFM]; });
     warp_mma_band<NFM, TX, NX>(
         acc, i0, [&](int ii, int l) { return ii < NV ? sQqf[ii + l * NV] : 0.0; },
         [&](int l, int j) { return sR[(NV + l) + j * NVF]; });
@@ -584,8 +612,10 @@ __global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS, 4) condense_ke
       double acc[TV][2];
 #pragma unroll
       for (int n = 0; n < TV; ++n) acc[n][0] = acc[n][1] = 0.0;
-      warp_mma_band<NVF, TV, NV>(
-          acc, i0, [&](int ii, int l) { return -sR[l + ii * NVF]; }, [&](int l, int j) { return sQu[l + j * NVF]; });
+      warp_mma_band<NV, TV, NV>(
+          acc, i0, [&](int ii, int l) { return -sR[l + ii * NVF]; }, [&](int l, int j) { return vQaa[l] * sZ[l + j * NVF]; });
+      warp_mma_band<NFM, TV, NV>(
+          acc, i0, [&](int ii, int l) { return -sR[(NV + l) + ii * NVF]; }, [&](int l, int j) { return sQuf[l + j * NFM]; });
       warp_mma_band<NFM, TV, NV>(
           acc, i0, [&](int ii, int l) { return ii < NV ? -sQqf[ii + l * NV] : 0.0; },
           [&](int l, int j) { return sZ[(NV + l) + j * NVF]; });
@@ -610,8 +640,10 @@ __global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS, 4) condense_ke
         acc[n][0] = (r >= np) ? gQuu[(r - np) + (j0 + 2 * t) * NU] : 0.0;
         acc[n][1] = (r >= np) ? gQuu[(r - np) + (j0 + 2 * t + 1) * NU] : 0.0;
       }
-      warp_mma_band<NVF, TU, NU>(
-          acc, r0, [&](int ii, int l) { return sZ[ii + l * NVF]; }, [&](int l, int j) { return sQu[l + (np + j) * NVF]; });
+      warp_mma_band<NV, TU, NU>(
+          acc, r0, [&](int ii, int l) { return sZ[ii + l * NVF]; }, [&](int l, int j) { return vQaa[l] * sZ[l + (np + j) * NVF]; });
+      warp_mma_band<NFM, TU, NU>(
+          acc, r0, [&](int ii, int l) { return sZ[ii + (NV + l) * NVF]; }, [&](int l, int j) { return sQuf[l + (np + j) * NFM]; });
 #pragma unroll
       for (int n = 0; n < TU; ++n) {
         const int j0 = tile_off(n, NU);
@@ -636,34 +668,19 @@ __global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS, 4) condense_ke
   });
   if (!impact) {
     matvec_N4(sZ, NVF, NV, NVF, vlaf, tid, NTHR, [&](int ii, double a) {
-      if (ii < np) ex[S.e_lup + ii] = lin[S.l_lup + ii] + a;
+      if (ii < np) ex[S.e_lup + ii] = vlup[ii] + a;
       else kkt[K.k_lu + ii - np] = vlu[ii - np] + a;
     });
   }
   // ---- state equation rows                                 contact_dynamics.cpp:130-135, impact_dynamics.cpp:71-74
   const double sdt = impact ? 1.0 : dt;
-  if (np == 6) {
-    if (tid == 0) se3_jac_inverse_dev(lin + S.l_se3 + 36, ex + S.e_Fqqpi);  // Fqq_prev_inv   state_equation.cpp:76
-    if (tid == 32) se3_jac_inverse_dev(lin + S.l_se3 + 72, Fi);              // Fqq_inv        :77-78
-  }
-  for (int ii = tid; ii < NX; ii += NTHR) {
-    double v = vFx[ii];
-    if (ii >= NV) v -= sdt * vr[ii - NV];
-    vFx[ii] = v;
-  }
-  __syncthreads();
   for (int e = tid; e < NX * NX; e += NTHR) {
     const int ii = e % NX, j = e / NX;
     double v;
     if (ii < NV) {
       if (np == 6 && ii < 6 && (j < 6 || (j >= NV && j < NV + 6))) {
-        if (j < 6) {  // Fqq top-left = -Fqq_inv * (dSub/dqf top-left)                       state_equation.cpp:80
-          double acc = 0.0;
-          for (int l = 0; l < 6; ++l) acc = fma(Fi[ii + l * 6], lin[S.l_se3 + l + j * 6], acc);
-          v = -acc;
-        } else {      // Fqv top-left = -dt Fqq_inv                                           :81
-          v = impact ? 0.0 : -dt * Fi[ii + (j - NV) * 6];
-        }
+        if (j < 6) v = -FiS[ii + j * 6];                              // Fqq top-left = -Fqq_inv * (dSub/dqf top-left)   state_equation.cpp:80
+        else v = impact ? 0.0 : -dt * Fi[ii + (j - NV) * 6];         // Fqv top-left = -dt Fqq_inv                      :81
       } else if (j < NV) {
         v = (ii == j) ? 1.0 : 0.0;
       } else {
@@ -677,12 +694,13 @@ __global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS, 4) condense_ke
   if (!impact)
     for (int e = tid; e < NV * NU; e += NTHR) kkt[K.k_Fvu + e] = dt * sZ[(e % NV) + (np + e / NV) * NVF];
   for (int ii = tid; ii < NX; ii += NTHR) {
-    double v = vFx[ii], f = vfx[ii];
+    auto Fxv = [&](int l) { return l >= NV ? vFx[l] - sdt * vr[l - NV] : vFx[l]; };
+    double v = Fxv(ii), f = impact ? 0.0 : vfx[ii];
     if (np == 6 && ii < 6) {  // Fq, fq head <- -Fqq_inv * (.)                                :83-85
       double a1 = 0.0, a2 = 0.0;
       for (int l = 0; l < 6; ++l) {
         a1 = fma(Fi[ii + l * 6], vFx[l], a1);
-        a2 = fma(Fi[ii + l * 6], vfx[l], a2);
+        a2 = fma(Fi[ii + l * 6], impact ? 0.0 : vfx[l], a2);
       }
       v = -a1;
       f = -a2;
@@ -717,7 +735,7 @@ __global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS, 4) condense_ke
   if (!impact) {
     const double g1 = 1.0 / c.ngrids_in_phase;
     matvec_T(sR, NVF, NVF, NX, vhaf, tid, NTHR, [&](int ii, double a) {
-      double v = lin[S.l_hx + ii] - a;
+      double v = vhx[ii] - a;
       if (ii < NV) {
         double a2 = 0.0;
         for (int l = 0; l < NFM; ++l) a2 = fma(sQqf[ii + l * NV], vr[NV + l], a2);
@@ -728,30 +746,30 @@ __global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS, 4) condense_ke
     for (int ii = tid; ii < NU; ii += NTHR) {
       double acc = 0.0;
       for (int l = 0; l < NVF; ++l) acc = fma(sZ[(np + ii) + l * NVF], vhaf[l], acc);
-      kkt[K.k_hu + ii] = (lin[S.l_hu + ii] + acc) * g1;
+      kkt[K.k_hu + ii] = (vhu[ii] + acc) * g1;
     }
-    if (tid == 0) {
-      double h = lin[S.l_sc + 0];
+    if (tid == NTHR - 1) {
+      double h = vsc[0];
       for (int l = 0; l < NVF; ++l) h = fma(-vr[l], vhaf[l], h);
-      const double Qtt = lin[S.l_sc + 1] * g1 * g1;
+      const double Qtt = vsc[1] * g1 * g1;
       kkt[K.k_sc + 0] = Qtt;
       kkt[K.k_sc + 1] = -Qtt;
       kkt[K.k_sc + 2] = h * g1;
       kkt[K.k_sc + 3] = 0.0;
     }
-    for (int e = tid; e < NVF; e += NTHR) ex[S.e_haf + e] = vhaf[e];
   }
   // ---- expansion record (Z is already there)
   for (int e = tid; e < NVF * NX; e += NTHR) {
-    ex[S.e_R + e] = sR[e];
-    ex[S.e_Qafqv + e] = sQa[e];
+    const int ii = e % NVF, j = e / NVF;
+    const double rv = sR[e];
+    ex[S.e_R + e] = rv;
+    ex[S.e_Qafqv + e] = (ii < NV) ? -vQaa[ii] * rv : sQaf[(ii - NV) + j * NFM];
   }
   if (!impact)
-    for (int e = tid; e < NVF * NV; e += NTHR) ex[S.e_Qafu + e] = sQu[e];
-  for (int e = tid; e < NVF; e += NTHR) {
-    ex[S.e_r + e] = vr[e];
-    ex[S.e_laf + e] = vlaf[e];
-  }
+    for (int e = tid; e < NVF * NV; e += NTHR) {
+      const int ii = e % NVF, j = e / NVF;
+      ex[S.e_Qafu + e] = (ii < NV) ? vQaa[ii] * sZ[ii + j * NVF] : sQuf[(ii - NV) + j * NFM];
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
