@@ -497,7 +497,8 @@ int rbt_stage_setup(rbt_handle* h, const rbt_stage_dims* sd, const rbt_constrain
                     S.l_lup - S.l_D == C::i_lup && S.l_se3 - S.l_D == C::i_se3 && S.l_dgdq - S.l_ha == C::IN2 &&
                     S.l_hf - S.l_ha == C::j_hf && S.l_hx - S.l_ha == C::j_hx && S.l_hu - S.l_ha == C::j_hu &&
                     S.l_fx - S.l_ha == C::j_fx && S.l_sc - S.l_ha == C::j_sc &&
-                    5 * S.ncp + gsz <= C::NVF * C::NX;  // PDIPM staging fits in the R buffer
+                    5 * S.ncp + gsz <= C::NVF * C::NX &&  // PDIPM staging fits in the R buffer
+                    S.l_J - S.l_M == rbt::MjtjCfg<18, 12>::o_J && S.l_D - S.l_M == rbt::MjtjCfg<18, 12>::MJ;
     if (!ok) {
       h->err = "[rbt_stage_setup] invalid argument: stage layout not supported by the compiled condensing kernel";
       return RBT_ERR_ARG;

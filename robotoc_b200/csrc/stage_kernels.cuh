@@ -147,8 +147,11 @@ __device__ __forceinline__ void warp_gemm(FA fa, FB fb, ST st) {
 template <int NV, int NFM>
 struct MjtjCfg {
   static constexpr int WARPS = 2;
-  static constexpr int o_L = 0, o_X = o_L + NV * NV, o_J = o_X + NV * NV, o_W = o_J + NFM * NV, o_S = o_W + NV * NFM,
-                       o_Y = o_S + NFM * NFM, o_d = o_Y + NFM * NFM, PER_WARP = o_d + 32;
+  // M | J are adjacent in the linearization record: one bulk copy lands both
+  static constexpr int o_L = 0, o_J = o_L + ((NV * NV + 1) & ~1), o_X = o_J + ((NFM * NV + 1) & ~1), o_W = o_X + NV * NV,
+                       o_S = o_W + NV * NFM, o_Y = o_S + NFM * NFM, o_d = o_Y + NFM * NFM, o_bar = o_d + 32,
+                       PER_WARP = o_bar + 2;
+  static constexpr int MJ = o_X;  // doubles copied
 };
 
 template <int NV, int NFM>
@@ -173,10 +176,19 @@ __global__ void __launch_bounds__(32 * MjtjCfg<NV, NFM>::WARPS, 10) mjtjinv_kern
   double* sS = smem + wid * C::PER_WARP + C::o_S;
   double* sY = smem + wid * C::PER_WARP + C::o_Y;
   double* dinv = smem + wid * C::PER_WARP + C::o_d;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + wid * C::PER_WARP + C::o_bar);
   int bad = 0;
-  for (int e = lane; e < NV * NV; e += 32) sL[e] = lin[S.l_M + e];
-  for (int e = lane; e < NFM * NV; e += 32) sJ[e] = ((e % NFM) < nf) ? lin[S.l_J + e] : 0.0;
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+    mbar_expect_tx(bar, uint32_t(C::MJ) * 8u);
+    tma_load_1d(sL, lin + S.l_M, uint32_t(C::MJ) * 8u, bar);
+  }
   for (int e = lane; e < NFM * NFM; e += 32) sY[e] = 0.0;
+  __syncwarp();
+  mbar_wait(bar, 0);
+  for (int e = lane; e < NFM * NV; e += 32)
+    if ((e % NFM) >= nf) sJ[e] = 0.0;
   __syncwarp();
   if (!warp_cholesky_ld<NV>(sL, NV, NV, dinv)) bad |= 4;
   __syncwarp();
