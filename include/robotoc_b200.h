@@ -84,7 +84,8 @@ long long rbt_buf_doubles(rbt_handle* h, int which); /* size of that buffer in d
  * d_; include/robotoc/solver/ocp_solver.hpp:219-236); this lets a GPU front-end or an NCCL all-gather work in place. */
 int rbt_bind_buffer(rbt_handle* h, int which, double* dev);
 
-int rbt_upload(rbt_handle* h, int which, const double* host, void* stream);   /* RBT_BUF_KKT or RBT_BUF_DX0 */
+/* RBT_BUF_KKT, RBT_BUF_DX0, RBT_BUF_LIN, RBT_BUF_CON (input fields slack | dual | residual only), RBT_BUF_SOL */
+int rbt_upload(rbt_handle* h, int which, const double* host, void* stream);
 int rbt_download(rbt_handle* h, int which, double* host, void* stream);       /* any output buffer */
 /* bytes rbt_upload(h, which, ..) actually moves host->device (KKT uploads skip record padding and, on stages without
  * a switching constraint / STO, the unused switching+STO sections) */
@@ -130,6 +131,13 @@ int rbt_update(rbt_handle* h, void* stream);
  * forward Riccati, step sizes, update, download the updated solution, the PDIPM data and the step sizes (NULL = skip). */
 int rbt_iteration_host(rbt_handle* h, const double* lin_host, const double* con_host, const double* sol_host,
                        const double* dx0_host, double* sol_out, double* con_out, double* steps_out, void* stream);
+/* Bytes one rbt_iteration_host call moves over PCIe.  Only what the kernels read and what persists is moved: record padding
+ * never, the switching-constraint section of a linearization record only on stages that carry one, of the PDIPM record
+ * slack | dual | residual go up and the updated slack | dual come back (the other PDIPM fields are per-iteration scratch that
+ * the reference keeps inside ConstraintComponentData; con_out's remaining fields are left untouched).  The call is
+ * pipelined over chunks of the batch (upload of chunk c+1, kernels of chunk c, download of chunk c-1 overlap on three
+ * streams); `stream` is ordered after the last download, so rbt_sync(h, stream) covers everything. */
+int rbt_iteration_host_bytes(rbt_handle* h, long long* h2d_bytes, long long* d2h_bytes);
 
 int rbt_sync(rbt_handle* h, void* stream);
 const char* rbt_last_error(rbt_handle* h);

@@ -9,6 +9,9 @@
 
 #include <cuda_runtime.h>
 
+#include <algorithm>
+#include <cstdlib>
+
 #include "../../include/robotoc_b200.h"
 #include "riccati_backward.cuh"
 #include "riccati_forward.cuh"
@@ -61,8 +64,16 @@ struct rbt_handle {
          *d_ones = nullptr;
   int timeline_cta = -1;
   long long launches = 0;
+  // batch window [cb0, cb0 + cnb) the launch helpers work on (cnb == 0: the whole batch); used by rbt_iteration_host to
+  // pipeline uploads, kernels and downloads over chunks of the batch
+  int cb0 = 0, cnb = 0;
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+  std::vector<cudaEvent_t> ev;
   std::string err;
 };
+
+static inline int win_b0(const rbt_handle* h) { return h->cnb ? h->cb0 : 0; }
+static inline int win_nb(const rbt_handle* h) { return h->cnb ? h->cnb : h->batch; }
 
 struct rbt_uhandle {
   int nv = 0, N = 0, batch = 0, device = 0;
@@ -161,6 +172,11 @@ int rbt_create(const rbt_dims* dims, int n_grid_max, int batch, int device, rbt_
 static double** buf_slot(rbt_handle* h, int which);
 
 int rbt_destroy(rbt_handle* h) {
+  if (h) {
+    if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
+    if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
+    for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
+  }
   if (!h) return RBT_ERR_ARG;
   cudaSetDevice(h->device);
   cudaFree(h->d_ctrl);
@@ -276,6 +292,9 @@ int rbt_bind_buffer(rbt_handle* h, int which, double* dev) {
   return RBT_OK;
 }
 
+static long long stage_xfer(rbt_handle* h, int which, bool up, const double* host_c, double* host_m, int b0, int nb,
+                            cudaStream_t st, bool do_copy, int* rc_out);
+
 // KKT upload plan: one strided copy of the core section [Fxx|Fvu|Fx|lx|lu|Qxx|Qxu|Quu] of every record (record padding and
 // unused switching/STO sections never cross PCIe), plus one strided copy per stage that carries extras.
 static long long kkt_upload(rbt_handle* h, const double* host, cudaStream_t st, bool do_copy, int* rc_out) {
@@ -310,10 +329,11 @@ static long long kkt_upload(rbt_handle* h, const double* host, cudaStream_t st, 
 
 long long rbt_upload_bytes(rbt_handle* h, int which) {
   if (!h || h->n_grid == 0) return -1;
-  if (which == RBT_BUF_DX0 || which == RBT_BUF_LIN || which == RBT_BUF_CON || which == RBT_BUF_SOL)
-    return rbt_buf_doubles(h, which) * 8;
-  if (which != RBT_BUF_KKT) return -1;
   int rc = RBT_OK;
+  if (which == RBT_BUF_DX0) return rbt_buf_doubles(h, which) * 8;
+  if (which == RBT_BUF_LIN || which == RBT_BUF_CON || which == RBT_BUF_SOL)
+    return h->stage_ready ? stage_xfer(h, which, true, nullptr, nullptr, 0, h->batch, nullptr, false, &rc) : -1;
+  if (which != RBT_BUF_KKT) return -1;
   return kkt_upload(h, nullptr, nullptr, false, &rc);
 }
 
@@ -329,6 +349,15 @@ int rbt_upload(rbt_handle* h, int which, const double* host, void* stream) {
     kkt_upload(h, host, (cudaStream_t)stream, true, &rc);
     if (rc != RBT_OK) {
       h->err = std::string("rbt_upload(KKT): ") + cudaGetErrorString(cudaGetLastError());
+      return rc;
+    }
+    return RBT_OK;
+  }
+  if (which != RBT_BUF_DX0) {  // trimmed strided copies (see stage_xfer)
+    int rc = RBT_OK;
+    stage_xfer(h, which, true, host, nullptr, 0, h->batch, (cudaStream_t)stream, true, &rc);
+    if (rc != RBT_OK) {
+      h->err = std::string("rbt_upload: ") + cudaGetErrorString(cudaGetLastError());
       return rc;
     }
     return RBT_OK;
@@ -371,21 +400,23 @@ static int launch_backward(rbt_handle* h, int write_fact, cudaStream_t st) {
   rbt::BwdParams p;
   p.L = h->L;
   p.ctrl = h->d_ctrl;
+  const int b0 = win_b0(h), nb = win_nb(h);
+  const size_t go = size_t(b0) * h->n_grid;
   p.n_grid = h->n_grid;
-  p.batch = h->batch;
+  p.batch = nb;
   p.max_dts0 = h->max_dts0;
-  p.kkt = h->d_kkt;
-  p.ric = h->d_ric;
-  p.fact = write_fact ? h->d_fact : nullptr;
-  p.info = h->d_info;
+  p.kkt = h->d_kkt + go * h->L.k_stride;
+  p.ric = h->d_ric + go * h->L.r_stride;
+  p.fact = write_fact ? h->d_fact + go * h->L.f_stride : nullptr;
+  p.info = h->d_info + b0;
   p.sm_arrivals = h->d_arrivals;
   p.stagger_ns = h->stagger_ns;
   p.timeline = h->d_timeline;
   p.timeline_cta = h->timeline_cta;
-  if (!h->keep_info) RBT_CUDA(h, cudaMemsetAsync(h->d_info, 0, size_t(h->batch) * sizeof(int), st));
+  if (!h->keep_info) RBT_CUDA(h, cudaMemsetAsync(h->d_info + b0, 0, size_t(nb) * sizeof(int), st));
   h->keep_info = false;
   if (h->stagger_ns > 0) RBT_CUDA(h, cudaMemsetAsync(h->d_arrivals, 0, 1024 * sizeof(int), st));
-  kern<<<h->batch, C::NTHREADS, C::SMEM_BYTES, st>>>(p);
+  kern<<<nb, C::NTHREADS, C::SMEM_BYTES, st>>>(p);
   RBT_CUDA(h, cudaGetLastError());
   h->launches += 1;
   return RBT_OK;
@@ -403,13 +434,15 @@ static int launch_forward(rbt_handle* h, cudaStream_t st) {
   rbt::FwdParams p;
   p.L = h->L;
   p.ctrl = h->d_ctrl;
+  const int b0 = win_b0(h), nb = win_nb(h);
+  const size_t go = size_t(b0) * h->n_grid;
   p.n_grid = h->n_grid;
-  p.batch = h->batch;
-  p.kkt = h->d_kkt;
-  p.ric = h->d_ric;
-  p.dx0 = h->d_dx0;
-  p.dir = h->d_dir;
-  kern<<<h->batch, C::NTHREADS, C::SMEM_BYTES, st>>>(p);
+  p.batch = nb;
+  p.kkt = h->d_kkt + go * h->L.k_stride;
+  p.ric = h->d_ric + go * h->L.r_stride;
+  p.dx0 = h->d_dx0 + size_t(b0) * h->L.nx;
+  p.dir = h->d_dir + go * h->L.d_stride;
+  kern<<<nb, C::NTHREADS, C::SMEM_BYTES, st>>>(p);
   RBT_CUDA(h, cudaGetLastError());
   h->launches += 1;
   return RBT_OK;
@@ -517,6 +550,8 @@ int rbt_stage_setup(rbt_handle* h, const rbt_stage_dims* sd, const rbt_constrain
   RBT_CUDA(h, cudaMalloc(&h->d_xd, per * h->S.x_stride * 8));
   RBT_CUDA(h, cudaMalloc(&h->d_steps, size_t(h->batch) * 2 * 8));
   RBT_CUDA(h, cudaMalloc(&h->d_ones, size_t(h->batch) * 2 * 8));
+  RBT_CUDA(h, cudaMemset(h->d_lin, 0, per * h->S.l_stride * 8));  // uploads skip record padding: keep it defined
+  RBT_CUDA(h, cudaMemset(h->d_sol, 0, per * h->S.s_stride * 8));
   RBT_CUDA(h, cudaMemset(h->d_ex, 0, per * h->S.e_stride * 8));
   RBT_CUDA(h, cudaMemset(h->d_xd, 0, per * h->S.x_stride * 8));
   RBT_CUDA(h, cudaMemset(h->d_con, 0, per * h->S.c_stride * 8));
@@ -533,17 +568,19 @@ static rbt::StageParams make_stage_params(rbt_handle* h) {
   p.S = h->S;
   p.tab = h->table;
   p.ctrl = h->d_ctrl;
+  const int b0 = win_b0(h);
+  const size_t go = size_t(b0) * h->n_grid;
   p.n_grid = h->n_grid;
-  p.batch = h->batch;
-  p.lin = h->d_lin;
-  p.con = h->d_con;
-  p.kkt = h->d_kkt;
-  p.ex = h->d_ex;
-  p.dir = h->d_dir;
-  p.xd = h->d_xd;
-  p.sol = h->d_sol;
-  p.steps = h->d_steps;
-  p.info = h->d_info;
+  p.batch = win_nb(h);
+  p.lin = h->d_lin + go * h->S.l_stride;
+  p.con = h->d_con + go * h->S.c_stride;
+  p.kkt = h->d_kkt + go * h->L.k_stride;
+  p.ex = h->d_ex + go * h->S.e_stride;
+  p.dir = h->d_dir + go * h->L.d_stride;
+  p.xd = h->d_xd + go * h->S.x_stride;
+  p.sol = h->d_sol + go * h->S.s_stride;
+  p.steps = h->d_steps + 2 * size_t(b0);
+  p.info = h->d_info + b0;
   // box rows acting on each target entry (var, idx), in ascending row order (deterministic accumulation on the device)
   for (int t = 0; t < RBT_MAX_TARGETS; ++t)
     for (int q = 0; q < 4; ++q) p.tgt_rows[t][q] = -1;
@@ -577,10 +614,11 @@ int rbt_condense(rbt_handle* h, void* stream) {
     attr_done = true;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  RBT_CUDA(h, cudaMemsetAsync(h->d_info, 0, size_t(h->batch) * sizeof(int), st));
-  rbt::mjtjinv_kernel<18, 12><<<(h->batch * h->n_grid + 1) / 2, 64, 0, st>>>(make_stage_params(h));  // K1: Z = [[M,J^T],[J,0]]^-1
+  const int nb = win_nb(h);
+  RBT_CUDA(h, cudaMemsetAsync(h->d_info + win_b0(h), 0, size_t(nb) * sizeof(int), st));
+  rbt::mjtjinv_kernel<18, 12><<<(nb * h->n_grid + 1) / 2, 64, 0, st>>>(make_stage_params(h));  // K1: Z = [[M,J^T],[J,0]]^-1
   RBT_CUDA(h, cudaGetLastError());
-  kern<<<h->batch * h->n_grid, C::NTHREADS, C::SMEM_BYTES, st>>>(make_stage_params(h));     // K2: condensing (DMMA)
+  kern<<<nb * h->n_grid, C::NTHREADS, C::SMEM_BYTES, st>>>(make_stage_params(h));     // K2: condensing (DMMA)
   RBT_CUDA(h, cudaGetLastError());
   h->launches += 2;
   h->keep_info = true;
@@ -590,8 +628,8 @@ int rbt_condense(rbt_handle* h, void* stream) {
 int rbt_expand_and_step_sizes(rbt_handle* h, void* stream) {
   RBT_STAGE_CHECK(h, "rbt_expand_and_step_sizes");
   cudaStream_t st = (cudaStream_t)stream;
-  RBT_CUDA(h, cudaMemcpyAsync(h->d_steps, h->d_ones, size_t(h->batch) * 2 * 8, cudaMemcpyDeviceToDevice, st));
-  rbt::expand_kernel<18, 12, 12><<<h->batch * h->n_grid, rbt::XTHR, 0, st>>>(make_stage_params(h));
+  RBT_CUDA(h, cudaMemcpyAsync(h->d_steps + 2 * size_t(win_b0(h)), h->d_ones, size_t(win_nb(h)) * 2 * 8, cudaMemcpyDeviceToDevice, st));
+  rbt::expand_kernel<18, 12, 12><<<win_nb(h) * h->n_grid, rbt::XTHR, 0, st>>>(make_stage_params(h));
   RBT_CUDA(h, cudaGetLastError());
   h->launches += 1;
   return RBT_OK;
@@ -599,28 +637,114 @@ int rbt_expand_and_step_sizes(rbt_handle* h, void* stream) {
 
 int rbt_update(rbt_handle* h, void* stream) {
   RBT_STAGE_CHECK(h, "rbt_update");
-  rbt::update_kernel<18, 12, 12><<<h->batch * h->n_grid, rbt::XTHR, 0, (cudaStream_t)stream>>>(make_stage_params(h));
+  rbt::update_kernel<18, 12, 12><<<win_nb(h) * h->n_grid, rbt::XTHR, 0, (cudaStream_t)stream>>>(make_stage_params(h));
   RBT_CUDA(h, cudaGetLastError());
   h->launches += 1;
+  return RBT_OK;
+}
+
+// Host <-> device traffic of the stage layer, for the batch window [b0, b0 + nb).  Only what the kernels read / what
+// persists crosses PCIe: record padding never does, the switching-constraint section of the linearization record only for
+// the stages that carry one, of the PDIPM record slack | dual | residual go up and slack | dual come back.
+static long long stage_xfer(rbt_handle* h, int which, bool up, const double* host_c, double* host_m, int b0, int nb,
+                            cudaStream_t st, bool do_copy, int* rc_out) {
+  const rbt_stage_layout& S = h->S;
+  const size_t rows = size_t(nb) * h->n_grid, go = size_t(b0) * h->n_grid;
+  long long bytes = 0;
+  auto copy2d = [&](double* dev, const double* hc, double* hm, size_t off, size_t stride, size_t width, size_t pitch_rows,
+                    size_t nrows) {
+    bytes += (long long)(width * 8 * nrows);
+    if (!do_copy || *rc_out != RBT_OK) return;
+    const size_t pitch = stride * pitch_rows * 8;
+    cudaError_t e = up ? cudaMemcpy2DAsync(dev + off, pitch, hc + off, pitch, width * 8, nrows, cudaMemcpyHostToDevice, st)
+                       : cudaMemcpy2DAsync(hm + off, pitch, dev + off, pitch, width * 8, nrows, cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) *rc_out = RBT_ERR_CUDA;
+  };
+  if (which == RBT_BUF_LIN) {
+    const size_t base = go * S.l_stride;
+    const size_t tail = size_t(S.l_dgdf) + ((15 * S.ncon + 1) & ~1) - S.l_ha;
+    copy2d(h->d_lin, host_c, host_m, base, S.l_stride, S.l_Phix, 1, rows);            // M .. se3
+    copy2d(h->d_lin, host_c, host_m, base + S.l_ha, S.l_stride, tail, 1, rows);       // ha .. dgdf
+    for (int i = 0; i < h->n_grid; ++i)
+      if (h->ctrl[i].ns > 0 && h->ctrl[i].type != RBT_IMPACT)                         // Phix, Phia, p, Phit
+        copy2d(h->d_lin, host_c, host_m, base + size_t(i) * S.l_stride + S.l_Phix, S.l_stride, S.l_ha - S.l_Phix, h->n_grid, nb);
+  } else if (which == RBT_BUF_CON) {
+    copy2d(h->d_con, host_c, host_m, go * S.c_stride + S.c_slack, S.c_stride, size_t(up ? 3 : 2) * S.ncp, 1, rows);
+  } else if (which == RBT_BUF_SOL) {
+    copy2d(h->d_sol, host_c, host_m, go * S.s_stride, S.s_stride, size_t(S.s_xi) + S.nsm, 1, rows);
+  } else if (which == RBT_BUF_DX0) {
+    copy2d(h->d_dx0, host_c, host_m, size_t(b0) * h->L.nx, h->L.nx, h->L.nx, 1, nb);
+  } else if (which == RBT_BUF_STEPS) {
+    copy2d(h->d_steps, host_c, host_m, 2 * size_t(b0), 2, 2, 1, nb);
+  }
+  return bytes;
+}
+
+int rbt_iteration_host_bytes(rbt_handle* h, long long* h2d, long long* d2h) {
+  if (!h || !h->stage_ready || h->n_grid == 0) return RBT_ERR_STATE;
+  int rc = RBT_OK;
+  long long up = 0, down = 0;
+  for (int w : {RBT_BUF_LIN, RBT_BUF_CON, RBT_BUF_SOL, RBT_BUF_DX0}) up += stage_xfer(h, w, true, nullptr, nullptr, 0, h->batch, nullptr, false, &rc);
+  for (int w : {RBT_BUF_SOL, RBT_BUF_CON, RBT_BUF_STEPS}) down += stage_xfer(h, w, false, nullptr, nullptr, 0, h->batch, nullptr, false, &rc);
+  if (h2d) *h2d = up;
+  if (d2h) *d2h = down;
   return RBT_OK;
 }
 
 int rbt_iteration_host(rbt_handle* h, const double* lin_host, const double* con_host, const double* sol_host,
                        const double* dx0_host, double* sol_out, double* con_out, double* steps_out, void* stream) {
   if (!h || !lin_host || !con_host || !sol_host || !dx0_host) return RBT_ERR_ARG;
-  int rc;
-  if ((rc = rbt_upload(h, RBT_BUF_LIN, lin_host, stream))) return rc;
-  if ((rc = rbt_upload(h, RBT_BUF_CON, con_host, stream))) return rc;
-  if ((rc = rbt_upload(h, RBT_BUF_SOL, sol_host, stream))) return rc;
-  if ((rc = rbt_upload(h, RBT_BUF_DX0, dx0_host, stream))) return rc;
-  if ((rc = rbt_condense(h, stream))) return rc;
-  if ((rc = rbt_riccati_backward(h, 0, stream))) return rc;
-  if ((rc = rbt_riccati_forward(h, stream))) return rc;
-  if ((rc = rbt_expand_and_step_sizes(h, stream))) return rc;
-  if ((rc = rbt_update(h, stream))) return rc;
-  if (sol_out && (rc = rbt_download(h, RBT_BUF_SOL, sol_out, stream))) return rc;
-  if (con_out && (rc = rbt_download(h, RBT_BUF_CON, con_out, stream))) return rc;
-  if (steps_out && (rc = rbt_download(h, RBT_BUF_STEPS, steps_out, stream))) return rc;
+  RBT_STAGE_CHECK(h, "rbt_iteration_host");
+  cudaStream_t st = (cudaStream_t)stream;
+  // chunks of the batch: the upload of chunk c+1, the kernels of chunk c and the download of chunk c-1 overlap
+  int n_chunks = h->batch >= 512 ? 8 : (h->batch >= 128 ? 4 : 1);
+  if (const char* e = getenv("RBT_E2E_CHUNKS")) n_chunks = std::max(1, std::min(atoi(e), h->batch));
+  if (!h->s_h2d) {
+    RBT_CUDA(h, cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
+    RBT_CUDA(h, cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
+  }
+  while ((int)h->ev.size() < 2 * n_chunks + 2) {
+    cudaEvent_t e;
+    RBT_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    h->ev.push_back(e);
+  }
+  cudaEvent_t ev_entry = h->ev[2 * n_chunks], ev_exit = h->ev[2 * n_chunks + 1];
+  RBT_CUDA(h, cudaEventRecord(ev_entry, st));            // device buffers may still be read by earlier work on `stream`
+  RBT_CUDA(h, cudaStreamWaitEvent(h->s_h2d, ev_entry, 0));
+  RBT_CUDA(h, cudaStreamWaitEvent(h->s_d2h, ev_entry, 0));
+  int rc = RBT_OK;
+  for (int c = 0; c < n_chunks && rc == RBT_OK; ++c) {
+    const int b0 = int((long long)h->batch * c / n_chunks), b1 = int((long long)h->batch * (c + 1) / n_chunks), nb = b1 - b0;
+    if (nb <= 0) continue;
+    stage_xfer(h, RBT_BUF_LIN, true, lin_host, nullptr, b0, nb, h->s_h2d, true, &rc);
+    stage_xfer(h, RBT_BUF_CON, true, con_host, nullptr, b0, nb, h->s_h2d, true, &rc);
+    stage_xfer(h, RBT_BUF_SOL, true, sol_host, nullptr, b0, nb, h->s_h2d, true, &rc);
+    stage_xfer(h, RBT_BUF_DX0, true, dx0_host, nullptr, b0, nb, h->s_h2d, true, &rc);
+    if (rc != RBT_OK) break;
+    RBT_CUDA(h, cudaEventRecord(h->ev[2 * c], h->s_h2d));
+    RBT_CUDA(h, cudaStreamWaitEvent(st, h->ev[2 * c], 0));
+    h->cb0 = b0;
+    h->cnb = nb;
+    if (!(rc = rbt_condense(h, stream)) && !(rc = rbt_riccati_backward(h, 0, stream)) && !(rc = rbt_riccati_forward(h, stream)) &&
+        !(rc = rbt_expand_and_step_sizes(h, stream)))
+      rc = rbt_update(h, stream);
+    h->cb0 = 0;
+    h->cnb = 0;
+    if (rc != RBT_OK) break;
+    RBT_CUDA(h, cudaEventRecord(h->ev[2 * c + 1], st));
+    RBT_CUDA(h, cudaStreamWaitEvent(h->s_d2h, h->ev[2 * c + 1], 0));
+    if (sol_out) stage_xfer(h, RBT_BUF_SOL, false, nullptr, sol_out, b0, nb, h->s_d2h, true, &rc);
+    if (con_out) stage_xfer(h, RBT_BUF_CON, false, nullptr, con_out, b0, nb, h->s_d2h, true, &rc);
+    if (steps_out) stage_xfer(h, RBT_BUF_STEPS, false, nullptr, steps_out, b0, nb, h->s_d2h, true, &rc);
+  }
+  h->cb0 = 0;
+  h->cnb = 0;
+  if (rc != RBT_OK) {
+    if (h->err.empty() || rc == RBT_ERR_CUDA) h->err = std::string("rbt_iteration_host: ") + cudaGetErrorString(cudaGetLastError());
+    return rc;
+  }
+  RBT_CUDA(h, cudaEventRecord(ev_exit, h->s_d2h));       // `stream` (what the caller synchronizes) covers the downloads too
+  RBT_CUDA(h, cudaStreamWaitEvent(st, ev_exit, 0));
   return RBT_OK;
 }
 

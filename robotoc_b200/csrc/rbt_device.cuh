@@ -64,6 +64,11 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                : "d"(a), "d"(b));
 }
 
+// Bulk L2 prefetch (no shared-memory destination, no completion tracking): bytes multiple of 16, 16-byte aligned source.
+__device__ __forceinline__ void l2_prefetch_bulk(const void* gmem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
+}
+
 // Tile origin for an extent M covered by 8-wide tiles: full tiles, then one tile pulled back to end at M
 // (overlapping rows/cols are simply computed twice with identical operands -> identical bits).
 __host__ __device__ constexpr int tile_off(int t, int M) { return (8 * t + 8 <= M) ? 8 * t : (M >= 8 ? M - 8 : 0); }

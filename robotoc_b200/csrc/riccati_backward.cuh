@@ -229,6 +229,8 @@ __global__ void __launch_bounds__(BwdCfg<NV, NU, NS>::NTHREADS, RBT_BWD_MIN_CTAS
     fence_proxy_async();
     mbar_expect_tx(&bars[0], uint32_t(L.k_stage_size) * 8u);
     tma_load_1d(sIn, rec + L.k_Fxx, uint32_t(L.k_stage_size) * 8u, &bars[0]);
+    // Qxx | Qxu | Quu are read as accumulator fragments straight from global memory in phase B: pull them into L2 now
+    l2_prefetch_bulk(rec + L.k_Qxx, uint32_t(L.k_core_size - L.k_stage_size) * 8u);
     if (cs.ns > 0 || cs.sto) {
       mbar_expect_tx(&bars[1], uint32_t(L.k_extra_size) * 8u);
       tma_load_1d(sEx, rec + L.k_Phix, uint32_t(L.k_extra_size) * 8u, &bars[1]);

@@ -71,6 +71,26 @@ class DirectMultipleShooting:
             self._up(SOL, sol, self.layout.s_stride, stream)
         _check(self._lib.rbt_update(self._h, stream), self.rr._err, "DirectMultipleShooting")
 
+    def iteration_host(self, lin, con, sol, dx0, stream=None):
+        """The linear-algebra body of OCPSolver::updateSolution (src/solver/ocp_solver.cpp:118-144) in ONE call with host
+        buffers (rbt_iteration_host): returns (updated solution, PDIPM record with slack / dual updated, step sizes).
+        Only slack and dual of the PDIPM record come back from the device; its other fields are returned as passed in."""
+        for a, st in ((lin, self.layout.l_stride), (con, self.layout.c_stride), (sol, self.layout.s_stride)):
+            if a.shape != self._shape(st):
+                raise ValueError(f"[DirectMultipleShooting] invalid argument: expected shape {self._shape(st)}, got {a.shape}")
+        sol_out, con_out = sol.copy(), con.copy()
+        steps = np.empty((self.rr.batch, 2))
+        _check(self._lib.rbt_iteration_host(self._h, _vp(lin), _vp(con), _vp(sol), _vp(dx0), _vp(sol_out), _vp(con_out),
+                                            _vp(steps), stream), self.rr._err, "DirectMultipleShooting")
+        self.rr.synchronize(stream)
+        return sol_out, con_out, steps
+
+    def iteration_host_bytes(self):
+        h2d, d2h = ctypes.c_longlong(), ctypes.c_longlong()
+        _check(self._lib.rbt_iteration_host_bytes(self._h, ctypes.byref(h2d), ctypes.byref(d2h)), self.rr._err,
+               "DirectMultipleShooting")
+        return h2d.value, d2h.value
+
     # -- data access ---------------------------------------------------------------------------------------
     def getKKT(self, stream=None):
         return self._down(0, self._shape(self.rr.layout.k_stride), stream)

@@ -2,6 +2,8 @@
 condense -> backward -> forward -> step sizes -> update, against the CPU oracle, through the C ABI."""
 import ctypes
 
+import os
+
 import numpy as np
 import pytest
 
@@ -99,6 +101,20 @@ def _run(ctrl, batch, seed):
             for f, n in (("e_Z", 900), ("e_R", 1080), ("e_Qafqv", 1080), ("e_r", 30), ("e_laf", 30)):
                 o = getattr(S, f)
                 _cmp(f"{f}[{i}]", ex[:, i, o:o + n], ref["ex_upd"][:, i, o:o + n])
+    # the one-call host path (chunked, trimmed transfers) gives the same bits as the step-by-step path
+    for chunks in ("1", "3"):
+        os.environ["RBT_E2E_CHUNKS"] = chunks
+        sol2, con2, steps2 = dms.iteration_host(lin, con, sol, dx0)
+        used = S.s_xi + S.nsm
+        np.testing.assert_array_equal(sol2[:, :, :used], sol_g[:, :, :used])
+        np.testing.assert_array_equal(steps2, steps)
+        for f in ("c_slack", "c_dual"):
+            o = getattr(S, f)
+            np.testing.assert_array_equal(con2[:, :, o:o + S.nc], cc[:, :, o:o + S.nc])
+        np.testing.assert_array_equal(con2[:, :, S.c_res:], con[:, :, S.c_res:])  # not refreshed from the device
+    del os.environ["RBT_E2E_CHUNKS"]
+    h2d, d2h = dms.iteration_host_bytes()
+    assert 0 < d2h < h2d < lin.nbytes + con.nbytes + sol.nbytes + dx0.nbytes
     rr.close()
 
 
