@@ -32,6 +32,10 @@ N_HORIZON = 40
 BYTES_PER_STAGE_BWD = (3468 + 1776) * 8      # backward reads 3468 + writes 1776
 BYTES_PER_STAGE_FWD = (3324 + 84) * 8        # forward reads 3324 + writes 84
 BYTES_PER_STAGE_CONDENSE = (2100 + 3600) * 8 + (3468) * 8  # 8(d): condense reads ~2.1k, writes ~3.6k (+ the KKT record when not fused)
+BYTES_PER_STAGE_MJTJINV = (324 + 216 + 900) * 8               # K1 reads M, J and writes Z
+# DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of one `ncu --set full` capture of this very command
+# at batch 1024 (profiles/r1_final_condense_kernel_ncu_summary.txt, profiles/r1_final_riccati_backward_kernel_ncu_summary.txt); scaled by batch/1024.
+NCU_TRAFFIC_1024 = {"condense": 1.865444e9 + 2.517468e9, "riccati_backward": 1.339999e9 + 0.670331e9}
 FLOP_PER_STAGE_BWD = 285.7e3
 FLOP_PER_STAGE_CONDENSE = 300e3
 
@@ -284,7 +288,7 @@ def main():
     rr.bind_buffer(7, ctypes.c_void_p(con_work.data_ptr()))
     rr.bind_buffer(9, ctypes.c_void_p(sol_work.data_ptr()))
 
-    NAMES = ["condense", "riccati_backward", "riccati_forward", "expand_step_sizes", "update"]
+    NAMES = ["condense_total", "riccati_backward", "riccati_forward", "expand_step_sizes", "update"]
 
     def step(ev=None):
         # restore the records the iteration mutates (D2D, outside the per-kernel event pairs but inside the step time)
@@ -296,7 +300,12 @@ def main():
         for k, call in enumerate(calls):
             if ev is not None:
                 ev[k].record(stream)
+                if k == 0:  # rbt_condense = MJtJinv kernel + condensing kernel: an event between them splits the two
+                    ev[7].record(stream)  # (creates the handle)
+                    lib.rbt_set_condense_event(rr._h, ctypes.c_void_p(ev[7].cuda_event))
             call()
+            if ev is not None and k == 0:
+                lib.rbt_set_condense_event(rr._h, None)
         if ev is not None:
             ev[len(calls)].record(stream)
         if world > 1:
@@ -308,7 +317,7 @@ def main():
         step()
     torch.cuda.synchronize()
     l0 = rr.launch_count()
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(7)] for _ in range(args.steps)]
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(8)] for _ in range(args.steps)]
     t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     clk = ClockSampler(local)
     if rank == 0 and not os.environ.get("RBT_BENCH_NO_CLOCKS"):
@@ -329,6 +338,8 @@ def main():
     launches = rr.launch_count() - l0
     ms = t_beg.elapsed_time(t_end)
     kms = {n: float(np.mean([e[k].elapsed_time(e[k + 1]) for e in evs])) for k, n in enumerate(NAMES)}
+    kms["mjtjinv"] = float(np.mean([e[0].elapsed_time(e[7]) for e in evs]))
+    kms["condense"] = float(np.mean([e[7].elapsed_time(e[1]) for e in evs]))
     if world > 1:
         kms["nccl_allgather_step"] = float(np.mean([e[5].elapsed_time(e[6]) for e in evs]))
     print(f"[bench] rank {rank}: {ms / args.steps:.3f} ms/step on its own device clock", file=sys.stderr, flush=True)
@@ -375,7 +386,7 @@ def main():
     if rank == 0:
         peak, peak_src = peaks()
         units = args.batch * N_HORIZON                       # standard stages per launch
-        dom = max(kms, key=kms.get)
+        dom = max((k for k in kms if k != "condense_total"), key=kms.get)
         alg_bytes = {"riccati_backward": BYTES_PER_STAGE_BWD, "riccati_forward": BYTES_PER_STAGE_FWD,
                      "condense": BYTES_PER_STAGE_CONDENSE}.get(dom, BYTES_PER_STAGE_BWD) * units
         ach = alg_bytes / (kms[dom] * 1e-3) / 1e9
@@ -398,11 +409,14 @@ def main():
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": args.e2e_steps,
                     "api": "rbt_iteration_host (pinned host linearisation/PDIPM/solution in; solution, slack/dual, step sizes out)"},
             "roofline": {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                         "traffic": (NCU_TRAFFIC_1024[dom] * args.batch / 1024) if dom in NCU_TRAFFIC_1024 else None,
+                         "traffic_source": "ncu --set full capture of this command, committed under profiles/ (per launch)",
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                          "per_kernel_GBps": {
                              "riccati_backward": BYTES_PER_STAGE_BWD * units / (kms["riccati_backward"] * 1e-3) / 1e9,
                              "riccati_forward": BYTES_PER_STAGE_FWD * units / (kms["riccati_forward"] * 1e-3) / 1e9,
-                             "condense": BYTES_PER_STAGE_CONDENSE * units / (kms["condense"] * 1e-3) / 1e9},
+                             "condense": BYTES_PER_STAGE_CONDENSE * units / (kms["condense"] * 1e-3) / 1e9,
+                             "mjtjinv": BYTES_PER_STAGE_MJTJINV * units / (kms["mjtjinv"] * 1e-3) / 1e9},
                          "fp64_tflops": {"riccati_backward": FLOP_PER_STAGE_BWD * units / (kms["riccati_backward"] * 1e-3) / 1e12,
                                          "condense": FLOP_PER_STAGE_CONDENSE * units / (kms["condense"] * 1e-3) / 1e12},
                          "fp64_peak_tflops": 37.1},

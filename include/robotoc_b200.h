@@ -118,6 +118,9 @@ int rbt_stage_setup(rbt_handle* h, const rbt_stage_dims* sdims, const rbt_constr
  * terminal_stage.cpp:102-106): Constraints::condenseSlackAndDual, condenseContactDynamics / condenseImpactDynamics,
  * correctLinearizeStateEquation, STO scaling.  Reads RBT_BUF_LIN, RBT_BUF_CON; writes RBT_BUF_KKT, RBT_BUF_EXP, RBT_BUF_CON. */
 int rbt_condense(rbt_handle* h, void* stream);
+/* Measurement aid: rbt_condense issues two kernels (MJtJinv, then the condensing proper); a caller-owned cudaEvent_t given
+ * here is recorded between them so each can be timed on its own (NULL switches it off). */
+int rbt_set_condense_event(rbt_handle* h, void* cuda_event);
 /* DirectMultipleShooting::computeStepSizes + maxPrimalStepSize / maxDualStepSize (direct_multiple_shooting.cpp:174-209):
  * expandPrimal of every stage, slack/dual directions, fraction-to-boundary, min over the horizon.
  * Reads RBT_BUF_DIR, RBT_BUF_EXP, RBT_BUF_LIN; writes RBT_BUF_XDIR (daf), RBT_BUF_CON (dslack, ddual), RBT_BUF_STEPS. */

@@ -67,6 +67,7 @@ struct rbt_handle {
   // batch window [cb0, cb0 + cnb) the launch helpers work on (cnb == 0: the whole batch); used by rbt_iteration_host to
   // pipeline uploads, kernels and downloads over chunks of the batch
   int cb0 = 0, cnb = 0;
+  cudaEvent_t ev_condense_mid = nullptr;  // caller-owned event recorded between the two kernels of rbt_condense (timing)
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
   std::vector<cudaEvent_t> ev;
   std::string err;
@@ -618,10 +619,17 @@ int rbt_condense(rbt_handle* h, void* stream) {
   RBT_CUDA(h, cudaMemsetAsync(h->d_info + win_b0(h), 0, size_t(nb) * sizeof(int), st));
   rbt::mjtjinv_kernel<18, 12><<<(nb * h->n_grid + 1) / 2, 64, 0, st>>>(make_stage_params(h));  // K1: Z = [[M,J^T],[J,0]]^-1
   RBT_CUDA(h, cudaGetLastError());
+  if (h->ev_condense_mid) RBT_CUDA(h, cudaEventRecord(h->ev_condense_mid, st));
   kern<<<nb * h->n_grid, C::NTHREADS, C::SMEM_BYTES, st>>>(make_stage_params(h));     // K2: condensing (DMMA)
   RBT_CUDA(h, cudaGetLastError());
   h->launches += 2;
   h->keep_info = true;
+  return RBT_OK;
+}
+
+int rbt_set_condense_event(rbt_handle* h, void* cuda_event) {
+  if (!h) return RBT_ERR_ARG;
+  h->ev_condense_mid = (cudaEvent_t)cuda_event;
   return RBT_OK;
 }
 
