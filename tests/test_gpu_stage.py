@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import oracle_lib
-from helpers import rel_err, small_event_schedule, trot_schedule
+from helpers import jump_sto_schedule, rel_err, small_event_schedule, trot_schedule
 from robotoc_b200 import ANYMAL, DirectMultipleShooting, Layout, RiccatiRecursion, StageDims, StageLayout, anymal_constraint_table
 from robotoc_b200.schedule import IMPACT, TERMINAL
 from robotoc_b200.stage import make_stage_inputs
@@ -126,3 +126,15 @@ def test_stage_layer_small_event_schedule():
 def test_stage_layer_trot_n40():
     td, ev, ctrl = trot_schedule(40)
     _run(ctrl, batch=2, seed=22)
+
+
+def test_stage_layer_small_event_schedule_sto():
+    """Switching-time optimisation on: hx / hu / fx / Qtt scaling in the condensing, dts terms in the dual expansion."""
+    td, ev, ctrl = small_event_schedule(True)
+    _run(ctrl, batch=3, seed=23)
+
+
+def test_stage_layer_jump_sto_n80():
+    """BASELINE.json configs[3] schedule (ANYmal jumping, STO, N=80) through the full iteration."""
+    td, ev, ctrl = jump_sto_schedule(80)
+    _run(ctrl, batch=2, seed=24)
