@@ -274,3 +274,106 @@ class RiccatiRecursion {
 };
 
 }  // namespace robotoc_b200
+
+// ---------------------------------------------------------------------------------------------------------------------
+// robotoc_b200::DirectMultipleShooting -- the part of robotoc::DirectMultipleShooting that is on the hot path
+// (include/robotoc/ocp/direct_multiple_shooting.hpp:86-199), over the stage-layer records of include/rbt_stage_layout.h.
+// It shares the handle (and so the KKT / direction buffers on the device) of a RiccatiRecursion, exactly as the
+// reference's OCPSolver owns both and passes kkt_matrix_ / d_ between them (src/solver/ocp_solver.cpp:118-144):
+//
+//   dms.evalKKT(lin, con);                 // condensing tail of evalKKT              direct_multiple_shooting.cpp:129-159
+//   riccati.backwardRiccatiRecursion();    // on the device-resident KKT records
+//   riccati.forwardRiccatiRecursion(dx0);
+//   dms.computeStepSizes();                //                                         :174-199
+//   dms.maxPrimalStepSize(); dms.maxDualStepSize();                                //  :202-209
+//   dms.integrateSolution(sol, con);       //                                         :212-241
+namespace robotoc_b200 {
+
+class DeviceRiccatiRecursion {  // batch-of-one-or-more variant that keeps everything on the device between calls
+ public:
+  DeviceRiccatiRecursion(const rbt_dims& dims, const std::vector<rbt_stage_ctrl>& ctrl, int batch, double max_dts0 = 0.1,
+                         int device = 0)
+      : dims_(dims), n_grid_(int(ctrl.size())), batch_(batch) {
+    if (max_dts0 <= 0) throw std::out_of_range("[RiccatiRecursion] invalid argument: 'max_dts0' must be positive!");
+    if (rbt_create(&dims_, n_grid_, batch, device, &h_) != RBT_OK) {
+      const std::string msg = h_ ? rbt_last_error(h_) : "unsupported robot dimensions";
+      if (h_) rbt_destroy(h_);
+      throw std::runtime_error("[RiccatiRecursion] cannot create the B200 handle: " + msg);
+    }
+    check(rbt_set_schedule(h_, ctrl.data(), n_grid_, max_dts0));
+  }
+  ~DeviceRiccatiRecursion() { if (h_) rbt_destroy(h_); }
+  DeviceRiccatiRecursion(const DeviceRiccatiRecursion&) = delete;
+  DeviceRiccatiRecursion& operator=(const DeviceRiccatiRecursion&) = delete;
+  void backwardRiccatiRecursion() { check(rbt_riccati_backward(h_, 0, nullptr)); }
+  void forwardRiccatiRecursion(const std::vector<double>& dx0) {
+    if (dx0.size() != size_t(batch_) * 2 * dims_.nv) throw std::invalid_argument("[RiccatiRecursion] invalid argument: dx0 size");
+    check(rbt_upload(h_, RBT_BUF_DX0, dx0.data(), nullptr));
+    check(rbt_riccati_forward(h_, nullptr));
+  }
+  std::vector<double> download(int which) {
+    std::vector<double> out(size_t(rbt_buf_doubles(h_, which)));
+    check(rbt_download(h_, which, out.data(), nullptr));
+    check(rbt_sync(h_, nullptr));
+    return out;
+  }
+  rbt_handle* handle() { return h_; }
+  int batch() const { return batch_; }
+  int n_grid() const { return n_grid_; }
+  void check(int rc) {
+    if (rc == RBT_OK) return;
+    const std::string msg = rbt_last_error(h_);
+    if (rc == RBT_ERR_ARG) throw std::invalid_argument("[robotoc_b200] invalid argument: " + msg);
+    throw std::runtime_error("[robotoc_b200] " + msg);
+  }
+
+ private:
+  rbt_dims dims_;
+  int n_grid_, batch_;
+  rbt_handle* h_ = nullptr;
+};
+
+class DirectMultipleShooting {
+ public:
+  DirectMultipleShooting(DeviceRiccatiRecursion& riccati, const rbt_stage_dims& sdims, const rbt_constraint_table& constraints)
+      : rr_(riccati), sdims_(sdims) {
+    rbt_make_stage_layout(&sdims_, &S_);
+    rr_.check(rbt_stage_setup(rr_.handle(), &sdims_, &constraints));
+  }
+  /// The condensing tail of evalKKT for every stage of every OCP ("Forms linear system", intermediate_stage.cpp:133-148).
+  void evalKKT(const std::vector<double>& lin, const std::vector<double>& con) {
+    expect(lin, S_.l_stride, "lin");
+    expect(con, S_.c_stride, "con");
+    rr_.check(rbt_upload(rr_.handle(), RBT_BUF_LIN, lin.data(), nullptr));
+    rr_.check(rbt_upload(rr_.handle(), RBT_BUF_CON, con.data(), nullptr));
+    rr_.check(rbt_condense(rr_.handle(), nullptr));
+  }
+  void computeStepSizes() {
+    rr_.check(rbt_expand_and_step_sizes(rr_.handle(), nullptr));
+    steps_ = rr_.download(RBT_BUF_STEPS);
+  }
+  /// per OCP of the batch (the reference's scalar is entry 0 for batch 1)
+  double maxPrimalStepSize(int ocp = 0) const { return steps_.at(2 * size_t(ocp)); }
+  double maxDualStepSize(int ocp = 0) const { return steps_.at(2 * size_t(ocp) + 1); }
+  /// integrateSolution with the step sizes computeStepSizes left on the device; `sol` is updated in place.
+  void integrateSolution(std::vector<double>& sol) {
+    expect(sol, S_.s_stride, "sol");
+    rr_.check(rbt_upload(rr_.handle(), RBT_BUF_SOL, sol.data(), nullptr));
+    rr_.check(rbt_update(rr_.handle(), nullptr));
+    rr_.check(rbt_download(rr_.handle(), RBT_BUF_SOL, sol.data(), nullptr));
+    rr_.check(rbt_sync(rr_.handle(), nullptr));
+  }
+  const rbt_stage_layout& layout() const { return S_; }
+
+ private:
+  void expect(const std::vector<double>& a, int stride, const char* what) const {
+    if (a.size() != size_t(rr_.batch()) * rr_.n_grid() * stride)
+      throw std::invalid_argument(std::string("[DirectMultipleShooting] invalid argument: size of '") + what + "'");
+  }
+  DeviceRiccatiRecursion& rr_;
+  rbt_stage_dims sdims_;
+  rbt_stage_layout S_;
+  std::vector<double> steps_;
+};
+
+}  // namespace robotoc_b200

@@ -7,11 +7,11 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _build(tmp):
-    exe = os.path.join(tmp, "test_riccati_recursion")
+def _build(tmp, name="test_riccati_recursion"):
+    exe = os.path.join(tmp, name)
     gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
     subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
-    cmd = [gxx, "-std=c++14", "-O1", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "test_riccati_recursion.cpp"),
+    cmd = [gxx, "-std=c++14", "-O1", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", name + ".cpp"),
            "-L", os.path.join(ROOT, "robotoc_b200"), "-lrobotoc_b200", "-L", os.path.join(ROOT, "oracle"), "-loracle",
            "-Wl,-rpath," + os.path.join(ROOT, "robotoc_b200"), "-Wl,-rpath," + os.path.join(ROOT, "oracle"), "-o", exe]
     subprocess.run(cmd, check=True)
@@ -21,11 +21,20 @@ def _build(tmp):
 def test_cpp_adaptor_compiles_and_links(tmp_path):
     """CPU: the header compiles as C++14 and links against the C ABI (no compute call)."""
     assert os.path.exists(_build(str(tmp_path)))
+    assert os.path.exists(_build(str(tmp_path), "test_direct_multiple_shooting"))
 
 
 @pytest.mark.gpu
 def test_cpp_adaptor_matches_oracle(tmp_path):
     exe = _build(str(tmp_path))
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    print(out.stdout, out.stderr)
+    assert out.returncode == 0, out.stdout + out.stderr
+
+
+@pytest.mark.gpu
+def test_cpp_direct_multiple_shooting_matches_oracle(tmp_path):
+    exe = _build(str(tmp_path), "test_direct_multiple_shooting")
     out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     print(out.stdout, out.stderr)
     assert out.returncode == 0, out.stdout + out.stderr
