@@ -67,13 +67,14 @@ def build_problem(batch, seed):
 def build_iteration_problem(batch, seed, getter=None, kgetter=None):
     from helpers import trot_schedule
     from robotoc_b200 import ANYMAL, Layout, StageDims, StageLayout, anymal_constraint_table
-    from robotoc_b200.stage import make_stage_inputs
+    from robotoc_b200.stage import make_stage_inputs, symmetrize_lin
     table = anymal_constraint_table()
     sd = StageDims(ANYMAL, nf_max=12, n_contacts=table.n_contacts, n_box=table.n_box)
     S = StageLayout(sd, getter=getter)
     K = Layout(ANYMAL, getter=kgetter)
     td, ev, ctrl = trot_schedule(N_HORIZON)
     lin, con, sol, dx0 = make_stage_inputs(sd, S, ctrl, batch, seed)
+    lin = symmetrize_lin(S, lin)  # inertia matrix / cost Hessians exactly symmetric, as the reference's containers hold them
     return dict(dims=ANYMAL, sd=sd, S=S, K=K, table=table, ctrl=ctrl, lin=lin, con=con, sol=sol, dx0=dx0)
 
 
@@ -359,8 +360,17 @@ def main():
     steps_o = torch.empty((args.batch, 2), dtype=torch.float64).pin_memory()
     P = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
 
+    # the host adaptor's output format: packed upper triangles of the symmetric blocks (include/rbt_stage_layout.h), made
+    # once outside the timed region -- it is what the host side hands over, like the records themselves
+    wire_p = pin(dms.pack_wire(lin))
+    use_wire = not os.environ.get("RBT_E2E_DENSE_RECORDS")
+
     def e2e_step():
-        rc = lib.rbt_iteration_host(rr._h, P(lin_p), P(con_p), P(sol_p), P(dx0_p), P(sol_o), P(con_o), P(steps_o), sp)
+        if use_wire:
+            rc = lib.rbt_iteration_host_wire(rr._h, P(wire_p), P(lin_p), P(con_p), P(sol_p), P(dx0_p), P(sol_o), P(con_o),
+                                             P(steps_o), sp)
+        else:
+            rc = lib.rbt_iteration_host(rr._h, P(lin_p), P(con_p), P(sol_p), P(dx0_p), P(sol_o), P(con_o), P(steps_o), sp)
         assert rc == 0, rr._err()
 
     e2e_step()
@@ -378,7 +388,7 @@ def main():
         tt = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_ms = float(tt.item())
-    h2d, d2h = dms.iteration_host_bytes()  # what the call actually moves (padding / unused sections never cross PCIe)
+    h2d, d2h = dms.iteration_host_bytes(wire=use_wire)  # what the call actually moves (padding / unused sections never cross PCIe)
     used = dms.layout.s_xi + dms.layout.nsm
     assert np.array_equal(sol_o.numpy()[:, :, :used], sol_dev[:, :, :used]) and np.array_equal(steps_o.numpy(), steps_dev), \
         "e2e path disagrees with the device-resident path"
@@ -407,7 +417,9 @@ def main():
                              "unit": "OCP-iterations/s", "note": "backward + forward sweeps only (the parity-checked core, 8d)"},
             "e2e": {"value": world * args.batch * args.e2e_steps / (e2e_ms * 1e-3), "unit": "OCP-iterations/s",
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": args.e2e_steps,
-                    "api": "rbt_iteration_host (pinned host linearisation/PDIPM/solution in; solution, slack/dual, step sizes out)"},
+                    "api": ("rbt_iteration_host_wire (pinned host wire records: linearisation with packed symmetric blocks, PDIPM slack|dual|res, "
+                            "solution in; solution, slack|dual, step sizes out; 8-chunk upload/compute/download pipeline)") if use_wire
+                           else "rbt_iteration_host (dense linearisation records)"},
             "roofline": {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "traffic": (NCU_TRAFFIC_1024[dom] * args.batch / 1024) if dom in NCU_TRAFFIC_1024 else None,
                          "traffic_source": "ncu --set full capture of this command, committed under profiles/ (per launch)",

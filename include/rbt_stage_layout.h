@@ -148,6 +148,56 @@ static inline RBT_HD void rbt_make_stage_layout(const rbt_stage_dims* d, rbt_sta
   L->x_stride = rbt_up16(o);
 }
 
+
+/* ---------------- host wire format of the linearization record (the PCIe-facing form used by rbt_iteration_host_wire)
+ * The symmetric blocks M, Qff, Qxx, Quu travel as packed upper triangles (column-major packed, element (i,j), i <= j, at
+ * j(j+1)/2 + i -- BLAS "UPLO=U" packed storage), everything else as the dense sections of the record, and neither padding
+ * nor the switching-constraint section (sent separately, only for stages that carry one) is part of it.
+ * A host adaptor fills it straight from the reference's Eigen members (SplitKKTMatrix::Qxx etc. are symmetric by
+ * construction); the device expands it back into the rbt_stage_layout record. */
+typedef struct rbt_wire_seg { int lin_off, wire_off, n, sym; } rbt_wire_seg; /* sym: n x n packed ; else n doubles copied */
+#define RBT_WIRE_MAX_SEGS 8
+typedef struct rbt_wire_layout { int nseg, w_stride; rbt_wire_seg seg[RBT_WIRE_MAX_SEGS]; } rbt_wire_layout;
+
+static inline RBT_HD void rbt_make_wire_layout(const rbt_stage_layout* L, rbt_wire_layout* W) {
+  int o = 0, k = 0;
+  const int tail = L->l_dgdf + rbt_up2(15 * L->ncon) - L->l_ha;
+  const int offs[RBT_WIRE_MAX_SEGS] = {L->l_M, L->l_J, L->l_Qff, L->l_Qqf, L->l_Qxx, L->l_Quu, L->l_lx, L->l_ha};
+  const int ns[RBT_WIRE_MAX_SEGS] = {L->nv, L->l_Qff - L->l_J, L->nfm, L->l_Qxx - L->l_Qqf, L->nx, L->nu, L->l_Phix - L->l_lx, tail};
+  const int sy[RBT_WIRE_MAX_SEGS] = {1, 0, 1, 0, 1, 1, 0, 0};
+  for (k = 0; k < RBT_WIRE_MAX_SEGS; ++k) {
+    W->seg[k].lin_off = offs[k]; W->seg[k].wire_off = o; W->seg[k].n = ns[k]; W->seg[k].sym = sy[k];
+    o += rbt_up2(sy[k] ? ns[k] * (ns[k] + 1) / 2 : ns[k]);
+  }
+  W->nseg = RBT_WIRE_MAX_SEGS;
+  W->w_stride = rbt_up2(o);
+}
+
+/* one record: rbt_stage_layout linearization record -> wire record (reads the upper triangles) */
+static inline void rbt_pack_wire_record(const rbt_wire_layout* W, const double* lin, double* wire) {
+  int k, i, j;
+  for (k = 0; k < W->nseg; ++k) {
+    const rbt_wire_seg* g = &W->seg[k];
+    double* dst = wire + g->wire_off;
+    const double* src = lin + g->lin_off;
+    if (!g->sym) { for (i = 0; i < g->n; ++i) dst[i] = src[i]; continue; }
+    for (j = 0; j < g->n; ++j)
+      for (i = 0; i <= j; ++i) dst[j * (j + 1) / 2 + i] = src[i + j * g->n];
+  }
+}
+/* wire record -> linearization record (what the device kernel does; used by the CPU tests) */
+static inline void rbt_unpack_wire_record(const rbt_wire_layout* W, const double* wire, double* lin) {
+  int k, i, j;
+  for (k = 0; k < W->nseg; ++k) {
+    const rbt_wire_seg* g = &W->seg[k];
+    const double* src = wire + g->wire_off;
+    double* dst = lin + g->lin_off;
+    if (!g->sym) { for (i = 0; i < g->n; ++i) dst[i] = src[i]; continue; }
+    for (j = 0; j < g->n; ++j)
+      for (i = 0; i < g->n; ++i) dst[i + j * g->n] = (i <= j) ? src[j * (j + 1) / 2 + i] : src[i * (i + 1) / 2 + j];
+  }
+}
+
 #define RBT_STAGE_LAYOUT_FIELDS(X) \
   X(nv) X(nu) X(nx) X(np) X(nfm) X(nvf) X(nsm) X(ncon) X(nbox) X(nc) X(ncp) X(nq) \
   X(l_M) X(l_J) X(l_D) X(l_IDC) X(l_Qaa) X(l_Qff) X(l_Qqf) X(l_Qxx) X(l_Quu) X(l_lx) X(l_la) X(l_lf) X(l_lu) X(l_Fx) \

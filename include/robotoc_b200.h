@@ -140,7 +140,17 @@ int rbt_iteration_host(rbt_handle* h, const double* lin_host, const double* con_
  * the reference keeps inside ConstraintComponentData; con_out's remaining fields are left untouched).  The call is
  * pipelined over chunks of the batch (upload of chunk c+1, kernels of chunk c, download of chunk c-1 overlap on three
  * streams); `stream` is ordered after the last download, so rbt_sync(h, stream) covers everything. */
-int rbt_iteration_host_bytes(rbt_handle* h, long long* h2d_bytes, long long* d2h_bytes);
+int rbt_iteration_host_bytes(rbt_handle* h, int wire, long long* h2d_bytes, long long* d2h_bytes);
+/* The same call with the linearization records in the host wire format of rbt_stage_layout.h (packed upper triangles of the
+ * symmetric blocks M, Qff, Qxx, Quu; no padding): 22 % fewer bytes over PCIe.  `lin_host_switching` = classic records, of
+ * which only the switching-constraint sections of the stages that carry one are read (NULL if the schedule has none).
+ * rbt_pack_wire is the host-side packing helper (what an adaptor does while copying out of SplitKKTMatrix::Qxx etc.);
+ * rbt_wire_doubles gives the size of one wire record. */
+int rbt_iteration_host_wire(rbt_handle* h, const double* wire_host, const double* lin_host_switching, const double* con_host,
+                            const double* sol_host, const double* dx0_host, double* sol_out, double* con_out,
+                            double* steps_out, void* stream);
+int rbt_wire_doubles(const rbt_stage_dims* sdims);
+int rbt_pack_wire(const rbt_stage_dims* sdims, const double* lin_host, double* wire_host, long long n_records);
 
 int rbt_sync(rbt_handle* h, void* stream);
 const char* rbt_last_error(rbt_handle* h);

@@ -67,6 +67,8 @@ struct rbt_handle {
   // batch window [cb0, cb0 + cnb) the launch helpers work on (cnb == 0: the whole batch); used by rbt_iteration_host to
   // pipeline uploads, kernels and downloads over chunks of the batch
   int cb0 = 0, cnb = 0;
+  double* d_wire = nullptr;  // packed host wire records (rbt_iteration_host_wire), allocated on first use
+  rbt_wire_layout W;
   cudaEvent_t ev_condense_mid = nullptr;  // caller-owned event recorded between the two kernels of rbt_condense (timing)
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
   std::vector<cudaEvent_t> ev;
@@ -174,6 +176,7 @@ static double** buf_slot(rbt_handle* h, int which);
 
 int rbt_destroy(rbt_handle* h) {
   if (h) {
+    cudaFree(h->d_wire);
     if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
     if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
@@ -295,6 +298,7 @@ int rbt_bind_buffer(rbt_handle* h, int which, double* dev) {
 
 static long long stage_xfer(rbt_handle* h, int which, bool up, const double* host_c, double* host_m, int b0, int nb,
                             cudaStream_t st, bool do_copy, int* rc_out);
+enum { RBT_XFER_WIRE = 100, RBT_XFER_SWITCHING = 101 };
 
 // KKT upload plan: one strided copy of the core section [Fxx|Fvu|Fx|lx|lu|Qxx|Qxu|Quu] of every record (record padding and
 // unused switching/STO sections never cross PCIe), plus one strided copy per stage that carries extras.
@@ -668,7 +672,14 @@ static long long stage_xfer(rbt_handle* h, int which, bool up, const double* hos
                        : cudaMemcpy2DAsync(hm + off, pitch, dev + off, pitch, width * 8, nrows, cudaMemcpyDeviceToHost, st);
     if (e != cudaSuccess) *rc_out = RBT_ERR_CUDA;
   };
-  if (which == RBT_BUF_LIN) {
+  if (which == RBT_XFER_WIRE) {  // packed wire records: contiguous
+    copy2d(h->d_wire, host_c, host_m, go * h->W.w_stride, h->W.w_stride, h->W.w_stride, 1, rows);
+  } else if (which == RBT_XFER_SWITCHING) {  // only the switching-constraint sections of the classic record
+    const size_t base = go * S.l_stride;
+    for (int i = 0; i < h->n_grid; ++i)
+      if (h->ctrl[i].ns > 0 && h->ctrl[i].type != RBT_IMPACT)
+        copy2d(h->d_lin, host_c, host_m, base + size_t(i) * S.l_stride + S.l_Phix, S.l_stride, S.l_ha - S.l_Phix, h->n_grid, nb);
+  } else if (which == RBT_BUF_LIN) {
     const size_t base = go * S.l_stride;
     const size_t tail = size_t(S.l_dgdf) + ((15 * S.ncon + 1) & ~1) - S.l_ha;
     copy2d(h->d_lin, host_c, host_m, base, S.l_stride, S.l_Phix, 1, rows);            // M .. se3
@@ -688,21 +699,39 @@ static long long stage_xfer(rbt_handle* h, int which, bool up, const double* hos
   return bytes;
 }
 
-int rbt_iteration_host_bytes(rbt_handle* h, long long* h2d, long long* d2h) {
+int rbt_iteration_host_bytes(rbt_handle* h, int wire, long long* h2d, long long* d2h) {
   if (!h || !h->stage_ready || h->n_grid == 0) return RBT_ERR_STATE;
   int rc = RBT_OK;
   long long up = 0, down = 0;
-  for (int w : {RBT_BUF_LIN, RBT_BUF_CON, RBT_BUF_SOL, RBT_BUF_DX0}) up += stage_xfer(h, w, true, nullptr, nullptr, 0, h->batch, nullptr, false, &rc);
+  rbt_make_wire_layout(&h->S, &h->W);
+  if (wire) {
+    up += stage_xfer(h, RBT_XFER_WIRE, true, nullptr, nullptr, 0, h->batch, nullptr, false, &rc);
+    up += stage_xfer(h, RBT_XFER_SWITCHING, true, nullptr, nullptr, 0, h->batch, nullptr, false, &rc);
+  } else {
+    up += stage_xfer(h, RBT_BUF_LIN, true, nullptr, nullptr, 0, h->batch, nullptr, false, &rc);
+  }
+  for (int w : {RBT_BUF_CON, RBT_BUF_SOL, RBT_BUF_DX0}) up += stage_xfer(h, w, true, nullptr, nullptr, 0, h->batch, nullptr, false, &rc);
   for (int w : {RBT_BUF_SOL, RBT_BUF_CON, RBT_BUF_STEPS}) down += stage_xfer(h, w, false, nullptr, nullptr, 0, h->batch, nullptr, false, &rc);
   if (h2d) *h2d = up;
   if (d2h) *d2h = down;
   return RBT_OK;
 }
 
-int rbt_iteration_host(rbt_handle* h, const double* lin_host, const double* con_host, const double* sol_host,
-                       const double* dx0_host, double* sol_out, double* con_out, double* steps_out, void* stream) {
-  if (!h || !lin_host || !con_host || !sol_host || !dx0_host) return RBT_ERR_ARG;
+static int iteration_host_impl(rbt_handle* h, const double* wire_host, const double* lin_host, const double* con_host,
+                               const double* sol_host, const double* dx0_host, double* sol_out, double* con_out,
+                               double* steps_out, void* stream) {
+  if (!h || (!lin_host && !wire_host) || !con_host || !sol_host || !dx0_host) return RBT_ERR_ARG;
   RBT_STAGE_CHECK(h, "rbt_iteration_host");
+  if (wire_host) {
+    rbt_make_wire_layout(&h->S, &h->W);
+    bool sw = false;
+    for (int i = 0; i < h->n_grid; ++i) sw = sw || (h->ctrl[i].ns > 0 && h->ctrl[i].type != RBT_IMPACT);
+    if (sw && !lin_host) {
+      h->err = "[rbt_iteration_host_wire] invalid argument: the schedule has switching-constraint stages, their sections come from lin_host_switching";
+      return RBT_ERR_ARG;
+    }
+    if (!h->d_wire) RBT_CUDA(h, cudaMalloc(&h->d_wire, size_t(h->batch) * h->n_grid_max * h->W.w_stride * 8));
+  }
   cudaStream_t st = (cudaStream_t)stream;
   // chunks of the batch: the upload of chunk c+1, the kernels of chunk c and the download of chunk c-1 overlap
   int n_chunks = h->batch >= 512 ? 8 : (h->batch >= 128 ? 4 : 1);
@@ -724,7 +753,12 @@ int rbt_iteration_host(rbt_handle* h, const double* lin_host, const double* con_
   for (int c = 0; c < n_chunks && rc == RBT_OK; ++c) {
     const int b0 = int((long long)h->batch * c / n_chunks), b1 = int((long long)h->batch * (c + 1) / n_chunks), nb = b1 - b0;
     if (nb <= 0) continue;
-    stage_xfer(h, RBT_BUF_LIN, true, lin_host, nullptr, b0, nb, h->s_h2d, true, &rc);
+    if (wire_host) {
+      stage_xfer(h, RBT_XFER_WIRE, true, wire_host, nullptr, b0, nb, h->s_h2d, true, &rc);
+      if (lin_host) stage_xfer(h, RBT_XFER_SWITCHING, true, lin_host, nullptr, b0, nb, h->s_h2d, true, &rc);
+    } else {
+      stage_xfer(h, RBT_BUF_LIN, true, lin_host, nullptr, b0, nb, h->s_h2d, true, &rc);
+    }
     stage_xfer(h, RBT_BUF_CON, true, con_host, nullptr, b0, nb, h->s_h2d, true, &rc);
     stage_xfer(h, RBT_BUF_SOL, true, sol_host, nullptr, b0, nb, h->s_h2d, true, &rc);
     stage_xfer(h, RBT_BUF_DX0, true, dx0_host, nullptr, b0, nb, h->s_h2d, true, &rc);
@@ -733,6 +767,15 @@ int rbt_iteration_host(rbt_handle* h, const double* lin_host, const double* con_
     RBT_CUDA(h, cudaStreamWaitEvent(st, h->ev[2 * c], 0));
     h->cb0 = b0;
     h->cnb = nb;
+    if (wire_host) {  // expand the packed records of this chunk into the linearization records
+      rbt::WireParams wp;
+      wp.W = h->W;
+      wp.l_stride = h->S.l_stride;
+      wp.wire = h->d_wire + size_t(b0) * h->n_grid * h->W.w_stride;
+      wp.lin = h->d_lin + size_t(b0) * h->n_grid * h->S.l_stride;
+      rbt::unpack_wire_kernel<<<nb * h->n_grid, 128, 0, st>>>(wp);
+      h->launches += 1;
+    }
     if (!(rc = rbt_condense(h, stream)) && !(rc = rbt_riccati_backward(h, 0, stream)) && !(rc = rbt_riccati_forward(h, stream)) &&
         !(rc = rbt_expand_and_step_sizes(h, stream)))
       rc = rbt_update(h, stream);
@@ -753,6 +796,38 @@ int rbt_iteration_host(rbt_handle* h, const double* lin_host, const double* con_
   }
   RBT_CUDA(h, cudaEventRecord(ev_exit, h->s_d2h));       // `stream` (what the caller synchronizes) covers the downloads too
   RBT_CUDA(h, cudaStreamWaitEvent(st, ev_exit, 0));
+  return RBT_OK;
+}
+
+int rbt_iteration_host(rbt_handle* h, const double* lin_host, const double* con_host, const double* sol_host,
+                       const double* dx0_host, double* sol_out, double* con_out, double* steps_out, void* stream) {
+  if (!lin_host) return RBT_ERR_ARG;
+  return iteration_host_impl(h, nullptr, lin_host, con_host, sol_host, dx0_host, sol_out, con_out, steps_out, stream);
+}
+
+int rbt_iteration_host_wire(rbt_handle* h, const double* wire_host, const double* lin_host_switching, const double* con_host,
+                            const double* sol_host, const double* dx0_host, double* sol_out, double* con_out,
+                            double* steps_out, void* stream) {
+  if (!wire_host) return RBT_ERR_ARG;
+  return iteration_host_impl(h, wire_host, lin_host_switching, con_host, sol_host, dx0_host, sol_out, con_out, steps_out, stream);
+}
+
+int rbt_wire_doubles(const rbt_stage_dims* sdims) {
+  if (!sdims) return -1;
+  rbt_stage_layout S;
+  rbt_wire_layout W;
+  rbt_make_stage_layout(sdims, &S);
+  rbt_make_wire_layout(&S, &W);
+  return W.w_stride;
+}
+
+int rbt_pack_wire(const rbt_stage_dims* sdims, const double* lin_host, double* wire_host, long long n_records) {
+  if (!sdims || !lin_host || !wire_host || n_records < 0) return RBT_ERR_ARG;
+  rbt_stage_layout S;
+  rbt_wire_layout W;
+  rbt_make_stage_layout(sdims, &S);
+  rbt_make_wire_layout(&S, &W);
+  for (long long r = 0; r < n_records; ++r) rbt_pack_wire_record(&W, lin_host + r * S.l_stride, wire_host + r * W.w_stride);
   return RBT_OK;
 }
 

@@ -785,6 +785,35 @@ __global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS, 5) condense_ke
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// Host wire records -> linearization records (rbt_stage_layout.h: packed upper triangles of M, Qff, Qxx, Quu).  HBM
+// streaming: one CTA per stage, coalesced reads of the 26 KB wire record, coalesced writes of the dense sections; the
+// symmetric blocks are gathered from the packed triangle.  Only used by the PCIe-facing rbt_iteration_host_wire path.
+struct WireParams {
+  rbt_wire_layout W;
+  int l_stride;
+  const double* wire;
+  double* lin;
+};
+
+__global__ void __launch_bounds__(128) unpack_wire_kernel(const WireParams p) {
+  const double* wire = p.wire + size_t(blockIdx.x) * p.W.w_stride;
+  double* lin = p.lin + size_t(blockIdx.x) * p.l_stride;
+  for (int k = 0; k < p.W.nseg; ++k) {
+    const rbt_wire_seg g = p.W.seg[k];
+    const double* src = wire + g.wire_off;
+    double* dst = lin + g.lin_off;
+    if (!g.sym) {
+      for (int e = threadIdx.x; e < g.n; e += 128) dst[e] = src[e];
+    } else {
+      for (int e = threadIdx.x; e < g.n * g.n; e += 128) {
+        const int i = e % g.n, j = e / g.n;
+        dst[e] = (i <= j) ? src[j * (j + 1) / 2 + i] : src[i * (i + 1) / 2 + j];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double warp_min(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));

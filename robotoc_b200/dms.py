@@ -85,11 +85,30 @@ class DirectMultipleShooting:
         self.rr.synchronize(stream)
         return sol_out, con_out, steps
 
-    def iteration_host_bytes(self):
+    def iteration_host_bytes(self, wire=False):
         h2d, d2h = ctypes.c_longlong(), ctypes.c_longlong()
-        _check(self._lib.rbt_iteration_host_bytes(self._h, ctypes.byref(h2d), ctypes.byref(d2h)), self.rr._err,
+        _check(self._lib.rbt_iteration_host_bytes(self._h, int(wire), ctypes.byref(h2d), ctypes.byref(d2h)), self.rr._err,
                "DirectMultipleShooting")
         return h2d.value, d2h.value
+
+    def pack_wire(self, lin):
+        """Linearization records -> host wire records (packed upper triangles of M, Qff, Qxx, Quu; include/rbt_stage_layout.h)."""
+        csd = self.sdims.c()
+        w = int(self._lib.rbt_wire_doubles(ctypes.byref(csd)))
+        out = np.zeros(lin.shape[:-1] + (w,))
+        _check(self._lib.rbt_pack_wire(ctypes.byref(csd), _vp(lin), _vp(out), int(np.prod(lin.shape[:-1]))), self.rr._err,
+               "DirectMultipleShooting")
+        return out
+
+    def iteration_host_wire(self, wire, lin_switching, con, sol, dx0, stream=None):
+        """iteration_host with the linearisations in the wire format (22 % fewer PCIe bytes)."""
+        sol_out, con_out = sol.copy(), con.copy()
+        steps = np.empty((self.rr.batch, 2))
+        _check(self._lib.rbt_iteration_host_wire(self._h, _vp(wire), _vp(lin_switching), _vp(con), _vp(sol), _vp(dx0),
+                                                 _vp(sol_out), _vp(con_out), _vp(steps), stream), self.rr._err,
+               "DirectMultipleShooting")
+        self.rr.synchronize(stream)
+        return sol_out, con_out, steps
 
     # -- data access ---------------------------------------------------------------------------------------
     def getKKT(self, stream=None):

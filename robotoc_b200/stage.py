@@ -173,3 +173,17 @@ def make_stage_inputs(sd: StageDims, S: StageLayout, ctrl, batch: int, seed: int
             con[:, i, S.c_res:S.c_res + nc] = 0.1 * _u(rng, batch, nc)
     dx0 = 0.1 * _u(rng, batch, nx)
     return np.ascontiguousarray(lin), np.ascontiguousarray(con), np.ascontiguousarray(sol), np.ascontiguousarray(dx0)
+
+
+def symmetrize_lin(S: StageLayout, lin):
+    """Makes the symmetric blocks of linearization records exactly symmetric (upper triangle authoritative), which is what
+    the reference's containers hold (cost Hessians, joint-space inertia) and what the host wire format assumes."""
+    out = lin.copy()
+    flat = out.reshape(-1, out.shape[-1])
+    for off, n in ((S.l_M, S.nv), (S.l_Qff, S.nfm), (S.l_Qxx, S.nx), (S.l_Quu, S.nu)):
+        blk = flat[:, off:off + n * n].reshape(-1, n, n)  # [rec, col, row] (column-major)
+        a = np.transpose(blk, (0, 2, 1))                  # a[rec, row, col]
+        up = np.triu(a)
+        sym = up + np.transpose(np.triu(a, 1), (0, 2, 1))
+        flat[:, off:off + n * n] = np.transpose(sym, (0, 2, 1)).reshape(-1, n * n)
+    return out

@@ -11,7 +11,7 @@ import oracle_lib
 from helpers import jump_sto_schedule, rel_err, small_event_schedule, trot_schedule
 from robotoc_b200 import ANYMAL, DirectMultipleShooting, Layout, RiccatiRecursion, StageDims, StageLayout, anymal_constraint_table
 from robotoc_b200.schedule import IMPACT, TERMINAL
-from robotoc_b200.stage import make_stage_inputs
+from robotoc_b200.stage import make_stage_inputs, symmetrize_lin
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-8
@@ -48,14 +48,14 @@ def _cmp(name, got, ref, tol=TOL):
     assert e < tol, f"{name}: rel err {e:.3e}"
 
 
-def _run(ctrl, batch, seed):
+def _run(ctrl, batch, seed, reserve=0):
     lib = oracle_lib.load()
     table = anymal_constraint_table()
     sd = StageDims(ANYMAL, nf_max=12, n_contacts=table.n_contacts, n_box=table.n_box)
     S, K = StageLayout(sd), Layout(ANYMAL)
     lin, con, sol, dx0 = make_stage_inputs(sd, S, ctrl, batch, seed)
     ref = _oracle_iteration(lib, sd, S, K, table, ctrl, lin, con, sol, dx0)
-    rr = RiccatiRecursion(ANYMAL, len(ctrl), batch)
+    rr = RiccatiRecursion(ANYMAL, len(ctrl) + reserve, batch)  # reserve: the reference sizes for N + 1 + reserved events
     rr.setTimeDiscretization(ctrl)
     dms = DirectMultipleShooting(rr, sd, table)
     dms.condense(lin, con)
@@ -115,6 +115,15 @@ def _run(ctrl, batch, seed):
     del os.environ["RBT_E2E_CHUNKS"]
     h2d, d2h = dms.iteration_host_bytes()
     assert 0 < d2h < h2d < lin.nbytes + con.nbytes + sol.nbytes + dx0.nbytes
+    # host wire format (packed symmetric blocks): same bits as the classic records once those are exactly symmetric
+    lin_s = symmetrize_lin(S, lin)
+    sol3, con3, steps3 = dms.iteration_host(lin_s, con, sol, dx0)
+    sol4, con4, steps4 = dms.iteration_host_wire(dms.pack_wire(lin_s), lin_s, con, sol, dx0)
+    np.testing.assert_array_equal(sol4, sol3)
+    np.testing.assert_array_equal(con4, con3)
+    np.testing.assert_array_equal(steps4, steps3)
+    assert rel_err(sol3[:, :, :used], sol_g[:, :, :used]) < 1e-9  # symmetrising moves the inputs by rounding only
+    assert dms.iteration_host_bytes(wire=True)[0] < 0.82 * h2d
     rr.close()
 
 
@@ -138,3 +147,10 @@ def test_stage_layer_jump_sto_n80():
     """BASELINE.json configs[3] schedule (ANYmal jumping, STO, N=80) through the full iteration."""
     td, ev, ctrl = jump_sto_schedule(80)
     _run(ctrl, batch=2, seed=24)
+
+
+def test_stage_layer_single_ocp_with_reserved_grid_points():
+    """batch = 1 (the reference's own use) on a handle sized for more grid points than the schedule has
+    (riccati_recursion.cpp:12-13: N + 1 + reserved_num_discrete_events)."""
+    td, ev, ctrl = small_event_schedule(False)
+    _run(ctrl, batch=1, seed=25, reserve=4)

@@ -110,3 +110,48 @@ def test_shard_range_partitions(batch, world):
     assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         shard_range(batch, world, world)
+
+
+def test_wire_format_pack_is_documented_packed_upper_storage():
+    """rbt_pack_wire (host helper of the C ABI) against an independent numpy restatement of the format in
+    include/rbt_stage_layout.h: dense sections copied, M / Qff / Qxx / Quu as column-major packed upper triangles."""
+    import ctypes
+    from robotoc_b200 import ANYMAL, StageDims, StageLayout, anymal_constraint_table
+    from robotoc_b200._lib import lib
+    from robotoc_b200.stage import make_stage_inputs, symmetrize_lin
+    from helpers import small_event_schedule
+    L = lib()
+    tab = anymal_constraint_table()
+    sd = StageDims(ANYMAL, nf_max=12, n_contacts=tab.n_contacts, n_box=tab.n_box)
+    S = StageLayout(sd)
+    td, ev, ctrl = small_event_schedule(False)
+    lin, con, sol, dx0 = make_stage_inputs(sd, S, ctrl, 2, seed=4)
+    lin = symmetrize_lin(S, lin)
+    csd = sd.c()
+    w = L.rbt_wire_doubles(ctypes.byref(csd))
+    assert w == 3320
+    wire = np.zeros(lin.shape[:-1] + (w,))
+    assert L.rbt_pack_wire(ctypes.byref(csd), lin.ctypes.data_as(ctypes.c_void_p), wire.ctypes.data_as(ctypes.c_void_p),
+                           lin.shape[0] * lin.shape[1]) == 0
+    tail = S.l_dgdf + 60 - S.l_ha
+    segs = [(S.l_M, 18, True), (S.l_J, S.l_Qff - S.l_J, False), (S.l_Qff, 12, True), (S.l_Qqf, S.l_Qxx - S.l_Qqf, False),
+            (S.l_Qxx, 36, True), (S.l_Quu, 12, True), (S.l_lx, S.l_Phix - S.l_lx, False), (S.l_ha, tail, False)]
+    rec, wrec = lin[1, 3], wire[1, 3]
+    back = np.zeros_like(rec)
+    o = 0
+    for off, n, sym in segs:
+        if not sym:
+            back[off:off + n] = wrec[o:o + n]
+            o += n + (n & 1)
+        else:
+            a = np.zeros((n, n))
+            for j in range(n):
+                for i in range(j + 1):
+                    a[i, j] = a[j, i] = wrec[o + j * (j + 1) // 2 + i]
+            back[off:off + n * n] = a.T.reshape(-1)
+            o += n * (n + 1) // 2 + ((n * (n + 1) // 2) & 1)
+    assert o == w
+    keep = np.ones(S.l_stride, bool)
+    keep[S.l_Phix:S.l_ha] = False            # the switching section is not part of the wire record
+    keep[S.l_dgdf + 60:] = False             # nor is the record padding
+    np.testing.assert_array_equal(back[keep], rec[keep])
