@@ -528,11 +528,11 @@ int rbt_stage_setup(rbt_handle* h, const rbt_stage_dims* sd, const rbt_constrain
     using C = rbt::CondCfg<18, 12, 12>;
     const rbt_stage_layout& S = h->S;
     const int gsz = (S.l_dgdf - S.l_dgdq) + ((15 * S.ncon + 1) & ~1);
-    const bool ok = S.l_Phix - S.l_D == C::IN1 && S.l_IDC - S.l_D == C::i_IDC && S.l_Qaa - S.l_D == C::i_Qaa &&
-                    S.l_Qff - S.l_D == C::i_Qff && S.l_Qqf - S.l_D == C::i_Qqf && S.l_Qxx - S.l_D == C::i_Qxx &&
-                    S.l_Quu - S.l_D == C::i_Quu && S.l_lx - S.l_D == C::i_lx && S.l_la - S.l_D == C::i_la &&
-                    S.l_lf - S.l_D == C::i_lf && S.l_lu - S.l_D == C::i_lu && S.l_Fx - S.l_D == C::i_Fx &&
-                    S.l_lup - S.l_D == C::i_lup && S.l_se3 - S.l_D == C::i_se3 && S.l_dgdq - S.l_ha == C::IN2 &&
+    const int q0 = S.l_Quu - C::IN1A;  // record offset that maps onto the second in-place mirror
+    const bool ok = S.l_Qxx - S.l_D == C::IN1A && S.l_Phix - S.l_Quu == C::IN1B && S.l_IDC - S.l_D == C::i_IDC &&
+                    S.l_Qaa - S.l_D == C::i_Qaa && S.l_Qff - S.l_D == C::i_Qff && S.l_Qqf - S.l_D == C::i_Qqf &&
+                    S.l_lx - q0 == C::i_lx && S.l_la - q0 == C::i_la && S.l_lf - q0 == C::i_lf && S.l_lu - q0 == C::i_lu &&
+                    S.l_Fx - q0 == C::i_Fx && S.l_lup - q0 == C::i_lup && S.l_se3 - q0 == C::i_se3 && S.l_dgdq - S.l_ha == C::IN2 &&
                     S.l_hf - S.l_ha == C::j_hf && S.l_hx - S.l_ha == C::j_hx && S.l_hu - S.l_ha == C::j_hu &&
                     S.l_fx - S.l_ha == C::j_fx && S.l_sc - S.l_ha == C::j_sc &&
                     5 * S.ncp + gsz <= C::NVF * C::NX &&  // PDIPM staging fits in the R buffer

@@ -281,10 +281,12 @@ __global__ void __launch_bounds__(32 * MjtjCfg<NV, NFM>::WARPS, 10) mjtjinv_kern
 // ------------------------------------------------------------------------------------------------------------------
 // K2: everything else of "Forms linear system", with all dense products on the fp64 tensor pipe (DMMA m8n8k4).
 //
-// Shared-memory plan (43 KB -> 5 CTAs per SM).  The part of the linearization record K2 needs is contiguous
-// ([l_D, l_Phix) and [l_ha, l_dgdq)), so it lands IN PLACE with two cp.async.bulk copies and is then used (and
-// modified: PDIPM terms) where it lies; Z (from K1) is a third copy; the PDIPM inputs (slack|dual|res, dg/dq|dg/df)
-// land in the buffer that later holds R.  Only the contact rows of Qafqv / Qafu are materialised (in the dead dIDCdqv
+// Shared-memory plan (35.8 KB -> 6 CTAs per SM).  The parts of the linearization record K2 needs are contiguous
+// ([l_D, l_Qxx), [l_Quu, l_Phix) and [l_ha, l_dgdq)), so they land IN PLACE with three cp.async.bulk copies and are then
+// used (and modified: PDIPM terms) where they lie; Z (from K1) is a fourth copy; the PDIPM inputs (slack|dual|res,
+// dg/dq|dg/df) land in the buffer that later holds R.  The cost Hessian Qxx is NOT staged: it is only the accumulator
+// seed of the Qxx product, so it is read from global memory (L2: prefetched at kernel start) straight into the DMMA
+// accumulator fragments, plus the PDIPM increments that are kept in shared memory (Qqq block + Qvv diagonal).  Only the contact rows of Qafqv / Qafu are materialised (in the dead dIDCdqv
 // buffer): their acceleration rows are diag(Qaa) times rows of R / Z and are formed on the fly in the fragment loads.
 template <int NV, int NU, int NFM>
 struct CondCfg {
@@ -295,9 +297,11 @@ struct CondCfg {
   static constexpr int up2(int x) { return (x + 1) & ~1; }
   // mirror of the record from l_D to l_Phix (same relative offsets as rbt_make_stage_layout)
   static constexpr int i_D = 0, i_IDC = i_D + up2(NVF * NX), i_Qaa = i_IDC + up2(NVF), i_Qff = i_Qaa + up2(NV),
-                       i_Qqf = i_Qff + up2(NFM * NFM), i_Qxx = i_Qqf + up2(NV * NFM), i_Quu = i_Qxx + up2(NX * NX),
-                       i_lx = i_Quu + up2(NU * NU), i_la = i_lx + up2(NX), i_lf = i_la + up2(NV), i_lu = i_lf + up2(NFM),
-                       i_Fx = i_lu + up2(NU), i_lup = i_Fx + up2(NX), i_se3 = i_lup + 6, IN1 = i_se3 + 108;
+                       i_Qqf = i_Qff + up2(NFM * NFM), IN1A = i_Qqf + up2(NV * NFM);   // [l_D, l_Qxx)
+  // mirror of the record from l_Quu to l_Phix
+  static constexpr int i_Quu = IN1A, i_lx = i_Quu + up2(NU * NU), i_la = i_lx + up2(NX), i_lf = i_la + up2(NV),
+                       i_lu = i_lf + up2(NFM), i_Fx = i_lu + up2(NU), i_lup = i_Fx + up2(NX), i_se3 = i_lup + 6,
+                       IN1 = i_se3 + 108, IN1B = IN1 - IN1A;
   // mirror of the record from l_ha to l_dgdq
   static constexpr int j_ha = 0, j_hf = j_ha + up2(NV), j_hx = j_hf + up2(NFM), j_hu = j_hx + up2(NX), j_fx = j_hu + up2(NU),
                        j_sc = j_fx + up2(NX), IN2 = j_sc + 4;
@@ -306,7 +310,8 @@ struct CondCfg {
   static constexpr int o_R = o_Z + NVF * NVF;      // R (ld NVF); before R exists: PDIPM staging
   static constexpr int o_in2 = o_R + NVF * NX;
   static constexpr int o_vec = o_in2 + IN2;
-  static constexpr int v_r = 0, v_laf = NVF, v_haf = 2 * NVF, v_Fi = 3 * NVF, v_FiS = v_Fi + 36, v_end = v_FiS + 36;
+  static constexpr int v_r = 0, v_laf = NVF, v_haf = 2 * NVF, v_Fi = 3 * NVF, v_FiS = v_Fi + 36, v_dQq = v_FiS + 36,
+                       v_dQv = v_dQq + NV * NV, v_end = v_dQv + up2(NV);  // dQq / dQv: PDIPM increments of Qqq, diag(Qvv)
   static constexpr int o_bar = (o_vec + v_end + 1) & ~1;
   static constexpr int SMEM_DOUBLES = o_bar + 2;
   static constexpr size_t SMEM_BYTES = size_t(SMEM_DOUBLES) * 8;
@@ -316,7 +321,7 @@ struct CondCfg {
 };
 
 template <int NV, int NU, int NFM>
-__global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS, 5) condense_kernel(const StageParams p) {
+__global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS, 6) condense_kernel(const StageParams p) {
   using C = CondCfg<NV, NU, NFM>;
   constexpr int NX = C::NX, NVF = C::NVF, NTHR = C::NTHREADS, TX = C::TX, TF = C::TF, TV = C::TV, TU = C::TU, TM = C::TM;
   extern __shared__ __align__(16) double smem[];
@@ -350,7 +355,7 @@ __global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS, 5) condense_ke
   double* vQaa = in1 + C::i_Qaa;
   double* sQff = in1 + C::i_Qff;
   double* sQqf = in1 + C::i_Qqf;
-  double* gQxx = in1 + C::i_Qxx;    // cost Hessian + PDIPM terms (working copy)
+  const double* gQxx = lin + S.l_Qxx;  // cost Hessian: global memory (accumulator seed only)
   double* gQuu = in1 + C::i_Quu;
   double* vlx = in1 + C::i_lx;
   double* vla = in1 + C::i_la;
@@ -374,6 +379,8 @@ __global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS, 5) condense_ke
   double* vhaf = vec + C::v_haf;
   double* Fi = vec + C::v_Fi;
   double* FiS = vec + C::v_FiS;
+  double* dQq = vec + C::v_dQq;     // PDIPM increment of Qqq (NV x NV)
+  double* dQv = vec + C::v_dQv;     // PDIPM increment of diag(Qvv)
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + C::o_bar);
   // PDIPM staging inside the (not yet written) R buffer
   const int ncp = S.ncp, nbox = p.tab.n_box, ncon = p.tab.n_contacts, nc = S.nc;
@@ -390,7 +397,9 @@ __global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS, 5) condense_ke
     uint32_t bytes = uint32_t(C::IN1 + NVF * NVF + C::IN2) * 8u;
     if (!impact) bytes += uint32_t(3 * ncp + gsz) * 8u;
     mbar_expect_tx(bar, bytes);
-    tma_load_1d(in1, lin + S.l_D, uint32_t(C::IN1) * 8u, bar);
+    l2_prefetch_bulk(lin + S.l_Qxx, uint32_t(NX * NX) * 8u);
+    tma_load_1d(in1, lin + S.l_D, uint32_t(C::IN1A) * 8u, bar);
+    tma_load_1d(in1 + C::IN1A, lin + S.l_Quu, uint32_t(C::IN1B) * 8u, bar);
     tma_load_1d(sZ, ex + S.e_Z, uint32_t(NVF * NVF) * 8u, bar);
     tma_load_1d(smem + C::o_in2, lin + S.l_ha, uint32_t(C::IN2) * 8u, bar);
     if (!impact) {
@@ -415,6 +424,7 @@ __global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS, 5) condense_ke
     vhaf[tid] = impact ? 0.0 : (tid < NV ? vha[tid] : (tid - NV < nf ? -vhf[tid - NV] : 0.0));
     if (tid >= NV && tid - NV >= nf) vlf[tid - NV] = 0.0;
   }
+  for (int e = tid; e < NV * NV + NV; e += NTHR) dQq[e] = 0.0;  // (dQv follows dQq)
   if (!impact) {
     const double mu = p.tab.barrier;
     for (int r = tid; r < nc; r += NTHR) {  // pdipm.hxx:27-100
@@ -459,7 +469,7 @@ __global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS, 5) condense_ke
       double acc = 0.0;
       for (int ci = 0; ci < ncon; ++ci)
         for (int r = 0; r < 5; ++r) acc = fma(sDq[ci * 5 * NV + r + ii * 5] * cW[nbox + 5 * ci + r], sDq[ci * 5 * NV + r + j * 5], acc);
-      gQxx[ii + j * NX] += acc;
+      dQq[ii + j * NV] = acc;
     }
     // Qqf[:, stack(c)] += dg_dq^T diag(w) dg_df ;  Qff[stack(c), stack(c)] += dg_df^T diag(w) dg_df     :219-222
     for (int e = tid; e < NV * 3 * ncon + 9 * ncon; e += NTHR) {
@@ -492,12 +502,12 @@ __global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS, 5) condense_ke
       for (int ci = 0; ci < ncon; ++ci)
         for (int r = 0; r < 5; ++r) acc = fma(sDq[ci * 5 * NV + r + lane * 5], cC[nbox + 5 * ci + r], acc);  // lq += dg_dq^T cond  :207
       vlx[lane] += acc;
-      gQxx[lane * (NX + 1)] += w;
+      dQq[lane * (NV + 1)] += w;
     } else if (warp == 1 && lane < NV) {
       double w, gs;
       gather(NV + lane, w, gs);
       vlx[NV + lane] += gs;
-      gQxx[(NV + lane) * (NX + 1)] += w;
+      dQv[lane] = w;
     } else if (warp == 2 && lane < NV) {
       double w, gs;
       gather(2 * NV + lane, w, gs);
@@ -602,8 +612,15 @@ __global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS, 5) condense_ke
 #pragma unroll
     for (int n = 0; n < TX; ++n) {
       const int j0 = tile_off(n, NX);
-      acc[n][0] = gQxx[(i0 + g) + (j0 + 2 * t) * NX];
-      acc[n][1] = gQxx[(i0 + g) + (j0 + 2 * t + 1) * NX];
+      const int r = i0 + g;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int cidx = j0 + 2 * t + q;
+        double v = __ldg(gQxx + r + cidx * NX);
+        if (r < NV && cidx < NV) v += dQq[r + cidx * NV];
+        else if (r == cidx) v += dQv[r - NV];
+        acc[n][q] = v;
+      }
     }
     warp_mma_band<NV, TX, NX>(
         acc, i0, [&](int ii, int l) { return -sR[l + ii * NVF]; }, [&](int l, int j) { return -vQaa[l] * sR[l + j * NVF]; });
