@@ -66,7 +66,7 @@ __device__ __forceinline__ void inv3_dev(const double* A, int lda, double* B, in
 }
 
 // SE3JacobianInverse::compute (se3_jacobian_inverse.hxx:17-32); one thread; Jac may be global, Jinv shared/global (ld 6)
-__device__ __forceinline__ void se3_jac_inverse_dev(const double* Jac, double* Jinv) {
+__device__ __noinline__ void se3_jac_inverse_dev(const double* Jac, double* Jinv) {
   double tmp[9];
   for (int q = 0; q < 36; ++q) Jinv[q] = 0.0;
   inv3_dev(Jac, 6, Jinv, 6);
@@ -740,21 +740,28 @@ __global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS, 6) condense_ke
   // ---- switching constraint                                contact_dynamics.cpp:138-153
   if (ns > 0) {
     const double* Phia = lin + S.l_Phia;
+#pragma unroll 1
     for (int e = tid; e < ns * NV; e += NTHR) ex[S.e_Phia + e] = Phia[e];
+#pragma unroll 1
     for (int e = tid; e < ns * NX; e += NTHR) {
       const int q = e % ns, j = e / ns;
       double acc = 0.0;
+#pragma unroll 2
       for (int l = 0; l < NV; ++l) acc = fma(Phia[q + l * ns], sR[l + j * NVF], acc);
       kkt[K.k_Phix + e] = lin[S.l_Phix + e] - acc;
     }
+#pragma unroll 1
     for (int e = tid; e < ns * NU; e += NTHR) {
       const int q = e % ns, j = e / ns;
       double acc = 0.0;
+#pragma unroll 2
       for (int l = 0; l < NV; ++l) acc = fma(Phia[q + l * ns], sZ[l + (np + j) * NVF], acc);
       kkt[K.k_Phiu + e] = acc;
     }
+#pragma unroll 1
     for (int q = tid; q < ns; q += NTHR) {
       double acc = 0.0;
+#pragma unroll 2
       for (int l = 0; l < NV; ++l) acc = fma(Phia[q + l * ns], vr[l], acc);
       kkt[K.k_p + q] = lin[S.l_p + q] - acc;
       kkt[K.k_Phit + q] = (lin[S.l_Phit + q] - acc) / c.ngrids_in_phase;  // incl. the STO scaling (intermediate_stage.cpp:146-148)
