@@ -9,7 +9,9 @@
  * its tests hold no golden vectors (randomised identities only).  This oracle
  * is therefore pinned by (i) the reference tests' algebraic identities re-run with fixed
  * seeds and (ii) an independent dense solve of the full block KKT system in numpy
- * (tests/test_oracle_kkt.py).  Against the reference binary itself: "parity unpinned".
+ * (tests/test_oracle_kkt.py; with the switching-time increment as an unknown for the STO path, in the
+ * configuration where the reference's recursion is an exact elimination).  Against the reference binary
+ * itself: "parity unpinned".
  *
  * Each function cites the reference file:line it restates.  The order of the floating
  * point operations follows the reference's expression order (Eigen evaluates each

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 import oracle_lib
-from helpers import dense_kkt_solve, small_event_schedule, rel_err
+from helpers import dense_kkt_solve, dense_kkt_solve_sto, small_event_schedule, rel_err
 from robotoc_b200 import ANYMAL, Layout
 from robotoc_b200.schedule import IMPACT, LIFT
 from robotoc_b200.synth import make_kkt
@@ -52,3 +52,45 @@ def test_oracle_riccati_symmetry_and_mutation():
             H = mat(kk[0, i], L.k_Qxu, nx, nu)
             Kt = mat(ric[0, i], L.r_K, nx, nu)
             assert rel_err(Kt.T, -np.linalg.solve(G, H.T)) < 1e-10
+
+
+def test_oracle_sto_direction_solves_full_kkt_single_impact():
+    """Switching-time optimisation, pinned independently of the Riccati algebra where the reference's recursion IS an exact
+    elimination: one STO-enabled impact event (phase transition without elimination of a later switching time), no time
+    dependence of the switching constraint.  Checks dx, du, the costate and the switching-time increment itself.
+    Not exact by construction of the reference (so not asserted here): a phase transition that eliminates the next
+    switching time keeps P unchanged (riccati_factorizer.cpp:149: riccati_m.P = riccati.P, no rank-one term), e.g.
+    lift -> impact sequences; with Phit != 0 the reference's step differs from this KKT model at the 1e-5 level."""
+    from robotoc_b200.schedule import ContactEvents, TimeDiscretization, stage_ctrl_array
+    dims = ANYMAL
+    L = Layout(dims)
+    ev = ContactEvents(phase_dimf=[6], phase_mask=[0b1001])
+    ev.push_back(True, 0.23, 12, impact_dimf=6, sto=True, post_mask=0b1111, impact_mask=0b0110)
+    td = TimeDiscretization(0.4, 8).discretize(ev, 0.0, sto=True)
+    ctrl = stage_ctrl_array(td, ev)
+    assert any(c.type == IMPACT for c in ctrl) and all(c.sto for c in ctrl[:-1])
+    for seed in (5, 11):
+        kkt, dx0 = make_kkt(dims, L, ctrl, batch=1, seed=seed)
+        kkt[:, :, L.k_sc + 0] *= 50.0   # convex in the switching time: the unregularised branch of the phase transition
+        kkt[:, :, L.k_sc + 1] *= 50.0
+        kkt[:, :, L.k_Phit:L.k_Phit + dims.ns_max] = 0.0
+        kk, ric, d, info = oracle_lib.riccati_batch(dims, L, ctrl, kkt, dx0, max_dts0=1e9)
+        assert info == 0
+        ref, phase, n_events = dense_kkt_solve_sto(dims, L, ctrl, kkt[0], dx0[0])
+        assert n_events == 1
+        ts = float(ref[("ts", 1)][0])
+        assert abs(ts) > 1e-3
+        for i in range(len(ctrl)):
+            di = d[0, i]
+            assert rel_err(di[L.d_dx:L.d_dx + dims.nx], ref[("dx", i)]) < 1e-9
+            if ctrl[i].type != IMPACT:
+                # (at the impact grid itself the reference evaluates the costate with dts_next = 0,
+                #  riccati_recursion.cpp:96-107 + riccati_factorizer.cpp:248-256, i.e. without the -Phi*ts term of the KKT)
+                assert rel_err(di[L.d_dlmdgmm:L.d_dlmdgmm + dims.nx], ref[("lmd", i)]) < 1e-8
+            if ("du", i) in ref:
+                assert rel_err(di[L.d_du:L.d_du + dims.nu], ref[("du", i)]) < 1e-9
+            if ("xi", i) in ref:
+                assert rel_err(di[L.d_dxi:L.d_dxi + ctrl[i].ns], ref[("xi", i)]) < 1e-7
+            if i < len(ctrl) - 1:  # phase 0: (dts, dts_next) = (0, ts) ; phase 1 (from the impact on): (ts, 0)
+                want = (0.0, ts) if phase[i] == 0 and ctrl[i].type != IMPACT else (ts, 0.0)
+                assert abs(di[L.d_dts] - want[0]) < 1e-9 * max(1.0, abs(ts)) and abs(di[L.d_dts + 1] - want[1]) < 1e-9 * max(1.0, abs(ts))
