@@ -299,6 +299,8 @@ def main():
                  lambda: rr.forwardRiccatiRecursion(stream=sp), lambda: dms.computeStepSizes(stream=sp),
                  lambda: dms.integrateSolution(stream=sp)]
         for k, call in enumerate(calls):
+            if world > 1 and k == 2:
+                stream.wait_stream(comm)  # the forward sweep overwrites the direction records the previous gather reads
             if ev is not None:
                 ev[k].record(stream)
                 if k == 0:  # rbt_condense = MJtJinv kernel + condensing kernel: an event between them splits the two
@@ -310,15 +312,22 @@ def main():
         if ev is not None:
             ev[len(calls)].record(stream)
         if world > 1:
-            allgather_step(d_local, out=d_all)  # the Newton step of every OCP on every rank (one NCCL all-gather)
-            if ev is not None:
-                ev[len(calls) + 1].record(stream)
+            # the Newton step of every OCP on every rank: one NCCL all-gather, on its own stream so that it overlaps the
+            # condensing and the backward sweep of the next iteration (it only has to finish before the next forward sweep)
+            comm.wait_stream(stream)
+            with torch.cuda.stream(comm):
+                if ev is not None:
+                    ev[8].record(comm)
+                allgather_step(d_local, out=d_all)
+                if ev is not None:
+                    ev[len(calls) + 1].record(comm)
 
+    comm = torch.cuda.Stream() if world > 1 else None
     for _ in range(max(args.warmup, 3)):
         step()
     torch.cuda.synchronize()
     l0 = rr.launch_count()
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(8)] for _ in range(args.steps)]
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(9)] for _ in range(args.steps)]
     t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     clk = ClockSampler(local)
     if rank == 0 and not os.environ.get("RBT_BENCH_NO_CLOCKS"):
@@ -330,6 +339,8 @@ def main():
     t_beg.record(stream)
     for k in range(args.steps):
         step(evs[k])
+    if world > 1:
+        stream.wait_stream(comm)  # the last gather is inside the timed region
     t_end.record(stream)
     torch.cuda.synchronize()
     if world > 1:
@@ -342,7 +353,7 @@ def main():
     kms["mjtjinv"] = float(np.mean([e[0].elapsed_time(e[7]) for e in evs]))
     kms["condense"] = float(np.mean([e[7].elapsed_time(e[1]) for e in evs]))
     if world > 1:
-        kms["nccl_allgather_step"] = float(np.mean([e[5].elapsed_time(e[6]) for e in evs]))
+        kms["nccl_allgather_step"] = float(np.mean([e[8].elapsed_time(e[6]) for e in evs]))  # timed on the comm stream
     print(f"[bench] rank {rank}: {ms / args.steps:.3f} ms/step on its own device clock", file=sys.stderr, flush=True)
     if world > 1:
         tt = torch.tensor([ms], dtype=torch.float64, device="cuda")
@@ -407,7 +418,7 @@ def main():
             "value": world * args.batch * args.steps / (ms * 1e-3), "unit": "OCP-iterations/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD.format(b=args.batch) + (" + NCCL all-gather of the step" if world > 1 else ""),
+            "config": {"workload": WORKLOAD.format(b=args.batch) + (" + NCCL all-gather of the step (overlapped with the next iteration's condensing / backward sweep)" if world > 1 else ""),
                        "n_grid": n_grid, "dims": "nv18 nu12 nx36, 92 inequality rows/stage", "parallelism": f"batch-sharded x{world}",
                        "l2": f"per-step working set {(lin.nbytes + rr.buf_doubles(0) * 8 + rr.buf_doubles(1) * 8) / 1e9:.2f} GB "
                              ">> 126 MB L2 (inputs larger than L2; no flush needed)"},
