@@ -259,6 +259,14 @@ def main():
         raise RuntimeError("bench.py needs a CUDA device: robotoc_b200 has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
+        # one process per GPU on a multi-socket host: run on the CPUs next to this GPU so that the pinned staging buffers of the
+        # end-to-end arm are first-touched on the local NUMA node (NVML knows the GPU's CPU affinity)
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
+        except Exception as e:  # noqa: BLE001  (affinity is an optimisation, never a requirement)
+            print(f"[bench] rank {rank}: CPU affinity not set ({e})", file=sys.stderr)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     pr = build_iteration_problem(args.batch, 20260927 + rank)
     dims, S, K, ctrl = pr["dims"], pr["S"], pr["K"], pr["ctrl"]
