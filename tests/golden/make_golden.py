@@ -24,7 +24,7 @@ from robotoc_b200 import ANYMAL, Layout, ULayout  # noqa: E402
 from robotoc_b200.stage import StageDims, StageLayout, anymal_constraint_table, make_stage_inputs  # noqa: E402
 from robotoc_b200.synth import make_kkt, make_unconstr_kkt  # noqa: E402
 
-SEEDS = {"riccati": 101, "riccati_sto": 102, "unconstr": 103, "iteration": 104}
+SEEDS = {"riccati": 101, "riccati_sto": 102, "unconstr": 103, "iteration": 104, "iteration_sto": 105, "unconstr_iteration": 106}
 
 
 def riccati_case(sto):
@@ -46,14 +46,27 @@ def unconstr_case():
     return ric, d
 
 
-def iteration_case():
+def unconstr_iteration_case():
+    """Full unconstrained iteration (iiwa14, N=20, batch 2): condense -> Riccati -> step sizes -> update."""
+    from robotoc_b200.unconstr_dms import UStageLayout, iiwa14_constraint_table, make_unconstr_stage_inputs
+    lib = oracle_lib.load()
+    tab = iiwa14_constraint_table()
+    S = UStageLayout(7, tab.n_box, getter=lib.orc_ustage_layout_get)
+    UL = ULayout(7, getter=lib.orc_ulayout_get)
+    lin, con, sol, dx0 = make_unconstr_stage_inputs(S, 20, 2, SEEDS["unconstr_iteration"])
+    out = oracle_lib.unconstr_iteration(7, UL, S, tab, 20, 0.05, lin, con, sol, dx0)
+    assert out["info"] == 0
+    return out["kkt"], out["steps"], out["sol"], out["con"]
+
+
+def iteration_case(sto=False):
     lib = oracle_lib.load()
     table = anymal_constraint_table()
     sd = StageDims(ANYMAL, nf_max=12, n_contacts=4, n_box=table.n_box)
     S = StageLayout(sd, getter=lib.orc_stage_layout_get)
     K = Layout(ANYMAL, getter=lib.orc_layout_get)
-    td, ev, ctrl = small_event_schedule(False)
-    lin, con, sol, dx0 = make_stage_inputs(sd, S, ctrl, 2, SEEDS["iteration"])
+    td, ev, ctrl = small_event_schedule(sto)
+    lin, con, sol, dx0 = make_stage_inputs(sd, S, ctrl, 2, SEEDS["iteration_sto" if sto else "iteration"])
     n_grid, batch = len(ctrl), 2
     csd = sd.c()
     kkt, ex = np.zeros((batch, n_grid, K.k_stride)), np.zeros((batch, n_grid, S.e_stride))
@@ -72,6 +85,10 @@ if __name__ == "__main__":
     ric_s, d_s = riccati_case(True)
     uric, ud = unconstr_case()
     kkt_c, steps, sol, con = iteration_case()
+    kkt_cs, steps_s, sol_s, con_s = iteration_case(True)
+    ukkt, usteps, usol, ucon = unconstr_iteration_case()
     np.savez_compressed(os.path.join(HERE, "golden_r1.npz"), ric=ric, d=d, ric_sto=ric_s, d_sto=d_s, uric=uric, ud=ud,
-                        kkt_condensed=kkt_c, steps=steps, sol=sol, con=con)
+                        kkt_condensed=kkt_c, steps=steps, sol=sol, con=con,
+                        kkt_condensed_sto=kkt_cs, steps_sto=steps_s, sol_sto=sol_s, con_sto=con_s,
+                        ukkt_condensed=ukkt, usteps=usteps, usol=usol, ucon=ucon)
     print("wrote", os.path.join(HERE, "golden_r1.npz"), os.path.getsize(os.path.join(HERE, "golden_r1.npz")) // 1024, "KiB")

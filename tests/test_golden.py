@@ -28,6 +28,12 @@ def test_oracle_reproduces_golden():
     kkt_c, steps, sol, con = mg.iteration_case()
     assert _close(kkt_c, G["kkt_condensed"], 1e-12) and _close(steps, G["steps"], 1e-12)
     assert _close(sol, G["sol"], 1e-12) and _close(con, G["con"], 1e-12)
+    kkt_c, steps, sol, con = mg.iteration_case(True)
+    assert _close(kkt_c, G["kkt_condensed_sto"], 1e-12) and _close(steps, G["steps_sto"], 1e-12)
+    assert _close(sol, G["sol_sto"], 1e-12) and _close(con, G["con_sto"], 1e-12)
+    ukkt, usteps, usol, ucon = mg.unconstr_iteration_case()
+    assert _close(ukkt, G["ukkt_condensed"], 1e-12) and _close(usteps, G["usteps"], 1e-12)
+    assert _close(usol, G["usol"], 1e-12) and _close(ucon, G["ucon"], 1e-12)
 
 
 @pytest.mark.gpu
@@ -57,18 +63,30 @@ def test_cuda_reproduces_golden():
     table = anymal_constraint_table()
     sd = StageDims(ANYMAL, nf_max=12, n_contacts=4, n_box=table.n_box)
     S = StageLayout(sd)
-    td, ev, ctrl = small_event_schedule(False)
-    lin, con, sol, dx0 = make_stage_inputs(sd, S, ctrl, 2, mg.SEEDS["iteration"])
-    rr = RiccatiRecursion(ANYMAL, len(ctrl), 2)
-    rr.setTimeDiscretization(ctrl)
-    dms = DirectMultipleShooting(rr, sd, table)
-    dms.condense(lin, con)
-    assert _close(dms.getKKT(), G["kkt_condensed"], 1e-8)
-    rr.backwardRiccatiRecursion()
-    rr.forwardRiccatiRecursion(dx0)
-    dms.computeStepSizes()
-    dms.integrateSolution(sol)
-    steps = np.stack([dms.maxPrimalStepSize(), dms.maxDualStepSize()], axis=1)
-    assert _close(steps, G["steps"], 1e-10)
-    assert _close(dms.getSolution(), G["sol"], 1e-8)
-    rr.close()
+    for sto, sfx in ((False, ""), (True, "_sto")):
+        td, ev, ctrl = small_event_schedule(sto)
+        lin, con, sol, dx0 = make_stage_inputs(sd, S, ctrl, 2, mg.SEEDS["iteration_sto" if sto else "iteration"])
+        rr = RiccatiRecursion(ANYMAL, len(ctrl), 2)
+        rr.setTimeDiscretization(ctrl)
+        dms = DirectMultipleShooting(rr, sd, table)
+        dms.condense(lin, con)
+        assert _close(dms.getKKT(), G["kkt_condensed" + sfx], 1e-8)
+        rr.backwardRiccatiRecursion()
+        rr.forwardRiccatiRecursion(dx0)
+        dms.computeStepSizes()
+        dms.integrateSolution(sol)
+        steps = np.stack([dms.maxPrimalStepSize(), dms.maxDualStepSize()], axis=1)
+        assert _close(steps, G["steps" + sfx], 1e-10)
+        assert _close(dms.getSolution(), G["sol" + sfx], 1e-8)
+        rr.close()
+    # unconstrained full iteration (iiwa14)
+    from robotoc_b200 import UnconstrDirectMultipleShooting, iiwa14_constraint_table
+    from robotoc_b200.unconstr_dms import make_unconstr_stage_inputs
+    tab = iiwa14_constraint_table()
+    ur = UnconstrRiccatiRecursion(7, 20, 0.05, 2)
+    udms = UnconstrDirectMultipleShooting(ur, tab)
+    lin, con, sol, dx0 = make_unconstr_stage_inputs(udms.layout, 20, 2, mg.SEEDS["unconstr_iteration"])
+    sol2, con2, steps2 = udms.iteration_host(lin, con, sol, dx0)
+    assert _close(udms.getKKT(), G["ukkt_condensed"], 1e-9)
+    assert _close(steps2, G["usteps"], 1e-10) and _close(sol2, G["usol"], 1e-9) and _close(con2, G["ucon"], 1e-9)
+    ur.close()
