@@ -1084,6 +1084,10 @@ __global__ void __launch_bounds__(XTHR) update_kernel(const StageParams p) {
   const double dt = c.dt;
   double dts = 0.0;
   if (!impact && c.ngrids_in_phase > 0) dts = (d[K.d_dts + 1] - d[K.d_dts]) / c.ngrids_in_phase;  // intermediate_stage.cpp:167-170
+  // old values of the entries this thread will update after the mat-vecs: fetched now, under the bulk copies (a load issued
+  // after the barriers would sit on every warp's critical path)
+  const double bm_old = (tid < nvf) ? (tid < NV ? sol[S.s_beta + tid] : sol[S.s_mu + tid - NV]) : 0.0;
+  const double nup_old = (nup && wid == 3 && (lane >> 2) < 6 && (lane & 3) == 0) ? sol[S.s_nup + (lane >> 2)] : 0.0;
   double extra = 0.0;  // the per-row terms of laf that do not come from the staged matrices
   if (tid < nvf) {
     extra = ex[S.e_laf + tid];
@@ -1125,7 +1129,7 @@ __global__ void __launch_bounds__(XTHR) update_kernel(const StageParams p) {
     if (prow < 6 && ppart == 0) {
       pn -= slup[prow];
       xd[S.x_dnup + prow] = pn;
-      sol[S.s_nup + prow] += ap * pn;
+      sol[S.s_nup + prow] = nup_old + ap * pn;
     }
   }
   __syncthreads();
@@ -1145,8 +1149,8 @@ __global__ void __launch_bounds__(XTHR) update_kernel(const StageParams p) {
   if (tid < nvf) {
     const double acc = (spart[0][tid] + spart[1][tid]) + (spart[2][tid] + spart[3][tid]);
     xd[S.x_dbetamu + tid] = acc;
-    if (tid < NV) sol[S.s_beta + tid] += ap * acc;
-    else sol[S.s_mu + tid - NV] += ap * acc;
+    if (tid < NV) sol[S.s_beta + tid] = bm_old + ap * acc;
+    else sol[S.s_mu + tid - NV] = bm_old + ap * acc;
   }
 }
 
