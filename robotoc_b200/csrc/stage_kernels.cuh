@@ -1,5 +1,6 @@
 // stage_kernels.cuh -- stage-parallel kernels of the hot path around the Riccati sweeps.
 //
+//   mjtjinv_kernel      Z = [[M,J^T],[J,0]]^-1 (Robot::computeMJtJinv, robot.hxx:642-683): one warp per stage, DMMA products
 //   condense_kernel     PDIPM condensing + contact/impact dynamics condensing + floating-base state-equation correction
 //                       (intermediate_stage.cpp:133-148, contact_dynamics.cpp:55-164, impact_dynamics.cpp:38-80,
 //                        state_equation.cpp:68-87, joint_*_limit.cpp:68-75, friction_cone.cpp:194-235, pdipm.hxx:27-100)
@@ -8,10 +9,11 @@
 //                        direct_multiple_shooting.cpp:174-209)
 //   update_kernel       dual expansion, costate correction, solution integrate, slack/dual update
 //                       (contact_dynamics.cpp:177-202, state_equation.cpp:90-95, split_solution.cpp:58-90)
+//   unpack_wire_kernel  host wire records (packed symmetric blocks) -> linearization records, for rbt_iteration_host_wire
 //
 // Unlike the Riccati sweeps these have NO dependency between stages: the grid is batch x n_grid CTAs (48k for config 3),
-// every stage is an independent small dense problem held in shared memory.  Round 1: plain fp64 FMA loops over shared
-// memory (correctness first); the dense products are candidates for the DMMA path of riccati_backward.cuh.
+// every stage is an independent small dense problem held in shared memory: inputs arrive by cp.async.bulk onto an mbarrier,
+// every dense product runs on the fp64 tensor pipe (DMMA m8n8k4), mat-vecs are split over the warps of the CTA.
 #pragma once
 #include "rbt_device.cuh"
 #include "riccati_backward.cuh"  // warp_cholesky, chol_solve_smem
