@@ -9,9 +9,10 @@
  * its tests hold no golden vectors (randomised identities only).  This oracle
  * is therefore pinned by (i) the reference tests' algebraic identities re-run with fixed
  * seeds and (ii) an independent dense solve of the full block KKT system in numpy
- * (tests/test_oracle_kkt.py; with the switching-time increment as an unknown for the STO path, in the
- * configuration where the reference's recursion is an exact elimination).  Against the reference binary
- * itself: "parity unpinned".
+ * (tests/test_oracle_kkt.py; for the STO path with the switching-time increments as unknowns: exact
+ * up to two terms where the reference itself departs from the exact Newton step, both restated here and
+ * documented at orc_debug_exact_chi / orc_debug_exact_transition).  Against the reference binary itself:
+ * "parity unpinned".
  *
  * Each function cites the reference file:line it restates.  The order of the floating
  * point operations follows the reference's expression order (Eigen evaluates each
@@ -25,6 +26,9 @@
 #include "../include/rbt_layout.h"
 
 #define IDX(i, j, ld) ((i) + (size_t)(j) * (ld))
+
+int orc_debug_exact_chi = 0; /* see the switching-constraint STO terms below; never set outside the tests */
+int orc_debug_exact_transition = 0; /* phase transition with the rank-one term of P (tests only), see phase_transition() */
 
 /* C(m x n) = beta*C + alpha * op(A) * op(B);  ta/tb: 0 = as is, 1 = transposed.
  * Loop forms are chosen so that gcc vectorises them (column axpy for op(A)=A, simd dot products over contiguous
@@ -353,7 +357,10 @@ static int backward_full(const rbt_layout* L, orc_ws* w, int ns, int sto, int st
     const double* ct = kkt + L->k_Phit;
     gemm(1, 0, nx, 1, ns, 1.0, ric + L->r_M, ns, ct, ns, 1.0, Psi, nx);    /* Psi += M^T Phit */
     xi += dot(ns, ric + L->r_mt, ct);
-    if (sto_next) chi += dot(ns, ric + L->r_mtn, ct);
+    /* NB: T already contains -SDG^T Phit, so T.phi_u above already carries Phit^T mt_next; the reference adds it once
+     * more here (riccati_factorizer.cpp:139).  Restated as it is; orc_debug_exact_chi = 1 (tests only) leaves it out,
+     * which makes the recursion the exact elimination of the KKT system (tests/test_oracle_kkt.py). */
+    if (sto_next && !orc_debug_exact_chi) chi += dot(ns, ric + L->r_mtn, ct);
     eta += dot(ns, ric + L->r_m, ct);
   }
   sc[0] = xi; sc[1] = chi; sc[2] = rho; sc[3] = eta; sc[4] = iota;
@@ -420,6 +427,13 @@ static void phase_transition(const rbt_layout* L, double max_dts0, const double*
     for (int i = 0; i < nx; ++i) m[L->r_Phi + i] -= (1.0 / sgm) * (Psi[i] - Phi[i]) * (xi - chi);
     msc[2] = xi - (1.0 / sgm) * (xi - chi) * (xi - chi);
     msc[4] = eta - (1.0 / sgm) * (xi - chi) * (eta - iota);
+    /* NB: minimising over the next switching time also gives P_m = P - (Psi-Phi)(Psi-Phi)^T / sgm; the reference keeps
+     * riccati_m.P = riccati.P (:149).  Restated as it is; orc_debug_exact_transition = 1 (tests only) adds the term. */
+    if (orc_debug_exact_transition) {
+      double* P_m = m + L->r_P;
+      for (int j = 0; j < nx; ++j)
+        for (int i = 0; i < nx; ++i) P_m[IDX(i, j, nx)] -= (1.0 / sgm) * (Psi[i] - Phi[i]) * (Psi[j] - Phi[j]);
+    }
   }
 }
 

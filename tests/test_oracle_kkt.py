@@ -54,13 +54,17 @@ def test_oracle_riccati_symmetry_and_mutation():
             assert rel_err(Kt.T, -np.linalg.solve(G, H.T)) < 1e-10
 
 
-def test_oracle_sto_direction_solves_full_kkt_single_impact():
+@pytest.mark.parametrize("with_phit", [False, True])
+def test_oracle_sto_direction_solves_full_kkt_single_impact(with_phit):
     """Switching-time optimisation, pinned independently of the Riccati algebra where the reference's recursion IS an exact
-    elimination: one STO-enabled impact event (phase transition without elimination of a later switching time), no time
-    dependence of the switching constraint.  Checks dx, du, the costate and the switching-time increment itself.
-    Not exact by construction of the reference (so not asserted here): a phase transition that eliminates the next
-    switching time keeps P unchanged (riccati_factorizer.cpp:149: riccati_m.P = riccati.P, no rank-one term), e.g.
-    lift -> impact sequences; with Phit != 0 the reference's step differs from this KKT model at the 1e-5 level."""
+    elimination: one STO-enabled impact event (phase transition without elimination of a later switching time).  Checks
+    dx, du, the costate, the switching-constraint multiplier and the switching-time increment itself.
+    with_phit: the switching constraint depends on the switching time (Phit != 0).  There the reference counts
+    Phit^T mt_next twice in chi (riccati_factorizer.cpp:139 on top of T.phi_u, backward_..._factorizer.cpp:118); the oracle
+    restates that, and its step then differs from the KKT solution at the 1e-5 level -- asserted -- while with the second
+    count left out (orc_debug_exact_chi, tests only) it IS the KKT solution to 1e-9, which pins every other Phit term.
+    (Phase transitions that eliminate a later switching time: next test.)"""
+    import ctypes
     from robotoc_b200.schedule import ContactEvents, TimeDiscretization, stage_ctrl_array
     dims = ANYMAL
     L = Layout(dims)
@@ -73,10 +77,20 @@ def test_oracle_sto_direction_solves_full_kkt_single_impact():
         kkt, dx0 = make_kkt(dims, L, ctrl, batch=1, seed=seed)
         kkt[:, :, L.k_sc + 0] *= 50.0   # convex in the switching time: the unregularised branch of the phase transition
         kkt[:, :, L.k_sc + 1] *= 50.0
-        kkt[:, :, L.k_Phit:L.k_Phit + dims.ns_max] = 0.0
-        kk, ric, d, info = oracle_lib.riccati_batch(dims, L, ctrl, kkt, dx0, max_dts0=1e9)
-        assert info == 0
+        if not with_phit:
+            kkt[:, :, L.k_Phit:L.k_Phit + dims.ns_max] = 0.0
         ref, phase, n_events = dense_kkt_solve_sto(dims, L, ctrl, kkt[0], dx0[0])
+        flag = ctypes.c_int.in_dll(oracle_lib.load(), "orc_debug_exact_chi")
+        if with_phit:  # the restated reference formula: close to, but not, the KKT solution
+            kk, ric, d, info = oracle_lib.riccati_batch(dims, L, ctrl, kkt, dx0, max_dts0=1e9)
+            dev = max(rel_err(d[0, i, L.d_dx:L.d_dx + dims.nx], ref[("dx", i)]) for i in range(len(ctrl)))
+            assert 1e-8 < dev < 1e-3
+            flag.value = 1
+        try:
+            kk, ric, d, info = oracle_lib.riccati_batch(dims, L, ctrl, kkt, dx0, max_dts0=1e9)
+        finally:
+            flag.value = 0
+        assert info == 0
         assert n_events == 1
         ts = float(ref[("ts", 1)][0])
         assert abs(ts) > 1e-3
@@ -94,3 +108,51 @@ def test_oracle_sto_direction_solves_full_kkt_single_impact():
             if i < len(ctrl) - 1:  # phase 0: (dts, dts_next) = (0, ts) ; phase 1 (from the impact on): (ts, 0)
                 want = (0.0, ts) if phase[i] == 0 and ctrl[i].type != IMPACT else (ts, 0.0)
                 assert abs(di[L.d_dts] - want[0]) < 1e-9 * max(1.0, abs(ts)) and abs(di[L.d_dts + 1] - want[1]) < 1e-9 * max(1.0, abs(ts))
+
+
+@pytest.mark.parametrize("seed", [5, 7])
+def test_oracle_sto_lift_impact_is_exact_kkt_up_to_two_documented_terms(seed):
+    """Lift -> impact with both events STO-enabled, a switching-constraint stage and Phit != 0: the phase transition at the
+    lift ELIMINATES the impact's switching time.  The reference's recursion differs from the exact Newton step of the LQ
+    sub-problem in exactly two places -- it keeps riccati_m.P = riccati.P where minimising over the switching time gives
+    P - (Psi-Phi)(Psi-Phi)^T/sgm (riccati_factorizer.cpp:149), and it counts Phit^T mt_next twice in chi (:139) -- and the
+    oracle restates both.  With the two terms put right (orc_debug_exact_* switches, tests only) the oracle's direction,
+    both switching-time increments included, IS the dense KKT solution to 1e-9: every other STO term (stage terms,
+    Hamiltonian factorisation, T / W / mt / mt_next, phase transition, STO policy, forward dts propagation, Lagrange
+    multipliers) is thereby pinned independently of the Riccati algebra.  As restated (default) the step is within 5e-2."""
+    import ctypes
+    dims = ANYMAL
+    L = Layout(dims)
+    td, ev, ctrl = small_event_schedule(sto=True)
+    assert [c.type for c in ctrl].count(LIFT) == 1 and [c.type for c in ctrl].count(IMPACT) == 1
+    kkt, dx0 = make_kkt(dims, L, ctrl, batch=1, seed=seed)
+    kkt[:, :, L.k_sc + 0] *= 50.0   # convex in the switching times: the unregularised branch of the phase transitions
+    kkt[:, :, L.k_sc + 1] *= 50.0
+    ref, phase, n_events = dense_kkt_solve_sto(dims, L, ctrl, kkt[0], dx0[0])
+    assert n_events == 2
+    ts = [float(ref[("ts", k)][0]) for k in (1, 2)]
+    lib = oracle_lib.load()
+    kk, ric, d, info = oracle_lib.riccati_batch(dims, L, ctrl, kkt, dx0, max_dts0=1e9)  # as the reference
+    dev = max(rel_err(d[0, i, L.d_dx:L.d_dx + dims.nx], ref[("dx", i)]) for i in range(len(ctrl)))
+    assert info == 0 and 1e-6 < dev < 5e-2
+    flags = [ctypes.c_int.in_dll(lib, n) for n in ("orc_debug_exact_chi", "orc_debug_exact_transition")]
+    try:
+        for f in flags:
+            f.value = 1
+        kk, ric, d, info = oracle_lib.riccati_batch(dims, L, ctrl, kkt, dx0, max_dts0=1e9)
+    finally:
+        for f in flags:
+            f.value = 0
+    assert info == 0
+    for i in range(len(ctrl)):
+        di = d[0, i]
+        assert rel_err(di[L.d_dx:L.d_dx + dims.nx], ref[("dx", i)]) < 1e-9
+        if ("du", i) in ref:
+            assert rel_err(di[L.d_du:L.d_du + dims.nu], ref[("du", i)]) < 1e-9
+        if ("xi", i) in ref:
+            assert rel_err(di[L.d_dxi:L.d_dxi + ctrl[i].ns], ref[("xi", i)]) < 1e-7
+        if ctrl[i].type != IMPACT and i < len(ctrl) - 1:
+            assert rel_err(di[L.d_dlmdgmm:L.d_dlmdgmm + dims.nx], ref[("lmd", i)]) < 1e-8
+            a = ts[phase[i] - 1] if phase[i] >= 1 else 0.0
+            b = ts[phase[i]] if phase[i] < n_events else 0.0
+            assert abs(di[L.d_dts] - a) < 1e-9 and abs(di[L.d_dts + 1] - b) < 1e-9
