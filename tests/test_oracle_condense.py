@@ -204,3 +204,99 @@ def test_expand_update_consistency():
         assert np.allclose(np.linalg.norm(quat, axis=1), 1.0)
         assert np.allclose(sol2[b, :, S.s_q + 7:S.s_q + 19], sol[b, :, S.s_q + 7:S.s_q + 19] + a * d[b, :, K.d_dx + 6:K.d_dx + nv])
         assert np.allclose(cc2[b][inter][:, S.c_slack:S.c_slack + S.nc], (sl[b] + a * dsl[b])[inter])
+
+
+def test_dual_expansion_satisfies_uncondensed_stationarity():
+    """expandContactDynamicsDual (contact_dynamics.cpp:177-202) pinned without its formulas: the multiplier directions it
+    returns make the UNCONDENSED stage Lagrangian stationary in the eliminated variables,
+        d/da : la' + Qaa' da + M dbeta + J^T dmu + dt dgmm+ (+ Phia^T dxi)            = 0
+        d/df : lf' + Qff' df + Qqf'^T dq - J dbeta                                      = 0
+        d/du : lu' + Quu' du - dbeta[actuated]                                          = 0
+        passive joints : lu_passive - dbeta[passive] + dnu_passive                      = 0   (*)
+    where ' marks the cost terms plus the PDIPM terms of the inequality rows (recomputed here as J^T diag(z/s) J and
+    J^T cond).  Intermediate and lift stages incl. the switching-constraint stage of an ANYmal schedule.
+    (*) on a switching-constraint stage the reference's dnu_passive (contact_dynamics.cpp:182-189) has no dxi term although
+    dbeta does (:193-195), so there the residual is Z[passive, a] Phia^T dxi instead of 0 -- restated, and asserted as such."""
+    table = anymal_constraint_table()
+    td, ev, ctrl = small_event_schedule(False)
+    lib, sd, S, K, lin, con, sol, dx0 = _setup(table, ctrl, batch=2, seed=13)
+    kkt, ex, cc = _condense(lib, sd, S, K, table, ctrl, lin, con)
+    kk, ric, d, info = oracle_lib.riccati_batch(ANYMAL, K, ctrl, kkt, dx0)
+    assert info == 0
+    batch, n_grid = 2, len(ctrl)
+    xd, steps = np.zeros((batch, n_grid, S.x_stride)), np.zeros((batch, 2))
+    csd = sd.c()
+    lib.orc_expand_batch(ctypes.byref(csd), ctypes.byref(table), ctrl, n_grid, batch, oracle_lib.ptr(lin), oracle_lib.ptr(ex),
+                         oracle_lib.ptr(d), oracle_lib.ptr(cc), oracle_lib.ptr(xd), oracle_lib.ptr(steps), 1)
+    sol2, cc2, d2, ex2 = sol.copy(), cc.copy(), d.copy(), ex.copy()
+    lib.orc_update_batch(ctypes.byref(csd), ctypes.byref(table), ctrl, n_grid, batch, oracle_lib.ptr(ex2), oracle_lib.ptr(d2),
+                         oracle_lib.ptr(xd), oracle_lib.ptr(cc2), oracle_lib.ptr(sol2), oracle_lib.ptr(steps), 1)
+    nv, nu, nx, npass = 18, 12, 36, 6
+    checked = 0
+    for b in range(batch):
+        for i in range(n_grid - 1):
+            c = ctrl[i]
+            if c.type == IMPACT:
+                # expandImpactDynamicsDual (impact_dynamics.cpp:90-96): the impulse change ddv plays the role of da, no dt
+                nf, l, x = c.nf, lin[b, i], xd[b, i]
+                M, J = mat(l, S.l_M, nv, nv), mat(l, S.l_J, 12, nv)[:nf]
+                ddv, df = x[S.x_daf:S.x_daf + nv], x[S.x_daf + nv:S.x_daf + nv + nf]
+                dbeta, dmu = x[S.x_dbetamu:S.x_dbetamu + nv], x[S.x_dbetamu + nv:S.x_dbetamu + nv + nf]
+                dgmm_n = d[b, i + 1, K.d_dlmdgmm + nv:K.d_dlmdgmm + nx]
+                ra = l[S.l_la:S.l_la + nv] + l[S.l_Qaa:S.l_Qaa + nv] * ddv + M @ dbeta + J.T @ dmu + dgmm_n
+                assert np.abs(ra).max() < 1e-9 * max(np.abs(M @ dbeta).max(), 1.0), f"impact d/ddv stage {i}"
+                rf = (l[S.l_lf:S.l_lf + nf] + mat(l, S.l_Qff, 12, 12)[:nf, :nf] @ df
+                      + mat(l, S.l_Qqf, nv, 12)[:, :nf].T @ d[b, i, K.d_dx:K.d_dx + nv] - J @ dbeta)
+                assert np.abs(rf).max() < 1e-9 * max(np.abs(J @ dbeta).max(), 1.0), f"impact d/df stage {i}"
+                checked += 1
+                continue
+            nf, dt, l = c.nf, c.dt, lin[b, i]
+            M, J = mat(l, S.l_M, nv, nv), mat(l, S.l_J, 12, nv)[:nf]
+            Qaa = l[S.l_Qaa:S.l_Qaa + nv].copy()
+            Qff, Qqf = mat(l, S.l_Qff, 12, 12)[:nf, :nf].copy(), mat(l, S.l_Qqf, nv, 12)[:, :nf].copy()
+            Quu = mat(l, S.l_Quu, nu, nu).copy()
+            la, lf, lu = l[S.l_la:S.l_la + nv].copy(), l[S.l_lf:S.l_lf + nf].copy(), l[S.l_lu:S.l_lu + nu].copy()
+            lup = l[S.l_lup:S.l_lup + npass]
+            # PDIPM terms, recomputed from slack / dual / residual
+            sl, du_, rs = (con[b, i, o:o + S.nc] for o in (S.c_slack, S.c_dual, S.c_res))
+            w = du_ / sl
+            cond = (du_ * rs - (sl * du_ - table.barrier)) / sl
+            for r in range(table.n_box):
+                br = table.box[r]
+                if br.var == 3:  # torque limits
+                    Quu[br.idx, br.idx] += w[r]
+                    lu[br.idx] += br.sign * cond[r]
+                elif br.var == 2:
+                    Qaa[br.idx] += w[r]
+                    la[br.idx] += br.sign * cond[r]
+            fst = 0
+            for ci in range(table.n_contacts):
+                if not (c.contact_mask >> ci) & 1:
+                    continue
+                rows = slice(table.n_box + 5 * ci, table.n_box + 5 * ci + 5)
+                dgdq = mat(l, S.l_dgdq + ci * 5 * nv, 5, nv)
+                dgdf = mat(l, S.l_dgdf + ci * 15, 5, 3)
+                Qff[fst:fst + 3, fst:fst + 3] += dgdf.T @ np.diag(w[rows]) @ dgdf
+                Qqf[:, fst:fst + 3] += dgdq.T @ np.diag(w[rows]) @ dgdf
+                lf[fst:fst + 3] += dgdf.T @ cond[rows]
+                fst += 3
+            di, dn, x = d[b, i], d[b, i + 1], xd[b, i]
+            dq, du = di[K.d_dx:K.d_dx + nv], di[K.d_du:K.d_du + nu]
+            da, df = x[S.x_daf:S.x_daf + nv], x[S.x_daf + nv:S.x_daf + nv + nf]
+            dbeta, dmu = x[S.x_dbetamu:S.x_dbetamu + nv], x[S.x_dbetamu + nv:S.x_dbetamu + nv + nf]
+            dnup = x[S.x_dnup:S.x_dnup + npass]
+            dgmm_n = dn[K.d_dlmdgmm + nv:K.d_dlmdgmm + nx]
+            ra = la + Qaa * da + M @ dbeta + J.T @ dmu + dt * dgmm_n
+            if c.ns > 0:
+                ra = ra + mat(l, S.l_Phia, c.ns, nv).T @ di[K.d_dxi:K.d_dxi + c.ns]
+            scale = max(np.abs(la).max(), np.abs(M @ dbeta).max(), 1.0)
+            assert np.abs(ra).max() < 1e-9 * scale, f"d/da stage {i}"
+            assert np.abs(lf + Qff @ df + Qqf.T @ dq - J @ dbeta).max() < 1e-9 * max(np.abs(J @ dbeta).max(), 1.0), f"d/df stage {i}"
+            assert np.abs(lu + Quu @ du - dbeta[npass:]).max() < 1e-9 * max(np.abs(dbeta).max(), 1.0), f"d/du stage {i}"
+            rp = lup - dbeta[:npass] + dnup
+            if c.ns > 0:
+                Zfull = np.linalg.inv(np.block([[M, J.T], [J, np.zeros((nf, nf))]]))
+                rp = rp - Zfull[:npass, :nv] @ (mat(l, S.l_Phia, c.ns, nv).T @ di[K.d_dxi:K.d_dxi + c.ns])
+            assert np.abs(rp).max() < 1e-9 * max(np.abs(dbeta).max(), 1.0), f"passive stage {i}"
+            checked += 1
+    assert checked == 2 * (n_grid - 1) and any(c.ns > 0 for c in ctrl) and any(c.type == IMPACT for c in ctrl)
