@@ -300,3 +300,44 @@ def test_dual_expansion_satisfies_uncondensed_stationarity():
             assert np.abs(rp).max() < 1e-9 * max(np.abs(dbeta).max(), 1.0), f"passive stage {i}"
             checked += 1
     assert checked == 2 * (n_grid - 1) and any(c.ns > 0 for c in ctrl) and any(c.type == IMPACT for c in ctrl)
+
+
+def test_floating_base_state_equation_correction():
+    """correctLinearizeStateEquation / correctCostateDirection (state_equation.cpp:68-95, se3_jacobian_inverse.hxx:17-32)
+    pinned without the block-inverse formula: with E = dSubtract/dq+ (the 6x6 block the reference inverts) the corrected
+    blocks satisfy  E Fqq[0:6,0:6] = -dSub/dqf,  E Fqv[0:6,0:6] = -dt I,  E Fq[0:6] = -Fq_uncorrected[0:6], and the costate
+    head satisfies  Fqq_prev^T dlmd_corrected[0:6] = -dlmd[0:6]."""
+    table = anymal_constraint_table()
+    td, ev, ctrl = small_event_schedule(False)
+    lib, sd, S, K, lin, con, sol, dx0 = _setup(table, ctrl, batch=1, seed=17)
+    kkt, ex, cc = _condense(lib, sd, S, K, table, ctrl, lin, con)
+    kkt0 = kkt.copy()
+    kk, ric, d, info = oracle_lib.riccati_batch(ANYMAL, K, ctrl, kkt, dx0)
+    n_grid = len(ctrl)
+    xd, steps = np.zeros((1, n_grid, S.x_stride)), np.zeros((1, 2))
+    csd = sd.c()
+    lib.orc_expand_batch(ctypes.byref(csd), ctypes.byref(table), ctrl, n_grid, 1, oracle_lib.ptr(lin), oracle_lib.ptr(ex),
+                         oracle_lib.ptr(d), oracle_lib.ptr(cc), oracle_lib.ptr(xd), oracle_lib.ptr(steps), 1)
+    d_before = d.copy()
+    sol2 = sol.copy()
+    lib.orc_update_batch(ctypes.byref(csd), ctypes.byref(table), ctrl, n_grid, 1, oracle_lib.ptr(ex), oracle_lib.ptr(d),
+                         oracle_lib.ptr(xd), oracle_lib.ptr(cc), oracle_lib.ptr(sol2), oracle_lib.ptr(steps), 1)
+    nv, nx = 18, 36
+    for i in range(n_grid):
+        l, k = lin[0, i], kkt0[0, i]
+        Fqq_prev = mat(l, S.l_se3 + 36, 6, 6)
+        old, new = d_before[0, i, K.d_dlmdgmm:K.d_dlmdgmm + 6], d[0, i, K.d_dlmdgmm:K.d_dlmdgmm + 6]
+        assert np.allclose(Fqq_prev.T @ new, -old, rtol=1e-10, atol=1e-12), f"costate head, grid {i}"
+        assert np.array_equal(d[0, i, K.d_dlmdgmm + 6:K.d_dlmdgmm + nx], d_before[0, i, K.d_dlmdgmm + 6:K.d_dlmdgmm + nx])
+        if ctrl[i].type == TERMINAL:
+            continue
+        E, dSub = mat(l, S.l_se3 + 72, 6, 6), mat(l, S.l_se3, 6, 6)
+        Fxx = mat(k, K.k_Fxx, nx, nx)
+        assert np.allclose(E @ Fxx[:6, :6], -dSub, rtol=1e-10, atol=1e-12), f"Fqq, grid {i}"
+        if ctrl[i].type == IMPACT:
+            assert not Fxx[:6, nv:nv + 6].any()
+        else:
+            assert np.allclose(E @ Fxx[:6, nv:nv + 6], -ctrl[i].dt * np.eye(6), rtol=1e-10, atol=1e-12), f"Fqv, grid {i}"
+        assert np.allclose(E @ k[K.k_Fx:K.k_Fx + 6], -l[S.l_Fx:S.l_Fx + 6], rtol=1e-10, atol=1e-12), f"Fq, grid {i}"
+        # the rest of the q rows is the fixed-base structure: identity / dt identity  (state_equation.cpp:52-55)
+        assert np.array_equal(Fxx[6:nv, :nv], np.eye(nv)[6:]) and np.array_equal(Fxx[:6, 6:nv], np.zeros((6, nv - 6)))
