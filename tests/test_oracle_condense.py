@@ -341,3 +341,40 @@ def test_floating_base_state_equation_correction():
         assert np.allclose(E @ k[K.k_Fx:K.k_Fx + 6], -l[S.l_Fx:S.l_Fx + 6], rtol=1e-10, atol=1e-12), f"Fq, grid {i}"
         # the rest of the q rows is the fixed-base structure: identity / dt identity  (state_equation.cpp:52-55)
         assert np.array_equal(Fxx[6:nv, :nv], np.eye(nv)[6:]) and np.array_equal(Fxx[:6, 6:nv], np.zeros((6, nv - 6)))
+
+
+def test_sto_sensitivities_are_the_substituted_hamiltonian_derivatives():
+    """STO sensitivities of the condensing (contact_dynamics.cpp:155-163) + the 1/num_grids_in_phase scaling
+    (intermediate_stage.cpp:140-148): with (a, f) = -R dx + Z[:, u] du - r substituted into the time derivative of the stage
+    Lagrangian  h + hx^T dx + hu^T du + ha^T da + hf^T df,  the coefficients are
+        hx - R^T [ha; -hf],   hu + Z[u, :] [ha; -hf],   h - r^T [ha; -hf]      (no inequality rows: the Qqf term vanishes)
+    with R = Z dIDCdqv, r = Z IDC and Z recomputed here as a dense inverse."""
+    table = rbt_constraint_table()
+    table.barrier, table.fraction_to_boundary = 1e-3, 0.995
+    td, ev, ctrl = small_event_schedule(True)
+    lib, sd, S, K, lin, con, sol, dx0 = _setup(table, ctrl, batch=1, seed=19)
+    kkt, ex, cc = _condense(lib, sd, S, K, table, ctrl, lin, con)
+    nv, nu, nx, npass, nvfm = 18, 12, 36, 6, 30
+    checked = 0
+    for i, c in enumerate(ctrl):
+        if c.type in (IMPACT, TERMINAL) or not c.sto:
+            continue
+        l, k, nf, g1 = lin[0, i], kkt[0, i], c.nf, 1.0 / c.ngrids_in_phase
+        M, J = mat(l, S.l_M, nv, nv), mat(l, S.l_J, 12, nv)[:nf]
+        Z = np.linalg.inv(np.block([[M, J.T], [J, np.zeros((nf, nf))]]))
+        D, IDC = mat(l, S.l_D, nvfm, nx)[:nv + nf], l[S.l_IDC:S.l_IDC + nv + nf]
+        R, r = Z @ D, Z @ IDC
+        haf = np.concatenate([l[S.l_ha:S.l_ha + nv], -l[S.l_hf:S.l_hf + nf]])
+        hx = (l[S.l_hx:S.l_hx + nx] - R.T @ haf) * g1
+        hu = (l[S.l_hu:S.l_hu + nu] + Z[npass:npass + nu, :] @ haf) * g1
+        h = (l[S.l_sc + 0] - r @ haf) * g1
+        assert np.allclose(k[K.k_hx:K.k_hx + nx], hx, rtol=1e-10, atol=1e-12), f"hx, grid {i}"
+        assert np.allclose(k[K.k_hu:K.k_hu + nu], hu, rtol=1e-10, atol=1e-12), f"hu, grid {i}"
+        assert np.isclose(k[K.k_sc + 2], h, rtol=1e-10, atol=1e-12), f"h, grid {i}"
+        assert np.isclose(k[K.k_sc + 0], l[S.l_sc + 1] * g1 * g1) and np.isclose(k[K.k_sc + 1], -k[K.k_sc + 0])
+        fx = l[S.l_fx:S.l_fx + nx].copy()  # fq head corrected on SE(3): E fq' = -fq  (state_equation.cpp:85)
+        E = mat(l, S.l_se3 + 72, 6, 6)
+        got = k[K.k_fx:K.k_fx + nx] / g1
+        assert np.allclose(E @ got[:6], -fx[:6], rtol=1e-10, atol=1e-12) and np.allclose(got[6:], fx[6:], rtol=1e-12, atol=0)
+        checked += 1
+    assert checked >= 8
