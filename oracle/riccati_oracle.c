@@ -29,6 +29,7 @@
 
 int orc_debug_exact_chi = 0; /* see the switching-constraint STO terms below; never set outside the tests */
 int orc_debug_exact_transition = 0; /* phase transition with the rank-one term of P (tests only), see phase_transition() */
+int orc_debug_exact_impact_costate = 0; /* costate at an impact grid with -Phi * (this event's dts) (tests only) */
 
 /* C(m x n) = beta*C + alpha * op(A) * op(B);  ta/tb: 0 = as is, 1 = transposed.
  * Loop forms are chosen so that gcc vectorises them (column axpy for op(A)=A, simd dot products over contiguous
@@ -502,7 +503,11 @@ static void costate_direction(const rbt_layout* L, const double* r, double* d, i
   for (int i = 0; i < nx; ++i) dl[i] -= r[L->r_s + i];
   const double dts = d[L->d_dts], dtsn = d[L->d_dts + 1];
   if (impact_form) {
-    if (sto) for (int i = 0; i < nx; ++i) dl[i] -= r[L->r_Phi + i] * dtsn;
+    /* NB: at the impact grid the forward sweep holds (dts, dts_next) = (this event's increment, 0 or the next event's), and
+     * the value function there depends on THIS event's increment through Phi; the reference multiplies Phi by dts_next
+     * (:262-264).  Restated as it is; orc_debug_exact_impact_costate = 1 (tests only) uses dts, which makes the costate
+     * the multiplier of the KKT system (tests/test_oracle_condense.py, test_oracle_kkt.py). */
+    if (sto) for (int i = 0; i < nx; ++i) dl[i] -= r[L->r_Phi + i] * (orc_debug_exact_impact_costate ? dts : dtsn);
   } else if (sto) {
     for (int i = 0; i < nx; ++i) dl[i] += r[L->r_Psi + i] * (dtsn - dts);
     if (sto_next) for (int i = 0; i < nx; ++i) dl[i] -= r[L->r_Phi + i] * dtsn;

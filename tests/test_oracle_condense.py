@@ -206,22 +206,34 @@ def test_expand_update_consistency():
         assert np.allclose(cc2[b][inter][:, S.c_slack:S.c_slack + S.nc], (sl[b] + a * dsl[b])[inter])
 
 
-def test_dual_expansion_satisfies_uncondensed_stationarity():
+@pytest.mark.parametrize("sto", [False, True])
+def test_dual_expansion_satisfies_uncondensed_stationarity(sto):
     """expandContactDynamicsDual (contact_dynamics.cpp:177-202) pinned without its formulas: the multiplier directions it
     returns make the UNCONDENSED stage Lagrangian stationary in the eliminated variables,
         d/da : la' + Qaa' da + M dbeta + J^T dmu + dt dgmm+ (+ Phia^T dxi)            = 0
         d/df : lf' + Qff' df + Qqf'^T dq - J dbeta                                      = 0
         d/du : lu' + Quu' du - dbeta[actuated]                                          = 0
+      (with switching-time optimisation each gets + dts * (ha | hf | hu), dts = (dts_next - dts) / num_grids_in_phase)
         passive joints : lu_passive - dbeta[passive] + dnu_passive                      = 0   (*)
     where ' marks the cost terms plus the PDIPM terms of the inequality rows (recomputed here as J^T diag(z/s) J and
     J^T cond).  Intermediate and lift stages incl. the switching-constraint stage of an ANYmal schedule.
     (*) on a switching-constraint stage the reference's dnu_passive (contact_dynamics.cpp:182-189) has no dxi term although
-    dbeta does (:193-195), so there the residual is Z[passive, a] Phia^T dxi instead of 0 -- restated, and asserted as such."""
+    dbeta does (:193-195), so there the residual is Z[passive, a] Phia^T dxi instead of 0 -- restated, and asserted as such;
+    the same holds for the dts * haf term (:197-200)."""
     table = anymal_constraint_table()
-    td, ev, ctrl = small_event_schedule(False)
+    td, ev, ctrl = small_event_schedule(sto)  # sto: the stage terms get + dts * (ha, hf), dts = (dts_next - dts) / N_phase
     lib, sd, S, K, lin, con, sol, dx0 = _setup(table, ctrl, batch=2, seed=13)
     kkt, ex, cc = _condense(lib, sd, S, K, table, ctrl, lin, con)
-    kk, ric, d, info = oracle_lib.riccati_batch(ANYMAL, K, ctrl, kkt, dx0)
+    # with STO the Riccati step is made the exact Newton step (test-only switches, see test_oracle_kkt.py): the reference's
+    # own approximations in the phase transition would otherwise show up as stationarity residuals next to a transition
+    flags = [ctypes.c_int.in_dll(lib, n) for n in ("orc_debug_exact_chi", "orc_debug_exact_transition", "orc_debug_exact_impact_costate")]
+    try:
+        for f in flags:
+            f.value = int(sto)
+        kk, ric, d, info = oracle_lib.riccati_batch(ANYMAL, K, ctrl, kkt, dx0, max_dts0=1e9 if sto else 0.1)
+    finally:
+        for f in flags:
+            f.value = 0
     assert info == 0
     batch, n_grid = 2, len(ctrl)
     xd, steps = np.zeros((batch, n_grid, S.x_stride)), np.zeros((batch, 2))
@@ -286,17 +298,22 @@ def test_dual_expansion_satisfies_uncondensed_stationarity():
             dbeta, dmu = x[S.x_dbetamu:S.x_dbetamu + nv], x[S.x_dbetamu + nv:S.x_dbetamu + nv + nf]
             dnup = x[S.x_dnup:S.x_dnup + npass]
             dgmm_n = dn[K.d_dlmdgmm + nv:K.d_dlmdgmm + nx]
-            ra = la + Qaa * da + M @ dbeta + J.T @ dmu + dt * dgmm_n
+            dts = (di[K.d_dts + 1] - di[K.d_dts]) / c.ngrids_in_phase if c.sto else 0.0   # intermediate_stage.cpp:167-170
+            ra = la + Qaa * da + M @ dbeta + J.T @ dmu + dt * dgmm_n + dts * l[S.l_ha:S.l_ha + nv]
+            lf = lf + dts * l[S.l_hf:S.l_hf + nf]
             if c.ns > 0:
                 ra = ra + mat(l, S.l_Phia, c.ns, nv).T @ di[K.d_dxi:K.d_dxi + c.ns]
             scale = max(np.abs(la).max(), np.abs(M @ dbeta).max(), 1.0)
             assert np.abs(ra).max() < 1e-9 * scale, f"d/da stage {i}"
             assert np.abs(lf + Qff @ df + Qqf.T @ dq - J @ dbeta).max() < 1e-9 * max(np.abs(J @ dbeta).max(), 1.0), f"d/df stage {i}"
-            assert np.abs(lu + Quu @ du - dbeta[npass:]).max() < 1e-9 * max(np.abs(dbeta).max(), 1.0), f"d/du stage {i}"
+            ru = lu + Quu @ du - dbeta[npass:] + dts * l[S.l_hu:S.l_hu + nu]
+            assert np.abs(ru).max() < 1e-9 * max(np.abs(dbeta).max(), 1.0), f"d/du stage {i}"
             rp = lup - dbeta[:npass] + dnup
+            Zfull = np.linalg.inv(np.block([[M, J.T], [J, np.zeros((nf, nf))]]))
             if c.ns > 0:
-                Zfull = np.linalg.inv(np.block([[M, J.T], [J, np.zeros((nf, nf))]]))
                 rp = rp - Zfull[:npass, :nv] @ (mat(l, S.l_Phia, c.ns, nv).T @ di[K.d_dxi:K.d_dxi + c.ns])
+            if dts != 0.0:  # (*) likewise the reference's dnu_passive has no dts * haf term
+                rp = rp - Zfull[:npass, :] @ (dts * np.concatenate([l[S.l_ha:S.l_ha + nv], -l[S.l_hf:S.l_hf + nf]]))
             assert np.abs(rp).max() < 1e-9 * max(np.abs(dbeta).max(), 1.0), f"passive stage {i}"
             checked += 1
     assert checked == 2 * (n_grid - 1) and any(c.ns > 0 for c in ctrl) and any(c.type == IMPACT for c in ctrl)

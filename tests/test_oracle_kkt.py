@@ -111,12 +111,13 @@ def test_oracle_sto_direction_solves_full_kkt_single_impact(with_phit):
 
 
 @pytest.mark.parametrize("seed", [5, 7])
-def test_oracle_sto_lift_impact_is_exact_kkt_up_to_two_documented_terms(seed):
+def test_oracle_sto_lift_impact_is_exact_kkt_up_to_three_documented_terms(seed):
     """Lift -> impact with both events STO-enabled, a switching-constraint stage and Phit != 0: the phase transition at the
     lift ELIMINATES the impact's switching time.  The reference's recursion differs from the exact Newton step of the LQ
-    sub-problem in exactly two places -- it keeps riccati_m.P = riccati.P where minimising over the switching time gives
-    P - (Psi-Phi)(Psi-Phi)^T/sgm (riccati_factorizer.cpp:149), and it counts Phit^T mt_next twice in chi (:139) -- and the
-    oracle restates both.  With the two terms put right (orc_debug_exact_* switches, tests only) the oracle's direction,
+    sub-problem in exactly three places -- it keeps riccati_m.P = riccati.P where minimising over the switching time gives
+    P - (Psi-Phi)(Psi-Phi)^T/sgm (riccati_factorizer.cpp:149), it counts Phit^T mt_next twice in chi (:139), and at an impact
+    grid it multiplies Phi by dts_next instead of the event's own dts in the costate (:262-264) -- and the oracle restates
+    all three.  With these put right (orc_debug_exact_* switches, tests only) the oracle's direction, costate included,
     both switching-time increments included, IS the dense KKT solution to 1e-9: every other STO term (stage terms,
     Hamiltonian factorisation, T / W / mt / mt_next, phase transition, STO policy, forward dts propagation, Lagrange
     multipliers) is thereby pinned independently of the Riccati algebra.  As restated (default) the step is within 5e-2."""
@@ -135,7 +136,7 @@ def test_oracle_sto_lift_impact_is_exact_kkt_up_to_two_documented_terms(seed):
     kk, ric, d, info = oracle_lib.riccati_batch(dims, L, ctrl, kkt, dx0, max_dts0=1e9)  # as the reference
     dev = max(rel_err(d[0, i, L.d_dx:L.d_dx + dims.nx], ref[("dx", i)]) for i in range(len(ctrl)))
     assert info == 0 and 1e-6 < dev < 5e-2
-    flags = [ctypes.c_int.in_dll(lib, n) for n in ("orc_debug_exact_chi", "orc_debug_exact_transition")]
+    flags = [ctypes.c_int.in_dll(lib, n) for n in ("orc_debug_exact_chi", "orc_debug_exact_transition", "orc_debug_exact_impact_costate")]
     try:
         for f in flags:
             f.value = 1
@@ -151,8 +152,8 @@ def test_oracle_sto_lift_impact_is_exact_kkt_up_to_two_documented_terms(seed):
             assert rel_err(di[L.d_du:L.d_du + dims.nu], ref[("du", i)]) < 1e-9
         if ("xi", i) in ref:
             assert rel_err(di[L.d_dxi:L.d_dxi + ctrl[i].ns], ref[("xi", i)]) < 1e-7
+        assert rel_err(di[L.d_dlmdgmm:L.d_dlmdgmm + dims.nx], ref[("lmd", i)]) < 1e-8  # (impact grid: third switch)
         if ctrl[i].type != IMPACT and i < len(ctrl) - 1:
-            assert rel_err(di[L.d_dlmdgmm:L.d_dlmdgmm + dims.nx], ref[("lmd", i)]) < 1e-8
             a = ts[phase[i] - 1] if phase[i] >= 1 else 0.0
             b = ts[phase[i]] if phase[i] < n_events else 0.0
             assert abs(di[L.d_dts] - a) < 1e-9 and abs(di[L.d_dts + 1] - b) < 1e-9
