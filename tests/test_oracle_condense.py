@@ -395,3 +395,75 @@ def test_sto_sensitivities_are_the_substituted_hamiltonian_derivatives():
         assert np.allclose(E @ got[:6], -fx[:6], rtol=1e-10, atol=1e-12) and np.allclose(got[6:], fx[6:], rtol=1e-12, atol=0)
         checked += 1
     assert checked >= 8
+
+
+def test_switching_constraint_condensing_is_the_substituted_constraint():
+    """contact_dynamics.cpp:138-153: with da = -R_a dx + Z_au du - r_a substituted into  Phix dx + Phia da + p (+ Phit dt'),
+    the condensed blocks are  Phix - Phia R_a,  Phia Z[a, u],  p - Phia r_a,  (Phit - Phia r_a) / num_grids_in_phase."""
+    table = rbt_constraint_table()
+    table.barrier, table.fraction_to_boundary = 1e-3, 0.995
+    td, ev, ctrl = small_event_schedule(True)
+    lib, sd, S, K, lin, con, sol, dx0 = _setup(table, ctrl, batch=1, seed=23)
+    kkt, ex, cc = _condense(lib, sd, S, K, table, ctrl, lin, con)
+    nv, nu, nx, npass, nvfm = 18, 12, 36, 6, 30
+    seen = 0
+    for i, c in enumerate(ctrl):
+        if c.ns == 0 or c.type in (IMPACT, TERMINAL):
+            continue
+        l, k, nf, ns = lin[0, i], kkt[0, i], c.nf, c.ns
+        M, J = mat(l, S.l_M, nv, nv), mat(l, S.l_J, 12, nv)[:nf]
+        Z = np.linalg.inv(np.block([[M, J.T], [J, np.zeros((nf, nf))]]))
+        R = Z @ mat(l, S.l_D, nvfm, nx)[:nv + nf]
+        r = Z @ l[S.l_IDC:S.l_IDC + nv + nf]
+        Phia = mat(l, S.l_Phia, ns, nv)
+        assert np.allclose(mat(k, K.k_Phix, ns, nx), mat(l, S.l_Phix, ns, nx) - Phia @ R[:nv], rtol=1e-10, atol=1e-12)
+        assert np.allclose(mat(k, K.k_Phiu, ns, nu), Phia @ Z[:nv, npass:npass + nu], rtol=1e-10, atol=1e-12)
+        assert np.allclose(k[K.k_p:K.k_p + ns], l[S.l_p:S.l_p + ns] - Phia @ r[:nv], rtol=1e-10, atol=1e-12)
+        assert np.allclose(k[K.k_Phit:K.k_Phit + ns], (l[S.l_Phit:S.l_Phit + ns] - Phia @ r[:nv]) / c.ngrids_in_phase,
+                           rtol=1e-10, atol=1e-12)
+        seen += 1
+    assert seen == 1
+
+
+def test_constraint_expansion_is_the_linearised_pdipm_system():
+    """expandSlackAndDual (joint_*_limit.cpp:78-83, friction_cone.cpp:238-268, pdipm.hxx:159-164): for every active row
+    g'(x) d + dslack + residual = 0  and  slack*ddual + dual*dslack + (slack*dual - barrier) = 0, with g' rebuilt here from the
+    constraint table and the friction-cone Jacobians; inactive cones get (1, 1) and never bind the step size."""
+    table = anymal_constraint_table()
+    td, ev, ctrl = small_event_schedule(False)
+    lib, sd, S, K, lin, con, sol, dx0 = _setup(table, ctrl, batch=1, seed=29)
+    kkt, ex, cc = _condense(lib, sd, S, K, table, ctrl, lin, con)
+    kk, ric, d, info = oracle_lib.riccati_batch(ANYMAL, K, ctrl, kkt, dx0)
+    n_grid = len(ctrl)
+    xd, steps = np.zeros((1, n_grid, S.x_stride)), np.zeros((1, 2))
+    csd = sd.c()
+    lib.orc_expand_batch(ctypes.byref(csd), ctypes.byref(table), ctrl, n_grid, 1, oracle_lib.ptr(lin), oracle_lib.ptr(ex),
+                         oracle_lib.ptr(d), oracle_lib.ptr(cc), oracle_lib.ptr(xd), oracle_lib.ptr(steps), 1)
+    nv, nu = 18, 12
+    lo_p, lo_d = 1.0, 1.0
+    for i, c in enumerate(ctrl):
+        if c.type in (IMPACT, TERMINAL):
+            continue
+        l, di, x, cr = lin[0, i], d[0, i], xd[0, i], cc[0, i]
+        sl, du_, rs, cm, ds, dd = (cr[o:o + S.nc] for o in (S.c_slack, S.c_dual, S.c_res, S.c_cmpl, S.c_dslack, S.c_ddual))
+        var = {0: di[K.d_dx:K.d_dx + nv], 1: di[K.d_dx + nv:K.d_dx + 2 * nv], 2: x[S.x_daf:S.x_daf + nv], 3: di[K.d_du:K.d_du + nu]}
+        gd = np.zeros(S.nc)
+        active = np.ones(S.nc, bool)
+        for r in range(table.n_box):
+            gd[r] = table.box[r].sign * var[table.box[r].var][table.box[r].idx]
+        fst = 0
+        for ci in range(table.n_contacts):
+            rows = slice(table.n_box + 5 * ci, table.n_box + 5 * ci + 5)
+            if not (c.contact_mask >> ci) & 1:
+                active[rows] = False
+                assert np.all(ds[rows] == 1.0) and np.all(dd[rows] == 1.0)
+                continue
+            gd[rows] = mat(l, S.l_dgdq + ci * 5 * nv, 5, nv) @ var[0] + mat(l, S.l_dgdf + ci * 15, 5, 3) @ x[S.x_daf + nv + fst:S.x_daf + nv + fst + 3]
+            fst += 3
+        assert np.allclose((gd + ds + rs)[active], 0, atol=1e-11)
+        assert np.allclose((sl * dd + du_ * ds + (sl * du_ - table.barrier))[active], 0, atol=1e-11)
+        assert np.allclose(cm[active], (sl * du_ - table.barrier)[active], rtol=1e-13)
+        fp, fd = -table.fraction_to_boundary * (sl / ds), -table.fraction_to_boundary * (du_ / dd)
+        lo_p = min([lo_p] + [f for f in fp if 0 < f < 1])
+        lo_d = min([lo_d] + [f for f in fd if 0 < f < 1])
+    assert steps[0, 0] == lo_p and steps[0, 1] == lo_d
