@@ -157,3 +157,54 @@ def test_oracle_sto_lift_impact_is_exact_kkt_up_to_three_documented_terms(seed):
             a = ts[phase[i] - 1] if phase[i] >= 1 else 0.0
             b = ts[phase[i]] if phase[i] < n_events else 0.0
             assert abs(di[L.d_dts] - a) < 1e-9 and abs(di[L.d_dts + 1] - b) < 1e-9
+
+
+def test_unconstr_oracle_direction_solves_full_kkt():
+    """Unconstrained (iiwa14) Riccati oracle (unconstr_riccati_recursion.cpp:26-48 and factorizers) against a dense solve of
+    the LQ KKT system with the implicit dynamics  x+ = [[I, dt I],[0, I]] x + [0; dt I] a + Fx."""
+    from robotoc_b200.layout import ULayout
+    from robotoc_b200.synth import make_unconstr_kkt, mat
+    nv, N, dt = 7, 12, 0.05
+    nx = 2 * nv
+    lib = oracle_lib.load()
+    UL = ULayout(nv, getter=lib.orc_ulayout_get)
+    kkt, dx0 = make_unconstr_kkt(nv, UL, N, 2, 31)
+    kk, ric, d, info = oracle_lib.unconstr_batch(nv, UL, N, dt, kkt, dx0)
+    assert info == 0
+    A = np.block([[np.eye(nv), dt * np.eye(nv)], [np.zeros((nv, nv)), np.eye(nv)]])
+    B = np.vstack([np.zeros((nv, nv)), dt * np.eye(nv)])
+    for b in range(2):
+        idx, n = {}, 0
+        for i in range(N + 1):
+            for name, size in (("dx", nx), ("lmd", nx)) + ((("da", nv),) if i < N else ()):
+                idx[(name, i)] = slice(n, n + size)
+                n += size
+        Kmat, rhs, I = np.zeros((n, n)), np.zeros(n), np.eye(nx)
+        for i in range(N + 1):
+            rec = kkt[b, i]
+            sx, sl = idx[("dx", i)], idx[("lmd", i)]
+            Kmat[sx, sx] += mat(rec, UL.k_Qxx, nx, nx)
+            Kmat[sx, sl] += -I
+            rhs[sx] += -rec[UL.k_lx:UL.k_lx + nx]
+            if i == 0:
+                Kmat[sl, sx] += I
+                rhs[sl] += dx0[b]
+            if i < N:
+                sa, sxn, sln = idx[("da", i)], idx[("dx", i + 1)], idx[("lmd", i + 1)]
+                Qxa = mat(rec, UL.k_Qxu, nx, nv)
+                Kmat[sx, sa] += Qxa
+                Kmat[sa, sx] += Qxa.T
+                Kmat[sa, sa] += mat(rec, UL.k_Qaa, nv, nv)
+                rhs[sa] += -rec[UL.k_la:UL.k_la + nv]
+                Kmat[sx, sln] += A.T
+                Kmat[sln, sx] += A
+                Kmat[sa, sln] += B.T
+                Kmat[sln, sa] += B
+                Kmat[sln, sxn] += -I
+                rhs[sln] += -rec[UL.k_Fx:UL.k_Fx + nx]
+        sol = np.linalg.solve(Kmat, rhs)
+        for i in range(N + 1):
+            assert rel_err(d[b, i, UL.d_dx:UL.d_dx + nx], sol[idx[("dx", i)]]) < 1e-9
+            assert rel_err(d[b, i, UL.d_dlmdgmm:UL.d_dlmdgmm + nx], sol[idx[("lmd", i)]]) < 1e-8
+            if i < N:
+                assert rel_err(d[b, i, UL.d_da:UL.d_da + nv], sol[idx[("da", i)]]) < 1e-9
