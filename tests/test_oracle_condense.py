@@ -467,3 +467,44 @@ def test_constraint_expansion_is_the_linearised_pdipm_system():
         lo_p = min([lo_p] + [f for f in fp if 0 < f < 1])
         lo_d = min([lo_d] + [f for f in fd if 0 < f < 1])
     assert steps[0, 0] == lo_p and steps[0, 1] == lo_d
+
+
+def test_free_flyer_integration_is_the_se3_exponential():
+    """SplitSolution::integrate on the floating base (robot.integrateConfiguration, Pinocchio's free-flyer joint:
+    q (+) v = q * exp6(v)), restated in oracle/condense_oracle.c without Pinocchio -- checked here against an independent
+    construction with scipy's Rotation: R+ = R exp(w^),  p+ = p + R V(w) v,  V = I + (1-cos t)/t^2 w^ + (t - sin t)/t^3 w^^2."""
+    from scipy.spatial.transform import Rotation
+    table = anymal_constraint_table()
+    td, ev, ctrl = small_event_schedule(False)
+    lib, sd, S, K, lin, con, sol, dx0 = _setup(table, ctrl, batch=2, seed=37)
+    kkt, ex, cc = _condense(lib, sd, S, K, table, ctrl, lin, con)
+    kk, ric, d, info = oracle_lib.riccati_batch(ANYMAL, K, ctrl, kkt, dx0)
+    batch, n_grid = 2, len(ctrl)
+    xd, steps = np.zeros((batch, n_grid, S.x_stride)), np.zeros((batch, 2))
+    csd = sd.c()
+    lib.orc_expand_batch(ctypes.byref(csd), ctypes.byref(table), ctrl, n_grid, batch, oracle_lib.ptr(lin), oracle_lib.ptr(ex),
+                         oracle_lib.ptr(d), oracle_lib.ptr(cc), oracle_lib.ptr(xd), oracle_lib.ptr(steps), 1)
+    d[:, :, K.d_dx:K.d_dx + 6] *= 25.0  # make the rotation large enough to exercise the trigonometric branch
+    sol2 = sol.copy()
+    lib.orc_update_batch(ctypes.byref(csd), ctypes.byref(table), ctrl, n_grid, batch, oracle_lib.ptr(ex), oracle_lib.ptr(d.copy()),
+                         oracle_lib.ptr(xd), oracle_lib.ptr(cc), oracle_lib.ptr(sol2), oracle_lib.ptr(steps), 1)
+
+    def hat(w):
+        return np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
+
+    biggest = 0.0
+    for b in range(batch):
+        a = steps[b, 0]
+        for i in range(n_grid):
+            q0, q1 = sol[b, i, S.s_q:S.s_q + 7], sol2[b, i, S.s_q:S.s_q + 7]
+            v, w = a * d[b, i, K.d_dx:K.d_dx + 3], a * d[b, i, K.d_dx + 3:K.d_dx + 6]
+            t = np.linalg.norm(w)
+            biggest = max(biggest, t)
+            W = hat(w)
+            V = np.eye(3) + (1 - np.cos(t)) / t**2 * W + (t - np.sin(t)) / t**3 * W @ W
+            R0 = Rotation.from_quat(q0[3:7])  # (x, y, z, w), Pinocchio's order
+            p1 = q0[:3] + R0.apply(V @ v)
+            R1 = R0 * Rotation.from_rotvec(w)
+            assert np.allclose(q1[:3], p1, rtol=1e-11, atol=1e-12)
+            assert np.allclose((Rotation.from_quat(q1[3:7]) * R1.inv()).magnitude(), 0.0, atol=1e-11)
+    assert biggest > 0.05
