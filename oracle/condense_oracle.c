@@ -4,12 +4,18 @@
  * primal / dual expansion, fraction-to-boundary step sizes and the primal/dual update.
  *
  * Plain-C restatement of the reference (robotoc @ d30d404), every function citing the lines it follows.
- * PARITY STATUS: the reference cannot be built here (Eigen3 / Pinocchio absent) and holds no golden vectors; this file is
- * pinned by the reference tests' identities re-run with fixed seeds (tests/test_oracle_condense.py: condensed system ==
- * Schur complement of the full uncondensed KKT system, MJtJinv == dense inverse, expansion recovers the eliminated
- * variables).  Robot::computeMJtJinv uses Pinocchio's sparse Cholesky of M; here M is factorised densely (same
- * mathematics, different rounding).  SE(3) integration of the floating base restates the textbook exp map that
- * pinocchio::integrate implements for a free-flyer joint: "parity unpinned" for that piece.
+ * PARITY STATUS: the reference cannot be built here (Eigen3 / Pinocchio absent) and holds no golden vectors: against the
+ * reference BINARY this file is "parity unpinned".  It is pinned by identities that do not reuse its formulas
+ * (tests/test_oracle_condense.py): MJtJinv == dense inverse; condensed quadratic model == uncondensed model with (a, f)
+ * substituted; PDIPM condensing == J^T diag(z/s) J, J^T cond; primal expansion satisfies the linearised contact dynamics;
+ * dual expansion (dbeta, dmu, dnu_passive; intermediate / lift / switching / impact stages, with and without STO) makes the
+ * uncondensed stage Lagrangian stationary in a, f, u and the passive torques; STO sensitivities == substituted Hamiltonian
+ * derivatives; switching-constraint blocks == substituted constraint; slack / dual directions solve the linearised PDIPM
+ * system and the step sizes are the admissible fraction-to-boundary minima; SE(3) state-equation / costate corrections
+ * satisfy E*F = -G; the free-flyer integration equals the SE(3) exponential built with scipy's Rotation.
+ * Robot::computeMJtJinv uses Pinocchio's sparse Cholesky of M; here M is factorised densely (same mathematics, different
+ * rounding).  Where the reference itself departs from the exact expressions (dnu_passive has no dxi / dts term) the
+ * departure is restated and documented in the tests.
  */
 #include <math.h>
 #include <stdlib.h>
