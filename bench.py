@@ -56,7 +56,7 @@ def build_problem(batch, seed):
     """Riccati-only inputs (KKT records) -- used by tools/ and the profiling scripts."""
     from helpers import trot_schedule
     from robotoc_b200 import ANYMAL, Layout
-    from robotoc_b200.synth import make_kkt
+    from synth import make_kkt
     dims = ANYMAL
     L = Layout(dims)
     td, ev, ctrl = trot_schedule(N_HORIZON)
@@ -67,7 +67,7 @@ def build_problem(batch, seed):
 def build_iteration_problem(batch, seed, getter=None, kgetter=None):
     from helpers import trot_schedule
     from robotoc_b200 import ANYMAL, Layout, StageDims, StageLayout, anymal_constraint_table
-    from robotoc_b200.stage import make_stage_inputs, symmetrize_lin
+    from synth import make_stage_inputs, symmetrize_lin
     table = anymal_constraint_table()
     sd = StageDims(ANYMAL, nf_max=12, n_contacts=table.n_contacts, n_box=table.n_box)
     S = StageLayout(sd, getter=getter)
@@ -291,6 +291,17 @@ def main():
     dms.computeStepSizes(stream=sp)
     dms.integrateSolution(sol, stream=sp)
     torch.cuda.synchronize()
+    # ---- parity gate (untimed): EVERY OCP of this rank's batch against the CPU oracle, before anything is timed
+    from iteration_check import compare_final, oracle_iteration
+    t_chk = time.perf_counter()
+    ref = oracle_iteration(pr["sd"], S, K, pr["table"], ctrl, lin, con, sol, dx0)
+    steps_chk = np.stack([dms.maxPrimalStepSize(sp), dms.maxDualStepSize(sp)], axis=1)
+    parity_worst = compare_final(S, K, ctrl, ref, rr.getRiccatiFactorization(sp), d_local.cpu().numpy(), steps_chk,
+                                 dms.getSolution(sp), dms.getConstraintData(sp), tol=1e-8)
+    print(f"[bench] rank {rank}: parity vs oracle on all {args.batch} OCPs: worst rel err {parity_worst:.2e} "
+          f"({time.perf_counter() - t_chk:.1f} s, untimed)", file=sys.stderr, flush=True)
+    d_ref_dir = ref["d_upd"]
+    del ref
     # the update mutates slack/dual and the solution in place: keep pristine copies and restore them every step (D2D)
     con_dev0, sol_dev0 = torch.from_numpy(con).cuda(), torch.from_numpy(sol).cuda()
     con_work, sol_work = con_dev0.clone(), sol_dev0.clone()
@@ -368,6 +379,11 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms = float(tt.item())
     assert int(rr.info().max()) == 0, "Cholesky failure flagged on device"
+    if world > 1:  # config 5: this rank's shard of the gathered step is the step the oracle computes for these OCPs
+        shard = d_all[rank * args.batch:(rank + 1) * args.batch].cpu().numpy()
+        nxu = K.d_dxi
+        err = np.max(np.abs(shard[..., :nxu] - d_ref_dir[..., :nxu])) / np.max(np.abs(d_ref_dir[..., :nxu]))
+        assert err < 1e-8, f"rank {rank}: gathered step disagrees with the oracle ({err:.2e})"
     sol_dev = dms.getSolution()
     steps_dev = np.stack([dms.maxPrimalStepSize(), dms.maxDualStepSize()], axis=1)
 
@@ -431,6 +447,7 @@ def main():
                        "l2": f"per-step working set {(lin.nbytes + rr.buf_doubles(0) * 8 + rr.buf_doubles(1) * 8) / 1e9:.2f} GB "
                              ">> 126 MB L2 (inputs larger than L2; no flush needed)"},
             "clocks": clocks, "gpu_launches": int(launches),
+            "parity": {"checked_ocps": args.batch, "worst_rel_err_vs_oracle": parity_worst, "tol": 1e-8},
             "kernels_ms": kms,
             "riccati_only": {"value": world * args.batch / ((kms["riccati_backward"] + kms["riccati_forward"]) * 1e-3),
                              "unit": "OCP-iterations/s", "note": "backward + forward sweeps only (the parity-checked core, 8d)"},

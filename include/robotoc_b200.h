@@ -91,6 +91,12 @@ int rbt_download(rbt_handle* h, int which, double* host, void* stream);       /*
  * a switching constraint / STO, the unused switching+STO sections) */
 long long rbt_upload_bytes(rbt_handle* h, int which);
 int rbt_download_info(rbt_handle* h, int* host_flags, void* stream);          /* per-OCP Cholesky status */
+/* Synchronises `stream` and turns the per-OCP flags into a return code: RBT_OK if every factorization of the last
+ * condense / backward sweep succeeded, RBT_ERR_NUMERIC otherwise (rbt_last_error names the first failing OCP and the flag:
+ * 1 = Quu + B^T P B not positive definite, 2 = switching-constraint Schur complement, 4 = M, 8 = J M^-1 J^T in the
+ * condensing).  The reference only asserts here (assert(llt_.info() == Eigen::Success), riccati_factorizer.cpp:50,64):
+ * the other OCPs of the batch are unaffected and their results are valid.  *first_bad (may be NULL) = index or -1. */
+int rbt_check_info(rbt_handle* h, int* first_bad, void* stream);
 
 /* RiccatiRecursion::backwardRiccatiRecursion(time_discretization, kkt_matrix, kkt_residual, factorization)
  *   src/riccati/riccati_recursion.cpp:32-80.  Reads RBT_BUF_KKT, writes RBT_BUF_RIC (P,s,K,k,M,m,STO terms,

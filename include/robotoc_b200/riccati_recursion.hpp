@@ -43,6 +43,8 @@ struct GridInfo {  // grid_info.hpp:25-92 (fields read on this path)
   int num_grids_in_phase = 1;
   int dims = 0;  // dimension of the switching constraint attached to this grid (impact dimf), 0 if none
   int dimf = 0;  // active contact dimension
+  int contact_mask = -1;  // bit per point contact that is closed on this grid (ContactStatus::isContactActive); must be given
+                          // whenever dimf > 0 -- the library never guesses which feet are on the ground
 };
 using TimeDiscretization = std::vector<GridInfo>;  // size() == N+1 grid points, last one Terminal
 
@@ -189,7 +191,10 @@ class RiccatiRecursion {
       get(f.Psi.data(), r + L_.r_Psi, nx);
       get(f.Phi.data(), r + L_.r_Phi, nx);
       f.xi = r[L_.r_sc + 0]; f.chi = r[L_.r_sc + 1]; f.rho = r[L_.r_sc + 2]; f.eta = r[L_.r_sc + 3]; f.iota = r[L_.r_sc + 4];
-      if (td[i].type == GridType::Terminal || td[i].type == GridType::Impact) continue;
+      if (td[i].type == GridType::Terminal) continue;
+      const double* fc = fact_.data() + size_t(i) * L_.f_stride;  // in-place mutation semantics of the reference
+      get(kkt_matrix[i].Qxx.data(), fc + L_.f_F, nx * nx);        // (impact stages too: riccati_factorizer.cpp:178-186)
+      if (td[i].type == GridType::Impact) continue;
       LQRPolicy& pol = lqr_policy_[i];
       get(pol.Kt.data(), r + L_.r_K, nx * nu);
       get(pol.k.data(), r + L_.r_k, nu);
@@ -202,8 +207,6 @@ class RiccatiRecursion {
         get(f.M_.data(), r + L_.r_M, ns * nx);
         get(f.m_.data(), r + L_.r_m, ns);
       }
-      const double* fc = fact_.data() + size_t(i) * L_.f_stride;  // in-place mutation semantics of the reference
-      get(kkt_matrix[i].Qxx.data(), fc + L_.f_F, nx * nx);
       get(kkt_matrix[i].Qxu.data(), fc + L_.f_H, nx * nu);
       get(kkt_matrix[i].Quu.data(), fc + L_.f_G, nu * nu);
       get(kkt_residual[i].lu.data(), fc + L_.f_lu, nu);
@@ -256,7 +259,9 @@ class RiccatiRecursion {
       c.ns = td[i].switching_constraint ? td[i].dims : 0;
       c.nf = td[i].dimf;
       c.ngrids_in_phase = td[i].num_grids_in_phase;
-      c.contact_mask = (1 << (td[i].dimf / 3)) - 1;
+      if (td[i].contact_mask < 0 && td[i].dimf > 0)
+        throw std::invalid_argument("[RiccatiRecursion] invalid argument: GridInfo::contact_mask must be set when dimf > 0");
+      c.contact_mask = td[i].contact_mask < 0 ? 0 : td[i].contact_mask;
       c.reserved_ = 0;
       c.dt = td[i].dt;
     }
@@ -300,7 +305,14 @@ class DeviceRiccatiRecursion {  // batch-of-one-or-more variant that keeps every
       if (h_) rbt_destroy(h_);
       throw std::runtime_error("[RiccatiRecursion] cannot create the B200 handle: " + msg);
     }
-    check(rbt_set_schedule(h_, ctrl.data(), n_grid_, max_dts0));
+    const int rc = rbt_set_schedule(h_, ctrl.data(), n_grid_, max_dts0);
+    if (rc != RBT_OK) {  // the destructor does not run when a constructor throws: release the handle here
+      const std::string msg = rbt_last_error(h_);
+      rbt_destroy(h_);
+      h_ = nullptr;
+      if (rc == RBT_ERR_ARG) throw std::invalid_argument("[robotoc_b200] invalid argument: " + msg);
+      throw std::runtime_error("[robotoc_b200] " + msg);
+    }
   }
   ~DeviceRiccatiRecursion() { if (h_) rbt_destroy(h_); }
   DeviceRiccatiRecursion(const DeviceRiccatiRecursion&) = delete;

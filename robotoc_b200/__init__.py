@@ -6,7 +6,7 @@ Host-side Python mirror of the reference interface for the hot path only (SURVEY
 All compute goes through the C ABI of librobotoc_b200.so (include/robotoc_b200.h); there is no CPU path.
 """
 from .layout import Dims, Layout, ULayout  # noqa: F401
-from .schedule import GridInfo, TimeDiscretization, stage_ctrl_array  # noqa: F401
+from .grid import GridInfo, plain_schedule  # noqa: F401
 from .riccati import RiccatiRecursion, UnconstrRiccatiRecursion  # noqa: F401
 from .stage import StageDims, StageLayout, anymal_constraint_table  # noqa: F401
 from .dms import DirectMultipleShooting  # noqa: F401

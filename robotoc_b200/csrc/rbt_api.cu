@@ -69,6 +69,7 @@ struct rbt_handle {
   int cb0 = 0, cnb = 0;
   double* d_wire = nullptr;  // packed host wire records (rbt_iteration_host_wire), allocated on first use
   rbt_wire_layout W;
+  bool attr_bwd = false, attr_fwd = false, attr_cond = false;  // MaxDynamicSharedMemorySize set on THIS handle's device
   cudaEvent_t ev_condense_mid = nullptr;  // caller-owned event recorded between the two kernels of rbt_condense (timing)
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
   std::vector<cudaEvent_t> ev;
@@ -174,6 +175,17 @@ int rbt_create(const rbt_dims* dims, int n_grid_max, int batch, int device, rbt_
 
 static double** buf_slot(rbt_handle* h, int which);
 
+// The stage kernels are compiled for nf_max / n_contacts of the constraint table: every grid of the schedule must fit.
+static int check_contacts(rbt_handle* h, const rbt_stage_ctrl* ctrl, int n_grid) {
+  if (!h->stage_ready) return RBT_OK;
+  for (int i = 0; i < n_grid; ++i)
+    if (ctrl[i].nf > h->sdims.nf_max || ctrl[i].contact_mask >= (1 << h->sdims.n_contacts)) {
+      h->err = "[rbt_set_schedule] invalid argument: grid " + std::to_string(i) + " has more contacts than the stage layer was set up for";
+      return RBT_ERR_ARG;
+    }
+  return RBT_OK;
+}
+
 int rbt_destroy(rbt_handle* h) {
   if (h) {
     cudaFree(h->d_wire);
@@ -215,7 +227,22 @@ int rbt_set_schedule(rbt_handle* h, const rbt_stage_ctrl* ctrl, int n_grid, doub
       h->err = "[rbt_set_schedule] invalid argument: inconsistent stage control table at grid " + std::to_string(i);
       return RBT_ERR_ARG;
     }
+    // contact bookkeeping: the stage kernels index fixed-size shared arrays with nv + nf and use popc(contact_mask) offsets
+    // into the stacked force block, so a table that lies about either is rejected here, not discovered on the device
+    const int nf_max = 3 * RBT_MAX_CONTACTS;
+    if (c.nf < 0 || c.nf > nf_max || c.nf % 3 != 0 || c.contact_mask < 0 || c.contact_mask >= (1 << RBT_MAX_CONTACTS) ||
+        3 * __builtin_popcount((unsigned)c.contact_mask) != c.nf || c.ngrids_in_phase < 0 || !(c.dt >= 0.0) ||
+        !(c.dt < 1.0e300) || (c.sto != 0 && c.sto != 1) || (c.sto_next != 0 && c.sto_next != 1)) {
+      h->err = "[rbt_set_schedule] invalid argument: grid " + std::to_string(i) +
+               ": need 0 <= nf <= 12, nf % 3 == 0, 3 * popcount(contact_mask) == nf, ngrids_in_phase >= 0, finite dt >= 0";
+      return RBT_ERR_ARG;
+    }
+    if (c.type == RBT_IMPACT && c.ns != 0) {
+      h->err = "[rbt_set_schedule] invalid argument: an impact grid carries no switching constraint (grid " + std::to_string(i) + ")";
+      return RBT_ERR_ARG;
+    }
   }
+  if (check_contacts(h, ctrl, n_grid) != RBT_OK) return RBT_ERR_ARG;
   RBT_CUDA(h, cudaSetDevice(h->device));
   RBT_CUDA(h, cudaMemcpy(h->d_ctrl, ctrl, sizeof(rbt_stage_ctrl) * n_grid, cudaMemcpyHostToDevice));
   // stage-conditional outputs (M, STO terms, policies) must not leak from a previous schedule
@@ -389,6 +416,23 @@ int rbt_download_info(rbt_handle* h, int* host_flags, void* stream) {
   return RBT_OK;
 }
 
+int rbt_check_info(rbt_handle* h, int* first_bad, void* stream) {
+  if (!h) return RBT_ERR_ARG;
+  RBT_CUDA(h, cudaSetDevice(h->device));
+  std::vector<int> flags(size_t(h->batch), 0);
+  RBT_CUDA(h, cudaMemcpyAsync(flags.data(), h->d_info, flags.size() * sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  RBT_CUDA(h, cudaStreamSynchronize((cudaStream_t)stream));
+  if (first_bad) *first_bad = -1;
+  for (int b = 0; b < h->batch; ++b)
+    if (flags[size_t(b)]) {
+      if (first_bad) *first_bad = b;
+      h->err = "numerical failure: OCP " + std::to_string(b) + " flag " + std::to_string(flags[size_t(b)]) +
+               " (1: Quu + B^T P B not positive definite, 2: switching-constraint Schur complement, 4: M, 8: J M^-1 J^T in the condensing)";
+      return RBT_ERR_NUMERIC;
+    }
+  return RBT_OK;
+}
+
 template <int NV, int NU, int NS>
 static int launch_backward(rbt_handle* h, int write_fact, cudaStream_t st) {
   using C = rbt::BwdCfg<NV, NU, NS>;
@@ -396,11 +440,10 @@ static int launch_backward(rbt_handle* h, int write_fact, cudaStream_t st) {
     h->err = "internal: shared-memory staging size does not match rbt_layout";
     return RBT_ERR_STATE;
   }
-  static bool attr_done = false;
   auto kern = rbt::riccati_backward_kernel<NV, NU, NS>;
-  if (!attr_done) {
+  if (!h->attr_bwd) {  // the attribute is per device: tracked per handle (a handle lives on one device)
     RBT_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
-    attr_done = true;
+    h->attr_bwd = true;
   }
   rbt::BwdParams p;
   p.L = h->L;
@@ -430,11 +473,10 @@ static int launch_backward(rbt_handle* h, int write_fact, cudaStream_t st) {
 template <int NV, int NU, int NS>
 static int launch_forward(rbt_handle* h, cudaStream_t st) {
   using C = rbt::FwdCfg<NV, NU, NS>;
-  static bool attr_done = false;
   auto kern = rbt::riccati_forward_kernel<NV, NU, NS>;
-  if (!attr_done) {
+  if (!h->attr_fwd) {
     RBT_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
-    attr_done = true;
+    h->attr_fwd = true;
   }
   rbt::FwdParams p;
   p.L = h->L;
@@ -521,8 +563,18 @@ int rbt_stage_setup(rbt_handle* h, const rbt_stage_dims* sd, const rbt_constrain
       }
     }
   }
+  if (h->stage_ready) {  // a second call would leak every stage buffer and leave stale own[] pointers behind a re-bound one
+    h->err = "[rbt_stage_setup] already set up on this handle (create a new handle for another constraint table)";
+    return RBT_ERR_STATE;
+  }
   h->sdims = *sd;
   h->table = *table;
+  h->stage_ready = true;  // (for check_contacts; reset below on failure)
+  if (h->n_grid > 0 && check_contacts(h, h->ctrl.data(), h->n_grid) != RBT_OK) {
+    h->stage_ready = false;
+    return RBT_ERR_ARG;
+  }
+  h->stage_ready = false;
   rbt_make_stage_layout(sd, &h->S);
   {  // condense_kernel lands [l_D, l_Phix) and [l_ha, l_dgdq) of the record in place: the static mirror must match
     using C = rbt::CondCfg<18, 12, 12>;
@@ -613,10 +665,9 @@ int rbt_condense(rbt_handle* h, void* stream) {
   RBT_STAGE_CHECK(h, "rbt_condense");
   using C = rbt::CondCfg<18, 12, 12>;
   auto kern = rbt::condense_kernel<18, 12, 12>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  if (!h->attr_cond) {
     RBT_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
-    attr_done = true;
+    h->attr_cond = true;
   }
   cudaStream_t st = (cudaStream_t)stream;
   const int nb = win_nb(h);

@@ -136,6 +136,12 @@ class RiccatiRecursion:
         self.synchronize(stream)
         return flags
 
+    def checkInfo(self, stream=None):
+        """Raises RuntimeError (RBT_ERR_NUMERIC) if a factorization of the last condense / backward sweep failed -- where
+        the reference asserts llt_.info() == Eigen::Success (riccati_factorizer.cpp:50,64).  Returns None otherwise."""
+        first = ctypes.c_int(-1)
+        _check(self._lib.rbt_check_info(self._h, ctypes.byref(first), stream), self._err, "RiccatiRecursion")
+
     def synchronize(self, stream=None):
         _check(self._lib.rbt_sync(self._h, stream), self._err, "RiccatiRecursion")
 

@@ -48,55 +48,6 @@ class UStageLayout:
             setattr(self, f, v)
 
 
-def make_unconstr_stage_inputs(S: UStageLayout, N: int, batch: int, seed: int):
-    """Synthetic linearization / PDIPM / solution records (no Pinocchio here): dID_da = M SPD, dense dID_dq / dID_dv,
-    diagonal cost Hessians as ConfigurationSpaceCost produces them, slack / dual > 0."""
-    rng = np.random.default_rng(seed)
-    nv, nx = S.nv, S.nx
-    u = lambda *shape: rng.uniform(-1.0, 1.0, size=shape)  # noqa: E731
-    lin = np.zeros((batch, N + 1, S.l_stride))
-    con = np.zeros((batch, N + 1, S.c_stride))
-    sol = np.zeros((batch, N + 1, S.s_stride))
-
-    def putm(rec, off, block):  # block[b, i, j] -> column-major
-        b, m, n = block.shape
-        rec[:, off:off + m * n] = np.transpose(block, (0, 2, 1)).reshape(b, m * n)
-
-    for i in range(N + 1):
-        rec = lin[:, i, :]
-        Qxx = np.zeros((batch, nx, nx))
-        Qxx[:, np.arange(nx), np.arange(nx)] = rng.uniform(0.01, 10.0, size=(batch, nx))
-        if i % 3 == 0:  # a dense symmetric part (task-space costs)
-            T = u(batch, nx, nx)
-            Qxx += 0.05 * T @ np.transpose(T, (0, 2, 1))
-        putm(rec, S.l_Qxx, Qxx)
-        rec[:, S.l_lx:S.l_lx + nx] = u(batch, nx)
-        for off in (S.s_q, S.s_v, S.s_a, S.s_u, S.s_beta, S.s_lmd, S.s_gmm):
-            sol[:, i, off:off + nv] = u(batch, nv)
-        if i == N:
-            continue
-        Sm = u(batch, nv, nv)
-        putm(rec, S.l_dIDda, np.eye(nv)[None] + 0.2 * Sm @ np.transpose(Sm, (0, 2, 1)))
-        putm(rec, S.l_dIDdq, u(batch, nv, nv))
-        putm(rec, S.l_dIDdv, 0.3 * u(batch, nv, nv))
-        rec[:, S.l_ID:S.l_ID + nv] = 0.5 * u(batch, nv)
-        Qaa = np.zeros((batch, nv, nv))
-        Qaa[:, np.arange(nv), np.arange(nv)] = rng.uniform(0.01, 1.0, size=(batch, nv))
-        putm(rec, S.l_Qaa, Qaa)
-        Quu = np.zeros((batch, nv, nv))
-        Quu[:, np.arange(nv), np.arange(nv)] = rng.uniform(0.01, 1.0, size=(batch, nv))
-        putm(rec, S.l_Quu, Quu)
-        rec[:, S.l_la:S.l_la + nv] = u(batch, nv)
-        rec[:, S.l_lu:S.l_lu + nv] = u(batch, nv)
-        rec[:, S.l_Fx:S.l_Fx + nx] = 0.1 * u(batch, nx)
-        nb = S.nbox
-        con[:, i, S.c_slack:S.c_slack + nb] = rng.uniform(0.01, 1.0, size=(batch, nb))
-        con[:, i, S.c_dual:S.c_dual + nb] = rng.uniform(0.01, 1.0, size=(batch, nb))
-        con[:, i, S.c_res:S.c_res + nb] = 0.1 * u(batch, nb)
-    dx0 = 0.1 * u(batch, nx)
-    return np.ascontiguousarray(lin), np.ascontiguousarray(con), np.ascontiguousarray(sol), np.ascontiguousarray(dx0)
-
-
 class UnconstrDirectMultipleShooting:
     def __init__(self, riccati: UnconstrRiccatiRecursion, table):
         self.rr = riccati

@@ -48,7 +48,7 @@ int main() {
   const GridType types[12] = {GridType::Intermediate, GridType::Intermediate, GridType::Lift, GridType::Intermediate,
                               GridType::Intermediate, GridType::Intermediate, GridType::Impact, GridType::Intermediate,
                               GridType::Intermediate, GridType::Intermediate, GridType::Intermediate, GridType::Terminal};
-  for (int i = 0; i < 12; ++i) { td[i].type = types[i]; td[i].dt = (types[i] == GridType::Impact || i == 11) ? 0.0 : 0.05; td[i].dimf = 12; }
+  for (int i = 0; i < 12; ++i) { td[i].type = types[i]; td[i].dt = (types[i] == GridType::Impact || i == 11) ? 0.0 : 0.05; td[i].dimf = 12; td[i].contact_mask = 0b1111; }
   td[4].switching_constraint = true; td[4].dims = ns;  // grid i+2 is the Impact
   const int n_grid = 12;
   KKTMatrix kkt_matrix(n_grid, SplitKKTMatrix(nv, nu, 12));

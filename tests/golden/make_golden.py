@@ -21,8 +21,9 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import oracle_lib  # noqa: E402
 from helpers import small_event_schedule  # noqa: E402
 from robotoc_b200 import ANYMAL, Layout, ULayout  # noqa: E402
-from robotoc_b200.stage import StageDims, StageLayout, anymal_constraint_table, make_stage_inputs  # noqa: E402
-from robotoc_b200.synth import make_kkt, make_unconstr_kkt  # noqa: E402
+from robotoc_b200.stage import StageDims, StageLayout, anymal_constraint_table  # noqa: E402
+from synth import make_stage_inputs  # noqa: E402
+from synth import make_kkt, make_unconstr_kkt  # noqa: E402
 
 SEEDS = {"riccati": 101, "riccati_sto": 102, "unconstr": 103, "iteration": 104, "iteration_sto": 105, "unconstr_iteration": 106}
 
@@ -48,7 +49,8 @@ def unconstr_case():
 
 def unconstr_iteration_case():
     """Full unconstrained iteration (iiwa14, N=20, batch 2): condense -> Riccati -> step sizes -> update."""
-    from robotoc_b200.unconstr_dms import UStageLayout, iiwa14_constraint_table, make_unconstr_stage_inputs
+    from robotoc_b200.unconstr_dms import UStageLayout, iiwa14_constraint_table
+    from synth import make_unconstr_stage_inputs
     lib = oracle_lib.load()
     tab = iiwa14_constraint_table()
     S = UStageLayout(7, tab.n_box, getter=lib.orc_ustage_layout_get)

@@ -2,9 +2,10 @@
 import numpy as np
 
 from robotoc_b200 import ANYMAL, Layout
-from robotoc_b200.schedule import (ContactEvents, TimeDiscretization, stage_ctrl_array, anymal_trot_events,
-                                   anymal_jump_sto_events, IMPACT, LIFT, TERMINAL)
-from robotoc_b200.synth import make_kkt, mat
+from robotoc_b200.grid import IMPACT, LIFT, TERMINAL
+from schedule_fixture import (ContactEvents, TimeDiscretization, stage_ctrl_array, anymal_trot_events,
+                              anymal_jump_sto_events)
+from synth import make_kkt, mat
 
 
 def small_event_schedule(sto=False):

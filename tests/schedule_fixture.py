@@ -1,38 +1,19 @@
-"""Host-side control-table producer.
+"""TEST FIXTURE (not product code): control-table producer for the BASELINE schedules.
 
 Restates robotoc::TimeDiscretization::discretize / correctTimeSteps
 (/root/reference/src/ocp/time_discretization.cpp:43-262) and the event bookkeeping of
 robotoc::ContactSequence (/root/reference/src/planner/contact_sequence.cpp:55-95) as far as the
 kernels need it: the per-grid-point GridInfo (grid_info.hpp:25-92) and, from it, the rbt_stage_ctrl
-table shared by a batch of OCPs.  This stays on the host in the reference as well.
+table shared by a batch of OCPs.  A real drop-in takes GridInfo from robotoc's own class.
 """
 import math
 from dataclasses import dataclass, field
-from typing import List, Sequence
+from typing import List
 
-from . import _lib
+from robotoc_b200 import _lib
+from robotoc_b200.grid import GridInfo, INTERMEDIATE, IMPACT, LIFT, TERMINAL, plain_schedule  # noqa: F401
 
-INTERMEDIATE, IMPACT, LIFT, TERMINAL = 0, 1, 2, 3  # robotoc::GridType order (grid_info.hpp:14-19)
 _EPS = math.sqrt(2.220446049250313e-16)
-
-
-@dataclass
-class GridInfo:
-    """Field-for-field mirror of robotoc::GridInfo (grid_info.hpp:25-92)."""
-    type: int = INTERMEDIATE
-    t0: float = 0.0
-    t: float = 0.0
-    dt: float = 0.0
-    dt_next: float = 0.0
-    phase: int = 0
-    stage: int = 0
-    impact_index: int = -1
-    lift_index: int = -1
-    stage_in_phase: int = 0
-    num_grids_in_phase: int = 0
-    sto: bool = False
-    sto_next: bool = False
-    switching_constraint: bool = False
 
 
 @dataclass
@@ -55,12 +36,16 @@ class ContactEvents:
             self.impact_times.append(time)
             self.sto_impact.append(sto)
             self.impact_dimf.append(impact_dimf)
-            self.impact_mask.append(impact_mask if impact_mask else (1 << (impact_dimf // 3)) - 1)
+            if 3 * bin(impact_mask).count("1") != impact_dimf:
+                raise ValueError("[ContactEvents] impact_mask must name exactly impact_dimf / 3 contacts")
+            self.impact_mask.append(impact_mask)
         else:
             self.lift_times.append(time)
             self.sto_lift.append(sto)
         self.phase_dimf.append(post_dimf)
-        self.phase_mask.append(post_mask if post_mask is not None else (1 << (post_dimf // 3)) - 1)
+        if post_mask is None or 3 * bin(post_mask).count("1") != post_dimf:
+            raise ValueError("[ContactEvents] post_mask must be given and name exactly post_dimf / 3 contacts")
+        self.phase_mask.append(post_mask)
 
 
 class TimeDiscretization:
@@ -85,8 +70,8 @@ class TimeDiscretization:
         return self.grid[i]
 
     def discretize(self, ev: ContactEvents, t: float = 0.0, sto: bool = True):
-        """discretize (time_discretization.cpp:43-183) followed by the STO flag pass of
-        correctTimeSteps (:219-262).  Time steps are left as produced by discretize."""
+        """discretize (time_discretization.cpp:43-183); with sto=True followed by correctTimeSteps (:186-262): the
+        per-phase uniform time steps and the STO flags, as OCPSolver applies it to PhaseBased / STO problems."""
         T, N_ = self.T, self.N
         n_imp, n_lift = len(ev.impact_times), len(ev.lift_times)
         size = N_ + n_lift + 2 * n_imp + 1
@@ -180,8 +165,42 @@ class TimeDiscretization:
         self.grid = g[:ng + 1]
         self.num_grids = ng
         if sto:
+            self._correct_time_steps(ev, t)
             self._set_sto(ev)
         return self
+
+    def _correct_time_steps(self, ev: ContactEvents, t: float):
+        """Per-phase uniform dt / t: time_discretization.cpp:186-225."""
+        g, ng = self.grid, self.num_grids
+        prev_stage, prev_time = 0, t
+        i = 0
+        while i < ng:
+            if g[i].type == IMPACT:
+                et = ev.impact_times[g[i + 1].impact_index]
+                dt = (et - prev_time) / g[i - 1].num_grids_in_phase
+                for j in range(prev_stage, i):
+                    g[j].t = prev_time + (j - prev_stage) * dt
+                    g[j].dt = dt
+                g[i].t, g[i].dt = et, 0.0
+                prev_time, prev_stage = et, i + 1
+                i += 1
+            elif g[i + 1].type == LIFT:
+                et = ev.lift_times[g[i + 1].lift_index]
+                dt = (et - prev_time) / g[i].num_grids_in_phase
+                for j in range(prev_stage, i + 1):
+                    g[j].t = prev_time + (j - prev_stage) * dt
+                    g[j].dt = dt
+                prev_time, prev_stage = et, i + 1
+            elif g[i + 1].type == TERMINAL:
+                dt = (t + self.T - prev_time) / g[i].num_grids_in_phase
+                for j in range(prev_stage, i + 1):
+                    g[j].t = prev_time + (j - prev_stage) * dt
+                    g[j].dt = dt
+            i += 1
+        g[ng].t, g[ng].dt = t + self.T, 0.0
+        for i in range(ng):
+            g[i].dt_next = g[i + 1].dt
+        g[ng].dt_next = 0.0
 
     def _set_sto(self, ev: ContactEvents):
         """STO flags: time_discretization.cpp:228-261."""
@@ -226,18 +245,6 @@ def stage_ctrl_array(td: TimeDiscretization, ev: ContactEvents):
             c.contact_mask = ev.phase_mask[gi.phase] if gi.phase < len(ev.phase_mask) else 0
         c.ngrids_in_phase = gi.num_grids_in_phase
         c.dt = gi.dt
-    return arr
-
-
-def plain_schedule(N: int, dt: float, nf: int = 0):
-    """N Intermediate stages + Terminal, no events (e.g. a standing robot)."""
-    arr = (_lib.rbt_stage_ctrl * (N + 1))()
-    for i in range(N + 1):
-        arr[i].type = INTERMEDIATE if i < N else TERMINAL
-        arr[i].dt = dt if i < N else 0.0
-        arr[i].nf = nf
-        arr[i].contact_mask = (1 << (nf // 3)) - 1
-        arr[i].ngrids_in_phase = N if i < N else 0
     return arr
 
 

@@ -41,8 +41,8 @@ def test_cuda_reproduces_golden():
     from helpers import small_event_schedule
     from robotoc_b200 import (ANYMAL, DirectMultipleShooting, Layout, RiccatiRecursion, StageDims, StageLayout, ULayout,
                               UnconstrRiccatiRecursion, anymal_constraint_table)
-    from robotoc_b200.stage import make_stage_inputs
-    from robotoc_b200.synth import make_kkt, make_unconstr_kkt
+    from synth import make_stage_inputs
+    from synth import make_kkt, make_unconstr_kkt
     L = Layout(ANYMAL)
     for sto, kr, kd in ((False, "ric", "d"), (True, "ric_sto", "d_sto")):
         td, ev, ctrl = small_event_schedule(sto)
@@ -81,7 +81,7 @@ def test_cuda_reproduces_golden():
         rr.close()
     # unconstrained full iteration (iiwa14)
     from robotoc_b200 import UnconstrDirectMultipleShooting, iiwa14_constraint_table
-    from robotoc_b200.unconstr_dms import make_unconstr_stage_inputs
+    from synth import make_unconstr_stage_inputs
     tab = iiwa14_constraint_table()
     ur = UnconstrRiccatiRecursion(7, 20, 0.05, 2)
     udms = UnconstrDirectMultipleShooting(ur, tab)

@@ -6,8 +6,8 @@ import pytest
 import oracle_lib
 from helpers import jump_sto_schedule, rel_err, small_event_schedule, trot_schedule
 from robotoc_b200 import ANYMAL, Layout, RiccatiRecursion, ULayout, UnconstrRiccatiRecursion
-from robotoc_b200.schedule import IMPACT
-from robotoc_b200.synth import make_kkt, make_unconstr_kkt
+from robotoc_b200.grid import IMPACT
+from synth import make_kkt, make_unconstr_kkt
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-8

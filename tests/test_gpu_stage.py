@@ -10,8 +10,8 @@ import pytest
 import oracle_lib
 from helpers import jump_sto_schedule, rel_err, small_event_schedule, trot_schedule
 from robotoc_b200 import ANYMAL, DirectMultipleShooting, Layout, RiccatiRecursion, StageDims, StageLayout, anymal_constraint_table
-from robotoc_b200.schedule import IMPACT, TERMINAL
-from robotoc_b200.stage import make_stage_inputs, symmetrize_lin
+from robotoc_b200.grid import IMPACT, TERMINAL
+from synth import make_stage_inputs, symmetrize_lin
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-8

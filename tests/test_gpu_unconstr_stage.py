@@ -7,7 +7,7 @@ import oracle_lib
 from helpers import rel_err
 from robotoc_b200 import UnconstrDirectMultipleShooting, UnconstrRiccatiRecursion, iiwa14_constraint_table
 from robotoc_b200.layout import ULayout
-from robotoc_b200.unconstr_dms import make_unconstr_stage_inputs
+from synth import make_unconstr_stage_inputs
 
 pytestmark = pytest.mark.gpu
 NV = 7

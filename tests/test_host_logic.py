@@ -9,7 +9,7 @@ import pytest
 import oracle_lib
 from helpers import jump_sto_schedule, small_event_schedule, trot_schedule
 from robotoc_b200 import ANYMAL, Layout, ULayout, _lib
-from robotoc_b200.schedule import IMPACT, INTERMEDIATE, LIFT, TERMINAL
+from robotoc_b200.grid import IMPACT, INTERMEDIATE, LIFT, TERMINAL
 from robotoc_b200.shard import shard_range
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -118,7 +118,7 @@ def test_wire_format_pack_is_documented_packed_upper_storage():
     import ctypes
     from robotoc_b200 import ANYMAL, StageDims, StageLayout, anymal_constraint_table
     from robotoc_b200._lib import lib
-    from robotoc_b200.stage import make_stage_inputs, symmetrize_lin
+    from synth import make_stage_inputs, symmetrize_lin
     from helpers import small_event_schedule
     L = lib()
     tab = anymal_constraint_table()

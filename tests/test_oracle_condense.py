@@ -13,9 +13,10 @@ import pytest
 import oracle_lib
 from helpers import small_event_schedule
 from robotoc_b200 import ANYMAL, Layout
-from robotoc_b200.schedule import IMPACT, TERMINAL, plain_schedule
-from robotoc_b200.stage import (StageDims, StageLayout, anymal_constraint_table, make_stage_inputs, rbt_constraint_table)
-from robotoc_b200.synth import mat
+from robotoc_b200.grid import IMPACT, TERMINAL, plain_schedule
+from robotoc_b200.stage import StageDims, StageLayout, anymal_constraint_table, rbt_constraint_table
+from synth import make_stage_inputs
+from synth import mat
 
 
 def _setup(table, ctrl, batch=2, seed=5):

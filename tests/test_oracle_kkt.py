@@ -7,8 +7,8 @@ import pytest
 import oracle_lib
 from helpers import dense_kkt_solve, dense_kkt_solve_sto, small_event_schedule, rel_err
 from robotoc_b200 import ANYMAL, Layout
-from robotoc_b200.schedule import IMPACT, LIFT
-from robotoc_b200.synth import make_kkt
+from robotoc_b200.grid import IMPACT, LIFT
+from synth import make_kkt
 
 
 @pytest.mark.parametrize("seed", [20260924, 7])
@@ -43,7 +43,7 @@ def test_oracle_riccati_symmetry_and_mutation():
     kkt, dx0 = make_kkt(dims, L, ctrl, batch=1, seed=3)
     kk, ric, d, info = oracle_lib.riccati_batch(dims, L, ctrl, kkt, dx0)
     nx, nu = dims.nx, dims.nu
-    from robotoc_b200.synth import mat
+    from synth import mat
     for i in range(len(ctrl) - 1):
         P = mat(ric[0, i], L.r_P, nx, nx)
         assert np.allclose(P, P.T, rtol=0, atol=1e-12 * np.abs(P).max())
@@ -65,7 +65,7 @@ def test_oracle_sto_direction_solves_full_kkt_single_impact(with_phit):
     count left out (orc_debug_exact_chi, tests only) it IS the KKT solution to 1e-9, which pins every other Phit term.
     (Phase transitions that eliminate a later switching time: next test.)"""
     import ctypes
-    from robotoc_b200.schedule import ContactEvents, TimeDiscretization, stage_ctrl_array
+    from schedule_fixture import ContactEvents, TimeDiscretization, stage_ctrl_array
     dims = ANYMAL
     L = Layout(dims)
     ev = ContactEvents(phase_dimf=[6], phase_mask=[0b1001])
@@ -163,7 +163,7 @@ def test_unconstr_oracle_direction_solves_full_kkt():
     """Unconstrained (iiwa14) Riccati oracle (unconstr_riccati_recursion.cpp:26-48 and factorizers) against a dense solve of
     the LQ KKT system with the implicit dynamics  x+ = [[I, dt I],[0, I]] x + [0; dt I] a + Fx."""
     from robotoc_b200.layout import ULayout
-    from robotoc_b200.synth import make_unconstr_kkt, mat
+    from synth import make_unconstr_kkt, mat
     nv, N, dt = 7, 12, 0.05
     nx = 2 * nv
     lib = oracle_lib.load()

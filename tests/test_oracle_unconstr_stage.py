@@ -10,7 +10,8 @@ import oracle_lib
 from oracle_lib import ptr
 from robotoc_b200.layout import ULayout
 from robotoc_b200.stage import VAR_A, VAR_Q, VAR_U, VAR_V
-from robotoc_b200.unconstr_dms import UStageLayout, iiwa14_constraint_table, make_unconstr_stage_inputs
+from robotoc_b200.unconstr_dms import UStageLayout, iiwa14_constraint_table
+from synth import make_unconstr_stage_inputs
 
 NV = 7
 

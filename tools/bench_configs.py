@@ -12,8 +12,8 @@ from helpers import jump_sto_schedule
 from robotoc_b200 import (ANYMAL, DirectMultipleShooting, Layout, RiccatiRecursion, StageDims, StageLayout,
                           UnconstrDirectMultipleShooting, UnconstrRiccatiRecursion, anymal_constraint_table, iiwa14_constraint_table)
 from robotoc_b200.layout import ULayout
-from robotoc_b200.stage import make_stage_inputs, symmetrize_lin
-from robotoc_b200.unconstr_dms import make_unconstr_stage_inputs
+from synth import make_stage_inputs, symmetrize_lin
+from synth import make_unconstr_stage_inputs
 
 
 def gpu_time(fn, reset, iters=10):

@@ -7,7 +7,7 @@ import numpy as np
 import torch
 from robotoc_b200 import ANYMAL, Layout, RiccatiRecursion
 from helpers import trot_schedule
-from robotoc_b200.synth import make_kkt
+from synth import make_kkt
 dims = ANYMAL; L = Layout(dims)
 td, ev, ctrl = trot_schedule(40)
 n_sm = torch.cuda.get_device_properties(0).multi_processor_count

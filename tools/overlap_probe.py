@@ -7,7 +7,7 @@ import numpy as np
 import torch
 from helpers import trot_schedule
 from robotoc_b200 import ANYMAL, DirectMultipleShooting, RiccatiRecursion, StageDims, StageLayout, anymal_constraint_table
-from robotoc_b200.stage import make_stage_inputs
+from synth import make_stage_inputs
 
 td, ev, ctrl = trot_schedule(40)
 table = anymal_constraint_table()
