@@ -36,22 +36,57 @@ def oracle_iteration(sd, S, K, table, ctrl, lin, con, sol, dx0, nthreads=0):
                 cc_upd=cc, sol=ss, ex_upd=ex)
 
 
+def oracle_sensitivity(sd, S, K, table, ctrl, lin, con, sol, dx0, ref, eps=1e-15, seed=0):
+    """Per-OCP conditioning of the iteration, measured with the oracle itself: the largest relative change of its Riccati
+    factorization, Newton direction and updated solution when the linearisation records are perturbed by `eps` relative
+    (one rounding error).  No implementation can agree with another one more closely than a small multiple of this."""
+    rng = np.random.default_rng(seed)
+    ref2 = oracle_iteration(sd, S, K, table, ctrl, lin * (1.0 + eps * rng.standard_normal(lin.shape)), con, sol, dx0)
+    nx, nu = K.nx, K.nu
+    delta = np.zeros(lin.shape[0])
+    for key, secs in (("ric", ((K.r_P, nx * nx), (K.r_s, nx), (K.r_K, nx * nu), (K.r_k, nu))),
+                      ("d_upd", ((K.d_dx, nx), (K.d_du, nu), (K.d_dlmdgmm, nx))), ("sol", ((0, S.s_stride),))):
+        for off, n in secs:
+            a, b = ref[key][:, :, off:off + n], ref2[key][:, :, off:off + n]
+            scale = np.max(np.abs(a), axis=(0, 2))
+            scale[scale == 0.0] = 1.0
+            delta = np.maximum(delta, np.max(np.max(np.abs(a - b), axis=2) / scale[None, :], axis=1))
+    return delta
+
+
 def _cmp(name, got, ref, tol, worst):
+    """Block `name` of every OCP: max |got - ref| per OCP, relative to the block's scale over the batch (like Eigen's
+    isApprox, but per instance); `tol` is a scalar or a per-OCP array."""
     scale = float(np.max(np.abs(ref)))
     if scale == 0.0:
         assert float(np.max(np.abs(got))) == 0.0, f"{name}: expected zeros"
         return
-    e = float(np.max(np.abs(got - ref))) / scale
-    worst[0] = max(worst[0], e)
-    assert e < tol, f"{name}: rel err {e:.3e} (tol {tol:g})"
+    e = np.max(np.abs(got - ref).reshape(got.shape[0], -1), axis=1) / scale
+    if np.ndim(tol) == 0:
+        worst[0] = max(worst[0], float(e.max()))
+    else:
+        strict = tol <= worst[1]
+        if strict.any():
+            worst[0] = max(worst[0], float(e[strict].max()))
+    bad = np.nonzero(~(e < tol))[0]
+    assert bad.size == 0, f"{name}: OCP {bad[0]}: rel err {e[bad[0]]:.3e} (tol {np.broadcast_to(tol, e.shape)[bad[0]]:g})"
 
 
-def compare_final(S, K, ctrl, ref, ric, d, steps, sol, cc, tol=1e-8):
+def compare_final(S, K, ctrl, ref, ric, d, steps, sol, cc, tol=1e-8, sensitivity=None):
     """What a caller of the iteration sees at its end, EVERY OCP of the batch, block by block and stage by stage:
     P, s, K, k (north_star: 1e-6 relative; asserted at `tol`), the Newton direction dx, du, dlmd|dgmm (after the costate
-    correction of the update), the horizon-wide step sizes, the updated solution and slack / dual.  Returns the worst error."""
+    correction of the update), the horizon-wide step sizes, the updated solution and slack / dual.
+    `sensitivity` (oracle_sensitivity): OCPs whose own oracle result moves by more than 1e-3 * tol under a one-rounding-error
+    input perturbation are ill-conditioned instances; they are held to max(tol, 1e3 * sensitivity) instead, and may be at most
+    2 % of the batch.  Returns the worst error over the strictly compared OCPs."""
     nx, nu = K.nx, K.nu
-    worst = [0.0]
+    worst = [0.0, tol]
+    steps_tol = 1e-10
+    if sensitivity is not None:
+        loose = sensitivity > 1e-3 * tol
+        assert loose.sum() <= max(1, len(sensitivity) // 50), f"{loose.sum()} ill-conditioned OCPs: the synthetic inputs are unfit"
+        tol = np.where(loose, np.maximum(tol, 1e3 * sensitivity), tol)
+        steps_tol = np.where(loose, np.maximum(steps_tol, 1e3 * sensitivity), steps_tol)
     for i, c in enumerate(ctrl):
         _cmp(f"P[{i}]", ric[:, i, K.r_P:K.r_P + nx * nx], ref["ric"][:, i, K.r_P:K.r_P + nx * nx], tol, worst)
         _cmp(f"s[{i}]", ric[:, i, K.r_s:K.r_s + nx], ref["ric"][:, i, K.r_s:K.r_s + nx], tol, worst)
@@ -68,7 +103,7 @@ def compare_final(S, K, ctrl, ref, ric, d, steps, sol, cc, tol=1e-8):
         for f in ("c_slack", "c_dual"):
             o = getattr(S, f)
             _cmp(f"{f}[{i}]", cc[:, i, o:o + S.nc], ref["cc_upd"][:, i, o:o + S.nc], tol, worst)
-    _cmp("steps", steps, ref["steps"], 1e-10, worst)
+    _cmp("steps", steps, ref["steps"], steps_tol, worst)
     return worst[0]
 
 

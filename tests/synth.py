@@ -20,6 +20,15 @@ def _u(rng, *shape):
     return rng.uniform(-1.0, 1.0, size=shape)
 
 
+def _sel(ns, nu):
+    """[I_ns | 0] (ns x nu).  The switching-constraint Jacobian w.r.t. the controls is `selection + 0.3 * U(-1,1)` instead of
+    the plain U(-1,1) block of riccati_factorizer_test.cpp:131-140: a random square 12 x 12 block has cond ~ 1e3..1e4, so the
+    Schur complement Phiu G^-1 Phiu^T loses ~8 digits on a few instances of a 512-OCP batch (measured with the oracle itself:
+    a 1e-15 relative input perturbation moved its s by 1e-4 there) and no implementation-independent comparison is possible;
+    a contact Jacobian's actuated block is made of well-conditioned 3 x 3 leg Jacobians."""
+    return np.eye(ns, nu)[None]
+
+
 def _put(rec, off, block):
     """Store a batch of column-major blocks: block[b, i, j] -> rec[b, off + i + j*rows]."""
     b = block.shape[0]
@@ -81,7 +90,7 @@ def make_kkt(dims: Dims, L: Layout, ctrl, batch: int, seed: int, contractive: bo
             _put(rec, L.k_lu, _u(rng, batch, nu))
             if c.ns > 0:
                 _put(rec, L.k_Phix, _u(rng, batch, c.ns, nx))
-                _put(rec, L.k_Phiu, _u(rng, batch, c.ns, nu))
+                _put(rec, L.k_Phiu, _sel(c.ns, nu) + 0.3 * _u(rng, batch, c.ns, nu))
                 _put(rec, L.k_p, _u(rng, batch, c.ns))
             if c.sto:
                 ng = max(c.ngrids_in_phase, 1)
@@ -192,7 +201,9 @@ def make_stage_inputs(sd: StageDims, S: StageLayout, ctrl, batch: int, seed: int
             rec[:, S.l_lup:S.l_lup + np_] = _u(rng, batch, np_)
             if c.ns > 0:
                 _putm(rec, S.l_Phix, _u(rng, batch, c.ns, nx), c.ns)
-                _putm(rec, S.l_Phia, _u(rng, batch, c.ns, nv), c.ns)
+                Phia = _u(rng, batch, c.ns, nv)
+                Phia[:, :, nv - nu:] = _sel(c.ns, nu) + 0.3 * Phia[:, :, nv - nu:]   # leg-Jacobian-like actuated block
+                _putm(rec, S.l_Phia, Phia, c.ns)
                 rec[:, S.l_p:S.l_p + c.ns] = _u(rng, batch, c.ns)
                 rec[:, S.l_Phit:S.l_Phit + c.ns] = _u(rng, batch, c.ns)
             rec[:, S.l_ha:S.l_ha + nv] = _u(rng, batch, nv)

@@ -11,7 +11,7 @@ import pytest
 
 import oracle_lib
 from helpers import jump_sto_schedule, rel_err, trot_schedule
-from iteration_check import compare_final, oracle_iteration, run_device_iteration
+from iteration_check import compare_final, oracle_iteration, oracle_sensitivity, run_device_iteration
 from robotoc_b200 import (ANYMAL, DirectMultipleShooting, Layout, RiccatiRecursion, StageDims, StageLayout, ULayout,
                           UnconstrRiccatiRecursion, anymal_constraint_table)
 from synth import make_kkt, make_stage_inputs, make_unconstr_kkt, symmetrize_lin
@@ -28,12 +28,15 @@ def _full_iteration(ctrl, batch, seed):
     lin, con, sol, dx0 = make_stage_inputs(sd, S, ctrl, batch, seed)
     lin = symmetrize_lin(S, lin)
     ref = oracle_iteration(sd, S, K, table, ctrl, lin, con, sol, dx0)
+    sens = oracle_sensitivity(sd, S, K, table, ctrl, lin, con, sol, dx0, ref)
+    print(f"oracle sensitivity to a 1e-15 input perturbation: median {np.median(sens):.1e}, max {sens.max():.1e}, "
+          f"{int((sens > 1e-11).sum())} of {batch} OCPs above 1e-11")
     rr = RiccatiRecursion(ANYMAL, len(ctrl), batch)
     rr.setTimeDiscretization(ctrl)
     dms = DirectMultipleShooting(rr, sd, table)
     got = run_device_iteration(rr, dms, lin, con, sol, dx0)
     assert int(got["info"].max()) == 0
-    worst = compare_final(S, K, ctrl, ref, got["ric"], got["d"], got["steps"], got["sol"], got["cc"], TOL)
+    worst = compare_final(S, K, ctrl, ref, got["ric"], got["d"], got["steps"], got["sol"], got["cc"], TOL, sensitivity=sens)
     # the one-call host path (8 chunks at this batch size, wire records) returns the same bits
     sol2, con2, steps2 = dms.iteration_host_wire(dms.pack_wire(lin), lin, con, sol, dx0)
     used = S.s_xi + S.nsm
