@@ -98,6 +98,15 @@ int rbt_download_info(rbt_handle* h, int* host_flags, void* stream);          /*
  * the other OCPs of the batch are unaffected and their results are valid.  *first_bad (may be NULL) = index or -1. */
 int rbt_check_info(rbt_handle* h, int* first_bad, void* stream);
 
+/* Structure of the state-equation blocks Fxx of the KKT records handed to rbt_riccati_backward.  Every linearisation robotoc
+ * produces has Fqq = I and Fqv = dt I outside their top-left dim_passive x dim_passive blocks (src/dynamics/state_equation.cpp:
+ * 52-55 and, for a floating base, :68-87; impact stages: Fqv = 0, impact_state_equation.cpp) -- the backward sweep has an
+ * instance that skips those rows of the two nx^3 products.  RBT_FXX_AUTO (default): the records are inspected on the device at
+ * every sweep and the general instance runs if any Fxx deviates (records written by rbt_condense are known to conform and are
+ * not inspected).  RBT_FXX_MECHANICAL: the caller guarantees the structure (no inspection).  RBT_FXX_GENERAL: arbitrary Fxx. */
+enum { RBT_FXX_AUTO = 0, RBT_FXX_MECHANICAL = 1, RBT_FXX_GENERAL = 2 };
+int rbt_set_fxx_structure(rbt_handle* h, int mode);
+
 /* RiccatiRecursion::backwardRiccatiRecursion(time_discretization, kkt_matrix, kkt_residual, factorization)
  *   src/riccati/riccati_recursion.cpp:32-80.  Reads RBT_BUF_KKT, writes RBT_BUF_RIC (P,s,K,k,M,m,STO terms,
  *   STOPolicy) and, if write_fact != 0, RBT_BUF_FACT (the values the reference leaves in Qxx,Qxu,Quu,lu). */

@@ -52,6 +52,9 @@ struct rbt_handle {
   double* own[12] = {};  // the handle's own allocation of a buffer that the caller re-bound (freed in destroy)
   int* d_info = nullptr;
   int* d_arrivals = nullptr;  // per-SM CTA arrival counters (CTA de-phasing in the backward kernel)
+  int* d_struct = nullptr;    // [0]: 1 = every Fxx of the KKT buffer has the mechanical structure (see rbt_set_fxx_structure)
+  int fxx_mode = RBT_FXX_AUTO;
+  bool kkt_from_condense = false;  // the KKT records were just written by rbt_condense: structure holds by construction
   int stagger_ns = 0;
   long long* d_timeline = nullptr;  // bring-up instrumentation (RBT_TIMELINE_CTA)
   // stage layer
@@ -160,6 +163,8 @@ int rbt_create(const rbt_dims* dims, int n_grid_max, int batch, int device, rbt_
   RBT_CUDA(h, cudaMalloc(&h->d_dx0, size_t(batch) * h->L.nx * 8));
   RBT_CUDA(h, cudaMalloc(&h->d_info, size_t(batch) * sizeof(int)));
   RBT_CUDA(h, cudaMalloc(&h->d_arrivals, 1024 * sizeof(int)));
+  RBT_CUDA(h, cudaMalloc(&h->d_struct, 4 * sizeof(int)));
+  RBT_CUDA(h, cudaMemset(h->d_struct, 0, 4 * sizeof(int)));
   h->stagger_ns = getenv("RBT_STAGGER_NS") ? atoi(getenv("RBT_STAGGER_NS")) : 0;
   if (getenv("RBT_TIMELINE_CTA")) {
     h->timeline_cta = atoi(getenv("RBT_TIMELINE_CTA"));
@@ -202,6 +207,7 @@ int rbt_destroy(rbt_handle* h) {
   }
   cudaFree(h->d_info);
   cudaFree(h->d_arrivals);
+  cudaFree(h->d_struct);
   cudaFree(h->d_timeline);
   cudaFree(h->d_steps);
   cudaFree(h->d_ones);
@@ -378,6 +384,7 @@ int rbt_upload(rbt_handle* h, int which, const double* host, void* stream) {
   RBT_CUDA(h, cudaSetDevice(h->device));
   if (which == RBT_BUF_KKT) {
     int rc = RBT_OK;
+    h->kkt_from_condense = false;
     kkt_upload(h, host, (cudaStream_t)stream, true, &rc);
     if (rc != RBT_OK) {
       h->err = std::string("rbt_upload(KKT): ") + cudaGetErrorString(cudaGetLastError());
@@ -435,14 +442,17 @@ int rbt_check_info(rbt_handle* h, int* first_bad, void* stream) {
 
 template <int NV, int NU, int NS>
 static int launch_backward(rbt_handle* h, int write_fact, cudaStream_t st) {
-  using C = rbt::BwdCfg<NV, NU, NS>;
+  constexpr int NP = 6;
+  using C = rbt::BwdCfg<NV, NU, NS, NP>;
   if (C::STAGE != h->L.k_stage_size || C::EXTRA != h->L.k_extra_size) {
     h->err = "internal: shared-memory staging size does not match rbt_layout";
     return RBT_ERR_STATE;
   }
-  auto kern = rbt::riccati_backward_kernel<NV, NU, NS>;
+  auto kern_s = rbt::riccati_backward_kernel<NV, NU, NS, NP, true>;   // Fqq = I, Fqv = dt I outside the floating-base blocks
+  auto kern_g = rbt::riccati_backward_kernel<NV, NU, NS, NP, false>;  // any Fxx
   if (!h->attr_bwd) {  // the attribute is per device: tracked per handle (a handle lives on one device)
-    RBT_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
+    RBT_CUDA(h, cudaFuncSetAttribute(kern_s, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
+    RBT_CUDA(h, cudaFuncSetAttribute(kern_g, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
     h->attr_bwd = true;
   }
   rbt::BwdParams p;
@@ -461,12 +471,36 @@ static int launch_backward(rbt_handle* h, int write_fact, cudaStream_t st) {
   p.stagger_ns = h->stagger_ns;
   p.timeline = h->d_timeline;
   p.timeline_cta = h->timeline_cta;
+  p.struct_flag = nullptr;
   if (!h->keep_info) RBT_CUDA(h, cudaMemsetAsync(h->d_info + b0, 0, size_t(nb) * sizeof(int), st));
   h->keep_info = false;
   if (h->stagger_ns > 0) RBT_CUDA(h, cudaMemsetAsync(h->d_arrivals, 0, 1024 * sizeof(int), st));
-  kern<<<nb, C::NTHREADS, C::SMEM_BYTES, st>>>(p);
+  // Which instance: the condensing kernel writes Fqq = I, Fqv = dt I outside the floating-base blocks by construction
+  // (state_equation.cpp:52-55,68-87), a caller can declare it (rbt_set_fxx_structure), otherwise (RBT_FXX_AUTO) the records are
+  // inspected on the device and BOTH instances are launched -- the one the flag does not select returns at once.
+  const bool known_struct = h->kkt_from_condense || h->fxx_mode == RBT_FXX_MECHANICAL;
+  h->kkt_from_condense = false;
+  if (known_struct) {
+    kern_s<<<nb, C::NTHREADS, C::SMEM_BYTES, st>>>(p);
+    h->launches += 1;
+  } else if (h->fxx_mode == RBT_FXX_GENERAL) {
+    kern_g<<<nb, C::NTHREADS, C::SMEM_BYTES, st>>>(p);
+    h->launches += 1;
+  } else {
+    RBT_CUDA(h, cudaMemsetAsync(h->d_struct, 0, 2 * sizeof(int), st));
+    rbt::check_fxx_structure_kernel<NV, NP><<<(nb * (h->n_grid - 1) + 7) / 8, 256, 0, st>>>(p, h->d_struct);
+    p.struct_flag = h->d_struct;
+    kern_s<<<nb, C::NTHREADS, C::SMEM_BYTES, st>>>(p);
+    kern_g<<<nb, C::NTHREADS, C::SMEM_BYTES, st>>>(p);
+    h->launches += 3;
+  }
   RBT_CUDA(h, cudaGetLastError());
-  h->launches += 1;
+  return RBT_OK;
+}
+
+int rbt_set_fxx_structure(rbt_handle* h, int mode) {
+  if (!h || (mode != RBT_FXX_AUTO && mode != RBT_FXX_MECHANICAL && mode != RBT_FXX_GENERAL)) return RBT_ERR_ARG;
+  h->fxx_mode = mode;
   return RBT_OK;
 }
 
@@ -679,6 +713,7 @@ int rbt_condense(rbt_handle* h, void* stream) {
   RBT_CUDA(h, cudaGetLastError());
   h->launches += 2;
   h->keep_info = true;
+  h->kkt_from_condense = true;
   return RBT_OK;
 }
 

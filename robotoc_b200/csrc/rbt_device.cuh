@@ -76,20 +76,38 @@ __host__ __device__ constexpr int num_tiles(int M) { return (M + 7) / 8; }
 
 // One warp accumulates NT 8x8 tiles of one 8-row band:  acc[n] += sum_k A(i0+g, k) * B(k, joff(n)+g).
 //   fa(i, k) / fb(k, j) return the operand element (shared-memory loads).  K need not be a multiple of 4.
+// n_begin (warp-uniform): tiles n < n_begin are skipped (symmetric products: only the tiles on/above the diagonal band).
 template <int K, int NT, int N, class FA, class FB>
-__device__ __forceinline__ void warp_mma_band(double (&acc)[NT][2], int i0, FA fa, FB fb) {
+__device__ __forceinline__ void warp_mma_band(double (&acc)[NT][2], int i0, FA fa, FB fb, int n_begin = 0) {
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-#pragma unroll
-  for (int k0 = 0; k0 < K; k0 += 4) {
+  constexpr int KS = (K + 3) / 4;
+  // Software-pipelined by hand: the operands of k-step ks+1 are loaded BEFORE the NT tensor instructions of k-step ks are
+  // issued.  (The volatile MMA statements are scheduling barriers for ptxas: with the natural "load b, mma, load b, mma"
+  // order every DMMA waited a full shared-memory latency for its own operand -- ~65 cycles per DMMA instead of 16.)
+  auto load = [&](int ks, double& a, double (&b)[NT]) {
+    const int k0 = 4 * ks;
     // K tail: load from a clamped (valid) index and zero the A operand arithmetically -- no per-thread branch
     // may surround the warp-convergent MMA.
     const int k = (K % 4 == 0) ? (k0 + t) : min(k0 + t, K - 1);
     const double msk = ((K % 4 == 0) || (k0 + t < K)) ? 1.0 : 0.0;
-    const double a = fa(i0 + g, k) * msk;
+    a = fa(i0 + g, k) * msk;
 #pragma unroll
-    for (int n = 0; n < NT; ++n) {
-      const double b = fb(k, tile_off(n, N) + g);
-      dmma884(acc[n][0], acc[n][1], a, b);
+    for (int n = 0; n < NT; ++n)
+      if (n >= n_begin) b[n] = fb(k, tile_off(n, N) + g);
+  };
+  double a0, b0[NT], a1, b1[NT];
+  load(0, a0, b0);
+#pragma unroll
+  for (int ks = 0; ks < KS; ks += 2) {
+    if (ks + 1 < KS) load(ks + 1, a1, b1);
+#pragma unroll
+    for (int n = 0; n < NT; ++n)
+      if (n >= n_begin) dmma884(acc[n][0], acc[n][1], a0, b0[n]);
+    if (ks + 1 < KS) {
+      if (ks + 2 < KS) load(ks + 2, a0, b0);
+#pragma unroll
+      for (int n = 0; n < NT; ++n)
+        if (n >= n_begin) dmma884(acc[n][0], acc[n][1], a1, b1[n]);
     }
   }
 }
@@ -140,6 +158,66 @@ __device__ __forceinline__ void matvec_N4(const double* A, int lda, int R, int K
     acc += __shfl_xor_sync(0xffffffffu, acc, 2);
     if (q == 0 && r < R) epi(r, acc);
   }
+}
+
+// ---- fast fp64 reciprocal / reciprocal square root: MUFU seed (rel. error 2^-23) + two Newton steps -> ~1 ulp.  The seeds
+// flush subnormals; pivots of the factorizations here are O(1e-6 .. 1e12).
+__device__ __forceinline__ double fast_rcp(double d) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  r = fma(r, fma(-d, r, 1.0), r);
+  r = fma(r, fma(-d, r, 1.0), r);
+  return r;
+}
+__device__ __forceinline__ double fast_rsqrt(double d) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  double h = 0.5 * d;
+  y = y * fma(-h * y, y, 1.5);
+  y = y * fma(-h * y, y, 1.5);
+  return y;
+}
+
+// Cholesky factor AND its inverse of an N x N (N <= 16) SPD matrix held in registers by ONE warp, N doubles per lane:
+//   lane r < N       holds ROW r of the matrix in c[0..N-1] (entries k <= r are read; the others are scratch),
+//   lane 16 + q      builds COLUMN q of the inverse of the unit-lower factor (starts as the unit vector e_q).
+// Square-root-free elimination A = L_u D L_u^T.  With the inverse kept column-wise, step j is the SAME statement on both
+// half-warps:  w = c[j] / d_j ;  c[s] -= w * a_sj  (s > j),  where a_sj = slot j of matrix lane s comes from ONE shuffle that
+// serves both halves (matrix lane r: a_rs -= (a_rj / d_j) a_sj;  inverse lane q: e_s[q] -= (a_sj / d_j) e_j[q]).
+// No shared-memory round trip, no __syncwarp, no per-element predicate.  The pivot chain is shuffle -> reciprocal (MUFU seed
+// + 2 Newton steps, ~47 cycles) -> multiply -> fma; the column shuffles are issued under the reciprocal (measured on B200:
+// a 64-bit shuffle issues every ~8.6 cycles, DFMA latency 8.4).  Square roots are taken once at the end, one per lane.
+// On exit:  lane r < N:   c[k] = L[r][k]      (k <= r; Cholesky factor, A = L L^T)
+//           lane 16 + q:  c[k] = (L^-1)[k][q] (k >= q; exactly 0 above the diagonal)
+//           rs (every lane l): 1 / L[l & 15][l & 15] on lanes with (l & 15) < N.
+// Returns false (on every lane) if a pivot was not positive.
+template <int N>
+__device__ __forceinline__ bool warp_chol_inv_reg(double (&c)[N], double& rs) {
+  static_assert(N <= 16, "two half-warps");
+  const int lane = threadIdx.x & 31;
+  const int idx = lane & 15;
+  bool ok = true;
+  double dsave = 1.0;
+  if (lane >= 16) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) c[k] = (k == idx) ? 1.0 : 0.0;
+  }
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    const double dj = __shfl_sync(0xffffffffu, c[j], j);  // pivot
+    double v[N];
+#pragma unroll
+    for (int s = j + 1; s < N; ++s) v[s] = __shfl_sync(0xffffffffu, c[j], s);  // unscaled column j: a_sj
+    ok = ok && (dj > 0.0);
+    if (idx == j) dsave = dj;
+    const double w = c[j] * fast_rcp(dj);
+#pragma unroll
+    for (int s = j + 1; s < N; ++s) c[s] = fma(-w, v[s], c[s]);
+  }
+  rs = fast_rsqrt(dsave);  // lanes (l & 15) == j hold 1 / sqrt(d_j)
+#pragma unroll
+  for (int j = 0; j < N; ++j) c[j] *= __shfl_sync(0xffffffffu, rs, j);  // L[r][j] = a_rj / sqrt(d_j) | (L^-1)[j][q] = e_j[q] / sqrt(d_j)
+  return ok;
 }
 
 __device__ __forceinline__ double dot_serial(const double* a, const double* b, int n) {

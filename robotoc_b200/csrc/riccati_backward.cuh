@@ -40,13 +40,17 @@ struct BwdParams {
   int* info;          // [batch]
   int* sm_arrivals;   // [>= #SMs], zeroed before the launch (CTA de-phasing)
   int stagger_ns;     // delay unit between co-resident CTAs (0 = off)
+  const int* struct_flag;  // device: 0 = every Fxx of the batch has the mechanical structure (nullptr: run unconditionally)
   long long* timeline;  // bring-up: [n_grid][2 roles][16] clock64 stamps of CTA `timeline_cta` (nullptr = off)
   int timeline_cta;
 };
 
-template <int NV, int NU, int NS>
+// NP = dim_passive (6: floating base, 0: fixed base).  STRUCT: the state-equation blocks have the structure every robotoc
+// linearisation has (state_equation.cpp:52-55, 68-87): Fqq = I and Fqv = dt I outside their top-left NP x NP blocks.
+template <int NV, int NU, int NS, int NP = 6>
 struct BwdCfg {
   static constexpr int NX = 2 * NV;
+  static constexpr int KR = NP + NV;  // rows of Fxx that are not structural: {0..NP-1} and {NV..2NV-1}
   static constexpr int LDF = NX + 1;  // padded row stride of the F scratch (conflict-free transpose reads)
   static constexpr int TX = num_tiles(NX);
   static constexpr int TU = num_tiles(NU);
@@ -83,7 +87,7 @@ struct BwdCfg {
                        x_M = x_SDG + NS * NU, x_DtM = x_M + NS * NX, x_Gc = x_DtM + NU * NX, x_end = x_Gc + NU * NU;
   static_assert(x_end <= STAGE, "Schur scratch must fit in the staging buffer");
   static_assert(NX >= 8 && NU >= 8 && NV >= 8, "DMMA tiling needs extents >= 8");
-  static_assert(NX % 2 == 0, "nx even");
+  static_assert(NX % 2 == 0 && NV % 2 == 0 && NP % 2 == 0, "nx, nv, np even (paired fragment loads)");
   static_assert(NU <= 32 && NS <= 32, "one-warp Cholesky");
 };
 
@@ -141,13 +145,16 @@ __device__ __forceinline__ void chol_solve_smem(const double* Lm, const double* 
   }
 }
 
-template <int NV, int NU, int NS>
 #ifndef RBT_BWD_MIN_CTAS
 #define RBT_BWD_MIN_CTAS 4
 #endif
-__global__ void __launch_bounds__(BwdCfg<NV, NU, NS>::NTHREADS, RBT_BWD_MIN_CTAS) riccati_backward_kernel(const BwdParams p) {
-  using C = BwdCfg<NV, NU, NS>;
-  constexpr int NX = C::NX, LDF = C::LDF, TX = C::TX, TU = C::TU, TV = C::TV, NTHR = C::NTHREADS, NG = C::NGEMM;
+template <int NV, int NU, int NS, int NP, bool STRUCT>
+__global__ void __launch_bounds__(BwdCfg<NV, NU, NS, NP>::NTHREADS, RBT_BWD_MIN_CTAS) riccati_backward_kernel(const BwdParams p) {
+  using C = BwdCfg<NV, NU, NS, NP>;
+  constexpr int NX = C::NX, LDF = C::LDF, TX = C::TX, TU = C::TU, TV = C::TV, NTHR = C::NTHREADS, NG = C::NGEMM, KR = C::KR;
+  // STRUCT launches are gated by the structure flag written by check_fxx_structure_kernel (or set by the condensing kernel,
+  // which produces the structure by construction); the general instance runs when the flag says otherwise.
+  if (p.struct_flag != nullptr && (*p.struct_flag == 0) != STRUCT) return;  // flag = number of violations seen (0: conforming)
   extern __shared__ __align__(16) double smem[];
   double* sP = smem + C::o_P;
   double* sAtP = smem + C::o_AtP;  // AtP row-major (ld NX); later F scratch row-major (ld LDF)
@@ -340,6 +347,30 @@ __global__ void __launch_bounds__(BwdCfg<NV, NU, NS>::NTHREADS, RBT_BWD_MIN_CTAS
 
     const int i0 = tile_off(gemm_warp ? warp : 0, NX);  // this GEMM warp's row band
     double cF[TX][2];                                   // F fragments (GEMM warps only)
+    double cH[TU][2];                                   // H fragments (GEMM warps only; feed Y = L^-1 H^T from registers)
+    const double dtS = cs.dt;                           // structural Fqv = dt I (0 on an impact stage)
+    // F = Qxx + A^T P+ A and F - Y^T Y are symmetric: band w only computes the tiles on / right of its diagonal tile and P
+    // takes F[min(r,c)][max(r,c)] (every element with r <= c lies in such a tile, also under the pulled-back last band).
+    // Not on switching-constraint stages: their correction K^T D^T M is symmetrised by averaging (riccati_factorizer.cpp:85-87).
+    const bool symF = (ns == 0);
+    const int nb0 = (symF && gemm_warp) ? warp : 0;
+    // non-structural rows of Fxx: {0..NP-1} (floating-base block rows) and {NV..2NV-1} (velocity rows)
+    auto rho_of = [](int k) { return k < NP ? k : k - NP + NV; };
+    // STRUCT: rows NP..NV-1 of Fxx are [e_rho^T, dt e_rho^T] (structural); rows {0..NP-1} and {NV..2NV-1} are contracted
+    // in full (K = KR = NP + NV), the structural rows contribute a shifted copy of the other operand.
+
+    // factor warp: Quu -> accumulator fragments of G, issued before it parks at the Bp barrier (L2 latency off its chain)
+    double cG[TU][TU][2];
+    if (!gemm_warp && !impact) {
+#pragma unroll
+      for (int ub = 0; ub < TU; ++ub)
+#pragma unroll
+        for (int n = 0; n < TU; ++n) {
+          const int u0 = tile_off(ub, NU), v0 = tile_off(n, NU);
+          cG[ub][n][0] = __ldg(rec + L.k_Quu + (u0 + g) + (v0 + 2 * t) * NU);
+          cG[ub][n][1] = __ldg(rec + L.k_Quu + (u0 + g) + (v0 + 2 * t + 1) * NU);
+        }
+    }
 
     // ---- wait for this stage's blocks
     RBT_TL(i, 0);
@@ -367,10 +398,26 @@ __global__ void __launch_bounds__(BwdCfg<NV, NU, NS>::NTHREADS, RBT_BWD_MIN_CTAS
       }
       {
         double acc[TX][2];
+        if constexpr (STRUCT) {
+          // (A^T P+)[r][c] = sum_{rho in R} A[rho][r] P+[rho][c]  +  (structural rows NP <= rho < NV:)  P+[r][c] if NP <= r < NV,
+          //                                                                                       dt P+[r-NV][c] if NV+NP <= r
+          const int r = i0 + g, rr = r < NV ? r : r - NV;
+          const double sc = (rr < NP) ? 0.0 : (r < NV ? 1.0 : dtS);
 #pragma unroll
-        for (int n = 0; n < TX; ++n) acc[n][0] = acc[n][1] = 0.0;
-        warp_mma_band<NX, TX, NX>(
-            acc, i0, [&](int ii, int k) { return sA[k + ii * NX]; }, [&](int k, int j) { return sP[k + j * NX]; });
+          for (int n = 0; n < TX; ++n) {
+            const int j0 = tile_off(n, NX);
+            const double2 pv = *reinterpret_cast<const double2*>(&sP[(j0 + 2 * t) + rr * NX]);  // P+ symmetric: row rr
+            acc[n][0] = sc * pv.x;
+            acc[n][1] = sc * pv.y;
+          }
+          warp_mma_band<KR, TX, NX>(
+              acc, i0, [&](int ii, int k) { return sA[rho_of(k) + ii * NX]; }, [&](int k, int j) { return sP[rho_of(k) + j * NX]; });
+        } else {
+#pragma unroll
+          for (int n = 0; n < TX; ++n) acc[n][0] = acc[n][1] = 0.0;
+          warp_mma_band<NX, TX, NX>(
+              acc, i0, [&](int ii, int k) { return sA[k + ii * NX]; }, [&](int k, int j) { return sP[k + j * NX]; });
+        }
 #pragma unroll
         for (int n = 0; n < TX; ++n) {
           const int j0 = tile_off(n, NX);
@@ -378,48 +425,75 @@ __global__ void __launch_bounds__(BwdCfg<NV, NU, NS>::NTHREADS, RBT_BWD_MIN_CTAS
         }
       }
       RBT_TL(i, 2);
-      // Qxx -> accumulator fragments of F: issued here so the loads fly during z / the barrier, but are not live
-      // (and spilled) across GEMM1
+      // Qxx -> accumulator fragments of F: issued here so the loads fly during z, but are not live across GEMM1
 #pragma unroll
       for (int n = 0; n < TX; ++n) {
         const int j0 = tile_off(n, NX);
-        cF[n][0] = __ldg(rec + L.k_Qxx + (i0 + g) + (j0 + 2 * t) * NX);
-        cF[n][1] = __ldg(rec + L.k_Qxx + (i0 + g) + (j0 + 2 * t + 1) * NX);
+        if (n >= nb0) {
+          cF[n][0] = __ldg(rec + L.k_Qxx + (i0 + g) + (j0 + 2 * t) * NX);
+          cF[n][1] = __ldg(rec + L.k_Qxx + (i0 + g) + (j0 + 2 * t + 1) * NX);
+        } else {
+          cF[n][0] = cF[n][1] = 0.0;
+        }
       }
-      matvec_N4(sP, NX, NX, NX, sFx, tid, NG, [&](int r, double a) { z[r] = s_n[r] - a; });
-      if (sto) {
-        if (!impact) matvec_N4(sP, NX, NX, NX, sfx, tid, NG, [&](int r, double a) { Pf[r] = a; });
-        if (tid < NX) Fxs[tid] = sFx[tid];
-      }
-      named_bar_sync(1, NG);      // AtP and z complete among the GEMM warps
-      RBT_TL(i, 3);
-
-      // ================= phase B (GEMM warps): F = Qxx + AtP A ; H = Qxu + AtP[:,nv:] Bv ; t1 = A^T z - lx
-      warp_mma_band<NX, TX, NX>(
-          cF, i0, [&](int ii, int k) { return sAtP[ii * NX + k]; }, [&](int k, int j) { return sA[k + j * NX]; });
-      RBT_TL(i, 4);
       if (!impact) {
-        double cH[TU][2];
 #pragma unroll
         for (int n = 0; n < TU; ++n) {
           const int u0 = tile_off(n, NU);
           cH[n][0] = __ldg(rec + L.k_Qxu + (i0 + g) + (u0 + 2 * t) * NX);
           cH[n][1] = __ldg(rec + L.k_Qxu + (i0 + g) + (u0 + 2 * t + 1) * NX);
         }
+      }
+      matvec_N4(sP, NX, NX, NX, sFx, tid, NG, [&](int r, double a) { z[r] = s_n[r] - a; });
+      if (sto) {
+        if (!impact) matvec_N4(sP, NX, NX, NX, sfx, tid, NG, [&](int r, double a) { Pf[r] = a; });
+        if (tid < NX) Fxs[tid] = sFx[tid];
+      }
+      __syncwarp();  // this warp's rows of AtP are all the next two products read of it
+      RBT_TL(i, 3);
+
+      // ================= phase B (GEMM warps): F = Qxx + AtP A ; H = Qxu + AtP[:,nv:] Bv
+      if constexpr (STRUCT) {
+        // (AtP A)[r][c] = sum_{rho in R} AtP[r][rho] A[rho][c]  +  AtP[r][c] if NP <= c < NV,  dt AtP[r][c-NV] if NV+NP <= c
+        const int r = i0 + g;
+#pragma unroll
+        for (int n = 0; n < TX; ++n) {
+          const int c = tile_off(n, NX) + 2 * t;  // NP, NV even: the pair (c, c+1) never straddles a boundary
+          const int cc = c < NV ? c : c - NV;
+          if (n >= nb0) {
+            const double2 av = *reinterpret_cast<const double2*>(&sAtP[r * NX + cc]);
+            const double sc = (cc < NP) ? 0.0 : (c < NV ? 1.0 : dtS);
+            cF[n][0] = fma(sc, av.x, cF[n][0]);
+            cF[n][1] = fma(sc, av.y, cF[n][1]);
+          }
+        }
+        warp_mma_band<KR, TX, NX>(
+            cF, i0, [&](int ii, int k) { return sAtP[ii * NX + rho_of(k)]; }, [&](int k, int j) { return sA[rho_of(k) + j * NX]; }, nb0);
+      } else {
+        warp_mma_band<NX, TX, NX>(
+            cF, i0, [&](int ii, int k) { return sAtP[ii * NX + k]; }, [&](int k, int j) { return sA[k + j * NX]; }, nb0);
+      }
+      RBT_TL(i, 4);
+      if (!impact) {
         warp_mma_band<NV, TU, NU>(
             cH, i0, [&](int ii, int k) { return sAtP[ii * NX + NV + k]; }, [&](int k, int u) { return sB[k + u * NV]; });
+        if (!plain || fct) {  // H in shared memory is only read by the switching-constraint (Schur) path
 #pragma unroll
-        for (int n = 0; n < TU; ++n) {
-          const int u0 = tile_off(n, NU);
-          sH[(i0 + g) + (u0 + 2 * t) * NX] = cH[n][0];
-          sH[(i0 + g) + (u0 + 2 * t + 1) * NX] = cH[n][1];
-          if (fct) {
-            fct[L.f_H + (i0 + g) + (u0 + 2 * t) * NX] = cH[n][0];
-            fct[L.f_H + (i0 + g) + (u0 + 2 * t + 1) * NX] = cH[n][1];
+          for (int n = 0; n < TU; ++n) {
+            const int u0 = tile_off(n, NU);
+            if (!plain) {
+              sH[(i0 + g) + (u0 + 2 * t) * NX] = cH[n][0];
+              sH[(i0 + g) + (u0 + 2 * t + 1) * NX] = cH[n][1];
+            }
+            if (fct) {
+              fct[L.f_H + (i0 + g) + (u0 + 2 * t) * NX] = cH[n][0];
+              fct[L.f_H + (i0 + g) + (u0 + 2 * t + 1) * NX] = cH[n][1];
+            }
           }
         }
       }
       RBT_TL(i, 5);
+      named_bar_sync(1, NG);  // z (and, for the STO terms, every row of AtP) complete among the GEMM warps
       if (!impact) {
         // lu' = lu - Bv^T z_v      (== lu + BtP Fx - Bv^T s+_v, backward_..factorizer.cpp:43-44)
         matvec_T(sB, NV, NV, NU, z + NV, tid, NG, [&](int u, double a) {
@@ -446,37 +520,46 @@ __global__ void __launch_bounds__(BwdCfg<NV, NU, NS>::NTHREADS, RBT_BWD_MIN_CTAS
         }
       }
     } else {
-      // ================= factor warp: G = Quu + (Bv^T P+_vv) Bv, L L^T = G, L^-1, lu' = lu - Bv^T z_v, y = L^-1 lu'
+      // ================= factor warp: G = Quu + (Bv^T P+_vv) Bv, then L (G = L L^T) and L^-1 in registers
       if (!impact) {
         named_bar_sync(3, NTHR);  // Bp = Bv^T P+[nv:, nv:] from the GEMM warps
         RBT_TL(i, 2);
 #pragma unroll
         for (int ub = 0; ub < TU; ++ub) {  // G = Quu + Bp Bv
           const int u0 = tile_off(ub, NU);
-          double cG[TU][2];
-#pragma unroll
-          for (int n = 0; n < TU; ++n) {
-            const int v0 = tile_off(n, NU);
-            cG[n][0] = __ldg(rec + L.k_Quu + (u0 + g) + (v0 + 2 * t) * NU);
-            cG[n][1] = __ldg(rec + L.k_Quu + (u0 + g) + (v0 + 2 * t + 1) * NU);
-          }
           warp_mma_band<NV, TU, NU>(
-              cG, u0, [&](int u, int k) { return sBp[u * NV + k]; }, [&](int k, int v) { return sB[k + v * NV]; });
+              cG[ub], u0, [&](int u, int k) { return sBp[u * NV + k]; }, [&](int k, int v) { return sB[k + v * NV]; });
 #pragma unroll
           for (int n = 0; n < TU; ++n) {
             const int v0 = tile_off(n, NU);
-            sG[(u0 + g) + (v0 + 2 * t) * NU] = cG[n][0];
-            sG[(u0 + g) + (v0 + 2 * t + 1) * NU] = cG[n][1];
+            sG[(u0 + g) + (v0 + 2 * t) * NU] = cG[ub][n][0];
+            sG[(u0 + g) + (v0 + 2 * t + 1) * NU] = cG[ub][n][1];
             if (fct) {
-              fct[L.f_G + (u0 + g) + (v0 + 2 * t) * NU] = cG[n][0];
-              fct[L.f_G + (u0 + g) + (v0 + 2 * t + 1) * NU] = cG[n][1];
+              fct[L.f_G + (u0 + g) + (v0 + 2 * t) * NU] = cG[ub][n][0];
+              fct[L.f_G + (u0 + g) + (v0 + 2 * t + 1) * NU] = cG[ub][n][1];
             }
           }
         }
         __syncwarp();
         RBT_TL(i, 3);
         if (plain) {
-          if (!warp_cholesky<NU>(sG, NU, dinv)) bad |= 1;
+          // Cholesky factor (rows on lanes 0..NU-1) and its inverse (columns on lanes 16..16+NU-1), broadcasts by shuffle
+          double gc[NU], rs;
+          const int idx = (lane & 15) < NU ? (lane & 15) : NU - 1;
+#pragma unroll
+          for (int k = 0; k < NU; ++k) gc[k] = sG[idx + k * NU];  // row of G (its lower part is read)
+          if (!warp_chol_inv_reg<NU>(gc, rs)) bad |= 1;
+          if ((lane & 15) < NU) {
+            if (lane < 16) {
+#pragma unroll
+              for (int k = 0; k < NU; ++k) sG[idx + k * NU] = (k <= idx) ? gc[k] : 0.0;  // L, col-major, lower triangular
+              dinv[idx] = rs;
+            } else {
+#pragma unroll
+              for (int k = 0; k < NU; k += 2)  // column idx of L^-1, col-major: contiguous
+                *reinterpret_cast<double2*>(&sLi[k + idx * NU]) = make_double2(gc[k], gc[k + 1]);
+            }
+          }
           __syncwarp();
         }
         RBT_TL(i, 4);
@@ -506,43 +589,35 @@ __global__ void __launch_bounds__(BwdCfg<NV, NU, NS>::NTHREADS, RBT_BWD_MIN_CTAS
         __syncthreads();
       }
       if (plain) {
-        // ================= phase C: Y = L^-1 [H^T | lu'] by forward substitution, one column per lane spread over the GEMM
-        // warps (column-oriented: 12 dependent steps); the factor warp inverts L meanwhile (needed only for K, T, W).
+        // ================= phase C: Y = L^-1 H^T on the tensor pipe, straight from the H accumulator fragments: with the
+        // contraction index u dealt to the lanes as u = u0 + 2t (+1), the C fragment of H (rows i0+g, columns u0+2t, u0+2t+1) IS
+        // the B operand H^T[u][i0+g] of  Y[:, band] = L^-1 (H[band, :])^T  -- H never goes through shared memory.  The second,
+        // pulled-back H tile overlaps the first in columns u0 .. 7: its A operand is zeroed there.
         if (gemm_warp) {
-          constexpr int CPW = (NX + 1 + TX - 1) / TX;  // columns per warp
-          const int c = warp * CPW + lane;
-          if (lane < CPW && c <= NX) {
-            double y[NU];
 #pragma unroll
-            for (int u = 0; u < NU; ++u) y[u] = (c < NX) ? sH[c + u * NX] : lu2[u];
+          for (int mt = 0; mt < TU; ++mt) {
+            const int m0 = tile_off(mt, NU);
+            double y0 = 0.0, y1 = 0.0;
 #pragma unroll
-            for (int k = 0; k < NU; ++k) {
-              y[k] *= dinv[k];
+            for (int n = 0; n < TU; ++n) {
+              const int u0 = tile_off(n, NU);
 #pragma unroll
-              for (int a = k + 1; a < NU; ++a) y[a] = fma(-sG[a + k * NU], y[k], y[a]);
+              for (int e = 0; e < 2; ++e) {
+                const int u = u0 + 2 * t + e;
+                const bool dup = (n > 0) && (u < 8 * n);  // already contracted by the previous tile
+                const double a = dup ? 0.0 : sLi[(m0 + g) + u * NU];
+                dmma884(y0, y1, a, cH[n][e]);
+              }
             }
-            if (c < NX) {
-#pragma unroll
-              for (int u = 0; u < NU; ++u) sY[u + c * NU] = y[u];
-            } else {
-#pragma unroll
-              for (int u = 0; u < NU; ++u) ylu[u] = y[u];
-            }
+            sY[(m0 + g) + (i0 + 2 * t) * NU] = y0;
+            sY[(m0 + g) + (i0 + 2 * t + 1) * NU] = y1;
           }
         } else if (lane < NU) {
-          // L^-1: lane c solves L x = e_c; rows above c are zero
-          const int c = lane;
-          double x[NU];
+          // y = L^-1 lu'   (row `lane` of L^-1 is contiguous in k with stride NU)
+          double a = 0.0;
 #pragma unroll
-          for (int a = 0; a < NU; ++a) x[a] = (a == c) ? 1.0 : 0.0;
-#pragma unroll
-          for (int k = 0; k < NU; ++k) {
-            x[k] *= dinv[k];
-#pragma unroll
-            for (int a = k + 1; a < NU; ++a) x[a] = fma(-sG[a + k * NU], x[k], x[a]);
-          }
-#pragma unroll
-          for (int a = 0; a < NU; ++a) sLi[a + c * NU] = x[a];
+          for (int k = 0; k < NU; ++k) a = fma(sLi[lane + k * NU], lu2[k], a);
+          ylu[lane] = a;
         }
         RBT_TL(i, 9);
         __syncthreads();  // ---- barrier 3: Y complete
@@ -551,7 +626,7 @@ __global__ void __launch_bounds__(BwdCfg<NV, NU, NS>::NTHREADS, RBT_BWD_MIN_CTAS
         if (gemm_warp) {
           // F -= Y^T Y
           warp_mma_band<NU, TX, NX>(
-              cF, i0, [&](int ii, int k) { return -sY[k + ii * NU]; }, [&](int k, int j) { return sY[k + j * NU]; });
+              cF, i0, [&](int ii, int k) { return -sY[k + ii * NU]; }, [&](int k, int j) { return sY[k + j * NU]; }, nb0);
           // s = t1 + Y^T y            (== A^T z - lx - H k)
           matvec_T(sY, NU, NU, NX, ylu, tid, NG, [&](int c, double a) {
             const double v = t1[c] + a;
@@ -782,8 +857,10 @@ __global__ void __launch_bounds__(BwdCfg<NV, NU, NS>::NTHREADS, RBT_BWD_MIN_CTAS
 #pragma unroll
       for (int n = 0; n < TX; ++n) {
         const int j0 = tile_off(n, NX);
-        sAtP[(i0 + g) * LDF + j0 + 2 * t] = cF[n][0];
-        sAtP[(i0 + g) * LDF + j0 + 2 * t + 1] = cF[n][1];
+        if (n >= nb0) {
+          sAtP[(i0 + g) * LDF + j0 + 2 * t] = cF[n][0];
+          sAtP[(i0 + g) * LDF + j0 + 2 * t + 1] = cF[n][1];
+        }
       }
     }
     RBT_TL(i, 11);
@@ -791,13 +868,26 @@ __global__ void __launch_bounds__(BwdCfg<NV, NU, NS>::NTHREADS, RBT_BWD_MIN_CTAS
     RBT_TL(i, 12);
 
     // ================= phase E: P = (F + F^T)/2 -> shared (next stage) and HBM ; STO vectors / scalars
-    for (int e = tid; e < NX * NX; e += NTHR) {
-      const int r = e % NX, c = e / NX;
-      const double f_rc = sAtP[r * LDF + c];
-      const double v = 0.5 * (f_rc + sAtP[c * LDF + r]);
-      sP[e] = v;
-      ric[L.r_P + e] = v;
-      if (fct && ns == 0) fct[L.f_F + e] = f_rc;
+    {
+      int r = tid % NX, c = tid / NX;  // (r, c) of e = tid + k * NTHR, advanced without a division per element
+      for (int e = tid; e < NX * NX; e += NTHR) {
+        double v, f_rc;
+        if (symF) {  // only the tiles on / above the diagonal were computed: mirror
+          v = f_rc = (r <= c) ? sAtP[r * LDF + c] : sAtP[c * LDF + r];
+        } else {
+          f_rc = sAtP[r * LDF + c];
+          v = 0.5 * (f_rc + sAtP[c * LDF + r]);
+        }
+        sP[e] = v;
+        ric[L.r_P + e] = v;
+        if (fct && ns == 0) fct[L.f_F + e] = f_rc;
+        r += NTHR % NX;
+        c += NTHR / NX;
+        if (r >= NX) {
+          r -= NX;
+          ++c;
+        }
+      }
     }
     if (sto) {
       if (!impact) {
@@ -885,6 +975,27 @@ __global__ void __launch_bounds__(BwdCfg<NV, NU, NS>::NTHREADS, RBT_BWD_MIN_CTAS
   }
   bad = __reduce_or_sync(0xffffffffu, bad);
   if (lane == 0 && bad) atomicOr(&p.info[b], bad);
+}
+
+// One warp per (OCP, stage < N): *viol = 1 if Fxx deviates from [[I, dt I], [*, *]] outside the top-left NP x NP blocks of
+// Fqq and Fqv (rows NP..NV-1 entirely, rows < NP outside the two blocks).  Reads 18 of the 36 rows of every Fxx once.
+template <int NV, int NP>
+__global__ void check_fxx_structure_kernel(const BwdParams p, int* viol) {
+  constexpr int NX = 2 * NV;
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int N = p.n_grid - 1;
+  if (w >= p.batch * N) return;
+  const int b = w / N, i = w % N;
+  const double dt = p.ctrl[i].dt;
+  const double* A = p.kkt + (size_t(b) * p.n_grid + i) * p.L.k_stride + p.L.k_Fxx;
+  bool bad = false;
+  for (int e = lane; e < NV * NX; e += 32) {
+    const int rho = e % NV, c = e / NV;
+    if (rho < NP && (c < NP || (c >= NV && c < NV + NP))) continue;  // the floating-base blocks are free
+    const double want = (c == rho) ? 1.0 : ((c == rho + NV) ? dt : 0.0);
+    bad |= !(A[rho + c * NX] == want);
+  }
+  if (__any_sync(0xffffffffu, bad) && lane == 0) atomicExch(viol, 1);
 }
 
 }  // namespace rbt

@@ -466,12 +466,21 @@ __global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS, 6) condense_ke
       }
     };
     // Qqq += sum_c dg_dq^T diag(w) dg_dq          friction_cone.cpp:217-218  (box diagonal below)
-    for (int e = tid; e < NV * NV; e += NTHR) {
-      const int ii = e % NV, j = e / NV;
-      double acc = 0.0;
-      for (int ci = 0; ci < ncon; ++ci)
-        for (int r = 0; r < 5; ++r) acc = fma(sDq[ci * 5 * NV + r + ii * 5] * cW[nbox + 5 * ci + r], sDq[ci * 5 * NV + r + j * 5], acc);
-      dQq[ii + j * NV] = acc;
+    // One NV x (5 ncon) x NV product on the tensor pipe: the cone rows of all contacts are the contraction index k = 5 ci + r
+    // (rows of inactive contacts were zeroed above).  The scalar version of this loop was 18 % of the kernel's shared-memory
+    // wavefronts (ncu, r2): 60 loads per output element.
+    {
+      constexpr int KC = 5 * (NFM / 3);
+      auto dq_at = [&](int k, int col) { return sDq[(k / 5) * 5 * NV + (k % 5) + col * 5]; };
+      for (int tile = warp; tile < TV * TV; tile += NTHR / 32) {
+        const int r0 = tile_off(tile / TV, NV), j0 = tile_off(tile % TV, NV);
+        double acc[1][2] = {{0.0, 0.0}};
+        warp_mma_band<KC, 1, 8>(
+            acc, r0, [&](int ii, int k) { return (k < 5 * ncon) ? dq_at(k, ii) * cW[nbox + k] : 0.0; },
+            [&](int k, int jj) { return (k < 5 * ncon) ? dq_at(k, j0 + jj) : 0.0; });
+        dQq[(r0 + g) + (j0 + 2 * t) * NV] = acc[0][0];
+        dQq[(r0 + g) + (j0 + 2 * t + 1) * NV] = acc[0][1];
+      }
     }
     // Qqf[:, stack(c)] += dg_dq^T diag(w) dg_df ;  Qff[stack(c), stack(c)] += dg_df^T diag(w) dg_df     :219-222
     for (int e = tid; e < NV * 3 * ncon + 9 * ncon; e += NTHR) {
