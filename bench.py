@@ -140,26 +140,68 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+_HOST_CORES = None
+
+
+def host_cores():
+    """Cached: must be taken BEFORE libgomp starts with OMP_PROC_BIND (it pins the calling thread to one place, after which the
+    affinity mask of this process reads 1)."""
+    global _HOST_CORES
+    if _HOST_CORES is None:
+        _HOST_CORES = _host_cores()
+    return _HOST_CORES
+
+
+def _host_cores():
+    """CPU cores this process may really use: the scheduler affinity mask AND the cgroup CPU quota (a 128-CPU host leased with
+    cpu.max = 16 cores only runs 16 threads at a time -- round 1 timed 64 threads there and got a 4x pessimistic baseline)."""
+    aff = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    quota = None
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            with open(path) as fh:
+                txt = fh.read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    quota = float(txt[0]) / float(txt[1])
+            else:
+                q = float(txt[0])
+                if q > 0:
+                    with open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as fh:
+                        quota = q / float(fh.read())
+            break
+        except (OSError, ValueError, IndexError):
+            continue
+    usable = aff if quota is None else max(1, min(aff, int(quota + 0.5)))
+    return {"logical_cpus": os.cpu_count(), "affinity": aff, "cgroup_quota_cores": quota, "usable": usable}
+
+
 def _oracle_runner(pr):
-    """Returns (cores, run): run() executes ONE timed pass of the oracle (CPU restatement of the reference algorithm) over
-    the whole batch -- condense, Riccati backward+forward, step sizes, update -- and returns seconds.  Inputs the algorithm
-    mutates in place are restored (untimed) before every pass; only the C calls are timed.  The thread count is the better
-    of {all logical CPUs, half of them} (hyper-threads hurt this fp64 code)."""
+    """Returns (cores_info, run): run(mode, nthreads) executes ONE timed pass of the oracle (CPU restatement of the reference
+    algorithm) over the whole batch -- condense, Riccati backward + forward, step sizes, update (orc_iteration_batch) -- and
+    returns seconds.  Inputs the algorithm mutates in place are restored (untimed) before every pass; only the C call is
+    timed.  mode 0: OpenMP over OCP instances ("best-case CPU"); mode 1: one OCP at a time, 4-thread stage loops, serial
+    Riccati recursion ("reference-faithful", what robotoc::OCPSolver does with nthreads = 4)."""
     import ctypes as ct
+    cores = host_cores()
+    # thread placement must be fixed before libgomp starts: one thread per core, neighbours close
+    os.environ.setdefault("OMP_PROC_BIND", "close")
+    os.environ.setdefault("OMP_PLACES", "cores")
+    os.environ.setdefault("OMP_DYNAMIC", "false")
     import oracle_lib
     lib = oracle_lib.load()
     native = os.path.join(oracle_lib.ORACLE_DIR, "liboracle_native.so")
     try:  # -march=native build of the same sources, made on this machine
         subprocess.run(["make", "-s", "-C", oracle_lib.ORACLE_DIR, "native"], check=True, stdout=subprocess.DEVNULL,
                        stderr=subprocess.DEVNULL)
-        nl = ct.CDLL(native)
-        for fn in ("orc_riccati_batch", "orc_condense_batch", "orc_expand_batch", "orc_update_batch"):
-            getattr(nl, fn).argtypes = getattr(lib, fn).argtypes
-            getattr(nl, fn).restype = getattr(lib, fn).restype
-        lib = nl
+        lib = ct.CDLL(native)
     except Exception:
         pass
-    ncpu = os.cpu_count() or 1
+    from robotoc_b200._lib import rbt_stage_ctrl
+    from robotoc_b200.stage import rbt_constraint_table, rbt_stage_dims
+    c_int, c_dbl, c_vp = ct.c_int, ct.c_double, ct.c_void_p
+    lib.orc_iteration_batch.argtypes = [ct.POINTER(rbt_stage_dims), ct.POINTER(rbt_constraint_table), ct.POINTER(rbt_stage_ctrl),
+                                        c_int, c_int, c_dbl] + [c_vp] * 10 + [c_int, c_int]
     S, K, sd, table, ctrl = pr["S"], pr["K"], pr["sd"], pr["table"], pr["ctrl"]
     lin, con0, sol0, dx0 = pr["lin"], pr["con"], pr["sol"], pr["dx0"]
     b, n_grid = lin.shape[0], lin.shape[1]
@@ -170,71 +212,100 @@ def _oracle_runner(pr):
     xd = np.zeros((b, n_grid, S.x_stride))
     con, sol = np.empty_like(con0), np.empty_like(sol0)
     steps = np.zeros((b, 2))
-    csd, cd = sd.c(), pr["dims"].c()
+    csd = sd.c()
     P = oracle_lib.ptr
 
-    def run(nthreads):
+    def run(mode, nthreads, nb=None):
+        nb = b if nb is None else nb
         np.copyto(con, con0)
         np.copyto(sol, sol0)
         t0 = time.perf_counter()
-        i1 = lib.orc_condense_batch(ct.byref(csd), ct.byref(table), ctrl, n_grid, b, P(lin), P(con), P(kkt), P(ex), nthreads)
-        i2 = lib.orc_riccati_batch(ct.byref(cd), ctrl, n_grid, 0.1, b, P(kkt), P(ric), P(dx0), P(d), nthreads)
-        lib.orc_expand_batch(ct.byref(csd), ct.byref(table), ctrl, n_grid, b, P(lin), P(ex), P(d), P(con), P(xd), P(steps), nthreads)
-        lib.orc_update_batch(ct.byref(csd), ct.byref(table), ctrl, n_grid, b, P(ex), P(d), P(xd), P(con), P(sol), P(steps), nthreads)
+        info = lib.orc_iteration_batch(ct.byref(csd), ct.byref(table), ctrl, n_grid, nb, 0.1, P(lin), P(con), P(kkt), P(ex), P(ric),
+                                       P(dx0), P(d), P(xd), P(sol), P(steps), mode, nthreads)
         el = time.perf_counter() - t0
-        assert i1 == 0 and i2 == 0
+        assert info == 0
         return el
 
-    cands = sorted({ncpu, max(1, ncpu // 2)})
-    best = None
-    for nt in cands:
-        run(nt)
-        t = min(run(nt) for _ in range(2))
-        if best is None or t < best[1]:
-            best = (nt, t)
-    nthreads = best[0]
-    return nthreads, (lambda: run(nthreads))
+    return cores, run
 
 
 WORKLOAD = "anymal_trot_N40 batch={b}/GPU: full hot-path iteration = condense + riccati backward + riccati forward + step sizes + update"
+METRIC = "SQP-iterations/s (ANYmal N=40, batch=1024) at 1/2/4/8 B200 vs CPU ref"
+
+
+def bench_config(batch, n_grid, world, l2_note):
+    """The `config` object both arms print (the driver compares them)."""
+    return {"workload": WORKLOAD.format(b=batch) + (" + NCCL all-gather of the step (overlapped with the next iteration's condensing / backward sweep)" if world > 1 else ""),
+            "n_grid": n_grid, "dims": "nv18 nu12 nx36, 92 inequality rows/stage", "parallelism": f"batch-sharded x{world}",
+            "l2": l2_note}
+
+
+def l2_note(pr):
+    lin, K = pr["lin"], pr["K"]
+    ws = lin.nbytes + lin.shape[0] * lin.shape[1] * (K.k_stride + K.r_stride) * 8
+    return f"per-step working set {ws / 1e9:.2f} GB >> 126 MB L2 (inputs larger than L2; no flush needed)"
+
+
+def cpu_modes(pr, min_seconds):
+    """Both BASELINE.md section 3 modes on the host cores this process may use."""
+    cores, run = _oracle_runner(pr)
+    b = pr["lin"].shape[0]
+    nt = cores["usable"]
+    run(0, nt)  # warm-up (page faults of the scratch arrays, libgomp start-up)
+    n, el = 0, 0.0
+    while el < min_seconds:
+        el += run(0, nt)
+        n += 1
+    best_case = b * n / el
+    nb_ref = min(b, 64)  # the serial-in-OCP mode is ~nt/2 times slower: a bounded sample of the same batch
+    run(1, 4, nb_ref)
+    n1, el1 = 0, 0.0
+    while el1 < min_seconds / 3:
+        el1 += run(1, 4, nb_ref)
+        n1 += 1
+    faithful = nb_ref * n1 / el1
+    return {"value": best_case, "unit": "OCP-iterations/s", "cores": nt, "kind": "port",
+            "sample": f"{n} passes over {b} OCPs, whole iteration per OCP inside one OpenMP loop over OCP instances "
+                      f"({nt} threads pinned one per core), {el:.1f} s of CPU-timed work",
+            "modes": {"batch_parallel": {"value": best_case, "threads": nt},
+                      "reference_faithful": {"value": faithful, "threads": 4, "sample": f"{n1} passes over {nb_ref} OCPs, one OCP at a time, "
+                                             "4-thread stage loops, serial Riccati recursion (robotoc::OCPSolver with nthreads = 4)"}},
+            "host": cores}
 
 
 def cpu_leg(pr, min_seconds):
-    cores, run = _oracle_runner(pr)
-    n, el = 0, 0.0
-    while el < min_seconds:
-        el += run()
-        n += 1
-    b = pr["lin"].shape[0]
-    return {"value": b * n / el, "unit": "OCP-iterations/s", "cores": cores, "kind": "port",
-            "sample": f"{n} passes over {b} OCPs (same full iteration; OpenMP over OCP instances, {cores} threads = best of "
-                      f"all/half logical CPUs), {el:.1f} s of CPU-timed work"}
+    return cpu_modes(pr, min_seconds)
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    host_cores()
+    os.environ.setdefault("OMP_PROC_BIND", "close")
+    os.environ.setdefault("OMP_PLACES", "cores")
     import oracle_lib
     lib = oracle_lib.load()
     pr = build_iteration_problem(args.batch, 20260927, getter=lib.orc_stage_layout_get, kgetter=lib.orc_layout_get)
     cores, run = _oracle_runner(pr)
+    nt = cores["usable"]
     for _ in range(max(args.warmup, 1)):
-        run()
+        run(0, nt)
     el = 0.0
     for _ in range(args.steps):
-        el += run()
+        el += run(0, nt)
     val = args.batch * args.steps / el
     line = {
-        "impl": "reference", "metric": "SQP-iterations/s (ANYmal N=40, batch=1024) at 1/2/4/8 B200 vs CPU ref",
+        "impl": "reference", "metric": METRIC,
         "value": val, "unit": "OCP-iterations/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD.format(b=args.batch), "n_grid": len(pr["ctrl"]),
-                   "note": "CPU restatement of the reference algorithm (oracle port; Eigen/Pinocchio absent so the reference "
-                           "itself cannot be built), OpenMP over OCP instances on the host threads"},
-        "cpu_baseline": {"value": val, "unit": "OCP-iterations/s", "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} passes over {args.batch} OCPs"},
+        "config": bench_config(args.batch, len(pr["ctrl"]), max(args.gpus, 1), l2_note(pr)),
+        "note": "CPU restatement of the reference algorithm (oracle port pinned against the reference's own Riccati sources, "
+                "see tests/test_golden_ref.py; the reference's CMake build needs Eigen3 + Pinocchio, absent here); best-case CPU "
+                "mode: OpenMP over OCP instances on every core this process may use",
+        "cpu_baseline": {"value": val, "unit": "OCP-iterations/s", "cores": nt, "kind": "port",
+                         "sample": f"{args.steps} passes over {args.batch} OCPs", "host": cores},
         "e2e": {"value": val, "unit": "OCP-iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -246,6 +317,10 @@ def main():
     if args.impl == "reference":
         run_reference(args)
         return
+    host_cores()
+    # (before anything loads libgomp) one OpenMP thread per core, neighbours close: the CPU legs and the parity gate
+    os.environ.setdefault("OMP_PROC_BIND", "close")
+    os.environ.setdefault("OMP_PLACES", "cores")
     import torch
     import torch.distributed as dist
     from robotoc_b200 import DirectMultipleShooting, RiccatiRecursion
@@ -294,7 +369,8 @@ def main():
     # ---- parity gate (untimed): EVERY OCP of this rank's batch against the CPU oracle, before anything is timed
     from iteration_check import compare_final, oracle_iteration
     t_chk = time.perf_counter()
-    ref = oracle_iteration(pr["sd"], S, K, pr["table"], ctrl, lin, con, sol, dx0)
+    ref = oracle_iteration(pr["sd"], S, K, pr["table"], ctrl, lin, con, sol, dx0,
+                           nthreads=max(1, host_cores()["usable"] // max(1, min(world, 8))))
     steps_chk = np.stack([dms.maxPrimalStepSize(sp), dms.maxDualStepSize(sp)], axis=1)
     parity_worst = compare_final(S, K, ctrl, ref, rr.getRiccatiFactorization(sp), d_local.cpu().numpy(), steps_chk,
                                  dms.getSolution(sp), dms.getConstraintData(sp), tol=1e-8)
@@ -438,14 +514,11 @@ def main():
         kname = {"riccati_backward": "riccati_backward_kernel<18,12,12>", "condense": "condense_kernel<18,12,12>",
                  "riccati_forward": "riccati_forward_kernel<18,12,12>"}.get(dom, dom)
         line = {
-            "metric": "SQP-iterations/s (ANYmal N=40, batch=1024) at 1/2/4/8 B200 vs CPU ref",
+            "metric": METRIC,
             "value": world * args.batch * args.steps / (ms * 1e-3), "unit": "OCP-iterations/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD.format(b=args.batch) + (" + NCCL all-gather of the step (overlapped with the next iteration's condensing / backward sweep)" if world > 1 else ""),
-                       "n_grid": n_grid, "dims": "nv18 nu12 nx36, 92 inequality rows/stage", "parallelism": f"batch-sharded x{world}",
-                       "l2": f"per-step working set {(lin.nbytes + rr.buf_doubles(0) * 8 + rr.buf_doubles(1) * 8) / 1e9:.2f} GB "
-                             ">> 126 MB L2 (inputs larger than L2; no flush needed)"},
+            "config": bench_config(args.batch, n_grid, world, l2_note(pr)),
             "clocks": clocks, "gpu_launches": int(launches),
             "parity": {"checked_ocps": args.batch, "worst_rel_err_vs_oracle": parity_worst, "tol": 1e-8},
             "kernels_ms": kms,

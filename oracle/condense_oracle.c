@@ -25,44 +25,7 @@
 
 #define IDX(i, j, ld) ((i) + (size_t)(j) * (ld))
 
-/* same loop forms as oracle/riccati_oracle.c: column axpy for op(A)=A, simd dot products for op(A)=A^T (gcc vectorises both) */
-static void gemm(int ta, int tb, int m, int n, int k, double alpha, const double* restrict A, int lda,
-                 const double* restrict B, int ldb, double beta, double* restrict C, int ldc) {
-  if (!ta) {
-    for (int j = 0; j < n; ++j) {
-      double* restrict c = C + (size_t)j * ldc;
-      if (beta == 0.0) {
-        for (int i = 0; i < m; ++i) c[i] = 0.0;
-      } else if (beta != 1.0) {
-        for (int i = 0; i < m; ++i) c[i] *= beta;
-      }
-      for (int l = 0; l < k; ++l) {
-        const double b = alpha * (tb ? B[IDX(j, l, ldb)] : B[IDX(l, j, ldb)]);
-        const double* restrict a = A + (size_t)l * lda;
-#pragma omp simd
-        for (int i = 0; i < m; ++i) c[i] += a[i] * b;
-      }
-    }
-  } else if (!tb) {
-    for (int j = 0; j < n; ++j) {
-      const double* restrict b = B + (size_t)j * ldb;
-      for (int i = 0; i < m; ++i) {
-        const double* restrict a = A + (size_t)i * lda;
-        double acc = 0.0;
-#pragma omp simd reduction(+ : acc)
-        for (int l = 0; l < k; ++l) acc += a[l] * b[l];
-        C[IDX(i, j, ldc)] = (beta == 0.0 ? 0.0 : beta * C[IDX(i, j, ldc)]) + alpha * acc;
-      }
-    }
-  } else {
-    for (int j = 0; j < n; ++j)
-      for (int i = 0; i < m; ++i) {
-        double acc = 0.0;
-        for (int l = 0; l < k; ++l) acc += A[IDX(l, i, lda)] * B[IDX(j, l, ldb)];
-        C[IDX(i, j, ldc)] = (beta == 0.0 ? 0.0 : beta * C[IDX(i, j, ldc)]) + alpha * acc;
-      }
-  }
-}
+#include "orc_linalg.h"  /* gemm(): register-blocked small GEMM shared by the oracle sources */
 
 static int chol_lower(int n, double* A, int lda) {
   for (int j = 0; j < n; ++j) {
@@ -210,11 +173,10 @@ int orc_stage_condense(const rbt_stage_dims* sd, const rbt_constraint_table* tab
   memcpy(lx, lin + S.l_lx, sizeof(double) * nx);
   memcpy(lu, lin + S.l_lu, sizeof(double) * nu);
   memcpy(Fx, lin + S.l_Fx, sizeof(double) * nx);
-  double* Qaa = (double*)calloc(nv, 8);
-  double* Qff = (double*)calloc((size_t)nfm * nfm, 8);
-  double* Qqf = (double*)calloc((size_t)nv * nfm, 8);
-  double* la = (double*)calloc(nv, 8);
-  double* lf = (double*)calloc(nfm, 8);
+  /* per-stage scratch on the stack (a heap allocation per stage would be charged to the CPU baseline) */
+  double Qaa[nv], Qff[(size_t)nfm * nfm + 1], Qqf[(size_t)nv * nfm + 1], la[nv], lf[nfm + 1];
+  memset(Qaa, 0, sizeof(Qaa)); memset(Qff, 0, sizeof(Qff)); memset(Qqf, 0, sizeof(Qqf));
+  memset(la, 0, sizeof(la)); memset(lf, 0, sizeof(lf));
   memcpy(Qaa, lin + S.l_Qaa, sizeof(double) * nv);
   memcpy(Qff, lin + S.l_Qff, sizeof(double) * nfm * nfm);
   memcpy(Qqf, lin + S.l_Qqf, sizeof(double) * nv * nfm);
@@ -300,9 +262,9 @@ int orc_stage_condense(const rbt_stage_dims* sd, const rbt_constraint_table* tab
   double* laf = ex + S.e_laf;
   const double* D = lin + S.l_D; /* ld nvfm */
   const double* IDC = lin + S.l_IDC;
-  double* ws = (double*)calloc((size_t)3 * nv * nv + 2 * nfm * nv + 2 * nfm * nfm + 16, 8);
+  double ws[(size_t)3 * nv * nv + 2 * nfm * nv + 2 * nfm * nfm + 16];
+  memset(ws, 0, sizeof(ws));
   info |= mjtjinv(nv, nf, lin + S.l_M, lin + S.l_J, nfm, Z, nvfm, ws);    /* contact_dynamics.cpp:64 / impact :42 */
-  free(ws);
   gemm(0, 0, nvf, nx, nvf, 1.0, Z, nvfm, D, nvfm, 0.0, R, nvfm);          /* MJtJinv_dIDCdqv = Z dIDCdqv   :65 */
   gemm(0, 0, nvf, 1, nvf, 1.0, Z, nvfm, IDC, nvfm, 0.0, r_, nvfm);        /* MJtJinv_IDC = Z IDC           :66 */
   for (int j = 0; j < nx; ++j) {
@@ -454,7 +416,7 @@ int orc_stage_condense(const rbt_stage_dims* sd, const rbt_constraint_table* tab
     if (ns > 0)
       for (int i = 0; i < ns; ++i) kkt[K.k_Phit + i] *= g1;
   }
-  free(Qaa); free(Qff); free(Qqf); free(la); free(lf);
+
   return info;
 }
 
@@ -754,5 +716,86 @@ int orc_mjtjinv(int nv, int nf, const double* M, const double* J, int ldj, doubl
   double* ws = (double*)calloc((size_t)3 * nv * nv + 2 * (nf + 1) * nv + 2 * (nf + 1) * (nf + 1) + 16, 8);
   int info = mjtjinv(nv, nf, M, J, ldj, Z, ldz, ws);
   free(ws);
+  return info;
+}
+
+/* ---------------- whole hot-path iteration drivers (CPU baseline of bench.py) ----------------
+ * The linear-algebra body of OCPSolver::updateSolution (src/solver/ocp_solver.cpp:118-144) for a batch of OCPs:
+ *   mode 0  "batch-parallel" (best-case CPU): OpenMP over OCP instances, each thread runs condense -> backward -> forward ->
+ *           step sizes -> update for its OCP back to back (records stay in its cache), `nthreads` threads;
+ *   mode 1  "reference-faithful": one OCP after the other; the stage loops are `omp parallel for num_threads(nthreads)` like
+ *           DirectMultipleShooting (src/ocp/direct_multiple_shooting.cpp:135-154, 184-199, 218-241; the examples use
+ *           nthreads = 4) and the Riccati recursion is serial (src/riccati/riccati_recursion.cpp:39,94).
+ * Returns the OR of the Cholesky flags. */
+int orc_riccati_backward(const rbt_dims* dims, const rbt_stage_ctrl* ctrl, int n_grid, double max_dts0, double* kkt, double* ric);
+void orc_riccati_forward(const rbt_dims* dims, const rbt_stage_ctrl* ctrl, int n_grid, const double* kkt, const double* ric, double* d);
+
+int orc_iteration_batch(const rbt_stage_dims* sd, const rbt_constraint_table* tab, const rbt_stage_ctrl* ctrl, int n_grid,
+                        int batch, double max_dts0, const double* lin, double* con, double* kkt, double* ex, double* ric,
+                        const double* dx0, double* d, double* xd, double* sol, double* steps, int mode, int nthreads) {
+  rbt_stage_layout S;
+  rbt_make_stage_layout(sd, &S);
+  rbt_dims kd = {sd->nv, sd->nu, sd->ns_max, sd->n_passive};
+  rbt_layout K;
+  rbt_make_layout(&kd, &K);
+  int info = 0;
+  if (nthreads < 1) nthreads = 1;
+  if (mode == 0) {
+#pragma omp parallel for schedule(dynamic) reduction(| : info) num_threads(nthreads)
+    for (int b = 0; b < batch; ++b) {
+      const size_t o0 = (size_t)b * n_grid;
+      for (int i = 0; i < n_grid; ++i)
+        info |= orc_stage_condense(sd, tab, &ctrl[i], lin + (o0 + i) * S.l_stride, con + (o0 + i) * S.c_stride,
+                                   kkt + (o0 + i) * K.k_stride, ex + (o0 + i) * S.e_stride);
+      info |= orc_riccati_backward(&kd, ctrl, n_grid, max_dts0, kkt + o0 * K.k_stride, ric + o0 * K.r_stride);
+      memcpy(d + o0 * K.d_stride + K.d_dx, dx0 + (size_t)b * K.nx, sizeof(double) * K.nx);
+      orc_riccati_forward(&kd, ctrl, n_grid, kkt + o0 * K.k_stride, ric + o0 * K.r_stride, d + o0 * K.d_stride);
+      double mp = 1.0, md = 1.0;
+      for (int i = 0; i < n_grid; ++i) {
+        double st[2];
+        orc_stage_expand_primal(sd, tab, &ctrl[i], lin + (o0 + i) * S.l_stride, ex + (o0 + i) * S.e_stride,
+                                d + (o0 + i) * K.d_stride, con + (o0 + i) * S.c_stride, xd + (o0 + i) * S.x_stride, st);
+        if (st[0] < mp) mp = st[0];
+        if (st[1] < md) md = st[1];
+      }
+      steps[2 * b] = mp;
+      steps[2 * b + 1] = md;
+      for (int i = 0; i < n_grid; ++i) {
+        const double* dn = (i + 1 < n_grid) ? d + (o0 + i + 1) * K.d_stride : NULL;
+        orc_stage_expand_dual_update(sd, tab, &ctrl[i], ex + (o0 + i) * S.e_stride, d + (o0 + i) * K.d_stride, dn,
+                                     xd + (o0 + i) * S.x_stride, con + (o0 + i) * S.c_stride, sol + (o0 + i) * S.s_stride, mp, md);
+      }
+    }
+    return info;
+  }
+  for (int b = 0; b < batch; ++b) {
+    const size_t o0 = (size_t)b * n_grid;
+#pragma omp parallel for reduction(| : info) num_threads(nthreads)
+    for (int i = 0; i < n_grid; ++i)
+      info |= orc_stage_condense(sd, tab, &ctrl[i], lin + (o0 + i) * S.l_stride, con + (o0 + i) * S.c_stride,
+                                 kkt + (o0 + i) * K.k_stride, ex + (o0 + i) * S.e_stride);
+    info |= orc_riccati_backward(&kd, ctrl, n_grid, max_dts0, kkt + o0 * K.k_stride, ric + o0 * K.r_stride);
+    memcpy(d + o0 * K.d_stride + K.d_dx, dx0 + (size_t)b * K.nx, sizeof(double) * K.nx);
+    orc_riccati_forward(&kd, ctrl, n_grid, kkt + o0 * K.k_stride, ric + o0 * K.r_stride, d + o0 * K.d_stride);
+    double mp = 1.0, md = 1.0;
+#pragma omp parallel for reduction(min : mp, md) num_threads(nthreads)
+    for (int i = 0; i < n_grid; ++i) {
+      double st[2];
+      orc_stage_expand_primal(sd, tab, &ctrl[i], lin + (o0 + i) * S.l_stride, ex + (o0 + i) * S.e_stride,
+                              d + (o0 + i) * K.d_stride, con + (o0 + i) * S.c_stride, xd + (o0 + i) * S.x_stride, st);
+      if (st[0] < mp) mp = st[0];
+      if (st[1] < md) md = st[1];
+    }
+    steps[2 * b] = mp;
+    steps[2 * b + 1] = md;
+    /* as in the reference's own stage-parallel integrateSolution: stage i reads dgmm of stage i+1, which the costate
+     * correction of stage i+1 never writes (it only rewrites the head of dlmd) */
+#pragma omp parallel for num_threads(nthreads)
+    for (int i = 0; i < n_grid; ++i) {
+      const double* dn = (i + 1 < n_grid) ? d + (o0 + i + 1) * K.d_stride : NULL;
+      orc_stage_expand_dual_update(sd, tab, &ctrl[i], ex + (o0 + i) * S.e_stride, d + (o0 + i) * K.d_stride, dn,
+                                   xd + (o0 + i) * S.x_stride, con + (o0 + i) * S.c_stride, sol + (o0 + i) * S.s_stride, mp, md);
+    }
+  }
   return info;
 }

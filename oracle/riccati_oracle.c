@@ -31,46 +31,7 @@ int orc_debug_exact_chi = 0; /* see the switching-constraint STO terms below; ne
 int orc_debug_exact_transition = 0; /* phase transition with the rank-one term of P (tests only), see phase_transition() */
 int orc_debug_exact_impact_costate = 0; /* costate at an impact grid with -Phi * (this event's dts) (tests only) */
 
-/* C(m x n) = beta*C + alpha * op(A) * op(B);  ta/tb: 0 = as is, 1 = transposed.
- * Loop forms are chosen so that gcc vectorises them (column axpy for op(A)=A, simd dot products over contiguous
- * columns for op(A)=A^T) -- the CPU baseline should be a fair stand-in for the reference's Eigen kernels. */
-static void gemm(int ta, int tb, int m, int n, int k, double alpha, const double* restrict A, int lda,
-                 const double* restrict B, int ldb, double beta, double* restrict C, int ldc) {
-  if (!ta) {
-    for (int j = 0; j < n; ++j) {
-      double* restrict c = C + (size_t)j * ldc;
-      if (beta == 0.0) {
-        for (int i = 0; i < m; ++i) c[i] = 0.0;
-      } else if (beta != 1.0) {
-        for (int i = 0; i < m; ++i) c[i] *= beta;
-      }
-      for (int l = 0; l < k; ++l) {
-        const double b = alpha * (tb ? B[IDX(j, l, ldb)] : B[IDX(l, j, ldb)]);
-        const double* restrict a = A + (size_t)l * lda;
-#pragma omp simd
-        for (int i = 0; i < m; ++i) c[i] += a[i] * b;
-      }
-    }
-  } else if (!tb) {
-    for (int j = 0; j < n; ++j) {
-      const double* restrict b = B + (size_t)j * ldb;
-      for (int i = 0; i < m; ++i) {
-        const double* restrict a = A + (size_t)i * lda;
-        double acc = 0.0;
-#pragma omp simd reduction(+ : acc)
-        for (int l = 0; l < k; ++l) acc += a[l] * b[l];
-        C[IDX(i, j, ldc)] = (beta == 0.0 ? 0.0 : beta * C[IDX(i, j, ldc)]) + alpha * acc;
-      }
-    }
-  } else {
-    for (int j = 0; j < n; ++j)
-      for (int i = 0; i < m; ++i) {
-        double acc = 0.0;
-        for (int l = 0; l < k; ++l) acc += A[IDX(l, i, lda)] * B[IDX(j, l, ldb)];
-        C[IDX(i, j, ldc)] = (beta == 0.0 ? 0.0 : beta * C[IDX(i, j, ldc)]) + alpha * acc;
-      }
-  }
-}
+#include "orc_linalg.h"  /* gemm(): register-blocked small GEMM shared by the oracle sources */
 
 static double dot(int n, const double* a, const double* b) {
   double s = 0.0;
