@@ -357,7 +357,9 @@ def main():
     # the Newton step lives in a torch tensor so NCCL can gather it in place
     d_local = torch.zeros((args.batch, n_grid, K.d_stride), dtype=torch.float64, device="cuda")
     rr.bind_buffer(DIR, ctypes.c_void_p(d_local.data_ptr()))
-    d_all = torch.empty((world * args.batch, n_grid, K.d_stride), dtype=torch.float64, device="cuda") if world > 1 else None
+    step_dbl = int(lib.rbt_step_doubles(rr._h))  # dx | du | dlmd,dgmm | dxi | dts,dts_next: the used prefix of a direction record
+    d_pack = torch.zeros((args.batch, n_grid, step_dbl), dtype=torch.float64, device="cuda") if world > 1 else None
+    d_all = torch.empty((world * args.batch, n_grid, step_dbl), dtype=torch.float64, device="cuda") if world > 1 else None
 
     # ---- device-resident arm: upload once; every step re-reads the same linearisation / PDIPM / solution records
     dms.condense(lin, con, stream=sp)
@@ -386,6 +388,21 @@ def main():
 
     NAMES = ["condense_total", "riccati_backward", "riccati_forward", "expand_step_sizes", "update"]
 
+    pending = [False]  # a packed step waits to be gathered
+
+    def gather_pending(ev=None):
+        # one NCCL all-gather of the previous iteration's packed step, on its own stream, launched once the condensing of the
+        # current iteration has been issued: it then overlaps the (latency / shared-memory bound) backward sweep instead of the
+        # HBM-bound condensing kernels
+        comm.wait_stream(stream)
+        with torch.cuda.stream(comm):
+            if ev is not None:
+                ev[8].record(comm)
+            allgather_step(d_pack, out=d_all)
+            if ev is not None:
+                ev[6].record(comm)
+        pending[0] = False
+
     def step(ev=None):
         # restore the records the iteration mutates (D2D, outside the per-kernel event pairs but inside the step time)
         con_work.copy_(con_dev0)
@@ -394,8 +411,6 @@ def main():
                  lambda: rr.forwardRiccatiRecursion(stream=sp), lambda: dms.computeStepSizes(stream=sp),
                  lambda: dms.integrateSolution(stream=sp)]
         for k, call in enumerate(calls):
-            if world > 1 and k == 2:
-                stream.wait_stream(comm)  # the forward sweep overwrites the direction records the previous gather reads
             if ev is not None:
                 ev[k].record(stream)
                 if k == 0:  # rbt_condense = MJtJinv kernel + condensing kernel: an event between them splits the two
@@ -404,22 +419,21 @@ def main():
             call()
             if ev is not None and k == 0:
                 lib.rbt_set_condense_event(rr._h, None)
+            if world > 1 and k == 0 and pending[0]:
+                gather_pending(ev)
         if ev is not None:
             ev[len(calls)].record(stream)
         if world > 1:
-            # the Newton step of every OCP on every rank: one NCCL all-gather, on its own stream so that it overlaps the
-            # condensing and the backward sweep of the next iteration (it only has to finish before the next forward sweep)
-            comm.wait_stream(stream)
-            with torch.cuda.stream(comm):
-                if ev is not None:
-                    ev[8].record(comm)
-                allgather_step(d_local, out=d_all)
-                if ev is not None:
-                    ev[len(calls) + 1].record(comm)
+            stream.wait_stream(comm)  # the previous gather has finished reading the pack buffer
+            rc = lib.rbt_pack_step(rr._h, ctypes.c_void_p(d_pack.data_ptr()), sp)
+            assert rc == 0, rr._err()
+            pending[0] = True
 
     comm = torch.cuda.Stream() if world > 1 else None
     for _ in range(max(args.warmup, 3)):
         step()
+    if world > 1:
+        gather_pending()
     torch.cuda.synchronize()
     l0 = rr.launch_count()
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(9)] for _ in range(args.steps)]
@@ -435,7 +449,8 @@ def main():
     for k in range(args.steps):
         step(evs[k])
     if world > 1:
-        stream.wait_stream(comm)  # the last gather is inside the timed region
+        gather_pending()          # the last step's gather is inside the timed region
+        stream.wait_stream(comm)
     t_end.record(stream)
     torch.cuda.synchronize()
     if world > 1:
@@ -448,7 +463,7 @@ def main():
     kms["mjtjinv"] = float(np.mean([e[0].elapsed_time(e[7]) for e in evs]))
     kms["condense"] = float(np.mean([e[7].elapsed_time(e[1]) for e in evs]))
     if world > 1:
-        kms["nccl_allgather_step"] = float(np.mean([e[8].elapsed_time(e[6]) for e in evs]))  # timed on the comm stream
+        kms["nccl_allgather_step"] = float(np.mean([e[8].elapsed_time(e[6]) for e in evs[1:]]))  # on the comm stream (steps 2..K)
     print(f"[bench] rank {rank}: {ms / args.steps:.3f} ms/step on its own device clock", file=sys.stderr, flush=True)
     if world > 1:
         tt = torch.tensor([ms], dtype=torch.float64, device="cuda")
@@ -457,7 +472,7 @@ def main():
     assert int(rr.info().max()) == 0, "Cholesky failure flagged on device"
     if world > 1:  # config 5: this rank's shard of the gathered step is the step the oracle computes for these OCPs
         shard = d_all[rank * args.batch:(rank + 1) * args.batch].cpu().numpy()
-        nxu = K.d_dxi
+        nxu = min(K.d_dxi, step_dbl)
         err = np.max(np.abs(shard[..., :nxu] - d_ref_dir[..., :nxu])) / np.max(np.abs(d_ref_dir[..., :nxu]))
         assert err < 1e-8, f"rank {rank}: gathered step disagrees with the oracle ({err:.2e})"
     sol_dev = dms.getSolution()

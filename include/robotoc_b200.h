@@ -48,7 +48,9 @@ enum {
   RBT_BUF_EXP = 8,   /* expansion records (MJtJinv, MJtJinv_dIDCdqv, ... kept by condensing for the expansion) */
   RBT_BUF_SOL = 9,   /* solution records (q, v, a, dv, u, f, lmd, gmm, beta, mu, nu_passive, xi), updated in place */
   RBT_BUF_XDIR = 10, /* expanded direction records (daf, dbetamu, dnu_passive) */
-  RBT_BUF_STEPS = 11 /* [batch][2] max primal / dual step size over the horizon */
+  RBT_BUF_STEPS = 11,/* [batch][2] max primal / dual step size over the horizon */
+  RBT_BUF_PERF = 12  /* [batch][8] PerformanceIndex of rbt_eval_kkt: {cost (0: not evaluated on this path), cost_barrier,
+                        primal_feasibility, dual_feasibility, kkt_error, sqrt(kkt_error) = OCPSolver::KKTError(), 0, 0} */
 };
 
 typedef struct rbt_handle rbt_handle;
@@ -144,6 +146,22 @@ int rbt_expand_and_step_sizes(rbt_handle* h, void* stream);
  * expandDual, correctCostateDirection, SplitSolution::integrate, updateSlack / updateDual. */
 int rbt_update(rbt_handle* h, void* stream);
 
+/* The PerformanceIndex that {Intermediate,Impact,Terminal}Stage::evalKKT summarise before condensing and
+ * DirectMultipleShooting::evalKKT sums over the horizon (src/ocp/intermediate_stage.cpp:128-132, impact_stage.cpp:109-113,
+ * terminal_stage.cpp:97-100, src/ocp/direct_multiple_shooting.cpp:155-158): squared KKT error (SplitKKTResidual::KKTError,
+ * split_kkt_residual.hxx:90-104, + contact dynamics + constraints), primal / dual feasibility (l1), log barrier
+ * (pdipm.hxx:194-200) -- per OCP into RBT_BUF_PERF, whose entry 5 is OCPSolver::KKTError() (ocp_solver.cpp:429-431), the
+ * quantity the SQP loop compares with kkt_tol (ocp_solver.cpp:183-208).  Reads RBT_BUF_LIN and RBT_BUF_CON as uploaded (it does
+ * not depend on rbt_condense having run).  The stage cost itself belongs to the cost evaluation (out of scope): entry 0 is 0. */
+int rbt_eval_kkt(rbt_handle* h, void* stream);
+/* pdipm::setSlackAndDualPositive (include/robotoc/constraints/pdipm.hxx:13-24) on RBT_BUF_CON: slack <- max(slack, sqrt(barrier)),
+ * dual <- barrier / slack -- what Constraints::setSlackAndDual applies when a solver is initialised (initConstraints). */
+int rbt_set_slack_and_dual_positive(rbt_handle* h, void* stream);
+/* computeInitialStateDirection (src/dynamics/state_equation.cpp:98-109) into RBT_BUF_DX0.  dq0_v0_host: [batch][2 nv] =
+ * {q0 (-) s[0].q from Robot::subtractConfiguration (the robot model stays on the host), v0}; uses the stage-0 Fqq_prev_inv that
+ * rbt_condense left in RBT_BUF_EXP and s[0].v of RBT_BUF_SOL, so call it after rbt_condense and before rbt_riccati_forward. */
+int rbt_initial_state_direction(rbt_handle* h, const double* dq0_v0_host, void* stream);
+
 /* One hot-path iteration with HOST buffers -- the linear-algebra body of OCPSolver::updateSolution
  * (src/solver/ocp_solver.cpp:118-144) given the stage linearisations: upload lin / con / sol / dx0, condense, backward and
  * forward Riccati, step sizes, update, download the updated solution, the PDIPM data and the step sizes (NULL = skip). */
@@ -166,6 +184,20 @@ int rbt_iteration_host_wire(rbt_handle* h, const double* wire_host, const double
                             double* steps_out, void* stream);
 int rbt_wire_doubles(const rbt_stage_dims* sdims);
 int rbt_pack_wire(const rbt_stage_dims* sdims, const double* lin_host, double* wire_host, long long n_records);
+
+/* Multi-GPU: OCP instances are independent, so a batch is sharded over ranks without any data-path collective;
+ * the one exchange is the Newton step of every OCP on every rank, e.g. for a host that advances all trajectories.
+ * rbt_allgather_step packs this rank's direction records to their used prefix -- rbt_step_doubles(h) = dx | du | dlmd,dgmm | dxi |
+ * dts,dts_next per grid point (98 of the 112-double record stride for ANYmal) -- and issues ONE ncclAllGather on `stream`:
+ * all_dev receives [nranks][batch][n_grid][rbt_step_doubles] doubles (device memory of this rank).  `nccl_comm` is the caller's
+ * ncclComm_t; NCCL is looked up in the calling process (dlsym, then libnccl.so.2), the library does not link against it.
+ * Put the call on its own stream to overlap it with the next iteration's condensing / backward sweep: the direction records are
+ * only overwritten by the next rbt_riccati_forward. */
+int rbt_step_doubles(rbt_handle* h);
+/* only the packing ([batch][n_grid][rbt_step_doubles] doubles into packed_dev), for a host that owns the collective itself
+ * (e.g. torch.distributed); the gather then reads the packed copy, so the next forward sweep need not wait for it */
+int rbt_pack_step(rbt_handle* h, double* packed_dev, void* stream);
+int rbt_allgather_step(rbt_handle* h, void* nccl_comm, double* all_dev, void* stream);
 
 int rbt_sync(rbt_handle* h, void* stream);
 const char* rbt_last_error(rbt_handle* h);

@@ -799,3 +799,107 @@ int orc_iteration_batch(const rbt_stage_dims* sd, const rbt_constraint_table* ta
   }
   return info;
 }
+
+/* ---------------- rows a12 / a13 / a16 of SURVEY.md 8a: what a device-resident SQP loop needs to terminate on its own ----------
+ * Stage part of the PerformanceIndex (include/robotoc/core/performance_index.hpp) as {Intermediate,Impact,Terminal}Stage::evalKKT
+ * summarise it BEFORE condensing (intermediate_stage.cpp:128-132, impact_stage.cpp:109-113, terminal_stage.cpp:97-100):
+ *   kkt_error          = SplitKKTResidual::KKTError() (split_kkt_residual.hxx:90-104: |Fx|^2 + |P|^2 + |lx|^2 + |lu|^2 + |la|^2 +
+ *                        |ldv|^2 + |lf|^2) + ContactDynamicsData::KKTError() (|IDC|^2 + |lu_passive|^2, contact_dynamics_data.hpp:204)
+ *                        + sum over constraint components of |residual|^2 + |cmpl|^2 (constraint_component_data.hpp:122)
+ *   primal_feasibility = |Fx|_1 + |P|_1 + |IDC|_1 + |residual|_1          (the <1> instantiations)
+ *   dual_feasibility   = |lx|_1 + |la|_1 + |ldv|_1 + |lf|_1 + |lu|_1 + |lu_passive|_1 + |cmpl|_1
+ *   cost_barrier       = - barrier * sum log(slack)                        (pdipm.hxx:194-200; active rows only, friction_cone.cpp:122-139)
+ * out = {cost_barrier, primal_feasibility, dual_feasibility, kkt_error}.  The stage cost itself comes from the (out-of-scope)
+ * cost evaluation.  cmpl = slack * dual - barrier (pdipm.hxx:27-63) is recomputed here, so the call does not depend on the
+ * condensing having run. */
+void orc_stage_perf_index(const rbt_stage_dims* sd, const rbt_constraint_table* tab, const rbt_stage_ctrl* c, const double* lin,
+                          const double* con, double* out) {
+  rbt_stage_layout S;
+  rbt_make_stage_layout(sd, &S);
+  const int nv = S.nv, nu = S.nu, nx = S.nx, np = S.np, nf = c->nf;
+  double kkt = 0.0, pf = 0.0, df = 0.0, lb = 0.0;
+#define ORC_ACC_P(ptr, n) for (int q_ = 0; q_ < (n); ++q_) { const double v_ = (ptr)[q_]; kkt += v_ * v_; pf += fabs(v_); }
+#define ORC_ACC_D(ptr, n) for (int q_ = 0; q_ < (n); ++q_) { const double v_ = (ptr)[q_]; kkt += v_ * v_; df += fabs(v_); }
+  ORC_ACC_D(lin + S.l_lx, nx)
+  if (c->type != RBT_TERMINAL) {
+    const int impact = c->type == RBT_IMPACT;
+    ORC_ACC_P(lin + S.l_Fx, nx)
+    ORC_ACC_D(lin + S.l_la, nv)           /* la on a control stage, ldv on an impact stage (same slot of the record) */
+    ORC_ACC_D(lin + S.l_lf, nf)
+    ORC_ACC_P(lin + S.l_IDC, nv + nf)
+    if (!impact) {
+      ORC_ACC_D(lin + S.l_lu, nu)
+      ORC_ACC_D(lin + S.l_lup, np)
+      ORC_ACC_P(lin + S.l_p, c->ns)
+      for (int r = 0; r < S.nc; ++r) {
+        const int cone = r >= S.nbox;
+        if (cone && !((c->contact_mask >> ((r - S.nbox) / 5)) & 1)) continue;  /* inactive contact: residual = cmpl = 0 */
+        const double sl = con[S.c_slack + r], du = con[S.c_dual + r], res = con[S.c_res + r];
+        const double cm = sl * du - tab->barrier;
+        kkt += res * res + cm * cm;
+        pf += fabs(res);
+        df += fabs(cm);
+        lb -= tab->barrier * log(sl);
+      }
+    }
+  }
+#undef ORC_ACC_P
+#undef ORC_ACC_D
+  out[0] = lb; out[1] = pf; out[2] = df; out[3] = kkt;
+}
+
+/* DirectMultipleShooting::evalKKT's sum over the horizon (direct_multiple_shooting.cpp:155-158), stage order 0..N, and
+ * OCPSolver::KKTError() = sqrt(kkt_error) (ocp_solver.cpp:429-431; no STO part here).
+ * perf[b] = {cost (0: not evaluated on this path), cost_barrier, primal_feasibility, dual_feasibility, kkt_error, sqrt(kkt_error), 0, 0} */
+void orc_perf_index_batch(const rbt_stage_dims* sd, const rbt_constraint_table* tab, const rbt_stage_ctrl* ctrl, int n_grid,
+                          int batch, const double* lin, const double* con, double* perf) {
+  rbt_stage_layout S;
+  rbt_make_stage_layout(sd, &S);
+  for (int b = 0; b < batch; ++b) {
+    double acc[4] = {0, 0, 0, 0};
+    for (int i = 0; i < n_grid; ++i) {
+      const size_t o = (size_t)b * n_grid + i;
+      double st[4];
+      orc_stage_perf_index(sd, tab, &ctrl[i], lin + o * S.l_stride, con + o * S.c_stride, st);
+      for (int q = 0; q < 4; ++q) acc[q] += st[q];
+    }
+    double* p = perf + (size_t)b * 8;
+    p[0] = 0.0; p[1] = acc[0]; p[2] = acc[1]; p[3] = acc[2]; p[4] = acc[3]; p[5] = sqrt(acc[3]); p[6] = 0.0; p[7] = 0.0;
+  }
+}
+
+/* pdipm::setSlackAndDualPositive (pdipm.hxx:13-24) on every inequality row of every constrained stage:
+ * slack <- max(slack, sqrt(barrier)), dual <- barrier / slack. */
+void orc_set_slack_dual_positive_batch(const rbt_stage_dims* sd, const rbt_constraint_table* tab, const rbt_stage_ctrl* ctrl,
+                                       int n_grid, int batch, double* con) {
+  rbt_stage_layout S;
+  rbt_make_stage_layout(sd, &S);
+  const double sb = sqrt(tab->barrier);
+  for (int b = 0; b < batch; ++b)
+    for (int i = 0; i < n_grid; ++i) {
+      if (ctrl[i].type == RBT_TERMINAL || ctrl[i].type == RBT_IMPACT) continue;
+      double* cc = con + ((size_t)b * n_grid + i) * S.c_stride;
+      for (int r = 0; r < S.nc; ++r) {
+        if (cc[S.c_slack + r] < sb) cc[S.c_slack + r] = sb;
+        cc[S.c_dual + r] = tab->barrier / cc[S.c_slack + r];
+      }
+    }
+}
+
+/* computeInitialStateDirection (src/dynamics/state_equation.cpp:98-109) given dq_raw = q0 (-) s0.q from the robot model
+ * (Robot::subtractConfiguration is Pinocchio's, out of scope): dq[0:6] = -Fqq_prev_inv dq_raw[0:6] for a floating base,
+ * dv = v0 - s0.v.  ex0 / sol0 = expansion / solution record of stage 0 of this OCP; dx0 has nx entries. */
+void orc_initial_state_direction(const rbt_stage_dims* sd, const double* ex0, const double* sol0, const double* dq_raw,
+                                 const double* v0, double* dx0) {
+  rbt_stage_layout S;
+  rbt_make_stage_layout(sd, &S);
+  const int nv = S.nv;
+  for (int i = 0; i < nv; ++i) dx0[i] = dq_raw[i];
+  if (S.np == 6)
+    for (int i = 0; i < 6; ++i) {
+      double a = 0.0;
+      for (int l = 0; l < 6; ++l) a += ex0[S.e_Fqqpi + IDX(i, l, 6)] * dq_raw[l];
+      dx0[i] = -a;
+    }
+  for (int i = 0; i < nv; ++i) dx0[nv + i] = v0[i] - sol0[S.s_v + i];
+}

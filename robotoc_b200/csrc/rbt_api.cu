@@ -8,6 +8,7 @@
 #include <vector>
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <cstdlib>
@@ -18,6 +19,7 @@
 #include "riccati_unconstr.cuh"
 #include "stage_kernels.cuh"
 #include "ustage_kernels.cuh"
+#include "eval_kernels.cuh"
 
 namespace {
 
@@ -65,6 +67,8 @@ struct rbt_handle {
   rbt_constraint_table table;
   double *d_lin = nullptr, *d_con = nullptr, *d_ex = nullptr, *d_sol = nullptr, *d_xd = nullptr, *d_steps = nullptr,
          *d_ones = nullptr;
+  double *d_stage_perf = nullptr, *d_perf = nullptr, *d_x0in = nullptr;  // eval_kernels.cuh
+  double* d_step_pack = nullptr;  // packed Newton step of this rank (rbt_allgather_step), allocated on first use
   int timeline_cta = -1;
   long long launches = 0;
   // batch window [cb0, cb0 + cnb) the launch helpers work on (cnb == 0: the whole batch); used by rbt_iteration_host to
@@ -211,6 +215,10 @@ int rbt_destroy(rbt_handle* h) {
   cudaFree(h->d_timeline);
   cudaFree(h->d_steps);
   cudaFree(h->d_ones);
+  cudaFree(h->d_step_pack);
+  cudaFree(h->d_stage_perf);
+  cudaFree(h->d_perf);
+  cudaFree(h->d_x0in);
   delete h;
   return RBT_OK;
 }
@@ -273,6 +281,7 @@ static double* buf_ptr(rbt_handle* h, int which) {
     case RBT_BUF_SOL: return h->d_sol;
     case RBT_BUF_XDIR: return h->d_xd;
     case RBT_BUF_STEPS: return h->d_steps;
+    case RBT_BUF_PERF: return h->d_perf;
     default: return nullptr;
   }
 }
@@ -288,6 +297,7 @@ long long rbt_buf_doubles(rbt_handle* h, int which) {
     case RBT_BUF_SOL: return per * h->S.s_stride;
     case RBT_BUF_XDIR: return per * h->S.x_stride;
     case RBT_BUF_STEPS: return 2LL * h->batch;
+    case RBT_BUF_PERF: return 8LL * h->batch;
     case RBT_BUF_KKT: return per * h->L.k_stride;
     case RBT_BUF_RIC: return per * h->L.r_stride;
     case RBT_BUF_FACT: return per * h->L.f_stride;
@@ -641,6 +651,10 @@ int rbt_stage_setup(rbt_handle* h, const rbt_stage_dims* sd, const rbt_constrain
   RBT_CUDA(h, cudaMalloc(&h->d_xd, per * h->S.x_stride * 8));
   RBT_CUDA(h, cudaMalloc(&h->d_steps, size_t(h->batch) * 2 * 8));
   RBT_CUDA(h, cudaMalloc(&h->d_ones, size_t(h->batch) * 2 * 8));
+  RBT_CUDA(h, cudaMalloc(&h->d_stage_perf, per * 4 * 8));
+  RBT_CUDA(h, cudaMalloc(&h->d_perf, size_t(h->batch) * 8 * 8));
+  RBT_CUDA(h, cudaMalloc(&h->d_x0in, size_t(h->batch) * 2 * h->dims.nv * 8));
+  RBT_CUDA(h, cudaMemset(h->d_perf, 0, size_t(h->batch) * 8 * 8));
   RBT_CUDA(h, cudaMemset(h->d_lin, 0, per * h->S.l_stride * 8));  // uploads skip record padding: keep it defined
   RBT_CUDA(h, cudaMemset(h->d_sol, 0, per * h->S.s_stride * 8));
   RBT_CUDA(h, cudaMemset(h->d_ex, 0, per * h->S.e_stride * 8));
@@ -736,6 +750,52 @@ int rbt_expand_and_step_sizes(rbt_handle* h, void* stream) {
 int rbt_update(rbt_handle* h, void* stream) {
   RBT_STAGE_CHECK(h, "rbt_update");
   rbt::update_kernel<18, 12, 12><<<win_nb(h) * h->n_grid, rbt::XTHR, 0, (cudaStream_t)stream>>>(make_stage_params(h));
+  RBT_CUDA(h, cudaGetLastError());
+  h->launches += 1;
+  return RBT_OK;
+}
+
+static rbt::EvalParams make_eval_params(rbt_handle* h) {
+  rbt::EvalParams q;
+  q.sp = make_stage_params(h);
+  const int b0 = win_b0(h);
+  q.stage_perf = h->d_stage_perf + size_t(b0) * h->n_grid * 4;
+  q.perf = h->d_perf + size_t(b0) * 8;
+  q.x0in = h->d_x0in + size_t(b0) * 2 * h->dims.nv;
+  q.dx0 = h->d_dx0 + size_t(b0) * h->L.nx;
+  return q;
+}
+
+int rbt_eval_kkt(rbt_handle* h, void* stream) {
+  RBT_STAGE_CHECK(h, "rbt_eval_kkt");
+  cudaStream_t st = (cudaStream_t)stream;
+  const rbt::EvalParams q = make_eval_params(h);
+  const int nb = win_nb(h);
+  rbt::perf_index_kernel<<<(nb * h->n_grid + 3) / 4, 128, 0, st>>>(q);
+  rbt::perf_reduce_kernel<<<(nb + 127) / 128, 128, 0, st>>>(q);
+  RBT_CUDA(h, cudaGetLastError());
+  h->launches += 2;
+  return RBT_OK;
+}
+
+int rbt_set_slack_and_dual_positive(rbt_handle* h, void* stream) {
+  RBT_STAGE_CHECK(h, "rbt_set_slack_and_dual_positive");
+  const rbt::EvalParams q = make_eval_params(h);
+  const long long total = (long long)win_nb(h) * h->n_grid * h->S.ncp;
+  rbt::slack_dual_positive_kernel<<<unsigned((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(q);
+  RBT_CUDA(h, cudaGetLastError());
+  h->launches += 1;
+  return RBT_OK;
+}
+
+int rbt_initial_state_direction(rbt_handle* h, const double* dq0_v0_host, void* stream) {
+  RBT_STAGE_CHECK(h, "rbt_initial_state_direction");
+  if (!dq0_v0_host) return RBT_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  RBT_CUDA(h, cudaMemcpyAsync(h->d_x0in, dq0_v0_host, size_t(h->batch) * 2 * h->dims.nv * 8, cudaMemcpyHostToDevice, st));
+  const rbt::EvalParams q = make_eval_params(h);
+  const int total = win_nb(h) * h->L.nx;
+  rbt::initial_state_direction_kernel<<<(total + 127) / 128, 128, 0, st>>>(q);
   RBT_CUDA(h, cudaGetLastError());
   h->launches += 1;
   return RBT_OK;
@@ -927,6 +987,72 @@ int rbt_riccati_solve_host(rbt_handle* h, const double* kkt_host, const double* 
   if ((rc = rbt_riccati_forward(h, stream))) return rc;
   if (ric_host && (rc = rbt_download(h, RBT_BUF_RIC, ric_host, stream))) return rc;
   if (dir_host && (rc = rbt_download(h, RBT_BUF_DIR, dir_host, stream))) return rc;
+  return RBT_OK;
+}
+
+// ---- multi-GPU: the Newton step of every OCP on every rank ----------------------------------------------------------------
+namespace {
+// NCCL is reached through dlsym so that the library neither links against a particular libnccl nor fails to load without
+// one: the communicator belongs to the host application, and it is the host's NCCL that must execute the collective.
+typedef int (*nccl_allgather_fn)(const void*, void*, size_t, int, void*, cudaStream_t);
+nccl_allgather_fn find_nccl_allgather() {
+  static nccl_allgather_fn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* sym = dlsym(RTLD_DEFAULT, "ncclAllGather");  // the NCCL the host process already uses
+    if (!sym) {
+      void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+      if (lib) sym = dlsym(lib, "ncclAllGather");
+    }
+    fn = reinterpret_cast<nccl_allgather_fn>(sym);
+  }
+  return fn;
+}
+
+// direction records (stride d_stride) -> packed step records (the used prefix dx | du | dlmd,dgmm | dxi | dts,dts_next)
+__global__ void pack_step_kernel(const double* __restrict__ dir, double* __restrict__ out, int d_stride, int step, long long n_rec) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_rec * step) return;
+  const long long rec = e / step;
+  const int k = int(e % step);
+  out[e] = dir[rec * d_stride + k];
+}
+}  // namespace
+
+int rbt_step_doubles(rbt_handle* h) { return h ? h->L.d_dts + 2 : -1; }
+
+int rbt_pack_step(rbt_handle* h, double* packed_dev, void* stream) {
+  if (!h || !packed_dev) return RBT_ERR_ARG;
+  if (h->n_grid == 0) return RBT_ERR_STATE;
+  RBT_CUDA(h, cudaSetDevice(h->device));
+  const int step = h->L.d_dts + 2;
+  const long long n_rec = (long long)h->batch * h->n_grid;
+  pack_step_kernel<<<unsigned((n_rec * step + 255) / 256), 256, 0, (cudaStream_t)stream>>>(h->d_dir, packed_dev, h->L.d_stride, step, n_rec);
+  RBT_CUDA(h, cudaGetLastError());
+  h->launches += 1;
+  return RBT_OK;
+}
+
+int rbt_allgather_step(rbt_handle* h, void* nccl_comm, double* all_dev, void* stream) {
+  if (!h || !nccl_comm || !all_dev) return RBT_ERR_ARG;
+  if (h->n_grid == 0) return RBT_ERR_STATE;
+  nccl_allgather_fn allgather = find_nccl_allgather();
+  if (!allgather) {
+    h->err = "[rbt_allgather_step] no NCCL in this process (ncclAllGather not found, libnccl.so.2 not loadable)";
+    return RBT_ERR_STATE;
+  }
+  RBT_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int step = h->L.d_dts + 2;
+  const long long n_rec = (long long)h->batch * h->n_grid;
+  if (!h->d_step_pack) RBT_CUDA(h, cudaMalloc(&h->d_step_pack, size_t(h->batch) * h->n_grid_max * step * 8));
+  if (int prc = rbt_pack_step(h, h->d_step_pack, stream)) return prc;
+  const int rc = allgather(h->d_step_pack, all_dev, size_t(n_rec) * step, /*ncclFloat64*/ 8, nccl_comm, st);
+  if (rc != 0) {
+    h->err = "[rbt_allgather_step] ncclAllGather failed with ncclResult_t " + std::to_string(rc);
+    return RBT_ERR_CUDA;
+  }
   return RBT_OK;
 }
 

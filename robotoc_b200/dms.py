@@ -16,7 +16,7 @@ import numpy as np
 from .riccati import RiccatiRecursion, _check, _vp
 from .stage import StageDims, StageLayout
 
-LIN, CON, EXP, SOL, XDIR, STEPS = 6, 7, 8, 9, 10, 11
+LIN, CON, EXP, SOL, XDIR, STEPS, PERF = 6, 7, 8, 9, 10, 11, 12
 
 
 class DirectMultipleShooting:
@@ -70,6 +70,40 @@ class DirectMultipleShooting:
         if sol is not None:
             self._up(SOL, sol, self.layout.s_stride, stream)
         _check(self._lib.rbt_update(self._h, stream), self.rr._err, "DirectMultipleShooting")
+
+    def evalKKT(self, lin=None, con=None, stream=None):
+        """The PerformanceIndex of DirectMultipleShooting::evalKKT (direct_multiple_shooting.cpp:129-158) from the stage
+        linearisations: returns [batch, 8] = {cost (0), cost_barrier, primal_feasibility, dual_feasibility, kkt_error,
+        KKTError() = sqrt(kkt_error), 0, 0} per OCP."""
+        if lin is not None:
+            self._up(LIN, lin, self.layout.l_stride, stream)
+        if con is not None:
+            self._up(CON, con, self.layout.c_stride, stream)
+        _check(self._lib.rbt_eval_kkt(self._h, stream), self.rr._err, "DirectMultipleShooting")
+        return self._down(PERF, (self.rr.batch, 8), stream)
+
+    def KKTError(self, stream=None):
+        """OCPSolver::KKTError() (ocp_solver.cpp:429-431) per OCP, of the records currently on the device."""
+        return self.evalKKT(stream=stream)[:, 5]
+
+    def setSlackAndDualPositive(self, con=None, stream=None):
+        """pdipm::setSlackAndDualPositive (pdipm.hxx:13-24) on the device-resident PDIPM records."""
+        if con is not None:
+            self._up(CON, con, self.layout.c_stride, stream)
+        _check(self._lib.rbt_set_slack_and_dual_positive(self._h, stream), self.rr._err, "DirectMultipleShooting")
+
+    def computeInitialStateDirection(self, dq0, v0, stream=None):
+        """direct_multiple_shooting.cpp:161-165 -> state_equation.cpp:98-109.  dq0 = q0 (-) s[0].q ([batch, nv], from the host's
+        robot model), v0 [batch, nv]; leaves d[0].dx in the handle's dx0 buffer (what forwardRiccatiRecursion starts from)."""
+        nv = self.sdims.dims.nv
+        if dq0.shape != (self.rr.batch, nv) or v0.shape != (self.rr.batch, nv):
+            raise ValueError("[DirectMultipleShooting] invalid argument: dq0 and v0 must be [batch, nv]")
+        buf = np.ascontiguousarray(np.concatenate([dq0, v0], axis=1))
+        _check(self._lib.rbt_initial_state_direction(self._h, _vp(buf), stream), self.rr._err, "DirectMultipleShooting")
+        self.rr.synchronize(stream)  # `buf` is a temporary: the copy must have been issued from live memory
+
+    def getInitialStateDirection(self, stream=None):
+        return self._down(4, (self.rr.batch, self.rr.dims.nx), stream)
 
     def iteration_host(self, lin, con, sol, dx0, stream=None):
         """The linear-algebra body of OCPSolver::updateSolution (src/solver/ocp_solver.cpp:118-144) in ONE call with host
