@@ -4,15 +4,20 @@
  * primal / dual expansion, fraction-to-boundary step sizes and the primal/dual update.
  *
  * Plain-C restatement of the reference (robotoc @ d30d404), every function citing the lines it follows.
- * PARITY STATUS: the reference cannot be built here (Eigen3 / Pinocchio absent) and holds no golden vectors: against the
- * reference BINARY this file is "parity unpinned".  It is pinned by identities that do not reuse its formulas
- * (tests/test_oracle_condense.py): MJtJinv == dense inverse; condensed quadratic model == uncondensed model with (a, f)
- * substituted; PDIPM condensing == J^T diag(z/s) J, J^T cond; primal expansion satisfies the linearised contact dynamics;
- * dual expansion (dbeta, dmu, dnu_passive; intermediate / lift / switching / impact stages, with and without STO) makes the
- * uncondensed stage Lagrangian stationary in a, f, u and the passive torques; STO sensitivities == substituted Hamiltonian
- * derivatives; switching-constraint blocks == substituted constraint; slack / dual directions solve the linearised PDIPM
- * system and the step sizes are the admissible fraction-to-boundary minima; SE(3) state-equation / costate corrections
- * satisfy E*F = -G; the free-flyer integration equals the SE(3) exponential built with scipy's Rotation.
+ * PARITY STATUS: PINNED against the reference's own code.  /root/reference/src/dynamics/{contact_dynamics,impact_dynamics,
+ * state_equation,impact_state_equation,terminal_state_equation,...}.cpp, src/constraints/{constraints,friction_cone,joint_*_limit,
+ * constraint_component_*}.cpp and src/core are compiled UNMODIFIED (oracle/Makefile.ref, Eigen / Robot stand-ins of oracle/shim)
+ * and driven stage by stage in the order Intermediate/Impact/TerminalStage use them (oracle/ref_wrap/ref_stage_wrap.cpp);
+ * tests/test_golden_ref_stage.py compares a FULL iteration of this file + riccati_oracle.c with a full iteration of that code
+ * (condensed KKT records, every expansion block, cmpl / cond / dslack / ddual, step sizes, dual expansion, costate correction,
+ * updated slack / dual) on event schedules with and without STO and on the BASELINE trot N=40 schedule: agreement < 1e-10
+ * (measured 1e-14), and against the committed reference output tests/golden/golden_ref_stage_r2.npz.  Not covered by the
+ * reference code here: Robot::computeMJtJinv (Pinocchio; dense restatement on both sides) and SplitSolution::integrate's SE(3)
+ * exponential (Pinocchio; pinned against scipy's Rotation in tests/test_oracle_condense.py).
+ * Additionally pinned by identities that do not reuse its formulas (tests/test_oracle_condense.py): MJtJinv == dense inverse;
+ * condensed quadratic model == uncondensed model with (a, f) substituted; PDIPM condensing == J^T diag(z/s) J; the expansions
+ * satisfy the linearised contact dynamics / make the uncondensed stage Lagrangian stationary; STO sensitivities == substituted
+ * Hamiltonian derivatives; SE(3) corrections satisfy E*F = -G.
  * Robot::computeMJtJinv uses Pinocchio's sparse Cholesky of M; here M is factorised densely (same mathematics, different
  * rounding).  Where the reference itself departs from the exact expressions (dnu_passive has no dxi / dts term) the
  * departure is restated and documented in the tests.

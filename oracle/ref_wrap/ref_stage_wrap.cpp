@@ -1,0 +1,326 @@
+// oracle/ref_wrap/ref_stage_wrap.cpp -- TEST INFRASTRUCTURE.  One OCP stage through the REFERENCE's own stage-layer code
+// (compiled unmodified from /root/reference/src/dynamics, src/constraints, src/core; oracle/Makefile.ref), in the order
+// {Intermediate,Impact}Stage use it (src/ocp/intermediate_stage.cpp:133-203, impact_stage.cpp:115-169):
+//   Constraints::condenseSlackAndDual -> condenseContactDynamics | condenseImpactDynamics -> correctLinearize(Impact)StateEquation
+//   -> [STO scaling of intermediate_stage.cpp:140-148, seven scalings restated here: they are lines of a member function that
+//      also evaluates costs] -> expandContactDynamicsPrimal -> Constraints::expandSlackAndDual -> maxSlackStepSize / maxDualStepSize
+//   -> expandContactDynamicsDual -> correctCostateDirection -> Constraints::updateSlack / updateDual
+// Inputs and outputs are the packed records of include/rbt_stage_layout.h / rbt_layout.h, so tests hand the same arrays to
+// the oracle (oracle/condense_oracle.c) and to this wrapper.  Pinocchio-side quantities are INPUTS of the hot path (they are
+// sections of the linearization record); Robot::computeMJtJinv is the shim's dense restatement.
+#include <cassert>
+#include <cmath>
+#include <cstring>
+#include <iostream>
+#include <limits>
+#include <memory>
+#include <random>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "Eigen/Core"
+#include "Eigen/LU"
+#include "robotoc/robot/robot.hpp"
+#include "robotoc/core/split_kkt_matrix.hpp"
+#include "robotoc/core/split_kkt_residual.hpp"
+#include "robotoc/core/split_direction.hpp"
+#include "robotoc/core/split_solution.hpp"
+#include "robotoc/dynamics/contact_dynamics.hpp"
+#include "robotoc/dynamics/impact_dynamics.hpp"
+#include "robotoc/dynamics/state_equation.hpp"
+#include "robotoc/dynamics/impact_state_equation.hpp"
+#include "robotoc/dynamics/terminal_state_equation.hpp"
+#include "robotoc/constraints/constraints.hpp"
+#include "robotoc/constraints/pdipm.hpp"
+#include "robotoc/constraints/joint_position_lower_limit.hpp"
+#include "robotoc/constraints/joint_position_upper_limit.hpp"
+#include "robotoc/constraints/joint_velocity_lower_limit.hpp"
+#include "robotoc/constraints/joint_velocity_upper_limit.hpp"
+#include "robotoc/constraints/joint_torques_lower_limit.hpp"
+#include "robotoc/constraints/joint_torques_upper_limit.hpp"
+#include "robotoc/constraints/friction_cone.hpp"
+
+#include "../../include/rbt_layout.h"
+#include "../../include/rbt_stage_layout.h"
+
+namespace {
+using namespace robotoc;
+
+template <class M> void put_m(M&& dst, const double* src, int rows, int cols, int ld) {
+  for (int j = 0; j < cols; ++j) for (int i = 0; i < rows; ++i) dst(i, j) = src[i + size_t(j) * ld];
+}
+template <class V> void put_v(V&& dst, const double* src, int n) { for (int i = 0; i < n; ++i) dst(i) = src[i]; }
+template <class M> void get_m(const M& src, double* dst, int rows, int cols, int ld) {
+  for (int j = 0; j < cols; ++j) for (int i = 0; i < rows; ++i) dst[i + size_t(j) * ld] = src(i, j);
+}
+template <class V> void get_v(const V& src, double* dst, int n) { for (int i = 0; i < n; ++i) dst[i] = src(i); }
+
+// the six joint-limit components + the friction cone of examples/anymal/trot.cpp:131-148, in the row order of the table
+std::shared_ptr<Constraints> make_constraints(const Robot& robot, const rbt_constraint_table* tab) {
+  auto c = std::make_shared<Constraints>(tab->barrier, tab->fraction_to_boundary);
+  c->add("joint_position_lower", std::make_shared<JointPositionLowerLimit>(robot));
+  c->add("joint_position_upper", std::make_shared<JointPositionUpperLimit>(robot));
+  c->add("joint_velocity_lower", std::make_shared<JointVelocityLowerLimit>(robot));
+  c->add("joint_velocity_upper", std::make_shared<JointVelocityUpperLimit>(robot));
+  c->add("joint_torques_lower", std::make_shared<JointTorquesLowerLimit>(robot));
+  c->add("joint_torques_upper", std::make_shared<JointTorquesUpperLimit>(robot));
+  c->add("friction_cone", std::make_shared<FrictionCone>(robot));
+  return c;
+}
+
+// component k of the table order -> its ConstraintComponentData inside ConstraintsData
+ConstraintComponentData& component(ConstraintsData& d, int k) {
+  switch (k) {
+    case 0: return d.position_level_data[0];
+    case 1: return d.position_level_data[1];
+    case 2: return d.velocity_level_data[0];
+    case 3: return d.velocity_level_data[1];
+    case 4: return d.acceleration_level_data[0];
+    case 5: return d.acceleration_level_data[1];
+    default: return d.acceleration_level_data[2];
+  }
+}
+}  // namespace
+
+extern "C" {
+
+// Returns 0.  phase: 1 = condensing only, 2 = + primal expansion and step sizes, 3 = + dual expansion and slack / dual update.
+// con: slack | dual | residual in; cmpl, cond, dslack, ddual and the updated slack | dual out.  d is updated like the reference
+// updates SplitDirection (costate correction).  steps_stage[2] = this stage's max primal / dual step size.
+int ref_stage(const rbt_stage_dims* sd, const rbt_constraint_table* tab, const rbt_stage_ctrl* c, const double* lin, double* con,
+              double* kkt, double* ex, double* d, const double* d_next, double* xd, double* steps_stage, double alpha_p,
+              double alpha_d, int phase) {
+  rbt_stage_layout S;
+  rbt_make_stage_layout(sd, &S);
+  rbt_dims kd = {sd->nv, sd->nu, sd->ns_max, sd->n_passive};
+  rbt_layout K;
+  rbt_make_layout(&kd, &K);
+  const int nv = S.nv, nu = S.nu, nx = S.nx, np = S.np, nfm = S.nfm, nvfm = S.nvf;
+  const bool impact = c->type == RBT_IMPACT;
+  const int nf = c->nf, nvf = nv + nf, ns = impact ? 0 : c->ns;
+  Robot robot(nv, np == 6, tab->n_contacts);
+  if (c->type == RBT_TERMINAL) {
+    // TerminalStage::evalKKT tail / expandDual (terminal_stage.cpp:102-106, 139-143): the cost Hessian and gradient are the KKT
+    // record; correctLinearizeTerminalStateEquation leaves Fqq_prev_inv for the costate correction
+    memcpy(kkt + K.k_Qxx, lin + S.l_Qxx, sizeof(double) * nx * nx);
+    memcpy(kkt + K.k_lx, lin + S.l_lx, sizeof(double) * nx);
+    StateEquationData se(robot);
+    SplitKKTMatrix km(robot);
+    if (np == 6) put_m(se.Fqq_prev.topLeftCorner(6, 6), lin + S.l_se3 + 36, 6, 6, 6);
+    correctLinearizeTerminalStateEquation(se, km);
+    if (np == 6) get_m(se.Fqq_prev_inv, ex + S.e_Fqqpi, 6, 6, 6);
+    steps_stage[0] = steps_stage[1] = 1.0;
+    if (phase >= 3) {
+      SplitDirection dd(robot);
+      put_v(dd.dlmdgmm, d + K.d_dlmdgmm, nx);
+      correctCostateDirection(se, dd);
+      get_v(dd.dlmdgmm, d + K.d_dlmdgmm, nx);
+    }
+    return 0;
+  }
+  {
+    Eigen::VectorXd lim = Eigen::VectorXd::Constant(nu, 1.0);
+    robot.setJointLimits(lim, lim, -lim, lim);
+  }
+  ContactStatus contact_status = robot.createContactStatus();
+  ImpactStatus impact_status = robot.createImpactStatus();
+  for (int ci = 0; ci < tab->n_contacts; ++ci)
+    if ((c->contact_mask >> ci) & 1) {
+      if (impact) impact_status.activateImpact(ci); else contact_status.activateContact(ci);
+    }
+  SplitKKTMatrix km(robot);
+  SplitKKTResidual kr(robot);
+  km.setContactDimension(nf); kr.setContactDimension(nf);
+  km.setSwitchingConstraintDimension(ns); kr.setSwitchingConstraintDimension(ns);
+  put_m(km.Qxx, lin + S.l_Qxx, nx, nx, nx);
+  put_v(kr.lx, lin + S.l_lx, nx);
+  put_v(kr.Fx, lin + S.l_Fx, nx);
+  for (int i = 0; i < nv; ++i) (impact ? km.Qdvdv : km.Qaa)(i, i) = lin[S.l_Qaa + i];
+  put_m(km.Qff(), lin + S.l_Qff, nf, nf, nfm);
+  put_m(km.Qqf(), lin + S.l_Qqf, nv, nf, nv);
+  put_v(impact ? kr.ldv : kr.la, lin + S.l_la, nv);
+  put_v(kr.lf(), lin + S.l_lf, nf);
+  // the state after linearize(Impact)StateEquation: Fqq = dSubtract/dqf (identity outside the floating-base block), Fqv = dt I
+  for (int i = 0; i < nv; ++i) km.Fqq()(i, i) = 1.0;
+  if (np == 6) put_m(km.Fqq().topLeftCorner(6, 6), lin + S.l_se3, 6, 6, 6);
+  if (!impact) {
+    for (int i = 0; i < nv; ++i) km.Fqv()(i, i) = c->dt;
+    put_m(km.Quu, lin + S.l_Quu, nu, nu, nu);
+    put_v(kr.lu, lin + S.l_lu, nu);
+    put_v(km.ha, lin + S.l_ha, nv);
+    put_v(km.hf(), lin + S.l_hf, nf);
+    put_v(km.hx, lin + S.l_hx, nx);
+    put_v(km.hu, lin + S.l_hu, nu);
+    put_v(km.fx, lin + S.l_fx, nx);
+    kr.h = lin[S.l_sc + 0];
+    km.Qtt = lin[S.l_sc + 1];
+    if (ns > 0) {
+      put_m(km.Phix(), lin + S.l_Phix, ns, nx, ns);
+      put_m(km.Phia(), lin + S.l_Phia, ns, nv, ns);
+      put_v(kr.P(), lin + S.l_p, ns);
+      put_v(km.Phit(), lin + S.l_Phit, ns);
+    }
+  }
+  ContactDynamicsData cd(robot);
+  cd.setContactDimension(nf);
+  cd.setSwitchingConstraintDimension(ns);
+  put_m(impact ? cd.dIDddv : cd.dIDda, lin + S.l_M, nv, nv, nv);
+  put_m(cd.dCda(), lin + S.l_J, nf, nv, nfm);
+  put_m(cd.dIDCdqv(), lin + S.l_D, nvf, nx, nvfm);
+  put_v(cd.IDC(), lin + S.l_IDC, nvf);
+  if (!impact && np > 0) put_v(cd.lu_passive, lin + S.l_lup, np);
+  StateEquationData se(robot);
+  if (np == 6) {
+    put_m(se.Fqq_prev.topLeftCorner(6, 6), lin + S.l_se3 + 36, 6, 6, 6);
+    Eigen::MatrixXd cur(6, 6);
+    put_m(cur, lin + S.l_se3 + 72, 6, 6, 6);
+    robot.injectdSubtractConfiguration_dq0(cur);
+  }
+  // ---- constraints: slack, dual, residual from the PDIPM record; cmpl as evalConstraint leaves it (pdipm.hxx:27-63)
+  std::shared_ptr<Constraints> constraints = make_constraints(robot, tab);
+  ConstraintsData cdata = constraints->createConstraintsData(robot, impact ? -1 : 2);
+  const int nj = nu;  // rows per joint-limit component
+  if (!impact) {
+    for (int k = 0; k < 7; ++k) {
+      ConstraintComponentData& cc = component(cdata, k);
+      const int off = k * nj, n = (k < 6) ? nj : 5 * tab->n_contacts;
+      put_v(cc.slack, con + S.c_slack + off, n);
+      put_v(cc.dual, con + S.c_dual + off, n);
+      put_v(cc.residual, con + S.c_res + off, n);
+      if (k < 6) {
+        pdipm::computeComplementarySlackness(tab->barrier, cc);
+      } else {
+        cc.cmpl.setZero();
+        for (int ci = 0; ci < tab->n_contacts; ++ci) {
+          if (!((c->contact_mask >> ci) & 1)) {
+            cc.residual.template segment<5>(5 * ci).setZero();  // FrictionCone::evalConstraint zeroes inactive contacts (:122-123)
+            continue;
+          }
+          pdipm::computeComplementarySlackness<5>(tab->barrier, cc, 5 * ci);
+          put_m(cc.J[ci], lin + S.l_dgdq + size_t(ci) * 5 * nv, 5, nv, 5);                       // dg_dq
+          put_m(cc.J[tab->n_contacts + ci], lin + S.l_dgdf + size_t(ci) * 15, 5, 3, 5);          // dg_df
+        }
+      }
+    }
+  }
+  // ---- "Forms linear system"
+  SplitSolution s_dummy(robot), s_next_dummy(robot);
+  if (!impact) {
+    constraints->condenseSlackAndDual(contact_status, cdata, km, kr);
+    condenseContactDynamics(robot, contact_status, c->dt, cd, km, kr);
+    correctLinearizeStateEquation(robot, c->dt, s_dummy, s_next_dummy, se, km, kr);
+    const double g1 = 1.0 / c->ngrids_in_phase;                    // intermediate_stage.cpp:140-148
+    kr.h *= g1;
+    km.hx.array() *= g1;
+    km.hu.array() *= g1;
+    km.fx.array() *= g1;
+    km.Qtt *= g1 * g1;
+    km.Qtt_prev = -km.Qtt;
+    if (ns > 0) km.Phit().array() *= g1;
+  } else {
+    constraints->condenseSlackAndDual(impact_status, cdata, km, kr);
+    condenseImpactDynamics(robot, impact_status, cd, km, kr);
+    correctLinearizeImpactStateEquation(robot, s_dummy, s_next_dummy, se, km, kr);
+  }
+  // ---- pack: KKT record, expansion record, PDIPM cmpl | cond
+  get_m(km.Fxx, kkt + K.k_Fxx, nx, nx, nx);
+  get_m(km.Qxx, kkt + K.k_Qxx, nx, nx, nx);
+  get_v(kr.Fx, kkt + K.k_Fx, nx);
+  get_v(kr.lx, kkt + K.k_lx, nx);
+  get_m(cd.MJtJinv(), ex + S.e_Z, nvf, nvf, nvfm);
+  get_m(cd.MJtJinv_dIDCdqv(), ex + S.e_R, nvf, nx, nvfm);
+  get_v(cd.MJtJinv_IDC(), ex + S.e_r, nvf);
+  get_m(cd.Qafqv(), ex + S.e_Qafqv, nvf, nx, nvfm);
+  get_v(cd.laf(), ex + S.e_laf, nvf);
+  if (np == 6) get_m(se.Fqq_prev_inv, ex + S.e_Fqqpi, 6, 6, 6);
+  if (!impact) {
+    get_m(km.Fvu, kkt + K.k_Fvu, nv, nu, nv);
+    get_m(km.Qxu, kkt + K.k_Qxu, nx, nu, nx);
+    get_m(km.Quu, kkt + K.k_Quu, nu, nu, nu);
+    get_v(kr.lu, kkt + K.k_lu, nu);
+    get_v(km.fx, kkt + K.k_fx, nx);
+    get_v(km.hx, kkt + K.k_hx, nx);
+    get_v(km.hu, kkt + K.k_hu, nu);
+    kkt[K.k_sc + 0] = km.Qtt; kkt[K.k_sc + 1] = km.Qtt_prev; kkt[K.k_sc + 2] = kr.h;
+    if (ns > 0) {
+      get_m(km.Phix(), kkt + K.k_Phix, ns, nx, ns);
+      get_m(km.Phiu(), kkt + K.k_Phiu, ns, nu, ns);
+      get_v(kr.P(), kkt + K.k_p, ns);
+      get_v(km.Phit(), kkt + K.k_Phit, ns);
+      get_m(cd.Phia(), ex + S.e_Phia, ns, nv, ns);
+    }
+    get_m(cd.Qafu_full(), ex + S.e_Qafu, nvf, nv, nvfm);
+    get_v(cd.haf(), ex + S.e_haf, nvf);
+    if (np > 0) {
+      get_m(cd.Qxu_passive, ex + S.e_Qxup, nx, np, nx);
+      get_m(cd.Quu_passive_topRight, ex + S.e_Quup, np, nu, np);
+      get_v(cd.lu_passive, ex + S.e_lup, np);
+    }
+    for (int k = 0; k < 7; ++k) {
+      ConstraintComponentData& cc = component(cdata, k);
+      const int off = k * nj, n = (k < 6) ? nj : 5 * tab->n_contacts;
+      get_v(cc.cmpl, con + S.c_cmpl + off, n);
+      get_v(cc.cond, con + S.c_cond + off, n);
+    }
+  }
+  if (phase < 2) return 0;
+
+  // ---- primal expansion + step sizes
+  SplitDirection dd(robot), dn(robot);
+  dd.setContactDimension(nf);
+  dd.setSwitchingConstraintDimension(ns);
+  put_v(dd.dx, d + K.d_dx, nx);
+  put_v(dd.dlmdgmm, d + K.d_dlmdgmm, nx);
+  dd.dts = d[K.d_dts];
+  dd.dts_next = d[K.d_dts + 1];
+  if (!impact) {
+    put_v(dd.du, d + K.d_du, nu);
+    if (ns > 0) put_v(dd.dxi(), d + K.d_dxi, ns);
+    expandContactDynamicsPrimal(cd, dd);
+    constraints->expandSlackAndDual(contact_status, cdata, dd);
+  } else {
+    expandImpactDynamicsPrimal(cd, dd);
+    constraints->expandSlackAndDual(impact_status, cdata, dd);
+  }
+  get_v(impact ? dd.ddvf() : dd.daf(), xd + S.x_daf, nvf);
+  steps_stage[0] = constraints->maxSlackStepSize(cdata);
+  steps_stage[1] = constraints->maxDualStepSize(cdata);
+  if (!impact)
+    for (int k = 0; k < 7; ++k) {
+      ConstraintComponentData& cc = component(cdata, k);
+      const int off = k * nj, n = (k < 6) ? nj : 5 * tab->n_contacts;
+      get_v(cc.dslack, con + S.c_dslack + off, n);
+      get_v(cc.ddual, con + S.c_ddual + off, n);
+    }
+  if (phase < 3) return 0;
+
+  // ---- dual expansion, costate correction, slack / dual update
+  put_v(dn.dlmdgmm, d_next + K.d_dlmdgmm, nx);
+  if (!impact) {
+    double dts = 0.0;
+    if (c->ngrids_in_phase > 0) dts = (dd.dts_next - dd.dts) / c->ngrids_in_phase;   // intermediate_stage.cpp:168-171
+    expandContactDynamicsDual(c->dt, dts, cd, dn, dd);
+  } else {
+    expandImpactDynamicsDual(cd, dn, dd);
+  }
+  correctCostateDirection(se, dd);
+  get_v(cd.laf(), ex + S.e_laf, nvf);  // expand*Dual completes laf / ldvf in place (contact_dynamics.cpp:180-188, impact_dynamics.cpp:92-94)
+  get_v(dd.dbetamu(), xd + S.x_dbetamu, nvf);
+  if (!impact && np > 0) get_v(dd.dnu_passive, xd + S.x_dnup, np);
+  get_v(dd.dlmdgmm, d + K.d_dlmdgmm, nx);
+  if (!impact) {
+    Constraints::updateSlack(cdata, alpha_p);
+    Constraints::updateDual(cdata, alpha_d);
+    for (int k = 0; k < 7; ++k) {
+      ConstraintComponentData& cc = component(cdata, k);
+      const int off = k * nj, n = (k < 6) ? nj : 5 * tab->n_contacts;
+      get_v(cc.slack, con + S.c_slack + off, n);
+      get_v(cc.dual, con + S.c_dual + off, n);
+    }
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -93,10 +93,26 @@ class Robot {
   template <typename... A> void computeImpactVelocityDerivatives(const A&...) RBT_SHIM_UNREACHABLE("computeImpactVelocityDerivatives")
   template <typename... A> void computeContactPositionResidual(const A&...) RBT_SHIM_UNREACHABLE("computeContactPositionResidual")
   template <typename... A> void computeContactPositionDerivative(const A&...) RBT_SHIM_UNREACHABLE("computeContactPositionDerivative")
-  template <typename... A> void integrateConfiguration(const A&...) const RBT_SHIM_UNREACHABLE("integrateConfiguration")
+  /// q <- q (+) step * dq for the JOINT coordinates only (vector space); the free-flyer part (SE(3) exponential, Pinocchio) is
+  /// left untouched -- the wrapper's callers compare only the joint part of q.
+  template <typename V, typename Q>
+  void integrateConfiguration(const Eigen::MatrixBase<V>& dq, const double step, const Eigen::MatrixBase<Q>& q) const {
+    Eigen::MatrixBase<Q>& qq = const_cast<Eigen::MatrixBase<Q>&>(q);
+    const int nb_q = floating_ ? 7 : 0, nb_v = floating_ ? 6 : 0;
+    for (int i = 0; i < dimv_ - nb_v; ++i) qq.coeffRef(nb_q + i) += step * dq.coeff(nb_v + i);
+  }
   template <typename... A> void subtractConfiguration(const A&...) const RBT_SHIM_UNREACHABLE("subtractConfiguration")
   template <typename... A> void dSubtractConfiguration_dqf(const A&...) const RBT_SHIM_UNREACHABLE("dSubtractConfiguration_dqf")
-  template <typename... A> void dSubtractConfiguration_dq0(const A&...) const RBT_SHIM_UNREACHABLE("dSubtractConfiguration_dq0")
+  /// Test hook: the reference's correctLinearize(Impact)StateEquation re-evaluates dSubtract/dq0 (a Pinocchio call) in the middle
+  /// of the linear algebra (state_equation.cpp:77, impact_state_equation.cpp:63); the wrapper queues the 6x6 block that call
+  /// has to return (it is an INPUT of the hot path: section l_se3 of the linearization record).
+  void injectdSubtractConfiguration_dq0(const Eigen::MatrixXd& top_left_6x6) { injected_ = top_left_6x6; has_injected_ = true; }
+  template <typename Q1, typename Q2, typename M>
+  void dSubtractConfiguration_dq0(const Q1&, const Q2&, const Eigen::MatrixBase<M>& out) const {
+    if (!has_injected_) { std::fprintf(stderr, "oracle/shim Robot::dSubtractConfiguration_dq0 called without an injected block\n"); std::abort(); }
+    Eigen::MatrixBase<M>& o = const_cast<Eigen::MatrixBase<M>&>(out);
+    o.topLeftCorner(6, 6) = injected_;
+  }
   template <typename... A> void dIntegrateTransport_dq(const A&...) const RBT_SHIM_UNREACHABLE("dIntegrateTransport_dq")
   template <typename... A> void dIntegrateTransport_dv(const A&...) const RBT_SHIM_UNREACHABLE("dIntegrateTransport_dv")
   template <typename... A> void normalizeConfiguration(const A&...) const RBT_SHIM_UNREACHABLE("normalizeConfiguration")
@@ -119,6 +135,8 @@ class Robot {
   std::vector<ContactType> contact_types_;
   std::vector<std::string> contact_frame_names_;
   Eigen::VectorXd limit_effort_, limit_velocity_, limit_qmin_, limit_qmax_;
+  Eigen::MatrixXd injected_;
+  bool has_injected_ = false;
 };
 
 }  // namespace robotoc

@@ -182,10 +182,13 @@ def make_stage_inputs(sd: StageDims, S: StageLayout, ctrl, batch: int, seed: int
         Sm = _u(rng, batch, nv, nv)
         _putm(rec, S.l_M, np.eye(nv)[None] + 0.1 * Sm @ np.transpose(Sm, (0, 2, 1)), nv)
         if nf > 0:
-            _putm(rec, S.l_J, _u(rng, batch, nf, nv), nfm)
+            Jimp = _u(rng, batch, nf, nv)
+            _putm(rec, S.l_J, Jimp, nfm)
         D = 0.5 * _u(rng, batch, nv + nf, nx)
         if impact:
             D[:, :nv, nv:] = 0.0  # dIDdv does not exist on an impact stage (impact_dynamics.cpp:44-52)
+            if nf > 0:            # ... and the Jacobian of MJtJinv IS the dCdv block of dIDCdqv there (impact_dynamics.cpp:40)
+                D[:, nv:nv + nf, nv:] = Jimp
         _putm(rec, S.l_D, D, nvfm)
         rec[:, S.l_IDC:S.l_IDC + nv + nf] = 0.5 * _u(rng, batch, nv + nf)
         rec[:, S.l_Qaa:S.l_Qaa + nv] = rng.uniform(0.01, 1.0, size=(batch, nv))

@@ -1,0 +1,111 @@
+"""The stage layer (condensing, expansion, step sizes, slack / dual update: SURVEY.md 8a rows a10-a16) pinned against the
+reference's own code.  tests/golden/golden_ref_stage_r2.npz holds one full iteration computed by /root/reference's sources
+(make_golden_ref_stage.py);
+  CPU: the oracle reproduces it; where oracle/_ref is available the oracle is also compared with the live reference code on the
+       BASELINE trot schedule and further seeds;
+  GPU: the CUDA path reproduces it through the C ABI."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+import make_golden_ref_stage as mg  # noqa: E402
+
+import oracle_lib  # noqa: E402
+from iteration_check import oracle_iteration  # noqa: E402
+from robotoc_b200.grid import IMPACT, TERMINAL  # noqa: E402
+
+G = np.load(os.path.join(HERE, "golden", "golden_ref_stage_r2.npz"))
+TOL = 1e-10
+
+
+def _cmp_records(S, K, ctrl, got, ref, tol, skip_sol=True):
+    """Every section the reference's code produces, stage by stage (sections it leaves untouched are not compared)."""
+    def rel(name, a, b):
+        s = float(np.max(np.abs(b)))
+        if s == 0.0:
+            assert float(np.max(np.abs(a))) == 0.0, name
+            return
+        e = float(np.max(np.abs(a - b))) / s
+        assert e < tol, f"{name}: {e:.2e}"
+    nx, nu, nv = K.nx, K.nu, K.nv
+    for i, c in enumerate(ctrl):
+        rel(f"Qxx[{i}]", got["kkt"][:, i, K.k_Qxx:K.k_Qxx + nx * nx], ref["kkt"][:, i, K.k_Qxx:K.k_Qxx + nx * nx])
+        rel(f"lx[{i}]", got["kkt"][:, i, K.k_lx:K.k_lx + nx], ref["kkt"][:, i, K.k_lx:K.k_lx + nx])
+        rel(f"P[{i}]", got["ric"][:, i, K.r_P:K.r_P + nx * nx], ref["ric"][:, i, K.r_P:K.r_P + nx * nx])
+        rel(f"dx[{i}]", got["d_upd"][:, i, K.d_dx:K.d_dx + nx], ref["d_upd"][:, i, K.d_dx:K.d_dx + nx])
+        rel(f"dlmdgmm[{i}]", got["d_upd"][:, i, K.d_dlmdgmm:K.d_dlmdgmm + nx], ref["d_upd"][:, i, K.d_dlmdgmm:K.d_dlmdgmm + nx])
+        if c.type == TERMINAL:
+            continue
+        nvf = nv + c.nf
+        rel(f"kkt[{i}]", got["kkt"][:, i], ref["kkt"][:, i])
+        for f, n in (("e_Z", S.nvf * S.nvf), ("e_R", S.nvf * nx), ("e_r", nvf), ("e_Qafqv", S.nvf * nx), ("e_laf", nvf), ("e_Fqqpi", 36)):
+            o = getattr(S, f)
+            rel(f"{f}[{i}]", got["ex_upd"][:, i, o:o + n], ref["ex_upd"][:, i, o:o + n])
+        rel(f"daf[{i}]", got["xd_exp"][:, i, S.x_daf:S.x_daf + nvf], ref["xd_exp"][:, i, S.x_daf:S.x_daf + nvf])
+        rel(f"dbetamu[{i}]", got["xd_upd"][:, i, S.x_dbetamu:S.x_dbetamu + nvf], ref["xd_upd"][:, i, S.x_dbetamu:S.x_dbetamu + nvf])
+        if c.type == IMPACT:
+            continue
+        for f, n in (("e_Qafu", S.nvf * nv), ("e_Qxup", nx * S.np), ("e_Quup", S.np * nu), ("e_lup", S.np), ("e_haf", nvf)):
+            o = getattr(S, f)
+            rel(f"{f}[{i}]", got["ex_upd"][:, i, o:o + n], ref["ex_upd"][:, i, o:o + n])
+        rel(f"dnup[{i}]", got["xd_upd"][:, i, S.x_dnup:S.x_dnup + S.np], ref["xd_upd"][:, i, S.x_dnup:S.x_dnup + S.np])
+        rel(f"K[{i}]", got["ric"][:, i, K.r_K:K.r_K + nx * nu], ref["ric"][:, i, K.r_K:K.r_K + nx * nu])
+        rel(f"du[{i}]", got["d_upd"][:, i, K.d_du:K.d_du + nu], ref["d_upd"][:, i, K.d_du:K.d_du + nu])
+        for key, fields in (("cc_cond", ("c_cmpl", "c_cond")), ("cc_exp", ("c_dslack", "c_ddual")), ("cc_upd", ("c_slack", "c_dual"))):
+            for f in fields:
+                o = getattr(S, f)
+                rel(f"{f}[{i}]", got[key][:, i, o:o + S.nc], ref[key][:, i, o:o + S.nc])
+    rel("steps", got["steps"], ref["steps"])
+
+
+def test_oracle_reproduces_the_reference_iteration_golden():
+    lib = oracle_lib.load()
+    table, sd, S, K, ctrl, lin, con, sol, dx0 = mg.problem(lib.orc_stage_layout_get, lib.orc_layout_get)
+    got = oracle_iteration(sd, S, K, table, ctrl, lin, con, sol, dx0)
+    _cmp_records(S, K, ctrl, got, G, TOL)
+
+
+@pytest.mark.parametrize("which,seed", [("small", 311), ("small_sto", 312), ("trot", 313)])
+def test_oracle_equals_live_reference_stage_layer(which, seed):
+    import ref_lib
+    if not ref_lib.available():
+        pytest.skip("oracle/_ref not built and /root/reference not present")
+    from helpers import small_event_schedule, trot_schedule
+    from robotoc_b200 import ANYMAL, Layout, StageDims, StageLayout, anymal_constraint_table
+    from synth import make_stage_inputs
+    lib = oracle_lib.load()
+    table = anymal_constraint_table()
+    sd = StageDims(ANYMAL, nf_max=12, n_contacts=table.n_contacts, n_box=table.n_box)
+    S, K = StageLayout(sd, getter=lib.orc_stage_layout_get), Layout(ANYMAL, getter=lib.orc_layout_get)
+    td, ev, ctrl = {"small": small_event_schedule(False), "small_sto": small_event_schedule(True), "trot": trot_schedule(40)}[which]
+    lin, con, sol, dx0 = make_stage_inputs(sd, S, ctrl, 1, seed)
+    ref = ref_lib.reference_iteration(sd, S, K, table, ctrl, lin, con, dx0)
+    got = oracle_iteration(sd, S, K, table, ctrl, lin, con, sol, dx0)
+    _cmp_records(S, K, ctrl, got, ref, TOL)
+
+
+@pytest.mark.gpu
+def test_cuda_reproduces_the_reference_iteration_golden():
+    from robotoc_b200 import ANYMAL, DirectMultipleShooting, RiccatiRecursion
+    table, sd, S, K, ctrl, lin, con, sol, dx0 = mg.problem()
+    rr = RiccatiRecursion(ANYMAL, len(ctrl), lin.shape[0])
+    rr.setTimeDiscretization(ctrl)
+    dms = DirectMultipleShooting(rr, sd, table)
+    dms.condense(lin, con)
+    got = dict(kkt=dms.getKKT(), cc_cond=dms.getConstraintData())
+    rr.backwardRiccatiRecursion()
+    rr.forwardRiccatiRecursion(dx0)
+    assert int(rr.info().max()) == 0
+    got["ric"] = rr.getRiccatiFactorization()
+    dms.computeStepSizes()
+    got["steps"] = np.stack([dms.maxPrimalStepSize(), dms.maxDualStepSize()], axis=1)
+    got["cc_exp"], got["xd_exp"] = dms.getConstraintData(), dms.getExpandedDirection()
+    dms.integrateSolution(sol)
+    got["d_upd"], got["xd_upd"], got["cc_upd"], got["ex_upd"] = (rr.getDirection(), dms.getExpandedDirection(), dms.getConstraintData(),
+                                                                 dms.getExpansionData())
+    _cmp_records(S, K, ctrl, got, G, 1e-8)
+    rr.close()
