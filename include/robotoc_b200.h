@@ -162,6 +162,31 @@ int rbt_set_slack_and_dual_positive(rbt_handle* h, void* stream);
  * rbt_condense left in RBT_BUF_EXP and s[0].v of RBT_BUF_SOL, so call it after rbt_condense and before rbt_riccati_forward. */
 int rbt_initial_state_direction(rbt_handle* h, const double* dq0_v0_host, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Line search -- the model-free half of robotoc::LineSearch::lineSearchFilterMethod
+ * (src/line_search/line_search.cpp:58-86), with the backtracking step sizes alpha_k = alpha_max * rate^k as an extra batch axis.
+ * rbt_line_search_trials: DirectMultipleShooting::integratePrimalSolution (direct_multiple_shooting.cpp:244-266) for n_trials
+ *   step sizes at once, after rbt_expand_and_step_sizes (alpha_max = the max primal step of RBT_BUF_STEPS) and BEFORE rbt_update.
+ *   Writes trial primal records [n_trials][batch][n_grid][rbt_trial_doubles() = 80] = {q (nq, padded to 20) | v | a or dv | u | f}
+ *   on the device (rbt_line_search_trial_dev; also to trial_host if not NULL), alphas [n_trials][batch], and the log-barrier of
+ *   the trial slacks (pdipm.hxx:194-200 on slack + alpha dslack) summed over the horizon, barrier [n_trials][batch].
+ *   evalOCP at the trial points -- stage costs, dynamics residuals -- needs the robot model: the caller (or a GPU front-end)
+ *   evaluates cost[k][b] and violation[k][b] from the trial records.
+ * rbt_line_search_filter: LineSearchFilter (src/line_search/line_search_filter.cpp:25-56) per OCP over those evaluations:
+ *   empty filter -> augment(cost0, violation0); the first trial k with alpha_k > min_step_size that the filter accepts is taken
+ *   (and augments the filter), otherwise the first alpha_k <= min_step_size is returned -- exactly the reference's loop.
+ *   cost_host excludes the barrier part (added here from rbt_line_search_trials).  The per-OCP filters persist across calls;
+ *   rbt_line_search_clear_history = LineSearch::clearHistory. */
+int rbt_trial_doubles(void);
+int rbt_line_search_trials(rbt_handle* h, int n_trials, double step_size_reduction_rate, double* alphas_host, double* barrier_host,
+                           double* trial_host, void* stream);
+double* rbt_line_search_trial_dev(rbt_handle* h);
+int rbt_line_search_filter(rbt_handle* h, int n_trials, double step_size_reduction_rate, double min_step_size,
+                           double filter_cost_reduction_rate, double filter_constraint_violation_reduction_rate,
+                           const double* cost0_host, const double* violation0_host, const double* cost_host,
+                           const double* violation_host, double* step_host, int* accepted_trial_host, void* stream);
+int rbt_line_search_clear_history(rbt_handle* h, void* stream);
+
 /* One hot-path iteration with HOST buffers -- the linear-algebra body of OCPSolver::updateSolution
  * (src/solver/ocp_solver.cpp:118-144) given the stage linearisations: upload lin / con / sol / dx0, condense, backward and
  * forward Riccati, step sizes, update, download the updated solution, the PDIPM data and the step sizes (NULL = skip). */

@@ -908,3 +908,123 @@ void orc_initial_state_direction(const rbt_stage_dims* sd, const double* ex0, co
     }
   for (int i = 0; i < nv; ++i) dx0[nv + i] = v0[i] - sol0[S.s_v + i];
 }
+
+/* ---------------- the model-free half of the line search, batched over trial step sizes --------------------
+ * LineSearch::lineSearchFilterMethod (src/line_search/line_search.cpp:58-86) tries alpha_k = alpha_max * rate^k (rate 0.75,
+ * line_search_settings.hpp) one after the other: integratePrimalSolution (direct_multiple_shooting.cpp:244-266 ->
+ * SplitSolution::integrate + Constraints::updateSlack), evalOCP, filter test.  The trial solutions of ALL k are independent of
+ * each other, so they form an extra batch axis; evalOCP needs the robot model (out of scope) except for the log-barrier of the
+ * trial slacks, which is computed here.
+ * Trial record (t_stride = 80 doubles): {q (nq, padded to 20) | v (18) | a or dv (18) | u (12) | f (12)} -- the primal variables
+ * evalOCP reads.  out_barrier = - barrier * sum log(slack + alpha dslack) over the active inequality rows of the stage. */
+#define ORC_T_Q 0
+#define ORC_T_V 20
+#define ORC_T_A 38
+#define ORC_T_U 56
+#define ORC_T_F 68
+#define ORC_T_STRIDE 80
+void orc_stage_trial(const rbt_stage_dims* sd, const rbt_constraint_table* tab, const rbt_stage_ctrl* c, const double* sol,
+                     const double* d, const double* xd, const double* con, double alpha, double* trial, double* out_barrier) {
+  rbt_stage_layout S;
+  rbt_make_stage_layout(sd, &S);
+  rbt_dims kd = {sd->nv, sd->nu, sd->ns_max, sd->n_passive};
+  rbt_layout K;
+  rbt_make_layout(&kd, &K);
+  const int nv = S.nv, nu = S.nu, np = S.np;
+  const int terminal = c->type == RBT_TERMINAL, impact = c->type == RBT_IMPACT;
+  const double* dx = d + K.d_dx;
+  memset(trial, 0, sizeof(double) * ORC_T_STRIDE);
+  double* q = trial + ORC_T_Q;
+  memcpy(q, sol + S.s_q, sizeof(double) * S.nq);
+  if (np == 6) {
+    integrate_free_flyer(q, dx, alpha);
+    for (int i = 6; i < nv; ++i) q[i + 1] += alpha * dx[i];
+  } else {
+    for (int i = 0; i < nv; ++i) q[i] += alpha * dx[i];
+  }
+  for (int i = 0; i < nv; ++i) trial[ORC_T_V + i] = sol[S.s_v + i] + alpha * dx[nv + i];
+  *out_barrier = 0.0;
+  if (terminal) return;
+  const double* daf = xd + S.x_daf;
+  for (int i = 0; i < nv; ++i) trial[ORC_T_A + i] = (impact ? sol[S.s_dv + i] : sol[S.s_a + i]) + alpha * daf[i];
+  if (!impact)
+    for (int i = 0; i < nu; ++i) trial[ORC_T_U + i] = sol[S.s_u + i] + alpha * d[K.d_du + i];
+  for (int i = 0; i < c->nf; ++i) trial[ORC_T_F + i] = sol[S.s_f + i] + alpha * daf[nv + i];
+  if (!impact) {
+    double lb = 0.0;
+    for (int r = 0; r < S.nc; ++r) {
+      if (r >= S.nbox && !((c->contact_mask >> ((r - S.nbox) / 5)) & 1)) continue;
+      lb -= tab->barrier * log(con[S.c_slack + r] + alpha * con[S.c_dslack + r]);
+    }
+    *out_barrier = lb;
+  }
+}
+
+/* alphas[k][b] = steps[b].primal * rate^k;  trial[k][b][i][80];  barrier[k][b] = sum over the horizon (stage order) */
+void orc_trial_batch(const rbt_stage_dims* sd, const rbt_constraint_table* tab, const rbt_stage_ctrl* ctrl, int n_grid, int batch,
+                     int n_trials, double rate, const double* sol, const double* d, const double* xd, const double* con,
+                     const double* steps, double* alphas, double* trial, double* barrier) {
+  rbt_stage_layout S;
+  rbt_make_stage_layout(sd, &S);
+  rbt_dims kd = {sd->nv, sd->nu, sd->ns_max, sd->n_passive};
+  rbt_layout K;
+  rbt_make_layout(&kd, &K);
+  for (int k = 0; k < n_trials; ++k)
+    for (int b = 0; b < batch; ++b) {
+      double a = steps[2 * b];
+      for (int q = 0; q < k; ++q) a *= rate;
+      alphas[(size_t)k * batch + b] = a;
+      double acc = 0.0;
+      for (int i = 0; i < n_grid; ++i) {
+        const size_t o = (size_t)b * n_grid + i;
+        double lb;
+        orc_stage_trial(sd, tab, &ctrl[i], sol + o * S.s_stride, d + o * K.d_stride, xd + o * S.x_stride, con + o * S.c_stride, a,
+                        trial + (((size_t)k * batch + b) * n_grid + i) * ORC_T_STRIDE, &lb);
+        acc += lb;
+      }
+      barrier[(size_t)k * batch + b] = acc;
+    }
+}
+
+/* LineSearchFilter (src/line_search/line_search_filter.cpp:25-56) with a fixed-capacity store: filt[2*cap] pairs, *n entries. */
+static int filter_accepted(const double* filt, int n, double cr, double vr, double cost, double viol) {
+  if (n == 0) return 1;
+  for (int e = 0; e < n; ++e)
+    if (cost < filt[2 * e] - cr * filt[2 * e + 1] || viol < (1.0 - vr) * filt[2 * e + 1]) return 1;
+  return 0;
+}
+static void filter_augment(double* filt, int* n, int cap, double cr, double vr, double cost, double viol) {
+  if (!filter_accepted(filt, *n, cr, vr, cost, viol)) return;
+  int w = 0;
+  for (int e = 0; e < *n; ++e)
+    if (!(filt[2 * e] <= cost && filt[2 * e + 1] <= viol)) { filt[2 * w] = filt[2 * e]; filt[2 * w + 1] = filt[2 * e + 1]; ++w; }
+  if (w < cap) { filt[2 * w] = cost; filt[2 * w + 1] = viol; ++w; }
+  *n = w;
+}
+/* lineSearchFilterMethod (line_search.cpp:58-86) for every OCP, given cost[k][b] (stage costs summed by the evaluator; the barrier
+ * part barrier[k][b] is added here) and violation[k][b] of the trials and cost0/viol0 of the current iterate:
+ *   if the filter is empty: augment(cost0, viol0);   alpha = alpha_max;
+ *   while (alpha > min_step): [trial k] if accepted -> augment, return alpha;  alpha *= rate;     return alpha
+ * filt: [batch][2*cap], nfilt: [batch].  out_step[b], out_k[b] (-1: none accepted). */
+void orc_line_search_filter(int batch, int n_trials, double rate, double min_step, double cr, double vr, int cap,
+                            const double* steps, const double* cost0, const double* viol0, const double* cost,
+                            const double* barrier, const double* viol, double* filt, int* nfilt, double* out_step, int* out_k) {
+  for (int b = 0; b < batch; ++b) {
+    double* f = filt + (size_t)b * 2 * cap;
+    if (nfilt[b] == 0) filter_augment(f, &nfilt[b], cap, cr, vr, cost0[b], viol0[b]);
+    double alpha = steps[2 * b];
+    int k = 0, acc = -1;
+    while (alpha > min_step && k < n_trials) {
+      const double c = cost[(size_t)k * batch + b] + barrier[(size_t)k * batch + b], v = viol[(size_t)k * batch + b];
+      if (filter_accepted(f, nfilt[b], cr, vr, c, v)) {
+        filter_augment(f, &nfilt[b], cap, cr, vr, c, v);
+        acc = k;
+        break;
+      }
+      alpha *= rate;
+      ++k;
+    }
+    out_step[b] = alpha;
+    out_k[b] = acc;
+  }
+}

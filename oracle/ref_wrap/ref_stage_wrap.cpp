@@ -41,6 +41,7 @@
 #include "robotoc/constraints/joint_torques_lower_limit.hpp"
 #include "robotoc/constraints/joint_torques_upper_limit.hpp"
 #include "robotoc/constraints/friction_cone.hpp"
+#include "robotoc/line_search/line_search_filter.hpp"
 
 #include "../../include/rbt_layout.h"
 #include "../../include/rbt_stage_layout.h"
@@ -319,6 +320,34 @@ int ref_stage(const rbt_stage_dims* sd, const rbt_constraint_table* tab, const r
       get_v(cc.slack, con + S.c_slack + off, n);
       get_v(cc.dual, con + S.c_dual + off, n);
     }
+  }
+  return 0;
+}
+
+// robotoc::LineSearchFilter (src/line_search/line_search_filter.cpp, compiled unmodified) driven like
+// LineSearch::lineSearchFilterMethod drives it (line_search.cpp:58-86) for ONE OCP over `rounds` consecutive line searches with
+// n_trials pre-evaluated candidates each: cost0/viol0 [rounds], cost/viol [rounds][n_trials] (barrier already included).
+// out_step[round], out_k[round].
+int ref_filter_line_search(int rounds, int n_trials, double rate, double min_step, double cost_rate, double viol_rate,
+                           const double* alpha_max, const double* cost0, const double* viol0, const double* cost, const double* viol,
+                           double* out_step, int* out_k) {
+  robotoc::LineSearchFilter filter(cost_rate, viol_rate);
+  for (int r = 0; r < rounds; ++r) {
+    if (filter.isEmpty()) filter.augment(cost0[r], viol0[r]);
+    double alpha = alpha_max[r];
+    int k = 0, acc = -1;
+    while (alpha > min_step && k < n_trials) {
+      const double c = cost[size_t(r) * n_trials + k], v = viol[size_t(r) * n_trials + k];
+      if (filter.isAccepted(c, v)) {
+        filter.augment(c, v);
+        acc = k;
+        break;
+      }
+      alpha *= rate;
+      ++k;
+    }
+    out_step[r] = alpha;
+    out_k[r] = acc;
   }
   return 0;
 }

@@ -10,6 +10,7 @@ from .grid import GridInfo, plain_schedule  # noqa: F401
 from .riccati import RiccatiRecursion, UnconstrRiccatiRecursion  # noqa: F401
 from .stage import StageDims, StageLayout, anymal_constraint_table  # noqa: F401
 from .dms import DirectMultipleShooting  # noqa: F401
+from .line_search import LineSearch, LineSearchSettings  # noqa: F401
 
 ANYMAL = Dims(nv=18, nu=12, ns_max=12, n_passive=6)
 IIWA14_NV = 7

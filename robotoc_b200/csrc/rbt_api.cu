@@ -20,6 +20,7 @@
 #include "stage_kernels.cuh"
 #include "ustage_kernels.cuh"
 #include "eval_kernels.cuh"
+#include "line_search_kernels.cuh"
 
 namespace {
 
@@ -68,6 +69,11 @@ struct rbt_handle {
   double *d_lin = nullptr, *d_con = nullptr, *d_ex = nullptr, *d_sol = nullptr, *d_xd = nullptr, *d_steps = nullptr,
          *d_ones = nullptr;
   double *d_stage_perf = nullptr, *d_perf = nullptr, *d_x0in = nullptr;  // eval_kernels.cuh
+  // line search (line_search_kernels.cuh): trial buffers sized on first use, filter state per OCP
+  int ls_trials = 0;
+  double *d_ls_alphas = nullptr, *d_ls_trial = nullptr, *d_ls_stage_barrier = nullptr, *d_ls_barrier = nullptr;
+  double *d_ls_in = nullptr, *d_ls_filt = nullptr, *d_ls_step = nullptr;
+  int *d_ls_nfilt = nullptr, *d_ls_k = nullptr;
   double* d_step_pack = nullptr;  // packed Newton step of this rank (rbt_allgather_step), allocated on first use
   int timeline_cta = -1;
   long long launches = 0;
@@ -216,6 +222,8 @@ int rbt_destroy(rbt_handle* h) {
   cudaFree(h->d_steps);
   cudaFree(h->d_ones);
   cudaFree(h->d_step_pack);
+  cudaFree(h->d_ls_alphas); cudaFree(h->d_ls_trial); cudaFree(h->d_ls_stage_barrier); cudaFree(h->d_ls_barrier);
+  cudaFree(h->d_ls_in); cudaFree(h->d_ls_filt); cudaFree(h->d_ls_step); cudaFree(h->d_ls_nfilt); cudaFree(h->d_ls_k);
   cudaFree(h->d_stage_perf);
   cudaFree(h->d_perf);
   cudaFree(h->d_x0in);
@@ -798,6 +806,104 @@ int rbt_initial_state_direction(rbt_handle* h, const double* dq0_v0_host, void* 
   rbt::initial_state_direction_kernel<<<(total + 127) / 128, 128, 0, st>>>(q);
   RBT_CUDA(h, cudaGetLastError());
   h->launches += 1;
+  return RBT_OK;
+}
+
+// ---- line search: trial step sizes as an extra batch axis -------------------------------------------------------------------
+enum { RBT_LS_FILTER_CAP = 16 };
+
+static int ls_ensure(rbt_handle* h, int n_trials) {
+  if (n_trials <= h->ls_trials) return RBT_OK;
+  cudaFree(h->d_ls_alphas); cudaFree(h->d_ls_trial); cudaFree(h->d_ls_stage_barrier); cudaFree(h->d_ls_barrier); cudaFree(h->d_ls_in);
+  h->d_ls_alphas = h->d_ls_trial = h->d_ls_stage_barrier = h->d_ls_barrier = h->d_ls_in = nullptr;
+  const size_t kb = size_t(n_trials) * h->batch;
+  RBT_CUDA(h, cudaMalloc(&h->d_ls_alphas, kb * 8));
+  RBT_CUDA(h, cudaMalloc(&h->d_ls_barrier, kb * 8));
+  RBT_CUDA(h, cudaMalloc(&h->d_ls_stage_barrier, kb * h->n_grid_max * 8));
+  RBT_CUDA(h, cudaMalloc(&h->d_ls_trial, kb * h->n_grid_max * rbt::T_STRIDE * 8));
+  RBT_CUDA(h, cudaMalloc(&h->d_ls_in, (2 * kb + 2 * size_t(h->batch)) * 8));  // cost | viol of the trials, cost0 | viol0
+  if (!h->d_ls_filt) {
+    RBT_CUDA(h, cudaMalloc(&h->d_ls_filt, size_t(h->batch) * 2 * RBT_LS_FILTER_CAP * 8));
+    RBT_CUDA(h, cudaMalloc(&h->d_ls_nfilt, size_t(h->batch) * sizeof(int)));
+    RBT_CUDA(h, cudaMalloc(&h->d_ls_step, size_t(h->batch) * 8));
+    RBT_CUDA(h, cudaMalloc(&h->d_ls_k, size_t(h->batch) * sizeof(int)));
+    RBT_CUDA(h, cudaMemset(h->d_ls_nfilt, 0, size_t(h->batch) * sizeof(int)));
+  }
+  h->ls_trials = n_trials;
+  return RBT_OK;
+}
+
+int rbt_trial_doubles(void) { return rbt::T_STRIDE; }
+
+int rbt_line_search_trials(rbt_handle* h, int n_trials, double step_size_reduction_rate, double* alphas_host, double* barrier_host,
+                           double* trial_host, void* stream) {
+  RBT_STAGE_CHECK(h, "rbt_line_search_trials");
+  if (n_trials < 1 || n_trials > 64 || !(step_size_reduction_rate > 0.0 && step_size_reduction_rate < 1.0)) {
+    h->err = "[rbt_line_search_trials] invalid argument: 1 <= n_trials <= 64, 0 < step_size_reduction_rate < 1";
+    return RBT_ERR_ARG;
+  }
+  if (int rc = ls_ensure(h, n_trials)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  rbt::TrialParams q;
+  q.sp = make_stage_params(h);
+  q.n_trials = n_trials;
+  q.rate = step_size_reduction_rate;
+  q.alphas = h->d_ls_alphas;
+  q.trial = h->d_ls_trial;
+  q.stage_barrier = h->d_ls_stage_barrier;
+  q.barrier = h->d_ls_barrier;
+  const long long warps = (long long)n_trials * h->batch * h->n_grid;
+  rbt::trial_solution_kernel<<<unsigned((warps + 3) / 4), 128, 0, st>>>(q);
+  rbt::trial_reduce_kernel<<<(n_trials * h->batch + 127) / 128, 128, 0, st>>>(q);
+  RBT_CUDA(h, cudaGetLastError());
+  h->launches += 2;
+  const size_t kb = size_t(n_trials) * h->batch;
+  if (alphas_host) RBT_CUDA(h, cudaMemcpyAsync(alphas_host, h->d_ls_alphas, kb * 8, cudaMemcpyDeviceToHost, st));
+  if (barrier_host) RBT_CUDA(h, cudaMemcpyAsync(barrier_host, h->d_ls_barrier, kb * 8, cudaMemcpyDeviceToHost, st));
+  if (trial_host) RBT_CUDA(h, cudaMemcpyAsync(trial_host, h->d_ls_trial, kb * h->n_grid * rbt::T_STRIDE * 8, cudaMemcpyDeviceToHost, st));
+  return RBT_OK;
+}
+
+double* rbt_line_search_trial_dev(rbt_handle* h) { return h ? h->d_ls_trial : nullptr; }
+
+int rbt_line_search_clear_history(rbt_handle* h, void* stream) {
+  if (!h) return RBT_ERR_ARG;
+  if (h->d_ls_nfilt) RBT_CUDA(h, cudaMemsetAsync(h->d_ls_nfilt, 0, size_t(h->batch) * sizeof(int), (cudaStream_t)stream));
+  return RBT_OK;
+}
+
+int rbt_line_search_filter(rbt_handle* h, int n_trials, double step_size_reduction_rate, double min_step_size,
+                           double filter_cost_reduction_rate, double filter_constraint_violation_reduction_rate,
+                           const double* cost0_host, const double* violation0_host, const double* cost_host,
+                           const double* violation_host, double* step_host, int* accepted_trial_host, void* stream) {
+  RBT_STAGE_CHECK(h, "rbt_line_search_filter");
+  if (n_trials < 1 || n_trials > h->ls_trials || !cost0_host || !violation0_host || !cost_host || !violation_host ||
+      !(filter_cost_reduction_rate > 0.0) || !(filter_constraint_violation_reduction_rate > 0.0)) {
+    h->err = "[rbt_line_search_filter] invalid argument (call rbt_line_search_trials with at least n_trials first; the reduction "
+             "rates must be positive like LineSearchFilter's, line_search_filter.cpp:15-20)";
+    return RBT_ERR_ARG;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t kb = size_t(n_trials) * h->batch;
+  double* d_cost = h->d_ls_in;
+  double* d_viol = h->d_ls_in + size_t(h->ls_trials) * h->batch;
+  double* d_c0 = h->d_ls_in + 2 * size_t(h->ls_trials) * h->batch;
+  double* d_v0 = d_c0 + h->batch;
+  RBT_CUDA(h, cudaMemcpyAsync(d_cost, cost_host, kb * 8, cudaMemcpyHostToDevice, st));
+  RBT_CUDA(h, cudaMemcpyAsync(d_viol, violation_host, kb * 8, cudaMemcpyHostToDevice, st));
+  RBT_CUDA(h, cudaMemcpyAsync(d_c0, cost0_host, size_t(h->batch) * 8, cudaMemcpyHostToDevice, st));
+  RBT_CUDA(h, cudaMemcpyAsync(d_v0, violation0_host, size_t(h->batch) * 8, cudaMemcpyHostToDevice, st));
+  rbt::FilterParams q;
+  q.batch = h->batch; q.n_trials = n_trials; q.cap = RBT_LS_FILTER_CAP;
+  q.rate = step_size_reduction_rate; q.min_step = min_step_size;
+  q.cost_rate = filter_cost_reduction_rate; q.viol_rate = filter_constraint_violation_reduction_rate;
+  q.steps = h->d_steps; q.cost0 = d_c0; q.viol0 = d_v0; q.cost = d_cost; q.barrier = h->d_ls_barrier; q.viol = d_viol;
+  q.filt = h->d_ls_filt; q.nfilt = h->d_ls_nfilt; q.out_step = h->d_ls_step; q.out_k = h->d_ls_k;
+  rbt::line_search_filter_kernel<<<(h->batch + 127) / 128, 128, 0, st>>>(q);
+  RBT_CUDA(h, cudaGetLastError());
+  h->launches += 1;
+  if (step_host) RBT_CUDA(h, cudaMemcpyAsync(step_host, h->d_ls_step, size_t(h->batch) * 8, cudaMemcpyDeviceToHost, st));
+  if (accepted_trial_host) RBT_CUDA(h, cudaMemcpyAsync(accepted_trial_host, h->d_ls_k, size_t(h->batch) * sizeof(int), cudaMemcpyDeviceToHost, st));
   return RBT_OK;
 }
 
