@@ -322,8 +322,11 @@ struct CondCfg {
   static_assert(NFM * NX + NFM * NV <= NVF * NX, "Qaf | Quf fit in the dIDCdqv buffer");
 };
 
+#ifndef RBT_COND_MIN_CTAS
+#define RBT_COND_MIN_CTAS 6
+#endif
 template <int NV, int NU, int NFM>
-__global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS, 6) condense_kernel(const StageParams p) {
+__global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS, RBT_COND_MIN_CTAS) condense_kernel(const StageParams p) {
   using C = CondCfg<NV, NU, NFM>;
   constexpr int NX = C::NX, NVF = C::NVF, NTHR = C::NTHREADS, TX = C::TX, TF = C::TF, TV = C::TV, TU = C::TU, TM = C::TM;
   extern __shared__ __align__(16) double smem[];

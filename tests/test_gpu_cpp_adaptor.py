@@ -22,6 +22,7 @@ def test_cpp_adaptor_compiles_and_links(tmp_path):
     """CPU: the header compiles as C++14 and links against the C ABI (no compute call)."""
     assert os.path.exists(_build(str(tmp_path)))
     assert os.path.exists(_build(str(tmp_path), "test_direct_multiple_shooting"))
+    assert os.path.exists(_build(str(tmp_path), "test_unconstr_riccati_recursion"))
 
 
 @pytest.mark.gpu
@@ -35,6 +36,14 @@ def test_cpp_adaptor_matches_oracle(tmp_path):
 @pytest.mark.gpu
 def test_cpp_direct_multiple_shooting_matches_oracle(tmp_path):
     exe = _build(str(tmp_path), "test_direct_multiple_shooting")
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    print(out.stdout, out.stderr)
+    assert out.returncode == 0, out.stdout + out.stderr
+
+
+@pytest.mark.gpu
+def test_cpp_unconstr_adaptor_matches_oracle(tmp_path):
+    exe = _build(str(tmp_path), "test_unconstr_riccati_recursion")
     out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     print(out.stdout, out.stderr)
     assert out.returncode == 0, out.stdout + out.stderr
