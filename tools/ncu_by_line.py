@@ -13,7 +13,8 @@ rows = list(csv.reader(io.StringIO(src)))
 secs = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
 data = None
 for si, s in enumerate(secs):
-    if a.kernel in rows[s][1]:
+    _n = lambda x: re.sub(r"\(int\)|\(bool\)|\s|rbt::|void", "", x)
+    if _n(a.kernel) in _n(rows[s][1]):
         e = secs[si + 1] if si + 1 < len(secs) else len(rows)
         hdr = rows[s + 1]
         data = [r for r in rows[s + 2:e] if len(r) == len(hdr)]
