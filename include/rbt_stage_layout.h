@@ -150,26 +150,37 @@ static inline RBT_HD void rbt_make_stage_layout(const rbt_stage_dims* d, rbt_sta
 
 
 /* ---------------- host wire format of the linearization record (the PCIe-facing form used by rbt_iteration_host_wire)
- * The symmetric blocks M, Qff, Qxx, Quu travel as packed upper triangles (column-major packed, element (i,j), i <= j, at
- * j(j+1)/2 + i -- BLAS "UPLO=U" packed storage), everything else as the dense sections of the record, and neither padding
- * nor the switching-constraint section (sent separately, only for stages that carry one) is part of it.
+ * Only what a robotoc linearisation can hold travels:
+ *  - the symmetric blocks M, Qff, Qxx, Quu as packed upper triangles (column-major packed, element (i,j), i <= j, at
+ *    j(j+1)/2 + i -- BLAS "UPLO=U" packed storage);
+ *  - Qqf is NOT part of the wire record: no cost writes it, it is zero until the friction-cone condensing fills it
+ *    (src/constraints/friction_cone.cpp:219 is the only writer; cost_function.cpp:194 only scales it) -- the device zero-fills it;
+ *  - the STO section [ha | hf | hx | hu | fx | {h, Qtt}] only if the schedule has a switching-time stage (with_sto; the
+ *    kernels read it on such stages only) -- otherwise the device zero-fills it;
+ *  - neither padding nor the switching-constraint section (sent separately, only for stages that carry one).
  * A host adaptor fills it straight from the reference's Eigen members (SplitKKTMatrix::Qxx etc. are symmetric by
  * construction); the device expands it back into the rbt_stage_layout record. */
 typedef struct rbt_wire_seg { int lin_off, wire_off, n, sym; } rbt_wire_seg; /* sym: n x n packed ; else n doubles copied */
+typedef struct rbt_wire_zero { int lin_off, n; } rbt_wire_zero;             /* sections of the record the device zero-fills */
 #define RBT_WIRE_MAX_SEGS 8
-typedef struct rbt_wire_layout { int nseg, w_stride; rbt_wire_seg seg[RBT_WIRE_MAX_SEGS]; } rbt_wire_layout;
+typedef struct rbt_wire_layout { int nseg, nzero, w_stride, with_sto; rbt_wire_seg seg[RBT_WIRE_MAX_SEGS]; rbt_wire_zero zero[2]; } rbt_wire_layout;
 
-static inline RBT_HD void rbt_make_wire_layout(const rbt_stage_layout* L, rbt_wire_layout* W) {
-  int o = 0, k = 0;
-  const int tail = L->l_dgdf + rbt_up2(15 * L->ncon) - L->l_ha;
-  const int offs[RBT_WIRE_MAX_SEGS] = {L->l_M, L->l_J, L->l_Qff, L->l_Qqf, L->l_Qxx, L->l_Quu, L->l_lx, L->l_ha};
-  const int ns[RBT_WIRE_MAX_SEGS] = {L->nv, L->l_Qff - L->l_J, L->nfm, L->l_Qxx - L->l_Qqf, L->nx, L->nu, L->l_Phix - L->l_lx, tail};
-  const int sy[RBT_WIRE_MAX_SEGS] = {1, 0, 1, 0, 1, 1, 0, 0};
+static inline RBT_HD void rbt_make_wire_layout(const rbt_stage_layout* L, int with_sto, rbt_wire_layout* W) {
+  int o = 0, k = 0, n = 0;
+  const int cone = L->l_dgdf + rbt_up2(15 * L->ncon) - L->l_dgdq;
+  const int offs[RBT_WIRE_MAX_SEGS] = {L->l_M, L->l_J, L->l_Qff, L->l_Qxx, L->l_Quu, L->l_lx, L->l_dgdq, L->l_ha};
+  const int ns[RBT_WIRE_MAX_SEGS] = {L->nv, L->l_Qff - L->l_J, L->nfm, L->nx, L->nu, L->l_Phix - L->l_lx, cone, L->l_dgdq - L->l_ha};
+  const int sy[RBT_WIRE_MAX_SEGS] = {1, 0, 1, 1, 1, 0, 0, 0};
+  n = with_sto ? RBT_WIRE_MAX_SEGS : RBT_WIRE_MAX_SEGS - 1;
   for (k = 0; k < RBT_WIRE_MAX_SEGS; ++k) {
     W->seg[k].lin_off = offs[k]; W->seg[k].wire_off = o; W->seg[k].n = ns[k]; W->seg[k].sym = sy[k];
-    o += rbt_up2(sy[k] ? ns[k] * (ns[k] + 1) / 2 : ns[k]);
+    if (k < n) o += rbt_up2(sy[k] ? ns[k] * (ns[k] + 1) / 2 : ns[k]);
   }
-  W->nseg = RBT_WIRE_MAX_SEGS;
+  W->nseg = n;
+  W->with_sto = with_sto ? 1 : 0;
+  W->zero[0].lin_off = L->l_Qqf; W->zero[0].n = L->l_Qxx - L->l_Qqf;
+  W->zero[1].lin_off = L->l_ha; W->zero[1].n = L->l_dgdq - L->l_ha;
+  W->nzero = with_sto ? 1 : 2;
   W->w_stride = rbt_up2(o);
 }
 
@@ -196,6 +207,8 @@ static inline void rbt_unpack_wire_record(const rbt_wire_layout* W, const double
     for (j = 0; j < g->n; ++j)
       for (i = 0; i < g->n; ++i) dst[i + j * g->n] = (i <= j) ? src[j * (j + 1) / 2 + i] : src[i * (i + 1) / 2 + j];
   }
+  for (k = 0; k < W->nzero; ++k)
+    for (i = 0; i < W->zero[k].n; ++i) lin[W->zero[k].lin_off + i] = 0.0;
 }
 
 #define RBT_STAGE_LAYOUT_FIELDS(X) \

@@ -198,17 +198,31 @@ int rbt_iteration_host(rbt_handle* h, const double* lin_host, const double* con_
  * the reference keeps inside ConstraintComponentData; con_out's remaining fields are left untouched).  The call is
  * pipelined over chunks of the batch (upload of chunk c+1, kernels of chunk c, download of chunk c-1 overlap on three
  * streams); `stream` is ordered after the last download, so rbt_sync(h, stream) covers everything. */
-int rbt_iteration_host_bytes(rbt_handle* h, int wire, long long* h2d_bytes, long long* d2h_bytes);
+int rbt_iteration_host_bytes(rbt_handle* h, int mode /* 0 dense records, 1 wire, 2 wire + resident state */, long long* h2d_bytes,
+                             long long* d2h_bytes);
 /* The same call with the linearization records in the host wire format of rbt_stage_layout.h (packed upper triangles of the
- * symmetric blocks M, Qff, Qxx, Quu; no padding): 22 % fewer bytes over PCIe.  `lin_host_switching` = classic records, of
- * which only the switching-constraint sections of the stages that carry one are read (NULL if the schedule has none).
- * rbt_pack_wire is the host-side packing helper (what an adaptor does while copying out of SplitKKTMatrix::Qxx etc.);
- * rbt_wire_doubles gives the size of one wire record. */
+ * symmetric blocks M, Qff, Qxx, Quu; no padding; no Qqf -- zero in every robotoc linearisation until the friction-cone
+ * condensing fills it; the STO section only when the schedule has a switching-time stage): 29 % fewer bytes over PCIe than the
+ * dense records.  `lin_host_switching` = classic records, of which only the switching-constraint sections of the stages that
+ * carry one are read (NULL if the schedule has none).  rbt_pack_wire is the host-side packing helper (what an adaptor does
+ * while copying out of SplitKKTMatrix::Qxx etc.); rbt_wire_doubles gives the size of one wire record; with_sto must be
+ * rbt_wire_with_sto(h) of the schedule in force (1 if any grid point has sto or sto_next set). */
 int rbt_iteration_host_wire(rbt_handle* h, const double* wire_host, const double* lin_host_switching, const double* con_host,
                             const double* sol_host, const double* dx0_host, double* sol_out, double* con_out,
                             double* steps_out, void* stream);
-int rbt_wire_doubles(const rbt_stage_dims* sdims);
-int rbt_pack_wire(const rbt_stage_dims* sdims, const double* lin_host, double* wire_host, long long n_records);
+/* The iteration as OCPSolver itself runs it: the solution s_ and the slack / dual variables are solver STATE (members of
+ * OCPSolver / ConstraintComponentData that only updateSolution modifies), so they stay resident on the device between
+ * iterations -- initialise them once with rbt_upload(RBT_BUF_SOL / RBT_BUF_CON) (or rbt_iteration_host_wire) -- and one
+ * iteration moves only what the host recomputed at the new linearisation point: the wire records, the PDIPM residuals
+ * res_host [batch][n_grid][ncp] (= g(x) + slack, ConstraintComponentData::residual; ncp = rbt_stage_layout.ncp) and dx0.
+ * Back come (NULL = skip) the updated solution records sol_out [batch][n_grid][s_stride], the updated slack | dual
+ * slack_dual_out [batch][n_grid][2 ncp] (compact: every transfer of this call is one contiguous DMA per chunk -- strided
+ * 2-D copies of ~1 KB rows cost the copy engine as much per row as 4 KB of payload) and the step sizes. */
+int rbt_iteration_host_resident(rbt_handle* h, const double* wire_host, const double* lin_host_switching, const double* res_host,
+                                const double* dx0_host, double* sol_out, double* slack_dual_out, double* steps_out, void* stream);
+int rbt_wire_with_sto(rbt_handle* h);
+int rbt_wire_doubles(const rbt_stage_dims* sdims, int with_sto);
+int rbt_pack_wire(const rbt_stage_dims* sdims, int with_sto, const double* lin_host, double* wire_host, long long n_records);
 
 /* Multi-GPU: OCP instances are independent, so a batch is sharded over ranks without any data-path collective;
  * the one exchange is the Newton step of every OCP on every rank, e.g. for a host that advances all trajectories.

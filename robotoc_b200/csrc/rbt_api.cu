@@ -81,6 +81,8 @@ struct rbt_handle {
   // pipeline uploads, kernels and downloads over chunks of the batch
   int cb0 = 0, cnb = 0;
   double* d_wire = nullptr;  // packed host wire records (rbt_iteration_host_wire), allocated on first use
+  double* d_res_stage = nullptr;  // rbt_iteration_host_resident: compact residuals in, compact slack|dual out
+  double* d_sd_stage = nullptr;
   rbt_wire_layout W;
   bool attr_bwd = false, attr_fwd = false, attr_cond = false;  // MaxDynamicSharedMemorySize set on THIS handle's device
   cudaEvent_t ev_condense_mid = nullptr;  // caller-owned event recorded between the two kernels of rbt_condense (timing)
@@ -204,6 +206,8 @@ static int check_contacts(rbt_handle* h, const rbt_stage_ctrl* ctrl, int n_grid)
 int rbt_destroy(rbt_handle* h) {
   if (h) {
     cudaFree(h->d_wire);
+    cudaFree(h->d_res_stage);
+    cudaFree(h->d_sd_stage);
     if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
     if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
@@ -349,7 +353,13 @@ int rbt_bind_buffer(rbt_handle* h, int which, double* dev) {
 
 static long long stage_xfer(rbt_handle* h, int which, bool up, const double* host_c, double* host_m, int b0, int nb,
                             cudaStream_t st, bool do_copy, int* rc_out);
-enum { RBT_XFER_WIRE = 100, RBT_XFER_SWITCHING = 101 };
+enum { RBT_XFER_WIRE = 100, RBT_XFER_SWITCHING = 101, RBT_XFER_RES = 102, RBT_XFER_SD = 103 };
+// the STO section of the linearization records is read on switching-time stages only (riccati_backward.cuh: cs.sto)
+static int schedule_has_sto(const rbt_handle* h) {
+  for (const auto& c : h->ctrl)
+    if (c.sto || c.sto_next) return 1;
+  return 0;
+}
 
 // KKT upload plan: one strided copy of the core section [Fxx|Fvu|Fx|lx|lu|Qxx|Qxu|Quu] of every record (record padding and
 // unused switching/STO sections never cross PCIe), plus one strided copy per stage that carries extras.
@@ -920,6 +930,12 @@ static long long stage_xfer(rbt_handle* h, int which, bool up, const double* hos
     bytes += (long long)(width * 8 * nrows);
     if (!do_copy || *rc_out != RBT_OK) return;
     const size_t pitch = stride * pitch_rows * 8;
+    if (pitch == width * 8) {  // contiguous: one linear DMA
+      cudaError_t e1 = up ? cudaMemcpyAsync(dev + off, hc + off, width * 8 * nrows, cudaMemcpyHostToDevice, st)
+                          : cudaMemcpyAsync(hm + off, dev + off, width * 8 * nrows, cudaMemcpyDeviceToHost, st);
+      if (e1 != cudaSuccess) *rc_out = RBT_ERR_CUDA;
+      return;
+    }
     cudaError_t e = up ? cudaMemcpy2DAsync(dev + off, pitch, hc + off, pitch, width * 8, nrows, cudaMemcpyHostToDevice, st)
                        : cudaMemcpy2DAsync(hm + off, pitch, dev + off, pitch, width * 8, nrows, cudaMemcpyDeviceToHost, st);
     if (e != cudaSuccess) *rc_out = RBT_ERR_CUDA;
@@ -939,10 +955,17 @@ static long long stage_xfer(rbt_handle* h, int which, bool up, const double* hos
     for (int i = 0; i < h->n_grid; ++i)
       if (h->ctrl[i].ns > 0 && h->ctrl[i].type != RBT_IMPACT)                         // Phix, Phia, p, Phit
         copy2d(h->d_lin, host_c, host_m, base + size_t(i) * S.l_stride + S.l_Phix, S.l_stride, S.l_ha - S.l_Phix, h->n_grid, nb);
+  } else if (which == RBT_XFER_RES) {  // compact PDIPM residuals [batch][n_grid][ncp]: one contiguous copy into the staging buffer
+    copy2d(h->d_res_stage, host_c, host_m, go * S.ncp, S.ncp, S.ncp, 1, rows);   // (unpack_wire_kernel scatters them into c_res)
+  } else if (which == RBT_XFER_SD) {   // compact slack | dual [batch][n_grid][2 ncp] (packed by pack_slack_dual_kernel): contiguous
+    copy2d(h->d_sd_stage, host_c, host_m, go * 2 * S.ncp, 2 * S.ncp, 2 * S.ncp, 1, rows);
+
   } else if (which == RBT_BUF_CON) {
     copy2d(h->d_con, host_c, host_m, go * S.c_stride + S.c_slack, S.c_stride, size_t(up ? 3 : 2) * S.ncp, 1, rows);
   } else if (which == RBT_BUF_SOL) {
-    copy2d(h->d_sol, host_c, host_m, go * S.s_stride, S.s_stride, size_t(S.s_xi) + S.nsm, 1, rows);
+    // whole records incl. the few padding doubles: ONE contiguous DMA instead of a strided 2-D copy of 1.4 KB rows (the copy
+    // engine spends as long per row as on ~4 KB of payload)
+    copy2d(h->d_sol, host_c, host_m, go * S.s_stride, S.s_stride, S.s_stride, 1, rows);
   } else if (which == RBT_BUF_DX0) {
     copy2d(h->d_dx0, host_c, host_m, size_t(b0) * h->L.nx, h->L.nx, h->L.nx, 1, nb);
   } else if (which == RBT_BUF_STEPS) {
@@ -955,7 +978,17 @@ int rbt_iteration_host_bytes(rbt_handle* h, int wire, long long* h2d, long long*
   if (!h || !h->stage_ready || h->n_grid == 0) return RBT_ERR_STATE;
   int rc = RBT_OK;
   long long up = 0, down = 0;
-  rbt_make_wire_layout(&h->S, &h->W);
+  rbt_make_wire_layout(&h->S, schedule_has_sto(h), &h->W);
+  if (wire == 2) {  // rbt_iteration_host_resident: wire records + residuals + dx0 up
+    up += stage_xfer(h, RBT_XFER_WIRE, true, nullptr, nullptr, 0, h->batch, nullptr, false, &rc);
+    up += stage_xfer(h, RBT_XFER_SWITCHING, true, nullptr, nullptr, 0, h->batch, nullptr, false, &rc);
+    up += stage_xfer(h, RBT_XFER_RES, true, nullptr, nullptr, 0, h->batch, nullptr, false, &rc);
+    up += stage_xfer(h, RBT_BUF_DX0, true, nullptr, nullptr, 0, h->batch, nullptr, false, &rc);
+    for (int w : {int(RBT_BUF_SOL), int(RBT_XFER_SD), int(RBT_BUF_STEPS)}) down += stage_xfer(h, w, false, nullptr, nullptr, 0, h->batch, nullptr, false, &rc);
+    if (h2d) *h2d = up;
+    if (d2h) *d2h = down;
+    return RBT_OK;
+  }
   if (wire) {
     up += stage_xfer(h, RBT_XFER_WIRE, true, nullptr, nullptr, 0, h->batch, nullptr, false, &rc);
     up += stage_xfer(h, RBT_XFER_SWITCHING, true, nullptr, nullptr, 0, h->batch, nullptr, false, &rc);
@@ -969,20 +1002,31 @@ int rbt_iteration_host_bytes(rbt_handle* h, int wire, long long* h2d, long long*
   return RBT_OK;
 }
 
+// res_host != NULL: resident mode (solution, slack and dual stay where the previous iteration left them on the device; only the
+// PDIPM residuals come from the host), con_host / sol_host are not read.
 static int iteration_host_impl(rbt_handle* h, const double* wire_host, const double* lin_host, const double* con_host,
-                               const double* sol_host, const double* dx0_host, double* sol_out, double* con_out,
-                               double* steps_out, void* stream) {
-  if (!h || (!lin_host && !wire_host) || !con_host || !sol_host || !dx0_host) return RBT_ERR_ARG;
+                               const double* sol_host, const double* res_host, const double* dx0_host, double* sol_out,
+                               double* con_out, double* steps_out, void* stream) {
+  if (!h || (!lin_host && !wire_host) || !dx0_host) return RBT_ERR_ARG;
+  if (!res_host && (!con_host || !sol_host)) return RBT_ERR_ARG;
   RBT_STAGE_CHECK(h, "rbt_iteration_host");
   if (wire_host) {
-    rbt_make_wire_layout(&h->S, &h->W);
+    rbt_make_wire_layout(&h->S, schedule_has_sto(h), &h->W);
     bool sw = false;
     for (int i = 0; i < h->n_grid; ++i) sw = sw || (h->ctrl[i].ns > 0 && h->ctrl[i].type != RBT_IMPACT);
     if (sw && !lin_host) {
       h->err = "[rbt_iteration_host_wire] invalid argument: the schedule has switching-constraint stages, their sections come from lin_host_switching";
       return RBT_ERR_ARG;
     }
-    if (!h->d_wire) RBT_CUDA(h, cudaMalloc(&h->d_wire, size_t(h->batch) * h->n_grid_max * h->W.w_stride * 8));
+    if (!h->d_wire) {
+      rbt_wire_layout wmax;
+      rbt_make_wire_layout(&h->S, 1, &wmax);
+      RBT_CUDA(h, cudaMalloc(&h->d_wire, size_t(h->batch) * h->n_grid_max * wmax.w_stride * 8));
+    }
+    if (res_host && !h->d_res_stage) {
+      RBT_CUDA(h, cudaMalloc(&h->d_res_stage, size_t(h->batch) * h->n_grid_max * h->S.ncp * 8));
+      RBT_CUDA(h, cudaMalloc(&h->d_sd_stage, size_t(h->batch) * h->n_grid_max * 2 * h->S.ncp * 8));
+    }
   }
   cudaStream_t st = (cudaStream_t)stream;
   // chunks of the batch: the upload of chunk c+1, the kernels of chunk c and the download of chunk c-1 overlap
@@ -1011,8 +1055,12 @@ static int iteration_host_impl(rbt_handle* h, const double* wire_host, const dou
     } else {
       stage_xfer(h, RBT_BUF_LIN, true, lin_host, nullptr, b0, nb, h->s_h2d, true, &rc);
     }
-    stage_xfer(h, RBT_BUF_CON, true, con_host, nullptr, b0, nb, h->s_h2d, true, &rc);
-    stage_xfer(h, RBT_BUF_SOL, true, sol_host, nullptr, b0, nb, h->s_h2d, true, &rc);
+    if (res_host) {
+      stage_xfer(h, RBT_XFER_RES, true, res_host, nullptr, b0, nb, h->s_h2d, true, &rc);
+    } else {
+      stage_xfer(h, RBT_BUF_CON, true, con_host, nullptr, b0, nb, h->s_h2d, true, &rc);
+      stage_xfer(h, RBT_BUF_SOL, true, sol_host, nullptr, b0, nb, h->s_h2d, true, &rc);
+    }
     stage_xfer(h, RBT_BUF_DX0, true, dx0_host, nullptr, b0, nb, h->s_h2d, true, &rc);
     if (rc != RBT_OK) break;
     RBT_CUDA(h, cudaEventRecord(h->ev[2 * c], h->s_h2d));
@@ -1025,6 +1073,9 @@ static int iteration_host_impl(rbt_handle* h, const double* wire_host, const dou
       wp.l_stride = h->S.l_stride;
       wp.wire = h->d_wire + size_t(b0) * h->n_grid * h->W.w_stride;
       wp.lin = h->d_lin + size_t(b0) * h->n_grid * h->S.l_stride;
+      wp.res = res_host ? h->d_res_stage + size_t(b0) * h->n_grid * h->S.ncp : nullptr;
+      wp.con = h->d_con + size_t(b0) * h->n_grid * h->S.c_stride;
+      wp.c_stride = h->S.c_stride; wp.c_res = h->S.c_res; wp.ncp = h->S.ncp;
       rbt::unpack_wire_kernel<<<nb * h->n_grid, 128, 0, st>>>(wp);
       h->launches += 1;
     }
@@ -1034,10 +1085,16 @@ static int iteration_host_impl(rbt_handle* h, const double* wire_host, const dou
     h->cb0 = 0;
     h->cnb = 0;
     if (rc != RBT_OK) break;
+    if (res_host && con_out) {
+      rbt::pack_slack_dual_kernel<<<nb * h->n_grid, 64, 0, st>>>(h->d_con + size_t(b0) * h->n_grid * h->S.c_stride, h->S.c_stride,
+                                                               h->S.c_slack, 2 * h->S.ncp,
+                                                               h->d_sd_stage + size_t(b0) * h->n_grid * 2 * h->S.ncp);
+      h->launches += 1;
+    }
     RBT_CUDA(h, cudaEventRecord(h->ev[2 * c + 1], st));
     RBT_CUDA(h, cudaStreamWaitEvent(h->s_d2h, h->ev[2 * c + 1], 0));
     if (sol_out) stage_xfer(h, RBT_BUF_SOL, false, nullptr, sol_out, b0, nb, h->s_d2h, true, &rc);
-    if (con_out) stage_xfer(h, RBT_BUF_CON, false, nullptr, con_out, b0, nb, h->s_d2h, true, &rc);
+    if (con_out) stage_xfer(h, res_host ? RBT_XFER_SD : RBT_BUF_CON, false, nullptr, con_out, b0, nb, h->s_d2h, true, &rc);
     if (steps_out) stage_xfer(h, RBT_BUF_STEPS, false, nullptr, steps_out, b0, nb, h->s_d2h, true, &rc);
   }
   h->cb0 = 0;
@@ -1054,31 +1111,43 @@ static int iteration_host_impl(rbt_handle* h, const double* wire_host, const dou
 int rbt_iteration_host(rbt_handle* h, const double* lin_host, const double* con_host, const double* sol_host,
                        const double* dx0_host, double* sol_out, double* con_out, double* steps_out, void* stream) {
   if (!lin_host) return RBT_ERR_ARG;
-  return iteration_host_impl(h, nullptr, lin_host, con_host, sol_host, dx0_host, sol_out, con_out, steps_out, stream);
+  return iteration_host_impl(h, nullptr, lin_host, con_host, sol_host, nullptr, dx0_host, sol_out, con_out, steps_out, stream);
 }
 
 int rbt_iteration_host_wire(rbt_handle* h, const double* wire_host, const double* lin_host_switching, const double* con_host,
                             const double* sol_host, const double* dx0_host, double* sol_out, double* con_out,
                             double* steps_out, void* stream) {
-  if (!wire_host) return RBT_ERR_ARG;
-  return iteration_host_impl(h, wire_host, lin_host_switching, con_host, sol_host, dx0_host, sol_out, con_out, steps_out, stream);
+  if (!wire_host || !con_host || !sol_host) return RBT_ERR_ARG;
+  return iteration_host_impl(h, wire_host, lin_host_switching, con_host, sol_host, nullptr, dx0_host, sol_out, con_out, steps_out, stream);
 }
 
-int rbt_wire_doubles(const rbt_stage_dims* sdims) {
+int rbt_iteration_host_resident(rbt_handle* h, const double* wire_host, const double* lin_host_switching, const double* res_host,
+                                const double* dx0_host, double* sol_out, double* slack_dual_out, double* steps_out, void* stream) {
+  if (!wire_host || !res_host) return RBT_ERR_ARG;
+  return iteration_host_impl(h, wire_host, lin_host_switching, nullptr, nullptr, res_host, dx0_host, sol_out, slack_dual_out, steps_out,
+                             stream);
+}
+
+int rbt_wire_with_sto(rbt_handle* h) {
+  if (!h || h->n_grid == 0) return -1;
+  return schedule_has_sto(h);
+}
+
+int rbt_wire_doubles(const rbt_stage_dims* sdims, int with_sto) {
   if (!sdims) return -1;
   rbt_stage_layout S;
   rbt_wire_layout W;
   rbt_make_stage_layout(sdims, &S);
-  rbt_make_wire_layout(&S, &W);
+  rbt_make_wire_layout(&S, with_sto, &W);
   return W.w_stride;
 }
 
-int rbt_pack_wire(const rbt_stage_dims* sdims, const double* lin_host, double* wire_host, long long n_records) {
+int rbt_pack_wire(const rbt_stage_dims* sdims, int with_sto, const double* lin_host, double* wire_host, long long n_records) {
   if (!sdims || !lin_host || !wire_host || n_records < 0) return RBT_ERR_ARG;
   rbt_stage_layout S;
   rbt_wire_layout W;
   rbt_make_stage_layout(sdims, &S);
-  rbt_make_wire_layout(&S, &W);
+  rbt_make_wire_layout(&S, with_sto, &W);
   for (long long r = 0; r < n_records; ++r) rbt_pack_wire_record(&W, lin_host + r * S.l_stride, wire_host + r * W.w_stride);
   return RBT_OK;
 }

@@ -823,14 +823,19 @@ __global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS, RBT_COND_MIN_C
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Host wire records -> linearization records (rbt_stage_layout.h: packed upper triangles of M, Qff, Qxx, Quu).  HBM
-// streaming: one CTA per stage, coalesced reads of the 26 KB wire record, coalesced writes of the dense sections; the
-// symmetric blocks are gathered from the packed triangle.  Only used by the PCIe-facing rbt_iteration_host_wire path.
+// Host wire records -> linearization records (rbt_stage_layout.h: packed upper triangles of M, Qff, Qxx, Quu; Qqf and, on
+// schedules without switching-time stages, the STO section do not travel and are zero-filled).  HBM streaming: one CTA per
+// stage, coalesced reads of the 24 KB wire record, coalesced writes of the dense sections; the symmetric blocks are gathered
+// from the packed triangle.  Only used by the PCIe-facing rbt_iteration_host_wire / _resident paths.
 struct WireParams {
   rbt_wire_layout W;
   int l_stride;
   const double* wire;
   double* lin;
+  // resident-state path: compact PDIPM residuals [record][ncp] -> the c_res section of the PDIPM records (res == nullptr: none)
+  const double* res;
+  double* con;
+  int c_stride, c_res, ncp;
 };
 
 __global__ void __launch_bounds__(128) unpack_wire_kernel(const WireParams p) {
@@ -849,6 +854,20 @@ __global__ void __launch_bounds__(128) unpack_wire_kernel(const WireParams p) {
       }
     }
   }
+  for (int k = 0; k < p.W.nzero; ++k)
+    for (int e = threadIdx.x; e < p.W.zero[k].n; e += 128) lin[p.W.zero[k].lin_off + e] = 0.0;
+  if (p.res) {
+    const double* r = p.res + size_t(blockIdx.x) * p.ncp;
+    double* c = p.con + size_t(blockIdx.x) * p.c_stride + p.c_res;
+    for (int e = threadIdx.x; e < p.ncp; e += 128) c[e] = r[e];
+  }
+}
+
+// slack | dual of the PDIPM records (adjacent: the first 2 ncp doubles) -> compact [record][2 ncp] for one contiguous download
+__global__ void __launch_bounds__(64) pack_slack_dual_kernel(const double* con, int c_stride, int c_slack, int n2, double* out) {
+  const double* c = con + size_t(blockIdx.x) * c_stride + c_slack;
+  double* o = out + size_t(blockIdx.x) * n2;
+  for (int e = threadIdx.x; e < n2; e += 64) o[e] = c[e];
 }
 
 // ------------------------------------------------------------------------------------------------------------------

@@ -54,6 +54,14 @@ class DirectMultipleShooting:
             self._up(CON, con, self.layout.c_stride, stream)
         _check(self._lib.rbt_condense(self._h, stream), self.rr._err, "DirectMultipleShooting")
 
+    def setSolution(self, sol, stream=None):
+        """Uploads the solution records (the solver state s_ of OCPSolver)."""
+        self._up(SOL, sol, self.layout.s_stride, stream)
+
+    def setConstraintData(self, con, stream=None):
+        """Uploads the PDIPM records (slack, dual, residual of every inequality row)."""
+        self._up(CON, con, self.layout.c_stride, stream)
+
     def computeStepSizes(self, stream=None):
         _check(self._lib.rbt_expand_and_step_sizes(self._h, stream), self.rr._err, "DirectMultipleShooting")
 
@@ -119,23 +127,43 @@ class DirectMultipleShooting:
         self.rr.synchronize(stream)
         return sol_out, con_out, steps
 
-    def iteration_host_bytes(self, wire=False):
+    def iteration_host_bytes(self, wire=False, resident=False):
+        """(H2D, D2H) bytes one call moves: dense records, wire records, or wire records with resident solver state."""
         h2d, d2h = ctypes.c_longlong(), ctypes.c_longlong()
-        _check(self._lib.rbt_iteration_host_bytes(self._h, int(wire), ctypes.byref(h2d), ctypes.byref(d2h)), self.rr._err,
-               "DirectMultipleShooting")
+        _check(self._lib.rbt_iteration_host_bytes(self._h, 2 if resident else int(wire), ctypes.byref(h2d), ctypes.byref(d2h)),
+               self.rr._err, "DirectMultipleShooting")
         return h2d.value, d2h.value
 
     def pack_wire(self, lin):
-        """Linearization records -> host wire records (packed upper triangles of M, Qff, Qxx, Quu; include/rbt_stage_layout.h)."""
+        """Linearization records -> host wire records (packed upper triangles of M, Qff, Qxx, Quu; no Qqf; the STO section
+        only if the schedule in force has a switching-time stage; include/rbt_stage_layout.h)."""
         csd = self.sdims.c()
-        w = int(self._lib.rbt_wire_doubles(ctypes.byref(csd)))
+        with_sto = int(self._lib.rbt_wire_with_sto(self._h))
+        if with_sto < 0:
+            raise RuntimeError("[DirectMultipleShooting] pack_wire: set the time discretization first")
+        w = int(self._lib.rbt_wire_doubles(ctypes.byref(csd), with_sto))
         out = np.zeros(lin.shape[:-1] + (w,))
-        _check(self._lib.rbt_pack_wire(ctypes.byref(csd), _vp(lin), _vp(out), int(np.prod(lin.shape[:-1]))), self.rr._err,
+        _check(self._lib.rbt_pack_wire(ctypes.byref(csd), with_sto, _vp(lin), _vp(out), int(np.prod(lin.shape[:-1]))), self.rr._err,
                "DirectMultipleShooting")
         return out
 
+    def iteration_host_resident(self, wire, lin_switching, res, dx0, stream=None):
+        """One iteration with the solver state (solution, slack, dual) resident on the device, as OCPSolver keeps s_ and the
+        constraint data between iterations: only the wire records, the PDIPM residuals `res` [batch, n_grid, ncp] and dx0 go up.
+        Initialise the state with setSolution / setConstraintData (or one iteration_host_wire call)."""
+        S = self.layout
+        if res.shape != (self.rr.batch, self.rr.n_grid, S.ncp):
+            raise ValueError(f"[DirectMultipleShooting] invalid argument: res must have shape {(self.rr.batch, self.rr.n_grid, S.ncp)}")
+        sol_out = np.zeros(self._shape(S.s_stride))
+        sd_out = np.zeros(self._shape(2 * S.ncp))  # [slack (ncp) | dual (ncp)] per grid point
+        steps = np.empty((self.rr.batch, 2))
+        _check(self._lib.rbt_iteration_host_resident(self._h, _vp(wire), _vp(lin_switching), _vp(res), _vp(dx0), _vp(sol_out),
+                                                     _vp(sd_out), _vp(steps), stream), self.rr._err, "DirectMultipleShooting")
+        self.rr.synchronize(stream)
+        return sol_out, sd_out, steps
+
     def iteration_host_wire(self, wire, lin_switching, con, sol, dx0, stream=None):
-        """iteration_host with the linearisations in the wire format (22 % fewer PCIe bytes)."""
+        """iteration_host with the linearisations in the wire format (29 % fewer PCIe bytes)."""
         sol_out, con_out = sol.copy(), con.copy()
         steps = np.empty((self.rr.batch, 2))
         _check(self._lib.rbt_iteration_host_wire(self._h, _vp(wire), _vp(lin_switching), _vp(con), _vp(sol), _vp(dx0),

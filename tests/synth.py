@@ -229,10 +229,12 @@ def make_stage_inputs(sd: StageDims, S: StageLayout, ctrl, batch: int, seed: int
 
 
 def symmetrize_lin(S: StageLayout, lin):
-    """Makes the symmetric blocks of linearization records exactly symmetric (upper triangle authoritative), which is what
-    the reference's containers hold (cost Hessians, joint-space inertia) and what the host wire format assumes."""
+    """Brings linearization records to what the reference's containers hold when the hot path starts, which is what the host
+    wire format assumes: the symmetric blocks exactly symmetric (upper triangle authoritative; cost Hessians, joint-space
+    inertia) and Qqf = 0 (no cost writes it: it is filled by the friction-cone condensing, friction_cone.cpp:219)."""
     out = lin.copy()
     flat = out.reshape(-1, out.shape[-1])
+    flat[:, S.l_Qqf:S.l_Qxx] = 0.0
     for off, n in ((S.l_M, S.nv), (S.l_Qff, S.nfm), (S.l_Qxx, S.nx), (S.l_Quu, S.nu)):
         blk = flat[:, off:off + n * n].reshape(-1, n, n)  # [rec, col, row] (column-major)
         a = np.transpose(blk, (0, 2, 1))                  # a[rec, row, col]

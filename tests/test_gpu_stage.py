@@ -123,7 +123,24 @@ def _run(ctrl, batch, seed, reserve=0):
     np.testing.assert_array_equal(con4, con3)
     np.testing.assert_array_equal(steps4, steps3)
     assert rel_err(sol3[:, :, :used], sol_g[:, :, :used]) < 1e-9  # symmetrising moves the inputs by rounding only
-    assert dms.iteration_host_bytes(wire=True)[0] < 0.82 * h2d
+    assert dms.iteration_host_bytes(wire=True)[0] < 0.80 * h2d
+    # resident solver state: solution, slack and dual stay on the device, only wire records + residuals + dx0 go up
+    dms.setSolution(sol)
+    dms.setConstraintData(con)
+    res = np.ascontiguousarray(con[:, :, S.c_res:S.c_res + S.ncp])
+    sol5, sd5, steps5 = dms.iteration_host_resident(dms.pack_wire(lin_s), lin_s, res, dx0)
+    np.testing.assert_array_equal(sol5[:, :, :used], sol3[:, :, :used])
+    np.testing.assert_array_equal(steps5, steps3)
+    np.testing.assert_array_equal(sd5[:, :, :S.nc], con3[:, :, S.c_slack:S.c_slack + S.nc])
+    np.testing.assert_array_equal(sd5[:, :, S.ncp:S.ncp + S.nc], con3[:, :, S.c_dual:S.c_dual + S.nc])
+    assert dms.iteration_host_bytes(resident=True)[0] < 0.90 * dms.iteration_host_bytes(wire=True)[0]
+    # ... and a second resident iteration continues from the updated state (what a host-driven SQP loop does)
+    sol6, sd6, steps6 = dms.iteration_host_resident(dms.pack_wire(lin_s), lin_s, res, dx0)
+    con_b = con3.copy()
+    con_b[:, :, S.c_res:S.c_res + S.ncp] = res
+    sol7, con7, steps7 = dms.iteration_host_wire(dms.pack_wire(lin_s), lin_s, con_b, sol3, dx0)
+    np.testing.assert_array_equal(sol6[:, :, :used], sol7[:, :, :used])
+    np.testing.assert_array_equal(steps6, steps7)
     rr.close()
 
 

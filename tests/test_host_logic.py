@@ -114,11 +114,12 @@ def test_shard_range_partitions(batch, world):
 
 def test_wire_format_pack_is_documented_packed_upper_storage():
     """rbt_pack_wire (host helper of the C ABI) against an independent numpy restatement of the format in
-    include/rbt_stage_layout.h: dense sections copied, M / Qff / Qxx / Quu as column-major packed upper triangles."""
+    include/rbt_stage_layout.h: dense sections copied, M / Qff / Qxx / Quu as column-major packed upper triangles, no Qqf,
+    the STO section only when asked for."""
     import ctypes
     from robotoc_b200 import ANYMAL, StageDims, StageLayout, anymal_constraint_table
     from robotoc_b200._lib import lib
-    from synth import make_stage_inputs, symmetrize_lin
+    from synth import make_stage_inputs
     from helpers import small_event_schedule
     L = lib()
     tab = anymal_constraint_table()
@@ -126,32 +127,42 @@ def test_wire_format_pack_is_documented_packed_upper_storage():
     S = StageLayout(sd)
     td, ev, ctrl = small_event_schedule(False)
     lin, con, sol, dx0 = make_stage_inputs(sd, S, ctrl, 2, seed=4)
-    lin = symmetrize_lin(S, lin)
     csd = sd.c()
-    w = L.rbt_wire_doubles(ctypes.byref(csd))
-    assert w == 3320
-    wire = np.zeros(lin.shape[:-1] + (w,))
-    assert L.rbt_pack_wire(ctypes.byref(csd), lin.ctypes.data_as(ctypes.c_void_p), wire.ctypes.data_as(ctypes.c_void_p),
-                           lin.shape[0] * lin.shape[1]) == 0
-    tail = S.l_dgdf + 60 - S.l_ha
-    segs = [(S.l_M, 18, True), (S.l_J, S.l_Qff - S.l_J, False), (S.l_Qff, 12, True), (S.l_Qqf, S.l_Qxx - S.l_Qqf, False),
-            (S.l_Qxx, 36, True), (S.l_Quu, 12, True), (S.l_lx, S.l_Phix - S.l_lx, False), (S.l_ha, tail, False)]
-    rec, wrec = lin[1, 3], wire[1, 3]
-    back = np.zeros_like(rec)
-    o = 0
-    for off, n, sym in segs:
-        if not sym:
-            back[off:off + n] = wrec[o:o + n]
-            o += n + (n & 1)
-        else:
-            a = np.zeros((n, n))
-            for j in range(n):
-                for i in range(j + 1):
-                    a[i, j] = a[j, i] = wrec[o + j * (j + 1) // 2 + i]
-            back[off:off + n * n] = a.T.reshape(-1)
-            o += n * (n + 1) // 2 + ((n * (n + 1) // 2) & 1)
-    assert o == w
-    keep = np.ones(S.l_stride, bool)
-    keep[S.l_Phix:S.l_ha] = False            # the switching section is not part of the wire record
-    keep[S.l_dgdf + 60:] = False             # nor is the record padding
-    np.testing.assert_array_equal(back[keep], rec[keep])
+    cone = S.l_dgdf + 60 - S.l_dgdq
+    for with_sto, wexp in ((1, 3104), (0, 2986)):
+        w = L.rbt_wire_doubles(ctypes.byref(csd), with_sto)
+        assert w == wexp
+        wire = np.zeros(lin.shape[:-1] + (w,))
+        assert L.rbt_pack_wire(ctypes.byref(csd), with_sto, lin.ctypes.data_as(ctypes.c_void_p),
+                               wire.ctypes.data_as(ctypes.c_void_p), lin.shape[0] * lin.shape[1]) == 0
+        segs = [(S.l_M, 18, True), (S.l_J, S.l_Qff - S.l_J, False), (S.l_Qff, 12, True), (S.l_Qxx, 36, True),
+                (S.l_Quu, 12, True), (S.l_lx, S.l_Phix - S.l_lx, False), (S.l_dgdq, cone, False)]
+        if with_sto:
+            segs.append((S.l_ha, S.l_dgdq - S.l_ha, False))
+        rec, wrec = lin[1, 3], wire[1, 3]
+        back = np.zeros_like(rec)
+        o = 0
+        for off, n, sym in segs:
+            if not sym:
+                back[off:off + n] = wrec[o:o + n]
+                o += n + (n & 1)
+            else:
+                a = np.zeros((n, n))
+                for j in range(n):
+                    for i in range(j + 1):
+                        a[i, j] = a[j, i] = wrec[o + j * (j + 1) // 2 + i]
+                back[off:off + n * n] = a.T.reshape(-1)
+                o += n * (n + 1) // 2 + ((n * (n + 1) // 2) & 1)
+        assert o == w
+        keep = np.ones(S.l_stride, bool)
+        keep[S.l_Phix:S.l_ha] = False            # the switching section is not part of the wire record
+        keep[S.l_dgdf + 60:] = False             # nor is the record padding
+        keep[S.l_Qqf:S.l_Qxx] = False            # nor Qqf (zero at this point of the reference's iteration)
+        if not with_sto:
+            keep[S.l_ha:S.l_dgdq] = False
+        for off, n in ((S.l_M, 18), (S.l_Qff, 12), (S.l_Qxx, 36), (S.l_Quu, 12)):  # packed blocks: upper triangle authoritative
+            blk = rec[off:off + n * n].reshape(n, n).T
+            blk = np.triu(blk) + np.triu(blk, 1).T
+            rec = rec.copy()
+            rec[off:off + n * n] = blk.T.reshape(-1)
+        np.testing.assert_array_equal(back[keep], rec[keep])
