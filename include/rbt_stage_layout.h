@@ -41,6 +41,10 @@ typedef struct rbt_box_row {
 typedef struct rbt_constraint_table {
   int n_box;
   int n_contacts;           /* max point contacts; each active one contributes 5 friction-cone rows (friction_cone.cpp) */
+  int impact_friction_cone; /* != 0: impact stages carry the same 5 rows per active impact (ImpactFrictionCone,
+                               src/constraints/impact_friction_cone.cpp; examples/anymal/run.cpp:173-181); box limits never act
+                               on impact stages (Constraints::condenseSlackAndDual(impact_status, ...), constraints.cpp:347-354) */
+  int pad_;
   double barrier;           /* mu  (constraint_component_base.hpp:44) */
   double fraction_to_boundary;  /* tau (constraint_component_base.hpp:45) */
   rbt_box_row box[RBT_MAX_BOX_ROWS];

@@ -188,8 +188,10 @@ int orc_stage_condense(const rbt_stage_dims* sd, const rbt_constraint_table* tab
   memcpy(la, lin + S.l_la, sizeof(double) * nv);
   memcpy(lf, lin + S.l_lf, sizeof(double) * nfm);
 
-  /* ---------------- PDIPM (Intermediate / Lift stages only: trot has no impact-level constraints) */
-  if (!impact) {
+  /* ---------------- PDIPM: box limits on Intermediate / Lift stages; friction cones there and -- if the table registers
+   * ImpactFrictionCone (impact_friction_cone.cpp:190-235, the same algebra on the impact forces) -- on Impact stages */
+  const int cones = !impact || tab->impact_friction_cone;
+  if (cones) {
     double* slack = con + S.c_slack;
     double* dual = con + S.c_dual;
     double* res = con + S.c_res;
@@ -197,7 +199,7 @@ int orc_stage_condense(const rbt_stage_dims* sd, const rbt_constraint_table* tab
     double* cond = con + S.c_cond;
     double* lq = lx;
     double* lv = lx + nv;
-    for (int r = 0; r < tab->n_box; ++r) {
+    for (int r = 0; r < (impact ? 0 : tab->n_box); ++r) {
       const rbt_box_row* b = &tab->box[r];
       cmpl[r] = slack[r] * dual[r] - tab->barrier;                         /* pdipm.hxx:27-31 */
       cond[r] = (dual[r] * res[r] - cmpl[r]) / slack[r];                   /* pdipm.hxx:66-70 */
@@ -463,7 +465,7 @@ void orc_stage_expand_primal(const rbt_stage_dims* sd, const rbt_constraint_tabl
   if (!impact) gemm(0, 0, nvf, 1, nu, 1.0, ex + S.e_Z + (size_t)np * nvfm, nvfm, du, nu, 1.0, daf, nvfm); /* += Z[:,np:np+nu] du :170-171 */
   for (int i = 0; i < nvf; ++i) daf[i] -= ex[S.e_r + i];                                                  /* -= r :172 */
   for (int i = 0; i < nf; ++i) daf[nv + i] *= -1.0;                                                       /* df *= -1 :173 */
-  if (impact) return;                                         /* no impact-level constraints in the table */
+  if (impact && !tab->impact_friction_cone) return;           /* no impact-level constraints in the table */
   double* slack = con + S.c_slack;
   double* dual = con + S.c_dual;
   double* res = con + S.c_res;
@@ -472,7 +474,7 @@ void orc_stage_expand_primal(const rbt_stage_dims* sd, const rbt_constraint_tabl
   double* ddual = con + S.c_ddual;
   double* dq = (double*)dx;
   double* dv = (double*)dx + nv;
-  for (int r = 0; r < tab->n_box; ++r) {
+  for (int r = 0; r < (impact ? 0 : tab->n_box); ++r) {
     const rbt_box_row* b = &tab->box[r];
     const double* var = var_ptr(dq, dv, daf, (double*)du, b->var);
     dslack[r] = -b->sign * var[b->idx] - res[r];                                                          /* joint_*_limit.cpp:78-82 */
@@ -494,8 +496,9 @@ void orc_stage_expand_primal(const rbt_stage_dims* sd, const rbt_constraint_tabl
     }
     fstack += 3;
   }
-  steps[0] = fraction_to_boundary(S.nc, tab->fraction_to_boundary, slack, dslack);
-  steps[1] = fraction_to_boundary(S.nc, tab->fraction_to_boundary, dual, ddual);
+  const int r0 = impact ? tab->n_box : 0;                     /* an impact stage only has the cone rows (impact_friction_cone.cpp:238-268) */
+  steps[0] = fraction_to_boundary(S.nc - r0, tab->fraction_to_boundary, slack + r0, dslack + r0);
+  steps[1] = fraction_to_boundary(S.nc - r0, tab->fraction_to_boundary, dual + r0, ddual + r0);
 }
 
 /* free-flyer part of Robot::integrateConfiguration: q(p, quat xyzw) <- q (+) step*dq, textbook SE(3) exponential */
@@ -624,8 +627,8 @@ void orc_stage_expand_dual_update(const rbt_stage_dims* sd, const rbt_constraint
     for (int i = 0; i < nf; ++i) sol[S.s_mu + i] += a_ * dbm[nv + i];
     if (ns > 0)
       for (int i = 0; i < ns; ++i) sol[S.s_xi + i] += a_ * d[K.d_dxi + i];
-    if (!impact) {
-      for (int r = 0; r < S.nc; ++r) {
+    if (!impact || tab->impact_friction_cone) {
+      for (int r = impact ? S.nbox : 0; r < S.nc; ++r) {
         con[S.c_slack + r] += primal_step * con[S.c_dslack + r];
         con[S.c_dual + r] += dual_step * con[S.c_ddual + r];
       }
@@ -836,7 +839,9 @@ void orc_stage_perf_index(const rbt_stage_dims* sd, const rbt_constraint_table* 
       ORC_ACC_D(lin + S.l_lu, nu)
       ORC_ACC_D(lin + S.l_lup, np)
       ORC_ACC_P(lin + S.l_p, c->ns)
-      for (int r = 0; r < S.nc; ++r) {
+    }
+    if (!impact || tab->impact_friction_cone) {
+      for (int r = impact ? S.nbox : 0; r < S.nc; ++r) {
         const int cone = r >= S.nbox;
         if (cone && !((c->contact_mask >> ((r - S.nbox) / 5)) & 1)) continue;  /* inactive contact: residual = cmpl = 0 */
         const double sl = con[S.c_slack + r], du = con[S.c_dual + r], res = con[S.c_res + r];
@@ -882,9 +887,9 @@ void orc_set_slack_dual_positive_batch(const rbt_stage_dims* sd, const rbt_const
   const double sb = sqrt(tab->barrier);
   for (int b = 0; b < batch; ++b)
     for (int i = 0; i < n_grid; ++i) {
-      if (ctrl[i].type == RBT_TERMINAL || ctrl[i].type == RBT_IMPACT) continue;
+      if (ctrl[i].type == RBT_TERMINAL || (ctrl[i].type == RBT_IMPACT && !tab->impact_friction_cone)) continue;
       double* cc = con + ((size_t)b * n_grid + i) * S.c_stride;
-      for (int r = 0; r < S.nc; ++r) {
+      for (int r = (ctrl[i].type == RBT_IMPACT) ? S.nbox : 0; r < S.nc; ++r) {
         if (cc[S.c_slack + r] < sb) cc[S.c_slack + r] = sb;
         cc[S.c_dual + r] = tab->barrier / cc[S.c_slack + r];
       }
@@ -950,9 +955,9 @@ void orc_stage_trial(const rbt_stage_dims* sd, const rbt_constraint_table* tab, 
   if (!impact)
     for (int i = 0; i < nu; ++i) trial[ORC_T_U + i] = sol[S.s_u + i] + alpha * d[K.d_du + i];
   for (int i = 0; i < c->nf; ++i) trial[ORC_T_F + i] = sol[S.s_f + i] + alpha * daf[nv + i];
-  if (!impact) {
+  if (!impact || tab->impact_friction_cone) {
     double lb = 0.0;
-    for (int r = 0; r < S.nc; ++r) {
+    for (int r = impact ? S.nbox : 0; r < S.nc; ++r) {
       if (r >= S.nbox && !((c->contact_mask >> ((r - S.nbox) / 5)) & 1)) continue;
       lb -= tab->barrier * log(con[S.c_slack + r] + alpha * con[S.c_dslack + r]);
     }

@@ -41,6 +41,7 @@
 #include "robotoc/constraints/joint_torques_lower_limit.hpp"
 #include "robotoc/constraints/joint_torques_upper_limit.hpp"
 #include "robotoc/constraints/friction_cone.hpp"
+#include "robotoc/constraints/impact_friction_cone.hpp"
 #include "robotoc/line_search/line_search_filter.hpp"
 
 #include "../../include/rbt_layout.h"
@@ -68,6 +69,7 @@ std::shared_ptr<Constraints> make_constraints(const Robot& robot, const rbt_cons
   c->add("joint_torques_lower", std::make_shared<JointTorquesLowerLimit>(robot));
   c->add("joint_torques_upper", std::make_shared<JointTorquesUpperLimit>(robot));
   c->add("friction_cone", std::make_shared<FrictionCone>(robot));
+  if (tab->impact_friction_cone) c->add("impact_friction_cone", std::make_shared<ImpactFrictionCone>(robot));  // run.cpp:173-181
   return c;
 }
 
@@ -206,6 +208,24 @@ int ref_stage(const rbt_stage_dims* sd, const rbt_constraint_table* tab, const r
       }
     }
   }
+  const bool icone = impact && tab->impact_friction_cone;
+  if (icone) {  // the ImpactFrictionCone component: same record rows, same J slots (impact_friction_cone.hpp:140-148)
+    ConstraintComponentData& cc = cdata.impact_level_data[0];
+    const int off = 6 * nj, n = 5 * tab->n_contacts;
+    put_v(cc.slack, con + S.c_slack + off, n);
+    put_v(cc.dual, con + S.c_dual + off, n);
+    put_v(cc.residual, con + S.c_res + off, n);
+    cc.cmpl.setZero();
+    for (int ci = 0; ci < tab->n_contacts; ++ci) {
+      if (!((c->contact_mask >> ci) & 1)) {
+        cc.residual.template segment<5>(5 * ci).setZero();  // ImpactFrictionCone::evalConstraint zeroes inactive contacts
+        continue;
+      }
+      pdipm::computeComplementarySlackness<5>(tab->barrier, cc, 5 * ci);
+      put_m(cc.J[ci], lin + S.l_dgdq + size_t(ci) * 5 * nv, 5, nv, 5);
+      put_m(cc.J[tab->n_contacts + ci], lin + S.l_dgdf + size_t(ci) * 15, 5, 3, 5);
+    }
+  }
   // ---- "Forms linear system"
   SplitSolution s_dummy(robot), s_next_dummy(robot);
   if (!impact) {
@@ -266,6 +286,11 @@ int ref_stage(const rbt_stage_dims* sd, const rbt_constraint_table* tab, const r
       get_v(cc.cond, con + S.c_cond + off, n);
     }
   }
+  if (icone) {
+    ConstraintComponentData& cc = cdata.impact_level_data[0];
+    get_v(cc.cmpl, con + S.c_cmpl + 6 * nj, 5 * tab->n_contacts);
+    get_v(cc.cond, con + S.c_cond + 6 * nj, 5 * tab->n_contacts);
+  }
   if (phase < 2) return 0;
 
   // ---- primal expansion + step sizes
@@ -295,6 +320,11 @@ int ref_stage(const rbt_stage_dims* sd, const rbt_constraint_table* tab, const r
       get_v(cc.dslack, con + S.c_dslack + off, n);
       get_v(cc.ddual, con + S.c_ddual + off, n);
     }
+  if (icone) {
+    ConstraintComponentData& cc = cdata.impact_level_data[0];
+    get_v(cc.dslack, con + S.c_dslack + 6 * nj, 5 * tab->n_contacts);
+    get_v(cc.ddual, con + S.c_ddual + 6 * nj, 5 * tab->n_contacts);
+  }
   if (phase < 3) return 0;
 
   // ---- dual expansion, costate correction, slack / dual update
@@ -320,6 +350,13 @@ int ref_stage(const rbt_stage_dims* sd, const rbt_constraint_table* tab, const r
       get_v(cc.slack, con + S.c_slack + off, n);
       get_v(cc.dual, con + S.c_dual + off, n);
     }
+  }
+  if (icone) {  // ImpactStage::updatePrimal / updateDual (impact_stage.cpp:151-165)
+    Constraints::updateSlack(cdata, alpha_p);
+    Constraints::updateDual(cdata, alpha_d);
+    ConstraintComponentData& cc = cdata.impact_level_data[0];
+    get_v(cc.slack, con + S.c_slack + 6 * nj, 5 * tab->n_contacts);
+    get_v(cc.dual, con + S.c_dual + 6 * nj, 5 * tab->n_contacts);
   }
   return 0;
 }

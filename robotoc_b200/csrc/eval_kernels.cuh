@@ -58,8 +58,10 @@ __global__ void __launch_bounds__(128) perf_index_kernel(const EvalParams q) {
       acc_d(lin + S.l_lu, S.nu);
       acc_d(lin + S.l_lup, S.np);
       acc_p(lin + S.l_p, c.ns);
+    }
+    if (!impact || p.tab.impact_friction_cone != 0) {  // impact stages: the ImpactFrictionCone rows only
       const double mu = p.tab.barrier;
-      for (int r = lane; r < S.nc; r += 32) {
+      for (int r = lane + (impact ? S.nbox : 0); r < S.nc; r += 32) {
         const bool cone = r >= S.nbox;
         if (cone && !((c.contact_mask >> ((r - S.nbox) / 5)) & 1)) continue;
         const double sl = con[S.c_slack + r], du = con[S.c_dual + r], res = con[S.c_res + r];
@@ -109,7 +111,7 @@ __global__ void slack_dual_positive_kernel(const EvalParams q) {
   const long long st = e / S.ncp;
   const int i = int(st % p.n_grid);
   const int type = p.ctrl[i].type;
-  if (r >= S.nc || type == RBT_TERMINAL || type == RBT_IMPACT) return;
+  if (r >= S.nc || type == RBT_TERMINAL || (type == RBT_IMPACT && (p.tab.impact_friction_cone == 0 || r < S.nbox))) return;
   double* con = p.con + size_t(st) * S.c_stride;
   const double sb = sqrt(p.tab.barrier);
   const double sl = fmax(con[S.c_slack + r], sb);

@@ -64,8 +64,8 @@ __global__ void __launch_bounds__(128) trial_solution_kernel(const TrialParams q
     if (!impact)
       for (int e = lane; e < nu; e += 32) tr[T_U + e] = sol[S.s_u + e] + alpha * d[K.d_du + e];
     for (int e = lane; e < c.nf; e += 32) tr[T_F + e] = sol[S.s_f + e] + alpha * xd[S.x_daf + nv + e];
-    if (!impact) {
-      for (int r = lane; r < S.nc; r += 32) {
+    if (!impact || p.tab.impact_friction_cone != 0) {
+      for (int r = lane + (impact ? S.nbox : 0); r < S.nc; r += 32) {
         if (r >= S.nbox && !((c.contact_mask >> ((r - S.nbox) / 5)) & 1)) continue;
         lb -= p.tab.barrier * log(con[S.c_slack + r] + alpha * con[S.c_dslack + r]);
       }

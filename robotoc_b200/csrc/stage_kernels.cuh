@@ -350,6 +350,9 @@ __global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS, RBT_COND_MIN_C
     return;
   }
   const bool impact = (c.type == RBT_IMPACT);
+  // inequality rows: box limits + friction cones on Intermediate / Lift stages; on Impact stages only the cones, and only if the
+  // table registers ImpactFrictionCone (impact_friction_cone.cpp:190-235 -- the same algebra on the impact forces)
+  const bool pdipm = !impact || p.tab.impact_friction_cone != 0;
   const int nf = c.nf, nvf = NV + nf, ns = impact ? 0 : c.ns;
   const double dt = c.dt;
   double* in1 = smem + C::o_in1;
@@ -400,14 +403,14 @@ __global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS, RBT_COND_MIN_C
     mbar_init(bar, 1);
     fence_mbar_init();
     uint32_t bytes = uint32_t(C::IN1 + NVF * NVF + C::IN2) * 8u;
-    if (!impact) bytes += uint32_t(3 * ncp + gsz) * 8u;
+    if (pdipm) bytes += uint32_t(3 * ncp + gsz) * 8u;
     mbar_expect_tx(bar, bytes);
     l2_prefetch_bulk(lin + S.l_Qxx, uint32_t(NX * NX) * 8u);
     tma_load_1d(in1, lin + S.l_D, uint32_t(C::IN1A) * 8u, bar);
     tma_load_1d(in1 + C::IN1A, lin + S.l_Quu, uint32_t(C::IN1B) * 8u, bar);
     tma_load_1d(sZ, ex + S.e_Z, uint32_t(NVF * NVF) * 8u, bar);
     tma_load_1d(smem + C::o_in2, lin + S.l_ha, uint32_t(C::IN2) * 8u, bar);
-    if (!impact) {
+    if (pdipm) {
       tma_load_1d(cSl, con + S.c_slack, uint32_t(3 * ncp) * 8u, bar);
       tma_load_1d(sDq, lin + S.l_dgdq, uint32_t(gsz) * 8u, bar);
     }
@@ -430,10 +433,15 @@ __global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS, RBT_COND_MIN_C
     if (tid >= NV && tid - NV >= nf) vlf[tid - NV] = 0.0;
   }
   for (int e = tid; e < NV * NV + NV; e += NTHR) dQq[e] = 0.0;  // (dQv follows dQq)
-  if (!impact) {
+  if (pdipm) {
     const double mu = p.tab.barrier;
     for (int r = tid; r < nc; r += NTHR) {  // pdipm.hxx:27-100
       const bool cone = r >= nbox;
+      if (impact && !cone) {  // box limits do not act on impact stages: no weight, no gradient, record untouched
+        cW[r] = 0.0;
+        cC[r] = 0.0;
+        continue;
+      }
       const bool act = !cone || ((c.contact_mask >> ((r - nbox) / 5)) & 1);
       double w = 0.0, cd = 0.0;
       if (act) {
@@ -456,7 +464,7 @@ __global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS, RBT_COND_MIN_C
 
   // ---- phase 2: PDIPM condensing applied to the working copies       joint_*_limit.cpp:68-75, friction_cone.cpp:194-235
   // A target (variable, index) gathers its box rows in table order (deterministic; a lower and an upper limit share it).
-  if (!impact) {
+  if (pdipm) {
     auto gather = [&](int tgt, double& w, double& gs) {
       w = 0.0; gs = 0.0;
 #pragma unroll
@@ -904,6 +912,7 @@ __global__ void __launch_bounds__(XTHR) expand_kernel(const StageParams p) {
   const rbt_stage_ctrl c = p.ctrl[i];
   if (c.type == RBT_TERMINAL) return;  // step sizes 1.0 (terminal_stage.cpp:127-136)
   const bool impact = (c.type == RBT_IMPACT);
+  const bool pdipm = !impact || p.tab.impact_friction_cone != 0;  // impact stages: cone rows only (impact_friction_cone.cpp:238-268)
   const int nf = c.nf, nvf = NV + nf, np = S.np;
   const double* lin = p.lin + o * S.l_stride;
   const double* ex = p.ex + o * S.e_stride;
@@ -915,11 +924,12 @@ __global__ void __launch_bounds__(XTHR) expand_kernel(const StageParams p) {
     mbar_init(&bar, 1);
     fence_mbar_init();
     uint32_t bytes = RSZ * 8;
-    if (!impact) bytes += ZSZ * 8 + gsz * 8 + 4 * S.ncp * 8;
+    if (!impact) bytes += ZSZ * 8;
+    if (pdipm) bytes += gsz * 8 + 4 * S.ncp * 8;
     mbar_expect_tx(&bar, bytes);
     tma_load_1d(sR, ex + S.e_R, RSZ * 8, &bar);
-    if (!impact) {
-      tma_load_1d(sZ, ex + S.e_Z + np * NVF, ZSZ * 8, &bar);
+    if (!impact) tma_load_1d(sZ, ex + S.e_Z + np * NVF, ZSZ * 8, &bar);
+    if (pdipm) {
       tma_load_1d(sG, lin + S.l_dgdq, gsz * 8, &bar);
       tma_load_1d(sC, con + S.c_slack, 4 * S.ncp * 8, &bar);
     }
@@ -946,11 +956,12 @@ __global__ void __launch_bounds__(XTHR) expand_kernel(const StageParams p) {
     sdaf[tid] = acc;
     xd[S.x_daf + tid] = acc;
   }
-  if (impact) return;
+  if (!pdipm) return;
   __syncthreads();
   const double tau = p.tab.fraction_to_boundary;
   double mp = 1.0, md = 1.0;
   for (int r = tid; r < S.nc; r += NTHR) {
+    if (impact && r < nbox) continue;
     const double c_sl = sC[r], c_du = sC[ncp + r], c_res = sC[2 * ncp + r], c_cm = sC[3 * ncp + r];
     double dsl, ddu;
     if (r < nbox) {
@@ -1069,8 +1080,8 @@ __global__ void __launch_bounds__(XTHR) update_kernel(const StageParams p) {
   for (int e = tid; e < NU; e += NTHR) sdu[e] = (terminal || impact) ? 0.0 : d[K.d_du + e];
   if (!terminal)
     for (int e = tid; e < NV; e += NTHR) sdgn[e] = d[K.d_stride + K.d_dlmdgmm + NV + e];  // dgmm of stage i+1 (not modified here)
-  if (!terminal && !impact) {
-    for (int r = tid; r < S.nc; r += NTHR) {  // updateSlack / updateDual    constraint_component_base.hxx:25-36
+  if (!terminal && (!impact || p.tab.impact_friction_cone != 0)) {
+    for (int r = tid + (impact ? p.tab.n_box : 0); r < S.nc; r += NTHR) {  // updateSlack / updateDual    constraint_component_base.hxx:25-36
       con[S.c_slack + r] += ap * con[S.c_dslack + r];
       con[S.c_dual + r] += ad * con[S.c_ddual + r];
     }

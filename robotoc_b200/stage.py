@@ -24,7 +24,8 @@ class rbt_box_row(ctypes.Structure):
 
 
 class rbt_constraint_table(ctypes.Structure):
-    _fields_ = [("n_box", ctypes.c_int), ("n_contacts", ctypes.c_int), ("barrier", ctypes.c_double),
+    _fields_ = [("n_box", ctypes.c_int), ("n_contacts", ctypes.c_int), ("impact_friction_cone", ctypes.c_int),
+                ("pad_", ctypes.c_int), ("barrier", ctypes.c_double),
                 ("fraction_to_boundary", ctypes.c_double), ("box", rbt_box_row * RBT_MAX_BOX_ROWS)]
 
 
@@ -40,11 +41,13 @@ _SFIELDS = ("nv nu nx np nfm nvf nsm ncon nbox nc ncp nq l_M l_J l_D l_IDC l_Qaa
             "x_dbetamu x_dnup x_stride").split()
 
 
-def anymal_constraint_table(barrier=1.0e-3, fraction_to_boundary=0.995):
+def anymal_constraint_table(barrier=1.0e-3, fraction_to_boundary=0.995, impact_friction_cone=False):
     """examples/anymal/trot.cpp:131-148: joint position / velocity / torque lower+upper limits on the 12 actuated joints
-    (72 box rows) and friction cones on the 4 feet (5 rows each) -> 92 inequalities per stage."""
+    (72 box rows) and friction cones on the 4 feet (5 rows each) -> 92 inequalities per stage.  `impact_friction_cone`:
+    the same cone rows on the impact forces of Impact stages (ImpactFrictionCone, as examples/anymal/run.cpp:173-181 adds)."""
     t = rbt_constraint_table()
     t.n_contacts = 4
+    t.impact_friction_cone = int(bool(impact_friction_cone))
     t.barrier, t.fraction_to_boundary = barrier, fraction_to_boundary
     r = 0
     for var, off in ((VAR_Q, 6), (VAR_V, 6), (VAR_U, 0)):

@@ -21,13 +21,15 @@ SEED, BATCH = 301, 1
 KEYS = ("kkt", "cc_cond", "ric", "d", "cc_exp", "xd_exp", "steps", "d_upd", "xd_upd", "cc_upd", "ex_upd")
 
 
-def problem(S_getter=None, K_getter=None):
+def problem(S_getter=None, K_getter=None, impact_cones=False):
+    """impact_cones: the same problem with ImpactFrictionCone registered (examples/anymal/run.cpp:173-181): the impact stage
+    carries friction-cone rows on the impact forces (golden keys prefixed "ic_")."""
     from robotoc_b200 import Layout, StageLayout
-    table = anymal_constraint_table()
+    table = anymal_constraint_table(impact_friction_cone=impact_cones)
     sd = StageDims(ANYMAL, nf_max=12, n_contacts=table.n_contacts, n_box=table.n_box)
     S, K = StageLayout(sd, getter=S_getter), Layout(ANYMAL, getter=K_getter)
     td, ev, ctrl = small_event_schedule(True)
-    lin, con, sol, dx0 = make_stage_inputs(sd, S, ctrl, BATCH, SEED)
+    lin, con, sol, dx0 = make_stage_inputs(sd, S, ctrl, BATCH, SEED, impact_cones=impact_cones)
     return table, sd, S, K, ctrl, lin, con, sol, dx0
 
 
@@ -37,6 +39,10 @@ if __name__ == "__main__":
     lib = oracle_lib.load()
     table, sd, S, K, ctrl, lin, con, sol, dx0 = problem(lib.orc_stage_layout_get, lib.orc_layout_get)
     out = ref_lib.reference_iteration(sd, S, K, table, ctrl, lin, con, dx0)
+    data = {k: out[k] for k in KEYS}
+    table, sd, S, K, ctrl, lin, con, sol, dx0 = problem(lib.orc_stage_layout_get, lib.orc_layout_get, impact_cones=True)
+    out = ref_lib.reference_iteration(sd, S, K, table, ctrl, lin, con, dx0)
+    data.update({"ic_" + k: out[k] for k in KEYS})
     path = os.path.join(HERE, "golden_ref_stage_r2.npz")
-    np.savez_compressed(path, **{k: out[k] for k in KEYS})
+    np.savez_compressed(path, **data)
     print("wrote", path, os.path.getsize(path) // 1024, "KiB")

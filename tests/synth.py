@@ -140,10 +140,12 @@ def _putm(rec, off, block, ld):
     view[:, :, :m] = np.transpose(block, (0, 2, 1))
 
 
-def make_stage_inputs(sd: StageDims, S: StageLayout, ctrl, batch: int, seed: int):
+def make_stage_inputs(sd: StageDims, S: StageLayout, ctrl, batch: int, seed: int, impact_cones: bool = False):
     """Synthetic linearization / PDIPM / solution records (there is no Pinocchio here).  Structure follows what the
     reference's linearize* halves produce: M SPD (joint-space inertia), J a contact Jacobian, diagonal Qaa, friction-cone
-    Jacobians per active contact, SE(3) blocks [[A,B],[0,D]] (se3_jacobian_inverse.hxx), slack/dual > 0."""
+    Jacobians per active contact, SE(3) blocks [[A,B],[0,D]] (se3_jacobian_inverse.hxx), slack/dual > 0.
+    impact_cones: also the ImpactFrictionCone rows of Impact stages (drawn from a second generator, so the other records do
+    not depend on the switch)."""
     rng = np.random.default_rng(seed)
     d = sd.dims
     nv, nu, nx, np_, nfm, nvfm = d.nv, d.nu, d.nx, d.n_passive, sd.nf_max, d.nv + sd.nf_max
@@ -225,6 +227,21 @@ def make_stage_inputs(sd: StageDims, S: StageLayout, ctrl, batch: int, seed: int
             con[:, i, S.c_dual:S.c_dual + nc] = rng.uniform(0.01, 1.0, size=(batch, nc))
             con[:, i, S.c_res:S.c_res + nc] = 0.1 * _u(rng, batch, nc)
     dx0 = 0.1 * _u(rng, batch, nx)
+    if impact_cones:
+        rng2 = np.random.default_rng(seed + 7919)
+        for i in range(n_grid):
+            c = ctrl[i]
+            if c.type != IMPACT:
+                continue
+            rec = lin[:, i]
+            for ci in range(sd.n_contacts):
+                if (c.contact_mask >> ci) & 1:
+                    _putm(rec, S.l_dgdq + ci * 5 * nv, 0.3 * _u(rng2, batch, 5, nv), 5)
+                    _putm(rec, S.l_dgdf + ci * 15, _u(rng2, batch, 5, 3), 5)
+            o0, o1 = S.nbox, S.nc
+            con[:, i, S.c_slack + o0:S.c_slack + o1] = rng2.uniform(0.01, 1.0, size=(batch, o1 - o0))
+            con[:, i, S.c_dual + o0:S.c_dual + o1] = rng2.uniform(0.01, 1.0, size=(batch, o1 - o0))
+            con[:, i, S.c_res + o0:S.c_res + o1] = 0.1 * _u(rng2, batch, o1 - o0)
     return np.ascontiguousarray(lin), np.ascontiguousarray(con), np.ascontiguousarray(sol), np.ascontiguousarray(dx0)
 
 

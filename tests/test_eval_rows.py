@@ -13,13 +13,13 @@ from robotoc_b200.grid import IMPACT, TERMINAL
 from synth import make_stage_inputs, mat
 
 
-def _setup(sched, batch, seed, getter=None):
+def _setup(sched, batch, seed, getter=None, impact_cones=False):
     lib = oracle_lib.load()
-    table = anymal_constraint_table()
+    table = anymal_constraint_table(impact_friction_cone=impact_cones)
     sd = StageDims(ANYMAL, nf_max=12, n_contacts=table.n_contacts, n_box=table.n_box)
     S = StageLayout(sd, getter=getter or lib.orc_stage_layout_get)
     td, ev, ctrl = sched
-    lin, con, sol, dx0 = make_stage_inputs(sd, S, ctrl, batch, seed)
+    lin, con, sol, dx0 = make_stage_inputs(sd, S, ctrl, batch, seed, impact_cones=impact_cones)
     # give the residual slots of the records something to measure
     rng = np.random.default_rng(seed + 1)
     for i, c in enumerate(ctrl):
@@ -56,13 +56,16 @@ def _numpy_perf(S, table, ctrl, lin, con):
         kkt += sq(Fx) + sq(la) + sq(lf) + sq(IDC)
         pf += l1(Fx) + l1(IDC)
         df += l1(la) + l1(lf)
-        if c.type == IMPACT:
+        if c.type == IMPACT and not table.impact_friction_cone:
             continue
-        lu, lup, p = rec[:, S.l_lu:S.l_lu + S.nu], rec[:, S.l_lup:S.l_lup + S.np], rec[:, S.l_p:S.l_p + c.ns]
-        kkt += sq(lu) + sq(lup) + sq(p)
-        df += l1(lu) + l1(lup)
-        pf += l1(p)
+        if c.type != IMPACT:
+            lu, lup, p = rec[:, S.l_lu:S.l_lu + S.nu], rec[:, S.l_lup:S.l_lup + S.np], rec[:, S.l_p:S.l_p + c.ns]
+            kkt += sq(lu) + sq(lup) + sq(p)
+            df += l1(lu) + l1(lup)
+            pf += l1(p)
         act = np.ones(S.nc, dtype=bool)
+        if c.type == IMPACT:
+            act[:S.nbox] = False  # impact stages only carry the ImpactFrictionCone rows
         for ci in range(S.ncon):
             if not (c.contact_mask >> ci) & 1:
                 act[S.nbox + 5 * ci:S.nbox + 5 * ci + 5] = False
@@ -75,10 +78,11 @@ def _numpy_perf(S, table, ctrl, lin, con):
     return np.stack([np.zeros(b), lb, pf, df, kkt, np.sqrt(kkt), np.zeros(b), np.zeros(b)], axis=1)
 
 
-@pytest.mark.parametrize("which", ["small", "small_sto", "trot"])
+@pytest.mark.parametrize("which", ["small", "small_sto", "trot", "trot_icone"])
 def test_oracle_performance_index_matches_the_reference_formulas(which):
-    sched = {"small": small_event_schedule(False), "small_sto": small_event_schedule(True), "trot": trot_schedule(40)}[which]
-    lib, table, sd, S, ctrl, lin, con, sol, dx0 = _setup(sched, 3, 61)
+    sched = {"small": small_event_schedule(False), "small_sto": small_event_schedule(True), "trot": trot_schedule(40),
+             "trot_icone": trot_schedule(40)}[which]
+    lib, table, sd, S, ctrl, lin, con, sol, dx0 = _setup(sched, 3, 61, impact_cones=which.endswith("icone"))
     got = _oracle_perf(lib, sd, table, ctrl, lin, con)
     want = _numpy_perf(S, table, ctrl, lin, con)
     np.testing.assert_allclose(got, want, rtol=1e-12, atol=0)
@@ -113,11 +117,12 @@ def test_oracle_set_slack_and_dual_positive_and_initial_state_direction():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("which,batch", [("small_sto", 3), ("trot", 16), ("jump", 4)])
+@pytest.mark.parametrize("which,batch", [("small_sto", 3), ("trot", 16), ("jump", 4), ("trot_icone", 5)])
 def test_cuda_eval_rows_match_the_oracle(which, batch):
     from robotoc_b200 import DirectMultipleShooting, RiccatiRecursion
-    sched = {"small_sto": small_event_schedule(True), "trot": trot_schedule(40), "jump": jump_sto_schedule(80)}[which]
-    lib, table, sd, S, ctrl, lin, con, sol, dx0 = _setup(sched, batch, 63, getter=None)
+    sched = {"small_sto": small_event_schedule(True), "trot": trot_schedule(40), "jump": jump_sto_schedule(80),
+             "trot_icone": trot_schedule(40)}[which]
+    lib, table, sd, S, ctrl, lin, con, sol, dx0 = _setup(sched, batch, 63, getter=None, impact_cones=which.endswith("icone"))
     S = StageLayout(sd)
     rr = RiccatiRecursion(ANYMAL, len(ctrl), batch)
     rr.setTimeDiscretization(ctrl)

@@ -22,7 +22,7 @@ G = np.load(os.path.join(HERE, "golden", "golden_ref_stage_r2.npz"))
 TOL = 1e-10
 
 
-def _cmp_records(S, K, ctrl, got, ref, tol, skip_sol=True):
+def _cmp_records(S, K, ctrl, got, ref, tol, skip_sol=True, impact_cones=False):
     """Every section the reference's code produces, stage by stage (sections it leaves untouched are not compared)."""
     def rel(name, a, b):
         s = float(np.max(np.abs(b)))
@@ -48,6 +48,11 @@ def _cmp_records(S, K, ctrl, got, ref, tol, skip_sol=True):
         rel(f"daf[{i}]", got["xd_exp"][:, i, S.x_daf:S.x_daf + nvf], ref["xd_exp"][:, i, S.x_daf:S.x_daf + nvf])
         rel(f"dbetamu[{i}]", got["xd_upd"][:, i, S.x_dbetamu:S.x_dbetamu + nvf], ref["xd_upd"][:, i, S.x_dbetamu:S.x_dbetamu + nvf])
         if c.type == IMPACT:
+            if impact_cones:  # the ImpactFrictionCone rows (the box rows do not exist on an impact stage)
+                for key, fields in (("cc_cond", ("c_cmpl", "c_cond")), ("cc_exp", ("c_dslack", "c_ddual")), ("cc_upd", ("c_slack", "c_dual"))):
+                    for f in fields:
+                        o = getattr(S, f)
+                        rel(f"impact {f}[{i}]", got[key][:, i, o + S.nbox:o + S.nc], ref[key][:, i, o + S.nbox:o + S.nc])
             continue
         for f, n in (("e_Qafu", S.nvf * nv), ("e_Qxup", nx * S.np), ("e_Quup", S.np * nu), ("e_lup", S.np), ("e_haf", nvf)):
             o = getattr(S, f)
@@ -62,14 +67,18 @@ def _cmp_records(S, K, ctrl, got, ref, tol, skip_sol=True):
     rel("steps", got["steps"], ref["steps"])
 
 
-def test_oracle_reproduces_the_reference_iteration_golden():
+@pytest.mark.parametrize("impact_cones", [False, True])
+def test_oracle_reproduces_the_reference_iteration_golden(impact_cones):
     lib = oracle_lib.load()
-    table, sd, S, K, ctrl, lin, con, sol, dx0 = mg.problem(lib.orc_stage_layout_get, lib.orc_layout_get)
+    table, sd, S, K, ctrl, lin, con, sol, dx0 = mg.problem(lib.orc_stage_layout_get, lib.orc_layout_get, impact_cones)
     got = oracle_iteration(sd, S, K, table, ctrl, lin, con, sol, dx0)
-    _cmp_records(S, K, ctrl, got, G, TOL)
+    ref = {k[3:]: G[k] for k in G.files if k.startswith("ic_")} if impact_cones else G
+    if impact_cones:  # the impact cones must matter: the iteration differs from the one without them
+        assert np.max(np.abs(ref["ric"] - G["ric"])) > 1e-6 and abs(float(ref["steps"][0, 0]) - float(G["steps"][0, 0])) >= 0.0
+    _cmp_records(S, K, ctrl, got, ref, TOL, impact_cones=impact_cones)
 
 
-@pytest.mark.parametrize("which,seed", [("small", 311), ("small_sto", 312), ("trot", 313)])
+@pytest.mark.parametrize("which,seed", [("small", 311), ("small_sto", 312), ("trot", 313), ("small_icone", 314), ("small_sto_icone", 315)])
 def test_oracle_equals_live_reference_stage_layer(which, seed):
     import ref_lib
     if not ref_lib.available():
@@ -78,20 +87,23 @@ def test_oracle_equals_live_reference_stage_layer(which, seed):
     from robotoc_b200 import ANYMAL, Layout, StageDims, StageLayout, anymal_constraint_table
     from synth import make_stage_inputs
     lib = oracle_lib.load()
-    table = anymal_constraint_table()
+    icone = which.endswith("_icone")
+    table = anymal_constraint_table(impact_friction_cone=icone)
     sd = StageDims(ANYMAL, nf_max=12, n_contacts=table.n_contacts, n_box=table.n_box)
     S, K = StageLayout(sd, getter=lib.orc_stage_layout_get), Layout(ANYMAL, getter=lib.orc_layout_get)
-    td, ev, ctrl = {"small": small_event_schedule(False), "small_sto": small_event_schedule(True), "trot": trot_schedule(40)}[which]
-    lin, con, sol, dx0 = make_stage_inputs(sd, S, ctrl, 1, seed)
+    td, ev, ctrl = {"small": small_event_schedule(False), "small_sto": small_event_schedule(True), "trot": trot_schedule(40),
+                    "small_icone": small_event_schedule(False), "small_sto_icone": small_event_schedule(True)}[which]
+    lin, con, sol, dx0 = make_stage_inputs(sd, S, ctrl, 1, seed, impact_cones=icone)
     ref = ref_lib.reference_iteration(sd, S, K, table, ctrl, lin, con, dx0)
     got = oracle_iteration(sd, S, K, table, ctrl, lin, con, sol, dx0)
-    _cmp_records(S, K, ctrl, got, ref, TOL)
+    _cmp_records(S, K, ctrl, got, ref, TOL, impact_cones=icone)
 
 
 @pytest.mark.gpu
-def test_cuda_reproduces_the_reference_iteration_golden():
+@pytest.mark.parametrize("impact_cones", [False, True])
+def test_cuda_reproduces_the_reference_iteration_golden(impact_cones):
     from robotoc_b200 import ANYMAL, DirectMultipleShooting, RiccatiRecursion
-    table, sd, S, K, ctrl, lin, con, sol, dx0 = mg.problem()
+    table, sd, S, K, ctrl, lin, con, sol, dx0 = mg.problem(impact_cones=impact_cones)
     rr = RiccatiRecursion(ANYMAL, len(ctrl), lin.shape[0])
     rr.setTimeDiscretization(ctrl)
     dms = DirectMultipleShooting(rr, sd, table)
@@ -107,5 +119,6 @@ def test_cuda_reproduces_the_reference_iteration_golden():
     dms.integrateSolution(sol)
     got["d_upd"], got["xd_upd"], got["cc_upd"], got["ex_upd"] = (rr.getDirection(), dms.getExpandedDirection(), dms.getConstraintData(),
                                                                  dms.getExpansionData())
-    _cmp_records(S, K, ctrl, got, G, 1e-8)
+    ref = {k[3:]: G[k] for k in G.files if k.startswith("ic_")} if impact_cones else G
+    _cmp_records(S, K, ctrl, got, ref, 1e-8, impact_cones=impact_cones)
     rr.close()

@@ -48,12 +48,22 @@ def _cmp(name, got, ref, tol=TOL):
     assert e < tol, f"{name}: rel err {e:.3e}"
 
 
-def _run(ctrl, batch, seed, reserve=0):
+def _cmp_rows(name, S, c, icone, f, got, ref):
+    """PDIPM rows of one stage: all rows on Intermediate / Lift stages, the ImpactFrictionCone rows on Impact stages."""
+    o = getattr(S, f)
+    if c.type == IMPACT:
+        if icone:
+            _cmp(name, got[:, o + S.nbox:o + S.nc], ref[:, o + S.nbox:o + S.nc])
+    else:
+        _cmp(name, got[:, o:o + S.nc], ref[:, o:o + S.nc])
+
+
+def _run(ctrl, batch, seed, reserve=0, impact_cones=False):
     lib = oracle_lib.load()
-    table = anymal_constraint_table()
+    table = anymal_constraint_table(impact_friction_cone=impact_cones)
     sd = StageDims(ANYMAL, nf_max=12, n_contacts=table.n_contacts, n_box=table.n_box)
     S, K = StageLayout(sd), Layout(ANYMAL)
-    lin, con, sol, dx0 = make_stage_inputs(sd, S, ctrl, batch, seed)
+    lin, con, sol, dx0 = make_stage_inputs(sd, S, ctrl, batch, seed, impact_cones=impact_cones)
     ref = _oracle_iteration(lib, sd, S, K, table, ctrl, lin, con, sol, dx0)
     rr = RiccatiRecursion(ANYMAL, len(ctrl) + reserve, batch)  # reserve: the reference sizes for N + 1 + reserved events
     rr.setTimeDiscretization(ctrl)
@@ -63,10 +73,9 @@ def _run(ctrl, batch, seed, reserve=0):
     assert int(rr.info().max()) == 0
     for i, c in enumerate(ctrl):
         _cmp(f"kkt[{i}]", kkt[:, i], ref["kkt"][:, i])
-        if c.type not in (IMPACT, TERMINAL):
+        if c.type != TERMINAL:
             for f in ("c_cmpl", "c_cond"):
-                o = getattr(S, f)
-                _cmp(f"{f}[{i}]", cc[:, i, o:o + S.nc], ref["cc_cond"][:, i, o:o + S.nc])
+                _cmp_rows(f"{f}[{i}]", S, c, impact_cones, f, cc[:, i], ref["cc_cond"][:, i])
     rr.backwardRiccatiRecursion()
     rr.forwardRiccatiRecursion(dx0)
     d = rr.getDirection()
@@ -79,10 +88,8 @@ def _run(ctrl, batch, seed, reserve=0):
         if c.type == TERMINAL:
             continue
         _cmp(f"daf[{i}]", xd[:, i, S.x_daf:S.x_daf + 18 + c.nf], ref["xd_exp"][:, i, S.x_daf:S.x_daf + 18 + c.nf])
-        if c.type != IMPACT:
-            for f in ("c_dslack", "c_ddual"):
-                o = getattr(S, f)
-                _cmp(f"{f}[{i}]", cc[:, i, o:o + S.nc], ref["cc_exp"][:, i, o:o + S.nc])
+        for f in ("c_dslack", "c_ddual"):
+            _cmp_rows(f"{f}[{i}]", S, c, impact_cones, f, cc[:, i], ref["cc_exp"][:, i])
     dms.integrateSolution(sol)
     sol_g, cc, xd, d2 = dms.getSolution(), dms.getConstraintData(), dms.getExpandedDirection(), rr.getDirection()
     for i, c in enumerate(ctrl):
@@ -92,9 +99,8 @@ def _run(ctrl, batch, seed, reserve=0):
             _cmp(f"dbetamu[{i}]", xd[:, i, S.x_dbetamu:S.x_dbetamu + 18 + c.nf], ref["xd_upd"][:, i, S.x_dbetamu:S.x_dbetamu + 18 + c.nf])
             if c.type != IMPACT:
                 _cmp(f"dnup[{i}]", xd[:, i, S.x_dnup:S.x_dnup + 6], ref["xd_upd"][:, i, S.x_dnup:S.x_dnup + 6])
-                for f in ("c_slack", "c_dual"):
-                    o = getattr(S, f)
-                    _cmp(f"{f}[{i}]", cc[:, i, o:o + S.nc], ref["cc_upd"][:, i, o:o + S.nc])
+            for f in ("c_slack", "c_dual"):
+                _cmp_rows(f"{f}[{i}]", S, c, impact_cones, f, cc[:, i], ref["cc_upd"][:, i])
     ex = dms.getExpansionData()
     for i, c in enumerate(ctrl):
         if c.type != TERMINAL:
@@ -152,6 +158,16 @@ def test_stage_layer_small_event_schedule():
 def test_stage_layer_trot_n40():
     td, ev, ctrl = trot_schedule(40)
     _run(ctrl, batch=2, seed=22)
+
+
+def test_stage_layer_impact_friction_cones():
+    """ImpactFrictionCone registered (examples/anymal/run.cpp:173-181): the Impact stages carry cone rows on the impact forces
+    -- condensing into Qqq / Qqf / Qff / lq / lf, slack / dual directions, step sizes, update (impact_friction_cone.cpp)."""
+    td, ev, ctrl = small_event_schedule(True)
+    assert any(c.type == IMPACT for c in ctrl)
+    _run(ctrl, batch=3, seed=26, impact_cones=True)
+    td, ev, ctrl = trot_schedule(40)
+    _run(ctrl, batch=2, seed=27, impact_cones=True)
 
 
 def test_stage_layer_small_event_schedule_sto():

@@ -63,14 +63,14 @@ def test_oracle_filter_loop_equals_the_reference_line_search_filter():
         assert nfilt[0] <= CAP
 
 
-def _problem(sched, batch, seed, getter=True):
+def _problem(sched, batch, seed, getter=True, impact_cones=False):
     lib = _orc()
-    table = anymal_constraint_table()
+    table = anymal_constraint_table(impact_friction_cone=impact_cones)
     sd = StageDims(ANYMAL, nf_max=12, n_contacts=table.n_contacts, n_box=table.n_box)
     S = StageLayout(sd, getter=lib.orc_stage_layout_get)
     K = Layout(ANYMAL, getter=lib.orc_layout_get)
     td, ev, ctrl = sched
-    lin, con, sol, dx0 = make_stage_inputs(sd, S, ctrl, batch, seed)
+    lin, con, sol, dx0 = make_stage_inputs(sd, S, ctrl, batch, seed, impact_cones=impact_cones)
     ref = oracle_iteration(sd, S, K, table, ctrl, lin, con, sol, dx0)
     return lib, table, sd, S, K, ctrl, lin, con, sol, dx0, ref
 
@@ -86,9 +86,10 @@ def _oracle_trials(lib, sd, table, ctrl, S, K, sol, ref, n_trials, rate=0.75):
     return alphas, barrier, trial
 
 
-def test_oracle_trial_zero_is_the_primal_part_of_the_update():
+@pytest.mark.parametrize("impact_cones", [False, True])
+def test_oracle_trial_zero_is_the_primal_part_of_the_update(impact_cones):
     """Trial k = 0 uses alpha_max, the step the update takes: its q, v, a | dv, u, f are the updated solution's."""
-    lib, table, sd, S, K, ctrl, lin, con, sol, dx0, ref = _problem(small_event_schedule(True), 2, 71)
+    lib, table, sd, S, K, ctrl, lin, con, sol, dx0, ref = _problem(small_event_schedule(True), 2, 71, impact_cones=impact_cones)
     alphas, barrier, trial = _oracle_trials(lib, sd, table, ctrl, S, K, sol, ref, 3)
     np.testing.assert_array_equal(alphas[0], ref["steps"][:, 0])
     np.testing.assert_allclose(alphas[2], ref["steps"][:, 0] * 0.75 ** 2, rtol=1e-15)
@@ -106,9 +107,11 @@ def test_oracle_trial_zero_is_the_primal_part_of_the_update():
     # barrier of trial 0 == log barrier of the updated slacks
     lb = np.zeros(2)
     for i, c in enumerate(ctrl):
-        if c.type in (IMPACT, TERMINAL):
+        if c.type == TERMINAL or (c.type == IMPACT and not impact_cones):
             continue
         act = np.ones(S.nc, dtype=bool)
+        if c.type == IMPACT:
+            act[:S.nbox] = False
         for ci in range(S.ncon):
             if not (c.contact_mask >> ci) & 1:
                 act[S.nbox + 5 * ci:S.nbox + 5 * ci + 5] = False
@@ -117,11 +120,11 @@ def test_oracle_trial_zero_is_the_primal_part_of_the_update():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("which,batch", [("small_sto", 3), ("trot", 8)])
+@pytest.mark.parametrize("which,batch", [("small_sto", 3), ("trot", 8), ("trot_icone", 4)])
 def test_cuda_line_search_matches_the_oracle(which, batch):
     from robotoc_b200 import DirectMultipleShooting, LineSearch, RiccatiRecursion
-    sched = {"small_sto": small_event_schedule(True), "trot": trot_schedule(40)}[which]
-    lib, table, sd, S, K, ctrl, lin, con, sol, dx0, ref = _problem(sched, batch, 72)
+    sched = {"small_sto": small_event_schedule(True), "trot": trot_schedule(40), "trot_icone": trot_schedule(40)}[which]
+    lib, table, sd, S, K, ctrl, lin, con, sol, dx0, ref = _problem(sched, batch, 72, impact_cones=which.endswith("icone"))
     S = StageLayout(sd)
     rr = RiccatiRecursion(ANYMAL, len(ctrl), batch)
     rr.setTimeDiscretization(ctrl)
