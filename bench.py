@@ -552,9 +552,10 @@ def main():
                              "unit": "OCP-iterations/s", "note": "backward + forward sweeps only (the parity-checked core, 8d)"},
             "e2e": {"value": world * args.batch * args.e2e_steps / (e2e_ms * 1e-3), "unit": "OCP-iterations/s",
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": args.e2e_steps,
-                    "api": {"resident": "rbt_iteration_host_resident (pinned host buffers: wire linearisation records with packed symmetric "
-                                        "blocks, PDIPM residuals, dx0 in; solution, slack|dual, step sizes out; solver state "
-                                        "resident on the device; 8-chunk upload/compute/download pipeline)",
+                    "api": {"resident": "rbt_iteration_host_resident (pinned host buffers: wire linearisation records -- packed symmetric "
+                                        "blocks, contact blocks sized by the active contacts -- PDIPM residuals, dx0 in; solution, "
+                                        "slack|dual, step sizes out; solver state resident on the device; 8-chunk "
+                                        "upload/compute/download pipeline)",
                             "wire": "rbt_iteration_host_wire (as resident, plus PDIPM slack|dual and the solution uploaded every step)",
                             "dense": "rbt_iteration_host (dense linearisation records)"}[e2e_mode]},
             "roofline": {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,

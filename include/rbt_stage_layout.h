@@ -153,39 +153,67 @@ static inline RBT_HD void rbt_make_stage_layout(const rbt_stage_dims* d, rbt_sta
 }
 
 
-/* ---------------- host wire format of the linearization record (the PCIe-facing form used by rbt_iteration_host_wire)
- * Only what a robotoc linearisation can hold travels:
- *  - the symmetric blocks M, Qff, Qxx, Quu as packed upper triangles (column-major packed, element (i,j), i <= j, at
+/* ---------------- host wire format of the linearization records (the PCIe-facing form used by rbt_iteration_host_wire /
+ * rbt_iteration_host_resident).  Only what a robotoc linearisation of THAT grid point holds travels, so the wire record of a
+ * grid point depends on the stage control word (type, nf, contact mask) -- like the reference's own containers, whose contact
+ * blocks are dimf-sized (SplitKKTMatrix::setContactDimension):
+ *  - the symmetric blocks M, Qff (nf x nf), Qxx, Quu as packed upper triangles (column-major packed, element (i,j), i <= j, at
  *    j(j+1)/2 + i -- BLAS "UPLO=U" packed storage);
+ *  - J = dCda as nf x nv, dIDCdqv as (nv+nf) x nx, IDC as nv+nf (column-major, leading dimension = the active row count);
+ *  - the friction-cone Jacobians dg/dq (5 x nv), dg/df (5 x 3) of the ACTIVE contacts only, in contact order;
  *  - Qqf is NOT part of the wire record: no cost writes it, it is zero until the friction-cone condensing fills it
  *    (src/constraints/friction_cone.cpp:219 is the only writer; cost_function.cpp:194 only scales it) -- the device zero-fills it;
  *  - the STO section [ha | hf | hx | hu | fx | {h, Qtt}] only if the schedule has a switching-time stage (with_sto; the
  *    kernels read it on such stages only) -- otherwise the device zero-fills it;
+ *  - a Terminal grid point sends Qxx, lx and the Fqq_prev block only (terminal_stage.cpp:94-106);
  *  - neither padding nor the switching-constraint section (sent separately, only for stages that carry one).
- * A host adaptor fills it straight from the reference's Eigen members (SplitKKTMatrix::Qxx etc. are symmetric by
- * construction); the device expands it back into the rbt_stage_layout record. */
-typedef struct rbt_wire_seg { int lin_off, wire_off, n, sym; } rbt_wire_seg; /* sym: n x n packed ; else n doubles copied */
+ * One OCP's wire records are concatenated in grid order (rbt_wire_layout::ocp_off = offset of the grid point inside the OCP's
+ * block; the OCP stride is the sum).  A host adaptor fills them straight from the reference's Eigen members; the device
+ * expands them back into the rbt_stage_layout records (inactive rows / contacts of the device record are never read). */
+typedef struct rbt_wire_seg { int lin_off, wire_off, rows, cols, ld, sym; } rbt_wire_seg;
+  /* sym: rows x rows packed upper triangle -> dense with leading dimension ld ; else rows x cols dense (ld rows on the wire) */
 typedef struct rbt_wire_zero { int lin_off, n; } rbt_wire_zero;             /* sections of the record the device zero-fills */
-#define RBT_WIRE_MAX_SEGS 8
-typedef struct rbt_wire_layout { int nseg, nzero, w_stride, with_sto; rbt_wire_seg seg[RBT_WIRE_MAX_SEGS]; rbt_wire_zero zero[2]; } rbt_wire_layout;
+#define RBT_WIRE_MAX_SEGS 20
+typedef struct rbt_wire_layout {
+  int nseg, nzero, w_doubles, ocp_off;
+  rbt_wire_seg seg[RBT_WIRE_MAX_SEGS];
+  rbt_wire_zero zero[2];
+} rbt_wire_layout;
 
-static inline RBT_HD void rbt_make_wire_layout(const rbt_stage_layout* L, int with_sto, rbt_wire_layout* W) {
-  int o = 0, k = 0, n = 0;
-  const int cone = L->l_dgdf + rbt_up2(15 * L->ncon) - L->l_dgdq;
-  const int offs[RBT_WIRE_MAX_SEGS] = {L->l_M, L->l_J, L->l_Qff, L->l_Qxx, L->l_Quu, L->l_lx, L->l_dgdq, L->l_ha};
-  const int ns[RBT_WIRE_MAX_SEGS] = {L->nv, L->l_Qff - L->l_J, L->nfm, L->nx, L->nu, L->l_Phix - L->l_lx, cone, L->l_dgdq - L->l_ha};
-  const int sy[RBT_WIRE_MAX_SEGS] = {1, 0, 1, 1, 1, 0, 0, 0};
-  n = with_sto ? RBT_WIRE_MAX_SEGS : RBT_WIRE_MAX_SEGS - 1;
-  for (k = 0; k < RBT_WIRE_MAX_SEGS; ++k) {
-    W->seg[k].lin_off = offs[k]; W->seg[k].wire_off = o; W->seg[k].n = ns[k]; W->seg[k].sym = sy[k];
-    if (k < n) o += rbt_up2(sy[k] ? ns[k] * (ns[k] + 1) / 2 : ns[k]);
+static inline RBT_HD void rbt_wire_add_(rbt_wire_layout* W, int lin_off, int rows, int cols, int ld, int sym) {
+  rbt_wire_seg* g = &W->seg[W->nseg++];
+  g->lin_off = lin_off; g->wire_off = W->w_doubles; g->rows = rows; g->cols = cols; g->ld = ld; g->sym = sym;
+  W->w_doubles += rbt_up2(sym ? rows * (rows + 1) / 2 : rows * cols);
+}
+
+static inline RBT_HD void rbt_make_wire_layout(const rbt_stage_layout* L, const rbt_stage_ctrl* c, int with_sto, rbt_wire_layout* W) {
+  const int nv = L->nv, nx = L->nx, nf = c->nf, nvf = nv + nf;
+  int ci;
+  W->nseg = 0; W->nzero = 0; W->w_doubles = 0; W->ocp_off = 0;
+  if (c->type == RBT_TERMINAL) {
+    rbt_wire_add_(W, L->l_Qxx, nx, nx, nx, 1);
+    rbt_wire_add_(W, L->l_lx, nx, 1, nx, 0);
+    rbt_wire_add_(W, L->l_se3 + 36, 36, 1, 36, 0);
+    return;
   }
-  W->nseg = n;
-  W->with_sto = with_sto ? 1 : 0;
+  rbt_wire_add_(W, L->l_M, nv, nv, nv, 1);
+  if (nf > 0) rbt_wire_add_(W, L->l_J, nf, nv, L->nfm, 0);
+  rbt_wire_add_(W, L->l_D, nvf, nx, L->nvf, 0);
+  rbt_wire_add_(W, L->l_IDC, nvf, 1, nvf, 0);
+  rbt_wire_add_(W, L->l_Qaa, nv, 1, nv, 0);
+  if (nf > 0) rbt_wire_add_(W, L->l_Qff, nf, nf, L->nfm, 1);
+  rbt_wire_add_(W, L->l_Qxx, nx, nx, nx, 1);
+  rbt_wire_add_(W, L->l_Quu, L->nu, L->nu, L->nu, 1);
+  rbt_wire_add_(W, L->l_lx, L->l_Phix - L->l_lx, 1, L->l_Phix - L->l_lx, 0);   /* lx | la | lf | lu | Fx | lup | SE(3) blocks */
+  for (ci = 0; ci < L->ncon; ++ci)
+    if ((c->contact_mask >> ci) & 1) {
+      rbt_wire_add_(W, L->l_dgdq + ci * 5 * nv, 5 * nv, 1, 5 * nv, 0);
+      rbt_wire_add_(W, L->l_dgdf + ci * 15, 15, 1, 15, 0);
+    }
+  if (with_sto) rbt_wire_add_(W, L->l_ha, L->l_dgdq - L->l_ha, 1, L->l_dgdq - L->l_ha, 0);
   W->zero[0].lin_off = L->l_Qqf; W->zero[0].n = L->l_Qxx - L->l_Qqf;
   W->zero[1].lin_off = L->l_ha; W->zero[1].n = L->l_dgdq - L->l_ha;
   W->nzero = with_sto ? 1 : 2;
-  W->w_stride = rbt_up2(o);
 }
 
 /* one record: rbt_stage_layout linearization record -> wire record (reads the upper triangles) */
@@ -195,9 +223,13 @@ static inline void rbt_pack_wire_record(const rbt_wire_layout* W, const double* 
     const rbt_wire_seg* g = &W->seg[k];
     double* dst = wire + g->wire_off;
     const double* src = lin + g->lin_off;
-    if (!g->sym) { for (i = 0; i < g->n; ++i) dst[i] = src[i]; continue; }
-    for (j = 0; j < g->n; ++j)
-      for (i = 0; i <= j; ++i) dst[j * (j + 1) / 2 + i] = src[i + j * g->n];
+    if (!g->sym) {
+      for (j = 0; j < g->cols; ++j)
+        for (i = 0; i < g->rows; ++i) dst[i + j * g->rows] = src[i + j * g->ld];
+      continue;
+    }
+    for (j = 0; j < g->rows; ++j)
+      for (i = 0; i <= j; ++i) dst[j * (j + 1) / 2 + i] = src[i + j * g->ld];
   }
 }
 /* wire record -> linearization record (what the device kernel does; used by the CPU tests) */
@@ -207,9 +239,13 @@ static inline void rbt_unpack_wire_record(const rbt_wire_layout* W, const double
     const rbt_wire_seg* g = &W->seg[k];
     const double* src = wire + g->wire_off;
     double* dst = lin + g->lin_off;
-    if (!g->sym) { for (i = 0; i < g->n; ++i) dst[i] = src[i]; continue; }
-    for (j = 0; j < g->n; ++j)
-      for (i = 0; i < g->n; ++i) dst[i + j * g->n] = (i <= j) ? src[j * (j + 1) / 2 + i] : src[i * (i + 1) / 2 + j];
+    if (!g->sym) {
+      for (j = 0; j < g->cols; ++j)
+        for (i = 0; i < g->rows; ++i) dst[i + j * g->ld] = src[i + j * g->rows];
+      continue;
+    }
+    for (j = 0; j < g->rows; ++j)
+      for (i = 0; i < g->rows; ++i) dst[i + j * g->ld] = (i <= j) ? src[j * (j + 1) / 2 + i] : src[i * (i + 1) / 2 + j];
   }
   for (k = 0; k < W->nzero; ++k)
     for (i = 0; i < W->zero[k].n; ++i) lin[W->zero[k].lin_off + i] = 0.0;

@@ -200,13 +200,16 @@ int rbt_iteration_host(rbt_handle* h, const double* lin_host, const double* con_
  * streams); `stream` is ordered after the last download, so rbt_sync(h, stream) covers everything. */
 int rbt_iteration_host_bytes(rbt_handle* h, int mode /* 0 dense records, 1 wire, 2 wire + resident state */, long long* h2d_bytes,
                              long long* d2h_bytes);
-/* The same call with the linearization records in the host wire format of rbt_stage_layout.h (packed upper triangles of the
- * symmetric blocks M, Qff, Qxx, Quu; no padding; no Qqf -- zero in every robotoc linearisation until the friction-cone
- * condensing fills it; the STO section only when the schedule has a switching-time stage): 29 % fewer bytes over PCIe than the
- * dense records.  `lin_host_switching` = classic records, of which only the switching-constraint sections of the stages that
- * carry one are read (NULL if the schedule has none).  rbt_pack_wire is the host-side packing helper (what an adaptor does
- * while copying out of SplitKKTMatrix::Qxx etc.); rbt_wire_doubles gives the size of one wire record; with_sto must be
- * rbt_wire_with_sto(h) of the schedule in force (1 if any grid point has sto or sto_next set). */
+/* The same call with the linearization records in the host wire format of rbt_stage_layout.h: per grid point only what a
+ * robotoc linearisation of that grid point holds -- packed upper triangles of the symmetric blocks M, Qff, Qxx, Quu; contact
+ * blocks sized by the active contact dimension nf and the active contacts (as the reference's own dimf-sized containers); no
+ * padding; no Qqf (zero until the friction-cone condensing fills it); the STO section only when the schedule has a
+ * switching-time stage; Qxx, lx and one SE(3) block on the terminal grid point.  ANYmal trot N=40: 45 % fewer bytes over PCIe
+ * than the dense records.  One OCP's wire records are concatenated in grid order: wire_host is [batch][rbt_wire_doubles].
+ * `lin_host_switching` = classic records, of which only the switching-constraint sections of the stages that carry one are
+ * read (NULL if the schedule has none).  rbt_pack_wire is the host-side packing helper (what an adaptor does while copying
+ * out of SplitKKTMatrix::Qxx etc.; rbt_wire_layout_get gives the segment table of grid point i for an adaptor that fills the
+ * wire records directly); `ctrl` / `n_grid` must be the schedule in force (rbt_set_schedule). */
 int rbt_iteration_host_wire(rbt_handle* h, const double* wire_host, const double* lin_host_switching, const double* con_host,
                             const double* sol_host, const double* dx0_host, double* sol_out, double* con_out,
                             double* steps_out, void* stream);
@@ -220,9 +223,10 @@ int rbt_iteration_host_wire(rbt_handle* h, const double* wire_host, const double
  * 2-D copies of ~1 KB rows cost the copy engine as much per row as 4 KB of payload) and the step sizes. */
 int rbt_iteration_host_resident(rbt_handle* h, const double* wire_host, const double* lin_host_switching, const double* res_host,
                                 const double* dx0_host, double* sol_out, double* slack_dual_out, double* steps_out, void* stream);
-int rbt_wire_with_sto(rbt_handle* h);
-int rbt_wire_doubles(const rbt_stage_dims* sdims, int with_sto);
-int rbt_pack_wire(const rbt_stage_dims* sdims, int with_sto, const double* lin_host, double* wire_host, long long n_records);
+int rbt_wire_doubles(const rbt_stage_dims* sdims, const rbt_stage_ctrl* ctrl, int n_grid);   /* doubles per OCP */
+int rbt_wire_layout_get(const rbt_stage_dims* sdims, const rbt_stage_ctrl* ctrl, int n_grid, int i, rbt_wire_layout* out);
+int rbt_pack_wire(const rbt_stage_dims* sdims, const rbt_stage_ctrl* ctrl, int n_grid, const double* lin_host, double* wire_host,
+                  long long n_ocps);
 
 /* Multi-GPU: OCP instances are independent, so a batch is sharded over ranks without any data-path collective;
  * the one exchange is the Newton step of every OCP on every rank, e.g. for a host that advances all trajectories.

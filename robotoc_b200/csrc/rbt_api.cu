@@ -83,7 +83,9 @@ struct rbt_handle {
   double* d_wire = nullptr;  // packed host wire records (rbt_iteration_host_wire), allocated on first use
   double* d_res_stage = nullptr;  // rbt_iteration_host_resident: compact residuals in, compact slack|dual out
   double* d_sd_stage = nullptr;
-  rbt_wire_layout W;
+  std::vector<rbt_wire_layout> Wv;   // per grid point (the wire record of a grid point depends on its control word)
+  rbt_wire_layout* d_W = nullptr;
+  long long w_ocp = 0;               // doubles of one OCP's concatenated wire records
   bool attr_bwd = false, attr_fwd = false, attr_cond = false;  // MaxDynamicSharedMemorySize set on THIS handle's device
   cudaEvent_t ev_condense_mid = nullptr;  // caller-owned event recorded between the two kernels of rbt_condense (timing)
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
@@ -206,6 +208,7 @@ static int check_contacts(rbt_handle* h, const rbt_stage_ctrl* ctrl, int n_grid)
 int rbt_destroy(rbt_handle* h) {
   if (h) {
     cudaFree(h->d_wire);
+    cudaFree(h->d_W);
     cudaFree(h->d_res_stage);
     cudaFree(h->d_sd_stage);
     if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
@@ -355,10 +358,28 @@ static long long stage_xfer(rbt_handle* h, int which, bool up, const double* hos
                             cudaStream_t st, bool do_copy, int* rc_out);
 enum { RBT_XFER_WIRE = 100, RBT_XFER_SWITCHING = 101, RBT_XFER_RES = 102, RBT_XFER_SD = 103 };
 // the STO section of the linearization records is read on switching-time stages only (riccati_backward.cuh: cs.sto)
-static int schedule_has_sto(const rbt_handle* h) {
-  for (const auto& c : h->ctrl)
-    if (c.sto || c.sto_next) return 1;
+static int ctrl_has_sto(const rbt_stage_ctrl* ctrl, int n_grid) {
+  for (int i = 0; i < n_grid; ++i)
+    if (ctrl[i].sto || ctrl[i].sto_next) return 1;
   return 0;
+}
+// wire layouts of all grid points of a schedule; returns the OCP stride in doubles
+static long long make_wire_layouts(const rbt_stage_layout& S, const rbt_stage_ctrl* ctrl, int n_grid, std::vector<rbt_wire_layout>& out) {
+  const int with_sto = ctrl_has_sto(ctrl, n_grid);
+  out.resize(n_grid);
+  long long off = 0;
+  for (int i = 0; i < n_grid; ++i) {
+    rbt_make_wire_layout(&S, &ctrl[i], with_sto, &out[i]);
+    out[i].ocp_off = int(off);
+    off += out[i].w_doubles;
+  }
+  return off;
+}
+static int ensure_wire_layouts(rbt_handle* h) {  // (re)built on every call: n_grid small structs + one H2D copy
+  h->w_ocp = make_wire_layouts(h->S, h->ctrl.data(), h->n_grid, h->Wv);
+  if (!h->d_W) RBT_CUDA(h, cudaMalloc(&h->d_W, size_t(h->n_grid_max) * sizeof(rbt_wire_layout)));
+  RBT_CUDA(h, cudaMemcpy(h->d_W, h->Wv.data(), size_t(h->n_grid) * sizeof(rbt_wire_layout), cudaMemcpyHostToDevice));
+  return RBT_OK;
 }
 
 // KKT upload plan: one strided copy of the core section [Fxx|Fvu|Fx|lx|lu|Qxx|Qxu|Quu] of every record (record padding and
@@ -941,7 +962,7 @@ static long long stage_xfer(rbt_handle* h, int which, bool up, const double* hos
     if (e != cudaSuccess) *rc_out = RBT_ERR_CUDA;
   };
   if (which == RBT_XFER_WIRE) {  // packed wire records: contiguous
-    copy2d(h->d_wire, host_c, host_m, go * h->W.w_stride, h->W.w_stride, h->W.w_stride, 1, rows);
+    copy2d(h->d_wire, host_c, host_m, size_t(b0) * h->w_ocp, h->w_ocp, h->w_ocp, 1, nb);
   } else if (which == RBT_XFER_SWITCHING) {  // only the switching-constraint sections of the classic record
     const size_t base = go * S.l_stride;
     for (int i = 0; i < h->n_grid; ++i)
@@ -978,7 +999,7 @@ int rbt_iteration_host_bytes(rbt_handle* h, int wire, long long* h2d, long long*
   if (!h || !h->stage_ready || h->n_grid == 0) return RBT_ERR_STATE;
   int rc = RBT_OK;
   long long up = 0, down = 0;
-  rbt_make_wire_layout(&h->S, schedule_has_sto(h), &h->W);
+  h->w_ocp = make_wire_layouts(h->S, h->ctrl.data(), h->n_grid, h->Wv);
   if (wire == 2) {  // rbt_iteration_host_resident: wire records + residuals + dx0 up
     up += stage_xfer(h, RBT_XFER_WIRE, true, nullptr, nullptr, 0, h->batch, nullptr, false, &rc);
     up += stage_xfer(h, RBT_XFER_SWITCHING, true, nullptr, nullptr, 0, h->batch, nullptr, false, &rc);
@@ -1011,17 +1032,20 @@ static int iteration_host_impl(rbt_handle* h, const double* wire_host, const dou
   if (!res_host && (!con_host || !sol_host)) return RBT_ERR_ARG;
   RBT_STAGE_CHECK(h, "rbt_iteration_host");
   if (wire_host) {
-    rbt_make_wire_layout(&h->S, schedule_has_sto(h), &h->W);
+    int rcw = ensure_wire_layouts(h);
+    if (rcw != RBT_OK) return rcw;
     bool sw = false;
     for (int i = 0; i < h->n_grid; ++i) sw = sw || (h->ctrl[i].ns > 0 && h->ctrl[i].type != RBT_IMPACT);
     if (sw && !lin_host) {
       h->err = "[rbt_iteration_host_wire] invalid argument: the schedule has switching-constraint stages, their sections come from lin_host_switching";
       return RBT_ERR_ARG;
     }
-    if (!h->d_wire) {
+    if (!h->d_wire) {  // sized for the largest possible record at every grid point
       rbt_wire_layout wmax;
-      rbt_make_wire_layout(&h->S, 1, &wmax);
-      RBT_CUDA(h, cudaMalloc(&h->d_wire, size_t(h->batch) * h->n_grid_max * wmax.w_stride * 8));
+      rbt_stage_ctrl cmax = {};
+      cmax.type = RBT_INTERMEDIATE; cmax.nf = h->S.nfm; cmax.contact_mask = (1 << h->S.ncon) - 1;
+      rbt_make_wire_layout(&h->S, &cmax, 1, &wmax);
+      RBT_CUDA(h, cudaMalloc(&h->d_wire, size_t(h->batch) * h->n_grid_max * wmax.w_doubles * 8));
     }
     if (res_host && !h->d_res_stage) {
       RBT_CUDA(h, cudaMalloc(&h->d_res_stage, size_t(h->batch) * h->n_grid_max * h->S.ncp * 8));
@@ -1069,9 +1093,11 @@ static int iteration_host_impl(rbt_handle* h, const double* wire_host, const dou
     h->cnb = nb;
     if (wire_host) {  // expand the packed records of this chunk into the linearization records
       rbt::WireParams wp;
-      wp.W = h->W;
+      wp.W = h->d_W;
+      wp.n_grid = h->n_grid;
+      wp.ocp_stride = h->w_ocp;
       wp.l_stride = h->S.l_stride;
-      wp.wire = h->d_wire + size_t(b0) * h->n_grid * h->W.w_stride;
+      wp.wire = h->d_wire + size_t(b0) * h->w_ocp;
       wp.lin = h->d_lin + size_t(b0) * h->n_grid * h->S.l_stride;
       wp.res = res_host ? h->d_res_stage + size_t(b0) * h->n_grid * h->S.ncp : nullptr;
       wp.con = h->d_con + size_t(b0) * h->n_grid * h->S.c_stride;
@@ -1128,27 +1154,34 @@ int rbt_iteration_host_resident(rbt_handle* h, const double* wire_host, const do
                              stream);
 }
 
-int rbt_wire_with_sto(rbt_handle* h) {
-  if (!h || h->n_grid == 0) return -1;
-  return schedule_has_sto(h);
+int rbt_wire_doubles(const rbt_stage_dims* sdims, const rbt_stage_ctrl* ctrl, int n_grid) {
+  if (!sdims || !ctrl || n_grid <= 0) return -1;
+  rbt_stage_layout S;
+  rbt_make_stage_layout(sdims, &S);
+  std::vector<rbt_wire_layout> W;
+  return int(make_wire_layouts(S, ctrl, n_grid, W));
 }
 
-int rbt_wire_doubles(const rbt_stage_dims* sdims, int with_sto) {
-  if (!sdims) return -1;
+int rbt_wire_layout_get(const rbt_stage_dims* sdims, const rbt_stage_ctrl* ctrl, int n_grid, int i, rbt_wire_layout* out) {
+  if (!sdims || !ctrl || !out || i < 0 || i >= n_grid) return RBT_ERR_ARG;
   rbt_stage_layout S;
-  rbt_wire_layout W;
   rbt_make_stage_layout(sdims, &S);
-  rbt_make_wire_layout(&S, with_sto, &W);
-  return W.w_stride;
+  std::vector<rbt_wire_layout> W;
+  make_wire_layouts(S, ctrl, n_grid, W);
+  *out = W[i];
+  return RBT_OK;
 }
 
-int rbt_pack_wire(const rbt_stage_dims* sdims, int with_sto, const double* lin_host, double* wire_host, long long n_records) {
-  if (!sdims || !lin_host || !wire_host || n_records < 0) return RBT_ERR_ARG;
+int rbt_pack_wire(const rbt_stage_dims* sdims, const rbt_stage_ctrl* ctrl, int n_grid, const double* lin_host, double* wire_host,
+                  long long n_ocps) {
+  if (!sdims || !ctrl || n_grid <= 0 || !lin_host || !wire_host || n_ocps < 0) return RBT_ERR_ARG;
   rbt_stage_layout S;
-  rbt_wire_layout W;
   rbt_make_stage_layout(sdims, &S);
-  rbt_make_wire_layout(&S, with_sto, &W);
-  for (long long r = 0; r < n_records; ++r) rbt_pack_wire_record(&W, lin_host + r * S.l_stride, wire_host + r * W.w_stride);
+  std::vector<rbt_wire_layout> W;
+  const long long w_ocp = make_wire_layouts(S, ctrl, n_grid, W);
+  for (long long b = 0; b < n_ocps; ++b)
+    for (int i = 0; i < n_grid; ++i)
+      rbt_pack_wire_record(&W[i], lin_host + (b * n_grid + i) * S.l_stride, wire_host + b * w_ocp + W[i].ocp_off);
   return RBT_OK;
 }
 

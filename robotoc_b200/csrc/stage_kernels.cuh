@@ -836,8 +836,9 @@ __global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS, RBT_COND_MIN_C
 // stage, coalesced reads of the 24 KB wire record, coalesced writes of the dense sections; the symmetric blocks are gathered
 // from the packed triangle.  Only used by the PCIe-facing rbt_iteration_host_wire / _resident paths.
 struct WireParams {
-  rbt_wire_layout W;
-  int l_stride;
+  const rbt_wire_layout* W;  // [n_grid] per-grid-point layouts (device memory)
+  int n_grid, l_stride;
+  long long ocp_stride;      // doubles of one OCP's concatenated wire records
   const double* wire;
   double* lin;
   // resident-state path: compact PDIPM residuals [record][ncp] -> the c_res section of the PDIPM records (res == nullptr: none)
@@ -847,23 +848,31 @@ struct WireParams {
 };
 
 __global__ void __launch_bounds__(128) unpack_wire_kernel(const WireParams p) {
-  const double* wire = p.wire + size_t(blockIdx.x) * p.W.w_stride;
+  const int i = int(blockIdx.x % p.n_grid);
+  const size_t b = blockIdx.x / p.n_grid;
+  const rbt_wire_layout& W = p.W[i];
+  const double* wire = p.wire + b * size_t(p.ocp_stride) + W.ocp_off;
   double* lin = p.lin + size_t(blockIdx.x) * p.l_stride;
-  for (int k = 0; k < p.W.nseg; ++k) {
-    const rbt_wire_seg g = p.W.seg[k];
+  const int nseg = W.nseg;
+  for (int k = 0; k < nseg; ++k) {
+    const rbt_wire_seg g = W.seg[k];
     const double* src = wire + g.wire_off;
     double* dst = lin + g.lin_off;
     if (!g.sym) {
-      for (int e = threadIdx.x; e < g.n; e += 128) dst[e] = src[e];
+      if (g.ld == g.rows) {
+        for (int e = threadIdx.x; e < g.rows * g.cols; e += 128) dst[e] = src[e];
+      } else {
+        for (int e = threadIdx.x; e < g.rows * g.cols; e += 128) dst[(e % g.rows) + (e / g.rows) * g.ld] = src[e];
+      }
     } else {
-      for (int e = threadIdx.x; e < g.n * g.n; e += 128) {
-        const int i = e % g.n, j = e / g.n;
-        dst[e] = (i <= j) ? src[j * (j + 1) / 2 + i] : src[i * (i + 1) / 2 + j];
+      for (int e = threadIdx.x; e < g.rows * g.rows; e += 128) {
+        const int r = e % g.rows, c = e / g.rows;
+        dst[r + c * g.ld] = (r <= c) ? src[c * (c + 1) / 2 + r] : src[r * (r + 1) / 2 + c];
       }
     }
   }
-  for (int k = 0; k < p.W.nzero; ++k)
-    for (int e = threadIdx.x; e < p.W.zero[k].n; e += 128) lin[p.W.zero[k].lin_off + e] = 0.0;
+  for (int k = 0; k < W.nzero; ++k)
+    for (int e = threadIdx.x; e < W.zero[k].n; e += 128) lin[W.zero[k].lin_off + e] = 0.0;
   if (p.res) {
     const double* r = p.res + size_t(blockIdx.x) * p.ncp;
     double* c = p.con + size_t(blockIdx.x) * p.c_stride + p.c_res;

@@ -135,15 +135,15 @@ class DirectMultipleShooting:
         return h2d.value, d2h.value
 
     def pack_wire(self, lin):
-        """Linearization records -> host wire records (packed upper triangles of M, Qff, Qxx, Quu; no Qqf; the STO section
-        only if the schedule in force has a switching-time stage; include/rbt_stage_layout.h)."""
+        """Linearization records [batch, n_grid, l_stride] -> host wire records [batch, wire doubles per OCP] of the schedule in
+        force (include/rbt_stage_layout.h: packed symmetric blocks, contact blocks sized by the active contacts, no Qqf, ...)."""
         csd = self.sdims.c()
-        with_sto = int(self._lib.rbt_wire_with_sto(self._h))
-        if with_sto < 0:
+        ctrl, n_grid = self.rr._ctrl, self.rr.n_grid
+        if n_grid == 0:
             raise RuntimeError("[DirectMultipleShooting] pack_wire: set the time discretization first")
-        w = int(self._lib.rbt_wire_doubles(ctypes.byref(csd), with_sto))
-        out = np.zeros(lin.shape[:-1] + (w,))
-        _check(self._lib.rbt_pack_wire(ctypes.byref(csd), with_sto, _vp(lin), _vp(out), int(np.prod(lin.shape[:-1]))), self.rr._err,
+        w = int(self._lib.rbt_wire_doubles(ctypes.byref(csd), ctrl, n_grid))
+        out = np.zeros((lin.shape[0], w))
+        _check(self._lib.rbt_pack_wire(ctypes.byref(csd), ctrl, n_grid, _vp(lin), _vp(out), lin.shape[0]), self.rr._err,
                "DirectMultipleShooting")
         return out
 

@@ -114,55 +114,78 @@ def test_shard_range_partitions(batch, world):
 
 def test_wire_format_pack_is_documented_packed_upper_storage():
     """rbt_pack_wire (host helper of the C ABI) against an independent numpy restatement of the format in
-    include/rbt_stage_layout.h: dense sections copied, M / Qff / Qxx / Quu as column-major packed upper triangles, no Qqf,
-    the STO section only when asked for."""
+    include/rbt_stage_layout.h: per grid point M / Qff / Qxx / Quu as column-major packed upper triangles, contact blocks sized
+    by the active contact dimension, cone Jacobians of the active contacts only, no Qqf, the STO section only on schedules with
+    a switching-time stage, three blocks on the terminal grid point."""
     import ctypes
     from robotoc_b200 import ANYMAL, StageDims, StageLayout, anymal_constraint_table
     from robotoc_b200._lib import lib
+    from robotoc_b200.grid import TERMINAL
     from synth import make_stage_inputs
     from helpers import small_event_schedule
     L = lib()
     tab = anymal_constraint_table()
     sd = StageDims(ANYMAL, nf_max=12, n_contacts=tab.n_contacts, n_box=tab.n_box)
     S = StageLayout(sd)
-    td, ev, ctrl = small_event_schedule(False)
-    lin, con, sol, dx0 = make_stage_inputs(sd, S, ctrl, 2, seed=4)
     csd = sd.c()
-    cone = S.l_dgdf + 60 - S.l_dgdq
-    for with_sto, wexp in ((1, 3104), (0, 2986)):
-        w = L.rbt_wire_doubles(ctypes.byref(csd), with_sto)
-        assert w == wexp
-        wire = np.zeros(lin.shape[:-1] + (w,))
-        assert L.rbt_pack_wire(ctypes.byref(csd), with_sto, lin.ctypes.data_as(ctypes.c_void_p),
-                               wire.ctypes.data_as(ctypes.c_void_p), lin.shape[0] * lin.shape[1]) == 0
-        segs = [(S.l_M, 18, True), (S.l_J, S.l_Qff - S.l_J, False), (S.l_Qff, 12, True), (S.l_Qxx, 36, True),
-                (S.l_Quu, 12, True), (S.l_lx, S.l_Phix - S.l_lx, False), (S.l_dgdq, cone, False)]
-        if with_sto:
-            segs.append((S.l_ha, S.l_dgdq - S.l_ha, False))
-        rec, wrec = lin[1, 3], wire[1, 3]
-        back = np.zeros_like(rec)
+    nv, nx, nu, nfm, nvfm = 18, 36, 12, 12, 30
+    up2 = lambda n: n + (n & 1)  # noqa: E731
+    for sto in (False, True):
+        td, ev, ctrl = small_event_schedule(sto)
+        n_grid = len(ctrl)
+        lin, con, sol, dx0 = make_stage_inputs(sd, S, ctrl, 2, seed=4)
+        with_sto = any(c.sto or c.sto_next for c in ctrl)
+        assert with_sto == sto
+        w = L.rbt_wire_doubles(ctypes.byref(csd), ctrl, n_grid)
+        wire = np.zeros((2, w))
+        assert L.rbt_pack_wire(ctypes.byref(csd), ctrl, n_grid, lin.ctypes.data_as(ctypes.c_void_p),
+                               wire.ctypes.data_as(ctypes.c_void_p), 2) == 0
         o = 0
-        for off, n, sym in segs:
-            if not sym:
-                back[off:off + n] = wrec[o:o + n]
-                o += n + (n & 1)
+        for i, c in enumerate(ctrl):
+            rec, back = lin[1, i], np.zeros(S.l_stride)
+            nf = c.nf
+            if c.type == TERMINAL:
+                segs = [("sym", S.l_Qxx, nx, nx), ("d", S.l_lx, nx, 1, nx), ("d", S.l_se3 + 36, 36, 1, 36)]
             else:
-                a = np.zeros((n, n))
-                for j in range(n):
-                    for i in range(j + 1):
-                        a[i, j] = a[j, i] = wrec[o + j * (j + 1) // 2 + i]
-                back[off:off + n * n] = a.T.reshape(-1)
-                o += n * (n + 1) // 2 + ((n * (n + 1) // 2) & 1)
+                segs = [("sym", S.l_M, nv, nv)]
+                if nf:
+                    segs.append(("d", S.l_J, nf, nv, nfm))
+                segs += [("d", S.l_D, nv + nf, nx, nvfm), ("d", S.l_IDC, nv + nf, 1, nv + nf), ("d", S.l_Qaa, nv, 1, nv)]
+                if nf:
+                    segs.append(("sym", S.l_Qff, nf, nfm))
+                segs += [("sym", S.l_Qxx, nx, nx), ("sym", S.l_Quu, nu, nu), ("d", S.l_lx, S.l_Phix - S.l_lx, 1, S.l_Phix - S.l_lx)]
+                for ci in range(4):
+                    if (c.contact_mask >> ci) & 1:
+                        segs += [("d", S.l_dgdq + ci * 90, 90, 1, 90), ("d", S.l_dgdf + ci * 15, 15, 1, 15)]
+                if with_sto:
+                    segs.append(("d", S.l_ha, S.l_dgdq - S.l_ha, 1, S.l_dgdq - S.l_ha))
+            keep = np.zeros(S.l_stride, bool)
+            want = rec.copy()
+            for sg in segs:
+                if sg[0] == "d":
+                    _, off, rows, cols, ld = sg
+                    blk = wire[1, o:o + rows * cols].reshape(cols, rows)
+                    for j in range(cols):
+                        back[off + j * ld:off + j * ld + rows] = blk[j]
+                        keep[off + j * ld:off + j * ld + rows] = True
+                    o += up2(rows * cols)
+                else:
+                    _, off, n, ld = sg
+                    a = np.zeros((n, n))
+                    for j in range(n):
+                        for r in range(j + 1):
+                            a[r, j] = a[j, r] = wire[1, o + j * (j + 1) // 2 + r]
+                    for j in range(n):
+                        back[off + j * ld:off + j * ld + n] = a[:, j]
+                        keep[off + j * ld:off + j * ld + n] = True
+                        col = want[off + j * ld:off + j * ld + n]
+                        for r in range(j + 1, n):           # upper triangle authoritative
+                            col[r] = rec[off + r * ld + j]
+                    o += up2(n * (n + 1) // 2)
+            np.testing.assert_array_equal(back[keep], want[keep])
+            assert not keep[S.l_Qqf:S.l_Qxx].any() and not keep[S.l_Phix:S.l_ha].any()
         assert o == w
-        keep = np.ones(S.l_stride, bool)
-        keep[S.l_Phix:S.l_ha] = False            # the switching section is not part of the wire record
-        keep[S.l_dgdf + 60:] = False             # nor is the record padding
-        keep[S.l_Qqf:S.l_Qxx] = False            # nor Qqf (zero at this point of the reference's iteration)
-        if not with_sto:
-            keep[S.l_ha:S.l_dgdq] = False
-        for off, n in ((S.l_M, 18), (S.l_Qff, 12), (S.l_Qxx, 36), (S.l_Quu, 12)):  # packed blocks: upper triangle authoritative
-            blk = rec[off:off + n * n].reshape(n, n).T
-            blk = np.triu(blk) + np.triu(blk, 1).T
-            rec = rec.copy()
-            rec[off:off + n * n] = blk.T.reshape(-1)
-        np.testing.assert_array_equal(back[keep], rec[keep])
+        if not sto:
+            full = 3104 - 118  # the record of a 4-contact intermediate grid point without the STO section
+            n4 = sum(1 for c in ctrl if c.type != TERMINAL and c.nf == 12)
+            assert w < full * n_grid and (n4 == 0 or w > 0)
