@@ -67,14 +67,16 @@ def build_problem(batch, seed):
 def build_iteration_problem(batch, seed, getter=None, kgetter=None):
     from helpers import trot_schedule
     from robotoc_b200 import ANYMAL, Layout, StageDims, StageLayout, anymal_constraint_table
-    from synth import make_stage_inputs, symmetrize_lin
+    from synth import make_stage_inputs, robotoc_cost_structure
     table = anymal_constraint_table()
     sd = StageDims(ANYMAL, nf_max=12, n_contacts=table.n_contacts, n_box=table.n_box)
     S = StageLayout(sd, getter=getter)
     K = Layout(ANYMAL, getter=kgetter)
     td, ev, ctrl = trot_schedule(N_HORIZON)
     lin, con, sol, dx0 = make_stage_inputs(sd, S, ctrl, batch, seed)
-    lin = symmetrize_lin(S, lin)  # inertia matrix / cost Hessians exactly symmetric, as the reference's containers hold them
+    # inertia matrix / cost Hessians exactly symmetric and structured as robotoc's cost components produce them (Qqq dense; Qvv,
+    # Quu, Qff diagonal; Qqv = Qqf = 0), as the reference's containers hold them when the hot path starts
+    lin = robotoc_cost_structure(S, lin)
     return dict(dims=ANYMAL, sd=sd, S=S, K=K, table=table, ctrl=ctrl, lin=lin, con=con, sol=sol, dx0=dx0)
 
 
@@ -488,6 +490,7 @@ def main():
 
     # the host adaptor's output format: packed upper triangles of the symmetric blocks (include/rbt_stage_layout.h), made
     # once outside the timed region -- it is what the host side hands over, like the records themselves
+    dms.setWireCostStructure(True)
     wire_p = pin(dms.pack_wire(lin))
     e2e_mode = os.environ.get("RBT_E2E_MODE", "resident")  # resident | wire | dense
     use_wire = e2e_mode != "dense"
@@ -553,7 +556,8 @@ def main():
             "e2e": {"value": world * args.batch * args.e2e_steps / (e2e_ms * 1e-3), "unit": "OCP-iterations/s",
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": args.e2e_steps,
                     "api": {"resident": "rbt_iteration_host_resident (pinned host buffers: wire linearisation records -- packed symmetric "
-                                        "blocks, contact blocks sized by the active contacts -- PDIPM residuals, dx0 in; solution, "
+                                        "blocks, contact blocks sized by the active contacts, cost Hessians as robotoc's cost components produce "
+                                        "them (Qqq dense; Qvv, Quu, Qff diagonal) -- PDIPM residuals, dx0 in; solution, "
                                         "slack|dual, step sizes out; solver state resident on the device; 8-chunk "
                                         "upload/compute/download pipeline)",
                             "wire": "rbt_iteration_host_wire (as resident, plus PDIPM slack|dual and the solution uploaded every step)",

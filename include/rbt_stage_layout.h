@@ -165,33 +165,56 @@ static inline RBT_HD void rbt_make_stage_layout(const rbt_stage_dims* d, rbt_sta
  *    (src/constraints/friction_cone.cpp:219 is the only writer; cost_function.cpp:194 only scales it) -- the device zero-fills it;
  *  - the STO section [ha | hf | hx | hu | fx | {h, Qtt}] only if the schedule has a switching-time stage (with_sto; the
  *    kernels read it on such stages only) -- otherwise the device zero-fills it;
+ *  - cost_structure RBT_COST_ROBOTOC: the cost Hessians as every cost component robotoc ships produces them -- Qqq dense
+ *    (packed), Qvv / Quu / Qff DIAGONAL, Qqv = 0 (src/cost/configuration_space_cost.cpp:308-322, task_space_*_cost.cpp, com_cost.cpp
+ *    and local_contact_force_cost.cpp:130 are the only writers; nothing writes Qqv or an off-diagonal of Qvv / Quu / Qff before
+ *    the condensing) -- RBT_COST_GENERAL sends Qxx, Quu, Qff as full packed triangles (user-defined cost components);
  *  - a Terminal grid point sends Qxx, lx and the Fqq_prev block only (terminal_stage.cpp:94-106);
  *  - neither padding nor the switching-constraint section (sent separately, only for stages that carry one).
  * One OCP's wire records are concatenated in grid order (rbt_wire_layout::ocp_off = offset of the grid point inside the OCP's
  * block; the OCP stride is the sum).  A host adaptor fills them straight from the reference's Eigen members; the device
  * expands them back into the rbt_stage_layout records (inactive rows / contacts of the device record are never read). */
 typedef struct rbt_wire_seg { int lin_off, wire_off, rows, cols, ld, sym; } rbt_wire_seg;
-  /* sym: rows x rows packed upper triangle -> dense with leading dimension ld ; else rows x cols dense (ld rows on the wire) */
-typedef struct rbt_wire_zero { int lin_off, n; } rbt_wire_zero;             /* sections of the record the device zero-fills */
+  /* sym 0: rows x cols dense (ld rows on the wire) -> leading dimension ld ; 1: rows x rows packed upper triangle -> dense, ld ;
+     2: the diagonal of a rows x rows block (rows doubles on the wire) -> element (k,k), ld */
+typedef struct rbt_wire_zero { int lin_off, n; } rbt_wire_zero;   /* sections of the record the device zero-fills (first) */
+enum { RBT_COST_GENERAL = 0, RBT_COST_ROBOTOC = 1 };
 #define RBT_WIRE_MAX_SEGS 20
+#define RBT_WIRE_MAX_ZERO 5
 typedef struct rbt_wire_layout {
   int nseg, nzero, w_doubles, ocp_off;
   rbt_wire_seg seg[RBT_WIRE_MAX_SEGS];
-  rbt_wire_zero zero[2];
+  rbt_wire_zero zero[RBT_WIRE_MAX_ZERO];
 } rbt_wire_layout;
 
 static inline RBT_HD void rbt_wire_add_(rbt_wire_layout* W, int lin_off, int rows, int cols, int ld, int sym) {
   rbt_wire_seg* g = &W->seg[W->nseg++];
   g->lin_off = lin_off; g->wire_off = W->w_doubles; g->rows = rows; g->cols = cols; g->ld = ld; g->sym = sym;
-  W->w_doubles += rbt_up2(sym ? rows * (rows + 1) / 2 : rows * cols);
+  W->w_doubles += rbt_up2(sym == 1 ? rows * (rows + 1) / 2 : (sym == 2 ? rows : rows * cols));
+}
+static inline RBT_HD void rbt_wire_zero_(rbt_wire_layout* W, int lin_off, int n) {
+  W->zero[W->nzero].lin_off = lin_off; W->zero[W->nzero].n = n; W->nzero++;
+}
+/* Qxx of a grid point: full packed triangle, or Qqq packed + diag(Qvv) with the rest zero-filled */
+static inline RBT_HD void rbt_wire_add_qxx_(const rbt_stage_layout* L, int cost_structure, rbt_wire_layout* W) {
+  const int nv = L->nv, nx = L->nx;
+  if (cost_structure == RBT_COST_ROBOTOC) {
+    rbt_wire_zero_(W, L->l_Qxx, nx * nx);
+    rbt_wire_add_(W, L->l_Qxx, nv, nv, nx, 1);
+    rbt_wire_add_(W, L->l_Qxx + nv * nx + nv, nv, nv, nx, 2);
+  } else {
+    rbt_wire_add_(W, L->l_Qxx, nx, nx, nx, 1);
+  }
 }
 
-static inline RBT_HD void rbt_make_wire_layout(const rbt_stage_layout* L, const rbt_stage_ctrl* c, int with_sto, rbt_wire_layout* W) {
+static inline RBT_HD void rbt_make_wire_layout(const rbt_stage_layout* L, const rbt_stage_ctrl* c, int with_sto, int cost_structure,
+                                               rbt_wire_layout* W) {
   const int nv = L->nv, nx = L->nx, nf = c->nf, nvf = nv + nf;
+  const int dc = (cost_structure == RBT_COST_ROBOTOC);
   int ci;
   W->nseg = 0; W->nzero = 0; W->w_doubles = 0; W->ocp_off = 0;
   if (c->type == RBT_TERMINAL) {
-    rbt_wire_add_(W, L->l_Qxx, nx, nx, nx, 1);
+    rbt_wire_add_qxx_(L, cost_structure, W);
     rbt_wire_add_(W, L->l_lx, nx, 1, nx, 0);
     rbt_wire_add_(W, L->l_se3 + 36, 36, 1, 36, 0);
     return;
@@ -201,9 +224,11 @@ static inline RBT_HD void rbt_make_wire_layout(const rbt_stage_layout* L, const 
   rbt_wire_add_(W, L->l_D, nvf, nx, L->nvf, 0);
   rbt_wire_add_(W, L->l_IDC, nvf, 1, nvf, 0);
   rbt_wire_add_(W, L->l_Qaa, nv, 1, nv, 0);
-  if (nf > 0) rbt_wire_add_(W, L->l_Qff, nf, nf, L->nfm, 1);
-  rbt_wire_add_(W, L->l_Qxx, nx, nx, nx, 1);
-  rbt_wire_add_(W, L->l_Quu, L->nu, L->nu, L->nu, 1);
+  if (dc) rbt_wire_zero_(W, L->l_Qff, L->nfm * L->nfm);
+  if (nf > 0) rbt_wire_add_(W, L->l_Qff, nf, nf, L->nfm, dc ? 2 : 1);
+  rbt_wire_add_qxx_(L, cost_structure, W);
+  if (dc) rbt_wire_zero_(W, L->l_Quu, L->nu * L->nu);
+  rbt_wire_add_(W, L->l_Quu, L->nu, L->nu, L->nu, dc ? 2 : 1);
   rbt_wire_add_(W, L->l_lx, L->l_Phix - L->l_lx, 1, L->l_Phix - L->l_lx, 0);   /* lx | la | lf | lu | Fx | lup | SE(3) blocks */
   for (ci = 0; ci < L->ncon; ++ci)
     if ((c->contact_mask >> ci) & 1) {
@@ -211,9 +236,8 @@ static inline RBT_HD void rbt_make_wire_layout(const rbt_stage_layout* L, const 
       rbt_wire_add_(W, L->l_dgdf + ci * 15, 15, 1, 15, 0);
     }
   if (with_sto) rbt_wire_add_(W, L->l_ha, L->l_dgdq - L->l_ha, 1, L->l_dgdq - L->l_ha, 0);
-  W->zero[0].lin_off = L->l_Qqf; W->zero[0].n = L->l_Qxx - L->l_Qqf;
-  W->zero[1].lin_off = L->l_ha; W->zero[1].n = L->l_dgdq - L->l_ha;
-  W->nzero = with_sto ? 1 : 2;
+  rbt_wire_zero_(W, L->l_Qqf, L->l_Qxx - L->l_Qqf);
+  if (!with_sto) rbt_wire_zero_(W, L->l_ha, L->l_dgdq - L->l_ha);
 }
 
 /* one record: rbt_stage_layout linearization record -> wire record (reads the upper triangles) */
@@ -228,6 +252,7 @@ static inline void rbt_pack_wire_record(const rbt_wire_layout* W, const double* 
         for (i = 0; i < g->rows; ++i) dst[i + j * g->rows] = src[i + j * g->ld];
       continue;
     }
+    if (g->sym == 2) { for (i = 0; i < g->rows; ++i) dst[i] = src[i * (g->ld + 1)]; continue; }
     for (j = 0; j < g->rows; ++j)
       for (i = 0; i <= j; ++i) dst[j * (j + 1) / 2 + i] = src[i + j * g->ld];
   }
@@ -235,6 +260,8 @@ static inline void rbt_pack_wire_record(const rbt_wire_layout* W, const double* 
 /* wire record -> linearization record (what the device kernel does; used by the CPU tests) */
 static inline void rbt_unpack_wire_record(const rbt_wire_layout* W, const double* wire, double* lin) {
   int k, i, j;
+  for (k = 0; k < W->nzero; ++k)
+    for (i = 0; i < W->zero[k].n; ++i) lin[W->zero[k].lin_off + i] = 0.0;
   for (k = 0; k < W->nseg; ++k) {
     const rbt_wire_seg* g = &W->seg[k];
     const double* src = wire + g->wire_off;
@@ -244,11 +271,10 @@ static inline void rbt_unpack_wire_record(const rbt_wire_layout* W, const double
         for (i = 0; i < g->rows; ++i) dst[i + j * g->ld] = src[i + j * g->rows];
       continue;
     }
+    if (g->sym == 2) { for (i = 0; i < g->rows; ++i) dst[i * (g->ld + 1)] = src[i]; continue; }
     for (j = 0; j < g->rows; ++j)
       for (i = 0; i < g->rows; ++i) dst[i + j * g->ld] = (i <= j) ? src[j * (j + 1) / 2 + i] : src[i * (i + 1) / 2 + j];
   }
-  for (k = 0; k < W->nzero; ++k)
-    for (i = 0; i < W->zero[k].n; ++i) lin[W->zero[k].lin_off + i] = 0.0;
 }
 
 #define RBT_STAGE_LAYOUT_FIELDS(X) \

@@ -223,10 +223,17 @@ int rbt_iteration_host_wire(rbt_handle* h, const double* wire_host, const double
  * 2-D copies of ~1 KB rows cost the copy engine as much per row as 4 KB of payload) and the step sizes. */
 int rbt_iteration_host_resident(rbt_handle* h, const double* wire_host, const double* lin_host_switching, const double* res_host,
                                 const double* dx0_host, double* sol_out, double* slack_dual_out, double* steps_out, void* stream);
-int rbt_wire_doubles(const rbt_stage_dims* sdims, const rbt_stage_ctrl* ctrl, int n_grid);   /* doubles per OCP */
-int rbt_wire_layout_get(const rbt_stage_dims* sdims, const rbt_stage_ctrl* ctrl, int n_grid, int i, rbt_wire_layout* out);
-int rbt_pack_wire(const rbt_stage_dims* sdims, const rbt_stage_ctrl* ctrl, int n_grid, const double* lin_host, double* wire_host,
-                  long long n_ocps);
+/* cost_structure (RBT_COST_GENERAL / RBT_COST_ROBOTOC, rbt_stage_layout.h): with RBT_COST_ROBOTOC the wire records carry the
+ * cost Hessians the way every cost component robotoc ships produces them -- Qqq dense, Qvv / Quu / Qff diagonal, Qqv = 0
+ * (configuration_space_cost.cpp:308-322, task_space_*_cost.cpp, com_cost.cpp, local_contact_force_cost.cpp:130) -- 23 % fewer
+ * bytes again; a problem with user-defined cost components that fill other entries uses RBT_COST_GENERAL (default).
+ * rbt_set_wire_cost_structure tells the handle which of the two the host's wire records are in. */
+int rbt_set_wire_cost_structure(rbt_handle* h, int cost_structure);
+int rbt_wire_doubles(const rbt_stage_dims* sdims, const rbt_stage_ctrl* ctrl, int n_grid, int cost_structure);   /* doubles per OCP */
+int rbt_wire_layout_get(const rbt_stage_dims* sdims, const rbt_stage_ctrl* ctrl, int n_grid, int cost_structure, int i,
+                        rbt_wire_layout* out);
+int rbt_pack_wire(const rbt_stage_dims* sdims, const rbt_stage_ctrl* ctrl, int n_grid, int cost_structure, const double* lin_host,
+                  double* wire_host, long long n_ocps);
 
 /* Multi-GPU: OCP instances are independent, so a batch is sharded over ranks without any data-path collective;
  * the one exchange is the Newton step of every OCP on every rank, e.g. for a host that advances all trajectories.

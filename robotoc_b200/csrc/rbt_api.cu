@@ -86,6 +86,7 @@ struct rbt_handle {
   std::vector<rbt_wire_layout> Wv;   // per grid point (the wire record of a grid point depends on its control word)
   rbt_wire_layout* d_W = nullptr;
   long long w_ocp = 0;               // doubles of one OCP's concatenated wire records
+  int cost_structure = RBT_COST_GENERAL;  // what the host's wire records hold (rbt_set_wire_cost_structure)
   bool attr_bwd = false, attr_fwd = false, attr_cond = false;  // MaxDynamicSharedMemorySize set on THIS handle's device
   cudaEvent_t ev_condense_mid = nullptr;  // caller-owned event recorded between the two kernels of rbt_condense (timing)
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
@@ -364,19 +365,20 @@ static int ctrl_has_sto(const rbt_stage_ctrl* ctrl, int n_grid) {
   return 0;
 }
 // wire layouts of all grid points of a schedule; returns the OCP stride in doubles
-static long long make_wire_layouts(const rbt_stage_layout& S, const rbt_stage_ctrl* ctrl, int n_grid, std::vector<rbt_wire_layout>& out) {
+static long long make_wire_layouts(const rbt_stage_layout& S, const rbt_stage_ctrl* ctrl, int n_grid, int cost_structure,
+                                   std::vector<rbt_wire_layout>& out) {
   const int with_sto = ctrl_has_sto(ctrl, n_grid);
   out.resize(n_grid);
   long long off = 0;
   for (int i = 0; i < n_grid; ++i) {
-    rbt_make_wire_layout(&S, &ctrl[i], with_sto, &out[i]);
+    rbt_make_wire_layout(&S, &ctrl[i], with_sto, cost_structure, &out[i]);
     out[i].ocp_off = int(off);
     off += out[i].w_doubles;
   }
   return off;
 }
 static int ensure_wire_layouts(rbt_handle* h) {  // (re)built on every call: n_grid small structs + one H2D copy
-  h->w_ocp = make_wire_layouts(h->S, h->ctrl.data(), h->n_grid, h->Wv);
+  h->w_ocp = make_wire_layouts(h->S, h->ctrl.data(), h->n_grid, h->cost_structure, h->Wv);
   if (!h->d_W) RBT_CUDA(h, cudaMalloc(&h->d_W, size_t(h->n_grid_max) * sizeof(rbt_wire_layout)));
   RBT_CUDA(h, cudaMemcpy(h->d_W, h->Wv.data(), size_t(h->n_grid) * sizeof(rbt_wire_layout), cudaMemcpyHostToDevice));
   return RBT_OK;
@@ -999,7 +1001,7 @@ int rbt_iteration_host_bytes(rbt_handle* h, int wire, long long* h2d, long long*
   if (!h || !h->stage_ready || h->n_grid == 0) return RBT_ERR_STATE;
   int rc = RBT_OK;
   long long up = 0, down = 0;
-  h->w_ocp = make_wire_layouts(h->S, h->ctrl.data(), h->n_grid, h->Wv);
+  h->w_ocp = make_wire_layouts(h->S, h->ctrl.data(), h->n_grid, h->cost_structure, h->Wv);
   if (wire == 2) {  // rbt_iteration_host_resident: wire records + residuals + dx0 up
     up += stage_xfer(h, RBT_XFER_WIRE, true, nullptr, nullptr, 0, h->batch, nullptr, false, &rc);
     up += stage_xfer(h, RBT_XFER_SWITCHING, true, nullptr, nullptr, 0, h->batch, nullptr, false, &rc);
@@ -1044,7 +1046,7 @@ static int iteration_host_impl(rbt_handle* h, const double* wire_host, const dou
       rbt_wire_layout wmax;
       rbt_stage_ctrl cmax = {};
       cmax.type = RBT_INTERMEDIATE; cmax.nf = h->S.nfm; cmax.contact_mask = (1 << h->S.ncon) - 1;
-      rbt_make_wire_layout(&h->S, &cmax, 1, &wmax);
+      rbt_make_wire_layout(&h->S, &cmax, 1, RBT_COST_GENERAL, &wmax);
       RBT_CUDA(h, cudaMalloc(&h->d_wire, size_t(h->batch) * h->n_grid_max * wmax.w_doubles * 8));
     }
     if (res_host && !h->d_res_stage) {
@@ -1154,31 +1156,38 @@ int rbt_iteration_host_resident(rbt_handle* h, const double* wire_host, const do
                              stream);
 }
 
-int rbt_wire_doubles(const rbt_stage_dims* sdims, const rbt_stage_ctrl* ctrl, int n_grid) {
+int rbt_set_wire_cost_structure(rbt_handle* h, int cost_structure) {
+  if (!h || (cost_structure != RBT_COST_GENERAL && cost_structure != RBT_COST_ROBOTOC)) return RBT_ERR_ARG;
+  h->cost_structure = cost_structure;
+  return RBT_OK;
+}
+
+int rbt_wire_doubles(const rbt_stage_dims* sdims, const rbt_stage_ctrl* ctrl, int n_grid, int cost_structure) {
   if (!sdims || !ctrl || n_grid <= 0) return -1;
   rbt_stage_layout S;
   rbt_make_stage_layout(sdims, &S);
   std::vector<rbt_wire_layout> W;
-  return int(make_wire_layouts(S, ctrl, n_grid, W));
+  return int(make_wire_layouts(S, ctrl, n_grid, cost_structure, W));
 }
 
-int rbt_wire_layout_get(const rbt_stage_dims* sdims, const rbt_stage_ctrl* ctrl, int n_grid, int i, rbt_wire_layout* out) {
+int rbt_wire_layout_get(const rbt_stage_dims* sdims, const rbt_stage_ctrl* ctrl, int n_grid, int cost_structure, int i,
+                        rbt_wire_layout* out) {
   if (!sdims || !ctrl || !out || i < 0 || i >= n_grid) return RBT_ERR_ARG;
   rbt_stage_layout S;
   rbt_make_stage_layout(sdims, &S);
   std::vector<rbt_wire_layout> W;
-  make_wire_layouts(S, ctrl, n_grid, W);
+  make_wire_layouts(S, ctrl, n_grid, cost_structure, W);
   *out = W[i];
   return RBT_OK;
 }
 
-int rbt_pack_wire(const rbt_stage_dims* sdims, const rbt_stage_ctrl* ctrl, int n_grid, const double* lin_host, double* wire_host,
-                  long long n_ocps) {
+int rbt_pack_wire(const rbt_stage_dims* sdims, const rbt_stage_ctrl* ctrl, int n_grid, int cost_structure, const double* lin_host,
+                  double* wire_host, long long n_ocps) {
   if (!sdims || !ctrl || n_grid <= 0 || !lin_host || !wire_host || n_ocps < 0) return RBT_ERR_ARG;
   rbt_stage_layout S;
   rbt_make_stage_layout(sdims, &S);
   std::vector<rbt_wire_layout> W;
-  const long long w_ocp = make_wire_layouts(S, ctrl, n_grid, W);
+  const long long w_ocp = make_wire_layouts(S, ctrl, n_grid, cost_structure, W);
   for (long long b = 0; b < n_ocps; ++b)
     for (int i = 0; i < n_grid; ++i)
       rbt_pack_wire_record(&W[i], lin_host + (b * n_grid + i) * S.l_stride, wire_host + b * w_ocp + W[i].ocp_off);

@@ -854,6 +854,9 @@ __global__ void __launch_bounds__(128) unpack_wire_kernel(const WireParams p) {
   const double* wire = p.wire + b * size_t(p.ocp_stride) + W.ocp_off;
   double* lin = p.lin + size_t(blockIdx.x) * p.l_stride;
   const int nseg = W.nseg;
+  for (int k = 0; k < W.nzero; ++k)
+    for (int e = threadIdx.x; e < W.zero[k].n; e += 128) lin[W.zero[k].lin_off + e] = 0.0;
+  __syncthreads();  // the diagonal / packed segments land inside zero-filled blocks
   for (int k = 0; k < nseg; ++k) {
     const rbt_wire_seg g = W.seg[k];
     const double* src = wire + g.wire_off;
@@ -864,6 +867,8 @@ __global__ void __launch_bounds__(128) unpack_wire_kernel(const WireParams p) {
       } else {
         for (int e = threadIdx.x; e < g.rows * g.cols; e += 128) dst[(e % g.rows) + (e / g.rows) * g.ld] = src[e];
       }
+    } else if (g.sym == 2) {
+      for (int e = threadIdx.x; e < g.rows; e += 128) dst[e * (g.ld + 1)] = src[e];
     } else {
       for (int e = threadIdx.x; e < g.rows * g.rows; e += 128) {
         const int r = e % g.rows, c = e / g.rows;
@@ -871,8 +876,6 @@ __global__ void __launch_bounds__(128) unpack_wire_kernel(const WireParams p) {
       }
     }
   }
-  for (int k = 0; k < W.nzero; ++k)
-    for (int e = threadIdx.x; e < W.zero[k].n; e += 128) lin[W.zero[k].lin_off + e] = 0.0;
   if (p.res) {
     const double* r = p.res + size_t(blockIdx.x) * p.ncp;
     double* c = p.con + size_t(blockIdx.x) * p.c_stride + p.c_res;

@@ -134,16 +134,23 @@ class DirectMultipleShooting:
                self.rr._err, "DirectMultipleShooting")
         return h2d.value, d2h.value
 
+    def setWireCostStructure(self, robotoc_costs: bool):
+        """Which cost-Hessian structure the host's wire records have: False = general (full packed triangles of Qxx, Quu, Qff),
+        True = what robotoc's shipped cost components produce (Qqq dense, Qvv / Quu / Qff diagonal, Qqv = 0)."""
+        self._cost_structure = 1 if robotoc_costs else 0
+        _check(self._lib.rbt_set_wire_cost_structure(self._h, self._cost_structure), self.rr._err, "DirectMultipleShooting")
+
     def pack_wire(self, lin):
         """Linearization records [batch, n_grid, l_stride] -> host wire records [batch, wire doubles per OCP] of the schedule in
         force (include/rbt_stage_layout.h: packed symmetric blocks, contact blocks sized by the active contacts, no Qqf, ...)."""
+        cs = getattr(self, "_cost_structure", 0)
         csd = self.sdims.c()
         ctrl, n_grid = self.rr._ctrl, self.rr.n_grid
         if n_grid == 0:
             raise RuntimeError("[DirectMultipleShooting] pack_wire: set the time discretization first")
-        w = int(self._lib.rbt_wire_doubles(ctypes.byref(csd), ctrl, n_grid))
+        w = int(self._lib.rbt_wire_doubles(ctypes.byref(csd), ctrl, n_grid, cs))
         out = np.zeros((lin.shape[0], w))
-        _check(self._lib.rbt_pack_wire(ctypes.byref(csd), ctrl, n_grid, _vp(lin), _vp(out), lin.shape[0]), self.rr._err,
+        _check(self._lib.rbt_pack_wire(ctypes.byref(csd), ctrl, n_grid, cs, _vp(lin), _vp(out), lin.shape[0]), self.rr._err,
                "DirectMultipleShooting")
         return out
 

@@ -261,6 +261,28 @@ def symmetrize_lin(S: StageLayout, lin):
     return out
 
 
+def robotoc_cost_structure(S: StageLayout, lin):
+    """Cost Hessians as every cost component robotoc ships produces them (configuration_space_cost.cpp:308-322,
+    task_space_*_cost.cpp, com_cost.cpp, local_contact_force_cost.cpp:130): Qqq dense, Qvv / Quu / Qff diagonal, Qqv = 0 (and
+    Qqf = 0, symmetric blocks exactly symmetric, like symmetrize_lin)."""
+    out = symmetrize_lin(S, lin)
+    flat = out.reshape(-1, out.shape[-1])
+    nv, nx = S.nv, S.nx
+    Q = flat[:, S.l_Qxx:S.l_Qxx + nx * nx].reshape(-1, nx, nx)   # [rec, col, row]
+    dv = np.einsum("rii->ri", Q[:, nv:, nv:]).copy()
+    Q[:, nv:, :] = 0.0
+    Q[:, :, nv:] = 0.0
+    for k in range(nv):
+        Q[:, nv + k, nv + k] = dv[:, k]
+    for off, n in ((S.l_Quu, S.nu), (S.l_Qff, S.nfm)):
+        B = flat[:, off:off + n * n].reshape(-1, n, n)
+        d = np.einsum("rii->ri", B).copy()
+        B[:] = 0.0
+        for k in range(n):
+            B[:, k, k] = d[:, k]
+    return out
+
+
 def make_unconstr_stage_inputs(S, N: int, batch: int, seed: int):
     """Synthetic linearization / PDIPM / solution records (no Pinocchio here): dID_da = M SPD, dense dID_dq / dID_dv,
     diagonal cost Hessians as ConfigurationSpaceCost produces them, slack / dual > 0."""

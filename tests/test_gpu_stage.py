@@ -11,7 +11,7 @@ import oracle_lib
 from helpers import jump_sto_schedule, rel_err, small_event_schedule, trot_schedule
 from robotoc_b200 import ANYMAL, DirectMultipleShooting, Layout, RiccatiRecursion, StageDims, StageLayout, anymal_constraint_table
 from robotoc_b200.grid import IMPACT, TERMINAL
-from synth import make_stage_inputs, symmetrize_lin
+from synth import make_stage_inputs, robotoc_cost_structure, symmetrize_lin
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-8
@@ -147,6 +147,18 @@ def _run(ctrl, batch, seed, reserve=0, impact_cones=False):
     sol7, con7, steps7 = dms.iteration_host_wire(dms.pack_wire(lin_s), lin_s, con_b, sol3, dx0)
     np.testing.assert_array_equal(sol6[:, :, :used], sol7[:, :, :used])
     np.testing.assert_array_equal(steps6, steps7)
+    # wire records with robotoc's cost structure (Qqq dense, Qvv / Quu / Qff diagonal): same bits as the dense records
+    lin_c = robotoc_cost_structure(S, lin)
+    sol8, con8, steps8 = dms.iteration_host(lin_c, con, sol, dx0)
+    w_gen = dms.pack_wire(lin_c)
+    dms.setWireCostStructure(True)
+    w_rob = dms.pack_wire(lin_c)
+    assert w_rob.shape[1] < 0.82 * w_gen.shape[1]
+    sol9, con9, steps9 = dms.iteration_host_wire(w_rob, lin_c, con, sol, dx0)
+    dms.setWireCostStructure(False)
+    np.testing.assert_array_equal(sol9, sol8)
+    np.testing.assert_array_equal(con9, con8)
+    np.testing.assert_array_equal(steps9, steps8)
     rr.close()
 
 

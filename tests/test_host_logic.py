@@ -136,9 +136,9 @@ def test_wire_format_pack_is_documented_packed_upper_storage():
         lin, con, sol, dx0 = make_stage_inputs(sd, S, ctrl, 2, seed=4)
         with_sto = any(c.sto or c.sto_next for c in ctrl)
         assert with_sto == sto
-        w = L.rbt_wire_doubles(ctypes.byref(csd), ctrl, n_grid)
+        w = L.rbt_wire_doubles(ctypes.byref(csd), ctrl, n_grid, 0)
         wire = np.zeros((2, w))
-        assert L.rbt_pack_wire(ctypes.byref(csd), ctrl, n_grid, lin.ctypes.data_as(ctypes.c_void_p),
+        assert L.rbt_pack_wire(ctypes.byref(csd), ctrl, n_grid, 0, lin.ctypes.data_as(ctypes.c_void_p),
                                wire.ctypes.data_as(ctypes.c_void_p), 2) == 0
         o = 0
         for i, c in enumerate(ctrl):
@@ -189,3 +189,74 @@ def test_wire_format_pack_is_documented_packed_upper_storage():
             full = 3104 - 118  # the record of a 4-contact intermediate grid point without the STO section
             n4 = sum(1 for c in ctrl if c.type != TERMINAL and c.nf == 12)
             assert w < full * n_grid and (n4 == 0 or w > 0)
+
+
+def test_wire_format_robotoc_cost_structure():
+    """RBT_COST_ROBOTOC wire records: Qqq packed + diag(Qvv), diag(Quu), diag(Qff) instead of the full packed triangles; the
+    segment table says where each piece sits, and the packed values are the diagonals / the Qqq triangle of the dense record."""
+    import ctypes
+    from robotoc_b200 import ANYMAL, StageDims, StageLayout, anymal_constraint_table
+    from robotoc_b200._lib import lib
+    from robotoc_b200.grid import TERMINAL
+    from synth import make_stage_inputs, robotoc_cost_structure
+    from helpers import small_event_schedule
+    L = lib()
+    tab = anymal_constraint_table()
+    sd = StageDims(ANYMAL, nf_max=12, n_contacts=tab.n_contacts, n_box=tab.n_box)
+    S = StageLayout(sd)
+    csd = sd.c()
+    td, ev, ctrl = small_event_schedule(False)
+    n_grid = len(ctrl)
+    lin, con, sol, dx0 = make_stage_inputs(sd, S, ctrl, 2, seed=5)
+    lin = robotoc_cost_structure(S, lin)
+    up2 = lambda n: n + (n & 1)  # noqa: E731
+    w0 = L.rbt_wire_doubles(ctypes.byref(csd), ctrl, n_grid, 0)
+    w1 = L.rbt_wire_doubles(ctypes.byref(csd), ctrl, n_grid, 1)
+    save = sum((666 - 172 - 18) + (0 if c.type == TERMINAL else (78 - 12) + up2(c.nf * (c.nf + 1) // 2) - up2(c.nf)) for c in ctrl)
+    assert w0 - w1 == save
+    wire = np.zeros((2, w1))
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+    assert L.rbt_pack_wire(ctypes.byref(csd), ctrl, n_grid, 1, P(lin), P(wire), 2) == 0
+
+    class Seg(ctypes.Structure):
+        _fields_ = [(k, ctypes.c_int) for k in ("lin_off", "wire_off", "rows", "cols", "ld", "sym")]
+
+    class Zero(ctypes.Structure):
+        _fields_ = [("lin_off", ctypes.c_int), ("n", ctypes.c_int)]
+
+    class WL(ctypes.Structure):
+        _fields_ = [(k, ctypes.c_int) for k in ("nseg", "nzero", "w_doubles", "ocp_off")] + [("seg", Seg * 20), ("zero", Zero * 5)]
+
+    for i, c in enumerate(ctrl):
+        W = WL()
+        assert L.rbt_wire_layout_get(ctypes.byref(csd), ctrl, n_grid, 1, i, ctypes.byref(W)) == 0
+        rec = lin[1, i]
+        back = rec.copy()
+        for k in range(W.nzero):
+            back[W.zero[k].lin_off:W.zero[k].lin_off + W.zero[k].n] = 0.0
+        kinds = set()
+        for k in range(W.nseg):
+            g = W.seg[k]
+            src = wire[1, W.ocp_off + g.wire_off:]
+            kinds.add(g.sym)
+            if g.sym == 0:
+                for j in range(g.cols):
+                    back[g.lin_off + j * g.ld:g.lin_off + j * g.ld + g.rows] = src[j * g.rows:(j + 1) * g.rows]
+            elif g.sym == 2:
+                for q in range(g.rows):
+                    back[g.lin_off + q * (g.ld + 1)] = src[q]
+            else:
+                for j in range(g.rows):
+                    for r in range(g.rows):
+                        back[g.lin_off + r + j * g.ld] = src[j * (j + 1) // 2 + r] if r <= j else src[r * (r + 1) // 2 + j]
+        assert 2 in kinds
+        # everything the kernels read of this grid point's record is reproduced exactly
+        if c.type == TERMINAL:
+            for off, n in ((S.l_Qxx, 36 * 36), (S.l_lx, 36), (S.l_se3 + 36, 36)):
+                np.testing.assert_array_equal(back[off:off + n], rec[off:off + n])
+        else:
+            keep = np.ones(S.l_stride, bool)
+            keep[S.l_Phix:S.l_ha] = False
+            keep[S.l_ha:S.l_dgdq] = False      # no switching-time stage in this schedule
+            keep[S.l_dgdf + 60:] = False
+            np.testing.assert_array_equal(back[keep], rec[keep])
