@@ -406,8 +406,10 @@ def main():
         pending[0] = False
 
     def step(ev=None):
-        # restore the records the iteration mutates (D2D, outside the per-kernel event pairs but inside the step time)
-        con_work.copy_(con_dev0)
+        # restore what the iteration mutates in place -- slack | dual of the PDIPM records and the solution records -- so that
+        # every timed step computes the same, oracle-checked iteration (D2D, outside the per-kernel event pairs but inside the
+        # step time; a real SQP loop has no such copy)
+        con_work[:, :, :2 * S.ncp].copy_(con_dev0[:, :, :2 * S.ncp])
         sol_work.copy_(sol_dev0)
         calls = [lambda: dms.condense(stream=sp), lambda: rr.backwardRiccatiRecursion(stream=sp),
                  lambda: rr.forwardRiccatiRecursion(stream=sp), lambda: dms.computeStepSizes(stream=sp),
@@ -502,7 +504,7 @@ def main():
             # the solver state (solution, slack, dual) lives on the device, as OCPSolver keeps s_ and the constraint data
             # between iterations; only what the host recomputes at a new linearisation point crosses PCIe.  (The D2D restore
             # of the state is a bench artefact -- every timed step then computes the same, oracle-checked iteration.)
-            con_work.copy_(con_dev0)
+            con_work[:, :, :2 * S.ncp].copy_(con_dev0[:, :, :2 * S.ncp])
             sol_work.copy_(sol_dev0)
             rc = lib.rbt_iteration_host_resident(rr._h, P(wire_p), P(lin_p), P(res_p), P(dx0_p), P(sol_o), P(sd_o), P(steps_o), sp)
         elif use_wire:

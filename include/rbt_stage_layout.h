@@ -60,7 +60,7 @@ typedef struct rbt_stage_layout {
   int l_M, l_J, l_D, l_IDC, l_Qaa, l_Qff, l_Qqf, l_Qxx, l_Quu, l_lx, l_la, l_lf, l_lu, l_Fx, l_lup, l_se3;
   int l_Phix, l_Phia, l_p, l_Phit, l_ha, l_hf, l_hx, l_hu, l_fx, l_sc, l_dgdq, l_dgdf, l_stride;
   /* ---- expansion record (written by condense, read by expand / update) */
-  int e_Z, e_R, e_r, e_Qafqv, e_Qafu, e_laf, e_Qxup, e_Quup, e_lup, e_Phia, e_haf, e_Fqqpi, e_stride;
+  int e_Z, e_R, e_r, e_Qafqv, e_Qafu, e_laf, e_Qxup, e_Quup, e_lup, e_Phia, e_haf, e_Fqqpi, e_Qaf, e_Quf, e_Qaa, e_stride;
   /* ---- PDIPM record */
   int c_slack, c_dual, c_res, c_cmpl, c_cond, c_dslack, c_ddual, c_stride;
   /* ---- solution record */
@@ -118,6 +118,13 @@ static inline RBT_HD void rbt_make_stage_layout(const rbt_stage_dims* d, rbt_sta
   L->e_Phia = o; o += rbt_up2(nsm * nv);
   L->e_haf = o; o += rbt_up2(nvf);
   L->e_Fqqpi = o; o += 36;
+  /* What the CUDA path keeps of Qafqv / Qafu_full (contact_dynamics.cpp:68-86): their contact rows, Qaf (nfm x nx, ld nfm) |
+   * Quf (nfm x nv, ld nfm), and diag(Qaa) after the PDIPM terms -- the acceleration rows are -diag(Qaa) R_a and diag(Qaa) Z_aa
+   * and are never materialised (the dual expansion uses Qaa o (da + r_a) for them).  e_Qafqv / e_Qafu (the full matrices) are
+   * written by the CPU oracle and the reference wrapper only. */
+  L->e_Qaf = o; o += rbt_up2(nfm * nx);
+  L->e_Quf = o; o += rbt_up2(nfm * nv);
+  L->e_Qaa = o; o += rbt_up2(nv);
   L->e_stride = rbt_up16(o);
 
   o = 0;
@@ -282,7 +289,7 @@ static inline void rbt_unpack_wire_record(const rbt_wire_layout* W, const double
   X(l_M) X(l_J) X(l_D) X(l_IDC) X(l_Qaa) X(l_Qff) X(l_Qqf) X(l_Qxx) X(l_Quu) X(l_lx) X(l_la) X(l_lf) X(l_lu) X(l_Fx) \
   X(l_lup) X(l_se3) X(l_Phix) X(l_Phia) X(l_p) X(l_Phit) X(l_ha) X(l_hf) X(l_hx) X(l_hu) X(l_fx) X(l_sc) X(l_dgdq) \
   X(l_dgdf) X(l_stride) \
-  X(e_Z) X(e_R) X(e_r) X(e_Qafqv) X(e_Qafu) X(e_laf) X(e_Qxup) X(e_Quup) X(e_lup) X(e_Phia) X(e_haf) X(e_Fqqpi) X(e_stride) \
+  X(e_Z) X(e_R) X(e_r) X(e_Qafqv) X(e_Qafu) X(e_laf) X(e_Qxup) X(e_Quup) X(e_lup) X(e_Phia) X(e_haf) X(e_Fqqpi) X(e_Qaf) X(e_Quf) X(e_Qaa) X(e_stride) \
   X(c_slack) X(c_dual) X(c_res) X(c_cmpl) X(c_cond) X(c_dslack) X(c_ddual) X(c_stride) \
   X(s_q) X(s_v) X(s_a) X(s_dv) X(s_u) X(s_f) X(s_lmd) X(s_gmm) X(s_beta) X(s_mu) X(s_nup) X(s_xi) X(s_stride) \
   X(x_daf) X(x_dbetamu) X(x_dnup) X(x_stride)

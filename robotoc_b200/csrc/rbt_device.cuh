@@ -55,6 +55,17 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
                : "memory");
 }
 
+// ---- 1-D TMA bulk store shared -> global (bulk async-group completion).  The issuing thread must (a) order the CTA's generic-
+// proxy writes to the source before the copy: barrier, then tma_store_fence(); (b) keep the source alive until the copy has READ
+// it: tma_store_wait_read() before the buffer is reused or the CTA exits.
+__device__ __forceinline__ void tma_store_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_1d(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
 // ---- DMMA m8n8k4: D(8x8) += A(8x4) * B(4x8), fp64.  lane = 4*g + t:
 //   a = A[g][t],  b = B[t][g],  c0 = C[g][2t], c1 = C[g][2t+1]
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {

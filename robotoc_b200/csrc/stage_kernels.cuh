@@ -320,6 +320,7 @@ struct CondCfg {
   static constexpr int QAF = 0, QUF = NFM * NX;    // contact rows of Qafqv (NFM x NX) and Qafu (NFM x NV) inside the dead D buffer
   static_assert(TF < NWARPS && TV <= NWARPS && 2 * TM < NWARPS, "one warp per row band, one warp left for the vectors");
   static_assert(NFM * NX + NFM * NV <= NVF * NX, "Qaf | Quf fit in the dIDCdqv buffer");
+  static_assert((NFM * NX) % 2 == 0 && (NFM * NV) % 2 == 0, "Qaf | Quf are adjacent in the expansion record (one bulk store)");
 };
 
 #ifndef RBT_COND_MIN_CTAS
@@ -447,8 +448,13 @@ __global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS, RBT_COND_MIN_C
       if (act) {
         const double sl = cSl[r], du = cSl[ncp + r];
         const double cm = sl * du - mu;
-        cd = (du * cSl[2 * ncp + r] - cm) / sl;
-        w = du / sl;
+        // one reciprocal (MUFU seed + 2 Newton steps) and a residual correction per quotient instead of two IEEE divisions:
+        // this loop is 92 threads wide and every warp of the CTA waits for it at the next barrier
+        const double rs = fast_rcp(sl), num = du * cSl[2 * ncp + r] - cm;
+        cd = num * rs;
+        cd = fma(fma(-sl, cd, num), rs, cd);
+        w = du * rs;
+        w = fma(fma(-sl, w, du), rs, w);
         con[S.c_cmpl + r] = cm;
       }
       con[S.c_cond + r] = cd;  // data.cond.setZero() for inactive contacts   friction_cone.cpp:198
@@ -516,6 +522,8 @@ __global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS, RBT_COND_MIN_C
       }
     }
     __syncthreads();  // the Qqq diagonal below touches elements the loop above also updates
+    // (measured: folding the diagonal weight into the tile epilogue to drop this barrier is 2.7 % SLOWER -- the divergent
+    //  gather costs more issue slots than the barrier wait it saves)
     // gradients and diagonals, one target per thread spread over the warps
     if (warp == 0 && lane < NV) {
       double w, gs;
@@ -621,10 +629,20 @@ __global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS, RBT_COND_MIN_C
       vlaf[r] = v;
       ex[S.e_laf + r] = v;
       ex[S.e_r + r] = vr[r];
-      if (!impact) ex[S.e_haf + r] = vhaf[r];
+      if (!impact) ex[S.e_haf + r] = (c.sto || c.sto_next) ? vhaf[r] : 0.0;
+      if (r < NV) ex[S.e_Qaa + r] = vQaa[r];
     }
   }
   __syncthreads();
+  // R and the contact rows [Qaf | Quf] are final and only read from here on: they go to the expansion record as two bulk
+  // shared -> global copies that run under the Hessian condensing (the element-wise copy-out loops were 9 % of the kernel's
+  // instructions; the acceleration rows of Qafqv / Qafu are not stored at all -- rbt_stage_layout.h)
+  if (tid == 0) {
+    tma_store_fence();
+    tma_store_1d(ex + S.e_R, sR, uint32_t(NVF * NX) * 8u);
+    tma_store_1d(ex + S.e_Qaf, sQaf, uint32_t(NFM * NX + NFM * NV) * 8u);
+    tma_store_commit();
+  }
 
   // ---- phase 5: Hessian condensing on the tensor pipe           contact_dynamics.cpp:88-121, impact_dynamics.cpp:64-66
   // Qafqv = [-diag(Qaa) R_a ; Qaf], Qafu = [diag(Qaa) Z_aa ; Quf]: the acceleration rows are formed in the fragment loads.
@@ -725,22 +743,30 @@ __global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS, RBT_COND_MIN_C
   }
   // ---- state equation rows                                 contact_dynamics.cpp:130-135, impact_dynamics.cpp:71-74
   const double sdt = impact ? 1.0 : dt;
-  for (int e = tid; e < NX * NX; e += NTHR) {
-    const int ii = e % NX, j = e / NX;
-    double v;
-    if (ii < NV) {
-      if (np == 6 && ii < 6 && (j < 6 || (j >= NV && j < NV + 6))) {
-        if (j < 6) v = -FiS[ii + j * 6];                              // Fqq top-left = -Fqq_inv * (dSub/dqf top-left)   state_equation.cpp:80
-        else v = impact ? 0.0 : -dt * Fi[ii + (j - NV) * 6];         // Fqv top-left = -dt Fqq_inv                      :81
-      } else if (j < NV) {
-        v = (ii == j) ? 1.0 : 0.0;
-      } else {
-        v = (!impact && ii == j - NV) ? dt : 0.0;
+  {  // thread = (row ii, column phase): the row decides the formula once, consecutive threads write consecutive addresses, and
+     // there is no div / mod in the loop (the flat version of this loop was 13 % of the kernel's executed instructions)
+    constexpr int CP = NTHR / NX;  // columns written per pass
+    if (tid < CP * NX) {
+      const int ii = tid % NX, j0 = tid / NX;
+      double* Fcol = kkt + K.k_Fxx + ii;
+      if (ii >= NV) {   // Fvq | Fvv = -dt R_a (+ I)
+        const double* rrow = sR + (ii - NV);
+#pragma unroll 3
+        for (int j = j0; j < NX; j += CP) Fcol[j * NX] = fma(-sdt, rrow[j * NVF], (j == ii) ? 1.0 : 0.0);
+      } else if (np == 6 && ii < 6) {  // floating base rows: Fqq = -Fqq_inv * (dSub/dqf), Fqv = -dt Fqq_inv   state_equation.cpp:80-81
+#pragma unroll 3
+        for (int j = j0; j < NX; j += CP) {
+          double v = 0.0;
+          if (j < 6) v = -FiS[ii + j * 6];
+          else if (j >= NV && j < NV + 6) v = impact ? 0.0 : -dt * Fi[ii + (j - NV) * 6];
+          Fcol[j * NX] = v;
+        }
+      } else {          // Fqq = I, Fqv = dt I
+        const double dtv = impact ? 0.0 : dt;
+#pragma unroll 3
+        for (int j = j0; j < NX; j += CP) Fcol[j * NX] = (j == ii) ? 1.0 : ((j == ii + NV) ? dtv : 0.0);
       }
-    } else {
-      v = -sdt * sR[(ii - NV) + j * NVF] + ((j >= NV && ii == j) ? 1.0 : 0.0);
     }
-    kkt[K.k_Fxx + e] = v;
   }
   if (!impact)
     for (int e = tid; e < NV * NU; e += NTHR) kkt[K.k_Fvu + e] = dt * sZ[(e % NV) + (np + e / NV) * NVF];
@@ -790,7 +816,10 @@ __global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS, RBT_COND_MIN_C
     }
   }
   // ---- STO sensitivities + scaling                         contact_dynamics.cpp:156-163, intermediate_stage.cpp:140-148
-  if (!impact) {
+  // Only grid points of a phase whose duration is optimised carry them: the sweeps read hx, hu, h, Qtt and haf under the
+  // same condition (riccati_backward.cuh: `if (sto)`, update_kernel: dts != 0), so the other grid points skip the work
+  // (6 % of this kernel's instructions on a schedule without switching-time optimisation).
+  if (!impact && (c.sto || c.sto_next)) {
     const double g1 = 1.0 / c.ngrids_in_phase;
     matvec_T(sR, NVF, NVF, NX, vhaf, tid, NTHR, [&](int ii, double a) {
       double v = vhx[ii] - a;
@@ -816,18 +845,7 @@ __global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS, RBT_COND_MIN_C
       kkt[K.k_sc + 3] = 0.0;
     }
   }
-  // ---- expansion record (Z is already there)
-  for (int e = tid; e < NVF * NX; e += NTHR) {
-    const int ii = e % NVF, j = e / NVF;
-    const double rv = sR[e];
-    ex[S.e_R + e] = rv;
-    ex[S.e_Qafqv + e] = (ii < NV) ? -vQaa[ii] * rv : sQaf[(ii - NV) + j * NFM];
-  }
-  if (!impact)
-    for (int e = tid; e < NVF * NV; e += NTHR) {
-      const int ii = e % NVF, j = e / NVF;
-      ex[S.e_Qafu + e] = (ii < NV) ? vQaa[ii] * sZ[ii + j * NVF] : sQuf[(ii - NV) + j * NFM];
-    }
+  if (tid == 0) tma_store_wait_read();  // the bulk stores of R | Qaf | Quf must have read shared memory before the CTA retires
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -1054,7 +1072,7 @@ __device__ __forceinline__ void integrate_free_flyer_dev(double* q, const double
 template <int NV, int NU, int NFM>
 __global__ void __launch_bounds__(XTHR) update_kernel(const StageParams p) {
   constexpr int NX = 2 * NV, NVF = NV + NFM, NTHR = XTHR;
-  constexpr int QSZ = ((NVF * NX + 1) & ~1) + ((NVF * NV + 1) & ~1);  // Qafqv | Qafu (adjacent in the record)
+  constexpr int QSZ = NFM * NX + NFM * NV + ((NV + 1) & ~1);  // contact rows Qaf | Quf and diag(Qaa) (adjacent in the record)
   constexpr int ZSZ = (NVF * NVF + 1) & ~1;
   constexpr int PSZ = ((NX * 6 + 1) & ~1) + ((6 * NU + 1) & ~1) + 6;     // Qxup | Quup | lup (floating base: np = 6)
   __shared__ __align__(16) double sQ[QSZ];
@@ -1080,7 +1098,7 @@ __global__ void __launch_bounds__(XTHR) update_kernel(const StageParams p) {
     mbar_init(&bar, 1);
     fence_mbar_init();
     mbar_expect_tx(&bar, (QSZ + ZSZ + (nup ? PSZ : 0)) * 8);
-    tma_load_1d(sQ, ex + S.e_Qafqv, QSZ * 8, &bar);
+    tma_load_1d(sQ, ex + S.e_Qaf, QSZ * 8, &bar);
     tma_load_1d(sZ, ex + S.e_Z, ZSZ * 8, &bar);
     if (nup) tma_load_1d(sP, ex + S.e_Qxup, PSZ * 8, &bar);
   }
@@ -1157,14 +1175,19 @@ __global__ void __launch_bounds__(XTHR) update_kernel(const StageParams p) {
       extra += sdgn[tid];                                                          // impact_dynamics.cpp:94
     }
   }
+  // acceleration rows of Qafqv dx + Qafu du: Qafqv_a = -diag(Qaa) R_a, Qafu_a = diag(Qaa) Z_aa, and da = -R_a dx + Z_a,u du - r_a
+  // (expand_kernel; ddv on an impact stage), so they are Qaa o (da + r_a) -- no matrix needed
+  const double da_r = (tid < NV) ? xd[S.x_daf + tid] + ex[S.e_r + tid] : 0.0;
   mbar_wait(&bar, 0);
-  {  // laf += Qafqv dx + Qafu du (+ dt dgmm+ / Phia^T dxi / dts haf)   contact_dynamics.cpp:191-201
+  if (tid < NV) extra = fma(sQ[NFM * NX + NFM * NV + tid], da_r, extra);
+  {  // laf += Qafqv dx + Qafu du (+ dt dgmm+ / Phia^T dxi / dts haf)   contact_dynamics.cpp:191-201: contact rows
     double acc = 0.0;
-    if (lane < nvf) {
-      for (int k = wid; k < NX; k += 4) acc = fma(sQ[lane + k * NVF], sdx[k], acc);
+    if (lane >= NV && lane < nvf) {
+      const double* q = sQ + (lane - NV);
+      for (int k = wid; k < NX; k += 4) acc = fma(q[k * NFM], sdx[k], acc);
       if (!impact) {
-        const double* sQu = sQ + ((NVF * NX + 1) & ~1) + np * NVF;
-        for (int k = wid; k < NU; k += 4) acc = fma(sQu[lane + k * NVF], sdu[k], acc);
+        const double* qu = q + NFM * NX + np * NFM;
+        for (int k = wid; k < NU; k += 4) acc = fma(qu[k * NFM], sdu[k], acc);
       }
     }
     spart[wid][lane] = acc;

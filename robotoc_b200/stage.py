@@ -36,7 +36,7 @@ class rbt_stage_dims(ctypes.Structure):
 
 _SFIELDS = ("nv nu nx np nfm nvf nsm ncon nbox nc ncp nq l_M l_J l_D l_IDC l_Qaa l_Qff l_Qqf l_Qxx l_Quu l_lx l_la l_lf l_lu "
             "l_Fx l_lup l_se3 l_Phix l_Phia l_p l_Phit l_ha l_hf l_hx l_hu l_fx l_sc l_dgdq l_dgdf l_stride e_Z e_R e_r "
-            "e_Qafqv e_Qafu e_laf e_Qxup e_Quup e_lup e_Phia e_haf e_Fqqpi e_stride c_slack c_dual c_res c_cmpl c_cond "
+            "e_Qafqv e_Qafu e_laf e_Qxup e_Quup e_lup e_Phia e_haf e_Fqqpi e_Qaf e_Quf e_Qaa e_stride c_slack c_dual c_res c_cmpl c_cond "
             "c_dslack c_ddual c_stride s_q s_v s_a s_dv s_u s_f s_lmd s_gmm s_beta s_mu s_nup s_xi s_stride x_daf "
             "x_dbetamu x_dnup x_stride").split()
 

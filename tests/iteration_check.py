@@ -107,6 +107,45 @@ def compare_final(S, K, ctrl, ref, ric, d, steps, sol, cc, tol=1e-8, sensitivity
     return worst[0]
 
 
+def mask_unread_sto(K, S, ctrl, kkt=None, ex=None):
+    """The CUDA condensing computes the switching-time sensitivities hx, hu, {Qtt, Qtt_prev, h} (KKT record) and haf (expansion
+    record) only on grid points whose phase duration is optimised (sto or sto_next) -- nothing reads them elsewhere; the
+    reference / oracle compute them everywhere.  Zeroes those sections on the other grid points (in place) so that whole
+    records can be compared."""
+    for i, c in enumerate(ctrl):
+        if c.sto or c.sto_next:
+            continue
+        if kkt is not None:
+            for off, n in ((K.k_hx, K.nx), (K.k_hu, K.nu), (K.k_sc, 4)):
+                kkt[:, i, off:off + n] = 0.0
+        if ex is not None:
+            ex[:, i, S.e_haf:S.e_haf + S.nvf] = 0.0
+    return kkt if kkt is not None else ex
+
+
+def reference_view_of_expansion(S, ex):
+    """The CUDA path keeps only the contact rows [Qaf | Quf] of Qafqv / Qafu_full plus diag(Qaa) (rbt_stage_layout.h); this
+    fills the full matrices the reference / oracle hold (contact_dynamics.cpp:68-86: acceleration rows -diag(Qaa) R_a and
+    diag(Qaa) Z_aa) into a copy of the expansion records, so that the same comparisons apply to both."""
+    out = ex.copy()
+    nv, nx, nfm, nvf = S.nv, S.nx, S.nfm, S.nvf
+    sh = ex.shape[:2]
+    Qaa = ex[..., S.e_Qaa:S.e_Qaa + nv]
+    R = ex[..., S.e_R:S.e_R + nvf * nx].reshape(sh + (nx, nvf))        # [.., col, row]
+    Z = ex[..., S.e_Z:S.e_Z + nvf * nvf].reshape(sh + (nvf, nvf))
+    Qaf = ex[..., S.e_Qaf:S.e_Qaf + nfm * nx].reshape(sh + (nx, nfm))
+    Quf = ex[..., S.e_Quf:S.e_Quf + nfm * nv].reshape(sh + (nv, nfm))
+    full = np.zeros(sh + (nx, nvf))
+    full[..., :nv] = -R[..., :nv] * Qaa[..., None, :]
+    full[..., nv:] = Qaf
+    out[..., S.e_Qafqv:S.e_Qafqv + nvf * nx] = full.reshape(sh + (-1,))
+    fullu = np.zeros(sh + (nv, nvf))
+    fullu[..., :nv] = Z[..., :nv, :nv] * Qaa[..., None, :]
+    fullu[..., nv:] = Quf
+    out[..., S.e_Qafu:S.e_Qafu + nvf * nv] = fullu.reshape(sh + (-1,))
+    return out
+
+
 def run_device_iteration(rr, dms, lin, con, sol, dx0, stream=None):
     """The five C-ABI calls of one iteration on device-resident records; returns what compare_final needs."""
     dms.condense(lin, con, stream=stream)

@@ -70,7 +70,9 @@ def test_cuda_reproduces_golden():
         rr.setTimeDiscretization(ctrl)
         dms = DirectMultipleShooting(rr, sd, table)
         dms.condense(lin, con)
-        assert _close(dms.getKKT(), G["kkt_condensed" + sfx], 1e-8)
+        from iteration_check import mask_unread_sto  # hx, hu, h, Qtt exist only where the phase duration is optimised
+        K = Layout(ANYMAL)
+        assert _close(mask_unread_sto(K, S, ctrl, kkt=dms.getKKT()), mask_unread_sto(K, S, ctrl, kkt=np.array(G["kkt_condensed" + sfx])), 1e-8)
         rr.backwardRiccatiRecursion()
         rr.forwardRiccatiRecursion(dx0)
         dms.computeStepSizes()

@@ -71,8 +71,10 @@ def _run(ctrl, batch, seed, reserve=0, impact_cones=False):
     dms.condense(lin, con)
     kkt, cc = dms.getKKT(), dms.getConstraintData()
     assert int(rr.info().max()) == 0
+    from iteration_check import mask_unread_sto
+    kkt, kkt_ref = mask_unread_sto(K, S, ctrl, kkt=kkt), mask_unread_sto(K, S, ctrl, kkt=ref["kkt"].copy())
     for i, c in enumerate(ctrl):
-        _cmp(f"kkt[{i}]", kkt[:, i], ref["kkt"][:, i])
+        _cmp(f"kkt[{i}]", kkt[:, i], kkt_ref[:, i])
         if c.type != TERMINAL:
             for f in ("c_cmpl", "c_cond"):
                 _cmp_rows(f"{f}[{i}]", S, c, impact_cones, f, cc[:, i], ref["cc_cond"][:, i])
@@ -101,10 +103,13 @@ def _run(ctrl, batch, seed, reserve=0, impact_cones=False):
                 _cmp(f"dnup[{i}]", xd[:, i, S.x_dnup:S.x_dnup + 6], ref["xd_upd"][:, i, S.x_dnup:S.x_dnup + 6])
             for f in ("c_slack", "c_dual"):
                 _cmp_rows(f"{f}[{i}]", S, c, impact_cones, f, cc[:, i], ref["cc_upd"][:, i])
-    ex = dms.getExpansionData()
+    from iteration_check import reference_view_of_expansion
+    ex = reference_view_of_expansion(S, dms.getExpansionData())  # full Qafqv / Qafu from the contact rows + diag(Qaa) kept on the device
     for i, c in enumerate(ctrl):
         if c.type != TERMINAL:
-            for f, n in (("e_Z", 900), ("e_R", 1080), ("e_Qafqv", 1080), ("e_r", 30), ("e_laf", 30)):
+            nz = 1080 if c.type == IMPACT else 1080 + 540  # Qafqv | Qafu (Qafu does not exist on an impact stage)
+            _cmp(f"Qafqv|Qafu[{i}]", ex[:, i, S.e_Qafqv:S.e_Qafqv + nz], ref["ex_upd"][:, i, S.e_Qafqv:S.e_Qafqv + nz])
+            for f, n in (("e_Z", 900), ("e_R", 1080), ("e_r", 30), ("e_laf", 30)):
                 o = getattr(S, f)
                 _cmp(f"{f}[{i}]", ex[:, i, o:o + n], ref["ex_upd"][:, i, o:o + n])
     # the one-call host path (chunked, trimmed transfers) gives the same bits as the step-by-step path
