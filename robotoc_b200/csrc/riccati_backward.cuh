@@ -566,6 +566,7 @@ __global__ void __launch_bounds__(BwdCfg<NV, NU, NS, NP>::NTHREADS, RBT_BWD_MIN_
       }
     }
     RBT_TL(i, 7);
+    if (tid == 0) tma_store_wait_read();  // the previous stage's bulk store of P has long read shared memory (issued ~3 us ago)
     __syncthreads();  // ---- barrier 2: AtP/H/t1 (GEMM warps) and G = L L^T, lu' (factor warp) are complete
     RBT_TL(i, 8);
 
@@ -852,23 +853,43 @@ __global__ void __launch_bounds__(BwdCfg<NV, NU, NS, NP>::NTHREADS, RBT_BWD_MIN_
       ric[L.r_s + tid] = t1[tid];
     }
 
-    // ================= spill F (row-major, ld LDF)
+    // ================= P = F - Y^T Y.  Symmetric stages (no switching constraint, no factorized-KKT output): the accumulator
+    // fragments with r <= c go straight to BOTH mirror positions of the next stage's P in shared memory (P+ is dead: its last
+    // readers were the phase A / B products, two barriers ago), and P leaves for HBM as ONE bulk shared -> global copy after
+    // the barrier.  (The element-wise symmetrise-and-store loop this replaces was 16 % of the sweep's instructions.)
+    const bool fastP = symF && fct == nullptr;
     if (gemm_warp) {
 #pragma unroll
       for (int n = 0; n < TX; ++n) {
         const int j0 = tile_off(n, NX);
         if (n >= nb0) {
-          sAtP[(i0 + g) * LDF + j0 + 2 * t] = cF[n][0];
-          sAtP[(i0 + g) * LDF + j0 + 2 * t + 1] = cF[n][1];
+          if (fastP) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              const int r = i0 + g, c = j0 + 2 * t + q;
+              if (r <= c) {
+                sP[r + c * NX] = cF[n][q];
+                sP[c + r * NX] = cF[n][q];
+              }
+            }
+          } else {  // spill F (row-major, ld LDF)
+            sAtP[(i0 + g) * LDF + j0 + 2 * t] = cF[n][0];
+            sAtP[(i0 + g) * LDF + j0 + 2 * t + 1] = cF[n][1];
+          }
         }
       }
     }
     RBT_TL(i, 11);
-    __syncthreads();  // ---- barrier 4: F scratch, s, k complete
+    __syncthreads();  // ---- barrier 4: P (or the F scratch), s, k complete
     RBT_TL(i, 12);
 
-    // ================= phase E: P = (F + F^T)/2 -> shared (next stage) and HBM ; STO vectors / scalars
-    {
+    if (fastP) {
+      if (tid == 0) {
+        tma_store_fence();
+        tma_store_1d(ric + L.r_P, sP, uint32_t(NX * NX) * 8u);
+        tma_store_commit();
+      }
+    } else {  // ================= phase E: P = (F + F^T)/2 -> shared (next stage) and HBM
       int r = tid % NX, c = tid / NX;  // (r, c) of e = tid + k * NTHR, advanced without a division per element
       for (int e = tid; e < NX * NX; e += NTHR) {
         double v, f_rc;
@@ -958,6 +979,7 @@ __global__ void __launch_bounds__(BwdCfg<NV, NU, NS, NP>::NTHREADS, RBT_BWD_MIN_
     if (!early_prefetch && tid == 0 && i > 0) issue_stage_load(i - 1);
   }
 
+  if (tid == 0) tma_store_wait_read();  // the last bulk store of P must have read shared memory before the CTA retires
   // ---- final phase transition at stage 0                       riccati_recursion.cpp:75-79
   {
     const rbt_stage_ctrl c0 = p.ctrl[0];
