@@ -484,41 +484,54 @@ __global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS, RBT_COND_MIN_C
     };
     // Qqq += sum_c dg_dq^T diag(w) dg_dq          friction_cone.cpp:217-218  (box diagonal below)
     // One NV x (5 ncon) x NV product on the tensor pipe: the cone rows of all contacts are the contraction index k = 5 ci + r
-    // (rows of inactive contacts were zeroed above).  The scalar version of this loop was 18 % of the kernel's shared-memory
-    // wavefronts (ncu, r2): 60 loads per output element.
-    {
-      constexpr int KC = 5 * (NFM / 3);
-      auto dq_at = [&](int k, int col) { return sDq[(k / 5) * 5 * NV + (k % 5) + col * 5]; };
-      for (int tile = warp; tile < TV * TV; tile += NTHR / 32) {
-        const int r0 = tile_off(tile / TV, NV), j0 = tile_off(tile % TV, NV);
-        double acc[1][2] = {{0.0, 0.0}};
-        warp_mma_band<KC, 1, 8>(
-            acc, r0, [&](int ii, int k) { return (k < 5 * ncon) ? dq_at(k, ii) * cW[nbox + k] : 0.0; },
-            [&](int k, int jj) { return (k < 5 * ncon) ? dq_at(k, j0 + jj) : 0.0; });
-        dQq[(r0 + g) + (j0 + 2 * t) * NV] = acc[0][0];
-        dQq[(r0 + g) + (j0 + 2 * t + 1) * NV] = acc[0][1];
+    // (rows of inactive contacts were zeroed above).  Warp w < TV owns row band w (A fragment and its weight loaded once per
+    // k-step, TV column tiles); the other warps do the Qqf / Qff terms meanwhile.  (A tile-per-warp version with generic
+    // operand lambdas spent 33 instructions per DMMA: 12 % of this kernel's instructions for 45 DMMAs.)
+    constexpr int KC = 5 * (NFM / 3);
+    static_assert(KC % 4 == 0 && TV < NTHR / 32, "cone rows fill whole k-steps; at least one warp left for Qqf / Qff");
+    if (warp < TV) {
+      const int r0 = tile_off(warp, NV);
+      double acc[TV][2];
+#pragma unroll
+      for (int n = 0; n < TV; ++n) acc[n][0] = acc[n][1] = 0.0;
+#pragma unroll
+      for (int ks = 0; ks < KC / 4; ++ks) {
+        const int k = 4 * ks + t;
+        const bool ok = k < 5 * ncon;
+        const double* col = sDq + (k / 5) * 5 * NV + (k % 5);   // element (k, x) of the stacked cone Jacobian at col[5 x]
+        const double a = ok ? col[(r0 + g) * 5] * cW[nbox + k] : 0.0;
+#pragma unroll
+        for (int n = 0; n < TV; ++n) {
+          const double bv = ok ? col[(tile_off(n, NV) + g) * 5] : 0.0;
+          dmma884(acc[n][0], acc[n][1], a, bv);
+        }
       }
-    }
-    // Qqf[:, stack(c)] += dg_dq^T diag(w) dg_df ;  Qff[stack(c), stack(c)] += dg_df^T diag(w) dg_df     :219-222
-    for (int e = tid; e < NV * 3 * ncon + 9 * ncon; e += NTHR) {
-      const bool isqf = e < NV * 3 * ncon;
-      const int ee = isqf ? e : e - NV * 3 * ncon;
-      const int ci = isqf ? ee / (NV * 3) : ee / 9;
-      if (!((c.contact_mask >> ci) & 1)) continue;
-      const int fstack = 3 * __popc(c.contact_mask & ((1 << ci) - 1));
-      const double* dq = sDq + ci * 5 * NV;
-      const double* df = sDf + ci * 15;
-      const double* w5 = cW + nbox + 5 * ci;
-      if (isqf) {
-        const int ii = (ee % (NV * 3)) % NV, j = (ee % (NV * 3)) / NV;
-        double acc = 0.0;
-        for (int r = 0; r < 5; ++r) acc = fma(dq[r + ii * 5] * w5[r], df[r + j * 5], acc);
-        sQqf[ii + (fstack + j) * NV] += acc;
-      } else {
-        const int ii = (ee % 9) % 3, j = (ee % 9) / 3;
-        double acc = 0.0;
-        for (int r = 0; r < 5; ++r) acc = fma(df[r + ii * 5] * w5[r], df[r + j * 5], acc);
-        sQff[(fstack + ii) + (fstack + j) * NFM] += acc;
+#pragma unroll
+      for (int n = 0; n < TV; ++n) {
+        const int j0 = tile_off(n, NV);
+        dQq[(r0 + g) + (j0 + 2 * t) * NV] = acc[n][0];
+        dQq[(r0 + g) + (j0 + 2 * t + 1) * NV] = acc[n][1];
+      }
+    } else {
+      // Qqf[:, stack(c)] += dg_dq^T diag(w) dg_df ;  Qff[stack(c), stack(c)] += dg_df^T diag(w) dg_df     :219-222
+      // thread u: one element (ii, j) of the NV x 3 block (u < 3 NV) or of the 3 x 3 block, looped over the active contacts
+      constexpr int NE = 3 * NV + 9;
+      for (int u = tid - 32 * TV; u < NE; u += NTHR - 32 * TV) {
+        const bool isqf = u < 3 * NV;
+        const int uu = isqf ? u : u - 3 * NV;
+        const int ii = isqf ? uu % NV : uu % 3, j = isqf ? uu / NV : uu / 3;
+        for (int ci = 0; ci < ncon; ++ci) {
+          if (!((c.contact_mask >> ci) & 1)) continue;
+          const int fstack = 3 * __popc(c.contact_mask & ((1 << ci) - 1));
+          const double* lhs = isqf ? sDq + ci * 5 * NV + ii * 5 : sDf + ci * 15 + ii * 5;
+          const double* df = sDf + ci * 15 + j * 5;
+          const double* w5 = cW + nbox + 5 * ci;
+          double acc = 0.0;
+#pragma unroll
+          for (int r = 0; r < 5; ++r) acc = fma(lhs[r] * w5[r], df[r], acc);
+          if (isqf) sQqf[ii + (fstack + j) * NV] += acc;
+          else sQff[(fstack + ii) + (fstack + j) * NFM] += acc;
+        }
       }
     }
     __syncthreads();  // the Qqq diagonal below touches elements the loop above also updates
@@ -743,28 +756,35 @@ __global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS, RBT_COND_MIN_C
   }
   // ---- state equation rows                                 contact_dynamics.cpp:130-135, impact_dynamics.cpp:71-74
   const double sdt = impact ? 1.0 : dt;
-  {  // thread = (row ii, column phase): the row decides the formula once, consecutive threads write consecutive addresses, and
-     // there is no div / mod in the loop (the flat version of this loop was 13 % of the kernel's executed instructions)
-    constexpr int CP = NTHR / NX;  // columns written per pass
-    if (tid < CP * NX) {
-      const int ii = tid % NX, j0 = tid / NX;
-      double* Fcol = kkt + K.k_Fxx + ii;
-      if (ii >= NV) {   // Fvq | Fvv = -dt R_a (+ I)
-        const double* rrow = sR + (ii - NV);
-#pragma unroll 3
-        for (int j = j0; j < NX; j += CP) Fcol[j * NX] = fma(-sdt, rrow[j * NVF], (j == ii) ? 1.0 : 0.0);
-      } else if (np == 6 && ii < 6) {  // floating base rows: Fqq = -Fqq_inv * (dSub/dqf), Fqv = -dt Fqq_inv   state_equation.cpp:80-81
-#pragma unroll 3
+  {  // thread = (pair of rows, column phase): 16-byte stores, the rows decide the formula once, no div / mod in the loop
+     // (the flat element loop was 13 % of the kernel's executed instructions, a row-per-thread version still 10 %)
+    constexpr int RP = NX / 2, CP = NTHR / RP;  // row pairs ; columns written per pass
+    static_assert(NX % 2 == 0 && NV % 2 == 0 && NVF % 2 == 0 && CP >= 1, "row pairs never straddle the q | v boundary");
+    if (tid < CP * RP) {
+      const int r0 = 2 * (tid % RP), j0 = tid / RP;
+      double* Fcol = kkt + K.k_Fxx + r0;
+      if (r0 >= NV) {   // Fvq | Fvv = -dt R_a (+ I)
+        const double* rrow = sR + (r0 - NV);
+#pragma unroll 2
         for (int j = j0; j < NX; j += CP) {
-          double v = 0.0;
-          if (j < 6) v = -FiS[ii + j * 6];
-          else if (j >= NV && j < NV + 6) v = impact ? 0.0 : -dt * Fi[ii + (j - NV) * 6];
-          Fcol[j * NX] = v;
+          const double2 rv = *reinterpret_cast<const double2*>(rrow + j * NVF);
+          *reinterpret_cast<double2*>(Fcol + j * NX) =
+              make_double2(fma(-sdt, rv.x, (j == r0) ? 1.0 : 0.0), fma(-sdt, rv.y, (j == r0 + 1) ? 1.0 : 0.0));
+        }
+      } else if (np == 6 && r0 < 6) {  // floating base rows: Fqq = -Fqq_inv * (dSub/dqf), Fqv = -dt Fqq_inv   state_equation.cpp:80-81
+#pragma unroll 2
+        for (int j = j0; j < NX; j += CP) {
+          double2 v = make_double2(0.0, 0.0);
+          if (j < 6) v = make_double2(-FiS[r0 + j * 6], -FiS[r0 + 1 + j * 6]);
+          else if (j >= NV && j < NV + 6 && !impact) v = make_double2(-dt * Fi[r0 + (j - NV) * 6], -dt * Fi[r0 + 1 + (j - NV) * 6]);
+          *reinterpret_cast<double2*>(Fcol + j * NX) = v;
         }
       } else {          // Fqq = I, Fqv = dt I
         const double dtv = impact ? 0.0 : dt;
-#pragma unroll 3
-        for (int j = j0; j < NX; j += CP) Fcol[j * NX] = (j == ii) ? 1.0 : ((j == ii + NV) ? dtv : 0.0);
+#pragma unroll 2
+        for (int j = j0; j < NX; j += CP)
+          *reinterpret_cast<double2*>(Fcol + j * NX) = make_double2((j == r0) ? 1.0 : ((j == r0 + NV) ? dtv : 0.0),
+                                                                    (j == r0 + 1) ? 1.0 : ((j == r0 + 1 + NV) ? dtv : 0.0));
       }
     }
   }
