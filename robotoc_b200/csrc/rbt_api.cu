@@ -81,6 +81,7 @@ struct rbt_handle {
   // pipeline uploads, kernels and downloads over chunks of the batch
   int cb0 = 0, cnb = 0;
   double* d_wire = nullptr;  // packed host wire records (rbt_iteration_host_wire), allocated on first use
+  int* d_tgt = nullptr;           // box rows per PDIPM target (stage_kernels.cuh: StageParams::tgt)
   double* d_res_stage = nullptr;  // rbt_iteration_host_resident: compact residuals in, compact slack|dual out
   double* d_sd_stage = nullptr;
   std::vector<rbt_wire_layout> Wv;   // per grid point (the wire record of a grid point depends on its control word)
@@ -210,6 +211,7 @@ int rbt_destroy(rbt_handle* h) {
   if (h) {
     cudaFree(h->d_wire);
     cudaFree(h->d_W);
+    cudaFree(h->d_tgt);
     cudaFree(h->d_res_stage);
     cudaFree(h->d_sd_stage);
     if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
@@ -619,6 +621,7 @@ int rbt_stage_layout_get(const rbt_stage_dims* sdims, const char* field) {
 int rbt_stage_setup(rbt_handle* h, const rbt_stage_dims* sd, const rbt_constraint_table* table) {
   if (!h || !sd || !table) return RBT_ERR_ARG;
   if (sd->nv != h->dims.nv || sd->nu != h->dims.nu || sd->ns_max != h->dims.ns_max || sd->n_passive != h->dims.n_passive ||
+      sd->n_passive != sd->nv - sd->nu /* dim_passive = dimv - dimu (robot.cpp): compiled into the stage kernels */ ||
       sd->nf_max != 12 || table->n_box != sd->n_box || table->n_contacts != sd->n_contacts || sd->n_box > RBT_MAX_BOX_ROWS ||
       sd->n_contacts > RBT_MAX_CONTACTS || !(table->barrier > 0) || !(table->fraction_to_boundary > 0) ||
       !(table->fraction_to_boundary <= 1)) {
@@ -695,6 +698,22 @@ int rbt_stage_setup(rbt_handle* h, const rbt_stage_dims* sd, const rbt_constrain
   RBT_CUDA(h, cudaMalloc(&h->d_stage_perf, per * 4 * 8));
   RBT_CUDA(h, cudaMalloc(&h->d_perf, size_t(h->batch) * 8 * 8));
   RBT_CUDA(h, cudaMalloc(&h->d_x0in, size_t(h->batch) * 2 * h->dims.nv * 8));
+  {  // box rows acting on each target entry (var, idx), in ascending row order (deterministic accumulation on the device):
+     // entry = (row + 1) * sign, 0 = none.  Device memory, not kernel parameters: the lanes of a warp look up different targets,
+     // and a divergent constant-bank access is serialised.
+    int tg[RBT_MAX_TARGETS][4] = {};
+    for (int r = 0; r < h->table.n_box; ++r) {
+      const rbt_box_row& b = h->table.box[r];
+      const int t = (b.var == RBT_VAR_U) ? 3 * h->sdims.nv + b.idx : b.var * h->sdims.nv + b.idx;
+      for (int q = 0; q < 4; ++q)
+        if (tg[t][q] == 0) {
+          tg[t][q] = (r + 1) * (b.sign < 0 ? -1 : 1);
+          break;
+        }
+    }
+    RBT_CUDA(h, cudaMalloc(&h->d_tgt, sizeof(tg)));
+    RBT_CUDA(h, cudaMemcpy(h->d_tgt, tg, sizeof(tg), cudaMemcpyHostToDevice));
+  }
   RBT_CUDA(h, cudaMemset(h->d_perf, 0, size_t(h->batch) * 8 * 8));
   RBT_CUDA(h, cudaMemset(h->d_lin, 0, per * h->S.l_stride * 8));  // uploads skip record padding: keep it defined
   RBT_CUDA(h, cudaMemset(h->d_sol, 0, per * h->S.s_stride * 8));
@@ -727,18 +746,7 @@ static rbt::StageParams make_stage_params(rbt_handle* h) {
   p.sol = h->d_sol + go * h->S.s_stride;
   p.steps = h->d_steps + 2 * size_t(b0);
   p.info = h->d_info + b0;
-  // box rows acting on each target entry (var, idx), in ascending row order (deterministic accumulation on the device)
-  for (int t = 0; t < RBT_MAX_TARGETS; ++t)
-    for (int q = 0; q < 4; ++q) p.tgt_rows[t][q] = -1;
-  for (int r = 0; r < h->table.n_box; ++r) {
-    const rbt_box_row& b = h->table.box[r];
-    const int t = (b.var == RBT_VAR_U) ? 3 * h->sdims.nv + b.idx : b.var * h->sdims.nv + b.idx;
-    for (int q = 0; q < 4; ++q)
-      if (p.tgt_rows[t][q] < 0) {
-        p.tgt_rows[t][q] = (short)r;
-        break;
-      }
-  }
+  p.tgt = reinterpret_cast<const int4*>(h->d_tgt);
   return p;
 }
 

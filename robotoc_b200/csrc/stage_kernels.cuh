@@ -38,7 +38,8 @@ struct StageParams {
   double* sol;
   double* steps;  // [batch][2]
   int* info;
-  short tgt_rows[RBT_MAX_TARGETS][4];  // box rows acting on target (var, idx) = var*nv + idx (u: 3*nv + idx), ascending, -1 = none
+  const int4* tgt;  // [RBT_MAX_TARGETS] box rows acting on target (var, idx) = var*nv + idx (u: 3*nv + idx), ascending:
+                    // (row + 1) * sign of the row, 0 = none
 };
 
 // C(m x n, ld ldc) = beta*C + alpha * op(A) op(B); all operands in shared (or global) memory; every thread of the CTA calls.
@@ -342,7 +343,7 @@ __global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS, RBT_COND_MIN_C
   double* con = p.con + o * S.c_stride;
   double* kkt = p.kkt + o * K.k_stride;
   double* ex = p.ex + o * S.e_stride;
-  const int np = S.np;
+  constexpr int np = NV - NU;  // dim_passive = dimv - dimu for every robot robotoc builds (checked at rbt_stage_setup)
 
   if (c.type == RBT_TERMINAL) {  // terminal_stage.cpp:94-106
     for (int e = tid; e < NX * NX; e += NTHR) kkt[K.k_Qxx + e] = lin[S.l_Qxx + e];
@@ -472,15 +473,16 @@ __global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS, RBT_COND_MIN_C
   // A target (variable, index) gathers its box rows in table order (deterministic; a lower and an upper limit share it).
   if (pdipm) {
     auto gather = [&](int tgt, double& w, double& gs) {
+      const int4 e4 = __ldg(p.tgt + tgt);
+      const int e[4] = {e4.x, e4.y, e4.z, e4.w};
       w = 0.0; gs = 0.0;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int r = p.tgt_rows[tgt][q];
-        if (r >= 0) {
+      for (int q = 0; q < 4; ++q)
+        if (e[q] != 0) {
+          const int r = (e[q] < 0 ? -e[q] : e[q]) - 1;
           w += cW[r];
-          gs += p.tab.box[r].sign * cC[r];
+          gs += (e[q] < 0) ? -cC[r] : cC[r];
         }
-      }
     };
     // Qqq += sum_c dg_dq^T diag(w) dg_dq          friction_cone.cpp:217-218  (box diagonal below)
     // One NV x (5 ncon) x NV product on the tensor pipe: the cone rows of all contacts are the contraction index k = 5 ci + r
@@ -512,6 +514,23 @@ __global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS, RBT_COND_MIN_C
         dQq[(r0 + g) + (j0 + 2 * t) * NV] = acc[n][0];
         dQq[(r0 + g) + (j0 + 2 * t + 1) * NV] = acc[n][1];
       }
+      // the cone parts of the gradients ride along here (the band products are short): lq += dg_dq^T cond, lf += dg_df^T cond
+      if (warp == 0 && lane < NV) {                                                                          // :207
+        double a = 0.0;
+        for (int ci = 0; ci < ncon; ++ci)
+#pragma unroll
+          for (int r = 0; r < 5; ++r) a = fma(sDq[ci * 5 * NV + r + lane * 5], cC[nbox + 5 * ci + r], a);
+        vlx[lane] += a;
+      } else if (warp == 1 && lane < 3 * ncon) {                                                             // :208-209
+        const int ci = lane / 3, j = lane % 3;
+        if ((c.contact_mask >> ci) & 1) {
+          const int fstack = 3 * __popc(c.contact_mask & ((1 << ci) - 1));
+          double a = 0.0;
+#pragma unroll
+          for (int r = 0; r < 5; ++r) a = fma(sDf[ci * 15 + r + j * 5], cC[nbox + 5 * ci + r], a);
+          vlf[fstack + j] += a;
+        }
+      }
     } else {
       // Qqf[:, stack(c)] += dg_dq^T diag(w) dg_df ;  Qff[stack(c), stack(c)] += dg_df^T diag(w) dg_df     :219-222
       // thread u: one element (ii, j) of the NV x 3 block (u < 3 NV) or of the 3 x 3 block, looped over the active contacts
@@ -541,10 +560,7 @@ __global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS, RBT_COND_MIN_C
     if (warp == 0 && lane < NV) {
       double w, gs;
       gather(lane, w, gs);
-      double acc = gs;
-      for (int ci = 0; ci < ncon; ++ci)
-        for (int r = 0; r < 5; ++r) acc = fma(sDq[ci * 5 * NV + r + lane * 5], cC[nbox + 5 * ci + r], acc);  // lq += dg_dq^T cond  :207
-      vlx[lane] += acc;
+      vlx[lane] += gs;
       dQq[lane * (NV + 1)] += w;
     } else if (warp == 1 && lane < NV) {
       double w, gs;
@@ -561,14 +577,6 @@ __global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS, RBT_COND_MIN_C
       gather(3 * NV + lane, w, gs);
       gQuu[lane * (NU + 1)] += w;
       vlu[lane] += gs;
-    } else if (warp == 4 && lane < 3 * ncon) {  // lf[stack(c) + j] += dg_df^T cond   :208-209
-      const int ci = lane / 3, j = lane % 3;
-      if ((c.contact_mask >> ci) & 1) {
-        const int fstack = 3 * __popc(c.contact_mask & ((1 << ci) - 1));
-        double acc = 0.0;
-        for (int r = 0; r < 5; ++r) acc = fma(sDf[ci * 15 + r + j * 5], cC[nbox + 5 * ci + r], acc);
-        vlf[fstack + j] += acc;
-      }
     }
     __syncthreads();  // staging (in the R buffer) is dead from here on
   }
@@ -963,7 +971,8 @@ __global__ void __launch_bounds__(XTHR) expand_kernel(const StageParams p) {
   if (c.type == RBT_TERMINAL) return;  // step sizes 1.0 (terminal_stage.cpp:127-136)
   const bool impact = (c.type == RBT_IMPACT);
   const bool pdipm = !impact || p.tab.impact_friction_cone != 0;  // impact stages: cone rows only (impact_friction_cone.cpp:238-268)
-  const int nf = c.nf, nvf = NV + nf, np = S.np;
+  constexpr int np = NV - NU;
+  const int nf = c.nf, nvf = NV + nf;
   const double* lin = p.lin + o * S.l_stride;
   const double* ex = p.ex + o * S.e_stride;
   const double* d = p.dir + o * K.d_stride;
@@ -1107,7 +1116,8 @@ __global__ void __launch_bounds__(XTHR) update_kernel(const StageParams p) {
   const int i = int(o % p.n_grid), b = int(o / p.n_grid);
   const rbt_stage_ctrl c = p.ctrl[i];
   const bool terminal = (c.type == RBT_TERMINAL), impact = (c.type == RBT_IMPACT);
-  const int nf = terminal ? 0 : c.nf, nvf = NV + nf, np = S.np, ns = (terminal || impact) ? 0 : c.ns;
+  constexpr int np = NV - NU;
+  const int nf = terminal ? 0 : c.nf, nvf = NV + nf, ns = (terminal || impact) ? 0 : c.ns;
   double* ex = p.ex + o * S.e_stride;
   double* d = p.dir + o * K.d_stride;
   double* xd = p.xd + o * S.x_stride;
