@@ -419,16 +419,18 @@ __global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS, RBT_COND_MIN_C
   }
   __syncthreads();
   if (np == 6) {  // the SE(3) inverses are long scalar chains: run them under the bulk copies, straight from global memory
-    if (tid == 32) se3_jac_inverse_dev(lin + S.l_se3 + 36, ex + S.e_Fqqpi);  // Fqq_prev_inv   state_equation.cpp:76
-    if (tid == 64) se3_jac_inverse_dev(lin + S.l_se3 + 72, Fi);              // Fqq_inv        :77-78
+    // two lanes of ONE warp (a lone thread still costs its warp every issue slot of the 370-instruction routine)
+    if (tid == 32 || tid == 33)  // Fqq_prev_inv (state_equation.cpp:76) | Fqq_inv (:77-78)
+      se3_jac_inverse_dev(lin + S.l_se3 + (tid == 32 ? 36 : 72), tid == 32 ? ex + S.e_Fqqpi : Fi);
   }
   mbar_wait(bar, 0);
 
   // ---- phase 1: mask what lies beyond the active contact dimension, per-row PDIPM quantities
-  for (int e = tid; e < NFM * NFM; e += NTHR)
-    if ((e % NFM) >= nf || (e / NFM) >= nf) sQff[e] = 0.0;
-  for (int e = tid; e < NV * NFM; e += NTHR)
-    if ((e / NV) >= nf) sQqf[e] = 0.0;
+  if (nf < NFM) {  // (loops over the inactive part only: this kernel is bound by issue slots, not by bytes)
+    for (int e = tid; e < NFM * NFM; e += NTHR)
+      if ((e % NFM) >= nf || (e / NFM) >= nf) sQff[e] = 0.0;
+    for (int e = nf * NV + tid; e < NV * NFM; e += NTHR) sQqf[e] = 0.0;
+  }
   if (tid < NVF) {
     if (tid >= nvf) vIDC[tid] = 0.0;
     vhaf[tid] = impact ? 0.0 : (tid < NV ? vha[tid] : (tid - NV < nf ? -vhf[tid - NV] : 0.0));
@@ -462,10 +464,12 @@ __global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS, RBT_COND_MIN_C
       cW[r] = w;
       cC[r] = cd;
     }
-    for (int e = tid; e < 5 * NV * ncon; e += NTHR)
-      if (!((c.contact_mask >> (e / (5 * NV))) & 1)) sDq[e] = 0.0;
-    for (int e = tid; e < 15 * ncon; e += NTHR)
-      if (!((c.contact_mask >> (e / 15)) & 1)) sDf[e] = 0.0;
+    for (int ci = 0; ci < ncon; ++ci)  // cone Jacobians of inactive contacts -> 0 (they are contraction rows of the products below)
+      if (!((c.contact_mask >> ci) & 1))
+        for (int e = tid; e < 5 * NV + 15; e += NTHR) {
+          if (e < 5 * NV) sDq[ci * 5 * NV + e] = 0.0;
+          else sDf[ci * 15 + e - 5 * NV] = 0.0;
+        }
   }
   __syncthreads();
 
@@ -690,11 +694,12 @@ __global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS, RBT_COND_MIN_C
     warp_mma_band<NFM, TX, NX>(
         acc, i0, [&](int ii, int l) { return ii < NV ? sQqf[ii + l * NV] : 0.0; },
         [&](int l, int j) { return sR[(NV + l) + j * NVF]; });
+    double* qxx_out = kkt + K.k_Qxx + (i0 + g) + 2 * t * NX;
 #pragma unroll
     for (int n = 0; n < TX; ++n) {
       const int j0 = tile_off(n, NX);
-      kkt[K.k_Qxx + (i0 + g) + (j0 + 2 * t) * NX] = acc[n][0];
-      kkt[K.k_Qxx + (i0 + g) + (j0 + 2 * t + 1) * NX] = acc[n][1];
+      qxx_out[j0 * NX] = acc[n][0];        // (one base pointer, compile-time offsets: the address arithmetic of a fresh
+      qxx_out[(j0 + 1) * NX] = acc[n][1];  //  64-bit address per store was two extra instructions per store)
     }
   }
   if (!impact) {
@@ -709,14 +714,17 @@ __global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS, RBT_COND_MIN_C
       warp_mma_band<NFM, TV, NV>(
           acc, i0, [&](int ii, int l) { return ii < NV ? -sQqf[ii + l * NV] : 0.0; },
           [&](int l, int j) { return sZ[(NV + l) + j * NVF]; });
+      double* qxup_out = ex + S.e_Qxup + (i0 + g);
+      double* qxu_out = kkt + K.k_Qxu + (i0 + g);
 #pragma unroll
       for (int n = 0; n < TV; ++n) {
         const int j0 = tile_off(n, NV);
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           const int j = j0 + 2 * t + q;
-          if (j < np) ex[S.e_Qxup + (i0 + g) + j * NX] = acc[n][q];
-          else kkt[K.k_Qxu + (i0 + g) + (j - np) * NX] = acc[n][q];  // pre-condense Qxu is zero (the cost has no x-u term)
+          // passive columns -> expansion record, actuated columns -> KKT record (pre-condense Qxu is zero: no x-u cost term)
+          double* dst = (j < np) ? qxup_out + j * NX : qxu_out + (j - np) * NX;
+          *dst = acc[n][q];
         }
       }
     }
