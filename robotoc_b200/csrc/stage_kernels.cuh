@@ -96,33 +96,45 @@ __device__ __noinline__ void se3_jac_inverse_dev(const double* Jac, double* Jinv
 // The two Choleskys and the two triangular inverses are dependency chains on one warp (lane = row / column); the seven
 // products run on the fp64 tensor pipe (DMMA m8n8k4, ~200 per stage) fed from 11 KB of shared memory per warp, so ~20
 // stages per SM are in flight and hide each other's fp64 latency.  Z goes to the expansion record; K2 reads it from L2.
-template <int NMAX>
-__device__ __forceinline__ bool warp_cholesky_ld(double* A, int ld, int n, double* dinv) {
+// Cholesky factor of the leading n x n block of A (lower triangle, column-major, leading dimension LD) by ONE warp: lane r
+// holds row r in registers; column j is published through shared memory (it is the storage of L anyway) and read back by
+// every lane with 16-byte loads.  Rows / columns >= n are carried as identity (no per-element predicates: entries above the
+// diagonal of a lane's row are scratch, and what is stored beyond n is the identity).  Pivots use the MUFU-seeded reciprocal
+// square root.  Writes L over A and dinv[j] = 1 / L[j][j].
+// (The first version predicated every update on the runtime n and on lane >= k and used the IEEE rsqrt: 2.8 k instructions for
+//  NMAX = 18 -- 52 % of mjtjinv_kernel's program; a pure shuffle version is 4.1 k: ptxas wraps every shuffle of this
+//  divergence-prone code in WARPSYNC / ENDCOLLECTIVE.)
+template <int NMAX, int LD>
+__device__ __forceinline__ bool warp_cholesky_ld(double* A, int n, double* dinv) {
+  static_assert(NMAX <= 32 && LD % 2 == 0, "one row per lane; 16-byte column loads");
   const int lane = threadIdx.x & 31;
   double a[NMAX];
 #pragma unroll
-  for (int k = 0; k < NMAX; ++k) a[k] = (lane < n && k <= lane && k < n) ? A[lane + k * ld] : 0.0;
+  for (int k = 0; k < NMAX; ++k) a[k] = (lane < n) ? ((k <= lane && k < n) ? A[lane + k * LD] : 0.0) : ((k == lane) ? 1.0 : 0.0);
   bool ok = true;
 #pragma unroll
   for (int j = 0; j < NMAX; ++j) {
-    if (j < n) {
-      const double d = __shfl_sync(0xffffffffu, a[j], j);
-      if (!(d > 0.0)) ok = false;
-      const double inv = rsqrt(d);
-      const double lij = (lane == j) ? d * inv : a[j] * inv;
-      a[j] = lij;
-      if (lane == j) dinv[j] = inv;
-      if (lane >= j && lane < n) A[lane + j * ld] = lij;
-      __syncwarp();
+    const double d = __shfl_sync(0xffffffffu, a[j], j);
+    ok = ok && (d > 0.0);
+    const double inv = fast_rsqrt(d);
+    const double lij = a[j] * inv;  // lane j: sqrt(d); lanes < j: scratch
+    if (lane >= j && lane < NMAX) A[lane + j * LD] = lij;
+    if (lane == j) dinv[j] = inv;
+    __syncwarp();
+    constexpr int dummy = 0;
+    (void)dummy;
 #pragma unroll
-      for (int k = j + 1; k < NMAX; ++k) {
-        if (k < n) {
-          const double lkj = A[k + j * ld];  // broadcast read
-          if (lane >= k) a[k] = fma(-lij, lkj, a[k]);
-        }
+    for (int k0 = (j + 1) & ~1; k0 < NMAX; k0 += 2) {  // column j, two rows per load (k0 even, LD even: 16-byte aligned)
+      if (k0 + 1 < NMAX || (NMAX % 2 == 0)) {
+        const double2 l2 = *reinterpret_cast<const double2*>(A + k0 + j * LD);
+        if (k0 > j) a[k0] = fma(-lij, l2.x, a[k0]);
+        if (k0 + 1 < NMAX) a[k0 + 1] = fma(-lij, l2.y, a[k0 + 1]);
+      } else {
+        a[k0] = fma(-lij, A[k0 + j * LD], a[k0]);
       }
     }
   }
+  __syncwarp();
   return ok;
 }
 
@@ -193,7 +205,7 @@ __global__ void __launch_bounds__(32 * MjtjCfg<NV, NFM>::WARPS, 10) mjtjinv_kern
   for (int e = lane; e < NFM * NV; e += 32)
     if ((e % NFM) >= nf) sJ[e] = 0.0;
   __syncwarp();
-  if (!warp_cholesky_ld<NV>(sL, NV, NV, dinv)) bad |= 4;
+  if (!warp_cholesky_ld<NV, NV>(sL, NV, dinv)) bad |= 4;
   __syncwarp();
   if (lane < NV) {  // X = L^-1, one column per lane (forward substitution; rows above the diagonal stay zero)
     double x[NV];
@@ -218,7 +230,7 @@ __global__ void __launch_bounds__(32 * MjtjCfg<NV, NFM>::WARPS, 10) mjtjinv_kern
     warp_gemm<NFM, NFM, NV>([&](int ii, int k) { return sW[k + ii * NV]; }, [&](int k, int j) { return sW[k + j * NV]; },
                             [&](int ii, int j, double v) { sS[ii + j * NFM] = v; });
     __syncwarp();
-    if (!warp_cholesky_ld<NFM>(sS, NFM, nf, dinv)) bad |= 8;
+    if (!warp_cholesky_ld<NFM, NFM>(sS, nf, dinv)) bad |= 8;
     __syncwarp();
     if (lane < nf) {  // Y = Ls^-1
       double x[NFM];
