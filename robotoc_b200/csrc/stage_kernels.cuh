@@ -215,7 +215,11 @@ __global__ void __launch_bounds__(32 * MjtjCfg<NV, NFM>::WARPS, 10) mjtjinv_kern
     for (int k = 0; k < NV; ++k) {
       x[k] *= dinv[k];
 #pragma unroll
-      for (int a = k + 1; a < NV; ++a) x[a] = fma(-sL[a + k * NV], x[k], x[a]);
+      for (int a0 = (k + 1) & ~1; a0 < NV; a0 += 2) {  // column k of L, two rows per (16-byte, broadcast) load
+        const double2 l2 = *reinterpret_cast<const double2*>(sL + a0 + k * NV);
+        if (a0 > k) x[a0] = fma(-l2.x, x[k], x[a0]);
+        if (a0 + 1 < NV) x[a0 + 1] = fma(-l2.y, x[k], x[a0 + 1]);
+      }
     }
 #pragma unroll
     for (int a = 0; a < NV; ++a) sX[a + lane * NV] = x[a];
@@ -238,11 +242,14 @@ __global__ void __launch_bounds__(32 * MjtjCfg<NV, NFM>::WARPS, 10) mjtjinv_kern
       for (int a = 0; a < NFM; ++a) x[a] = (a == lane) ? 1.0 : 0.0;
 #pragma unroll
       for (int k = 0; k < NFM; ++k) {
-        if (k < nf) {
-          x[k] *= dinv[k];
+        // (rows / columns >= nf of Ls are the identity -- warp_cholesky_ld -- so the inactive part needs no predicate: it
+        //  stays e_lane there, and lanes >= nf do not run this block)
+        x[k] *= dinv[k];
 #pragma unroll
-          for (int a = k + 1; a < NFM; ++a)
-            if (a < nf) x[a] = fma(-sS[a + k * NFM], x[k], x[a]);
+        for (int a0 = (k + 1) & ~1; a0 < NFM; a0 += 2) {
+          const double2 l2 = *reinterpret_cast<const double2*>(sS + a0 + k * NFM);
+          if (a0 > k) x[a0] = fma(-l2.x, x[k], x[a0]);
+          if (a0 + 1 < NFM) x[a0 + 1] = fma(-l2.y, x[k], x[a0 + 1]);
         }
       }
 #pragma unroll
