@@ -978,8 +978,11 @@ __device__ __forceinline__ void atomic_min_pos(double* addr, double v) {  // v >
 // column of a mat-vec (lane = row, conflict-free) and the partial sums meet in shared memory.
 constexpr int XTHR = 128;
 
+#ifndef RBT_EXP_MIN_CTAS
+#define RBT_EXP_MIN_CTAS 10  // (48 registers, no spills; shared memory allows 10)
+#endif
 template <int NV, int NU, int NFM>
-__global__ void __launch_bounds__(XTHR) expand_kernel(const StageParams p) {
+__global__ void __launch_bounds__(XTHR, RBT_EXP_MIN_CTAS) expand_kernel(const StageParams p) {
   constexpr int NX = 2 * NV, NVF = NV + NFM, NTHR = XTHR;
   constexpr int RSZ = ((NVF * NX + 1) & ~1) + ((NVF + 1) & ~1);  // R | r (adjacent in the record)
   constexpr int ZSZ = NVF * NU;
@@ -1125,8 +1128,11 @@ __device__ __forceinline__ void integrate_free_flyer_dev(double* q, const double
   q[3] = nx_ * nrm; q[4] = ny * nrm; q[5] = nz * nrm; q[6] = nw * nrm;
 }
 
+#ifndef RBT_UPD_MIN_CTAS
+#define RBT_UPD_MIN_CTAS 12  // latency-bound streaming kernel: 12 CTAs/SM (40 registers) is 25 % faster than 8 (63 registers); 14: slower
+#endif
 template <int NV, int NU, int NFM>
-__global__ void __launch_bounds__(XTHR) update_kernel(const StageParams p) {
+__global__ void __launch_bounds__(XTHR, RBT_UPD_MIN_CTAS) update_kernel(const StageParams p) {
   constexpr int NX = 2 * NV, NVF = NV + NFM, NTHR = XTHR;
   constexpr int QSZ = NFM * NX + NFM * NV + ((NV + 1) & ~1);  // contact rows Qaf | Quf and diag(Qaa) (adjacent in the record)
   constexpr int ZSZ = (NVF * NVF + 1) & ~1;
