@@ -28,14 +28,34 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np  # noqa: E402
 
 N_HORIZON = 40
-# SURVEY.md 8(d) algorithmic figures per standard stage (doubles -> bytes)
-BYTES_PER_STAGE_BWD = (3468 + 1776) * 8      # backward reads 3468 + writes 1776
+# Algorithmic bytes per standard stage (doubles -> bytes): SURVEY.md 8(d)'s accounting, applied to what the kernels move today.
+BYTES_PER_STAGE_BWD = (3468 + 1776) * 8      # backward reads the 3468-double KKT record, writes P | s | K | k (1776)
 BYTES_PER_STAGE_FWD = (3324 + 84) * 8        # forward reads 3324 + writes 84
-BYTES_PER_STAGE_CONDENSE = (2100 + 3600) * 8 + (3468) * 8  # 8(d): condense reads ~2.1k, writes ~3.6k (+ the KKT record when not fused)
+# condense: 8(d) counts ~2.1k doubles read and ~3.6k written (expansion record) + the 3468-double KKT record (not fused with the
+# sweep).  Round 2 no longer stores the acceleration rows of Qafqv / Qafu (1620 -> 648 + 18 doubles): 3.6k -> 2646.
+BYTES_PER_STAGE_CONDENSE = (2100 + 2646 + 3468) * 8
+BYTES_PER_STAGE_CONDENSE_8D = 46 * 1024      # 8(d)'s literal per-stage figure (without the KKT record), for frac_8d_literal
 BYTES_PER_STAGE_MJTJINV = (324 + 216 + 900) * 8               # K1 reads M, J and writes Z
-# DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of one `ncu --set full` capture of this very command
-# at batch 1024 (profiles/r1_final_condense_kernel_ncu_summary.txt, profiles/r1_final_riccati_backward_kernel_ncu_summary.txt); scaled by batch/1024.
-NCU_TRAFFIC_1024 = {"condense": 1.865444e9 + 2.517468e9, "riccati_backward": 1.339999e9 + 0.670331e9}
+# whole iteration, per standard stage: linearisation 4234 read + KKT 3468 written and read back + Riccati 1776 written and
+# read back + expansion ~2.9k written, ~5k read by expand / update + direction / solution / PDIPM records
+BYTES_PER_STAGE_ITERATION = (4234 + 2 * 3468 + 2 * 1776 + 2900 + 5000 + 1500) * 8
+
+
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum (bytes per launch at batch 1024) of the committed `ncu --set full` capture of
+    this very command: profiles/r2_final_<kernel>_ncu_summary.txt."""
+    path = os.path.join(ROOT, "profiles", f"r2_final_{kernel}_kernel_ncu_summary.txt")
+    tot, unit = 0.0, {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+    try:
+        for line in open(path):
+            f = line.split()
+            if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                tot += float(f[1]) * unit[f[2]]
+    except OSError:
+        return None, None
+    return (tot or None), os.path.relpath(path, ROOT)
+
+
 FLOP_PER_STAGE_BWD = 285.7e3
 FLOP_PER_STAGE_CONDENSE = 300e3
 
@@ -542,6 +562,7 @@ def main():
         alg_bytes = {"riccati_backward": BYTES_PER_STAGE_BWD, "riccati_forward": BYTES_PER_STAGE_FWD,
                      "condense": BYTES_PER_STAGE_CONDENSE}.get(dom, BYTES_PER_STAGE_BWD) * units
         ach = alg_bytes / (kms[dom] * 1e-3) / 1e9
+        traffic, traffic_src = ncu_traffic(dom) if dom in ("condense", "riccati_backward") else (None, None)
         kname = {"riccati_backward": "riccati_backward_kernel<18,12,12>", "condense": "condense_kernel<18,12,12>",
                  "riccati_forward": "riccati_forward_kernel<18,12,12>"}.get(dom, dom)
         line = {
@@ -565,8 +586,12 @@ def main():
                             "wire": "rbt_iteration_host_wire (as resident, plus PDIPM slack|dual and the solution uploaded every step)",
                             "dense": "rbt_iteration_host (dense linearisation records)"}[e2e_mode]},
             "roofline": {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": (NCU_TRAFFIC_1024[dom] * args.batch / 1024) if dom in NCU_TRAFFIC_1024 else None,
-                         "traffic_source": "ncu --set full capture of this command, committed under profiles/ (per launch)",
+                         "traffic": (traffic * args.batch / 1024) if traffic else None,
+                         "traffic_source": f"dram__bytes_read + write of the ncu --set full capture of this command ({traffic_src}), per launch",
+                         "frac_8d_literal": (BYTES_PER_STAGE_CONDENSE_8D * units / (kms[dom] * 1e-3) / 1e9 / peak) if dom == "condense" else None,
+                         "iteration": {"algorithmic_bytes": BYTES_PER_STAGE_ITERATION * units,
+                                       "achieved": BYTES_PER_STAGE_ITERATION * units / (ms / args.steps * 1e-3) / 1e9,
+                                       "frac": BYTES_PER_STAGE_ITERATION * units / (ms / args.steps * 1e-3) / 1e9 / peak},
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                          "per_kernel_GBps": {
                              "riccati_backward": BYTES_PER_STAGE_BWD * units / (kms["riccati_backward"] * 1e-3) / 1e9,
