@@ -36,9 +36,9 @@ BYTES_PER_STAGE_FWD = (3324 + 84) * 8        # forward reads 3324 + writes 84
 BYTES_PER_STAGE_CONDENSE = (2100 + 2646 + 3468) * 8
 BYTES_PER_STAGE_CONDENSE_8D = 46 * 1024      # 8(d)'s literal per-stage figure (without the KKT record), for frac_8d_literal
 BYTES_PER_STAGE_MJTJINV = (324 + 216 + 900) * 8               # K1 reads M, J and writes Z
-# whole iteration, per standard stage: linearisation 4234 read + KKT 3468 written and read back + Riccati 1776 written and
-# read back + expansion ~2.9k written, ~5k read by expand / update + direction / solution / PDIPM records
-BYTES_PER_STAGE_ITERATION = (4234 + 2 * 3468 + 2 * 1776 + 2900 + 5000 + 1500) * 8
+# whole iteration, per standard stage: VERDICT r1's accounting (69.2 + 45.6 + 5 kB = stage layer + sweeps + small records),
+# minus the acceleration rows of Qafqv / Qafu that are no longer written by the condensing nor read by the update
+BYTES_PER_STAGE_ITERATION = int((69.2 + 45.6 + 5.0) * 1000) - 2 * (1620 - 666) * 8
 
 
 def ncu_traffic(kernel):

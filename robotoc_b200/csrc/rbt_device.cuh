@@ -106,6 +106,19 @@ __device__ __forceinline__ void warp_mma_band(double (&acc)[NT][2], int i0, FA f
     for (int n = 0; n < NT; ++n)
       if (n >= n_begin) b[n] = fb(k, tile_off(n, N) + g);
   };
+#ifdef RBT_MMA_NOPIPE  // A/B switch: one fragment set (NT + 1 fewer live doubles), loads of step ks issued right before its MMAs
+  {
+    double a, b[NT];
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      load(ks, a, b);
+#pragma unroll
+      for (int n = 0; n < NT; ++n)
+        if (n >= n_begin) dmma884(acc[n][0], acc[n][1], a, b[n]);
+    }
+    return;
+  }
+#endif
   double a0, b0[NT], a1, b1[NT];
   load(0, a0, b0);
 #ifdef RBT_MMA_ROLLED
