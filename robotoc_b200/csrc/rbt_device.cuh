@@ -88,7 +88,9 @@ __host__ __device__ constexpr int num_tiles(int M) { return (M + 7) / 8; }
 // One warp accumulates NT 8x8 tiles of one 8-row band:  acc[n] += sum_k A(i0+g, k) * B(k, joff(n)+g).
 //   fa(i, k) / fb(k, j) return the operand element (shared-memory loads).  K need not be a multiple of 4.
 // n_begin (warp-uniform): tiles n < n_begin are skipped (symmetric products: only the tiles on/above the diagonal band).
-template <int K, int NT, int N, class FA, class FB>
+// PIPE = false: one fragment set, the loads of k-step ks issued right before its MMAs (NT + 1 fewer live doubles) -- for the
+// register-starved backward sweep (80-register cap: the second fragment set only adds spills there; measured 4.5 % faster).
+template <int K, int NT, int N, bool PIPE = true, class FA, class FB>
 __device__ __forceinline__ void warp_mma_band(double (&acc)[NT][2], int i0, FA fa, FB fb, int n_begin = 0) {
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   constexpr int KS = (K + 3) / 4;
@@ -106,8 +108,7 @@ __device__ __forceinline__ void warp_mma_band(double (&acc)[NT][2], int i0, FA f
     for (int n = 0; n < NT; ++n)
       if (n >= n_begin) b[n] = fb(k, tile_off(n, N) + g);
   };
-#ifdef RBT_MMA_NOPIPE  // A/B switch: one fragment set (NT + 1 fewer live doubles), loads of step ks issued right before its MMAs
-  {
+  if constexpr (!PIPE) {
     double a, b[NT];
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
@@ -118,7 +119,6 @@ __device__ __forceinline__ void warp_mma_band(double (&acc)[NT][2], int i0, FA f
     }
     return;
   }
-#endif
   double a0, b0[NT], a1, b1[NT];
   load(0, a0, b0);
 #ifdef RBT_MMA_ROLLED

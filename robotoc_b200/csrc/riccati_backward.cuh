@@ -389,7 +389,7 @@ __global__ void __launch_bounds__(BwdCfg<NV, NU, NS, NP>::NTHREADS, RBT_BWD_MIN_
         for (int tile = warp; tile < TU * TV; tile += TX) {
           const int u0 = tile_off(tile / TV, NU), j0 = tile_off(tile % TV, NV);
           double acc[1][2] = {{0.0, 0.0}};
-          warp_mma_band<NV, 1, 8>(
+          warp_mma_band<NV, 1, 8, false>(
               acc, u0, [&](int u, int k) { return sB[k + u * NV]; },
               [&](int k, int jj) { return sP[(NV + k) + (NV + j0 + jj) * NX]; });
           *reinterpret_cast<double2*>(&sBp[(u0 + g) * NV + j0 + 2 * t]) = make_double2(acc[0][0], acc[0][1]);
@@ -410,12 +410,12 @@ __global__ void __launch_bounds__(BwdCfg<NV, NU, NS, NP>::NTHREADS, RBT_BWD_MIN_
             acc[n][0] = sc * pv.x;
             acc[n][1] = sc * pv.y;
           }
-          warp_mma_band<KR, TX, NX>(
+          warp_mma_band<KR, TX, NX, false>(
               acc, i0, [&](int ii, int k) { return sA[rho_of(k) + ii * NX]; }, [&](int k, int j) { return sP[rho_of(k) + j * NX]; });
         } else {
 #pragma unroll
           for (int n = 0; n < TX; ++n) acc[n][0] = acc[n][1] = 0.0;
-          warp_mma_band<NX, TX, NX>(
+          warp_mma_band<NX, TX, NX, false>(
               acc, i0, [&](int ii, int k) { return sA[k + ii * NX]; }, [&](int k, int j) { return sP[k + j * NX]; });
         }
 #pragma unroll
@@ -467,15 +467,15 @@ __global__ void __launch_bounds__(BwdCfg<NV, NU, NS, NP>::NTHREADS, RBT_BWD_MIN_
             cF[n][1] = fma(sc, av.y, cF[n][1]);
           }
         }
-        warp_mma_band<KR, TX, NX>(
+        warp_mma_band<KR, TX, NX, false>(
             cF, i0, [&](int ii, int k) { return sAtP[ii * NX + rho_of(k)]; }, [&](int k, int j) { return sA[rho_of(k) + j * NX]; }, nb0);
       } else {
-        warp_mma_band<NX, TX, NX>(
+        warp_mma_band<NX, TX, NX, false>(
             cF, i0, [&](int ii, int k) { return sAtP[ii * NX + k]; }, [&](int k, int j) { return sA[k + j * NX]; }, nb0);
       }
       RBT_TL(i, 4);
       if (!impact) {
-        warp_mma_band<NV, TU, NU>(
+        warp_mma_band<NV, TU, NU, false>(
             cH, i0, [&](int ii, int k) { return sAtP[ii * NX + NV + k]; }, [&](int k, int u) { return sB[k + u * NV]; });
         if (!plain || fct) {  // H in shared memory is only read by the switching-constraint (Schur) path
 #pragma unroll
@@ -527,7 +527,7 @@ __global__ void __launch_bounds__(BwdCfg<NV, NU, NS, NP>::NTHREADS, RBT_BWD_MIN_
 #pragma unroll
         for (int ub = 0; ub < TU; ++ub) {  // G = Quu + Bp Bv
           const int u0 = tile_off(ub, NU);
-          warp_mma_band<NV, TU, NU>(
+          warp_mma_band<NV, TU, NU, false>(
               cG[ub], u0, [&](int u, int k) { return sBp[u * NV + k]; }, [&](int k, int v) { return sB[k + v * NV]; });
 #pragma unroll
           for (int n = 0; n < TU; ++n) {
@@ -626,7 +626,7 @@ __global__ void __launch_bounds__(BwdCfg<NV, NU, NS, NP>::NTHREADS, RBT_BWD_MIN_
         // ================= phase D
         if (gemm_warp) {
           // F -= Y^T Y
-          warp_mma_band<NU, TX, NX>(
+          warp_mma_band<NU, TX, NX, false>(
               cF, i0, [&](int ii, int k) { return -sY[k + ii * NU]; }, [&](int k, int j) { return sY[k + j * NU]; }, nb0);
           // s = t1 + Y^T y            (== A^T z - lx - H k)
           matvec_T(sY, NU, NU, NX, ylu, tid, NG, [&](int c, double a) {
@@ -642,7 +642,7 @@ __global__ void __launch_bounds__(BwdCfg<NV, NU, NS, NP>::NTHREADS, RBT_BWD_MIN_
             double acc[TX][2];
 #pragma unroll
             for (int n = 0; n < TX; ++n) acc[n][0] = acc[n][1] = 0.0;
-            warp_mma_band<NU, TX, NX>(
+            warp_mma_band<NU, TX, NX, false>(
                 acc, u0, [&](int u, int k) { return -sLi[k + u * NU]; }, [&](int k, int j) { return sY[k + j * NU]; });
 #pragma unroll
             for (int n = 0; n < TX; ++n) {
@@ -816,7 +816,7 @@ __global__ void __launch_bounds__(BwdCfg<NV, NU, NS, NP>::NTHREADS, RBT_BWD_MIN_
         __syncthreads();
         if (gemm_warp) {
           // F -= K^T (G K)                                                                   backward_..factorizer.cpp:83
-          warp_mma_band<NU, TX, NX>(
+          warp_mma_band<NU, TX, NX, false>(
               cF, i0, [&](int ii, int k) { return -sKt[ii + k * NX]; }, [&](int k, int j) { return sY[k + j * NU]; });
           if (fct) {  // the reference leaves Qxx = F - K^T G K here; spill it before the constraint correction
 #pragma unroll
@@ -827,7 +827,7 @@ __global__ void __launch_bounds__(BwdCfg<NV, NU, NS, NP>::NTHREADS, RBT_BWD_MIN_
             }
           }
           // P = sym(F) - KtDtM - KtDtM^T = sym(F - 2 K^T DtM)                                 riccati_factorizer.cpp:85-87
-          warp_mma_band<NU, TX, NX>(
+          warp_mma_band<NU, TX, NX, false>(
               cF, i0, [&](int ii, int k) { return -2.0 * sKt[ii + k * NX]; }, [&](int k, int j) { return DtM[k + j * NU]; });
         }
         if (sto) {
