@@ -155,5 +155,5 @@ def test_cuda_line_search_matches_the_oracle(which, batch):
         got_step, got_k = ls.computeStepSize(cost0, viol0, lambda tr, a: (cost, viol))
         want_step, want_k = _filter_oracle(lib, steps, cost0.copy(), viol0.copy(), cost, np.ascontiguousarray(bar), viol, filt, nfilt)
         np.testing.assert_array_equal(got_k, want_k)
-        np.testing.assert_allclose(got_step, want_step, rtol=1e-15)
+        np.testing.assert_allclose(got_step, want_step, rtol=1e-12)  # alpha_max comes from the device / the oracle: equal to rounding
     rr.close()
