@@ -52,7 +52,10 @@ typedef struct rbt_stage_ctrl {
   int ngrids_in_phase; /* GridInfo::num_grids_in_phase */
   int contact_mask;    /* bit c set: point contact c is active in this stage's phase (ContactStatus::isContactActive);
                           on an Impact stage: the contacts of the ImpactStatus */
-  int reserved_;
+  int ineq_gate;       /* which inequality levels act on this grid point (ConstraintsData::setTimeStage, constraints_data.cpp:20-45):
+                          0 = all; 1 = no position-level limits (GridInfo::stage == 1); 2 = neither position- nor velocity-level
+                          (GridInfo::stage == 0).  = max(0, 2 - GridInfo::stage); acceleration-level rows (torque limits,
+                          friction cones) always act */
   double dt;           /* GridInfo::dt */
 } rbt_stage_ctrl;
 

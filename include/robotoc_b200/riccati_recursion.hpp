@@ -45,6 +45,8 @@ struct GridInfo {  // grid_info.hpp:25-92 (fields read on this path)
   int dimf = 0;  // active contact dimension
   int contact_mask = -1;  // bit per point contact that is closed on this grid (ContactStatus::isContactActive); must be given
                           // whenever dimf > 0 -- the library never guesses which feet are on the ground
+  int stage = -1;         // GridInfo::stage (index of the grid point): the reference gates the position- / velocity-level
+                          // inequality constraints on stages 0 and 1 with it; -1 = all levels act
 };
 using TimeDiscretization = std::vector<GridInfo>;  // size() == N+1 grid points, last one Terminal
 
@@ -262,7 +264,7 @@ class RiccatiRecursion {
       if (td[i].contact_mask < 0 && td[i].dimf > 0)
         throw std::invalid_argument("[RiccatiRecursion] invalid argument: GridInfo::contact_mask must be set when dimf > 0");
       c.contact_mask = td[i].contact_mask < 0 ? 0 : td[i].contact_mask;
-      c.reserved_ = 0;
+      c.ineq_gate = td[i].stage < 0 ? 0 : (td[i].stage >= 2 ? 0 : 2 - td[i].stage);  // constraints_data.cpp:20-45
       c.dt = td[i].dt;
     }
     check(rbt_set_schedule(h_, ctrl_.data(), int(td.size()), max_dts0_));

@@ -135,6 +135,14 @@ static double* var_ptr(double* q, double* v, double* a, double* u, int var) {
   return var == RBT_VAR_Q ? q : var == RBT_VAR_V ? v : var == RBT_VAR_A ? a : u;
 }
 
+/* Does box row r act on this grid point?  Box limits never act on impact stages (constraints.cpp:347-354), and the position- /
+ * velocity-level limits not on the first two grid points: ConstraintsData::setTimeStage (constraints_data.cpp:20-45) validates the
+ * position level from GridInfo::stage >= 2, the velocity level from >= 1 (c->ineq_gate = max(0, 2 - stage)). */
+static inline int box_row_on(const rbt_constraint_table* tab, const rbt_stage_ctrl* c, int r) {
+  const int level = tab->box[r].var == RBT_VAR_Q ? 2 : (tab->box[r].var == RBT_VAR_V ? 1 : 0);
+  return c->type != RBT_IMPACT && level + c->ineq_gate <= 2;
+}
+
 /*
  * One stage of "Forms linear system" (intermediate_stage.cpp:133-148 / impact_stage.cpp:115-121 / terminal_stage.cpp:102-106):
  *   pdipm::computeComplementarySlackness + Constraints::condenseSlackAndDual      pdipm.hxx:27-100, joint_*_limit.cpp:68-83,
@@ -199,7 +207,8 @@ int orc_stage_condense(const rbt_stage_dims* sd, const rbt_constraint_table* tab
     double* cond = con + S.c_cond;
     double* lq = lx;
     double* lv = lx + nv;
-    for (int r = 0; r < (impact ? 0 : tab->n_box); ++r) {
+    for (int r = 0; r < tab->n_box; ++r) {
+      if (!box_row_on(tab, c, r)) continue;
       const rbt_box_row* b = &tab->box[r];
       cmpl[r] = slack[r] * dual[r] - tab->barrier;                         /* pdipm.hxx:27-31 */
       cond[r] = (dual[r] * res[r] - cmpl[r]) / slack[r];                   /* pdipm.hxx:66-70 */
@@ -474,7 +483,8 @@ void orc_stage_expand_primal(const rbt_stage_dims* sd, const rbt_constraint_tabl
   double* ddual = con + S.c_ddual;
   double* dq = (double*)dx;
   double* dv = (double*)dx + nv;
-  for (int r = 0; r < (impact ? 0 : tab->n_box); ++r) {
+  for (int r = 0; r < tab->n_box; ++r) {
+    if (!box_row_on(tab, c, r)) continue;
     const rbt_box_row* b = &tab->box[r];
     const double* var = var_ptr(dq, dv, daf, (double*)du, b->var);
     dslack[r] = -b->sign * var[b->idx] - res[r];                                                          /* joint_*_limit.cpp:78-82 */
@@ -496,9 +506,16 @@ void orc_stage_expand_primal(const rbt_stage_dims* sd, const rbt_constraint_tabl
     }
     fstack += 3;
   }
-  const int r0 = impact ? tab->n_box : 0;                     /* an impact stage only has the cone rows (impact_friction_cone.cpp:238-268) */
-  steps[0] = fraction_to_boundary(S.nc - r0, tab->fraction_to_boundary, slack + r0, dslack + r0);
-  steps[1] = fraction_to_boundary(S.nc - r0, tab->fraction_to_boundary, dual + r0, ddual + r0);
+  /* rows that do not act on this grid point (box rows of an impact stage, gated levels) take no part: maxSlackStepSize /
+   * maxDualStepSize only visit the valid levels (constraints.cpp:397-440) */
+  steps[0] = 1.0; steps[1] = 1.0;
+  for (int r = 0; r < S.nc; ++r) {
+    if (r < tab->n_box && !box_row_on(tab, c, r)) continue;
+    const double fp = fraction_to_boundary(1, tab->fraction_to_boundary, slack + r, dslack + r);
+    const double fd = fraction_to_boundary(1, tab->fraction_to_boundary, dual + r, ddual + r);
+    if (fp < steps[0]) steps[0] = fp;
+    if (fd < steps[1]) steps[1] = fd;
+  }
 }
 
 /* free-flyer part of Robot::integrateConfiguration: q(p, quat xyzw) <- q (+) step*dq, textbook SE(3) exponential */
@@ -628,7 +645,8 @@ void orc_stage_expand_dual_update(const rbt_stage_dims* sd, const rbt_constraint
     if (ns > 0)
       for (int i = 0; i < ns; ++i) sol[S.s_xi + i] += a_ * d[K.d_dxi + i];
     if (!impact || tab->impact_friction_cone) {
-      for (int r = impact ? S.nbox : 0; r < S.nc; ++r) {
+      for (int r = 0; r < S.nc; ++r) {
+        if (r < S.nbox && !box_row_on(tab, c, r)) continue;
         con[S.c_slack + r] += primal_step * con[S.c_dslack + r];
         con[S.c_dual + r] += dual_step * con[S.c_ddual + r];
       }
@@ -841,9 +859,10 @@ void orc_stage_perf_index(const rbt_stage_dims* sd, const rbt_constraint_table* 
       ORC_ACC_P(lin + S.l_p, c->ns)
     }
     if (!impact || tab->impact_friction_cone) {
-      for (int r = impact ? S.nbox : 0; r < S.nc; ++r) {
+      for (int r = 0; r < S.nc; ++r) {
         const int cone = r >= S.nbox;
         if (cone && !((c->contact_mask >> ((r - S.nbox) / 5)) & 1)) continue;  /* inactive contact: residual = cmpl = 0 */
+        if (!cone && !box_row_on(tab, c, r)) continue;                         /* level not valid on this grid point */
         const double sl = con[S.c_slack + r], du = con[S.c_dual + r], res = con[S.c_res + r];
         const double cm = sl * du - tab->barrier;
         kkt += res * res + cm * cm;
@@ -889,7 +908,8 @@ void orc_set_slack_dual_positive_batch(const rbt_stage_dims* sd, const rbt_const
     for (int i = 0; i < n_grid; ++i) {
       if (ctrl[i].type == RBT_TERMINAL || (ctrl[i].type == RBT_IMPACT && !tab->impact_friction_cone)) continue;
       double* cc = con + ((size_t)b * n_grid + i) * S.c_stride;
-      for (int r = (ctrl[i].type == RBT_IMPACT) ? S.nbox : 0; r < S.nc; ++r) {
+      for (int r = 0; r < S.nc; ++r) {
+        if (r < S.nbox && !box_row_on(tab, &ctrl[i], r)) continue;
         if (cc[S.c_slack + r] < sb) cc[S.c_slack + r] = sb;
         cc[S.c_dual + r] = tab->barrier / cc[S.c_slack + r];
       }
@@ -957,8 +977,9 @@ void orc_stage_trial(const rbt_stage_dims* sd, const rbt_constraint_table* tab, 
   for (int i = 0; i < c->nf; ++i) trial[ORC_T_F + i] = sol[S.s_f + i] + alpha * daf[nv + i];
   if (!impact || tab->impact_friction_cone) {
     double lb = 0.0;
-    for (int r = impact ? S.nbox : 0; r < S.nc; ++r) {
+    for (int r = 0; r < S.nc; ++r) {
       if (r >= S.nbox && !((c->contact_mask >> ((r - S.nbox) / 5)) & 1)) continue;
+      if (r < S.nbox && !box_row_on(tab, c, r)) continue;
       lb -= tab->barrier * log(con[S.c_slack + r] + alpha * con[S.c_dslack + r]);
     }
     *out_barrier = lb;

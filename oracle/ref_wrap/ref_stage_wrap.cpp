@@ -183,7 +183,10 @@ int ref_stage(const rbt_stage_dims* sd, const rbt_constraint_table* tab, const r
   }
   // ---- constraints: slack, dual, residual from the PDIPM record; cmpl as evalConstraint leaves it (pdipm.hxx:27-63)
   std::shared_ptr<Constraints> constraints = make_constraints(robot, tab);
-  ConstraintsData cdata = constraints->createConstraintsData(robot, impact ? -1 : 2);
+  // GridInfo::stage decides which constraint levels act (ConstraintsData::setTimeStage, constraints_data.cpp:20-45); the control
+  // word carries max(0, 2 - stage)
+  ConstraintsData cdata = constraints->createConstraintsData(robot, impact ? -1 : 2 - c->ineq_gate);
+  auto comp_valid = [&](int k) { return k >= 4 || (k >= 2 ? c->ineq_gate <= 1 : c->ineq_gate == 0); };
   const int nj = nu;  // rows per joint-limit component
   if (!impact) {
     for (int k = 0; k < 7; ++k) {
@@ -280,6 +283,7 @@ int ref_stage(const rbt_stage_dims* sd, const rbt_constraint_table* tab, const r
       get_v(cd.lu_passive, ex + S.e_lup, np);
     }
     for (int k = 0; k < 7; ++k) {
+      if (!comp_valid(k)) continue;  // the reference does not touch the data of a level that is not valid on this grid point
       ConstraintComponentData& cc = component(cdata, k);
       const int off = k * nj, n = (k < 6) ? nj : 5 * tab->n_contacts;
       get_v(cc.cmpl, con + S.c_cmpl + off, n);
@@ -315,6 +319,7 @@ int ref_stage(const rbt_stage_dims* sd, const rbt_constraint_table* tab, const r
   steps_stage[1] = constraints->maxDualStepSize(cdata);
   if (!impact)
     for (int k = 0; k < 7; ++k) {
+      if (!comp_valid(k)) continue;
       ConstraintComponentData& cc = component(cdata, k);
       const int off = k * nj, n = (k < 6) ? nj : 5 * tab->n_contacts;
       get_v(cc.dslack, con + S.c_dslack + off, n);
@@ -345,6 +350,7 @@ int ref_stage(const rbt_stage_dims* sd, const rbt_constraint_table* tab, const r
     Constraints::updateSlack(cdata, alpha_p);
     Constraints::updateDual(cdata, alpha_d);
     for (int k = 0; k < 7; ++k) {
+      if (!comp_valid(k)) continue;
       ConstraintComponentData& cc = component(cdata, k);
       const int off = k * nj, n = (k < 6) ? nj : 5 * tab->n_contacts;
       get_v(cc.slack, con + S.c_slack + off, n);

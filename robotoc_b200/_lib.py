@@ -16,7 +16,7 @@ class rbt_dims(ctypes.Structure):
 class rbt_stage_ctrl(ctypes.Structure):
     _fields_ = [("type", ctypes.c_int), ("sto", ctypes.c_int), ("sto_next", ctypes.c_int), ("ns", ctypes.c_int),
                 ("nf", ctypes.c_int), ("ngrids_in_phase", ctypes.c_int), ("contact_mask", ctypes.c_int),
-                ("reserved_", ctypes.c_int), ("dt", ctypes.c_double)]
+                ("ineq_gate", ctypes.c_int), ("dt", ctypes.c_double)]
 
 
 _lib = None

@@ -64,6 +64,7 @@ __global__ void __launch_bounds__(128) perf_index_kernel(const EvalParams q) {
       for (int r = lane + (impact ? S.nbox : 0); r < S.nc; r += 32) {
         const bool cone = r >= S.nbox;
         if (cone && !((c.contact_mask >> ((r - S.nbox) / 5)) & 1)) continue;
+        if (!cone && __ldg(p.row_level + r) + c.ineq_gate > 2) continue;  // level not valid on this grid point
         const double sl = con[S.c_slack + r], du = con[S.c_dual + r], res = con[S.c_res + r];
         const double cm = sl * du - mu;
         kkt = fma(res, res, kkt);
@@ -112,6 +113,7 @@ __global__ void slack_dual_positive_kernel(const EvalParams q) {
   const int i = int(st % p.n_grid);
   const int type = p.ctrl[i].type;
   if (r >= S.nc || type == RBT_TERMINAL || (type == RBT_IMPACT && (p.tab.impact_friction_cone == 0 || r < S.nbox))) return;
+  if (r < S.nbox && __ldg(p.row_level + r) + p.ctrl[i].ineq_gate > 2) return;  // level not valid on this grid point
   double* con = p.con + size_t(st) * S.c_stride;
   const double sb = sqrt(p.tab.barrier);
   const double sl = fmax(con[S.c_slack + r], sb);

@@ -67,6 +67,7 @@ __global__ void __launch_bounds__(128) trial_solution_kernel(const TrialParams q
     if (!impact || p.tab.impact_friction_cone != 0) {
       for (int r = lane + (impact ? S.nbox : 0); r < S.nc; r += 32) {
         if (r >= S.nbox && !((c.contact_mask >> ((r - S.nbox) / 5)) & 1)) continue;
+        if (r < S.nbox && __ldg(p.row_level + r) + c.ineq_gate > 2) continue;
         lb -= p.tab.barrier * log(con[S.c_slack + r] + alpha * con[S.c_dslack + r]);
       }
     }

@@ -264,9 +264,11 @@ int rbt_set_schedule(rbt_handle* h, const rbt_stage_ctrl* ctrl, int n_grid, doub
     const int nf_max = 3 * RBT_MAX_CONTACTS;
     if (c.nf < 0 || c.nf > nf_max || c.nf % 3 != 0 || c.contact_mask < 0 || c.contact_mask >= (1 << RBT_MAX_CONTACTS) ||
         3 * __builtin_popcount((unsigned)c.contact_mask) != c.nf || c.ngrids_in_phase < 0 || !(c.dt >= 0.0) ||
-        !(c.dt < 1.0e300) || (c.sto != 0 && c.sto != 1) || (c.sto_next != 0 && c.sto_next != 1)) {
+        !(c.dt < 1.0e300) || (c.sto != 0 && c.sto != 1) || (c.sto_next != 0 && c.sto_next != 1) || c.ineq_gate < 0 ||
+        c.ineq_gate > 2) {
       h->err = "[rbt_set_schedule] invalid argument: grid " + std::to_string(i) +
-               ": need 0 <= nf <= 12, nf % 3 == 0, 3 * popcount(contact_mask) == nf, ngrids_in_phase >= 0, finite dt >= 0";
+               ": need 0 <= nf <= 12, nf % 3 == 0, 3 * popcount(contact_mask) == nf, ngrids_in_phase >= 0, finite dt >= 0, "
+               "ineq_gate in {0, 1, 2}";
       return RBT_ERR_ARG;
     }
     if (c.type == RBT_IMPACT && c.ns != 0) {
@@ -711,8 +713,13 @@ int rbt_stage_setup(rbt_handle* h, const rbt_stage_dims* sd, const rbt_constrain
           break;
         }
     }
-    RBT_CUDA(h, cudaMalloc(&h->d_tgt, sizeof(tg)));
+    // ... followed by the level of every box row (2 = position, 1 = velocity, 0 = acceleration / torque): a row acts on a grid
+    // point iff level + ineq_gate <= 2 (ConstraintsData::setTimeStage)
+    int lvl[RBT_MAX_BOX_ROWS] = {};
+    for (int r = 0; r < h->table.n_box; ++r) lvl[r] = h->table.box[r].var == RBT_VAR_Q ? 2 : (h->table.box[r].var == RBT_VAR_V ? 1 : 0);
+    RBT_CUDA(h, cudaMalloc(&h->d_tgt, sizeof(tg) + sizeof(lvl)));
     RBT_CUDA(h, cudaMemcpy(h->d_tgt, tg, sizeof(tg), cudaMemcpyHostToDevice));
+    RBT_CUDA(h, cudaMemcpy(h->d_tgt + RBT_MAX_TARGETS * 4, lvl, sizeof(lvl), cudaMemcpyHostToDevice));
   }
   RBT_CUDA(h, cudaMemset(h->d_perf, 0, size_t(h->batch) * 8 * 8));
   RBT_CUDA(h, cudaMemset(h->d_lin, 0, per * h->S.l_stride * 8));  // uploads skip record padding: keep it defined
@@ -747,6 +754,7 @@ static rbt::StageParams make_stage_params(rbt_handle* h) {
   p.steps = h->d_steps + 2 * size_t(b0);
   p.info = h->d_info + b0;
   p.tgt = reinterpret_cast<const int4*>(h->d_tgt);
+  p.row_level = h->d_tgt + RBT_MAX_TARGETS * 4;
   return p;
 }
 

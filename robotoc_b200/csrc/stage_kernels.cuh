@@ -40,6 +40,7 @@ struct StageParams {
   int* info;
   const int4* tgt;  // [RBT_MAX_TARGETS] box rows acting on target (var, idx) = var*nv + idx (u: 3*nv + idx), ascending:
                     // (row + 1) * sign of the row, 0 = none
+  const int* row_level;  // [n_box] 2 = position-, 1 = velocity-, 0 = acceleration-level row: acts iff level + ctrl.ineq_gate <= 2
 };
 
 // C(m x n, ld ldc) = beta*C + alpha * op(A) op(B); all operands in shared (or global) memory; every thread of the CTA calls.
@@ -460,7 +461,9 @@ __global__ void __launch_bounds__(CondCfg<NV, NU, NFM>::NTHREADS, RBT_COND_MIN_C
     const double mu = p.tab.barrier;
     for (int r = tid; r < nc; r += NTHR) {  // pdipm.hxx:27-100
       const bool cone = r >= nbox;
-      if (impact && !cone) {  // box limits do not act on impact stages: no weight, no gradient, record untouched
+      if (!cone && (impact || __ldg(p.row_level + r) + c.ineq_gate > 2)) {
+        // box limits do not act on impact stages, position- / velocity-level limits not on the first two grid points
+        // (constraints_data.cpp:20-45): no weight, no gradient, record untouched
         cW[r] = 0.0;
         cC[r] = 0.0;
         continue;
@@ -1050,7 +1053,7 @@ __global__ void __launch_bounds__(XTHR, RBT_EXP_MIN_CTAS) expand_kernel(const St
   const double tau = p.tab.fraction_to_boundary;
   double mp = 1.0, md = 1.0;
   for (int r = tid; r < S.nc; r += NTHR) {
-    if (impact && r < nbox) continue;
+    if (r < nbox && (impact || __ldg(p.row_level + r) + c.ineq_gate > 2)) continue;  // row does not act here: record untouched
     const double c_sl = sC[r], c_du = sC[ncp + r], c_res = sC[2 * ncp + r], c_cm = sC[3 * ncp + r];
     double dsl, ddu;
     if (r < nbox) {
@@ -1175,6 +1178,7 @@ __global__ void __launch_bounds__(XTHR, RBT_UPD_MIN_CTAS) update_kernel(const St
     for (int e = tid; e < NV; e += NTHR) sdgn[e] = d[K.d_stride + K.d_dlmdgmm + NV + e];  // dgmm of stage i+1 (not modified here)
   if (!terminal && (!impact || p.tab.impact_friction_cone != 0)) {
     for (int r = tid + (impact ? p.tab.n_box : 0); r < S.nc; r += NTHR) {  // updateSlack / updateDual    constraint_component_base.hxx:25-36
+      if (r < p.tab.n_box && __ldg(p.row_level + r) + c.ineq_gate > 2) continue;  // level not valid on this grid point
       con[S.c_slack + r] += ap * con[S.c_dslack + r];
       con[S.c_dual + r] += ad * con[S.c_ddual + r];
     }

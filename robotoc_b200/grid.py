@@ -45,4 +45,5 @@ def plain_schedule(N: int, dt: float, nf: int = 0, contact_mask: int = None):
         arr[i].nf = nf
         arr[i].contact_mask = contact_mask
         arr[i].ngrids_in_phase = N if i < N else 0
+        arr[i].ineq_gate = max(0, 2 - i) if i < N else 0  # position- / velocity-level limits act from stage 2 / 1 on
     return arr

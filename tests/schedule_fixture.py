@@ -245,6 +245,7 @@ def stage_ctrl_array(td: TimeDiscretization, ev: ContactEvents):
             c.contact_mask = ev.phase_mask[gi.phase] if gi.phase < len(ev.phase_mask) else 0
         c.ngrids_in_phase = gi.num_grids_in_phase
         c.dt = gi.dt
+        c.ineq_gate = max(0, 2 - gi.stage) if gi.type in (INTERMEDIATE, LIFT) else 0  # ConstraintsData::setTimeStage(grid.stage)
     return arr
 
 

@@ -66,6 +66,10 @@ def _numpy_perf(S, table, ctrl, lin, con):
         act = np.ones(S.nc, dtype=bool)
         if c.type == IMPACT:
             act[:S.nbox] = False  # impact stages only carry the ImpactFrictionCone rows
+        for r in range(S.nbox):  # ConstraintsData::setTimeStage: position level from stage 2, velocity level from stage 1 on
+            level = {0: 2, 1: 1}.get(table.box[r].var, 0)
+            if level + c.ineq_gate > 2:
+                act[r] = False
         for ci in range(S.ncon):
             if not (c.contact_mask >> ci) & 1:
                 act[S.nbox + 5 * ci:S.nbox + 5 * ci + 5] = False
@@ -100,11 +104,12 @@ def test_oracle_set_slack_and_dual_positive_and_initial_state_direction():
     for i, c in enumerate(ctrl):
         if c.type in (IMPACT, TERMINAL):
             continue
+        on = np.array([r >= S.nbox or {0: 2, 1: 1}.get(table.box[r].var, 0) + c.ineq_gate <= 2 for r in range(S.nc)])
         sl = np.maximum(want[:, i, S.c_slack:S.c_slack + S.nc], sb)
-        want[:, i, S.c_slack:S.c_slack + S.nc] = sl
-        want[:, i, S.c_dual:S.c_dual + S.nc] = table.barrier / sl
+        want[:, i, S.c_slack:S.c_slack + S.nc] = np.where(on, sl, want[:, i, S.c_slack:S.c_slack + S.nc])
+        want[:, i, S.c_dual:S.c_dual + S.nc] = np.where(on, table.barrier / sl, want[:, i, S.c_dual:S.c_dual + S.nc])
     np.testing.assert_array_equal(con, want)
-    assert (con[:, :-1, S.c_slack:S.c_slack + S.nc][:, [i for i, c in enumerate(ctrl[:-1]) if c.type != IMPACT]] >= sb).all()
+    assert (con[:, 2:-1, S.c_slack:S.c_slack + S.nc][:, [i - 2 for i, c in enumerate(ctrl[:-1]) if i >= 2 and c.type != IMPACT]] >= sb).all()
     # initial state direction: dq[0:6] = -Fqq_prev_inv dq_raw[0:6], dv = v0 - v
     ex0 = rng.uniform(-1, 1, size=S.e_stride)
     dq_raw, v0 = rng.uniform(-1, 1, size=18), rng.uniform(-1, 1, size=18)

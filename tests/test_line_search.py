@@ -112,6 +112,9 @@ def test_oracle_trial_zero_is_the_primal_part_of_the_update(impact_cones):
         act = np.ones(S.nc, dtype=bool)
         if c.type == IMPACT:
             act[:S.nbox] = False
+        for r in range(S.nbox):
+            if {0: 2, 1: 1}.get(table.box[r].var, 0) + c.ineq_gate > 2:
+                act[r] = False
         for ci in range(S.ncon):
             if not (c.contact_mask >> ci) & 1:
                 act[S.nbox + 5 * ci:S.nbox + 5 * ci + 5] = False
