@@ -87,7 +87,14 @@ ConstraintComponentData& component(ConstraintsData& d, int k) {
 }
 }  // namespace
 
+// {cost_barrier, primal_feasibility, dual_feasibility, kkt_error} of the last ref_stage call, summarised BEFORE "Forms linear
+// system" with the reference's own member functions, exactly as {Intermediate,Impact,Terminal}Stage::evalKKT do
+// (intermediate_stage.cpp:124-132, impact_stage.cpp:104-113, terminal_stage.cpp:94-100)
+static double g_last_perf[4] = {0, 0, 0, 0};
+
 extern "C" {
+
+void ref_last_perf(double* out) { for (int q = 0; q < 4; ++q) out[q] = g_last_perf[q]; }
 
 // Returns 0.  phase: 1 = condensing only, 2 = + primal expansion and step sizes, 3 = + dual expansion and slack / dual update.
 // con: slack | dual | residual in; cmpl, cond, dslack, ddual and the updated slack | dual out.  d is updated like the reference
@@ -114,6 +121,14 @@ int ref_stage(const rbt_stage_dims* sd, const rbt_constraint_table* tab, const r
     if (np == 6) put_m(se.Fqq_prev.topLeftCorner(6, 6), lin + S.l_se3 + 36, 6, 6, 6);
     correctLinearizeTerminalStateEquation(se, km);
     if (np == 6) get_m(se.Fqq_prev_inv, ex + S.e_Fqqpi, 6, 6, 6);
+    {  // terminal_stage.cpp:94-100: only the cost gradient lx (the state-equation residual of the last interval lives on N-1)
+      SplitKKTResidual krT(robot);
+      put_v(krT.lx, lin + S.l_lx, nx);
+      g_last_perf[0] = 0.0;
+      g_last_perf[1] = krT.primalFeasibility<1>();
+      g_last_perf[2] = krT.dualFeasibility<1>();
+      g_last_perf[3] = krT.KKTError();
+    }
     steps_stage[0] = steps_stage[1] = 1.0;
     if (phase >= 3) {
       SplitDirection dd(robot);
@@ -228,6 +243,18 @@ int ref_stage(const rbt_stage_dims* sd, const rbt_constraint_table* tab, const r
       put_m(cc.J[ci], lin + S.l_dgdq + size_t(ci) * 5 * nv, 5, nv, 5);
       put_m(cc.J[tab->n_contacts + ci], lin + S.l_dgdf + size_t(ci) * 15, 5, 3, 5);
     }
+  }
+  {  // PerformanceIndex as evalKKT summarises it before condensing: log barrier per valid component (what evalConstraint
+     // accumulates, constraint_component_base / friction_cone.cpp:122-139), then the members of OCPData and SplitKKTResidual
+    for (int k = 0; k < 6; ++k) component(cdata, k).log_barrier = pdipm::logBarrier(tab->barrier, component(cdata, k).slack);
+    ConstraintComponentData& cone = impact ? (icone ? cdata.impact_level_data[0] : component(cdata, 6)) : component(cdata, 6);
+    cone.log_barrier = 0.0;
+    for (int ci = 0; ci < tab->n_contacts; ++ci)
+      if ((c->contact_mask >> ci) & 1) cone.log_barrier += pdipm::logBarrier(tab->barrier, cone.slack.template segment<5>(5 * ci));
+    g_last_perf[0] = cdata.logBarrier();
+    g_last_perf[1] = cdata.primalFeasibility<1>() + cd.primalFeasibility<1>() + kr.primalFeasibility<1>();
+    g_last_perf[2] = cdata.dualFeasibility<1>() + cd.dualFeasibility<1>() + kr.dualFeasibility<1>();
+    g_last_perf[3] = cdata.KKTError() + cd.KKTError() + kr.KKTError();
   }
   // ---- "Forms linear system"
   SplitSolution s_dummy(robot), s_next_dummy(robot);

@@ -18,7 +18,7 @@ from robotoc_b200.stage import StageDims, anymal_constraint_table  # noqa: E402
 from synth import make_stage_inputs  # noqa: E402
 
 SEED, BATCH = 301, 1
-KEYS = ("kkt", "cc_cond", "ric", "d", "cc_exp", "xd_exp", "steps", "d_upd", "xd_upd", "cc_upd", "ex_upd")
+KEYS = ("kkt", "cc_cond", "ric", "d", "cc_exp", "xd_exp", "steps", "d_upd", "xd_upd", "cc_upd", "ex_upd", "perf_stage")
 
 
 def problem(S_getter=None, K_getter=None, impact_cones=False):

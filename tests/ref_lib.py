@@ -92,7 +92,10 @@ def stage(sd, table, c, lin, con, d, d_next, alpha_p, alpha_d, phase=3):
     rc = lib.ref_stage(ctypes.byref(csd), ctypes.byref(table), ctypes.byref(c), _ptr(np.ascontiguousarray(lin)), _ptr(cc), _ptr(kkt),
                        _ptr(ex), _ptr(dd), _ptr(dn), _ptr(xd), _ptr(steps), alpha_p, alpha_d, phase)
     assert rc == 0
-    return dict(kkt=kkt, ex=ex, con=cc, d=dd, xd=xd, steps=steps)
+    perf = np.zeros(4)  # {cost_barrier, primal_feasibility, dual_feasibility, kkt_error} as the stage's evalKKT summarises them
+    lib.ref_last_perf.argtypes = [ctypes.c_void_p]
+    lib.ref_last_perf(_ptr(perf))
+    return dict(kkt=kkt, ex=ex, con=cc, d=dd, xd=xd, steps=steps, perf=perf)
 
 
 def reference_iteration(sd, S, K, table, ctrl, lin, con, dx0):
@@ -107,11 +110,13 @@ def reference_iteration(sd, S, K, table, ctrl, lin, con, dx0):
     kkt = np.zeros((batch, n_grid, K.k_stride))
     ex = np.zeros((batch, n_grid, S.e_stride))
     cc_cond = con.copy()
+    perf_stage = np.zeros((batch, n_grid, 4))
     zero_d = np.zeros(K.d_stride)
     for b in range(batch):
         for i, c in enumerate(ctrl):
             o = stage(sd, table, c, lin[b, i], con[b, i], zero_d, zero_d, 1.0, 1.0, phase=1)
             kkt[b, i], ex[b, i], cc_cond[b, i] = o["kkt"], o["ex"], o["con"]
+            perf_stage[b, i] = o["perf"]
     kk, ric, d = riccati_batch(ANYMAL, K, ctrl, kkt, dx0)
     steps = np.ones((batch, 2))
     cc_exp, xd_exp = con.copy(), np.zeros((batch, n_grid, S.x_stride))
@@ -129,4 +134,4 @@ def reference_iteration(sd, S, K, table, ctrl, lin, con, dx0):
             o = stage(sd, table, c, lin[b, i], con[b, i], d[b, i], dn, steps[b, 0], steps[b, 1], phase=3)
             d_upd[b, i], xd_upd[b, i], cc_upd[b, i], ex_upd[b, i] = o["d"], o["xd"], o["con"], o["ex"]
     return dict(kkt=kkt, cc_cond=cc_cond, ric=ric, d=d, cc_exp=cc_exp, xd_exp=xd_exp, steps=steps, d_upd=d_upd, xd_upd=xd_upd,
-                cc_upd=cc_upd, ex_upd=ex_upd)
+                cc_upd=cc_upd, ex_upd=ex_upd, perf_stage=perf_stage)

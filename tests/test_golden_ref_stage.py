@@ -82,6 +82,49 @@ def test_oracle_reproduces_the_reference_iteration_golden(impact_cones):
     _cmp_records(S, K, ctrl, got, ref, TOL, impact_cones=impact_cones)
 
 
+def _oracle_perf_stage(lib, sd, S, table, ctrl, lin, con):
+    """orc_stage_perf_index per grid point: {cost_barrier, primal_feasibility, dual_feasibility, kkt_error}."""
+    import ctypes
+    lib.orc_stage_perf_index.argtypes = [ctypes.c_void_p] * 6
+    out = np.zeros((lin.shape[0], len(ctrl), 4))
+    csd = sd.c()
+    for b in range(lin.shape[0]):
+        for i, c in enumerate(ctrl):
+            st = np.zeros(4)
+            lib.orc_stage_perf_index(ctypes.byref(csd), ctypes.byref(table), ctypes.byref(c), oracle_lib.ptr(np.ascontiguousarray(lin[b, i])),
+                                     oracle_lib.ptr(np.ascontiguousarray(con[b, i])), oracle_lib.ptr(st))
+            out[b, i] = st
+    return out
+
+
+@pytest.mark.parametrize("impact_cones", [False, True])
+def test_oracle_performance_index_equals_the_reference_evalKKT_summary(impact_cones):
+    """PerformanceIndex of every grid point (log barrier, primal / dual feasibility, squared KKT error) as the reference's own
+    members compute it before condensing (OCPData / SplitKKTResidual / ConstraintsData / ContactDynamicsData ::KKTError etc.,
+    intermediate_stage.cpp:124-132, impact_stage.cpp:104-113, terminal_stage.cpp:94-100) -- golden fixture, and live where
+    oracle/_ref is available."""
+    lib = oracle_lib.load()
+    table, sd, S, K, ctrl, lin, con, sol, dx0 = mg.problem(lib.orc_stage_layout_get, lib.orc_layout_get, impact_cones)
+    got = _oracle_perf_stage(lib, sd, S, table, ctrl, lin, con)
+    ref = G["ic_perf_stage" if impact_cones else "perf_stage"]
+    np.testing.assert_allclose(got, ref, rtol=1e-12, atol=1e-300)
+    assert (ref[:, :, 3] > 0).all() and (ref[:, :-1, 0] != 0).any()
+    import ref_lib
+    if ref_lib.available():
+        from helpers import trot_schedule
+        from robotoc_b200 import ANYMAL, Layout, StageDims, StageLayout, anymal_constraint_table
+        from synth import make_stage_inputs
+        table = anymal_constraint_table(impact_friction_cone=impact_cones)
+        td, ev, ctrl = trot_schedule(40)
+        lin, con, sol, dx0 = make_stage_inputs(sd, S, ctrl, 1, 316, impact_cones=impact_cones)
+        rng = np.random.default_rng(5)
+        for i, c in enumerate(ctrl):  # give the switching-constraint residual something to measure
+            if c.ns > 0:
+                lin[:, i, S.l_p:S.l_p + c.ns] = rng.uniform(-1, 1, size=(1, c.ns))
+        live = ref_lib.reference_iteration(sd, S, K, table, ctrl, lin, con, dx0)["perf_stage"]
+        np.testing.assert_allclose(_oracle_perf_stage(lib, sd, S, table, ctrl, lin, con), live, rtol=1e-12, atol=1e-300)
+
+
 @pytest.mark.parametrize("which,seed", [("small", 311), ("small_sto", 312), ("trot", 313), ("small_icone", 314), ("small_sto_icone", 315)])
 def test_oracle_equals_live_reference_stage_layer(which, seed):
     import ref_lib
@@ -111,6 +154,11 @@ def test_cuda_reproduces_the_reference_iteration_golden(impact_cones):
     rr = RiccatiRecursion(ANYMAL, len(ctrl), lin.shape[0])
     rr.setTimeDiscretization(ctrl)
     dms = DirectMultipleShooting(rr, sd, table)
+    # PerformanceIndex of evalKKT: {cost (not on this path), barrier, primal / dual feasibility, KKT error, sqrt} vs the reference's sums
+    perf = dms.evalKKT(lin, con)
+    pref = (G["ic_perf_stage"] if impact_cones else G["perf_stage"]).sum(axis=1)
+    np.testing.assert_allclose(perf[:, 1:5], pref, rtol=1e-11)
+    np.testing.assert_allclose(perf[:, 5], np.sqrt(pref[:, 3]), rtol=1e-11)
     dms.condense(lin, con)
     got = dict(kkt=dms.getKKT(), cc_cond=dms.getConstraintData())
     rr.backwardRiccatiRecursion()
