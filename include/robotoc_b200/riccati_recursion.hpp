@@ -377,6 +377,61 @@ class DirectMultipleShooting {
     rr_.check(rbt_download(rr_.handle(), RBT_BUF_SOL, sol.data(), nullptr));
     rr_.check(rbt_sync(rr_.handle(), nullptr));
   }
+  /// OCPSolver::KKTError() of every OCP (ocp_solver.cpp:429-431): the PerformanceIndex that evalKKT summarises before condensing
+  /// (direct_multiple_shooting.cpp:155-158), from the records uploaded by evalKKT.  perf(ocp) = {cost (0: the cost evaluation is
+  /// not on this path), cost_barrier, primal_feasibility, dual_feasibility, kkt_error, sqrt(kkt_error), 0, 0}.
+  void evalPerformanceIndex() {
+    rr_.check(rbt_eval_kkt(rr_.handle(), nullptr));
+    perf_ = rr_.download(RBT_BUF_PERF);
+  }
+  double KKTError(int ocp = 0) const { return perf_.at(8 * size_t(ocp) + 5); }
+  const double* performanceIndex(int ocp = 0) const { return perf_.data() + 8 * size_t(ocp); }
+  /// pdipm::setSlackAndDualPositive on the uploaded PDIPM records (Constraints::setSlackAndDual at initConstraints); `con` is
+  /// uploaded, adjusted on the device and read back.
+  void setSlackAndDualPositive(std::vector<double>& con) {
+    expect(con, S_.c_stride, "con");
+    rr_.check(rbt_upload(rr_.handle(), RBT_BUF_CON, con.data(), nullptr));
+    rr_.check(rbt_set_slack_and_dual_positive(rr_.handle(), nullptr));
+    rr_.check(rbt_download(rr_.handle(), RBT_BUF_CON, con.data(), nullptr));
+    rr_.check(rbt_sync(rr_.handle(), nullptr));
+  }
+  /// computeInitialStateDirection (state_equation.cpp:98-109): dq0_v0 = [batch][2 nv] = {q0 (-) s[0].q, v0}; call after evalKKT
+  /// (and with the solution uploaded, e.g. by a previous integrateSolution) and before forwardRiccatiRecursion.
+  void computeInitialStateDirection(const std::vector<double>& dq0_v0) {
+    if (dq0_v0.size() != size_t(rr_.batch()) * 2 * S_.nv) throw std::invalid_argument("[DirectMultipleShooting] invalid argument: size of 'dq0_v0'");
+    rr_.check(rbt_initial_state_direction(rr_.handle(), dq0_v0.data(), nullptr));
+  }
+  /// Host wire records of the schedule in force (rbt_stage_layout.h): what an adaptor sends instead of the dense records.
+  void setWireCostStructure(bool robotoc_costs) {
+    cost_structure_ = robotoc_costs ? RBT_COST_ROBOTOC : RBT_COST_GENERAL;
+    rr_.check(rbt_set_wire_cost_structure(rr_.handle(), cost_structure_));
+  }
+  std::vector<double> packWire(const std::vector<double>& lin, const std::vector<rbt_stage_ctrl>& ctrl) const {
+    expect(lin, S_.l_stride, "lin");
+    const int w = rbt_wire_doubles(&sdims_, ctrl.data(), int(ctrl.size()), cost_structure_);
+    std::vector<double> wire(size_t(rr_.batch()) * w);
+    rr_.check(rbt_pack_wire(&sdims_, ctrl.data(), int(ctrl.size()), cost_structure_, lin.data(), wire.data(), rr_.batch()));
+    return wire;
+  }
+  /// Uploads the solver state (solution, slack / dual) that rbt_iteration_host_resident keeps on the device between iterations.
+  void setState(const std::vector<double>& sol, const std::vector<double>& con) {
+    expect(sol, S_.s_stride, "sol");
+    expect(con, S_.c_stride, "con");
+    rr_.check(rbt_upload(rr_.handle(), RBT_BUF_SOL, sol.data(), nullptr));
+    rr_.check(rbt_upload(rr_.handle(), RBT_BUF_CON, con.data(), nullptr));
+  }
+  /// One iteration from host memory with the solver state resident on the device: wire records, PDIPM residuals [batch][n_grid][ncp]
+  /// and dx0 in; updated solution records, slack | dual [batch][n_grid][2 ncp] and the step sizes out.
+  void iterationHostResident(const std::vector<double>& wire, const std::vector<double>& lin_switching, const std::vector<double>& res,
+                             const std::vector<double>& dx0, std::vector<double>& sol_out, std::vector<double>& slack_dual_out) {
+    expect(res, S_.ncp, "res");
+    sol_out.resize(size_t(rr_.batch()) * rr_.n_grid() * S_.s_stride);
+    slack_dual_out.resize(size_t(rr_.batch()) * rr_.n_grid() * 2 * S_.ncp);
+    steps_.resize(2 * size_t(rr_.batch()));
+    rr_.check(rbt_iteration_host_resident(rr_.handle(), wire.data(), lin_switching.empty() ? nullptr : lin_switching.data(), res.data(),
+                                          dx0.data(), sol_out.data(), slack_dual_out.data(), steps_.data(), nullptr));
+    rr_.check(rbt_sync(rr_.handle(), nullptr));
+  }
   const rbt_stage_layout& layout() const { return S_; }
 
  private:
@@ -387,7 +442,8 @@ class DirectMultipleShooting {
   DeviceRiccatiRecursion& rr_;
   rbt_stage_dims sdims_;
   rbt_stage_layout S_;
-  std::vector<double> steps_;
+  std::vector<double> steps_, perf_;
+  int cost_structure_ = RBT_COST_GENERAL;
 };
 
 }  // namespace robotoc_b200

@@ -16,6 +16,8 @@ void orc_expand_batch(const rbt_stage_dims*, const rbt_constraint_table*, const 
                       const double*, const double*, double*, double*, double*, int);
 void orc_update_batch(const rbt_stage_dims*, const rbt_constraint_table*, const rbt_stage_ctrl*, int, int, double*, double*, double*,
                       double*, double*, const double*, int);
+void orc_perf_index_batch(const rbt_stage_dims*, const rbt_constraint_table*, const rbt_stage_ctrl*, int, int, const double*,
+                          const double*, double*);
 }
 using namespace robotoc_b200;
 
@@ -111,7 +113,17 @@ int main() {
   // ---- the adaptor (GPU)
   DeviceRiccatiRecursion riccati_recursion(dims, ctrl, batch, 0.1);
   DirectMultipleShooting dms(riccati_recursion, sd, tab);
+  const std::vector<double> sol_in = sol, con_in = con;
   dms.evalKKT(lin, con);
+  // OCPSolver::KKTError() (PerformanceIndex of evalKKT) against the oracle
+  dms.evalPerformanceIndex();
+  std::vector<double> operf(8 * size_t(batch), 0.0);
+  orc_perf_index_batch(&sd, &tab, ctrl.data(), n_grid, batch, lin.data(), con.data(), operf.data());
+  double kworst = 0.0;
+  for (int b = 0; b < batch; ++b)
+    for (int q = 1; q <= 5; ++q)
+      kworst = std::fmax(kworst, std::fabs(dms.performanceIndex(b)[q] - operf[8 * b + q]) / std::fabs(operf[8 * b + q]));
+  if (!(dms.KKTError(0) > 0.0)) return 4;
   riccati_recursion.backwardRiccatiRecursion();
   riccati_recursion.forwardRiccatiRecursion(dx0);
   dms.computeStepSizes();
@@ -126,6 +138,22 @@ int main() {
   }
   std::printf("robotoc_b200::DirectMultipleShooting vs oracle: solution rel err %.3e, step sizes rel err %.3e (primal %.4f dual %.4f)\n",
               worst, sworst, dms.maxPrimalStepSize(0), dms.maxDualStepSize(0));
+  // the one-call host path with resident solver state and wire records: same bits as the step-by-step path
+  std::vector<double> sol_r, sd_r, res(per * S.ncp, 0.0);
+  for (size_t o = 0; o < per; ++o)
+    for (int i = 0; i < S.ncp; ++i) res[o * S.ncp + i] = con_in[o * S.c_stride + S.c_res + i];
+  dms.setWireCostStructure(false);
+  const std::vector<double> wire = dms.packWire(lin, ctrl);
+  dms.setState(sol_in, con_in);
+  dms.iterationHostResident(wire, std::vector<double>(), res, dx0, sol_r, sd_r);
+  const int used = S.s_xi + S.nsm;
+  bool same = wire.size() < lin.size();
+  for (size_t o = 0; o < per && same; ++o)
+    for (int i = 0; i < used; ++i) same = same && (sol_r[o * S.s_stride + i] == sol[o * S.s_stride + i]);
+  for (int b = 0; b < batch; ++b) same = same && dms.maxPrimalStepSize(b) > 0.0 && dms.maxPrimalStepSize(b) <= 1.0;
+  std::printf("KKT error rel err %.3e; resident wire path %s the step-by-step path (%zu vs %zu doubles up)\n", kworst,
+              same ? "reproduces" : "DIFFERS FROM", wire.size() + res.size(), lin.size() + con.size() + sol.size());
+  if (!same || !(kworst < 1e-10)) return 5;
   bool threw = false;
   try { std::vector<double> bad(3); dms.evalKKT(bad, con); } catch (const std::invalid_argument&) { threw = true; }
   if (!threw) return 3;
