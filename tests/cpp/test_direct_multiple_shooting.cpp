@@ -59,6 +59,8 @@ int main() {
         for (int k = 0; k < n; ++k) acc += sc * t[i + size_t(k) * n] * t[j + size_t(k) * n];
         dst[i + size_t(j) * ld] = acc;
       }
+    for (int j = 0; j < n; ++j)  // exactly symmetric, as the reference's containers are (the wire format sends the upper triangle)
+      for (int i = j + 1; i < n; ++i) dst[i + size_t(j) * ld] = dst[j + size_t(i) * ld];
   };
   for (size_t o = 0; o < per; ++o) {
     double* rec = lin.data() + o * S.l_stride;
