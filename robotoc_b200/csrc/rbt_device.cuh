@@ -121,11 +121,7 @@ __device__ __forceinline__ void warp_mma_band(double (&acc)[NT][2], int i0, FA f
   }
   double a0, b0[NT], a1, b1[NT];
   load(0, a0, b0);
-#ifdef RBT_MMA_ROLLED
-#pragma unroll 1  // A/B switch: a real loop over pairs of k-steps (smaller code; the condensing kernel starves on instruction fetch)
-#else
 #pragma unroll
-#endif
   for (int ks = 0; ks < KS; ks += 2) {
     if (ks + 1 < KS) load(ks + 1, a1, b1);
 #pragma unroll

@@ -107,7 +107,7 @@ __device__ __noinline__ void se3_jac_inverse_dev(const double* Jac, double* Jinv
 //  divergence-prone code in WARPSYNC / ENDCOLLECTIVE.)
 template <int NMAX, int LD>
 __device__ __forceinline__ bool warp_cholesky_ld(double* A, int n, double* dinv) {
-  static_assert(NMAX <= 32 && LD % 2 == 0, "one row per lane; 16-byte column loads");
+  static_assert(NMAX <= 32 && NMAX % 2 == 0 && LD % 2 == 0, "one row per lane; 16-byte column loads of row pairs");
   const int lane = threadIdx.x & 31;
   double a[NMAX];
 #pragma unroll
@@ -122,17 +122,11 @@ __device__ __forceinline__ bool warp_cholesky_ld(double* A, int n, double* dinv)
     if (lane >= j && lane < NMAX) A[lane + j * LD] = lij;
     if (lane == j) dinv[j] = inv;
     __syncwarp();
-    constexpr int dummy = 0;
-    (void)dummy;
 #pragma unroll
     for (int k0 = (j + 1) & ~1; k0 < NMAX; k0 += 2) {  // column j, two rows per load (k0 even, LD even: 16-byte aligned)
-      if (k0 + 1 < NMAX || (NMAX % 2 == 0)) {
-        const double2 l2 = *reinterpret_cast<const double2*>(A + k0 + j * LD);
-        if (k0 > j) a[k0] = fma(-lij, l2.x, a[k0]);
-        if (k0 + 1 < NMAX) a[k0 + 1] = fma(-lij, l2.y, a[k0 + 1]);
-      } else {
-        a[k0] = fma(-lij, A[k0 + j * LD], a[k0]);
-      }
+      const double2 l2 = *reinterpret_cast<const double2*>(A + k0 + j * LD);
+      if (k0 > j) a[k0] = fma(-lij, l2.x, a[k0]);
+      a[k0 + 1] = fma(-lij, l2.y, a[k0 + 1]);
     }
   }
   __syncwarp();
