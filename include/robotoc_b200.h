@@ -157,6 +157,16 @@ int rbt_eval_kkt(rbt_handle* h, void* stream);
 /* pdipm::setSlackAndDualPositive (include/robotoc/constraints/pdipm.hxx:13-24) on RBT_BUF_CON: slack <- max(slack, sqrt(barrier)),
  * dual <- barrier / slack -- what Constraints::setSlackAndDual applies when a solver is initialised (initConstraints). */
 int rbt_set_slack_and_dual_positive(rbt_handle* h, void* stream);
+/* SURVEY.md 8f-2, first slice -- the joint-limit half of Constraints::linearizeConstraints (src/constraints/constraints.cpp:283-306
+ * over JointPosition / Velocity / Torques Lower / Upper Limit, joint_*_limit.cpp:47-63) on the device, from the solution records
+ * the library already holds: for every box row whose level is valid on the grid point,
+ *   residual = sign (x - bound) + slack  -> RBT_BUF_CON (evalConstraint),   l_x += sign dual -> the gradient section of RBT_BUF_LIN
+ * (evalDerivatives).  A host that uses it uploads linearisation records whose gradients lack the joint-limit terms and PDIPM
+ * residuals for the friction-cone rows only (those need frame kinematics).  rbt_set_joint_limits: bound_host[n_box] = the limit
+ * of each box row of the constraint table (qmin / qmax, -vmax / vmax, -umax / umax of the robot model); call once.
+ * Order: rbt_upload(LIN, CON, SOL) -> rbt_linearize_joint_limits -> rbt_eval_kkt / rbt_condense. */
+int rbt_set_joint_limits(rbt_handle* h, const double* bound_host);
+int rbt_linearize_joint_limits(rbt_handle* h, void* stream);
 /* computeInitialStateDirection (src/dynamics/state_equation.cpp:98-109) into RBT_BUF_DX0.  dq0_v0_host: [batch][2 nv] =
  * {q0 (-) s[0].q from Robot::subtractConfiguration (the robot model stays on the host), v0}; uses the stage-0 Fqq_prev_inv that
  * rbt_condense left in RBT_BUF_EXP and s[0].v of RBT_BUF_SOL, so call it after rbt_condense and before rbt_riccati_forward. */

@@ -1054,3 +1054,39 @@ void orc_line_search_filter(int batch, int n_trials, double rate, double min_ste
     out_k[b] = acc;
   }
 }
+
+
+/* ---------------- SURVEY.md 8f-2 (first slice): Constraints::linearizeConstraints for the joint-limit components
+ * (constraints.cpp:283-306 -> joint_{position,velocity,torques}_{lower,upper}_limit.cpp:47-63):
+ *   evalConstraint:    residual = sign * (x - bound) + slack        (lower: qmin - q + slack, upper: q - qmax + slack)
+ *   evalDerivatives:   l_x += sign * dual                          (lower: lq.tail -= dual, upper: lq.tail += dual)
+ * for every box row whose level is valid on the grid point; x = s.q (joint part), s.v, s.a or s.u of the solution record.
+ * bound[r] = the limit of row r (from the robot model).  The friction cones need frame kinematics and stay with the host. */
+void orc_linearize_joint_limits_batch(const rbt_stage_dims* sd, const rbt_constraint_table* tab, const rbt_stage_ctrl* ctrl,
+                                      int n_grid, int batch, const double* bound, const double* sol, double* lin, double* con) {
+  rbt_stage_layout S;
+  rbt_make_stage_layout(sd, &S);
+  const int nv = S.nv;
+  for (int b = 0; b < batch; ++b)
+    for (int i = 0; i < n_grid; ++i) {
+      const rbt_stage_ctrl* c = &ctrl[i];
+      if (c->type == RBT_TERMINAL || c->type == RBT_IMPACT) continue;
+      const size_t o = (size_t)b * n_grid + i;
+      const double* s = sol + o * S.s_stride;
+      double* l = lin + o * S.l_stride;
+      double* cc = con + o * S.c_stride;
+      for (int r = 0; r < tab->n_box; ++r) {
+        if (!box_row_on(tab, c, r)) continue;
+        const rbt_box_row* br = &tab->box[r];
+        double x, *g;
+        switch (br->var) {
+          case RBT_VAR_Q: x = s[S.s_q + br->idx + (S.np == 6 ? 1 : 0)]; g = l + S.l_lx + br->idx; break;  /* q has one more entry (quaternion) */
+          case RBT_VAR_V: x = s[S.s_v + br->idx]; g = l + S.l_lx + nv + br->idx; break;
+          case RBT_VAR_A: x = s[S.s_a + br->idx]; g = l + S.l_la + br->idx; break;
+          default: x = s[S.s_u + br->idx]; g = l + S.l_lu + br->idx; break;
+        }
+        cc[S.c_res + r] = br->sign * (x - bound[r]) + cc[S.c_slack + r];
+        *g += br->sign * cc[S.c_dual + r];
+      }
+    }
+}

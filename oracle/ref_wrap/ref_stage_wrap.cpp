@@ -394,6 +394,60 @@ int ref_stage(const rbt_stage_dims* sd, const rbt_constraint_table* tab, const r
   return 0;
 }
 
+// Constraints::linearizeConstraints (constraints.cpp:283-306) over the six joint-limit components of the reference, for one grid
+// point: residual of the valid levels -> con (c_res rows), gradient terms -> the lx / la / lu sections of the linearization record.
+// bound: limit of each box row in the table order of make_constraints (q lower | q upper | v lower | v upper | u lower | u upper;
+// the reference's velocity / torque limits are symmetric: bound[v lower] == -bound[v upper]).
+int ref_linearize_joint_limits(const rbt_stage_dims* sd, const rbt_constraint_table* tab, const rbt_stage_ctrl* c, const double* bound,
+                               const double* sol, double* lin, double* con) {
+  rbt_stage_layout S;
+  rbt_make_stage_layout(sd, &S);
+  const int nv = S.nv, nu = S.nu, nx = S.nx, np = S.np;
+  if (c->type == RBT_TERMINAL || c->type == RBT_IMPACT) return 0;
+  Robot robot(nv, np == 6, tab->n_contacts);
+  Eigen::VectorXd effort(nu), velocity(nu), qmin(nu), qmax(nu);
+  for (int j = 0; j < nu; ++j) {
+    qmin(j) = bound[j]; qmax(j) = bound[nu + j];
+    velocity(j) = bound[3 * nu + j]; effort(j) = bound[5 * nu + j];
+    if (bound[2 * nu + j] != -velocity(j) || bound[4 * nu + j] != -effort(j)) return 1;
+  }
+  robot.setJointLimits(effort, velocity, qmin, qmax);
+  auto constraints = std::make_shared<Constraints>(tab->barrier, tab->fraction_to_boundary);
+  constraints->add("joint_position_lower", std::make_shared<JointPositionLowerLimit>(robot));
+  constraints->add("joint_position_upper", std::make_shared<JointPositionUpperLimit>(robot));
+  constraints->add("joint_velocity_lower", std::make_shared<JointVelocityLowerLimit>(robot));
+  constraints->add("joint_velocity_upper", std::make_shared<JointVelocityUpperLimit>(robot));
+  constraints->add("joint_torques_lower", std::make_shared<JointTorquesLowerLimit>(robot));
+  constraints->add("joint_torques_upper", std::make_shared<JointTorquesUpperLimit>(robot));
+  ConstraintsData cdata = constraints->createConstraintsData(robot, 2 - c->ineq_gate);
+  auto comp = [&](int k) -> ConstraintComponentData& {
+    return k < 2 ? cdata.position_level_data[k] : (k < 4 ? cdata.velocity_level_data[k - 2] : cdata.acceleration_level_data[k - 4]);
+  };
+  for (int k = 0; k < 6; ++k) {
+    put_v(comp(k).slack, con + S.c_slack + k * nu, nu);
+    put_v(comp(k).dual, con + S.c_dual + k * nu, nu);
+  }
+  SplitSolution s(robot);
+  put_v(s.q, sol + S.s_q, S.nq);
+  put_v(s.v, sol + S.s_v, nv);
+  put_v(s.a, sol + S.s_a, nv);
+  put_v(s.u, sol + S.s_u, nu);
+  SplitKKTResidual kr(robot);
+  put_v(kr.lx, lin + S.l_lx, nx);
+  put_v(kr.la, lin + S.l_la, nv);
+  put_v(kr.lu, lin + S.l_lu, nu);
+  ContactStatus contact_status = robot.createContactStatus();
+  constraints->linearizeConstraints(robot, contact_status, cdata, s, kr);
+  get_v(kr.lx, lin + S.l_lx, nx);
+  get_v(kr.la, lin + S.l_la, nv);
+  get_v(kr.lu, lin + S.l_lu, nu);
+  for (int k = 0; k < 6; ++k) {
+    const bool valid = k >= 4 || (k >= 2 ? c->ineq_gate <= 1 : c->ineq_gate == 0);
+    if (valid) get_v(comp(k).residual, con + S.c_res + k * nu, nu);
+  }
+  return 0;
+}
+
 // robotoc::LineSearchFilter (src/line_search/line_search_filter.cpp, compiled unmodified) driven like
 // LineSearch::lineSearchFilterMethod drives it (line_search.cpp:58-86) for ONE OCP over `rounds` consecutive line searches with
 // n_trials pre-evaluated candidates each: cost0/viol0 [rounds], cost/viol [rounds][n_trials] (barrier already included).

@@ -121,6 +121,48 @@ __global__ void slack_dual_positive_kernel(const EvalParams q) {
   con[S.c_dual + r] = p.tab.barrier / sl;
 }
 
+// SURVEY.md 8f-2, first slice: Constraints::linearizeConstraints of the joint-limit components (constraints.cpp:283-306,
+// joint_*_limit.cpp:47-63) -- residual = sign (x - bound) + slack into the PDIPM record, l_x += sign dual into the gradient of
+// the linearization record, for the rows whose level is valid on the grid point.  One thread per (grid point, target entry
+// (var, idx)): the lower and the upper limit of an entry meet on one gradient entry and are added in table order, like the
+// reference's component loop (bit-reproducible).
+__global__ void linearize_joint_limits_kernel(const EvalParams q, const double* __restrict__ bound) {
+  const StageParams& p = q.sp;
+  const rbt_stage_layout& S = p.S;
+  const int nt = 3 * S.nv + S.nu;
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (long long)p.batch * p.n_grid * nt) return;
+  const int t = int(e % nt);
+  const long long st = e / nt;
+  const rbt_stage_ctrl c = p.ctrl[int(st % p.n_grid)];
+  if (c.type == RBT_TERMINAL || c.type == RBT_IMPACT) return;
+  const int4 e4 = __ldg(p.tgt + t);
+  if (e4.x == 0) return;  // no limit acts on this entry
+  const int var = t < 3 * S.nv ? t / S.nv : RBT_VAR_U, idx = t < 3 * S.nv ? t % S.nv : t - 3 * S.nv;
+  const double* s = p.sol + size_t(st) * S.s_stride;
+  double* l = const_cast<double*>(p.lin) + size_t(st) * S.l_stride;
+  double* con = p.con + size_t(st) * S.c_stride;
+  double x, *g;
+  switch (var) {
+    case RBT_VAR_Q: x = s[S.s_q + idx + (S.np == 6 ? 1 : 0)]; g = l + S.l_lx + idx; break;  // q has one more entry (quaternion)
+    case RBT_VAR_V: x = s[S.s_v + idx]; g = l + S.l_lx + S.nv + idx; break;
+    case RBT_VAR_A: x = s[S.s_a + idx]; g = l + S.l_la + idx; break;
+    default: x = s[S.s_u + idx]; g = l + S.l_lu + idx; break;
+  }
+  const int ent[4] = {e4.x, e4.y, e4.z, e4.w};
+  double grad = *g;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (ent[k] == 0) continue;
+    const int r = (ent[k] < 0 ? -ent[k] : ent[k]) - 1;
+    if (__ldg(p.row_level + r) + c.ineq_gate > 2) continue;
+    const double sg = ent[k] < 0 ? -1.0 : 1.0;
+    con[S.c_res + r] = sg * (x - bound[r]) + con[S.c_slack + r];
+    grad += sg * con[S.c_dual + r];
+  }
+  *g = grad;
+}
+
 // dx0 = [ -Fqq_prev_inv (q0 (-) q)[0:6] | (q0 (-) q)[6:] | v0 - v ]   (Fqq_prev_inv of stage 0 is left by the condensing kernel)
 __global__ void initial_state_direction_kernel(const EvalParams q) {
   const StageParams& p = q.sp;

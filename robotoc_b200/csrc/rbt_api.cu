@@ -82,6 +82,7 @@ struct rbt_handle {
   int cb0 = 0, cnb = 0;
   double* d_wire = nullptr;  // packed host wire records (rbt_iteration_host_wire), allocated on first use
   int* d_tgt = nullptr;           // box rows per PDIPM target (stage_kernels.cuh: StageParams::tgt)
+  double* d_bound = nullptr;      // joint limits per box row (rbt_set_joint_limits)
   double* d_res_stage = nullptr;  // rbt_iteration_host_resident: compact residuals in, compact slack|dual out
   double* d_sd_stage = nullptr;
   std::vector<rbt_wire_layout> Wv;   // per grid point (the wire record of a grid point depends on its control word)
@@ -212,6 +213,7 @@ int rbt_destroy(rbt_handle* h) {
     cudaFree(h->d_wire);
     cudaFree(h->d_W);
     cudaFree(h->d_tgt);
+    cudaFree(h->d_bound);
     cudaFree(h->d_res_stage);
     cudaFree(h->d_sd_stage);
     if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
@@ -840,6 +842,32 @@ int rbt_set_slack_and_dual_positive(rbt_handle* h, void* stream) {
   const rbt::EvalParams q = make_eval_params(h);
   const long long total = (long long)win_nb(h) * h->n_grid * h->S.ncp;
   rbt::slack_dual_positive_kernel<<<unsigned((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(q);
+  RBT_CUDA(h, cudaGetLastError());
+  h->launches += 1;
+  return RBT_OK;
+}
+
+int rbt_set_joint_limits(rbt_handle* h, const double* bound_host) {
+  if (!h || !bound_host) return RBT_ERR_ARG;
+  if (!h->stage_ready) {
+    h->err = "[rbt_set_joint_limits] stage layer not set up";
+    return RBT_ERR_STATE;
+  }
+  RBT_CUDA(h, cudaSetDevice(h->device));
+  if (!h->d_bound) RBT_CUDA(h, cudaMalloc(&h->d_bound, sizeof(double) * RBT_MAX_BOX_ROWS));
+  RBT_CUDA(h, cudaMemcpy(h->d_bound, bound_host, sizeof(double) * h->table.n_box, cudaMemcpyHostToDevice));
+  return RBT_OK;
+}
+
+int rbt_linearize_joint_limits(rbt_handle* h, void* stream) {
+  RBT_STAGE_CHECK(h, "rbt_linearize_joint_limits");
+  if (!h->d_bound) {
+    h->err = "[rbt_linearize_joint_limits] call rbt_set_joint_limits first";
+    return RBT_ERR_STATE;
+  }
+  const rbt::EvalParams q = make_eval_params(h);
+  const long long total = (long long)win_nb(h) * h->n_grid * (3 * h->S.nv + h->S.nu);
+  rbt::linearize_joint_limits_kernel<<<unsigned((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(q, h->d_bound);
   RBT_CUDA(h, cudaGetLastError());
   h->launches += 1;
   return RBT_OK;

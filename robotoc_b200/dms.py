@@ -62,6 +62,16 @@ class DirectMultipleShooting:
         """Uploads the PDIPM records (slack, dual, residual of every inequality row)."""
         self._up(CON, con, self.layout.c_stride, stream)
 
+    def setJointLimits(self, bound):
+        """Limit of each box row of the constraint table (qmin / qmax, -vmax / vmax, -umax / umax), for linearizeJointLimits."""
+        bound = np.ascontiguousarray(bound, dtype=np.float64)
+        _check(self._lib.rbt_set_joint_limits(self._h, _vp(bound)), self.rr._err, "DirectMultipleShooting")
+
+    def linearizeJointLimits(self, stream=None):
+        """The joint-limit half of Constraints::linearizeConstraints on the device (rbt_linearize_joint_limits): PDIPM residuals
+        of the box rows from the resident solution, and their dual terms added to the gradients of the linearization records."""
+        _check(self._lib.rbt_linearize_joint_limits(self._h, stream), self.rr._err, "DirectMultipleShooting")
+
     def computeStepSizes(self, stream=None):
         _check(self._lib.rbt_expand_and_step_sizes(self._h, stream), self.rr._err, "DirectMultipleShooting")
 
