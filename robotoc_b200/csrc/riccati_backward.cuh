@@ -418,10 +418,14 @@ __global__ void __launch_bounds__(BwdCfg<NV, NU, NS, NP>::NTHREADS, RBT_BWD_MIN_
           warp_mma_band<NX, TX, NX, false>(
               acc, i0, [&](int ii, int k) { return sA[k + ii * NX]; }, [&](int k, int j) { return sP[k + j * NX]; });
         }
+        // The last band is pulled back (NX = 36: rows 28..35) and recomputes rows the band before it owns: only the owner stores
+        // them (the values are bit-identical, but two warps storing and loading the same words without a barrier is a data race).
+        constexpr int OWN0 = 8 * (TX - 1);  // first row only the last band computes
+        const bool mine = !(NX % 8 != 0 && warp == TX - 1 && i0 + g < OWN0);
 #pragma unroll
         for (int n = 0; n < TX; ++n) {
           const int j0 = tile_off(n, NX);
-          *reinterpret_cast<double2*>(&sAtP[(i0 + g) * NX + j0 + 2 * t]) = make_double2(acc[n][0], acc[n][1]);
+          if (mine) *reinterpret_cast<double2*>(&sAtP[(i0 + g) * NX + j0 + 2 * t]) = make_double2(acc[n][0], acc[n][1]);
         }
       }
       RBT_TL(i, 2);
@@ -449,7 +453,8 @@ __global__ void __launch_bounds__(BwdCfg<NV, NU, NS, NP>::NTHREADS, RBT_BWD_MIN_
         if (!impact) matvec_N4(sP, NX, NX, NX, sfx, tid, NG, [&](int r, double a) { Pf[r] = a; });
         if (tid < NX) Fxs[tid] = sFx[tid];
       }
-      __syncwarp();  // this warp's rows of AtP are all the next two products read of it
+      __syncwarp();  // this warp's rows of AtP are all the next two products read of it ...
+      if (NX % 8 != 0 && warp >= TX - 2) named_bar_sync(5, 64);  // ... plus, for the last band, the rows the band before it stored
       RBT_TL(i, 3);
 
       // ================= phase B (GEMM warps): F = Qxx + AtP A ; H = Qxu + AtP[:,nv:] Bv
@@ -548,6 +553,7 @@ __global__ void __launch_bounds__(BwdCfg<NV, NU, NS, NP>::NTHREADS, RBT_BWD_MIN_
           const int idx = (lane & 15) < NU ? (lane & 15) : NU - 1;
 #pragma unroll
           for (int k = 0; k < NU; ++k) gc[k] = sG[idx + k * NU];  // row of G (its lower part is read)
+          __syncwarp();  // every lane has read its row before any lane overwrites G with L below
           if (!warp_chol_inv_reg<NU>(gc, rs)) bad |= 1;
           if ((lane & 15) < NU) {
             if (lane < 16) {
@@ -859,10 +865,12 @@ __global__ void __launch_bounds__(BwdCfg<NV, NU, NS, NP>::NTHREADS, RBT_BWD_MIN_
     // the barrier.  (The element-wise symmetrise-and-store loop this replaces was 16 % of the sweep's instructions.)
     const bool fastP = symF && fct == nullptr;
     if (gemm_warp) {
+      // rows the pulled-back last band shares with the band before it are stored by their owner only (identical values)
+      const bool mine = !(NX % 8 != 0 && warp == TX - 1 && i0 + g < 8 * (TX - 1));
 #pragma unroll
       for (int n = 0; n < TX; ++n) {
         const int j0 = tile_off(n, NX);
-        if (n >= nb0) {
+        if (n >= nb0 && mine) {
           if (fastP) {
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
