@@ -89,6 +89,7 @@ struct rbt_handle {
   rbt_wire_layout* d_W = nullptr;
   long long w_ocp = 0;               // doubles of one OCP's concatenated wire records
   int cost_structure = RBT_COST_GENERAL;  // what the host's wire records hold (rbt_set_wire_cost_structure)
+  bool wire_dirty = true;                 // per-grid-point wire layouts on the device are stale (schedule / cost structure changed)
   bool attr_bwd = false, attr_fwd = false, attr_cond = false;  // MaxDynamicSharedMemorySize set on THIS handle's device
   cudaEvent_t ev_condense_mid = nullptr;  // caller-owned event recorded between the two kernels of rbt_condense (timing)
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
@@ -287,6 +288,7 @@ int rbt_set_schedule(rbt_handle* h, const rbt_stage_ctrl* ctrl, int n_grid, doub
   h->n_grid = n_grid;
   h->max_dts0 = max_dts0;
   h->ctrl.assign(ctrl, ctrl + n_grid);
+  h->wire_dirty = true;
   return RBT_OK;
 }
 
@@ -383,10 +385,12 @@ static long long make_wire_layouts(const rbt_stage_layout& S, const rbt_stage_ct
   }
   return off;
 }
-static int ensure_wire_layouts(rbt_handle* h) {  // (re)built on every call: n_grid small structs + one H2D copy
+static int ensure_wire_layouts(rbt_handle* h) {  // rebuilt only when the schedule or the cost structure changed
+  if (!h->wire_dirty && h->d_W) return RBT_OK;
   h->w_ocp = make_wire_layouts(h->S, h->ctrl.data(), h->n_grid, h->cost_structure, h->Wv);
   if (!h->d_W) RBT_CUDA(h, cudaMalloc(&h->d_W, size_t(h->n_grid_max) * sizeof(rbt_wire_layout)));
   RBT_CUDA(h, cudaMemcpy(h->d_W, h->Wv.data(), size_t(h->n_grid) * sizeof(rbt_wire_layout), cudaMemcpyHostToDevice));
+  h->wire_dirty = false;
   return RBT_OK;
 }
 
@@ -1202,6 +1206,7 @@ int rbt_iteration_host_resident(rbt_handle* h, const double* wire_host, const do
 
 int rbt_set_wire_cost_structure(rbt_handle* h, int cost_structure) {
   if (!h || (cost_structure != RBT_COST_GENERAL && cost_structure != RBT_COST_ROBOTOC)) return RBT_ERR_ARG;
+  if (h->cost_structure != cost_structure) h->wire_dirty = true;
   h->cost_structure = cost_structure;
   return RBT_OK;
 }
