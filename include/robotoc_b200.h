@@ -214,7 +214,7 @@ int rbt_iteration_host_bytes(rbt_handle* h, int mode /* 0 dense records, 1 wire,
  * robotoc linearisation of that grid point holds -- packed upper triangles of the symmetric blocks M, Qff, Qxx, Quu; contact
  * blocks sized by the active contact dimension nf and the active contacts (as the reference's own dimf-sized containers); no
  * padding; no Qqf (zero until the friction-cone condensing fills it); the STO section only when the schedule has a
- * switching-time stage; Qxx, lx and one SE(3) block on the terminal grid point.  ANYmal trot N=40: 45 % fewer bytes over PCIe
+ * switching-time stage; Qxx, lx and one SE(3) block on the terminal grid point.  ANYmal trot N=40: 42 % fewer bytes over PCIe
  * than the dense records.  One OCP's wire records are concatenated in grid order: wire_host is [batch][rbt_wire_doubles].
  * `lin_host_switching` = classic records, of which only the switching-constraint sections of the stages that carry one are
  * read (NULL if the schedule has none).  rbt_pack_wire is the host-side packing helper (what an adaptor does while copying
