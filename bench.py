@@ -214,7 +214,8 @@ def _oracle_runner(pr):
     lib = oracle_lib.load()
     native = os.path.join(oracle_lib.ORACLE_DIR, "liboracle_native.so")
     try:  # -march=native build of the same sources, made on this machine
-        subprocess.run(["make", "-s", "-C", oracle_lib.ORACLE_DIR, "native"], check=True, stdout=subprocess.DEVNULL,
+        # -B: always rebuilt here -- a copy that travelled from another machine was tuned for that machine's CPU
+        subprocess.run(["make", "-s", "-B", "-C", oracle_lib.ORACLE_DIR, "native"], check=True, stdout=subprocess.DEVNULL,
                        stderr=subprocess.DEVNULL)
         lib = ct.CDLL(native)
     except Exception:
